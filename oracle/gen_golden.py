@@ -1,0 +1,178 @@
+#!/usr/bin/env python
+"""Freeze outputs of the LIVE, UNMODIFIED reference into tests/golden/ (build container only).
+
+TEST INFRASTRUCTURE.  Run:  python oracle/gen_golden.py [--big]
+Inputs come from tscode_b200.synth (seeded); only seeds/params + the reference's outputs are
+stored, so the fixtures stay small.  --big adds the N=10k/20k/50k M=80 masks (≈2 min).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import ref_harness  # noqa: E402
+from tscode_b200.synth import gen_ensemble, gen_poses, materialise_poses, mask_digest  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--big", action="store_true")
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    os.makedirs(GOLD, exist_ok=True)
+    ref_harness.install(full=True)
+    import numba
+    from tscode.rmsd_pruning import prune_conformers_rmsd, rmsd_and_max_numba, _rmsd_similarity
+    from tscode.numba_functions import compenetration_check
+    from tscode.embeds import get_embed
+    from tscode.utils import rotation_matrix_from_vectors
+    from tscode.algebra import align_vec_pair, rot_mat_from_pointer
+
+    meta = {"numba": numba.__version__, "numpy": np.__version__, "threads": numba.get_num_threads()}
+    want = lambda k: (not args.only) or (k in args.only.split(","))
+
+    # ---- A1: rmsd_and_max_numba on explicit pairs -------------------------------------------
+    if want("pairs"):
+        rng = np.random.default_rng(1234)
+        P, Q, out = [], [], []
+        for M in (3, 5, 17, 40, 80):
+            S = gen_ensemble(100 + M, 24, M, 4, sigma_noise=0.1)
+            for a in range(0, 24, 2):
+                p, q = S[a], S[a + 1]
+                if a % 6 == 0:       # exact rotated duplicate (rmsd ~ 0 after rotation)
+                    A = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+                    A *= np.sign(np.linalg.det(A))
+                    q = p @ A
+                P.append(p); Q.append(q); out.append(rmsd_and_max_numba(p, q))
+        np.savez_compressed(os.path.join(GOLD, "rmsd_pairs.npz"),
+                            **{f"p{i}": p for i, p in enumerate(P)}, **{f"q{i}": q for i, q in enumerate(Q)},
+                            out=np.array(out))
+        print("pairs:", len(out))
+
+    # ---- A4: prune_conformers_rmsd masks ------------------------------------------------------
+    if want("prune"):
+        rows = [
+            dict(seed=0, N=1000, M=40, n_clusters=100, sigma_noise=0.05, thr=0.5),
+            dict(seed=1, N=1000, M=40, n_clusters=1000, sigma_noise=0.05, thr=0.5),
+            dict(seed=2, N=1000, M=40, n_clusters=20, sigma_noise=0.15, thr=0.5),
+            dict(seed=3, N=5000, M=40, n_clusters=500, sigma_noise=0.05, thr=0.5),
+            dict(seed=4, N=2000, M=80, n_clusters=200, sigma_noise=0.08, thr=0.5),
+            dict(seed=5, N=777, M=40, n_clusters=60, sigma_noise=0.05, thr=0.25, mixed_h=True),
+            dict(seed=6, N=1037, M=33, n_clusters=90, sigma_noise=0.06, thr=0.3, mixed_h=True),
+            dict(seed=7, N=3001, M=21, n_clusters=250, sigma_noise=0.05, thr=0.5),
+            dict(seed=8, N=300, M=40, n_clusters=300, sigma_noise=1.0, thr=0.5),     # all distinct
+            dict(seed=9, N=400, M=12, n_clusters=1, sigma_noise=0.01, thr=0.5),      # all similar
+            dict(seed=10, N=1, M=10, n_clusters=1, sigma_noise=0.05, thr=0.5),
+            dict(seed=11, N=2, M=10, n_clusters=1, sigma_noise=0.05, thr=0.5),
+            dict(seed=12, N=45, M=10, n_clusters=5, sigma_noise=0.05, thr=0.5),
+        ]
+        if args.big:
+            rows += [dict(seed=3, N=10000, M=80, n_clusters=1000, sigma_noise=0.05, thr=0.5),
+                     dict(seed=3, N=20000, M=80, n_clusters=2000, sigma_noise=0.05, thr=0.5),
+                     dict(seed=3, N=50000, M=80, n_clusters=5000, sigma_noise=0.05, thr=0.5)]
+        res = []
+        for r in rows:
+            S = gen_ensemble(r["seed"], r["N"], r["M"], r["n_clusters"], sigma_noise=r["sigma_noise"])
+            atomnos = np.full(r["M"], 6)
+            if r.get("mixed_h"):
+                atomnos[np.random.default_rng(r["seed"]).random(r["M"]) < 0.3] = 1
+            t0 = time.perf_counter()
+            out, mask = prune_conformers_rmsd(S, atomnos, rmsd_thr=r["thr"])
+            dt = time.perf_counter() - t0
+            assert np.array_equal(out, S[mask])
+            r = dict(r, survivors=int(mask.sum()), digest=mask_digest(mask), wall_s=round(dt, 3),
+                     mask_hex=np.packbits(mask.astype(np.uint8)).tobytes().hex() if r["N"] <= 5000 else None)
+            res.append(r)
+            print("prune:", {k: v for k, v in r.items() if k != "mask_hex"})
+        name = "prune_masks_big.json" if args.big else "prune_masks.json"
+        if args.big:
+            res = [r for r in res if r["N"] >= 10000]
+        json.dump({"meta": meta, "rows": res}, open(os.path.join(GOLD, name), "w"), indent=1)
+
+    # ---- A5: _rmsd_similarity -----------------------------------------------------------------
+    if want("simlist"):
+        S = gen_ensemble(21, 64, 30, 6, sigma_noise=0.2)
+        out = [bool(_rmsd_similarity(S[i], list(S[i + 1:i + 9]), rmsd_thr=1.0)) for i in range(0, 55)]
+        json.dump({"seed": 21, "N": 64, "M": 30, "n_clusters": 6, "sigma_noise": 0.2, "rmsd_thr": 1.0,
+                   "window": 8, "out": out}, open(os.path.join(GOLD, "rmsd_similarity.json"), "w"))
+        print("simlist:", sum(out), "of", len(out))
+
+    # ---- A7/A8: get_embed + compenetration_check ---------------------------------------------
+    if want("clash"):
+        rows = [
+            dict(seed=0, P=100000, n_atoms=(50, 50), thresh=1.5, max_clashes=0),
+            dict(seed=1, P=100000, n_atoms=(50, 50), thresh=1.5, max_clashes=3),
+            dict(seed=2, P=50000, n_atoms=(50, 50, 50), thresh=1.5, max_clashes=0),
+            dict(seed=3, P=20000, n_atoms=(30, 45, 60), thresh=1.4, max_clashes=1),
+            dict(seed=4, P=5000, n_atoms=(7, 13), thresh=2.0, max_clashes=2),
+            dict(seed=5, P=3000, n_atoms=(33, 1, 65), thresh=1.7, max_clashes=5),
+        ]
+        res = []
+        for r in rows:
+            frags, conf, R, t = gen_poses(r["seed"], r["P"], r["n_atoms"])
+            ids = np.array(r["n_atoms"])
+
+            class Mol:  # the three attributes get_embed reads (embeds.py:969)
+                pass
+            mols = [Mol() for _ in ids]
+            for k, m in enumerate(mols):
+                m.atomcoords = frags[k]
+            verd = np.zeros(r["P"], np.uint8)
+            emb_sum = 0.0
+            t0 = time.perf_counter()
+            for p in range(r["P"]):
+                for k, m in enumerate(mols):
+                    m.rotation = R[p, k]; m.position = t[p, k]
+                pose = get_embed(mols, conf[p])
+                if p < 64:
+                    emb_sum += float(np.abs(pose - materialise_poses(frags, conf, R, t, [p])[0]).max())
+                v = compenetration_check(pose, ids=ids, thresh=r["thresh"], max_clashes=r["max_clashes"])
+                assert type(v) is int
+                verd[p] = v
+            dt = time.perf_counter() - t0
+            r = dict(r, passes=int(verd.sum()), digest=mask_digest(verd), wall_s=round(dt, 2),
+                     embed_vs_vectorised_maxabs=emb_sum,
+                     verdict_hex=np.packbits(verd).tobytes().hex())
+            res.append(r)
+            print("clash:", {k: v for k, v in r.items() if k != "verdict_hex"})
+        # ids=None (intramolecular count_clashes) on a handful of poses
+        frags, conf, R, t = gen_poses(7, 400, (20, 20), blob=1.0, dmin=0.0, dmax=1.0)
+        S = materialise_poses(frags, conf, R, t)
+        none_rows = []
+        for mc in (0, 2, 6):
+            v = [int(compenetration_check(S[p], None, 1.5, mc)) for p in range(400)]
+            none_rows.append(dict(max_clashes=mc, verdict_hex=np.packbits(np.array(v, np.uint8)).tobytes().hex(),
+                                  passes=int(sum(v))))
+        print("clash none:", [(x["max_clashes"], x["passes"]) for x in none_rows])
+        json.dump({"meta": meta, "rows": res,
+                   "ids_none": dict(seed=7, P=400, n_atoms=(20, 20), blob=1.0, dmin=0.0, dmax=1.0, rows=none_rows)},
+                  open(os.path.join(GOLD, "clash_verdicts.json"), "w"), indent=1)
+
+    # ---- A8: pose (R, t) builders ------------------------------------------------------------
+    if want("rot"):
+        rng = np.random.default_rng(99)
+        v1 = rng.normal(size=(40, 3)); v2 = rng.normal(size=(40, 3))
+        v2[0] = v1[0] * 2.0          # parallel
+        v2[1] = -v1[1] * 0.5         # antiparallel
+        rmv = np.array([rotation_matrix_from_vectors(a, b) for a, b in zip(v1, v2)])
+        ang = rng.uniform(-180, 180, size=40)
+        rmp = np.array([rot_mat_from_pointer(a, float(x)) for a, x in zip(v1, ang)])
+        ref = rng.normal(size=(40, 2, 3)); tgt = rng.normal(size=(40, 2, 3))
+        avp = np.array([align_vec_pair(a, b) for a, b in zip(ref, tgt)])
+        np.savez_compressed(os.path.join(GOLD, "rotation_builders.npz"), v1=v1, v2=v2, rmv=rmv, ang=ang,
+                            rmp=rmp, ref=ref, tgt=tgt, avp=avp)
+        print("rot: saved")
+
+
+if __name__ == "__main__":
+    main()

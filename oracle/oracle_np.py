@@ -1,0 +1,155 @@
+"""numpy restatement of the reference hot path.  TEST INFRASTRUCTURE — see oracle/__init__.py.
+
+Uses LAPACK's SVD through numpy exactly where the reference does (rmsd_pruning.py:19), so it is
+the closest thing to the reference that can travel to the GPU box; pure-Python loops, so only
+for small cases.  Cross-checks oracle.c (different SVD) in tests/test_oracle_golden.py.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+LADDER = (5e5, 2e5, 1e5, 5e4, 2e4, 1e4, 5000, 2000, 1000, 500, 200, 100, 50, 20, 10, 5, 2, 1)
+
+
+def rmsd_and_max(p, q):
+    """rmsd_pruning.py:6-41 — rotation-only Kabsch about the origin, RMSD and max deviation."""
+    p = np.asarray(p, float); q = np.asarray(q, float)
+    cov = p.T @ q                                        # :15
+    v, _, w = np.linalg.svd(cov)                         # :19
+    if np.linalg.det(v) * np.linalg.det(w) < 0.0:        # :20-23
+        v[:, -1] = -v[:, -1]
+    rot = v @ w                                          # :26
+    diff = p @ rot - q                                   # :29-32
+    rmsd = np.sqrt((diff * diff).sum() / len(diff))      # :35
+    maxdev = np.sqrt((diff * diff).sum(axis=1)).max()    # :39
+    return float(rmsd), float(maxdev)
+
+
+def sim_matrix(H, thr):
+    """sim[i, j] (i < j) = rmsd < thr and maxdev < 2*thr   (rmsd_pruning.py:75, :95)."""
+    N = len(H)
+    sim = np.zeros((N, N), bool)
+    for i in range(N):
+        for j in range(i + 1, N):
+            r, d = rmsd_and_max(H[i], H[j])
+            sim[i, j] = (r < thr) and (d < 2 * thr)
+    return sim
+
+
+def ladder_model(sim, N, gate=20):
+    """SURVEY Appendix A.2 — the elimination of rmsd_pruning.py:81-206 on a precomputed sim
+    matrix (callable or array).  Returns (mask, rounds_run)."""
+    get = sim if callable(sim) else (lambda i, j: sim[i, j])
+    mask = np.ones(N, bool)
+    cache = set()
+    rounds = []
+    for k in LADDER:
+        if k == 1 or gate * k < np.count_nonzero(mask):                     # :192
+            rounds.append(k)
+            cs = int(N // k)                                               # :136
+            new = np.zeros(N, bool)
+            add = []
+            for c in range(int(k)):
+                first = c * cs
+                last = N if c == k - 1 else cs * (c + 1)                   # :141-144
+                for i in range(first, last):
+                    if not mask[i]:
+                        continue
+                    keep = True
+                    for j in range(i + 1, last):
+                        if mask[j]:
+                            key = (first, first + j - i)                   # :65
+                            if key in cache:                               # :66-67
+                                break
+                            if get(i, j):                                  # :75-77
+                                add.append(key); keep = False
+                                break
+                    new[i] = keep
+            cache.update(add)                                              # :204
+            mask = new
+    return mask, rounds
+
+
+def prune_conformers_rmsd(structures, atomnos, rmsd_thr=0.5):
+    """rmsd_pruning.py:164-206."""
+    structures = np.asarray(structures)
+    H = structures[:, np.asarray(atomnos) != 1]
+    memo = {}
+
+    def get(i, j):
+        if (i, j) not in memo:
+            r, d = rmsd_and_max(H[i], H[j])
+            memo[(i, j)] = (r < rmsd_thr) and (d < 2 * rmsd_thr)
+        return memo[(i, j)]
+    mask, _ = ladder_model(get, len(H))
+    return structures[mask], mask
+
+
+def all_dists(A, B):
+    """algebra.py:98-157."""
+    d = A[:, None, :] - B[None, :, :]
+    return np.sqrt((d * d).sum(-1))
+
+
+def compenetration_check(coords, ids=None, thresh=1.5, max_clashes=0) -> int:
+    """numba_functions.py:59-105."""
+    coords = np.asarray(coords, float)
+    if ids is None:
+        D = all_dists(coords, coords)
+        return 0 if np.count_nonzero((D < 0.5) & (D > 0)) > max_clashes else 1       # :49-56, :71-72
+    if len(ids) == 2:
+        m1, m2 = coords[:ids[0]], coords[ids[0]:]
+        return 0 if np.count_nonzero(all_dists(m2, m1) < thresh) > max_clashes else 1  # :74-81
+    m1 = coords[:ids[0]]; m2 = coords[ids[0]:ids[0] + ids[1]]; m3 = coords[ids[0] + ids[1]:]
+    clashes = 0
+    for a, b in ((m2, m1), (m3, m2), (m1, m3)):                                        # :92-103
+        clashes += np.count_nonzero(all_dists(a, b) < thresh)
+        if clashes > max_clashes:
+            return 0
+    return 1
+
+
+def get_embed(frags, conf_ids, R, t):
+    """embeds.py:961-969."""
+    return np.concatenate([(R[k] @ frags[k][c].T).T + t[k] for k, c in enumerate(conf_ids)])
+
+
+# --- pose (R, t) builders -------------------------------------------------------------------
+def quaternion_to_rotation_matrix(Q):
+    """algebra.py:284-323 (scalar-last input)."""
+    q0, q1, q2, q3 = Q[3], Q[0], Q[1], Q[2]
+    return np.array([[2 * (q0 * q0 + q1 * q1) - 1, 2 * (q1 * q2 - q0 * q3), 2 * (q1 * q3 + q0 * q2)],
+                     [2 * (q1 * q2 + q0 * q3), 2 * (q0 * q0 + q2 * q2) - 1, 2 * (q2 * q3 - q0 * q1)],
+                     [2 * (q1 * q3 - q0 * q2), 2 * (q2 * q3 + q0 * q1), 2 * (q0 * q0 + q3 * q3) - 1]])
+
+
+def rot_mat_from_pointer(pointer, angle):
+    """algebra.py:325-344 (angle in degrees)."""
+    pointer = np.asarray(pointer, float)
+    pointer = pointer / np.sqrt((pointer * pointer).sum())
+    a = angle * np.pi / 180
+    return quaternion_to_rotation_matrix(np.array([np.sin(a / 2) * pointer[0], np.sin(a / 2) * pointer[1],
+                                                   np.sin(a / 2) * pointer[2], np.cos(a / 2)]))
+
+
+def rotation_matrix_from_vectors(vec1, vec2):
+    """utils.py:183-208."""
+    a = vec1 / np.sqrt((vec1 * vec1).sum()); b = vec2 / np.sqrt((vec2 * vec2).sum())
+    v = np.cross(a, b)
+    s = np.sqrt((v * v).sum())
+    if s != 0:
+        c = a @ b
+        K = np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+        return np.eye(3) + K + K @ K * ((1 - c) / s ** 2)
+    if np.sqrt(((a + b) ** 2).sum()) == 0:
+        return rot_mat_from_pointer(np.array([0., 0., 1.]), 180)
+    return np.eye(3)
+
+
+def align_vec_pair(ref, tgt):
+    """algebra.py:258-282."""
+    B = np.einsum("ji,jk->ik", np.asarray(ref, float), np.asarray(tgt, float))
+    u, s, vh = np.linalg.svd(B)
+    if np.linalg.det(u @ vh) < 0:
+        u[:, -1] = -u[:, -1]
+    return u @ vh

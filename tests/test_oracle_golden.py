@@ -1,0 +1,120 @@
+"""Pin the oracle (oracle.c and oracle_np.py) against outputs of the LIVE reference frozen in
+tests/golden/ by oracle/gen_golden.py.  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle_c, oracle_np
+from tscode_b200.synth import gen_ensemble, gen_poses, materialise_poses, mask_digest
+
+from conftest import GOLDEN
+
+
+def _atomnos(r):
+    a = np.full(r["M"], 6)
+    if r.get("mixed_h"):
+        a[np.random.default_rng(r["seed"]).random(r["M"]) < 0.3] = 1
+    return a
+
+
+def test_rmsd_and_max_matches_reference_pairs():
+    g = np.load(os.path.join(GOLDEN, "rmsd_pairs.npz"))
+    out = g["out"]
+    for i in range(len(out)):
+        p, q = g[f"p{i}"], g[f"q{i}"]
+        rc, dc = oracle_c.rmsd_and_max(p, q)
+        rn, dn = oracle_np.rmsd_and_max(p, q)
+        M = len(p)
+        if M == 3 and np.linalg.svd(p.T @ q)[1][2] < 1e-9:
+            continue
+        # RMSD within 1e-9 A of the reference (north star); in practice ~1e-14
+        assert abs(rc - out[i, 0]) < 1e-9 and abs(dc - out[i, 1]) < 1e-9, (i, M, rc, out[i])
+        assert abs(rn - out[i, 0]) < 1e-12 and abs(dn - out[i, 1]) < 1e-12
+
+
+_rows = json.load(open(os.path.join(GOLDEN, "prune_masks.json")))["rows"]
+
+
+@pytest.mark.parametrize("r", _rows, ids=[f"s{r['seed']}_N{r['N']}_M{r['M']}" for r in _rows])
+def test_prune_mask_matches_reference(r):
+    S = gen_ensemble(r["seed"], r["N"], r["M"], r["n_clusters"], sigma_noise=r["sigma_noise"])
+    out, mask = oracle_c.prune_conformers_rmsd(S, _atomnos(r), r["thr"])
+    ref = np.unpackbits(np.frombuffer(bytes.fromhex(r["mask_hex"]), np.uint8))[:r["N"]].astype(bool)
+    assert mask.sum() == r["survivors"]
+    assert np.array_equal(mask, ref)
+    assert mask_digest(mask) == r["digest"]
+    assert np.array_equal(out, S[mask])
+
+
+def test_prune_numpy_oracle_small():
+    for r in _rows:
+        if r["N"] > 400:
+            continue
+        S = gen_ensemble(r["seed"], r["N"], r["M"], r["n_clusters"], sigma_noise=r["sigma_noise"])
+        _, mask = oracle_np.prune_conformers_rmsd(S, _atomnos(r), r["thr"])
+        assert mask_digest(mask) == r["digest"], r["seed"]
+
+
+def test_ladder_replay_on_precomputed_sim():
+    """orc_prune_rmsd with a precomputed sim matrix == lazy evaluation == numpy ladder model."""
+    r = _rows[5]
+    S = gen_ensemble(r["seed"], r["N"], r["M"], r["n_clusters"], sigma_noise=r["sigma_noise"])
+    H = oracle_c.heavy(S, _atomnos(r))
+    sim = oracle_c.sim_rows(H, r["thr"], 0, r["N"])
+    m1, ne, rounds = oracle_c.prune_heavy(H, r["thr"], sim_bytes=sim)
+    assert ne == 0 and mask_digest(m1) == r["digest"]
+    m2, rounds2 = oracle_np.ladder_model(sim.astype(bool), r["N"])
+    assert np.array_equal(m1, m2) and rounds == list(rounds2)
+
+
+def test_rmsd_similarity_matches_reference():
+    g = json.load(open(os.path.join(GOLDEN, "rmsd_similarity.json")))
+    S = gen_ensemble(g["seed"], g["N"], g["M"], g["n_clusters"], sigma_noise=g["sigma_noise"])
+    out = [oracle_c.rmsd_similarity(S[i], S[i + 1:i + 1 + g["window"]], g["rmsd_thr"]) for i in range(len(g["out"]))]
+    assert out == g["out"]
+
+
+_clash = json.load(open(os.path.join(GOLDEN, "clash_verdicts.json")))
+
+
+@pytest.mark.parametrize("r", _clash["rows"], ids=[f"s{r['seed']}_P{r['P']}" for r in _clash["rows"]])
+def test_clash_verdicts_match_reference(r):
+    frags, conf, R, t = gen_poses(r["seed"], r["P"], tuple(r["n_atoms"]))
+    v = oracle_c.embed_clash_batch(frags, conf, R, t, r["thresh"], r["max_clashes"])
+    ref = np.unpackbits(np.frombuffer(bytes.fromhex(r["verdict_hex"]), np.uint8))[:r["P"]]
+    assert int(v.sum()) == r["passes"]
+    assert np.array_equal(v, ref)
+    assert mask_digest(v) == r["digest"]
+    # materialised route + numpy oracle on a slice
+    sel = np.arange(0, min(r["P"], 300))
+    S = materialise_poses(frags, conf, R, t, sel)
+    v2 = oracle_c.clash_structs(S, np.array(r["n_atoms"]), r["thresh"], r["max_clashes"])
+    assert np.array_equal(v2, ref[sel])
+    v3 = [oracle_np.compenetration_check(S[i], np.array(r["n_atoms"]), r["thresh"], r["max_clashes"]) for i in range(100)]
+    assert np.array_equal(np.array(v3), ref[:100])
+
+
+def test_clash_ids_none_matches_reference():
+    g = _clash["ids_none"]
+    frags, conf, R, t = gen_poses(g["seed"], g["P"], tuple(g["n_atoms"]), blob=g["blob"], dmin=g["dmin"], dmax=g["dmax"])
+    S = materialise_poses(frags, conf, R, t)
+    for row in g["rows"]:
+        ref = np.unpackbits(np.frombuffer(bytes.fromhex(row["verdict_hex"]), np.uint8))[:g["P"]]
+        v = oracle_c.clash_structs(S, None, 1.5, row["max_clashes"])
+        assert np.array_equal(v, ref)
+        assert [oracle_np.compenetration_check(S[i], None, 1.5, row["max_clashes"]) for i in range(50)] == list(ref[:50])
+
+
+def test_get_embed_and_rotation_builders():
+    frags, conf, R, t = gen_poses(0, 16, (5, 9, 4))
+    for p in range(16):
+        a = oracle_c.get_embed(frags, conf[p], R[p], t[p])
+        b = oracle_np.get_embed(frags, conf[p], R[p], t[p])
+        assert np.abs(a - b).max() < 1e-13
+    g = np.load(os.path.join(GOLDEN, "rotation_builders.npz"))
+    for i in range(len(g["v1"])):
+        assert np.abs(oracle_np.rotation_matrix_from_vectors(g["v1"][i], g["v2"][i]) - g["rmv"][i]).max() < 1e-12
+        assert np.abs(oracle_np.rot_mat_from_pointer(g["v1"][i], g["ang"][i]) - g["rmp"][i]).max() < 1e-12
+        assert np.abs(oracle_np.align_vec_pair(g["ref"][i], g["tgt"][i]) - g["avp"][i]).max() < 1e-10
