@@ -1,0 +1,119 @@
+/*
+ * tscode_b200.h — C-ABI of libtscode_b200.so: the B200-native conformer-ensemble hot path of
+ * TSCoDe (RMSD pruning, clash screen, rigid-body pose transforms).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless marked [host]; arrays are row-major, FP64
+ *     unless typed otherwise; `stream` is a cudaStream_t passed as void*;
+ *   - every compute entry point is asynchronous on `stream` and returns 0 or a cudaError_t
+ *     (tsc_error_string() decodes it); nothing allocates, nothing synchronises;
+ *   - no torch / Python types cross this boundary.  The Python package binds it with ctypes
+ *     (tscode_b200/_lib.py); INTEGRATION.md shows the binding a TSCoDe maintainer would add.
+ *
+ * Reference interfaces replaced (paths relative to the TSCoDe tree, tscode/...):
+ *   rmsd_pruning.py:164   prune_conformers_rmsd   -> tsc_pack + tsc_rmsd_sim_tiles +
+ *                                                    tsc_rmsd_verify + tsc_elim_*
+ *   rmsd_pruning.py:6     rmsd_and_max_numba      -> tsc_rmsd_pairs
+ *   rmsd_pruning.py:208   _rmsd_similarity        -> tsc_rmsd_pairs (broadcast_p = 1)
+ *   numba_functions.py:60 compenetration_check    -> tsc_clash_structs / tsc_embed_clash
+ *   embeds.py:961         get_embed               -> tsc_embed_gather (and fused in tsc_embed_clash)
+ */
+#ifndef TSCODE_B200_H
+#define TSCODE_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- bookkeeping ------------------------------------------------------------------------ */
+int tsc_version(void);                         /* 100 = 0.1.0 */
+const char* tsc_error_string(int code);        /* [host] */
+int32_t tsc_device_sm_count(void);
+
+/* Packed-ensemble geometry (see tscode_b200/csrc/tsc_common.cuh):
+ *   conformer blocks of 32 (count rounded up to even = nb_pad), atom slabs of 20;
+ *   packed[slab][block][xyz][32][20] doubles; sim rows have W = nb_pad 32-bit words. */
+int64_t tsc_num_blocks_padded(int64_t N);
+int32_t tsc_num_slabs(int32_t M);
+int64_t tsc_packed_doubles(int64_t N, int32_t M);
+
+/* ---- prune_conformers_rmsd ---------------------------------------------------------------- */
+/* Heavy-atom gather (rmsd_pruning.py:178-179) + repack + squared norms.
+ *   S (N, A, 3); heavy_idx (M) int32 = indices with atomnos != 1;
+ *   packed: tsc_packed_doubles(N, M) doubles; G: nb_pad*32 doubles (sum |p|^2 per conformer). */
+int tsc_pack(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M,
+             double* packed, double* G, void* stream);
+
+/* All-pairs similarity screen over a list of 32 x 64 pair tiles.
+ *   tiles (n_tiles, 4) int32: {ib, jp, lb, 0} = I block ib, J blocks 2jp and 2jp+1, rows written
+ *   at local row block lb of sim_bits.  For every owned row block ib the caller lists jp from
+ *   ib/2 to nb_pad/2 - 1, so that all words >= ib of the row are written.
+ *   sim_bits (n_local_blocks*32, W) uint32: bit j of row i set iff pair (i, j>i) may have
+ *   rmsd < thr (screen; tsc_rmsd_verify makes the bits exact).
+ *   variant 0 = FP64 tensor cores (DMMA), 1 = FP64 FMA pipe.  grid_ctas 0 = one CTA per SM. */
+int tsc_rmsd_sim_tiles(const double* packed, const double* G, int64_t N, int32_t M,
+                       const int32_t* tiles, int64_t n_tiles, double thr, uint32_t* sim_bits,
+                       int32_t variant, int32_t grid_ctas, void* stream);
+
+/* Exact re-evaluation of every set bit, the way rmsd_and_max_numba does it (rmsd_pruning.py:6-41);
+ * afterwards bit (i,j) == (rmsd < thr and maxdev < 2*thr)  (:75, :95).
+ *   row_blocks (n_rb) int32: global block index of each local row block.
+ *   stats (4) uint64, accumulated: candidates, confirmed, within 1e-6 A of a threshold,
+ *   degenerate optimal rotation. */
+int tsc_rmsd_verify(const double* packed, int64_t N, int32_t M, const int32_t* row_blocks,
+                    int32_t n_rb, double thr, uint32_t* sim_bits, uint64_t* stats, void* stream);
+
+/* Batched rmsd_and_max_numba on explicit pairs: P, Q (n, M, 3) -> rmsd (n), maxdev (n).
+ * broadcast_p = 1 compares P[0] with every Q[k] (_rmsd_similarity, rmsd_pruning.py:208-224). */
+int tsc_rmsd_pairs(const double* P, const double* Q, int64_t n, int32_t M, int32_t broadcast_p,
+                   double* rmsd, double* maxdev, void* stream);
+
+/* One ladder round (rmsd_pruning.py:123-162) in three steps; cs = int(N // k) (:136).
+ *   cachebits ((N+31)/32 words): bit s set iff key (first, s) is cached and `first` starts a
+ *   chunk of this round;   key_first/key_second (N) int32 + n_keys (1) int32: the cache (:183,:204). */
+int tsc_elim_cachebits(const int32_t* key_first, const int32_t* key_second, const int32_t* n_keys,
+                       int64_t N, int64_t cs, int64_t k, uint32_t* cachebits, void* stream);
+/*   out_mask (N) uint8 and out_key_second (N) int32 (-1 = none) are written for owned rows only. */
+int tsc_elim_round(const uint32_t* sim_bits, const int32_t* row_blocks, int32_t n_rb,
+                   const uint32_t* active_words, const uint32_t* cachebits, int64_t N, int64_t cs,
+                   int64_t k, uint8_t* out_mask, int32_t* out_key_second, void* stream);
+/*   mask bytes -> active words (+ n_active), emitted keys appended to the cache. */
+int tsc_elim_commit(const uint8_t* mask, const int32_t* key_second_per_row, int64_t N, int64_t cs,
+                    int64_t k, uint32_t* active_words_out, int32_t* key_first, int32_t* key_second,
+                    int32_t* n_keys, int32_t* n_active, void* stream);
+
+/* ---- compenetration_check / get_embed -------------------------------------------------- */
+/* Fused pose transform + clash screen (embeds.py:116-118 / 713-714 / 841-842).
+ *   frag_lib: all fragments' conformers back to back; frag_off (F) int64 = offset in doubles of
+ *   fragment k; conformer c of fragment k at frag_off[k] + c*3*n_atoms[k].  conf (P, F) int32,
+ *   R (P, F, 3, 3), t (P, F, 3).  F in {2, 3}.  t2: d < thresh <=> d*d < t2 (host computes the
+ *   exact image of thresh under correctly-rounded sqrt).  verdict (P) uint8 = 1 pass / 0 clash.
+ *   near_count (1) uint64 or NULL: if given, early exit is disabled and pairs with
+ *   |d - thresh| < 1e-9 are counted (parity reporting). */
+int tsc_embed_clash(const double* frag_lib, const int64_t* frag_off, const int32_t* n_atoms, int32_t F,
+                    int32_t A_total, const int32_t* conf, const double* R, const double* t, int64_t P,
+                    double t2, double thresh, int64_t max_clashes, uint8_t* verdict,
+                    uint64_t* near_count, void* stream);
+/* compenetration_check on materialised structures S (P, A, 3) (embedder.py:1245-1248).
+ *   F = 0 (ids NULL): intramolecular count of 0 < d < 0.5 over the full symmetric matrix
+ *   (numba_functions.py:49-56, t2_half = image of 0.5); F = 2: only ids[0] is read; F = 3. */
+int tsc_clash_structs(const double* S, int64_t P, int32_t A, const int32_t* ids, int32_t F, double t2,
+                      double thresh, double t2_half, int64_t max_clashes, uint8_t* verdict,
+                      uint64_t* near_count, void* stream);
+/* get_embed (embeds.py:961-969) for poses keep_idx (n_keep) int64 (NULL = first n_keep poses):
+ *   S_out (n_keep, A_total, 3). */
+int tsc_embed_gather(const double* frag_lib, const int64_t* frag_off, const int32_t* n_atoms, int32_t F,
+                     int32_t A_total, const int32_t* conf, const double* R, const double* t,
+                     const int64_t* keep_idx, int64_t n_keep, double* S_out, void* stream);
+
+/* ---- measurement aid (not on the product path) ------------------------------------------ */
+/* Self-measured FP64 ceilings: kind 0 = DFMA, 1 = DMMA.8x8x4, 2 = both at once (even warps
+ * DMMA, odd warps DFMA).  SYNCHRONOUS: times one launch with CUDA events on `stream`.
+ *   scratch: >= 1 double (device); flops_out [host] (2): {tensor flop, FMA flop}; ms_out [host]. */
+int tsc_bench_fp64(int32_t kind, int32_t iters, int32_t ctas_per_sm, int32_t threads, double* scratch,
+                   double* flops_out, float* ms_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

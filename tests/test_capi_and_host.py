@@ -1,0 +1,114 @@
+"""CPU-only checks: the C-ABI library builds, loads and exports exactly what include/*.h
+declares (no compute calls); host-side bookkeeping (tiles, sharding, ladder, thresholds)."""
+import ctypes
+import math
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from tscode_b200 import _host, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "tscode_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tsc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_loads_and_exports_header_symbols():
+    from tscode_b200.csrc import build
+    so = build.build()
+    assert os.path.exists(so)
+    L = ctypes.CDLL(so)
+    names = _header_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/tscode_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
+    assert _lib.lib().tsc_version() == 100
+    # geometry helpers are host-only and must agree with the numpy mirror
+    for N in (1, 31, 32, 33, 64, 1000, 50000):
+        assert _lib.lib().tsc_num_blocks_padded(N) == _host.num_blocks_padded(N)
+        for M in (1, 20, 21, 80):
+            assert _lib.lib().tsc_packed_doubles(N, M) == _host.packed_doubles(N, M)
+
+
+def test_sass_uses_dmma_and_bulk_tma():
+    """The hot kernel must really be on the FP64 tensor pipe and stage through bulk TMA."""
+    from tscode_b200.csrc import build
+    so = build.build()
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    assert "DMMA.8x8x4" in sass
+    assert "UBLKCP" in sass
+    assert "DFMA" in sass
+
+
+def test_product_has_no_oracle_or_cpu_fallback():
+    for root, _, files in os.walk(os.path.join(ROOT, "tscode_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                s = open(os.path.join(root, f)).read()
+                assert "import oracle" not in s and "from oracle" not in s, f
+    import torch
+    if not torch.cuda.is_available():
+        from tscode_b200.rmsd_pruning import prune_conformers_rmsd
+        from tscode_b200.numba_functions import compenetration_check
+        with pytest.raises(RuntimeError):
+            prune_conformers_rmsd(np.zeros((4, 3, 3)), np.full(3, 6))
+        with pytest.raises(RuntimeError):
+            compenetration_check(np.zeros((4, 3)), np.array([2, 2]))
+
+
+@pytest.mark.parametrize("N", [1, 2, 31, 32, 33, 64, 65, 1000, 1037, 4096])
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_tiles_cover_upper_triangle(N, world):
+    nb, nbp = _host.num_blocks(N), _host.num_blocks_padded(N)
+    covered = np.zeros((nb, nbp), bool)
+    total = 0
+    for rank in range(world):
+        rb = _host.owned_row_blocks(N, rank, world)
+        tiles = _host.build_tiles(N, rb)
+        total += len(tiles)
+        assert np.all(tiles[:, 2] < max(len(rb), 1))
+        for ib, jp, lb, _ in tiles:
+            assert rb[lb] == ib
+            assert not covered[ib, 2 * jp] and not covered[ib, 2 * jp + 1]
+            covered[ib, 2 * jp] = covered[ib, 2 * jp + 1] = True
+    for ib in range(nb):
+        assert covered[ib, ib:].all()            # every word >= ib of every row block is written
+    assert total == sum(nbp // 2 - ib // 2 for ib in range(nb))
+
+
+def test_row_sharding_is_balanced():
+    N = 50000
+    loads = [len(_host.build_tiles(N, _host.owned_row_blocks(N, r, 8))) for r in range(8)]
+    assert max(loads) / min(loads) < 1.01
+
+
+def test_ladder_schedule_matches_reference_rule():
+    # rmsd_pruning.py:186-192 with a mask that never shrinks
+    assert _host.run_ladder(1000, lambda k, cs: 1000) == [20, 10, 5, 2, 1]
+    assert _host.run_ladder(777, lambda k, cs: 777) == [20, 10, 5, 2, 1]
+    assert _host.run_ladder(1037, lambda k, cs: 1037) == [50, 20, 10, 5, 2, 1]
+    assert _host.run_ladder(50000, lambda k, cs: 50000)[0] == 2000
+    assert _host.run_ladder(1, lambda k, cs: 1) == [1]
+    seen = []
+    _host.run_ladder(1037, lambda k, cs: seen.append((k, cs)) or 1037)
+    assert seen[0] == (50, 20) and seen[-1] == (1, 1037)
+    # a shrinking mask skips rounds
+    it = iter([100, 100, 100, 100])
+    assert _host.run_ladder(1000, lambda k, cs: next(it)) == [20, 2, 1]
+
+
+@pytest.mark.parametrize("thr", [1.5, 0.5, 1.4, 2.0, 1.7, 1e-3, 3.3333333333333335, 0.1])
+def test_sqrt_threshold_image(thr):
+    t2 = _host.sqrt_threshold_image(thr)
+    assert math.sqrt(t2) >= thr and math.sqrt(math.nextafter(t2, -math.inf)) < thr
+    rng = np.random.default_rng(0)
+    x = thr * thr * (1 + (rng.random(20000) - 0.5) * 1e-14)
+    assert np.array_equal(np.sqrt(x) < thr, x < t2)

@@ -1,0 +1,104 @@
+"""Host-side bookkeeping of the RMSD prune that needs no GPU: packed-layout geometry, tile
+lists, row sharding, the k-ladder schedule.  Pure numpy so the CPU test-suite covers it."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+CB = 32          # conformers per block   (tsc_common.cuh)
+KS = 20          # atoms per slab
+
+#: the reference's ladder of chunk counts, tscode/rmsd_pruning.py:186-188
+LADDER = (5e5, 2e5, 1e5, 5e4, 2e4, 1e4, 5000, 2000, 1000, 500, 200, 100, 50, 20, 10, 5, 2, 1)
+
+
+def num_blocks(N: int) -> int:
+    return (N + CB - 1) // CB
+
+
+def num_blocks_padded(N: int) -> int:
+    nb = num_blocks(N)
+    nb += nb & 1
+    return max(nb, 2)
+
+
+def num_slabs(M: int) -> int:
+    return (M + KS - 1) // KS
+
+
+def packed_doubles(N: int, M: int) -> int:
+    return num_slabs(M) * num_blocks_padded(N) * 3 * CB * KS
+
+
+def owned_row_blocks(N: int, rank: int = 0, world: int = 1) -> np.ndarray:
+    """Block-cyclic row sharding: row block ib has ~(nb - ib) column blocks of
+    work, so contiguous ranges would be badly imbalanced; cyclic assignment balances to 1/nb."""
+    return np.arange(rank, num_blocks(N), world, dtype=np.int32)
+
+
+def build_tiles(N: int, row_blocks: np.ndarray) -> np.ndarray:
+    """(n_tiles, 4) int32 rows {ib, jp, lb, 0}: for each owned row block ib (local index lb) the
+    J block pairs jp = ib//2 .. nb_pad/2 - 1 (every word >= ib of the row gets written)."""
+    njp = num_blocks_padded(N) // 2
+    rb = np.asarray(row_blocks, dtype=np.int64)
+    if rb.size == 0:
+        return np.zeros((0, 4), np.int32)
+    first = rb // 2
+    counts = njp - first
+    total = int(counts.sum())
+    lb = np.repeat(np.arange(rb.size, dtype=np.int64), counts)
+    ib = rb[lb]
+    start = np.cumsum(counts) - counts
+    jp = np.arange(total, dtype=np.int64) - np.repeat(start, counts) + np.repeat(first, counts)
+    tiles = np.zeros((total, 4), np.int32)
+    tiles[:, 0] = ib
+    tiles[:, 1] = jp
+    tiles[:, 2] = lb
+    return tiles
+
+
+def pairs_in_tiles(N: int) -> int:
+    return N * (N - 1) // 2
+
+
+def ladder_gate(k, n_active: int, gate: int = 20) -> bool:
+    """`k == 1 or 20*k < count_nonzero(mask)`  (rmsd_pruning.py:192)."""
+    return k == 1 or gate * k < n_active
+
+
+def chunk_size(N: int, k) -> int:
+    """`int(len(structures) // k)`  (rmsd_pruning.py:136)."""
+    return int(N // k)
+
+
+def run_ladder(N: int, round_fn, gate: int = 20):
+    """Drive the ladder: round_fn(k:int, cs:int) -> n_active after the round.
+    Returns the list of k actually run (data dependent)."""
+    n_active = N
+    ran = []
+    for k in LADDER:
+        if ladder_gate(k, n_active, gate):
+            n_active = int(round_fn(int(k), chunk_size(N, k)))
+            ran.append(int(k))
+    return ran
+
+
+def global_rows_of(row_blocks: np.ndarray) -> np.ndarray:
+    """Global row index of every local sim row (n_rb*32,), for reassembling gathered shards."""
+    rb = np.asarray(row_blocks, dtype=np.int64)
+    return (rb[:, None] * CB + np.arange(CB, dtype=np.int64)[None, :]).reshape(-1)
+
+
+def sqrt_threshold_image(thresh: float) -> float:
+    """Smallest double t2 with sqrt(t2) >= thresh under correctly-rounded sqrt, so that
+    `sqrt(d2) < thresh`  <=>  `d2 < t2` exactly (all_dists + `< thresh`, algebra.py:98-157)."""
+    thresh = float(thresh)
+    if not (thresh > 0.0):
+        return 0.0
+    x = thresh * thresh
+    while math.sqrt(x) >= thresh:
+        x = math.nextafter(x, -math.inf)
+    while math.sqrt(x) < thresh:
+        x = math.nextafter(x, math.inf)
+    return x

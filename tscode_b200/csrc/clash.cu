@@ -1,0 +1,282 @@
+// clash.cu — fused rigid-body pose transform + inter-fragment clash screen.
+//
+// Reference per pose (tscode/embeds.py:116-118, 713-714, 841-842):
+//     pose = get_embed(mols, conf_ids)              # concat((R_k @ X_k.T).T + t_k), embeds.py:961-969
+//     ok   = compenetration_check(pose, ids, thresh, max_clashes)      # numba_functions.py:59-105
+// compenetration_check counts atom pairs of different fragments closer than `thresh`
+// (all_dists, algebra.py:98-157, then `< thresh`) over (m2,m1) [, (m3,m2), (m1,m3)] and
+// passes the pose iff the count is <= max_clashes; the early returns between the three
+// blocks cannot change the verdict because counts only grow.
+//
+// Here one warp owns one pose: fragment conformers are read from the (L2-resident) fragment
+// library, rotated + translated on the fly into a per-warp shared-memory SoA image, and the
+// pair tests run from there — the pose is never materialised in HBM.  Per pose the kernel
+// reads F*(9+3) doubles + F ints and writes one verdict byte.
+//     d < thresh  is evaluated as  d^2 < t2  with t2 the exact image of the threshold under
+// correctly-rounded sqrt (computed on the host), so no sqrt is needed and the comparison is
+// the same predicate.  A warp stops as soon as count > max_clashes.
+//
+// Roofline: FP64 FMA pipe (6 FP64 instructions per atom pair); bytes are negligible.
+#include "tsc_common.cuh"
+
+namespace tsc {
+
+constexpr int CLASH_WARPS = 8;
+
+struct ClashThresh {
+    double t2;        // d < thresh  <=>  d2 < t2
+    double near_lo2;  // (thresh - 1e-9)^2   (REPORT mode only)
+    double near_hi2;  // (thresh + 1e-9)^2
+};
+
+// count pairs (a in A-set, b in B-set) with d2 < t2; stop once total > max_clashes.
+template <bool REPORT>
+__device__ __forceinline__ bool count_block(const double* xa, const double* ya, const double* za, int na,
+                                            const double* xb, const double* yb, const double* zb, int nb,
+                                            const ClashThresh& th, long long max_clashes, long long& count,
+                                            unsigned long long& near, int lane) {
+    int a = 0, b = lane;
+    while (b >= nb && a < na) { b -= nb; a++; }
+    while (true) {
+        const bool live = a < na;
+        if (!__any_sync(0xffffffffu, live)) break;
+        bool hit = false;
+        if (live) {
+            const double dx = xa[a] - xb[b], dy = ya[a] - yb[b], dz = za[a] - zb[b];
+            const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            hit = d2 < th.t2;
+            if (REPORT) near += (d2 > th.near_lo2 && d2 < th.near_hi2);
+        }
+        count += __popc(__ballot_sync(0xffffffffu, hit));
+        if (!REPORT && count > max_clashes) return true;
+        b += 32;
+        while (b >= nb && a < na) { b -= nb; a++; }
+    }
+    return count > max_clashes;
+}
+
+template <bool REPORT>
+__device__ __forceinline__ int verdict_fragments(const double* sx, const double* sy, const double* sz,
+                                                 const int* off, const int* n, int F, const ClashThresh& th,
+                                                 long long max_clashes, unsigned long long& near, int lane) {
+    long long count = 0;
+    bool over;
+    // (m2, m1)
+    over = count_block<REPORT>(sx + off[1], sy + off[1], sz + off[1], n[1], sx + off[0], sy + off[0], sz + off[0],
+                               n[0], th, max_clashes, count, near, lane);
+    if (over && !REPORT) return 0;
+    if (F == 3) {
+        over = count_block<REPORT>(sx + off[2], sy + off[2], sz + off[2], n[2], sx + off[1], sy + off[1],
+                                   sz + off[1], n[1], th, max_clashes, count, near, lane);
+        if (over && !REPORT) return 0;
+        over = count_block<REPORT>(sx + off[0], sy + off[0], sz + off[0], n[0], sx + off[2], sy + off[2],
+                                   sz + off[2], n[2], th, max_clashes, count, near, lane);
+    }
+    return count > max_clashes ? 0 : 1;
+}
+
+// ids=None branch: count_clashes over the full symmetric matrix, (d < 0.5) & (d > 0); each
+// close pair is counted twice (numba_functions.py:49-56).
+__device__ __forceinline__ int verdict_intramolecular(const double* sx, const double* sy, const double* sz, int A,
+                                                      double t2_half, long long max_clashes, int lane) {
+    long long count = 0;
+    for (int a = 0; a + 1 < A; a++) {
+        for (int b0 = a + 1; b0 < A; b0 += 32) {
+            const int b = b0 + lane;
+            bool hit = false;
+            if (b < A) {
+                const double dx = sx[a] - sx[b], dy = sy[a] - sy[b], dz = sz[a] - sz[b];
+                const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                hit = (d2 < t2_half) && (d2 > 0.0);
+            }
+            count += 2 * __popc(__ballot_sync(0xffffffffu, hit));
+            if (count > max_clashes) return 0;
+        }
+    }
+    return 1;
+}
+
+template <bool REPORT>
+__global__ void __launch_bounds__(CLASH_WARPS * 32) embed_clash_kernel(
+    const double* __restrict__ frag_lib, const int64_t* __restrict__ frag_off, const int32_t* __restrict__ n_atoms,
+    int F, const int32_t* __restrict__ conf, const double* __restrict__ R, const double* __restrict__ t, int64_t P,
+    int A_total, ClashThresh th, long long max_clashes, uint8_t* __restrict__ verdict, unsigned long long* near_out) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* sx = smem + (size_t)warp * 3 * A_total;
+    double* sy = sx + A_total;
+    double* sz = sy + A_total;
+    int off[3] = {0, 0, 0}, n[3] = {0, 0, 0};
+    {
+        int o = 0;
+        for (int k = 0; k < F; k++) { n[k] = n_atoms[k]; off[k] = o; o += n[k]; }
+    }
+    unsigned long long near = 0;
+    const int64_t warp_g = (int64_t)blockIdx.x * CLASH_WARPS + warp;
+    const int64_t nwarps = (int64_t)gridDim.x * CLASH_WARPS;
+    for (int64_t p = warp_g; p < P; p += nwarps) {
+        for (int k = 0; k < F; k++) {
+            const double* X = frag_lib + frag_off[k] + (int64_t)conf[p * F + k] * 3 * n[k];
+            const double* r = R + (p * F + k) * 9;
+            const double* tt = t + (p * F + k) * 3;
+            const double r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3], r4 = r[4], r5 = r[5], r6 = r[6], r7 = r[7],
+                         r8 = r[8], t0 = tt[0], t1 = tt[1], t2 = tt[2];
+            for (int a = lane; a < n[k]; a += 32) {
+                const double x = X[3 * a], y = X[3 * a + 1], z = X[3 * a + 2];
+                sx[off[k] + a] = fma(r2, z, fma(r1, y, r0 * x)) + t0;
+                sy[off[k] + a] = fma(r5, z, fma(r4, y, r3 * x)) + t1;
+                sz[off[k] + a] = fma(r8, z, fma(r7, y, r6 * x)) + t2;
+            }
+        }
+        __syncwarp();
+        const int v = verdict_fragments<REPORT>(sx, sy, sz, off, n, F, th, max_clashes, near, lane);
+        if (lane == 0) verdict[p] = (uint8_t)v;
+        __syncwarp();
+    }
+    if (REPORT) {
+        near = __reduce_add_sync(0xffffffffu, (unsigned)near);
+        if (lane == 0 && near && near_out) atomicAdd(near_out, near);
+    }
+}
+
+template <bool REPORT>
+__global__ void __launch_bounds__(CLASH_WARPS * 32) clash_structs_kernel(
+    const double* __restrict__ S, int64_t P, int A, const int32_t* __restrict__ ids, int F, ClashThresh th,
+    double t2_half, long long max_clashes, uint8_t* __restrict__ verdict, unsigned long long* near_out) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* sx = smem + (size_t)warp * 3 * A;
+    double* sy = sx + A;
+    double* sz = sy + A;
+    int off[3] = {0, 0, 0}, n[3] = {0, 0, 0};
+    if (F == 2) {             // only ids[0] is read (numba_functions.py:77-78)
+        n[0] = ids[0]; n[1] = A - n[0]; off[1] = n[0];
+    } else if (F == 3) {
+        n[0] = ids[0]; n[1] = ids[1]; n[2] = A - n[0] - n[1]; off[1] = n[0]; off[2] = n[0] + n[1];
+    }
+    unsigned long long near = 0;
+    const int64_t warp_g = (int64_t)blockIdx.x * CLASH_WARPS + warp;
+    const int64_t nwarps = (int64_t)gridDim.x * CLASH_WARPS;
+    for (int64_t p = warp_g; p < P; p += nwarps) {
+        const double* X = S + p * (int64_t)A * 3;
+        for (int e = lane; e < 3 * A; e += 32) {          // coalesced AoS read, SoA scatter
+            const double v = X[e];
+            const int a = e / 3, c = e - 3 * a;
+            (c == 0 ? sx : c == 1 ? sy : sz)[a] = v;
+        }
+        __syncwarp();
+        int v;
+        if (F == 0) v = verdict_intramolecular(sx, sy, sz, A, t2_half, max_clashes, lane);
+        else v = verdict_fragments<REPORT>(sx, sy, sz, off, n, F, th, max_clashes, near, lane);
+        if (lane == 0) verdict[p] = (uint8_t)v;
+        __syncwarp();
+    }
+    if (REPORT) {
+        near = __reduce_add_sync(0xffffffffu, (unsigned)near);
+        if (lane == 0 && near && near_out) atomicAdd(near_out, near);
+    }
+}
+
+// get_embed for a selected set of poses: S_out[q] = pose keep_idx[q]   (embeds.py:961-969)
+__global__ void __launch_bounds__(256) embed_gather_kernel(const double* __restrict__ frag_lib,
+                                                           const int64_t* __restrict__ frag_off,
+                                                           const int32_t* __restrict__ n_atoms, int F,
+                                                           const int32_t* __restrict__ conf,
+                                                           const double* __restrict__ R, const double* __restrict__ t,
+                                                           const int64_t* __restrict__ keep_idx, int64_t n_keep,
+                                                           int A_total, double* __restrict__ S_out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t warp_g = (int64_t)blockIdx.x * 8 + warp;
+    const int64_t nwarps = (int64_t)gridDim.x * 8;
+    for (int64_t q = warp_g; q < n_keep; q += nwarps) {
+        const int64_t p = keep_idx ? keep_idx[q] : q;
+        int o = 0;
+        for (int k = 0; k < F; k++) {
+            const int nk = n_atoms[k];
+            const double* X = frag_lib + frag_off[k] + (int64_t)conf[p * F + k] * 3 * nk;
+            const double* r = R + (p * F + k) * 9;
+            const double* tt = t + (p * F + k) * 3;
+            for (int a = lane; a < nk; a += 32) {
+                const double x = X[3 * a], y = X[3 * a + 1], z = X[3 * a + 2];
+                double* d = S_out + (q * A_total + o + a) * 3;
+                d[0] = fma(r[2], z, fma(r[1], y, r[0] * x)) + tt[0];
+                d[1] = fma(r[5], z, fma(r[4], y, r[3] * x)) + tt[1];
+                d[2] = fma(r[8], z, fma(r[7], y, r[6] * x)) + tt[2];
+            }
+            o += nk;
+        }
+    }
+}
+
+static int clash_grid(int64_t P) {
+    int64_t blocks = (P + CLASH_WARPS - 1) / CLASH_WARPS;
+    const int64_t cap = 148 * 8;         // 8 resident CTAs of 8 warps per SM
+    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace tsc
+
+extern "C" int tsc_embed_clash(const double* frag_lib, const int64_t* frag_off, const int32_t* n_atoms, int32_t F,
+                               int32_t A_total, const int32_t* conf, const double* R, const double* t, int64_t P,
+                               double t2, double thresh, int64_t max_clashes, uint8_t* verdict,
+                               uint64_t* near_count, void* stream) {
+    using namespace tsc;
+    if (P <= 0) return 0;
+    if (F != 2 && F != 3) return (int)cudaErrorInvalidValue;
+    ClashThresh th{t2, (thresh - 1e-9) * (thresh - 1e-9), (thresh + 1e-9) * (thresh + 1e-9)};
+    const size_t smem = (size_t)CLASH_WARPS * 3 * A_total * sizeof(double);
+    if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
+    cudaError_t e;
+    if (near_count) {
+        e = cudaFuncSetAttribute(embed_clash_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        embed_clash_kernel<true><<<clash_grid(P), CLASH_WARPS * 32, smem, (cudaStream_t)stream>>>(
+            frag_lib, frag_off, n_atoms, F, conf, R, t, P, A_total, th, max_clashes, verdict,
+            reinterpret_cast<unsigned long long*>(near_count));
+    } else {
+        e = cudaFuncSetAttribute(embed_clash_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        embed_clash_kernel<false><<<clash_grid(P), CLASH_WARPS * 32, smem, (cudaStream_t)stream>>>(
+            frag_lib, frag_off, n_atoms, F, conf, R, t, P, A_total, th, max_clashes, verdict, nullptr);
+    }
+    TSC_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int tsc_clash_structs(const double* S, int64_t P, int32_t A, const int32_t* ids, int32_t F, double t2,
+                                 double thresh, double t2_half, int64_t max_clashes, uint8_t* verdict,
+                                 uint64_t* near_count, void* stream) {
+    using namespace tsc;
+    if (P <= 0) return 0;
+    if (F != 0 && F != 2 && F != 3) return (int)cudaErrorInvalidValue;
+    ClashThresh th{t2, (thresh - 1e-9) * (thresh - 1e-9), (thresh + 1e-9) * (thresh + 1e-9)};
+    const size_t smem = (size_t)CLASH_WARPS * 3 * A * sizeof(double);
+    if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
+    cudaError_t e;
+    if (near_count && F != 0) {
+        e = cudaFuncSetAttribute(clash_structs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        clash_structs_kernel<true><<<clash_grid(P), CLASH_WARPS * 32, smem, (cudaStream_t)stream>>>(
+            S, P, A, ids, F, th, t2_half, max_clashes, verdict, reinterpret_cast<unsigned long long*>(near_count));
+    } else {
+        e = cudaFuncSetAttribute(clash_structs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        clash_structs_kernel<false><<<clash_grid(P), CLASH_WARPS * 32, smem, (cudaStream_t)stream>>>(
+            S, P, A, ids, F, th, t2_half, max_clashes, verdict, nullptr);
+    }
+    TSC_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int tsc_embed_gather(const double* frag_lib, const int64_t* frag_off, const int32_t* n_atoms, int32_t F,
+                                int32_t A_total, const int32_t* conf, const double* R, const double* t,
+                                const int64_t* keep_idx, int64_t n_keep, double* S_out, void* stream) {
+    using namespace tsc;
+    if (n_keep <= 0) return 0;
+    int64_t blocks = (n_keep + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    embed_gather_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(frag_lib, frag_off, n_atoms, F, conf, R,
+                                                                           t, keep_idx, n_keep, A_total, S_out);
+    TSC_CHECK_LAUNCH();
+    return 0;
+}

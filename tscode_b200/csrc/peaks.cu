@@ -1,0 +1,111 @@
+// peaks.cu — self-measured FP64 peaks (register-resident DFMA / DMMA loops on every SM).
+//
+// MEASURED_PEAKS.json carries HBM and bf16 numbers only; the RMSD kernel is bounded by the FP64
+// pipes, so bench.py measures their ceiling on the same GPU in the same run and quotes
+// fractions "of self-measured FP64 peak" (SURVEY 8(d)).  Not on the product path.
+#include "tsc_common.cuh"
+
+namespace tsc {
+
+constexpr int PK_CHAINS = 12;
+
+__global__ void __launch_bounds__(512) peak_dfma_kernel(double* out, int iters, double seed) {
+    double a[PK_CHAINS];
+    const double x = 1.0 + seed * 1e-9, y = seed * 1e-7 * (threadIdx.x & 7);
+#pragma unroll
+    for (int c = 0; c < PK_CHAINS; c++) a[c] = c + threadIdx.x * 1e-3;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < PK_CHAINS; c++) a[c] = fma(a[c], x, y);
+    }
+    double s = 0;
+#pragma unroll
+    for (int c = 0; c < PK_CHAINS; c++) s += a[c];
+    if (s == 12345.678) out[0] = s;
+}
+
+__global__ void __launch_bounds__(512) peak_dmma_kernel(double* out, int iters, double seed) {
+    double c0[PK_CHAINS], c1[PK_CHAINS];
+    const double a = 1.0 + seed * 1e-9 * threadIdx.x, b = 1e-3 * seed * (threadIdx.x & 3);
+#pragma unroll
+    for (int c = 0; c < PK_CHAINS; c++) { c0[c] = c; c1[c] = -c; }
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < PK_CHAINS; c++) dmma884(c0[c], c1[c], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int c = 0; c < PK_CHAINS; c++) s += c0[c] + c1[c];
+    if (s == 12345.678) out[0] = s;
+}
+
+// even warps DMMA, odd warps DFMA: do the two share a pipe?
+__global__ void __launch_bounds__(512) peak_mixed_kernel(double* out, int iters, double seed) {
+    const int warp = threadIdx.x >> 5;
+    double c0[PK_CHAINS], c1[PK_CHAINS];
+    const double a = 1.0 + seed * 1e-9 * threadIdx.x, b = 1e-3 * seed * (threadIdx.x & 3);
+#pragma unroll
+    for (int c = 0; c < PK_CHAINS; c++) { c0[c] = c; c1[c] = -c; }
+    if (warp & 1) {
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < PK_CHAINS; c++) c0[c] = fma(c0[c], a, b);
+        }
+    } else {
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < PK_CHAINS; c++) dmma884(c0[c], c1[c], a, b);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int c = 0; c < PK_CHAINS; c++) s += c0[c] + c1[c];
+    if (s == 12345.678) out[0] = s;
+}
+
+}  // namespace tsc
+
+// kind 0 = DFMA, 1 = DMMA, 2 = mixed (even warps DMMA, odd warps DFMA).
+// Synchronous (times itself with CUDA events on `stream`).  flops_out = FP64 flop executed,
+// for kind 2: flops_out[0] = DMMA part, flops_out[1] = DFMA part.  ms_out = elapsed.
+extern "C" int tsc_bench_fp64(int32_t kind, int32_t iters, int32_t ctas_per_sm, int32_t threads, double* scratch,
+                              double* flops_out, float* ms_out, void* stream) {
+    using namespace tsc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (threads <= 0 || threads > 512) threads = 512;
+    if (ctas_per_sm <= 0) ctas_per_sm = 2;
+    const int grid = sms * ctas_per_sm;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int rep = 0; rep < 2; rep++) {        // rep 0 = warm-up
+        cudaEventRecord(e0, st);
+        if (kind == 0) peak_dfma_kernel<<<grid, threads, 0, st>>>(scratch, iters, 1.0);
+        else if (kind == 1) peak_dmma_kernel<<<grid, threads, 0, st>>>(scratch, iters, 1.0);
+        else peak_mixed_kernel<<<grid, threads, 0, st>>>(scratch, iters, 1.0);
+        cudaEventRecord(e1, st);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) return (int)e;
+    }
+    cudaEventElapsedTime(ms_out, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double nthreads = (double)grid * threads, nwarps = nthreads / 32.0;
+    const double per = (double)iters * 4 * PK_CHAINS;
+    if (kind == 0) { flops_out[0] = 0; flops_out[1] = nthreads * per * 2.0; }
+    else if (kind == 1) { flops_out[0] = nwarps * per * 512.0; flops_out[1] = 0; }
+    else { flops_out[0] = (nwarps / 2) * per * 512.0; flops_out[1] = (nthreads / 2) * per * 2.0; }
+    TSC_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,108 @@
+// tsc_common.cuh — layout constants, PTX wrappers (mbarrier, bulk-TMA, DMMA) and error plumbing
+// shared by the sm_100a kernels of tscode_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tsc {
+
+// ------------------------------------------------------------------------------------------
+// Packed ensemble layout in HBM ("tiled SoA", produced by pack.cu, consumed by every RMSD kernel)
+//
+//   packed[slab s][block b][comp a][conformer c][atom k]      doubles
+//     CB = 32 conformers per block, KS = 20 atoms per slab, comp in {x,y,z}
+//     element (conformer i, heavy atom m, comp a) lives at
+//       (((m / KS) * nb_pad + i / CB) * 3 + a) * (CB * KS) + (i % CB) * KS + (m % KS)
+//   nb_pad = number of conformer blocks rounded up to even, nslab = ceil(M / KS); padding
+//   conformers / atoms are zero (they contribute nothing to covariances or norms).
+//
+// One (slab, block) chunk is 3*32*20 doubles = 15 360 B contiguous: the unit of a bulk-TMA
+// copy, and already the shared-memory image the MMA fragments are read from.  The row stride
+// of 20 doubles (== 4 mod 16) makes the DMMA fragment loads (lane -> conformer lane/4, atom
+// lane%4) hit 16 distinct 8-byte banks per half-warp.
+// ------------------------------------------------------------------------------------------
+constexpr int CB = 32;
+constexpr int KS = 20;
+constexpr int CHUNK_D = 3 * CB * KS;          // doubles per (slab, block) chunk
+constexpr int CHUNK_BYTES = CHUNK_D * 8;      // 15360
+
+__host__ __device__ inline int64_t num_blocks_padded(int64_t N) {
+    int64_t nb = (N + CB - 1) / CB;
+    nb += nb & 1;
+    return nb < 2 ? 2 : nb;
+}
+__host__ __device__ inline int num_slabs(int M) { return (M + KS - 1) / KS; }
+__host__ __device__ inline int64_t packed_index(int64_t i, int m, int a, int64_t nb_pad) {
+    return (((int64_t)(m / KS) * nb_pad + i / CB) * 3 + a) * (CB * KS) + (i % CB) * KS + (m % KS);
+}
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk TMA: global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// FP64 tensor-core MMA, D(8x8) += A(8x4, row) * B(4x8, col)   (SASS: DMMA.8x8x4)
+//   A: lane holds A[lane>>2][lane&3];  B: lane holds B[lane&3][lane>>2];
+//   C/D: lane holds C[lane>>2][2*(lane&3) + {0,1}]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+#endif
+
+}  // namespace tsc
+
+#define TSC_CHECK_LAUNCH()                                  \
+    do {                                                    \
+        cudaError_t e__ = cudaGetLastError();               \
+        if (e__ != cudaSuccess) return (int)e__;            \
+    } while (0)

@@ -1,0 +1,191 @@
+// tsc_math.cuh — per-pair closed-form math shared by the RMSD kernels.
+//
+// Everything here is __host__ __device__ so that tests/hostmath (a test-only harness compiled
+// with nvcc for the CPU) can check the numerics in the GPU-less build container.  The product
+// library only ever calls these from device code.
+//
+// Reference semantics being reproduced: rmsd_and_max_numba, tscode/rmsd_pruning.py:6-41
+// (rotation-only Kabsch about the origin, improper-rotation fix, RMSD and max deviation).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define TSC_HD __host__ __device__ __forceinline__
+#else
+#define TSC_HD inline
+#endif
+
+namespace tsc {
+
+// ------------------------------------------------------------------------------------------
+// Horn's 4x4 key matrix of the cross-covariance S (S[a][b] = sum_m p_m[a] * q_m[b]).
+// Its largest eigenvalue is max over PROPER rotations R of sum_m (R p_m) . q_m, i.e.
+// sigma1 + sigma2 + sign(det S) * sigma3 — exactly what Kabsch with the reflection fix
+// (rmsd_pruning.py:20-23) attains.  Stored as the 10 upper-triangular entries.
+// ------------------------------------------------------------------------------------------
+struct Key4 {
+    double k00, k01, k02, k03, k11, k12, k13, k22, k23, k33;
+};
+
+TSC_HD Key4 key_matrix(const double S[9]) {
+    Key4 K;
+    K.k00 = S[0] + S[4] + S[8];
+    K.k01 = S[5] - S[7];
+    K.k02 = S[6] - S[2];
+    K.k03 = S[1] - S[3];
+    K.k11 = S[0] - S[4] - S[8];
+    K.k12 = S[1] + S[3];
+    K.k13 = S[6] + S[2];
+    K.k22 = -S[0] + S[4] - S[8];
+    K.k23 = S[5] + S[7];
+    K.k33 = -S[0] - S[4] + S[8];
+    return K;
+}
+
+// Characteristic polynomial of the (traceless) key matrix: P(x) = x^4 + c2 x^2 + c1 x + c0,
+//   c2 = -2 ||S||_F^2,  c1 = -8 det S,  c0 = det K.
+TSC_HD void key_charpoly(const double S[9], double& c2, double& c1, double& c0) {
+    double f = S[0] * S[0];
+    f = fma(S[1], S[1], f); f = fma(S[2], S[2], f);
+    f = fma(S[3], S[3], f); f = fma(S[4], S[4], f); f = fma(S[5], S[5], f);
+    f = fma(S[6], S[6], f); f = fma(S[7], S[7], f); f = fma(S[8], S[8], f);
+    c2 = -2.0 * f;
+    double d = S[0] * fma(S[4], S[8], -S[5] * S[7]);
+    d = fma(-S[1], fma(S[3], S[8], -S[5] * S[6]), d);
+    d = fma(S[2], fma(S[3], S[7], -S[4] * S[6]), d);
+    c1 = -8.0 * d;
+    Key4 K = key_matrix(S);
+    // det of the symmetric 4x4 through 2x2 minors of rows (0,1) and rows (2,3)
+    double a01 = fma(K.k00, K.k11, -K.k01 * K.k01);
+    double a02 = fma(K.k00, K.k12, -K.k02 * K.k01);
+    double a03 = fma(K.k00, K.k13, -K.k03 * K.k01);
+    double a12 = fma(K.k01, K.k12, -K.k02 * K.k11);
+    double a13 = fma(K.k01, K.k13, -K.k03 * K.k11);
+    double a23 = fma(K.k02, K.k13, -K.k03 * K.k12);
+    double b01 = fma(K.k02, K.k13, -K.k12 * K.k03);
+    double b02 = fma(K.k02, K.k23, -K.k22 * K.k03);
+    double b03 = fma(K.k02, K.k33, -K.k23 * K.k03);
+    double b12 = fma(K.k12, K.k23, -K.k22 * K.k13);
+    double b13 = fma(K.k12, K.k33, -K.k23 * K.k13);
+    double b23 = fma(K.k22, K.k33, -K.k23 * K.k23);
+    double det = a01 * b23;
+    det = fma(-a02, b13, det);
+    det = fma(a03, b12, det);
+    det = fma(a12, b03, det);
+    det = fma(-a13, b02, det);
+    det = fma(a23, b01, det);
+    c0 = det;
+}
+
+// ------------------------------------------------------------------------------------------
+// Screen: can this pair possibly have rmsd < thr ?
+//   E_opt = G - 2*lambda_max  (G = |p|^2 + |q|^2),   rmsd^2 = E_opt / M.
+//   rmsd < thr  <=>  lambda_max > lam_t := (G - M*thr^2) / 2.
+// All roots of P are real (K symmetric), so by Budan-Fourier the number of roots above x
+// equals the number of sign changes in (P, P', P'', P''', P'''')(x).  P'''' = 24 > 0, hence
+//   "no root above lam_t"  <=>  P, P', P'', P''' all > 0 at lam_t.
+// No eigen-solve, no iteration, no divergence.  `e_thr_pad` is M*thr^2 plus a safety margin
+// (callers use M*thr^2*(1+1e-6) + 1e-10*G): every pair the screen passes is re-evaluated
+// exactly (rotation applied, explicit differences) before its bit is trusted, so the margin
+// only costs a few extra verifications and can never lose a true pair.
+// Returns true when the pair is a CANDIDATE (cannot be excluded).
+// ------------------------------------------------------------------------------------------
+TSC_HD bool screen_candidate(const double S[9], double G, double e_thr_pad) {
+    double lam = 0.5 * (G - e_thr_pad);
+    if (!(lam > 0.0)) return true;
+    double c2, c1, c0;
+    key_charpoly(S, c2, c1, c0);
+    double l2 = lam * lam;
+    double p2 = fma(12.0, l2, 2.0 * c2);                 // P''
+    double p1 = fma(fma(4.0, l2, 2.0 * c2), lam, c1);    // P'
+    double p0 = fma(fma(l2 + c2, lam, c1), lam, c0);     // P
+    return !((p0 > 0.0) && (p1 > 0.0) && (p2 > 0.0));
+}
+
+// ------------------------------------------------------------------------------------------
+// Largest eigenpair of the key matrix by cyclic Jacobi (always converges, any eigenvector of a
+// degenerate top eigenspace is an optimal rotation).  q = (q0, q1, q2, q3) unit quaternion,
+// scalar first.  Returns lambda_max; *gap receives lambda_1 - lambda_2.
+// ------------------------------------------------------------------------------------------
+TSC_HD double key_top_eigen(const Key4& K, double q[4], double* gap) {
+    double A[4][4] = {{K.k00, K.k01, K.k02, K.k03},
+                      {K.k01, K.k11, K.k12, K.k13},
+                      {K.k02, K.k12, K.k22, K.k23},
+                      {K.k03, K.k13, K.k23, K.k33}};
+    double V[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+    double scale = 0.0;
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) scale += A[i][j] * A[i][j];
+    for (int sweep = 0; sweep < 30; sweep++) {
+        double off = 0.0;
+        for (int i = 0; i < 3; i++)
+            for (int j = i + 1; j < 4; j++) off += A[i][j] * A[i][j];
+        if (off <= 1e-32 * scale) break;
+#pragma unroll
+        for (int p = 0; p < 3; p++)
+#pragma unroll
+            for (int r = p + 1; r < 4; r++) {
+                double apr = A[p][r];
+                if (apr == 0.0) continue;
+                double theta = (A[r][r] - A[p][p]) / (2.0 * apr);
+                double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+                double c = 1.0 / sqrt(fma(t, t, 1.0)), s = t * c;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    double akp = A[k][p], akr = A[k][r];
+                    A[k][p] = c * akp - s * akr;
+                    A[k][r] = s * akp + c * akr;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    double apk = A[p][k], ark = A[r][k];
+                    A[p][k] = c * apk - s * ark;
+                    A[r][k] = s * apk + c * ark;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    double vkp = V[k][p], vkr = V[k][r];
+                    V[k][p] = c * vkp - s * vkr;
+                    V[k][r] = s * vkp + c * vkr;
+                }
+            }
+    }
+    double best = A[0][0], second = -1e300;
+    int bi = 0;
+#pragma unroll
+    for (int i = 1; i < 4; i++) {
+        if (A[i][i] > best) { second = best; best = A[i][i]; bi = i; }
+        else if (A[i][i] > second) second = A[i][i];
+    }
+    // select column bi without dynamic indexing (keeps V in registers on the device)
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        q[k] = (bi == 0) ? V[k][0] : (bi == 1) ? V[k][1] : (bi == 2) ? V[k][2] : V[k][3];
+    double n = 1.0 / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    q[0] *= n; q[1] *= n; q[2] *= n; q[3] *= n;
+    if (gap) *gap = best - second;
+    return best;
+}
+
+// Rotation matrix (column-vector convention, x' = R x) of a unit quaternion, scalar first.
+TSC_HD void quat_to_rot(const double q[4], double R[9]) {
+    double q00 = q[0] * q[0], q11 = q[1] * q[1], q22 = q[2] * q[2], q33 = q[3] * q[3];
+    double q01 = q[0] * q[1], q02 = q[0] * q[2], q03 = q[0] * q[3];
+    double q12 = q[1] * q[2], q13 = q[1] * q[3], q23 = q[2] * q[3];
+    R[0] = q00 + q11 - q22 - q33; R[1] = 2.0 * (q12 - q03);       R[2] = 2.0 * (q13 + q02);
+    R[3] = 2.0 * (q12 + q03);       R[4] = q00 - q11 + q22 - q33; R[5] = 2.0 * (q23 - q01);
+    R[6] = 2.0 * (q13 - q02);       R[7] = 2.0 * (q23 + q01);       R[8] = q00 - q11 - q22 + q33;
+}
+
+// Optimal proper rotation taking p onto q (x' = R x) from their cross-covariance.
+// The reference's `rot_mat` (rmsd_pruning.py:26, row-vector convention p @ rot) is R^T.
+TSC_HD void kabsch_rot_from_cov(const double S[9], double R[9], double* lambda_max, double* gap) {
+    Key4 K = key_matrix(S);
+    double q[4];
+    double lam = key_top_eigen(K, q, gap);
+    if (lambda_max) *lambda_max = lam;
+    quat_to_rot(q, R);
+}
+
+}  // namespace tsc

@@ -1,0 +1,259 @@
+"""B200-native drop-in for tscode/rmsd_pruning.py.
+
+Same call signatures and return values as the reference:
+
+    prune_conformers_rmsd(structures, atomnos, rmsd_thr=0.5) -> (structures[mask], mask)   # :164-206
+    rmsd_and_max_numba(p, q) -> (rmsd, max_deviation)                                      # :6-41
+    _rmsd_similarity(ref, structures, rmsd_thr=0.5) -> bool                                # :208-224
+
+plus the device-resident, batched form (`RmsdPruner`) that bench.py and multi-GPU runs use.
+All arithmetic runs in hand-written sm_100a kernels behind the C-ABI of
+include/tscode_b200.h; torch only owns device memory, streams and the process group.
+There is no CPU fallback: without the built extension or a CUDA device every call raises.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _host
+from ._lib import check, lib, ptr, require_cuda, stream_ptr
+
+VARIANTS = {"dmma": 0, "fma": 1}
+
+
+class RmsdPruner:
+    """All-pairs Kabsch similarity + k-ladder elimination for one ensemble, resident in HBM.
+
+    structures : (N, A, 3) float64, numpy array or torch tensor (host or device)
+    atomnos    : (A,) ints; hydrogens (== 1) are ignored        (rmsd_pruning.py:178-179)
+    rank/world/group : row-block sharding over one process per GPU (block-cyclic);
+                 every rank holds the whole packed ensemble, computes the similarity rows it
+                 owns, and per elimination round contributes its rows' verdicts to an NCCL
+                 all-gather.
+    """
+
+    def __init__(self, structures, atomnos, rmsd_thr=0.5, *, variant="dmma", device=None,
+                 rank=0, world=1, group=None, grid_ctas=0):
+        torch = require_cuda()
+        self.torch = torch
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.thr = float(rmsd_thr)
+        self.variant = VARIANTS[variant] if isinstance(variant, str) else int(variant)
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.grid_ctas = int(grid_ctas)
+        atomnos = np.asarray(atomnos)
+        heavy = np.flatnonzero(atomnos != 1).astype(np.int32)
+        if torch.is_tensor(structures):
+            S = structures.to(self.device, dtype=torch.float64).contiguous()
+        else:
+            S = torch.as_tensor(np.ascontiguousarray(structures, dtype=np.float64)).to(self.device)
+        if S.dim() != 3 or S.shape[2] != 3 or S.shape[1] != atomnos.shape[0]:
+            raise ValueError(f"structures must be (N, {atomnos.shape[0]}, 3), got {tuple(S.shape)}")
+        self.S = S
+        self.N, self.A, self.M = int(S.shape[0]), int(S.shape[1]), int(heavy.size)
+        N, M = self.N, self.M
+        self.nb_pad = _host.num_blocks_padded(N)
+        self.W = self.nb_pad
+        with torch.cuda.device(self.device):
+            dev = self.device
+            self.heavy_idx = torch.from_numpy(heavy).to(dev)
+            self.row_blocks_np = _host.owned_row_blocks(N, self.rank, self.world)
+            self.n_rb = int(self.row_blocks_np.size)
+            self.row_blocks = torch.from_numpy(self.row_blocks_np).to(dev)
+            tiles = _host.build_tiles(N, self.row_blocks_np)
+            self.n_tiles = int(tiles.shape[0])
+            self.tiles = torch.from_numpy(tiles).to(dev)
+            self.packed = torch.empty(max(_host.packed_doubles(N, max(M, 1)), 1), dtype=torch.float64, device=dev)
+            self.G = torch.empty(self.nb_pad * _host.CB, dtype=torch.float64, device=dev)
+            self.sim_bits = torch.empty((max(self.n_rb, 1) * _host.CB, self.W), dtype=torch.int32, device=dev)
+            self.stats = torch.zeros(4, dtype=torch.int64, device=dev)
+            nw = (N + 31) // 32
+            rows_pad = self.nb_pad * _host.CB
+            self.active = torch.empty(max(nw, 1), dtype=torch.int32, device=dev)
+            self.cachebits = torch.empty(max(nw, 1), dtype=torch.int32, device=dev)
+            self.mask_bytes = torch.ones(rows_pad, dtype=torch.uint8, device=dev)
+            self.row_keys = torch.full((rows_pad,), -1, dtype=torch.int32, device=dev)
+            self.key_first = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+            self.key_second = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+            self.n_keys = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.n_active = torch.zeros(1, dtype=torch.int32, device=dev)
+            if self.world > 1:
+                self._init_shards()
+        self.rounds = []
+        self.packed_ready = False
+
+    # ---- multi-GPU plumbing -------------------------------------------------------------------
+    def _init_shards(self):
+        torch = self.torch
+        n_rb_all = [_host.owned_row_blocks(self.N, r, self.world).size for r in range(self.world)]
+        self.n_rb_max = max(max(n_rb_all), 1)
+        L = self.n_rb_max * _host.CB
+        rows_pad = self.nb_pad * _host.CB
+        gidx = np.full((self.world, L), rows_pad, dtype=np.int64)     # rows_pad = scratch slot
+        for r in range(self.world):
+            g = _host.global_rows_of(_host.owned_row_blocks(self.N, r, self.world))
+            gidx[r, :g.size] = g
+        dev = self.device
+        self.gather_index = torch.from_numpy(gidx.reshape(-1)).to(dev)
+        self.my_rows = torch.from_numpy(np.minimum(gidx[self.rank], rows_pad - 1)).to(dev)
+        self.loc_mask = torch.zeros(L, dtype=torch.uint8, device=dev)
+        self.loc_keys = torch.full((L,), -1, dtype=torch.int32, device=dev)
+        self.all_mask = torch.empty(self.world * L, dtype=torch.uint8, device=dev)
+        self.all_keys = torch.empty(self.world * L, dtype=torch.int32, device=dev)
+        self.mask_scratch = torch.ones(rows_pad + 1, dtype=torch.uint8, device=dev)
+        self.keys_scratch = torch.full((rows_pad + 1,), -1, dtype=torch.int32, device=dev)
+
+    def _exchange_round(self):
+        """All-gather this round's per-row verdicts and emitted keys (NCCL over NVLink)."""
+        import torch.distributed as dist
+        torch = self.torch
+        L = self.n_rb_max * _host.CB
+        n_mine = self.n_rb * _host.CB
+        self.loc_mask[:n_mine] = self.mask_bytes[self.my_rows[:n_mine]]
+        self.loc_keys[:n_mine] = self.row_keys[self.my_rows[:n_mine]]
+        dist.all_gather_into_tensor(self.all_mask, self.loc_mask, group=self.group)
+        dist.all_gather_into_tensor(self.all_keys, self.loc_keys, group=self.group)
+        self.mask_scratch.index_copy_(0, self.gather_index, self.all_mask)
+        self.keys_scratch.index_copy_(0, self.gather_index, self.all_keys)
+        rows_pad = self.nb_pad * _host.CB
+        self.mask_bytes.copy_(self.mask_scratch[:rows_pad])
+        self.row_keys.copy_(self.keys_scratch[:rows_pad])
+
+    # ---- phases -------------------------------------------------------------------------------
+    def pack(self):
+        if self.N == 0 or self.M == 0:
+            return
+        L = lib()
+        with self.torch.cuda.device(self.device):
+            check(L.tsc_pack(ptr(self.S), self.N, self.A, ptr(self.heavy_idx), self.M, ptr(self.packed),
+                             ptr(self.G), stream_ptr()), "tsc_pack")
+        self.packed_ready = True
+
+    def screen(self):
+        """All-pairs contraction + closed-form screen (the hot kernel)."""
+        if self.n_tiles == 0 or self.M == 0:
+            return
+        if not self.packed_ready:
+            self.pack()
+        L = lib()
+        with self.torch.cuda.device(self.device):
+            check(L.tsc_rmsd_sim_tiles(ptr(self.packed), ptr(self.G), self.N, self.M, ptr(self.tiles),
+                                       self.n_tiles, self.thr, ptr(self.sim_bits), self.variant, self.grid_ctas,
+                                       stream_ptr()), "tsc_rmsd_sim_tiles")
+
+    def verify(self):
+        """Exact re-evaluation of screened pairs; afterwards sim_bits are final."""
+        if self.n_rb == 0 or self.M == 0:
+            return
+        L = lib()
+        with self.torch.cuda.device(self.device):
+            check(L.tsc_rmsd_verify(ptr(self.packed), self.N, self.M, ptr(self.row_blocks), self.n_rb, self.thr,
+                                    ptr(self.sim_bits), ptr(self.stats), stream_ptr()), "tsc_rmsd_verify")
+
+    def similarity(self):
+        self.screen()
+        self.verify()
+
+    def _round(self, k: int, cs: int) -> int:
+        L = lib()
+        N = self.N
+        st = stream_ptr()
+        check(L.tsc_elim_cachebits(ptr(self.key_first), ptr(self.key_second), ptr(self.n_keys), N, cs, k,
+                                   ptr(self.cachebits), st), "tsc_elim_cachebits")
+        if self.n_rb:
+            check(L.tsc_elim_round(ptr(self.sim_bits), ptr(self.row_blocks), self.n_rb, ptr(self.active),
+                                   ptr(self.cachebits), N, cs, k, ptr(self.mask_bytes), ptr(self.row_keys), st),
+                  "tsc_elim_round")
+        if self.world > 1:
+            self._exchange_round()
+        check(L.tsc_elim_commit(ptr(self.mask_bytes), ptr(self.row_keys), N, cs, k, ptr(self.active),
+                                ptr(self.key_first), ptr(self.key_second), ptr(self.n_keys), ptr(self.n_active), st),
+              "tsc_elim_commit")
+        return int(self.n_active.item())
+
+    def eliminate(self):
+        """The k-ladder (rmsd_pruning.py:186-204).  Returns the boolean mask as a device tensor."""
+        torch = self.torch
+        N = self.N
+        if N == 0:
+            return torch.zeros(0, dtype=torch.bool, device=self.device)
+        with torch.cuda.device(self.device):
+            self.mask_bytes.fill_(1)
+            self.row_keys.fill_(-1)
+            self.n_keys.zero_()
+            if self.M == 0:
+                # no heavy atoms: every covariance is empty -> rmsd 0 for all pairs in the reference
+                raise ValueError("prune_conformers_rmsd needs at least one non-hydrogen atom")
+            # active words from an all-ones mask (k/cs irrelevant: no keys emitted)
+            check(lib().tsc_elim_commit(ptr(self.mask_bytes), ptr(self.row_keys), N, N, 1, ptr(self.active),
+                                        ptr(self.key_first), ptr(self.key_second), ptr(self.n_keys),
+                                        ptr(self.n_active), stream_ptr()), "tsc_elim_commit(init)")
+            self.rounds = _host.run_ladder(N, self._round)
+            return self.mask_bytes[:N].to(torch.bool)
+
+    def run(self):
+        self.pack()
+        self.similarity()
+        return self.eliminate()
+
+    # ---- introspection ------------------------------------------------------------------------
+    def stats_dict(self):
+        s = self.stats.tolist()
+        return {"candidates": s[0], "confirmed": s[1], "near_threshold": s[2], "degenerate": s[3]}
+
+    def sim_rows_dense(self):
+        """Owned similarity rows as a dense bool matrix (n_rb*32, N) — tests only."""
+        torch = self.torch
+        bits = self.sim_bits[: self.n_rb * _host.CB].cpu().numpy().view(np.uint32)
+        rows = _host.global_rows_of(self.row_blocks_np)
+        dense = np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little")[:, : self.N].astype(bool)
+        # words left of the diagonal block are never written (and never read): blank them
+        col = np.arange(self.N)[None, :]
+        dense &= col > rows[:, None]
+        return rows, dense
+
+
+def prune_conformers_rmsd(structures, atomnos, rmsd_thr=0.5):
+    """Drop-in for tscode.rmsd_pruning.prune_conformers_rmsd (rmsd_pruning.py:164-206).
+
+    Removes similar structures (rmsd < rmsd_thr and max atomic deviation < 2*rmsd_thr on the
+    non-hydrogen atoms, rotation-only Kabsch about the origin) with the reference's k-ladder,
+    cache behaviour included.  Returns (structures[mask], mask) as numpy arrays."""
+    structures = np.asarray(structures)
+    N = structures.shape[0]
+    if N == 0:
+        return structures[:0], np.zeros(0, dtype=np.bool_)
+    pr = RmsdPruner(structures, atomnos, rmsd_thr)
+    mask = pr.run().cpu().numpy().astype(np.bool_)
+    return structures[mask], mask
+
+
+def rmsd_and_max_batch(P, Q, broadcast_p=False):
+    """rmsd_and_max_numba over explicit pairs: P, Q (n, M, 3) -> (rmsd (n,), maxdev (n,)) numpy."""
+    torch = require_cuda()
+    dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+    Pt = torch.as_tensor(np.ascontiguousarray(P, dtype=np.float64)).to(dev)
+    Qt = torch.as_tensor(np.ascontiguousarray(Q, dtype=np.float64)).to(dev)
+    n, M = int(Qt.shape[0]), int(Qt.shape[1])
+    r = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+    d = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+    if n and M:
+        check(lib().tsc_rmsd_pairs(ptr(Pt), ptr(Qt), n, M, 1 if broadcast_p else 0, ptr(r), ptr(d), stream_ptr()),
+              "tsc_rmsd_pairs")
+    return r[:n].cpu().numpy(), d[:n].cpu().numpy()
+
+
+def rmsd_and_max_numba(p, q):
+    """Drop-in for tscode.rmsd_pruning.rmsd_and_max_numba (rmsd_pruning.py:6-41)."""
+    r, d = rmsd_and_max_batch(np.asarray(p)[None], np.asarray(q)[None])
+    return float(r[0]), float(d[0])
+
+
+def _rmsd_similarity(ref, structures, rmsd_thr=0.5):
+    """Drop-in for tscode.rmsd_pruning._rmsd_similarity (rmsd_pruning.py:208-224): is `ref`
+    similar to any of `structures` (all atoms, no cache)."""
+    structures = list(structures) if not isinstance(structures, np.ndarray) else structures
+    if len(structures) == 0:
+        return False
+    r, d = rmsd_and_max_batch(np.asarray(ref)[None], np.asarray(structures), broadcast_p=True)
+    return bool(np.any((r < rmsd_thr) & (d < 2 * rmsd_thr)))
