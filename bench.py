@@ -282,7 +282,9 @@ def run_b200(args):
 
     # ---- e2e through the public drop-in API, host buffers (N = 1: the API is single-GPU) -------
     e2e = None
-    if world == 1:
+    if args.skip_extras:
+        pass
+    elif world == 1:
         for _ in range(2):
             prune_conformers_rmsd(S_pinned_np, atomnos, thr)
         ts = []
@@ -320,7 +322,7 @@ def run_b200(args):
         return
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------
-    peaks = fp64_peaks(torch)
+    peaks = fp64_peaks(torch) if not args.skip_extras else {"dfma": 34.2, "dmma": 37.1, "mixed": 36.7}
     mp, mp_src = measured_peaks()
     flops = 18.0 * M * pairs / world
     achieved = flops / (screen_ms * 1e-3) / 1e12
@@ -335,12 +337,12 @@ def run_b200(args):
 
     # ---- CPU baseline (rank 0, bounded sample) --------------------------------------------------------
     cpu = None
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and not args.skip_extras:
         cpu, _, _ = cpu_baseline_pairs(S_host, thr, target_s=12.0)
 
     # ---- secondary metric: clash-checked poses/s (BASELINE configs[1]) ------------------------------------
     clash = None
-    if world == 1:
+    if world == 1 and not args.skip_extras:
         frags, conf, R, tt = gen_poses(C2["seed"], C2["P"], C2["n_atoms"])
         pb = PoseBatch(frags, conf, R, tt)
         for _ in range(3):
@@ -398,6 +400,8 @@ def main():
     ap.add_argument("--n-conformers", type=int, default=0, help="override N (testing only; invalid as a bench value)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--lazy-n", type=int, default=10000)
+    ap.add_argument("--skip-extras", action="store_true",
+                    help="profiling aid: only the timed prune steps (no e2e / clash / peak legs); not a bench value")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -97,7 +97,7 @@ def test_rmsd_similarity_vs_reference(gpu):
 @pytest.mark.parametrize("seed,N,M,nc,noise,thr", [
     (0, 1000, 40, 100, 0.05, 0.5),
     (5, 777, 29, 60, 0.05, 0.25),
-    (6, 1037, 33, 90, 0.3, 0.5),       # many pairs near the threshold
+    (6, 1037, 33, 90, 0.205, 0.5),     # same-cluster pairs straddle the threshold
     (9, 400, 12, 1, 0.01, 0.5),        # everything similar
     (8, 300, 40, 300, 1.0, 0.5),       # nothing similar
     (13, 65, 80, 3, 0.2, 0.5),

@@ -137,6 +137,7 @@ class RmsdPruner:
             self.pack()
         L = lib()
         with self.torch.cuda.device(self.device):
+            self.stats.zero_()
             check(L.tsc_rmsd_sim_tiles(ptr(self.packed), ptr(self.G), self.N, self.M, ptr(self.tiles),
                                        self.n_tiles, self.thr, ptr(self.sim_bits), self.variant, self.grid_ctas,
                                        stream_ptr()), "tsc_rmsd_sim_tiles")
