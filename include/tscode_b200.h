@@ -17,6 +17,8 @@
  *   rmsd_pruning.py:208   _rmsd_similarity        -> tsc_rmsd_pairs (broadcast_p = 1)
  *   numba_functions.py:60 compenetration_check    -> tsc_clash_structs / tsc_embed_clash
  *   embeds.py:961         get_embed               -> tsc_embed_gather (and fused in tsc_embed_clash)
+ *   torsion_module.py:953 rotationally_corrected_rmsd / :1013 prune_conformers_rmsd_rot_corr
+ *                                                 -> tsc_rotcorr_pairs + tsc_rotcorr_apply
  */
 #ifndef TSCODE_B200_H
 #define TSCODE_B200_H
@@ -105,6 +107,29 @@ int tsc_clash_structs(const double* S, int64_t P, int32_t A, const int32_t* ids,
 int tsc_embed_gather(const double* frag_lib, const int64_t* frag_off, const int32_t* n_atoms, int32_t F,
                      int32_t A_total, const int32_t* conf, const double* R, const double* t,
                      const int64_t* keep_idx, int64_t n_keep, double* S_out, void* stream);
+
+/* ---- prune_conformers_rmsd_rot_corr ---------------------------------------------------------- */
+/* Rotor-corrected RMSD of every pair (i in [row_begin,row_end), j > i), stateless from the centred
+ * structures Sc (N, A, 3)  (rotationally_corrected_rmsd, torsion_module.py:953-1011).
+ *   heavy (A) uint8; T <= 10 rotors: tor_i2/tor_i3 (T) int32 = bond atoms (axis = x[i2]-x[i3], centre
+ *   x[i3], utils.py:389-414); n_ang (T) <= 6; sin_half/cos_half (T, 6) of angle/2 (host-computed so the
+ *   quaternion of algebra.py:325-344 is bit-identical); rot_mask (T, A) uint8 = _get_rotation_mask
+ *   (:301-325); node_mask (T, A) uint8 = heavy atoms of the rotor's sub-graph (:964-977).
+ *   sim_bits (N, (N+31)/32) uint32: rows [row_begin,row_end) are zeroed, then bit j of row i set iff
+ *   rmsd < max_rmsd (:1118).  codes (N, N) uint32 or NULL: best angle index of rotor t in bits
+ *   [3t, 3t+3).  rmsd_out (N, N) or NULL.  near_count (1) uint64: pairs within 1e-6 A of max_rmsd. */
+int tsc_rotcorr_pairs(const double* Sc, int64_t N, int32_t A, const uint8_t* heavy, int32_t T,
+                      const int32_t* tor_i2, const int32_t* tor_i3, const int32_t* n_ang,
+                      const double* sin_half, const double* cos_half, const uint8_t* rot_mask,
+                      const uint8_t* node_mask, int64_t row_begin, int64_t row_end, double max_rmsd,
+                      uint32_t* sim_bits, uint32_t* codes, double* rmsd_out, uint64_t* near_count,
+                      void* stream);
+/* Structures idx (n) int64 with rotor t turned by its accumulated angle (sin_half/cos_half (n, T)),
+ * in torsion order about the current axis: what the reference's in-place mutation leaves behind
+ * in the structures it returns (torsion_module.py:1004-1008, :1161).  out (n, A, 3). */
+int tsc_rotcorr_apply(const double* Sc, int64_t n, int32_t A, const int64_t* idx, int32_t T,
+                      const int32_t* tor_i2, const int32_t* tor_i3, const double* sin_half,
+                      const double* cos_half, const uint8_t* rot_mask, double* out, void* stream);
 
 /* ---- measurement aid (not on the product path) ------------------------------------------ */
 /* Self-measured FP64 ceilings: kind 0 = DFMA, 1 = DMMA.8x8x4, 2 = both at once (even warps

@@ -173,6 +173,74 @@ def main():
                             rmp=rmp, ref=ref, tgt=tgt, avp=avp)
         print("rot: saved")
 
+    # ---- A6: prune_conformers_rmsd_rot_corr (stub harness: rmsd==1.4 stand-in, see ref_harness) ---
+    if want("rotcorr"):
+        import copy
+        import rotor_molecules as rm
+        from tscode.graph_manipulations import graphize
+        from tscode.torsion_module import (prune_conformers_rmsd_rot_corr, rotationally_corrected_rmsd,
+                                           _get_hydrogen_bonds, _get_torsions, _is_nondummy, _get_rotation_mask)
+        from tscode.utils import get_double_bonds_indices
+        import networkx as nx
+
+        def perceive(ref, atomnos, graph):
+            """exactly the set-up block of torsion_module.py:1026-1049, then the pair-independent
+            per-torsion quantities of :964-977 and :301-325"""
+            graph = copy.deepcopy(graph)
+            hbs = _get_hydrogen_bonds(ref, atomnos, graph)
+            for hb in hbs:
+                graph.add_edge(*hb)
+            tors = _get_torsions(graph, hydrogen_bonds=_get_hydrogen_bonds(ref, atomnos, graph),
+                                 double_bonds=get_double_bonds_indices(ref, atomnos), keepdummy=True)
+            tors = [t for t in tors if not (_is_nondummy(t.i2, t.i3, graph) and _is_nondummy(t.i3, t.i2, graph))]
+            tors = [t for t in tors if 1 not in [atomnos[i] for i in t.torsion]]
+            angles = [t.get_angles() for t in tors]
+            tors = [t.torsion if _is_nondummy(t.i2, t.i3, graph) else list(reversed(t.torsion)) for t in tors]
+            masks, nodes = [], []
+            for t in tors:
+                for o in tors:
+                    if o is not t:
+                        graph.remove_edge(o[1], o[2])
+                nodes.append(sorted(i for i in [s for s in nx.connected_components(graph) if t[1] in s][0] if atomnos[i] != 1))
+                for o in tors:
+                    if o is not t:
+                        graph.add_edge(o[1], o[2])
+                masks.append(_get_rotation_mask(graph, t))
+            return [list(map(int, t)) for t in tors], [list(a) for a in angles], np.array(masks), nodes, graph
+
+        fixtures = {}
+        for name, builder, seed, N, thr in (("neopentyl_s1", rm.ensemble_neopentyl, 1, 40, 0.25),
+                                            ("neopentyl_s2", rm.ensemble_neopentyl, 2, 200, 0.25),
+                                            ("ditbu_s0", rm.ensemble_ditbu, 0, 120, 0.25),
+                                            ("ditbu_s5", rm.ensemble_ditbu, 5, 300, 0.25)):
+            S, atomnos = builder(seed, N)
+            graph = graphize(S[0], atomnos)
+            Sc = np.array([s - s.mean(axis=0) for s in S])
+            tors, angles, masks, nodes, gfull = perceive(Sc[0], atomnos, graph)
+            logs = []
+            t0 = time.perf_counter()
+            out, mask = prune_conformers_rmsd_rot_corr(S.copy(), atomnos, copy.deepcopy(graph), max_rmsd=thr,
+                                                       logfunction=logs.append)
+            dt = time.perf_counter() - t0
+            # stateless pair values on fresh copies (reference function, reference graph handling)
+            rng = np.random.default_rng(seed + 100)
+            pi = rng.integers(0, N, size=60); pj = rng.integers(0, N, size=60)
+            vals, mutated = [], []
+            for a, b in zip(pi, pj):
+                cb = Sc[b].copy()
+                vals.append(rotationally_corrected_rmsd(Sc[a].copy(), cb, atomnos, tors, gfull, angles))
+                mutated.append(cb)
+            fixtures[name] = dict(seed=seed, N=N, thr=thr, torsions=tors, angles=angles, survivors=int(mask.sum()),
+                                  digest=mask_digest(mask), wall_s=round(dt, 2), log=[l for l in logs if l.strip()])
+            np.savez_compressed(os.path.join(GOLD, f"rotcorr_{name}.npz"), atomnos=atomnos, rot_masks=masks,
+                                node_lists=np.array([np.isin(np.arange(len(atomnos)), n) for n in nodes]),
+                                mask=mask, out=out, pair_i=pi, pair_j=pj, pair_rmsd=np.array(vals),
+                                pair_mutated=np.array(mutated))
+            print("rotcorr:", name, {k: v for k, v in fixtures[name].items() if k != "log"})
+        json.dump({"meta": meta, "note": "rmsd==1.4 replaced by the Appendix A.6 stand-in (parity pinned against "
+                   "the stub, not the absent wheel)", "fixtures": fixtures},
+                  open(os.path.join(GOLD, "rotcorr.json"), "w"), indent=1)
+
 
 if __name__ == "__main__":
     main()

@@ -153,3 +153,95 @@ def align_vec_pair(ref, tgt):
     if np.linalg.det(u @ vh) < 0:
         u[:, -1] = -u[:, -1]
     return u @ vh
+
+
+# --- rotor-corrected RMSD (torsion_module.py:953-1161) ------------------------------------------
+def rotate_dihedral(coords, torsion, angle, mask):
+    """utils.py:389-414 — rotate coords[mask] by `angle` degrees about the i2->i3 bond axis
+    (axis = coords[i2] - coords[i3], centre coords[i3]).  Returns a new array."""
+    _, i2, i3, _ = torsion
+    out = np.array(coords, dtype=float, copy=True)
+    mat = rot_mat_from_pointer(out[i2] - out[i3], angle)
+    c = out[i3].copy()
+    out[mask] = (mat @ (out[mask] - c).T).T + c
+    return out
+
+
+def kabsch_rmsd(P, Q):
+    """rmsd==1.4 kabsch_rmsd(P, Q, translate=False): rotation-only Kabsch of P onto Q, then RMSD.
+    (third-party, not vendored: restated from the published algorithm)."""
+    return rmsd_and_max(P, Q)[0]
+
+
+def rotationally_corrected_rmsd(ref, coord, heavy_mask, torsions, angles, rot_masks, node_lists):
+    """torsion_module.py:953-1011, stateless (works on a copy of `coord`).
+    torsions: list of 4-tuples oriented so that the dummy side is last (:1049);
+    angles[t]: tuple of degrees (:112-118); rot_masks[t]: bool (A,) = _get_rotation_mask(graph, t)
+    (:301-325); node_lists[t]: heavy atoms of the component holding t[1] once every OTHER torsion's
+    central bond is cut (:964-977).  Returns (rmsd, corrections, corrected copy of coord)."""
+    coord = np.array(coord, dtype=float, copy=True)
+    corrections = [0] * len(torsions)
+    for t, torsion in enumerate(torsions):
+        best = 1e10
+        nodes = node_lists[t]
+        for angle in angles[t]:                                               # :982-999
+            trial = rotate_dihedral(coord, torsion, angle, rot_masks[t])
+            local = kabsch_rmsd(ref[nodes], trial[nodes])
+            if local < best:
+                best = local
+                corrections[t] = angle
+    coord = apply_rotor_state(coord, torsions, corrections, rot_masks)       # :1004-1008
+    return kabsch_rmsd(ref[heavy_mask], coord[heavy_mask]), corrections, coord  # :1011
+
+
+def apply_rotor_state(coord, torsions, angles_deg, rot_masks):
+    """Rotate every rotor by its angle, in torsion order, each about the CURRENT bond axis."""
+    for torsion, ang, m in zip(torsions, angles_deg, rot_masks):
+        coord = rotate_dihedral(coord, torsion, ang, m)
+    return coord
+
+
+def rotcorr_ladder_model(similar, N, best_angles=None):
+    """SURVEY Appendix A.4b — literal restatement of the grouping loop of
+    prune_conformers_rmsd_rot_corr (torsion_module.py:1076-1152) on a precomputed boolean matrix
+    similar[i, j] = (rot-corrected rmsd(i, j) < max_rmsd), i < j.
+
+    The reference mutates the second structure of every comparison in place (utils.py:412 via
+    torsion_module.py:1004-1008): its rotors are left at the angles that best matched the first
+    structure *in that structure's current, possibly already mutated, state*.  Because every
+    angle set is a full n-fold orbit, the state of rotor t of structure j after comparing (i, j) is
+        state[j][t] = (stateless_best_angle(i, j)[t] + state[i][t]) mod 360,
+    which this model tracks when best_angles (N, N, T degrees, from the ORIGINAL coordinates) is
+    given.  Returns (final_mask, state) — state is (N, T) degrees, all zero without best_angles."""
+    import networkx as nx
+    final_mask = np.ones(N, dtype=bool)
+    cache_set = set()
+    T = 0 if best_angles is None else best_angles.shape[2]
+    state = np.zeros((N, T))
+    for k in LADDER:
+        num_active_str = np.count_nonzero(final_mask)
+        if k == 1 or 5 * k < num_active_str:                                  # :1083
+            d = int(N // k)
+            for step in range(int(k)):
+                if step == k - 1:
+                    _l = len(range(d * step, num_active_str))                  # :1093-1094 (quirk)
+                else:
+                    _l = len(range(d * step, int(d * (step + 1))))
+                matches = set()
+                for i_rel in range(_l):
+                    for j_rel in range(i_rel + 1, _l):
+                        i_abs = i_rel + d * step
+                        j_abs = j_rel + d * step
+                        if (i_abs, j_abs) not in cache_set:                   # :1107
+                            if T:
+                                state[j_abs] = (best_angles[i_abs, j_abs] + state[i_abs]) % 360.0
+                            if similar[i_abs, j_abs]:                         # :1118
+                                matches.add((i_rel, j_rel))
+                                break
+                            cache_set.add((i_abs, j_abs))
+                g = nx.Graph(matches)                                         # node order = set order
+                groups = [tuple(g.subgraph(c).nodes) for c in nx.connected_components(g)]
+                for group in groups:                                          # :1141-1152
+                    for i in set(group) - {group[0]}:
+                        final_mask[i + d * step] = 0
+    return final_mask, state

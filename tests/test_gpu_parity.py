@@ -311,3 +311,70 @@ def test_clash_full_size_c2_and_trimolecular(gpu):
     flips = int((v1 != v2).sum())
     print("1M trimolecular poses: passes", int(v1.sum()), "verdict flips under rigid motion:", flips)
     assert flips <= 2        # only poses with a distance within rounding of thresh may flip
+
+
+# ------------------------------------------------------------------------------------------
+# rot_corr
+# ------------------------------------------------------------------------------------------
+_rc = json.load(open(os.path.join(GOLDEN, "rotcorr.json")))["fixtures"]
+
+
+def _rc_load(name):
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import rotor_molecules as rm
+    from tscode_b200.torsion_module import TorsionInfo
+    f = _rc[name]
+    g = np.load(os.path.join(GOLDEN, f"rotcorr_{name}.npz"))
+    build = rm.ensemble_neopentyl if name.startswith("neopentyl") else rm.ensemble_ditbu
+    S, atomnos = build(f["seed"], f["N"])
+    info = TorsionInfo([tuple(t) for t in f["torsions"]], [tuple(a) for a in f["angles"]],
+                       g["rot_masks"].astype(bool), g["node_lists"].astype(bool))
+    return f, g, S, atomnos, info
+
+
+@pytest.mark.parametrize("name", list(_rc))
+def test_rot_corr_vs_reference(gpu, name):
+    """Mask, returned (centred + mutated) structures and per-pair values against the live
+    reference (rmsd==1.4 replaced by the A.6 stand-in when the fixtures were made)."""
+    from tscode_b200.synth import mask_digest
+    from tscode_b200.torsion_module import RotCorrPruner, prune_conformers_rmsd_rot_corr, rotationally_corrected_rmsd
+    f, g, S, atomnos, info = _rc_load(name)
+    logs = []
+    out, mask = prune_conformers_rmsd_rot_corr(S.copy(), atomnos, None, max_rmsd=f["thr"], logfunction=logs.append,
+                                               torsion_info=info)
+    assert int(mask.sum()) == f["survivors"] and mask_digest(mask) == f["digest"]
+    assert np.array_equal(mask, g["mask"])
+    dev = np.abs(out - g["out"]).max()
+    print(name, "max |returned structures - reference| =", dev)
+    assert dev < 1e-9
+    assert any("fold" in l for l in logs)
+    # stateless pair values + the in-place mutation of the scalar entry point
+    Sc = np.array([s - s.mean(axis=0) for s in S])
+    pr = RotCorrPruner(Sc, atomnos, info, f["thr"], want_rmsd=True)
+    pr.similarity()
+    R = pr.rmsd.cpu().numpy()
+    worst = 0.0
+    for a, b, v, mut in zip(g["pair_i"], g["pair_j"], g["pair_rmsd"], g["pair_mutated"]):
+        if a < b:
+            worst = max(worst, abs(R[a, b] - v))
+    cb = Sc[g["pair_j"][0]].copy()
+    r = rotationally_corrected_rmsd(Sc[g["pair_i"][0]], cb, atomnos, None, None, None, torsion_info=info)
+    assert abs(r - g["pair_rmsd"][0]) < 1e-9 and np.abs(cb - g["pair_mutated"][0]).max() < 1e-9
+    print(name, "worst |rmsd - reference| over sampled pairs =", worst, "near-threshold pairs:", int(pr.near.item()))
+    assert worst < 1e-9
+
+
+def test_rot_corr_guard_and_no_rotors(gpu):
+    from tscode_b200.torsion_module import TorsionInfo, prune_conformers_rmsd_rot_corr
+    f, g, S, atomnos, info = _rc_load("neopentyl_s1")
+    big = np.concatenate([S] * 20)                       # 800 > 750: the reference returns all-True (:1056)
+    out, mask = prune_conformers_rmsd_rot_corr(big, atomnos, None, torsion_info=info)
+    assert mask.all() and np.allclose(out, big - big.mean(axis=1, keepdims=True))
+    empty = TorsionInfo([], [], np.zeros((0, len(atomnos)), bool), np.zeros((0, len(atomnos)), bool))
+    out, mask = prune_conformers_rmsd_rot_corr(S, atomnos, None, torsion_info=empty)
+    assert mask.all()
+    # guard lifted: beyond the reference's own limit, checked against the oracle's literal model instead
+    out2, mask2 = prune_conformers_rmsd_rot_corr(big, atomnos, None, torsion_info=info, max_structures=None)
+    assert mask2.sum() < 20

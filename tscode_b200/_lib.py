@@ -31,6 +31,9 @@ SIGNATURES = {
     "tsc_elim_commit": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tsc_embed_clash": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _f64, _f64, _i64, _vp, _vp, _vp]),
     "tsc_clash_structs": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _f64, _f64, _f64, _i64, _vp, _vp, _vp]),
+    "tsc_rotcorr_pairs": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f64,
+                                    _vp, _vp, _vp, _vp, _vp]),
+    "tsc_rotcorr_apply": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tsc_bench_fp64": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "tsc_embed_gather": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
 }

@@ -11,16 +11,20 @@
 // exactly those pairs the way the reference does (explicit rotation, RMSD and max deviation)
 // and clears the bits that fail.  Bits are final only after verification.
 //
-// Structure (one persistent CTA per SM, 8 warps, 255 registers per thread):
-//   thread 0       : also the producer — walks this CTA's tiles two slabs ahead of the math,
-//                    streaming (slab, block) chunks of the packed ensemble into a 4-stage
-//                    shared-memory ring with 1-D bulk TMA (cp.async.bulk -> UBLKCP), completion
-//                    on "full" mbarriers.  (A ninth warp would cap every thread at 168
-//                    registers: allocation is per 4-warp group.)
-//   warps 0..7     : consumers — each owns a 16 x 16 pair sub-tile (72 FP64 accumulators per
-//                    thread), waits on "full", issues the MMAs/FMAs from shared memory,
-//                    releases the stage on an "empty" mbarrier, and after the last slab runs
-//                    the screen and writes 16 result bits per row straight to HBM.
+// Structure (one persistent CTA per SM, 12 warps = 3 warpgroups, registers re-split with setmaxnreg):
+//   warp 8, lane 0 : producer (warpgroup 2 shrinks to 40 registers/thread) — walks this CTA's
+//                    tiles a full ring ahead of the math, streaming (slab, block) chunks of the
+//                    packed ensemble into a 4-stage shared-memory ring with 1-D bulk TMA
+//                    (cp.async.bulk -> UBLKCP), completion on "full" mbarriers; with the last
+//                    slab of a tile it also delivers the tile descriptor and the 32 + 64 squared
+//                    norms the epilogue needs, so consumers never touch global memory for input
+//   warps 0..7     : consumers (warpgroups 0-1 grow to 232 registers/thread; 72 FP64
+//                    accumulators each) — each owns a 16 x 16 pair sub-tile, waits on "full",
+//                    issues the MMAs/FMAs from shared memory, releases the stage on an "empty"
+//                    mbarrier, and after the last slab runs the screen and writes 16 result bits
+//                    per row straight to HBM.
+//   (round-1 first version had thread 0 double as producer two slabs ahead: ncu showed 4.9 % of
+//   warp samples in the full-barrier wait and 2.4 % on the epilogue's G loads, profiles/r01_*.)
 // No __syncthreads() after setup; HBM traffic is 1 bit per pair out, operands come from L2.
 //
 // Roofline: FP64 pipe (tensor or FMA).  Algorithmic work 18*M flop per pair.
@@ -30,11 +34,16 @@
 namespace tsc {
 
 constexpr int SIM_NSTAGE = 4;
-constexpr int SIM_STAGE_D = 3 * CHUNK_D;                // I chunk + 2 J chunks, doubles
-constexpr int SIM_STAGE_BYTES = SIM_STAGE_D * 8;        // 46080
+constexpr int SIM_DATA_D = 3 * CHUNK_D;                 // I chunk + 2 J chunks, doubles
+constexpr int SIM_DATA_BYTES = SIM_DATA_D * 8;          // 46080
+constexpr int SIM_G_D = CB + 2 * CB;                    // G of the 32 rows and 64 columns (last slab only)
+constexpr int SIM_G_BYTES = SIM_G_D * 8;                // 768
+constexpr int SIM_STAGE_D = SIM_DATA_D + SIM_G_D + 2;   // + int4 tile descriptor
+constexpr int SIM_STAGE_BYTES = SIM_STAGE_D * 8;        // 46864
 constexpr int SIM_CONSUMER_WARPS = 8;
-constexpr int SIM_THREADS = SIM_CONSUMER_WARPS * 32;
-constexpr int SIM_LOOKAHEAD = 2;                       // slabs in flight ahead of the consumers (< SIM_NSTAGE)
+constexpr int SIM_THREADS = (SIM_CONSUMER_WARPS + 4) * 32;   // + producer warpgroup
+constexpr int SIM_REGS_CONSUMER = 232;
+constexpr int SIM_REGS_PRODUCER = 40;
 constexpr size_t SIM_SMEM_BYTES = (size_t)SIM_NSTAGE * SIM_STAGE_BYTES + 2 * SIM_NSTAGE * sizeof(uint64_t);
 
 struct SimParams {
@@ -97,11 +106,12 @@ struct ConsumerDMMA {
         }
     }
     // i0/j0: global conformer index of the warp tile's first row / column
-    __device__ __forceinline__ void epilogue(int64_t i0, int64_t j0, int64_t row0, int lane, const SimParams& p) {
+    __device__ __forceinline__ void epilogue(int64_t i0, int64_t j0, int64_t row0, int lane, const SimParams& p,
+                                             const double* __restrict__ gI, const double* __restrict__ gJ) {
 #pragma unroll
         for (int u = 0; u < 2; u++) {
             const int64_t i = i0 + u * 8 + (lane >> 2);
-            const double Gi = p.G[i];
+            const double Gi = gI[u * 8 + (lane >> 2)];
             uint32_t bits = 0;
 #pragma unroll
             for (int v = 0; v < 2; v++)
@@ -112,7 +122,7 @@ struct ConsumerDMMA {
                     double S[9];
 #pragma unroll
                     for (int c = 0; c < 9; c++) S[c] = acc[u][v][c][e];
-                    bits |= screen_bit(S, Gi, p.G[j], i, j, p) << jc;
+                    bits |= screen_bit(S, Gi, gJ[jc], i, j, p) << jc;
                 }
             bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
             bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
@@ -163,18 +173,19 @@ struct ConsumerFMA {
                         }
         }
     }
-    __device__ __forceinline__ void epilogue(int64_t i0, int64_t j0, int64_t row0, int lane, const SimParams& p) {
+    __device__ __forceinline__ void epilogue(int64_t i0, int64_t j0, int64_t row0, int lane, const SimParams& p,
+                                             const double* __restrict__ gI, const double* __restrict__ gJ) {
         const int g = lane >> 3, h = lane & 7;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             const int64_t i = i0 + g + 4 * r;
-            const double Gi = p.G[i];
+            const double Gi = gI[g + 4 * r];
             uint32_t bits = 0;
 #pragma unroll
             for (int s = 0; s < 2; s++) {
                 const int jc = h + 8 * s;
                 const int64_t j = j0 + jc;
-                bits |= screen_bit(acc[r][s], Gi, p.G[j], i, j, p) << jc;
+                bits |= screen_bit(acc[r][s], Gi, gJ[jc], i, j, p) << jc;
             }
             bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
             bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
@@ -201,43 +212,45 @@ __global__ void __launch_bounds__(SIM_THREADS, 1) rmsd_sim_kernel(const SimParam
     }
     __syncthreads();
 
-    // ---- producer cursor (used by thread 0 only): runs SIM_LOOKAHEAD slabs ahead of the consumers
-    int64_t pt = blockIdx.x;       // tile the next load belongs to
-    int ps = 0;                    // slab within that tile
-    int pstage = 0;
-    uint32_t pphase = 0;
-    auto produce_one = [&]() {
-        if (pt >= p.n_tiles) return;
-        const int4 tl = p.tiles[pt];
-        mbar_wait(&empty_bar[pstage], pphase ^ 1u);
-        double* dst = stages + (size_t)pstage * SIM_STAGE_D;
-        const double* srcI = p.packed + ((int64_t)ps * p.nb_pad + tl.x) * CHUNK_D;
-        const double* srcJ = p.packed + ((int64_t)ps * p.nb_pad + 2 * (int64_t)tl.y) * CHUNK_D;
-        mbar_arrive_expect_tx(&full_bar[pstage], SIM_STAGE_BYTES);
-        bulk_g2s(dst, srcI, CHUNK_BYTES, &full_bar[pstage]);
-        bulk_g2s(dst + CHUNK_D, srcJ, 2 * CHUNK_BYTES, &full_bar[pstage]);
-        if (++pstage == SIM_NSTAGE) { pstage = 0; pphase ^= 1u; }
-        if (++ps == p.nslab) { ps = 0; pt += gridDim.x; }
-    };
-    if (threadIdx.x == 0) {
-#pragma unroll 1
-        for (int a = 0; a < SIM_LOOKAHEAD; a++) produce_one();
-    }
-
-    // ---- consumers (all 8 warps) ----
     int stage = 0;
     uint32_t phase = 0;
+    if (warp >= SIM_CONSUMER_WARPS) {
+        // ===== producer warpgroup =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SIM_REGS_PRODUCER));
+        if (warp == SIM_CONSUMER_WARPS && lane == 0) {
+            for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+                const int4 tl = p.tiles[t];
+                for (int s = 0; s < p.nslab; s++) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    double* dst = stages + (size_t)stage * SIM_STAGE_D;
+                    const double* srcI = p.packed + ((int64_t)s * p.nb_pad + tl.x) * CHUNK_D;
+                    const double* srcJ = p.packed + ((int64_t)s * p.nb_pad + 2 * (int64_t)tl.y) * CHUNK_D;
+                    const bool last = (s == p.nslab - 1);
+                    if (last) *reinterpret_cast<int4*>(dst + SIM_DATA_D + SIM_G_D) = tl;
+                    mbar_arrive_expect_tx(&full_bar[stage], SIM_DATA_BYTES + (last ? SIM_G_BYTES : 0));
+                    bulk_g2s(dst, srcI, CHUNK_BYTES, &full_bar[stage]);
+                    bulk_g2s(dst + CHUNK_D, srcJ, 2 * CHUNK_BYTES, &full_bar[stage]);
+                    if (last) {
+                        bulk_g2s(dst + SIM_DATA_D, p.G + (int64_t)tl.x * CB, CB * 8, &full_bar[stage]);
+                        bulk_g2s(dst + SIM_DATA_D + CB, p.G + (int64_t)tl.y * 2 * CB, 2 * CB * 8, &full_bar[stage]);
+                    }
+                    if (++stage == SIM_NSTAGE) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumer warpgroups =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SIM_REGS_CONSUMER));
     const int ihalf = warp & 1;            // rows 16*ihalf .. +15 of the 32-row I block
     const int jquart = warp >> 1;          // columns 16*jquart .. +15 of the 64-column J pair
     const int woffI = ihalf * 16 * KS;
     const int woffJ = CHUNK_D * (1 + (jquart >> 1)) + (jquart & 1) * 16 * KS;
     Consumer cons;
     for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-        const int4 tl = p.tiles[t];
         cons.zero();
-        for (int s = 0; s < p.nslab; s++) {
-            if (threadIdx.x == 0) produce_one();      // slab (current + LOOKAHEAD)
-            __syncwarp();
+        for (int s = 0; s < p.nslab - 1; s++) {
             mbar_wait(&full_bar[stage], phase);
             const double* st = stages + (size_t)stage * SIM_STAGE_D;
             cons.slab(st + woffI, st + woffJ, lane);
@@ -245,8 +258,17 @@ __global__ void __launch_bounds__(SIM_THREADS, 1) rmsd_sim_kernel(const SimParam
             if (lane == 0) mbar_arrive(&empty_bar[stage]);
             if (++stage == SIM_NSTAGE) { stage = 0; phase ^= 1u; }
         }
+        // last slab: its stage also carries G and the tile descriptor; release it after the epilogue
+        mbar_wait(&full_bar[stage], phase);
+        const double* st = stages + (size_t)stage * SIM_STAGE_D;
+        cons.slab(st + woffI, st + woffJ, lane);
+        const int4 tl = *reinterpret_cast<const int4*>(st + SIM_DATA_D + SIM_G_D);
         cons.epilogue((int64_t)tl.x * CB + ihalf * 16, (int64_t)tl.y * 2 * CB + jquart * 16,
-                      (int64_t)tl.z * CB + ihalf * 16, lane, p);
+                      (int64_t)tl.z * CB + ihalf * 16, lane, p, st + SIM_DATA_D + ihalf * 16,
+                      st + SIM_DATA_D + CB + jquart * 16);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == SIM_NSTAGE) { stage = 0; phase ^= 1u; }
     }
 }
 

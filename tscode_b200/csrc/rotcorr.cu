@@ -1,0 +1,265 @@
+// rotcorr.cu — rotor-corrected RMSD for prune_conformers_rmsd_rot_corr.
+//
+// Reference per pair (tscode/torsion_module.py:953-1011, rotationally_corrected_rmsd):
+//   for every "dummy" (locally symmetric) rotor t: try each angle of its n-fold set, rotating the
+//   rotor's moving atoms of the second structure about the i2->i3 bond (utils.py:389-414,
+//   rotation matrix from algebra.py:284-344), keep the angle with the smallest local Kabsch RMSD
+//   over the heavy atoms of the rotor's sub-graph (:982-999, strict <); then apply every best
+//   rotation in torsion order (:1004-1008) and return the heavy-atom Kabsch RMSD (:1011; the
+//   structures were centred on the all-atom centroid beforehand, :1023; kabsch_rmsd of rmsd==1.4
+//   is rotation-only).  Similarity is the single test rmsd < max_rmsd (:1118).
+//
+// Everything graph-derived (torsion quadruplets, angle sets, rotation masks, sub-graph node
+// lists) is pair-independent and arrives precomputed.  The evaluation here is STATELESS (always
+// from the centred input): the reference's in-place mutation is reproduced on the host by
+// tracking rotor states (tscode_b200/torsion_module.py), which needs the per-pair best-angle
+// codes this kernel can emit.
+//
+// One warp per pair, lanes over atoms, both structures staged in per-warp shared memory.
+// FP64-pipe bound (sum_t n_t + 1 eigen-solves per pair); reported as pairs/s.
+#include "tsc_common.cuh"
+#include "tsc_math.cuh"
+
+namespace tsc {
+
+constexpr int RC_WARPS = 8;
+constexpr int RC_MAX_T = 10;
+constexpr int RC_MAX_ANG = 6;
+
+struct RotCorrParams {
+    const double* Sc;            // (N, A, 3) centred
+    int64_t N;
+    int A;
+    const uint8_t* heavy;        // (A)
+    int T;
+    const int32_t* i2;           // (T)
+    const int32_t* i3;           // (T)
+    const int32_t* n_ang;        // (T)
+    const double* sin_half;      // (T, 6)
+    const double* cos_half;      // (T, 6)
+    const uint8_t* rot_mask;     // (T, A)
+    const uint8_t* node_mask;    // (T, A)
+    int64_t row_begin, row_end;
+    double max_rmsd;
+    uint32_t* sim_bits;          // (N, Wb)
+    int64_t Wb;
+    uint32_t* codes;             // (N, N) or null
+    double* rmsd_out;            // (N, N) or null
+    unsigned long long* near_count;
+};
+
+// algebra.py:325-344 + :284-323 — rotation about `axis` (not normalised) given sin/cos of half the angle
+__device__ __forceinline__ void rot_from_axis(double ax, double ay, double az, double sh, double ch, double R[9]) {
+    const double n = sqrt(ax * ax + ay * ay + az * az);
+    ax /= n; ay /= n; az /= n;
+    const double q1 = sh * ax, q2 = sh * ay, q3 = sh * az, q0 = ch;
+    R[0] = 2 * (q0 * q0 + q1 * q1) - 1; R[1] = 2 * (q1 * q2 - q0 * q3);     R[2] = 2 * (q1 * q3 + q0 * q2);
+    R[3] = 2 * (q1 * q2 + q0 * q3);     R[4] = 2 * (q0 * q0 + q2 * q2) - 1; R[5] = 2 * (q2 * q3 - q0 * q1);
+    R[6] = 2 * (q1 * q3 - q0 * q2);     R[7] = 2 * (q2 * q3 + q0 * q1);     R[8] = 2 * (q0 * q0 + q3 * q3) - 1;
+}
+
+__device__ __forceinline__ void rot_point(const double R[9], double cx, double cy, double cz, double& x, double& y,
+                                          double& z) {
+    const double dx = x - cx, dy = y - cy, dz = z - cz;
+    x = (R[0] * dx + R[1] * dy + R[2] * dz) + cx;
+    y = (R[3] * dx + R[4] * dy + R[5] * dz) + cy;
+    z = (R[6] * dx + R[7] * dy + R[8] * dz) + cz;
+}
+
+__global__ void __launch_bounds__(RC_WARPS * 32) rotcorr_pairs_kernel(const RotCorrParams p) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int A = p.A;
+    double* rx = smem + (size_t)warp * 6 * A;
+    double* ry = rx + A; double* rz = ry + A;
+    double* cx = rz + A; double* cy = cx + A; double* cz = cy + A;
+    const int64_t warp_g = (int64_t)blockIdx.x * RC_WARPS + warp;
+    const int64_t nwarps = (int64_t)gridDim.x * RC_WARPS;
+    const int64_t nrows = p.row_end - p.row_begin;
+    unsigned long long near = 0;
+    for (int64_t idx = warp_g; idx < nrows * p.N; idx += nwarps) {
+        const int64_t i = p.row_begin + idx / p.N, j = idx % p.N;
+        if (j <= i) continue;
+        const double* Pi = p.Sc + i * (int64_t)A * 3;
+        const double* Pj = p.Sc + j * (int64_t)A * 3;
+        __syncwarp();
+        for (int a = lane; a < A; a += 32) {
+            rx[a] = Pi[3 * a]; ry[a] = Pi[3 * a + 1]; rz[a] = Pi[3 * a + 2];
+            cx[a] = Pj[3 * a]; cy[a] = Pj[3 * a + 1]; cz[a] = Pj[3 * a + 2];
+        }
+        __syncwarp();
+        uint32_t code = 0;
+        int best_idx[RC_MAX_T];
+        // ---- search phase: every rotor on the unmodified second structure (:982-999) ----
+        for (int t = 0; t < p.T; t++) {
+            const int a2 = p.i2[t], a3 = p.i3[t];
+            const double ox = cx[a3], oy = cy[a3], oz = cz[a3];
+            const double ax = cx[a2] - ox, ay = cy[a2] - oy, az = cz[a2] - oz;
+            const uint8_t* rm = p.rot_mask + (size_t)t * A;
+            const uint8_t* nm = p.node_mask + (size_t)t * A;
+            double best = 1e10;
+            int bi = 0;
+            for (int k = 0; k < p.n_ang[t]; k++) {
+                double R[9];
+                rot_from_axis(ax, ay, az, p.sin_half[t * RC_MAX_ANG + k], p.cos_half[t * RC_MAX_ANG + k], R);
+                double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, G = 0.0, cnt = 0.0;
+                for (int a = lane; a < A; a += 32) {
+                    if (!nm[a]) continue;
+                    const double px = rx[a], py = ry[a], pz = rz[a];
+                    double qx = cx[a], qy = cy[a], qz = cz[a];
+                    if (rm[a]) rot_point(R, ox, oy, oz, qx, qy, qz);
+                    S[0] = fma(px, qx, S[0]); S[1] = fma(px, qy, S[1]); S[2] = fma(px, qz, S[2]);
+                    S[3] = fma(py, qx, S[3]); S[4] = fma(py, qy, S[4]); S[5] = fma(py, qz, S[5]);
+                    S[6] = fma(pz, qx, S[6]); S[7] = fma(pz, qy, S[7]); S[8] = fma(pz, qz, S[8]);
+                    G += px * px + py * py + pz * pz + qx * qx + qy * qy + qz * qz;
+                    cnt += 1.0;
+                }
+#pragma unroll
+                for (int c = 0; c < 9; c++) S[c] = warp_sum(S[c]);
+                G = warp_sum(G);
+                cnt = warp_sum(cnt);
+                double q[4];
+                const double lam = key_top_eigen(key_matrix(S), q, nullptr);
+                const double local = sqrt(fmax(G - 2.0 * lam, 0.0) / cnt);
+                if (local < best) { best = local; bi = k; }
+            }
+            best_idx[t] = bi;
+            code |= (uint32_t)bi << (3 * t);
+        }
+        // ---- apply phase: best rotations in torsion order, each about the CURRENT axis (:1004-1008) ----
+        for (int t = 0; t < p.T; t++) {
+            const int k = best_idx[t];
+            if (k == 0 && p.sin_half[t * RC_MAX_ANG] == 0.0) continue;      // angle 0: identity
+            const int a2 = p.i2[t], a3 = p.i3[t];
+            const double ox = cx[a3], oy = cy[a3], oz = cz[a3];
+            double R[9];
+            rot_from_axis(cx[a2] - ox, cy[a2] - oy, cz[a2] - oz, p.sin_half[t * RC_MAX_ANG + k],
+                          p.cos_half[t * RC_MAX_ANG + k], R);
+            __syncwarp();
+            const uint8_t* rm = p.rot_mask + (size_t)t * A;
+            for (int a = lane; a < A; a += 32)
+                if (rm[a]) {
+                    double x = cx[a], y = cy[a], z = cz[a];
+                    rot_point(R, ox, oy, oz, x, y, z);
+                    cx[a] = x; cy[a] = y; cz[a] = z;
+                }
+            __syncwarp();
+        }
+        // ---- global heavy-atom Kabsch RMSD, explicit rotation and differences (:1011) ----
+        double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, cnt = 0.0;
+        for (int a = lane; a < A; a += 32) {
+            if (!p.heavy[a]) continue;
+            const double px = rx[a], py = ry[a], pz = rz[a], qx = cx[a], qy = cy[a], qz = cz[a];
+            S[0] = fma(px, qx, S[0]); S[1] = fma(px, qy, S[1]); S[2] = fma(px, qz, S[2]);
+            S[3] = fma(py, qx, S[3]); S[4] = fma(py, qy, S[4]); S[5] = fma(py, qz, S[5]);
+            S[6] = fma(pz, qx, S[6]); S[7] = fma(pz, qy, S[7]); S[8] = fma(pz, qz, S[8]);
+            cnt += 1.0;
+        }
+#pragma unroll
+        for (int c = 0; c < 9; c++) S[c] = warp_sum(S[c]);
+        cnt = warp_sum(cnt);
+        double R[9];
+        kabsch_rot_from_cov(S, R, nullptr, nullptr);
+        double ss = 0.0;
+        for (int a = lane; a < A; a += 32) {
+            if (!p.heavy[a]) continue;
+            const double px = rx[a], py = ry[a], pz = rz[a];
+            const double dx = fma(R[0], px, fma(R[1], py, R[2] * pz)) - cx[a];
+            const double dy = fma(R[3], px, fma(R[4], py, R[5] * pz)) - cy[a];
+            const double dz = fma(R[6], px, fma(R[7], py, R[8] * pz)) - cz[a];
+            ss += fma(dx, dx, fma(dy, dy, dz * dz));
+        }
+        ss = warp_sum(ss);
+        const double rmsd = sqrt(ss / cnt);
+        if (lane == 0) {
+            if (rmsd < p.max_rmsd) atomicOr(&p.sim_bits[i * p.Wb + (j >> 5)], 1u << (j & 31));
+            if (p.codes) p.codes[i * p.N + j] = code;
+            if (p.rmsd_out) p.rmsd_out[i * p.N + j] = rmsd;
+            near += fabs(rmsd - p.max_rmsd) < 1e-6;
+        }
+    }
+    if (lane == 0 && near && p.near_count) atomicAdd(p.near_count, near);
+}
+
+// Returned structures: rotor t of structure idx[s] rotated by its accumulated state angle
+// (sin/cos of half the angle per (s, t)), in torsion order, each about the current axis.
+__global__ void __launch_bounds__(RC_WARPS * 32) rotcorr_apply_kernel(
+    const double* __restrict__ Sc, int64_t n, int A, const int64_t* __restrict__ idx, int T,
+    const int32_t* __restrict__ i2, const int32_t* __restrict__ i3, const double* __restrict__ sin_half,
+    const double* __restrict__ cos_half, const uint8_t* __restrict__ rot_mask, double* __restrict__ out) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* cx = smem + (size_t)warp * 3 * A;
+    double* cy = cx + A; double* cz = cy + A;
+    for (int64_t s = (int64_t)blockIdx.x * RC_WARPS + warp; s < n; s += (int64_t)gridDim.x * RC_WARPS) {
+        const double* P = Sc + idx[s] * (int64_t)A * 3;
+        __syncwarp();
+        for (int a = lane; a < A; a += 32) { cx[a] = P[3 * a]; cy[a] = P[3 * a + 1]; cz[a] = P[3 * a + 2]; }
+        __syncwarp();
+        for (int t = 0; t < T; t++) {
+            const double sh = sin_half[s * T + t], ch = cos_half[s * T + t];
+            if (sh == 0.0 && ch == 1.0) continue;
+            const int a2 = i2[t], a3 = i3[t];
+            const double ox = cx[a3], oy = cy[a3], oz = cz[a3];
+            double R[9];
+            rot_from_axis(cx[a2] - ox, cy[a2] - oy, cz[a2] - oz, sh, ch, R);
+            __syncwarp();
+            const uint8_t* rm = rot_mask + (size_t)t * A;
+            for (int a = lane; a < A; a += 32)
+                if (rm[a]) {
+                    double x = cx[a], y = cy[a], z = cz[a];
+                    rot_point(R, ox, oy, oz, x, y, z);
+                    cx[a] = x; cy[a] = y; cz[a] = z;
+                }
+            __syncwarp();
+        }
+        double* O = out + s * (int64_t)A * 3;
+        for (int a = lane; a < A; a += 32) { O[3 * a] = cx[a]; O[3 * a + 1] = cy[a]; O[3 * a + 2] = cz[a]; }
+    }
+}
+
+}  // namespace tsc
+
+extern "C" int tsc_rotcorr_pairs(const double* Sc, int64_t N, int32_t A, const uint8_t* heavy, int32_t T,
+                                 const int32_t* tor_i2, const int32_t* tor_i3, const int32_t* n_ang,
+                                 const double* sin_half, const double* cos_half, const uint8_t* rot_mask,
+                                 const uint8_t* node_mask, int64_t row_begin, int64_t row_end, double max_rmsd,
+                                 uint32_t* sim_bits, uint32_t* codes, double* rmsd_out, uint64_t* near_count,
+                                 void* stream) {
+    using namespace tsc;
+    if (N <= 1 || row_end <= row_begin) return 0;
+    if (T < 0 || T > RC_MAX_T) return (int)cudaErrorInvalidValue;
+    RotCorrParams p{Sc, N, A, heavy, T, tor_i2, tor_i3, n_ang, sin_half, cos_half, rot_mask, node_mask, row_begin,
+                    row_end, max_rmsd, sim_bits, (N + 31) / 32, codes, rmsd_out,
+                    reinterpret_cast<unsigned long long*>(near_count)};
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(sim_bits + row_begin * p.Wb, 0, (size_t)(row_end - row_begin) * p.Wb * 4, st);
+    if (e != cudaSuccess) return (int)e;
+    const size_t smem = (size_t)RC_WARPS * 6 * A * sizeof(double);
+    if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
+    e = cudaFuncSetAttribute(rotcorr_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int64_t work = (row_end - row_begin) * N;
+    int64_t blocks = (work + RC_WARPS - 1) / RC_WARPS;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    rotcorr_pairs_kernel<<<(unsigned)blocks, RC_WARPS * 32, smem, st>>>(p);
+    TSC_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int tsc_rotcorr_apply(const double* Sc, int64_t n, int32_t A, const int64_t* idx, int32_t T,
+                                 const int32_t* tor_i2, const int32_t* tor_i3, const double* sin_half,
+                                 const double* cos_half, const uint8_t* rot_mask, double* out, void* stream) {
+    using namespace tsc;
+    if (n <= 0) return 0;
+    const size_t smem = (size_t)RC_WARPS * 3 * A * sizeof(double);
+    if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(rotcorr_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int64_t blocks = (n + RC_WARPS - 1) / RC_WARPS;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    rotcorr_apply_kernel<<<(unsigned)blocks, RC_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        Sc, n, A, idx, T, tor_i2, tor_i3, sin_half, cos_half, rot_mask, out);
+    TSC_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,277 @@
+"""B200-native drop-in for the rotor-corrected RMSD pruning of tscode/torsion_module.py.
+
+    prune_conformers_rmsd_rot_corr(structures, atomnos, graph, max_rmsd=0.25, verbose=False,
+                                   logfunction=None) -> (structures_centred[mask], mask)      # :1013-1161
+    rotationally_corrected_rmsd(ref, coord, atomnos, torsions, graph, angles) -> float          # :953-1011
+
+Split of work:
+  * chemistry perception (which bonds are "dummy" rotors, their n-fold angle sets, rotation
+    masks, sub-graph node lists) is pair-independent host work and stays in Python.  It is
+    delegated to the reference's own helpers when `tscode` is importable (the drop-in scenario:
+    `perceive_torsions`), or supplied by the caller as a `TorsionInfo` (tests, benchmarks);
+  * the per-pair numerics — sum_t n_t local Kabsch RMSDs + rotations + one global Kabsch RMSD —
+    run on the GPU for all pairs at once, statelessly (rotcorr.cu);
+  * the grouping loop (:1076-1152) is replayed literally on the host on the resulting boolean
+    matrix, with Python `set` -> `nx.Graph` -> `connected_components` exactly as the reference
+    builds them, because which member of a cluster survives depends on that iteration order;
+  * the reference mutates compared structures in place and returns them mutated; the host replay
+    tracks every structure's rotor state ((best angle of the pair) + (state of the first
+    structure), mod 360 — exact because every angle set is a full n-fold orbit) and the returned
+    coordinates are produced from those states (tsc_rotcorr_apply).
+
+Reference guard kept: more than `max_structures` (750, :1056) structures or no dummy rotor ->
+centred structures and an all-True mask.  Pass max_structures=None to lift it (beyond what the
+reference itself would run; say so when quoting such a number).
+"""
+from __future__ import annotations
+
+import copy
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _host
+from ._lib import check, lib, ptr, require_cuda, stream_ptr
+
+MAX_T, MAX_ANG = 10, 6
+_SYMBOLS = ("X H He Li Be B C N O F Ne Na Mg Al Si P S Cl Ar K Ca Sc Ti V Cr Mn Fe Co Ni Cu Zn Ga Ge As Se Br Kr "
+            "Rb Sr Y Zr Nb Mo Tc Ru Rh Pd Ag Cd In Sn Sb Te I Xe").split()
+
+
+@dataclass
+class TorsionInfo:
+    """Pair-independent description of the dummy rotors of one molecule."""
+    torsions: list                      # T quadruplets (i1, i2, i3, i4), dummy side last (:1049)
+    angles: list                        # T tuples of degrees (:112-118)
+    rot_masks: np.ndarray               # (T, A) bool, _get_rotation_mask (:301-325)
+    node_masks: np.ndarray              # (T, A) bool, heavy atoms of the rotor's sub-graph (:964-977)
+    log: list = field(default_factory=list)
+
+    @property
+    def T(self):
+        return len(self.torsions)
+
+
+def perceive_torsions(ref_centred, atomnos, graph) -> TorsionInfo:
+    """Set-up block of prune_conformers_rmsd_rot_corr (:1026-1049) plus the per-torsion
+    quantities rotationally_corrected_rmsd recomputes for every pair (:964-977, :984).  Uses the
+    reference's perception helpers: requires the `tscode` package (drop-in scenario)."""
+    try:
+        import networkx as nx
+        from tscode.torsion_module import (_get_hydrogen_bonds, _get_rotation_mask, _get_torsions, _is_nondummy)
+        from tscode.utils import get_double_bonds_indices
+    except Exception as e:           # pragma: no cover - exercised only without the reference
+        raise RuntimeError("torsion perception is delegated to the reference's helpers "
+                           "(tscode.torsion_module); install TSCoDe or pass torsion_info=...") from e
+    atomnos = np.asarray(atomnos)
+    g = copy.deepcopy(graph)
+    for hb in _get_hydrogen_bonds(ref_centred, atomnos, g):
+        g.add_edge(*hb)
+    tors = _get_torsions(g, hydrogen_bonds=_get_hydrogen_bonds(ref_centred, atomnos, g),
+                         double_bonds=get_double_bonds_indices(ref_centred, atomnos), keepdummy=True)
+    tors = [t for t in tors if not (_is_nondummy(t.i2, t.i3, g) and _is_nondummy(t.i3, t.i2, g))]
+    tors = [t for t in tors if 1 not in [atomnos[i] for i in t.torsion]]
+    angles = [tuple(t.get_angles()) for t in tors]
+    quads = [tuple(t.torsion) if _is_nondummy(t.i2, t.i3, g) else tuple(reversed(t.torsion)) for t in tors]
+    A = len(atomnos)
+    rot, nodes = np.zeros((len(quads), A), bool), np.zeros((len(quads), A), bool)
+    for k, t in enumerate(quads):
+        for o in quads:
+            if o is not t:
+                g.remove_edge(o[1], o[2])
+        comp = [s for s in nx.connected_components(g) if t[1] in s][0]
+        for o in quads:
+            if o is not t:
+                g.add_edge(o[1], o[2])
+        nodes[k, [i for i in comp if atomnos[i] != 1]] = True
+        rot[k] = _get_rotation_mask(g, t)
+    return TorsionInfo([tuple(int(x) for x in q) for q in quads], angles, rot, nodes)
+
+
+class RotCorrPruner:
+    """All-pairs rotor-corrected RMSD on the GPU + literal host replay of the grouping loop."""
+
+    def __init__(self, structures_centred, atomnos, info: TorsionInfo, max_rmsd=0.25, *, want_codes=True,
+                 want_rmsd=False):
+        torch = require_cuda()
+        self.torch = torch
+        dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+        self.dev = dev
+        Sc = np.ascontiguousarray(structures_centred, dtype=np.float64)
+        self.N, self.A = Sc.shape[0], Sc.shape[1]
+        self.info, self.max_rmsd = info, float(max_rmsd)
+        T = info.T
+        if T > MAX_T or any(len(a) > MAX_ANG for a in info.angles):
+            raise ValueError(f"at most {MAX_T} rotors with {MAX_ANG} angles each are supported")
+        self.Sc = torch.from_numpy(Sc).to(dev)
+        atomnos = np.asarray(atomnos)
+        self.heavy = torch.from_numpy((atomnos != 1).astype(np.uint8)).to(dev)
+        self.i2 = torch.tensor([t[1] for t in info.torsions], dtype=torch.int32, device=dev)
+        self.i3 = torch.tensor([t[2] for t in info.torsions], dtype=torch.int32, device=dev)
+        self.n_ang = torch.tensor([len(a) for a in info.angles], dtype=torch.int32, device=dev)
+        ang = np.zeros((max(T, 1), MAX_ANG))
+        for k, a in enumerate(info.angles):
+            ang[k, :len(a)] = a
+        half = ang * np.pi / 180 / 2                                 # algebra.py:337-341
+        self.ang_table = ang
+        self.sin_half = torch.from_numpy(np.sin(half)).to(dev)
+        self.cos_half = torch.from_numpy(np.cos(half)).to(dev)
+        self.rot_mask = torch.from_numpy(np.ascontiguousarray(info.rot_masks, dtype=np.uint8)).to(dev) \
+            if T else torch.zeros((1, self.A), dtype=torch.uint8, device=dev)
+        self.node_mask = torch.from_numpy(np.ascontiguousarray(info.node_masks, dtype=np.uint8)).to(dev) \
+            if T else torch.zeros((1, self.A), dtype=torch.uint8, device=dev)
+        N = self.N
+        self.Wb = (N + 31) // 32
+        self.sim_bits = torch.zeros((max(N, 1), max(self.Wb, 1)), dtype=torch.int32, device=dev)
+        self.codes = torch.zeros((N, N), dtype=torch.int32, device=dev) if want_codes else None
+        self.rmsd = torch.zeros((N, N), dtype=torch.float64, device=dev) if want_rmsd else None
+        self.near = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def similarity(self, row_begin=0, row_end=None):
+        row_end = self.N if row_end is None else row_end
+        check(lib().tsc_rotcorr_pairs(ptr(self.Sc), self.N, self.A, ptr(self.heavy), self.info.T, ptr(self.i2),
+                                      ptr(self.i3), ptr(self.n_ang), ptr(self.sin_half), ptr(self.cos_half),
+                                      ptr(self.rot_mask), ptr(self.node_mask), row_begin, row_end, self.max_rmsd,
+                                      ptr(self.sim_bits), ptr(self.codes), ptr(self.rmsd), ptr(self.near),
+                                      stream_ptr()), "tsc_rotcorr_pairs")
+
+    def similar_matrix(self):
+        """(N, N) bool, upper triangle, on the host."""
+        bits = self.sim_bits.cpu().numpy().view(np.uint32)
+        return np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little")[:, : self.N].astype(bool)
+
+    def best_angles(self):
+        """(N, N, T) degrees decoded from the per-pair codes."""
+        codes = self.codes.cpu().numpy().view(np.uint32)
+        T = self.info.T
+        out = np.zeros((self.N, self.N, T))
+        for t in range(T):
+            out[:, :, t] = self.ang_table[t][(codes >> (3 * t)) & 7]
+        return out
+
+    def apply_states(self, idx, state_deg):
+        """Centred structures idx with rotor states applied -> numpy (n, A, 3)."""
+        torch = self.torch
+        idx = np.asarray(idx, dtype=np.int64)
+        n, T = idx.size, self.info.T
+        if n == 0:
+            return np.zeros((0, self.A, 3))
+        half = (np.asarray(state_deg, dtype=np.float64).reshape(n, T) if T else np.zeros((n, 1))) * np.pi / 180 / 2
+        out = torch.empty((n, self.A, 3), dtype=torch.float64, device=self.dev)
+        sh = torch.from_numpy(np.ascontiguousarray(np.sin(half))).to(self.dev)
+        ch = torch.from_numpy(np.ascontiguousarray(np.cos(half))).to(self.dev)
+        check(lib().tsc_rotcorr_apply(ptr(self.Sc), n, self.A, ptr(torch.from_numpy(idx).to(self.dev)), T,
+                                      ptr(self.i2), ptr(self.i3), ptr(sh), ptr(ch), ptr(self.rot_mask), ptr(out),
+                                      stream_ptr()), "tsc_rotcorr_apply")
+        return out.cpu().numpy()
+
+
+def ladder_replay(similar, N, best_angles=None, verbose=False):
+    """Literal replay of the grouping loop (torsion_module.py:1076-1152) on similar[i, j]
+    (i < j) with rotor-state tracking (see module docstring).  The inner pair loop is vectorised
+    per row — same visiting order, same cache contents, same `matches` set insertion order.
+    Returns (final_mask, state (N, T) degrees)."""
+    import networkx as nx
+    final_mask = np.ones(N, dtype=bool)
+    cached = np.zeros((N, N), dtype=bool)          # cache_set (:1054) as a dense matrix
+    T = 0 if best_angles is None else best_angles.shape[2]
+    state = np.zeros((N, T))
+    for k in _host.LADDER:
+        num_active = int(np.count_nonzero(final_mask))
+        if not (k == 1 or 5 * k < num_active):                                     # :1083
+            continue
+        if verbose:
+            print(f"Working on subgroups with k={k} ({num_active} candidates left) {' ' * 10}", end="\r")
+        d = int(N // k)
+        for step in range(int(k)):
+            if step == k - 1:
+                _l = len(range(d * step, num_active))                              # :1093-1094 (quirk kept)
+            else:
+                _l = len(range(d * step, int(d * (step + 1))))
+            if _l <= 1:
+                continue
+            base = d * step
+            matches = set()
+            for i_rel in range(_l):
+                i = base + i_rel
+                lo, hi = i + 1, base + _l
+                if lo >= hi:
+                    continue
+                fresh = ~cached[i, lo:hi]
+                hits = np.flatnonzero(fresh & similar[i, lo:hi])
+                stop = hits[0] if hits.size else hi - lo                            # first uncached similar pair
+                visited = np.flatnonzero(fresh[:stop + 1]) if hits.size else np.flatnonzero(fresh)
+                if visited.size == 0:
+                    continue
+                js = lo + visited
+                if T:                                                               # in-place mutation (:1004-1008)
+                    state[js] = (best_angles[i, js] + state[i]) % 360.0
+                if hits.size:
+                    cached[i, js[:-1]] = True                                       # :1123-1125
+                    matches.add((i_rel, int(js[-1] - base)))                        # :1119-1120
+                else:
+                    cached[i, js] = True
+            g = nx.Graph(matches)                                                  # :1136
+            groups = [tuple(g.subgraph(c).nodes) for c in nx.connected_components(g)]
+            for group in groups:                                                   # :1141-1152
+                for r in set(group) - {group[0]}:
+                    final_mask[r + base] = 0
+    return final_mask, state
+
+
+def prune_conformers_rmsd_rot_corr(structures, atomnos, graph, max_rmsd=0.25, verbose=False, logfunction=None,
+                                   *, torsion_info: TorsionInfo | None = None, max_structures=750):
+    """Drop-in for tscode.torsion_module.prune_conformers_rmsd_rot_corr (:1013-1161)."""
+    structures = np.array([s - s.mean(axis=0) for s in np.asarray(structures, dtype=np.float64)])     # :1023
+    atomnos = np.asarray(atomnos)
+    N = structures.shape[0]
+    final_mask = np.ones(N, dtype=bool)
+    if N == 0:
+        return structures, final_mask
+    info = torsion_info if torsion_info is not None else perceive_torsions(structures[0], atomnos, graph)
+    if info.T == 0 or (max_structures is not None and N > max_structures):                            # :1056-1060
+        return structures[final_mask], final_mask
+    if logfunction is not None:                                                                       # :1063-1074
+        logfunction('\n >> Dihedrals considered for subsymmetry corrections:')
+        for i, (torsion, angle) in enumerate(zip(info.torsions, info.angles)):
+            sym = ''.join(_SYMBOLS[atomnos[a]] if atomnos[a] < len(_SYMBOLS) else '?' for a in torsion)
+            logfunction(' {:2s} - {:21s} : {} : {}-fold'.format(str(i), str(list(torsion)), sym, len(angle)))
+        logfunction("\n")
+    pr = RotCorrPruner(structures, atomnos, info, max_rmsd)
+    pr.similarity()
+    mask, state = ladder_replay(pr.similar_matrix(), N, pr.best_angles(), verbose=verbose)
+    keep = np.flatnonzero(mask)
+    out = pr.apply_states(keep, state[keep])
+    return out, mask
+
+
+def rotationally_corrected_rmsd(ref, coord, atomnos, torsions, graph, angles, *, torsion_info=None):
+    """Drop-in for tscode.torsion_module.rotationally_corrected_rmsd (:953-1011), including its
+    side effect: `coord` is rotated IN PLACE to the best rotor angles.  `graph` is only needed
+    when torsion_info is not given (masks / node lists are then taken from the reference's
+    helpers)."""
+    ref = np.asarray(ref, dtype=np.float64)
+    atomnos = np.asarray(atomnos)
+    if torsion_info is None:
+        import networkx as nx
+        from tscode.torsion_module import _get_rotation_mask
+        A = len(atomnos)
+        rot, nodes = np.zeros((len(torsions), A), bool), np.zeros((len(torsions), A), bool)
+        for k, t in enumerate(torsions):
+            for o in torsions:
+                if o is not t:
+                    graph.remove_edge(o[1], o[2])
+            comp = [s for s in nx.connected_components(graph) if t[1] in s][0]
+            for o in torsions:
+                if o is not t:
+                    graph.add_edge(o[1], o[2])
+            nodes[k, [i for i in comp if atomnos[i] != 1]] = True
+            rot[k] = _get_rotation_mask(graph, t)
+        torsion_info = TorsionInfo([tuple(t) for t in torsions], [tuple(a) for a in angles], rot, nodes)
+    pr = RotCorrPruner(np.stack([ref, np.asarray(coord, dtype=np.float64)]), atomnos, torsion_info, 1e300,
+                       want_codes=True, want_rmsd=True)
+    pr.similarity()
+    r = float(pr.rmsd[0, 1].item())
+    best = pr.best_angles()[0, 1]
+    coord[...] = pr.apply_states([1], best[None])[0]
+    return r
