@@ -212,7 +212,8 @@ def main():
         for name, builder, seed, N, thr in (("neopentyl_s1", rm.ensemble_neopentyl, 1, 40, 0.25),
                                             ("neopentyl_s2", rm.ensemble_neopentyl, 2, 200, 0.25),
                                             ("ditbu_s0", rm.ensemble_ditbu, 0, 120, 0.25),
-                                            ("ditbu_s5", rm.ensemble_ditbu, 5, 300, 0.25)):
+                                            ("ditbu_s5", rm.ensemble_ditbu, 5, 300, 0.25),
+                                            ("tritbu63_s7", rm.ensemble_tritbu63, 7, 300, 0.25)):
             S, atomnos = builder(seed, N)
             graph = graphize(S[0], atomnos)
             Sc = np.array([s - s.mean(axis=0) for s in S])

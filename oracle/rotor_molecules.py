@@ -74,3 +74,39 @@ def ensemble_ditbu(seed, N):
                                     rng.choice([0, 40, 80, 120]) + rng.normal(0, 2.0))
         out.append(c + rng.normal(0, 0.02, size=c.shape))
     return np.array(out), atomnos
+
+
+def tri_tbu_tripropynylbenzene(phis):
+    """63 atoms: 1,3,5-tri-tert-butyl-2,4,6-tri(prop-1-ynyl)benzene.  Order: 6 ring C, then for ring
+    positions 0,2,4 a tBu [Cq, 3 Me C, 9 H], then for positions 1,3,5 a propynyl [C, C, C, 3 H]
+    pointing radially (uncrowded, so the bond perception sees the intended graph)."""
+    ring = np.array([[1.39 * np.cos(np.deg2rad(60 * k)), 1.39 * np.sin(np.deg2rad(60 * k)), 0.0] for k in range(6)])
+    atoms = [r for r in ring]
+    atomnos = [6] * 6
+    for pos, phi in zip((0, 2, 4), phis):
+        cq = ring[pos] * (1.39 + 1.53) / 1.39
+        me = tetra(cq, ring[pos], 1.54, 3, phi)
+        mh = []
+        for m in me:
+            mh += tetra(m, cq, 1.09, 3, 60.0)
+        atoms += [cq] + me + mh
+        atomnos += [6] * 4 + [1] * 9
+    for pos in (1, 3, 5):
+        u = ring[pos] / 1.39
+        c1 = u * (1.39 + 1.43); c2 = u * (1.39 + 1.43 + 1.20); c3 = u * (1.39 + 1.43 + 1.20 + 1.46)
+        atoms += [c1, c2, c3] + tetra(c3, c2, 1.09, 3, 15.0)
+        atomnos += [6, 6, 6, 1, 1, 1]
+    return np.array(atoms), np.array(atomnos)
+
+
+def ensemble_tritbu63(seed, N):
+    """BASELINE configs[3] shape (~60 atoms, three symmetric 3-fold rotors)."""
+    rng = np.random.default_rng(seed)
+    base = np.array([0.0, 40.0, 80.0])
+    out = []
+    atomnos = None
+    for _ in range(N):
+        phis = rng.choice(base, size=3) + rng.normal(0, 2.0, size=3) + rng.choice([0, 120, 240], size=3)
+        c, atomnos = tri_tbu_tripropynylbenzene(phis)
+        out.append(c + rng.normal(0, 0.02, size=c.shape))
+    return np.array(out), atomnos

@@ -327,7 +327,7 @@ def _rc_load(name):
     from tscode_b200.torsion_module import TorsionInfo
     f = _rc[name]
     g = np.load(os.path.join(GOLDEN, f"rotcorr_{name}.npz"))
-    build = rm.ensemble_neopentyl if name.startswith("neopentyl") else rm.ensemble_ditbu
+    build = {"neopentyl": rm.ensemble_neopentyl, "ditbu": rm.ensemble_ditbu, "tritbu63": rm.ensemble_tritbu63}[name.split("_")[0]]
     S, atomnos = build(f["seed"], f["N"])
     info = TorsionInfo([tuple(t) for t in f["torsions"]], [tuple(a) for a in f["angles"]],
                        g["rot_masks"].astype(bool), g["node_lists"].astype(bool))

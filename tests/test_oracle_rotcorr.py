@@ -15,7 +15,7 @@ import rotor_molecules as rm  # noqa: E402
 from tscode_b200.synth import mask_digest  # noqa: E402
 
 FX = json.load(open(os.path.join(GOLDEN, "rotcorr.json")))["fixtures"]
-BUILD = {"neopentyl": rm.ensemble_neopentyl, "ditbu": rm.ensemble_ditbu}
+BUILD = {"neopentyl": rm.ensemble_neopentyl, "ditbu": rm.ensemble_ditbu, "tritbu63": rm.ensemble_tritbu63}
 
 
 def load(name):

@@ -12,6 +12,7 @@ import sys
 
 from . import numba_functions as _nf
 from . import rmsd_pruning as _rp
+from . import torsion_module as _tm
 
 # defining module -> {name: replacement}
 _PATCHES = {
@@ -25,6 +26,9 @@ _PATCHES = {
     },
     "tscode.embeds": {
         "get_embed": _nf.get_embed,
+    },
+    "tscode.torsion_module": {
+        "prune_conformers_rmsd_rot_corr": _tm.prune_conformers_rmsd_rot_corr,
     },
 }
 # modules that import those names with `from ... import`

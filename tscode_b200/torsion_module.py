@@ -141,13 +141,16 @@ class RotCorrPruner:
         return np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little")[:, : self.N].astype(bool)
 
     def best_angles(self):
-        """(N, N, T) degrees decoded from the per-pair codes."""
+        """Per-pair best rotor angles as a lookup `f(i, js) -> (len(js), T) degrees`, decoded lazily
+        from the (N, N) uint32 codes (3 bits per rotor) so that large N stays at 4 bytes per pair."""
         codes = self.codes.cpu().numpy().view(np.uint32)
-        T = self.info.T
-        out = np.zeros((self.N, self.N, T))
-        for t in range(T):
-            out[:, :, t] = self.ang_table[t][(codes >> (3 * t)) & 7]
-        return out
+        T, table = self.info.T, self.ang_table
+
+        def lookup(i, js):
+            c = codes[i, js]
+            return np.stack([table[t][(c >> (3 * t)) & 7] for t in range(T)], axis=-1)
+        lookup.T = T
+        return lookup
 
     def apply_states(self, idx, state_deg):
         """Centred structures idx with rotor states applied -> numpy (n, A, 3)."""
@@ -174,7 +177,12 @@ def ladder_replay(similar, N, best_angles=None, verbose=False):
     import networkx as nx
     final_mask = np.ones(N, dtype=bool)
     cached = np.zeros((N, N), dtype=bool)          # cache_set (:1054) as a dense matrix
-    T = 0 if best_angles is None else best_angles.shape[2]
+    if best_angles is None:
+        T, lookup = 0, None
+    elif callable(best_angles):
+        T, lookup = best_angles.T, best_angles
+    else:
+        T, lookup = best_angles.shape[2], (lambda i, js: best_angles[i, js])
     state = np.zeros((N, T))
     for k in _host.LADDER:
         num_active = int(np.count_nonzero(final_mask))
@@ -205,7 +213,7 @@ def ladder_replay(similar, N, best_angles=None, verbose=False):
                     continue
                 js = lo + visited
                 if T:                                                               # in-place mutation (:1004-1008)
-                    state[js] = (best_angles[i, js] + state[i]) % 360.0
+                    state[js] = (lookup(i, js) + state[i]) % 360.0
                 if hits.size:
                     cached[i, js[:-1]] = True                                       # :1123-1125
                     matches.add((i_rel, int(js[-1] - base)))                        # :1119-1120
@@ -272,6 +280,6 @@ def rotationally_corrected_rmsd(ref, coord, atomnos, torsions, graph, angles, *,
                        want_codes=True, want_rmsd=True)
     pr.similarity()
     r = float(pr.rmsd[0, 1].item())
-    best = pr.best_angles()[0, 1]
-    coord[...] = pr.apply_states([1], best[None])[0]
+    best = pr.best_angles()(0, np.array([1]))
+    coord[...] = pr.apply_states([1], best)[0]
     return r
