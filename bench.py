@@ -326,12 +326,20 @@ def run_b200(args):
     mp, mp_src = measured_peaks()
     flops = 18.0 * M * pairs / world
     achieved = flops / (screen_ms * 1e-3) / 1e12
-    peak = max(peaks["dmma"], peaks["dfma"])
-    roofline = {"bound": "tensor", "kernel": f"rmsd_sim_kernel<{'ConsumerDMMA' if args.variant == 'dmma' else 'ConsumerFMA'}>",
+    if args.variant == "tf32":
+        peak = mp["bf16_tflops"] / 2.0
+        kname = "rmsd_tf32_kernel"
+        psrc = (f"TF32 dense = half of the {mp_src} cuBLAS bf16 burst figure in MEASURED_PEAKS.json "
+                f"({mp['bf16_tflops']} TFLOP/s); the kernel is epilogue- (FP64 screen) not MMA-bound, see DESIGN.md")
+    else:
+        peak = max(peaks["dmma"], peaks["dfma"])
+        kname = f"rmsd_sim_kernel<{'ConsumerDMMA' if args.variant == 'dmma' else 'ConsumerFMA'}>"
+        psrc = ("self-measured FP64 ceiling on this GPU in this run (tsc_bench_fp64: register-resident "
+                f"DMMA.8x8x4 {peaks['dmma']} / DFMA {peaks['dfma']} / both {peaks['mixed']} TFLOP/s); "
+                f"MEASURED_PEAKS.json ({mp_src}) has no FP64 entry")
+    roofline = {"bound": "tensor", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": "self-measured FP64 ceiling on this GPU in this run (tsc_bench_fp64: register-resident "
-                               f"DMMA.8x8x4 {peaks['dmma']} / DFMA {peaks['dfma']} / both {peaks['mixed']} TFLOP/s); "
-                               f"MEASURED_PEAKS.json ({mp_src}) has no FP64 entry",
+                "peak_source": psrc,
                 "algorithmic_flop_per_pair": 18 * M, "kernel_ms": screen_ms,
                 "kernel_share_of_step": screen_ms / step_ms}
 
@@ -396,7 +404,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--variant", default="dmma", choices=["dmma", "fma"])
+    ap.add_argument("--variant", default="dmma", choices=["dmma", "fma", "tf32"])
     ap.add_argument("--n-conformers", type=int, default=0, help="override N (testing only; invalid as a bench value)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--lazy-n", type=int, default=10000)

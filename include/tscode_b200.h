@@ -57,6 +57,24 @@ int tsc_rmsd_sim_tiles(const double* packed, const double* G, int64_t N, int32_t
                        const int32_t* tiles, int64_t n_tiles, double thr, uint32_t* sim_bits,
                        int32_t variant, int32_t grid_ctas, void* stream);
 
+/* Variant 2 of the screen: tcgen05 (kind::tf32, accumulators in TMEM) pre-screen with a rigorous
+ * error bound folded into the threshold; same sim_bits contract as tsc_rmsd_sim_tiles (a superset of
+ * the similar pairs is set; tsc_rmsd_verify makes the bits exact).
+ *   tsc_pack_tf32 writes the TF32-rounded operand images PA (tsc_tf32_pa_floats floats: panels of
+ *   128 conformers, [panel][xyz][M/4][128][4]) and PB (tsc_tf32_pb_floats floats: tiles of 16
+ *   conformers, [tile][M/4][xyz*16][4]) plus exact G and sqrt(G) (ceil(N/128)*128 doubles each).
+ *   items (n_items, 4) int32: {panel, first j tile, j tile count, local row block (32-row units) of
+ *   the panel inside sim_bits}; for an owned panel p list j tiles from 8p to ceil(N/128)*8 - 1.
+ *   Returns cudaErrorInvalidValue if M is too large for the stationary-panel layout (M > 120):
+ *   use variant 0 then. */
+int64_t tsc_tf32_pa_floats(int64_t N, int32_t M);
+int64_t tsc_tf32_pb_floats(int64_t N, int32_t M);
+int tsc_pack_tf32(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M, float* PA,
+                  float* PB, double* G, double* sG, void* stream);
+int tsc_rmsd_sim_tf32(const float* PA, const float* PB, const double* G, const double* sG, int64_t N,
+                      int32_t M, const int32_t* items, int32_t n_items, double thr, uint32_t* sim_bits,
+                      int32_t grid_ctas, void* stream);
+
 /* Exact re-evaluation of every set bit, the way rmsd_and_max_numba does it (rmsd_pruning.py:6-41);
  * afterwards bit (i,j) == (rmsd < thr and maxdev < 2*thr)  (:75, :95).
  *   row_blocks (n_rb) int32: global block index of each local row block.
@@ -124,6 +142,20 @@ int tsc_rotcorr_pairs(const double* Sc, int64_t N, int32_t A, const uint8_t* hea
                       const uint8_t* node_mask, int64_t row_begin, int64_t row_end, double max_rmsd,
                       uint32_t* sim_bits, uint32_t* codes, double* rmsd_out, uint64_t* near_count,
                       void* stream);
+/* Stateful mode — exact emulation of the reference's in-place mutation (utils.py:412 through
+ * torsion_module.py:984-1008), one row of the grouping loop (:1101-1125) at a time:
+ *   tsc_rotcorr_row evaluates (i, js[k]) for k < n from the CURRENT structures cur (N, A, 3) and stages
+ *   the rotor-corrected copy of js[k] in staged (n, A, 3) together with rmsd (n) and codes (n);
+ *   tsc_rotcorr_commit writes the first n_accept staged copies back into cur (the structures the
+ *   reference visited before its `break`).  Rotor descriptors as in tsc_rotcorr_pairs. */
+int tsc_rotcorr_row(const double* cur, int64_t N, int32_t A, const uint8_t* heavy, int32_t T,
+                    const int32_t* tor_i2, const int32_t* tor_i3, const int32_t* n_ang,
+                    const double* sin_half, const double* cos_half, const uint8_t* rot_mask,
+                    const uint8_t* node_mask, int64_t i, const int32_t* js, int32_t n, double* rmsd,
+                    uint32_t* codes, double* staged, void* stream);
+int tsc_rotcorr_commit(double* cur, const double* staged, const int32_t* js, int32_t n_accept, int32_t A,
+                       void* stream);
+
 /* Structures idx (n) int64 with rotor t turned by its accumulated angle (sin_half/cos_half (n, T)),
  * in torsion order about the current axis: what the reference's in-place mutation leaves behind
  * in the structures it returns (torsion_module.py:1004-1008, :1161).  out (n, A, 3). */

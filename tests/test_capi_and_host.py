@@ -82,12 +82,25 @@ def test_tiles_cover_upper_triangle(N, world):
     for ib in range(nb):
         assert covered[ib, ib:].all()            # every word >= ib of every row block is written
     assert total == sum(nbp // 2 - ib // 2 for ib in range(nb))
+    # tcgen05 work items: every 16-column tile right of a panel's first row, exactly once
+    njt = ((N + 127) // 128) * 8
+    seen = set()
+    for rank in range(world):
+        rb = _host.owned_row_blocks(N, rank, world)
+        for p, j0, cnt, lb in _host.build_tf32_items(N, rb):
+            assert rb[lb] == 4 * p and cnt >= 1
+            for jt in range(j0, j0 + cnt):
+                assert (p, jt) not in seen
+                seen.add((p, jt))
+    assert seen == {(p, jt) for p in range((N + 127) // 128) for jt in range(8 * p, njt)}
 
 
 def test_row_sharding_is_balanced():
     N = 50000
     loads = [len(_host.build_tiles(N, _host.owned_row_blocks(N, r, 8))) for r in range(8)]
-    assert max(loads) / min(loads) < 1.01
+    assert max(loads) / min(loads) < 1.005
+    items = [_host.build_tf32_items(N, _host.owned_row_blocks(N, r, 8))[:, 2].sum() for r in range(8)]
+    assert max(items) / min(items) < 1.005
 
 
 def test_ladder_schedule_matches_reference_rule():

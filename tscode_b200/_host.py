@@ -31,10 +31,40 @@ def packed_doubles(N: int, M: int) -> int:
     return num_slabs(M) * num_blocks_padded(N) * 3 * CB * KS
 
 
+PANEL_BLOCKS = 4      # 128-row panels (the tcgen05 variant's UMMA M) = 4 row blocks of 32
+
+
 def owned_row_blocks(N: int, rank: int = 0, world: int = 1) -> np.ndarray:
-    """Block-cyclic row sharding: row block ib has ~(nb - ib) column blocks of
-    work, so contiguous ranges would be badly imbalanced; cyclic assignment balances to 1/nb."""
-    return np.arange(rank, num_blocks(N), world, dtype=np.int32)
+    """Row sharding: row block ib has ~(nb - ib) column blocks of work, so contiguous
+    ranges would be badly imbalanced.  128-row panels are dealt to the ranks in snake order
+    (0..w-1, w-1..0, ...), which cancels the linear decrease of work per panel (< 0.5 % imbalance)."""
+    ib = np.arange(num_blocks(N), dtype=np.int32)
+    panel = ib // PANEL_BLOCKS
+    grp, pos = panel // world, panel % world
+    owner = np.where(grp % 2 == 0, pos, world - 1 - pos)
+    return ib[owner == rank]
+
+
+def build_tf32_items(N: int, row_blocks: np.ndarray, chunk: int = 128) -> np.ndarray:
+    """Work items of the tcgen05 pre-screen: (n_items, 4) int32 rows {panel, first j tile, j tile
+    count, local row block of the panel}.  Panel p (128 rows) needs the 16-column j tiles from 8p
+    up to the padded end; they are cut into chunks so that items are of similar size."""
+    rb = np.asarray(row_blocks, dtype=np.int64)
+    njt = ((N + 127) // 128) * 8
+    items = []
+    for lb, ib in enumerate(rb):
+        if ib % PANEL_BLOCKS:
+            continue
+        p = int(ib // PANEL_BLOCKS)
+        for j0 in range(8 * p, njt, chunk):
+            items.append((p, j0, min(chunk, njt - j0), lb))
+    # longest items first would not matter (all ~chunk); interleave panels so that concurrently
+    # running CTAs share B tiles in L2
+    return np.asarray(items, dtype=np.int32).reshape(-1, 4)
+
+
+def tf32_rows_padded(N: int) -> int:
+    return ((N + 127) // 128) * 128
 
 
 def build_tiles(N: int, row_blocks: np.ndarray) -> np.ndarray:

@@ -24,6 +24,10 @@ SIGNATURES = {
     "tsc_device_sm_count": (_i32, []),
     "tsc_pack": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
     "tsc_rmsd_sim_tiles": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i64, _f64, _vp, _i32, _i32, _vp]),
+    "tsc_tf32_pa_floats": (_i64, [_i64, _i32]),
+    "tsc_tf32_pb_floats": (_i64, [_i64, _i32]),
+    "tsc_pack_tf32": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "tsc_rmsd_sim_tf32": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _i32, _vp]),
     "tsc_rmsd_verify": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp]),
     "tsc_rmsd_pairs": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "tsc_elim_cachebits": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
@@ -33,6 +37,9 @@ SIGNATURES = {
     "tsc_clash_structs": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _f64, _f64, _f64, _i64, _vp, _vp, _vp]),
     "tsc_rotcorr_pairs": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f64,
                                     _vp, _vp, _vp, _vp, _vp]),
+    "tsc_rotcorr_row": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32,
+                                  _vp, _vp, _vp, _vp]),
+    "tsc_rotcorr_commit": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "tsc_rotcorr_apply": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tsc_bench_fp64": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "tsc_embed_gather": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),

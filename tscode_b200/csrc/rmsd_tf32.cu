@@ -1,0 +1,323 @@
+// rmsd_tf32.cu — tcgen05 / TMEM pre-screen of the all-pairs Kabsch similarity (variant 2).
+//
+// Idea: almost every pair of a conformer ensemble is FAR from the RMSD threshold, and a pair can
+// be *proved* dissimilar from an approximate cross-covariance as long as the approximation error
+// is bounded.  So the 3x3 covariances are first computed on the 5th-generation tensor cores in
+// TF32 (operands pre-rounded to TF32 by pack_tf32, FP32 accumulation in TMEM), ~25x the FP64
+// rate, and the screen of rmsd_sim.cu (Budan-Fourier sign test on the key-matrix quartic,
+// tsc_math.cuh) is run in FP64 on the approximate S with the threshold eigenvalue lowered by a
+// rigorous bound on the approximation error:
+//     |S~_ab - S_ab| <= eps * sum_m |p_ma q_mb| <= eps * sqrt(G_i^a G_j^b)        (Cauchy-Schwarz)
+//     => ||S~ - S||_F <= eps * sqrt(G_i G_j),   lambda_max(S) <= lambda_max(S~) + sqrt(3) ||S~ - S||_F
+// with eps = 1.05e-3 covering two TF32 roundings (2 * 2^-11), the FP64->FP32 conversion and a
+// generous allowance (80 * 2^-22 per term) for the tensor core's FP32 accumulation.  Pairs that
+// cannot be excluded get their bit set, exactly like the FP64 variants, and rmsd_verify.cu
+// re-evaluates them exactly in FP64 — so the final bits are identical; only the number of
+// candidates differs (pairs within ~0.1 A above the threshold become candidates too).
+//
+// GEMM shape.  For a panel of 128 conformers i and a tile of 16 conformers j, three MMAs per
+// 8-atom K block compute  D_a[i, (b, j)] = sum_m A_a[i, m] * B[(b, j), m]   (a, b in {x,y,z}):
+// M = 128 (TMEM lanes = rows i), N = 48, K = 8, kind::tf32.  With the three D_a side by side in
+// TMEM, thread i of the epilogue reads all nine entries of pair (i, j) from its own lane.
+//
+// Roles (one persistent CTA per SM, 10 warps):
+//   warp 0 lane 0 : producer — bulk-TMA (cp.async.bulk) of the A panel (stationary, 1536*Mp B)
+//                   and of a ring of B tiles (192*Mp B each), operands laid out in HBM by pack_tf32
+//                   in the canonical no-swizzle K-major core-matrix order, so no tensor map is needed
+//   warp 1        : TMEM allocation; lane 0 issues tcgen05.mma and tcgen05.commit
+//   warps 2..9    : epilogue — two groups of 4 warps alternate over tiles: tcgen05.ld the 16 x 9
+//                   accumulators of their row, release the TMEM buffer, run the FP64 screen,
+//                   store 16 bits per row
+// Pipelines: A full/empty, B ring full/empty, 3 TMEM accumulator buffers full/empty.
+#include "tsc_common.cuh"
+#include "tsc_math.cuh"
+
+namespace tsc {
+
+constexpr int TF_ROWS = 128;                   // conformers per A panel  (UMMA M)
+constexpr int TF_J = 16;                       // conformers per B tile
+constexpr int TF_N = 3 * TF_J;                 // UMMA N = 48
+constexpr int TF_ACC_COLS = 3 * TF_N;          // 144 TMEM columns per accumulator buffer
+constexpr int TF_NACC = 3;                     // accumulator buffers (432 of 512 columns)
+constexpr int TF_TMEM_COLS = 512;
+constexpr int TF_MAX_BSTAGES = 6;
+constexpr int TF_THREADS = 320;
+constexpr double TF_EPS = 1.05e-3;             // see header
+constexpr int TF_CHUNK_TILES = 128;            // j tiles per work item
+
+struct TfParams {
+    const float* PA;          // [panel][a][kc][128][4]
+    const float* PB;          // [jtile][kc][48][4]
+    const double* G;          // (>= njt*16) squared norms, exact FP64
+    const double* sG;         // sqrt(G)
+    const int4* items;        // (panel, jt_begin, jt_count, local_row_block_of_panel)
+    int n_items;
+    int64_t N;
+    int Mp;                   // atoms padded to a multiple of 8
+    int nb_stages;
+    double e_thr;             // M thr^2 (1 + 1e-6)
+    uint16_t* sim_bits16;
+    int64_t W;                // words per sim row
+};
+
+// pack: FP64 AoS -> TF32-rounded FP32 operand images + exact G, sqrt(G)
+__global__ void __launch_bounds__(256) pack_tf32_kernel(const double* __restrict__ S, int64_t N, int A,
+                                                        const int32_t* __restrict__ heavy_idx, int M, int Mp,
+                                                        int64_t n_rows_pad, float* __restrict__ PA,
+                                                        float* __restrict__ PB, double* __restrict__ G,
+                                                        double* __restrict__ sG) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * 8 + warp;          // one warp per conformer (incl. padding rows)
+    if (i >= n_rows_pad) return;
+    const bool live = i < N;
+    const double* src = S + (live ? i : 0) * (int64_t)A * 3;
+    const int nkc = Mp / 4;
+    const int64_t panel = i / TF_ROWS, r = i % TF_ROWS;
+    const int64_t jt = i / TF_J, jj = i % TF_J;
+    double g = 0.0;
+    for (int m = lane; m < Mp; m += 32) {
+        double x = 0.0, y = 0.0, z = 0.0;
+        if (live && m < M) {
+            const double* a = src + (int64_t)heavy_idx[m] * 3;
+            x = a[0]; y = a[1]; z = a[2];
+            g = fma(x, x, fma(y, y, fma(z, z, g)));
+        }
+        const float fx = to_tf32((float)x), fy = to_tf32((float)y), fz = to_tf32((float)z);
+        const int kc = m >> 2, e = m & 3;
+        float* pa = PA + (((panel * 3) * nkc + kc) * TF_ROWS + r) * 4 + e;
+        pa[0] = fx;
+        pa[(int64_t)nkc * TF_ROWS * 4] = fy;
+        pa[(int64_t)2 * nkc * TF_ROWS * 4] = fz;
+        float* pb = PB + ((jt * nkc + kc) * TF_N + jj) * 4 + e;
+        pb[0] = fx;
+        pb[TF_J * 4] = fy;
+        pb[2 * TF_J * 4] = fz;
+    }
+    g = warp_sum(g);
+    if (lane == 0) { G[i] = g; sG[i] = sqrt(g); }
+}
+
+__device__ __forceinline__ void tmem_ld_x8_raw(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+// tcgen05.wait::ld carrying 24 registers as in/out operands so that no use can be hoisted above it
+__device__ __forceinline__ void tmem_wait_bind24(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                   "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),
+                   "+r"(r[22]), "+r"(r[23])::"memory");
+}
+
+__global__ void __launch_bounds__(TF_THREADS, 1) rmsd_tf32_kernel(const TfParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int nkc = p.Mp / 4;
+    const uint32_t a_bytes = 3u * nkc * TF_ROWS * 16u;        // 1536 * Mp
+    const uint32_t b_bytes = (uint32_t)nkc * TF_N * 16u;      // 192 * Mp
+    float* smA = reinterpret_cast<float*>(smem_raw);
+    unsigned char* smB = smem_raw + a_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + a_bytes + (size_t)p.nb_stages * b_bytes);
+    uint64_t* a_full = bars;                   // 1
+    uint64_t* a_empty = bars + 1;              // 1
+    uint64_t* b_full = bars + 2;               // nb_stages
+    uint64_t* b_empty = b_full + TF_MAX_BSTAGES;
+    uint64_t* t_full = b_empty + TF_MAX_BSTAGES;      // TF_NACC
+    uint64_t* t_empty = t_full + TF_NACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + TF_NACC);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        for (int s = 0; s < p.nb_stages; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int t = 0; t < TF_NACC; t++) { mbar_init(&t_full[t], 1); mbar_init(&t_empty[t], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TF_TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== producer =====================
+        if (lane == 0) {
+            int bs = 0; uint32_t bph = 0, aph = 0;
+            for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+                const int4 w = p.items[it];
+                mbar_wait(a_empty, aph ^ 1u);
+                mbar_arrive_expect_tx(a_full, a_bytes);
+                {   // the panel image is contiguous; copy it in <= 32 KB pieces
+                    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.PA) + (size_t)w.x * a_bytes;
+                    for (uint32_t off = 0; off < a_bytes; off += 32768u) {
+                        const uint32_t n = (a_bytes - off < 32768u) ? (a_bytes - off) : 32768u;
+                        bulk_g2s(reinterpret_cast<unsigned char*>(smA) + off, src + off, n, a_full);
+                    }
+                }
+                aph ^= 1u;
+                for (int t = 0; t < w.z; t++) {
+                    mbar_wait(&b_empty[bs], bph ^ 1u);
+                    mbar_arrive_expect_tx(&b_full[bs], b_bytes);
+                    bulk_g2s(smB + (size_t)bs * b_bytes,
+                             reinterpret_cast<const unsigned char*>(p.PB) + (size_t)(w.y + t) * b_bytes, b_bytes,
+                             &b_full[bs]);
+                    if (++bs == p.nb_stages) { bs = 0; bph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(TF_ROWS, TF_N);
+            const uint32_t a_addr = smem_u32(smA);
+            const uint32_t a_lbo = TF_ROWS * 16u, b_lbo = TF_N * 16u;      // next 16-byte K chunk
+            const uint32_t a_comp = (uint32_t)nkc * TF_ROWS * 16u;         // next component image
+            int bs = 0, acc = 0; uint32_t bph = 0, aph = 0, tph = 0;
+            for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+                const int4 w = p.items[it];
+                mbar_wait(a_full, aph);
+                aph ^= 1u;
+                for (int t = 0; t < w.z; t++) {
+                    mbar_wait(&b_full[bs], bph);
+                    mbar_wait(&t_empty[acc], tph ^ 1u);
+                    tcgen05_fence_after();
+                    const uint32_t b_addr = smem_u32(smB + (size_t)bs * b_bytes);
+                    const uint32_t d0 = tmem_base + (uint32_t)acc * TF_ACC_COLS;
+                    for (int kb = 0; kb < p.Mp / 8; kb++) {
+                        const uint64_t bd = umma_desc_kmajor(b_addr + (uint32_t)kb * 2u * b_lbo, b_lbo, 128u);
+#pragma unroll
+                        for (int a = 0; a < 3; a++) {
+                            const uint64_t ad =
+                                umma_desc_kmajor(a_addr + (uint32_t)a * a_comp + (uint32_t)kb * 2u * a_lbo, a_lbo, 128u);
+                            umma_tf32_ss(d0 + (uint32_t)a * TF_N, ad, bd, idesc, kb > 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&b_empty[bs]);        // smem stage reusable once these MMAs retire
+                    umma_commit(&t_full[acc]);        // accumulators ready for the epilogue
+                    if (++bs == p.nb_stages) { bs = 0; bph ^= 1u; }
+                    if (++acc == TF_NACC) { acc = 0; tph ^= 1u; }
+                }
+                umma_commit(a_empty);                 // A panel reusable once every MMA of the item retired
+            }
+        }
+    } else {
+        // ===================== epilogue (8 warps, two groups alternating over tiles) =====================
+        const int ew = warp - 2;                      // 0..7
+        const int grp = ew >> 2;                      // tiles with (tile index & 1) == grp
+        const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
+        const int row_in_panel = quad * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        int acc = 0; uint32_t tph = 0;
+        int64_t tile_seq = 0;                         // running tile counter of this CTA
+        for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+            const int4 w = p.items[it];
+            const int64_t i = (int64_t)w.x * TF_ROWS + row_in_panel;
+            const double Gi = p.G[i], sGi = p.sG[i];
+            uint16_t* out_row = p.sim_bits16 + ((int64_t)w.w * CB + row_in_panel) * (2 * p.W);
+            for (int t = 0; t < w.z; t++, tile_seq++) {
+                const bool mine = ((tile_seq & 1) == grp);
+                if (mine) {
+                    mbar_wait(&t_full[acc], tph);
+                    tcgen05_fence_after();
+                    const uint32_t d0 = tmem_base + lane_addr + (uint32_t)acc * TF_ACC_COLS;
+                    const int64_t j0 = (int64_t)(w.y + t) * TF_J;
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int half = 0; half < 2; half++) {
+                        uint32_t r[72];
+#pragma unroll
+                        for (int a = 0; a < 3; a++)
+#pragma unroll
+                            for (int b = 0; b < 3; b++)
+                                tmem_ld_x8_raw(d0 + (uint32_t)(a * TF_N + b * TF_J + half * 8), &r[(3 * a + b) * 8]);
+                        tmem_wait_bind24(&r[0]);
+                        tmem_wait_bind24(&r[24]);
+                        tmem_wait_bind24(&r[48]);
+                        if (half == 1) {              // every value of this buffer is now in registers
+                            tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&t_empty[acc]);
+                        }
+#pragma unroll
+                        for (int c = 0; c < 8; c++) {
+                            const int64_t j = j0 + half * 8 + c;
+                            if (j > i && j < p.N && i < p.N) {
+                                double S[9];
+#pragma unroll
+                                for (int q = 0; q < 9; q++) S[q] = (double)__uint_as_float(r[q * 8 + c]);
+                                const double Gs = Gi + p.G[j];
+                                const double pad = fma(1e-10, Gs, p.e_thr) + (2.0 * 1.7320508075688772 * TF_EPS) * sGi * p.sG[j];
+                                if (screen_candidate(S, Gs, pad)) bits |= 1u << (half * 8 + c);
+                            }
+                        }
+                    }
+                    if (i < p.N && (j0 >> 4) < 2 * p.W) out_row[j0 >> 4] = (uint16_t)bits;
+                }
+                if (++acc == TF_NACC) { acc = 0; tph ^= 1u; }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TF_TMEM_COLS);
+}
+
+}  // namespace tsc
+
+extern "C" int64_t tsc_tf32_pa_floats(int64_t N, int32_t M) {
+    const int64_t Mp = (M + 7) / 8 * 8, npanel = (N + tsc::TF_ROWS - 1) / tsc::TF_ROWS;
+    return npanel * 3 * Mp * tsc::TF_ROWS;
+}
+extern "C" int64_t tsc_tf32_pb_floats(int64_t N, int32_t M) {
+    const int64_t Mp = (M + 7) / 8 * 8, npanel = (N + tsc::TF_ROWS - 1) / tsc::TF_ROWS;
+    return npanel * (tsc::TF_ROWS / tsc::TF_J) * Mp * tsc::TF_N;
+}
+
+extern "C" int tsc_pack_tf32(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M, float* PA,
+                             float* PB, double* G, double* sG, void* stream) {
+    using namespace tsc;
+    if (N <= 0 || M <= 0) return 0;
+    const int Mp = (M + 7) / 8 * 8;
+    const int64_t rows_pad = (N + TF_ROWS - 1) / TF_ROWS * TF_ROWS;
+    pack_tf32_kernel<<<(unsigned)((rows_pad + 7) / 8), 256, 0, (cudaStream_t)stream>>>(S, N, A, heavy_idx, M, Mp,
+                                                                                     rows_pad, PA, PB, G, sG);
+    TSC_CHECK_LAUNCH();
+    return 0;
+}
+
+// items (n_items, 4) int32: {panel, first j tile, number of j tiles (<= 128 recommended), local row
+// block (32-row units) of the panel's first row inside sim_bits}.
+extern "C" int tsc_rmsd_sim_tf32(const float* PA, const float* PB, const double* G, const double* sG, int64_t N,
+                                 int32_t M, const int32_t* items, int32_t n_items, double thr, uint32_t* sim_bits,
+                                 int32_t grid_ctas, void* stream) {
+    using namespace tsc;
+    if (n_items <= 0 || N <= 0) return 0;
+    TfParams p;
+    p.PA = PA; p.PB = PB; p.G = G; p.sG = sG;
+    p.items = reinterpret_cast<const int4*>(items);
+    p.n_items = n_items;
+    p.N = N;
+    p.Mp = (M + 7) / 8 * 8;
+    p.e_thr = (double)M * thr * thr * (1.0 + 1e-6);
+    p.sim_bits16 = reinterpret_cast<uint16_t*>(sim_bits);
+    p.W = num_blocks_padded(N);
+    const size_t a_bytes = (size_t)1536 * p.Mp, b_bytes = (size_t)192 * p.Mp;
+    const size_t budget = 227 * 1024 - 512;
+    if (a_bytes + 2 * b_bytes > budget) return (int)cudaErrorInvalidValue;       // caller falls back to variant 0
+    int nb = (int)((budget - a_bytes) / b_bytes);
+    if (nb > TF_MAX_BSTAGES) nb = TF_MAX_BSTAGES;
+    p.nb_stages = nb;
+    const size_t smem = a_bytes + nb * b_bytes + 512;
+    cudaError_t e = cudaFuncSetAttribute(rmsd_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int grid = grid_ctas > 0 ? grid_ctas : sms;
+    if (grid > n_items) grid = n_items;
+    rmsd_tf32_kernel<<<grid, TF_THREADS, smem, (cudaStream_t)stream>>>(p);
+    TSC_CHECK_LAUNCH();
+    return 0;
+}

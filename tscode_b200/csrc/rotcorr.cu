@@ -66,6 +66,100 @@ __device__ __forceinline__ void rot_point(const double R[9], double cx, double c
     z = (R[6] * dx + R[7] * dy + R[8] * dz) + cz;
 }
 
+// One pair, both structures already staged in this warp's shared memory (r* = first structure,
+// c* = second structure, which is left rotated to the best rotor angles on return — the
+// reference's in-place mutation).  All lanes return the same rmsd / code.
+__device__ __forceinline__ double rotcorr_eval(const RotCorrParams& p, const double* rx, const double* ry,
+                                               const double* rz, double* cx, double* cy, double* cz, int lane,
+                                               uint32_t& code_out) {
+    const int A = p.A;
+    uint32_t code = 0;
+    int best_idx[RC_MAX_T];
+    // ---- search phase: every rotor on the unmodified second structure (:982-999) ----
+    for (int t = 0; t < p.T; t++) {
+        const int a2 = p.i2[t], a3 = p.i3[t];
+        const double ox = cx[a3], oy = cy[a3], oz = cz[a3];
+        const double ax = cx[a2] - ox, ay = cy[a2] - oy, az = cz[a2] - oz;
+        const uint8_t* rm = p.rot_mask + (size_t)t * A;
+        const uint8_t* nm = p.node_mask + (size_t)t * A;
+        double best = 1e10;
+        int bi = 0;
+        for (int k = 0; k < p.n_ang[t]; k++) {
+            double R[9];
+            rot_from_axis(ax, ay, az, p.sin_half[t * RC_MAX_ANG + k], p.cos_half[t * RC_MAX_ANG + k], R);
+            double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, G = 0.0, cnt = 0.0;
+            for (int a = lane; a < A; a += 32) {
+                if (!nm[a]) continue;
+                const double px = rx[a], py = ry[a], pz = rz[a];
+                double qx = cx[a], qy = cy[a], qz = cz[a];
+                if (rm[a]) rot_point(R, ox, oy, oz, qx, qy, qz);
+                S[0] = fma(px, qx, S[0]); S[1] = fma(px, qy, S[1]); S[2] = fma(px, qz, S[2]);
+                S[3] = fma(py, qx, S[3]); S[4] = fma(py, qy, S[4]); S[5] = fma(py, qz, S[5]);
+                S[6] = fma(pz, qx, S[6]); S[7] = fma(pz, qy, S[7]); S[8] = fma(pz, qz, S[8]);
+                G += px * px + py * py + pz * pz + qx * qx + qy * qy + qz * qz;
+                cnt += 1.0;
+            }
+#pragma unroll
+            for (int c = 0; c < 9; c++) S[c] = warp_sum(S[c]);
+            G = warp_sum(G);
+            cnt = warp_sum(cnt);
+            double q[4];
+            const double lam = key_top_eigen(key_matrix(S), q, nullptr);
+            const double local = sqrt(fmax(G - 2.0 * lam, 0.0) / cnt);
+            if (local < best) { best = local; bi = k; }
+        }
+        best_idx[t] = bi;
+        code |= (uint32_t)bi << (3 * t);
+    }
+    // ---- apply phase: best rotations in torsion order, each about the CURRENT axis (:1004-1008) ----
+    for (int t = 0; t < p.T; t++) {
+        const int k = best_idx[t];
+        if (k == 0 && p.sin_half[t * RC_MAX_ANG] == 0.0) continue;      // angle 0: identity
+        const int a2 = p.i2[t], a3 = p.i3[t];
+        const double ox = cx[a3], oy = cy[a3], oz = cz[a3];
+        double R[9];
+        rot_from_axis(cx[a2] - ox, cy[a2] - oy, cz[a2] - oz, p.sin_half[t * RC_MAX_ANG + k],
+                      p.cos_half[t * RC_MAX_ANG + k], R);
+        __syncwarp();
+        const uint8_t* rm = p.rot_mask + (size_t)t * A;
+        for (int a = lane; a < A; a += 32)
+            if (rm[a]) {
+                double x = cx[a], y = cy[a], z = cz[a];
+                rot_point(R, ox, oy, oz, x, y, z);
+                cx[a] = x; cy[a] = y; cz[a] = z;
+            }
+        __syncwarp();
+    }
+    // ---- global heavy-atom Kabsch RMSD, explicit rotation and differences (:1011) ----
+    double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, cnt = 0.0;
+    for (int a = lane; a < A; a += 32) {
+        if (!p.heavy[a]) continue;
+        const double px = rx[a], py = ry[a], pz = rz[a], qx = cx[a], qy = cy[a], qz = cz[a];
+        S[0] = fma(px, qx, S[0]); S[1] = fma(px, qy, S[1]); S[2] = fma(px, qz, S[2]);
+        S[3] = fma(py, qx, S[3]); S[4] = fma(py, qy, S[4]); S[5] = fma(py, qz, S[5]);
+        S[6] = fma(pz, qx, S[6]); S[7] = fma(pz, qy, S[7]); S[8] = fma(pz, qz, S[8]);
+        cnt += 1.0;
+    }
+#pragma unroll
+    for (int c = 0; c < 9; c++) S[c] = warp_sum(S[c]);
+    cnt = warp_sum(cnt);
+    double R[9];
+    kabsch_rot_from_cov(S, R, nullptr, nullptr);
+    double ss = 0.0;
+    for (int a = lane; a < A; a += 32) {
+        if (!p.heavy[a]) continue;
+        const double px = rx[a], py = ry[a], pz = rz[a];
+        const double dx = fma(R[0], px, fma(R[1], py, R[2] * pz)) - cx[a];
+        const double dy = fma(R[3], px, fma(R[4], py, R[5] * pz)) - cy[a];
+        const double dz = fma(R[6], px, fma(R[7], py, R[8] * pz)) - cz[a];
+        ss += fma(dx, dx, fma(dy, dy, dz * dz));
+    }
+    ss = warp_sum(ss);
+    const double rmsd = sqrt(ss / cnt);
+    code_out = code;
+    return rmsd;
+}
+
 __global__ void __launch_bounds__(RC_WARPS * 32) rotcorr_pairs_kernel(const RotCorrParams p) {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -88,89 +182,8 @@ __global__ void __launch_bounds__(RC_WARPS * 32) rotcorr_pairs_kernel(const RotC
             cx[a] = Pj[3 * a]; cy[a] = Pj[3 * a + 1]; cz[a] = Pj[3 * a + 2];
         }
         __syncwarp();
-        uint32_t code = 0;
-        int best_idx[RC_MAX_T];
-        // ---- search phase: every rotor on the unmodified second structure (:982-999) ----
-        for (int t = 0; t < p.T; t++) {
-            const int a2 = p.i2[t], a3 = p.i3[t];
-            const double ox = cx[a3], oy = cy[a3], oz = cz[a3];
-            const double ax = cx[a2] - ox, ay = cy[a2] - oy, az = cz[a2] - oz;
-            const uint8_t* rm = p.rot_mask + (size_t)t * A;
-            const uint8_t* nm = p.node_mask + (size_t)t * A;
-            double best = 1e10;
-            int bi = 0;
-            for (int k = 0; k < p.n_ang[t]; k++) {
-                double R[9];
-                rot_from_axis(ax, ay, az, p.sin_half[t * RC_MAX_ANG + k], p.cos_half[t * RC_MAX_ANG + k], R);
-                double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, G = 0.0, cnt = 0.0;
-                for (int a = lane; a < A; a += 32) {
-                    if (!nm[a]) continue;
-                    const double px = rx[a], py = ry[a], pz = rz[a];
-                    double qx = cx[a], qy = cy[a], qz = cz[a];
-                    if (rm[a]) rot_point(R, ox, oy, oz, qx, qy, qz);
-                    S[0] = fma(px, qx, S[0]); S[1] = fma(px, qy, S[1]); S[2] = fma(px, qz, S[2]);
-                    S[3] = fma(py, qx, S[3]); S[4] = fma(py, qy, S[4]); S[5] = fma(py, qz, S[5]);
-                    S[6] = fma(pz, qx, S[6]); S[7] = fma(pz, qy, S[7]); S[8] = fma(pz, qz, S[8]);
-                    G += px * px + py * py + pz * pz + qx * qx + qy * qy + qz * qz;
-                    cnt += 1.0;
-                }
-#pragma unroll
-                for (int c = 0; c < 9; c++) S[c] = warp_sum(S[c]);
-                G = warp_sum(G);
-                cnt = warp_sum(cnt);
-                double q[4];
-                const double lam = key_top_eigen(key_matrix(S), q, nullptr);
-                const double local = sqrt(fmax(G - 2.0 * lam, 0.0) / cnt);
-                if (local < best) { best = local; bi = k; }
-            }
-            best_idx[t] = bi;
-            code |= (uint32_t)bi << (3 * t);
-        }
-        // ---- apply phase: best rotations in torsion order, each about the CURRENT axis (:1004-1008) ----
-        for (int t = 0; t < p.T; t++) {
-            const int k = best_idx[t];
-            if (k == 0 && p.sin_half[t * RC_MAX_ANG] == 0.0) continue;      // angle 0: identity
-            const int a2 = p.i2[t], a3 = p.i3[t];
-            const double ox = cx[a3], oy = cy[a3], oz = cz[a3];
-            double R[9];
-            rot_from_axis(cx[a2] - ox, cy[a2] - oy, cz[a2] - oz, p.sin_half[t * RC_MAX_ANG + k],
-                          p.cos_half[t * RC_MAX_ANG + k], R);
-            __syncwarp();
-            const uint8_t* rm = p.rot_mask + (size_t)t * A;
-            for (int a = lane; a < A; a += 32)
-                if (rm[a]) {
-                    double x = cx[a], y = cy[a], z = cz[a];
-                    rot_point(R, ox, oy, oz, x, y, z);
-                    cx[a] = x; cy[a] = y; cz[a] = z;
-                }
-            __syncwarp();
-        }
-        // ---- global heavy-atom Kabsch RMSD, explicit rotation and differences (:1011) ----
-        double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, cnt = 0.0;
-        for (int a = lane; a < A; a += 32) {
-            if (!p.heavy[a]) continue;
-            const double px = rx[a], py = ry[a], pz = rz[a], qx = cx[a], qy = cy[a], qz = cz[a];
-            S[0] = fma(px, qx, S[0]); S[1] = fma(px, qy, S[1]); S[2] = fma(px, qz, S[2]);
-            S[3] = fma(py, qx, S[3]); S[4] = fma(py, qy, S[4]); S[5] = fma(py, qz, S[5]);
-            S[6] = fma(pz, qx, S[6]); S[7] = fma(pz, qy, S[7]); S[8] = fma(pz, qz, S[8]);
-            cnt += 1.0;
-        }
-#pragma unroll
-        for (int c = 0; c < 9; c++) S[c] = warp_sum(S[c]);
-        cnt = warp_sum(cnt);
-        double R[9];
-        kabsch_rot_from_cov(S, R, nullptr, nullptr);
-        double ss = 0.0;
-        for (int a = lane; a < A; a += 32) {
-            if (!p.heavy[a]) continue;
-            const double px = rx[a], py = ry[a], pz = rz[a];
-            const double dx = fma(R[0], px, fma(R[1], py, R[2] * pz)) - cx[a];
-            const double dy = fma(R[3], px, fma(R[4], py, R[5] * pz)) - cy[a];
-            const double dz = fma(R[6], px, fma(R[7], py, R[8] * pz)) - cz[a];
-            ss += fma(dx, dx, fma(dy, dy, dz * dz));
-        }
-        ss = warp_sum(ss);
-        const double rmsd = sqrt(ss / cnt);
+        uint32_t code;
+        const double rmsd = rotcorr_eval(p, rx, ry, rz, cx, cy, cz, lane, code);
         if (lane == 0) {
             if (rmsd < p.max_rmsd) atomicOr(&p.sim_bits[i * p.Wb + (j >> 5)], 1u << (j & 31));
             if (p.codes) p.codes[i * p.N + j] = code;
@@ -179,6 +192,49 @@ __global__ void __launch_bounds__(RC_WARPS * 32) rotcorr_pairs_kernel(const RotC
         }
     }
     if (lane == 0 && near && p.near_count) atomicAdd(p.near_count, near);
+}
+
+
+// Stateful mode (exact emulation of the reference's in-place mutation): one row of the grouping
+// loop.  cur (N, A, 3) holds the CURRENT (mutated) structures; for the first structure i and a
+// list of second structures js[k] this evaluates every pair from the current coordinates and
+// stages the mutated copy of js[k]; the host finds the first similar k and commits the staged
+// copies of everything visited (tsc_rotcorr_commit).
+__global__ void __launch_bounds__(RC_WARPS * 32) rotcorr_row_kernel(const RotCorrParams p, int64_t i,
+                                                                    const int32_t* __restrict__ js, int n,
+                                                                    double* __restrict__ rmsd, uint32_t* __restrict__ codes,
+                                                                    double* __restrict__ staged) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int A = p.A;
+    double* rx = smem + (size_t)warp * 6 * A;
+    double* ry = rx + A; double* rz = ry + A;
+    double* cx = rz + A; double* cy = cx + A; double* cz = cy + A;
+    const double* Pi = p.Sc + i * (int64_t)A * 3;
+    for (int k = blockIdx.x * RC_WARPS + warp; k < n; k += gridDim.x * RC_WARPS) {
+        const double* Pj = p.Sc + (int64_t)js[k] * A * 3;
+        __syncwarp();
+        for (int a = lane; a < A; a += 32) {
+            rx[a] = Pi[3 * a]; ry[a] = Pi[3 * a + 1]; rz[a] = Pi[3 * a + 2];
+            cx[a] = Pj[3 * a]; cy[a] = Pj[3 * a + 1]; cz[a] = Pj[3 * a + 2];
+        }
+        __syncwarp();
+        uint32_t code;
+        const double r = rotcorr_eval(p, rx, ry, rz, cx, cy, cz, lane, code);
+        __syncwarp();
+        double* O = staged + (int64_t)k * A * 3;
+        for (int a = lane; a < A; a += 32) { O[3 * a] = cx[a]; O[3 * a + 1] = cy[a]; O[3 * a + 2] = cz[a]; }
+        if (lane == 0) { rmsd[k] = r; codes[k] = code; }
+    }
+}
+
+__global__ void rotcorr_commit_kernel(double* __restrict__ cur, const double* __restrict__ staged,
+                                      const int32_t* __restrict__ js, int n_accept, int A3) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)n_accept * A3;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(e / A3), o = (int)(e % A3);
+        cur[(int64_t)js[k] * A3 + o] = staged[e];
+    }
 }
 
 // Returned structures: rotor t of structure idx[s] rotated by its accumulated state angle
@@ -260,6 +316,38 @@ extern "C" int tsc_rotcorr_apply(const double* Sc, int64_t n, int32_t A, const i
     if (blocks > 148 * 8) blocks = 148 * 8;
     rotcorr_apply_kernel<<<(unsigned)blocks, RC_WARPS * 32, smem, (cudaStream_t)stream>>>(
         Sc, n, A, idx, T, tor_i2, tor_i3, sin_half, cos_half, rot_mask, out);
+    TSC_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int tsc_rotcorr_row(const double* cur, int64_t N, int32_t A, const uint8_t* heavy, int32_t T,
+                               const int32_t* tor_i2, const int32_t* tor_i3, const int32_t* n_ang,
+                               const double* sin_half, const double* cos_half, const uint8_t* rot_mask,
+                               const uint8_t* node_mask, int64_t i, const int32_t* js, int32_t n, double* rmsd,
+                               uint32_t* codes, double* staged, void* stream) {
+    using namespace tsc;
+    if (n <= 0) return 0;
+    if (T < 0 || T > RC_MAX_T) return (int)cudaErrorInvalidValue;
+    RotCorrParams p{cur, N, A, heavy, T, tor_i2, tor_i3, n_ang, sin_half, cos_half, rot_mask, node_mask, 0, 0,
+                    0.0, nullptr, 0, nullptr, nullptr, nullptr};
+    const size_t smem = (size_t)RC_WARPS * 6 * A * sizeof(double);
+    if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(rotcorr_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int blocks = (n + RC_WARPS - 1) / RC_WARPS;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    rotcorr_row_kernel<<<blocks, RC_WARPS * 32, smem, (cudaStream_t)stream>>>(p, i, js, n, rmsd, codes, staged);
+    TSC_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int tsc_rotcorr_commit(double* cur, const double* staged, const int32_t* js, int32_t n_accept, int32_t A,
+                                  void* stream) {
+    if (n_accept <= 0) return 0;
+    const int64_t total = (int64_t)n_accept * A * 3;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    tsc::rotcorr_commit_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cur, staged, js, n_accept, A * 3);
     TSC_CHECK_LAUNCH();
     return 0;
 }

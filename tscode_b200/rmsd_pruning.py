@@ -18,7 +18,8 @@ import numpy as np
 from . import _host
 from ._lib import check, lib, ptr, require_cuda, stream_ptr
 
-VARIANTS = {"dmma": 0, "fma": 1}
+VARIANTS = {"dmma": 0, "fma": 1, "tf32": 2}
+TF32_MAX_M = 120        # stationary A panel + 2 B stages must fit in shared memory
 
 
 class RmsdPruner:
@@ -39,6 +40,7 @@ class RmsdPruner:
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.thr = float(rmsd_thr)
         self.variant = VARIANTS[variant] if isinstance(variant, str) else int(variant)
+        self.variant_requested = self.variant
         self.rank, self.world, self.group = int(rank), int(world), group
         self.grid_ctas = int(grid_ctas)
         atomnos = np.asarray(atomnos)
@@ -54,6 +56,8 @@ class RmsdPruner:
         N, M = self.N, self.M
         self.nb_pad = _host.num_blocks_padded(N)
         self.W = self.nb_pad
+        if self.variant == 2 and M > TF32_MAX_M:
+            self.variant = 0             # documented fallback: FP64 tensor cores (include/tscode_b200.h)
         with torch.cuda.device(self.device):
             dev = self.device
             self.heavy_idx = torch.from_numpy(heavy).to(dev)
@@ -64,7 +68,16 @@ class RmsdPruner:
             self.n_tiles = int(tiles.shape[0])
             self.tiles = torch.from_numpy(tiles).to(dev)
             self.packed = torch.empty(max(_host.packed_doubles(N, max(M, 1)), 1), dtype=torch.float64, device=dev)
-            self.G = torch.empty(self.nb_pad * _host.CB, dtype=torch.float64, device=dev)
+            n_g = max(self.nb_pad * _host.CB, _host.tf32_rows_padded(N))
+            self.G = torch.empty(n_g, dtype=torch.float64, device=dev)
+            if self.variant == 2:
+                L = lib()
+                self.sG = torch.empty(n_g, dtype=torch.float64, device=dev)
+                self.PA = torch.empty(max(L.tsc_tf32_pa_floats(N, max(M, 1)), 1), dtype=torch.float32, device=dev)
+                self.PB = torch.empty(max(L.tsc_tf32_pb_floats(N, max(M, 1)), 1), dtype=torch.float32, device=dev)
+                items = _host.build_tf32_items(N, self.row_blocks_np)
+                self.n_items = int(items.shape[0])
+                self.items = torch.from_numpy(np.ascontiguousarray(items)).to(dev)
             self.sim_bits = torch.empty((max(self.n_rb, 1) * _host.CB, self.W), dtype=torch.int32, device=dev)
             self.stats = torch.zeros(4, dtype=torch.int64, device=dev)
             nw = (N + 31) // 32
@@ -127,6 +140,9 @@ class RmsdPruner:
         with self.torch.cuda.device(self.device):
             check(L.tsc_pack(ptr(self.S), self.N, self.A, ptr(self.heavy_idx), self.M, ptr(self.packed),
                              ptr(self.G), stream_ptr()), "tsc_pack")
+            if self.variant == 2:
+                check(L.tsc_pack_tf32(ptr(self.S), self.N, self.A, ptr(self.heavy_idx), self.M, ptr(self.PA),
+                                      ptr(self.PB), ptr(self.G), ptr(self.sG), stream_ptr()), "tsc_pack_tf32")
         self.packed_ready = True
 
     def screen(self):
@@ -138,9 +154,14 @@ class RmsdPruner:
         L = lib()
         with self.torch.cuda.device(self.device):
             self.stats.zero_()
-            check(L.tsc_rmsd_sim_tiles(ptr(self.packed), ptr(self.G), self.N, self.M, ptr(self.tiles),
-                                       self.n_tiles, self.thr, ptr(self.sim_bits), self.variant, self.grid_ctas,
-                                       stream_ptr()), "tsc_rmsd_sim_tiles")
+            if self.variant == 2:
+                check(L.tsc_rmsd_sim_tf32(ptr(self.PA), ptr(self.PB), ptr(self.G), ptr(self.sG), self.N, self.M,
+                                          ptr(self.items), self.n_items, self.thr, ptr(self.sim_bits),
+                                          self.grid_ctas, stream_ptr()), "tsc_rmsd_sim_tf32")
+            else:
+                check(L.tsc_rmsd_sim_tiles(ptr(self.packed), ptr(self.G), self.N, self.M, ptr(self.tiles),
+                                           self.n_tiles, self.thr, ptr(self.sim_bits), self.variant, self.grid_ctas,
+                                           stream_ptr()), "tsc_rmsd_sim_tiles")
 
     def verify(self):
         """Exact re-evaluation of screened pairs; afterwards sim_bits are final."""

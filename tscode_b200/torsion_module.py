@@ -152,6 +152,70 @@ class RotCorrPruner:
         lookup.T = T
         return lookup
 
+    def prune_stateful(self, verbose=False):
+        """Exact emulation of the reference loop (:1076-1152) INCLUDING its in-place mutation: rows are
+        replayed in the reference's order; each row is one kernel launch over the not-yet-cached
+        second structures, evaluated from the current (mutated) coordinates; the copies of the
+        structures visited before the reference's `break` are committed.  Returns
+        (mutated structures[mask] as numpy, mask, n_near_threshold)."""
+        import networkx as nx
+        torch, N, A, L = self.torch, self.N, self.A, lib()
+        cur = self.Sc.clone()
+        staged = torch.empty((N, A, 3), dtype=torch.float64, device=self.dev)
+        rmsd_d = torch.empty(N, dtype=torch.float64, device=self.dev)
+        codes_d = torch.empty(N, dtype=torch.int32, device=self.dev)
+        js_d = torch.empty(N, dtype=torch.int32, device=self.dev)
+        js_pin = torch.empty(N, dtype=torch.int32).pin_memory()
+        final_mask = np.ones(N, dtype=bool)
+        cached = np.zeros((N, N), dtype=bool)
+        near = 0
+        st = stream_ptr()
+        for k in _host.LADDER:
+            num_active = int(np.count_nonzero(final_mask))
+            if not (k == 1 or 5 * k < num_active):
+                continue
+            if verbose:
+                print(f"Working on subgroups with k={k} ({num_active} candidates left) {' ' * 10}", end="\r")
+            d = int(N // k)
+            for step in range(int(k)):
+                _l = len(range(d * step, num_active)) if step == k - 1 else len(range(d * step, int(d * (step + 1))))
+                if _l <= 1:
+                    continue
+                base = d * step
+                matches = set()
+                for i_rel in range(_l):
+                    i, lo, hi = base + i_rel, base + i_rel + 1, base + _l
+                    if lo >= hi:
+                        continue
+                    js = lo + np.flatnonzero(~cached[i, lo:hi])
+                    n = int(js.size)
+                    if n == 0:
+                        continue
+                    js_pin[:n] = torch.from_numpy(js.astype(np.int32))
+                    js_d[:n].copy_(js_pin[:n], non_blocking=True)
+                    check(L.tsc_rotcorr_row(ptr(cur), N, A, ptr(self.heavy), self.info.T, ptr(self.i2), ptr(self.i3),
+                                            ptr(self.n_ang), ptr(self.sin_half), ptr(self.cos_half), ptr(self.rot_mask),
+                                            ptr(self.node_mask), i, ptr(js_d), n, ptr(rmsd_d), ptr(codes_d),
+                                            ptr(staged), st), "tsc_rotcorr_row")
+                    r = rmsd_d[:n].cpu().numpy()
+                    hits = np.flatnonzero(r < self.max_rmsd)
+                    if hits.size:
+                        h = int(hits[0])
+                        n_acc = h + 1
+                        cached[i, js[:h]] = True
+                        matches.add((i_rel, int(js[h] - base)))
+                    else:
+                        n_acc = n
+                        cached[i, js] = True
+                    near += int(np.count_nonzero(np.abs(r[:n_acc] - self.max_rmsd) < 1e-6))
+                    check(L.tsc_rotcorr_commit(ptr(cur), ptr(staged), ptr(js_d), n_acc, A, st), "tsc_rotcorr_commit")
+                g = nx.Graph(matches)
+                for group in [tuple(g.subgraph(c).nodes) for c in nx.connected_components(g)]:
+                    for rr in set(group) - {group[0]}:
+                        final_mask[rr + base] = 0
+        keep = torch.from_numpy(np.flatnonzero(final_mask)).to(self.dev)
+        return cur[keep].cpu().numpy(), final_mask, near
+
     def apply_states(self, idx, state_deg):
         """Centred structures idx with rotor states applied -> numpy (n, A, 3)."""
         torch = self.torch
@@ -228,8 +292,15 @@ def ladder_replay(similar, N, best_angles=None, verbose=False):
 
 
 def prune_conformers_rmsd_rot_corr(structures, atomnos, graph, max_rmsd=0.25, verbose=False, logfunction=None,
-                                   *, torsion_info: TorsionInfo | None = None, max_structures=750):
-    """Drop-in for tscode.torsion_module.prune_conformers_rmsd_rot_corr (:1013-1161)."""
+                                   *, torsion_info: TorsionInfo | None = None, max_structures=750, mode=None):
+    """Drop-in for tscode.torsion_module.prune_conformers_rmsd_rot_corr (:1013-1161).
+
+    mode "exact" (default up to 2000 structures): row-by-row replay from the current, mutated
+    coordinates — same visiting order, same mutations, same returned structures as the reference.
+    mode "stateless" (default above): all pairs at once from the centred input + host replay with
+    rotor-state algebra; masks agree with the reference on every fixture, but for rotors whose
+    n-fold images differ only at noise level (e.g. a methyl-capped alkyne: the heavy atoms sit on
+    the axis) the hydrogens of the returned structures may end up in another image."""
     structures = np.array([s - s.mean(axis=0) for s in np.asarray(structures, dtype=np.float64)])     # :1023
     atomnos = np.asarray(atomnos)
     N = structures.shape[0]
@@ -245,6 +316,12 @@ def prune_conformers_rmsd_rot_corr(structures, atomnos, graph, max_rmsd=0.25, ve
             sym = ''.join(_SYMBOLS[atomnos[a]] if atomnos[a] < len(_SYMBOLS) else '?' for a in torsion)
             logfunction(' {:2s} - {:21s} : {} : {}-fold'.format(str(i), str(list(torsion)), sym, len(angle)))
         logfunction("\n")
+    if mode is None:
+        mode = "exact" if N <= 2000 else "stateless"
+    if mode == "exact":
+        pr = RotCorrPruner(structures, atomnos, info, max_rmsd, want_codes=False)
+        out, mask, _ = pr.prune_stateful(verbose=verbose)
+        return out, mask
     pr = RotCorrPruner(structures, atomnos, info, max_rmsd)
     pr.similarity()
     mask, state = ladder_replay(pr.similar_matrix(), N, pr.best_angles(), verbose=verbose)
