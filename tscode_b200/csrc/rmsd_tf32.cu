@@ -204,25 +204,34 @@ __global__ void __launch_bounds__(TF_THREADS, 1) rmsd_tf32_kernel(const TfParams
         }
     } else {
         // ===================== epilogue (8 warps, two groups alternating over tiles) =====================
+        // Per pair:  lam = threshold eigenvalue lowered by the TF32 error bound (3 FP64 ops);
+        //   fast path (FP32, no conversion): Samuelson's bound lambda_max <= sqrt(3) ||S~||_F, i.e. the
+        //     pair is excluded if 3 * sum(S~^2) <= lam^2  — decided per half-tile with one warp vote;
+        //   full path (FP64, branch-free): Budan-Fourier sign test on the key-matrix quartic at lam.
         const int ew = warp - 2;                      // 0..7
         const int grp = ew >> 2;                      // tiles with (tile index & 1) == grp
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
         const int row_in_panel = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        const double cc = 1.7320508075688772 * TF_EPS;
+        const double hs = 0.5 * (1.0 - 1e-10);
         int acc = 0; uint32_t tph = 0;
         int64_t tile_seq = 0;                         // running tile counter of this CTA
         for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
             const int4 w = p.items[it];
             const int64_t i = (int64_t)w.x * TF_ROWS + row_in_panel;
-            const double Gi = p.G[i], sGi = p.sG[i];
+            const double Gi = p.G[i];
+            const double hi = fma(hs, Gi, -0.5 * p.e_thr), ci = -cc * p.sG[i];
             uint16_t* out_row = p.sim_bits16 + ((int64_t)w.w * CB + row_in_panel) * (2 * p.W);
             for (int t = 0; t < w.z; t++, tile_seq++) {
                 const bool mine = ((tile_seq & 1) == grp);
                 if (mine) {
+                    const int64_t j0 = (int64_t)(w.y + t) * TF_J;
+                    // lanes 0..15 fetch G[j0+lane], lanes 16..31 sqrt(G)[j0+lane-16]; broadcast by shuffle later
+                    const double gv = (lane < 16) ? p.G[j0 + lane] : p.sG[j0 + lane - 16];
                     mbar_wait(&t_full[acc], tph);
                     tcgen05_fence_after();
                     const uint32_t d0 = tmem_base + lane_addr + (uint32_t)acc * TF_ACC_COLS;
-                    const int64_t j0 = (int64_t)(w.y + t) * TF_J;
                     uint32_t bits = 0;
 #pragma unroll
                     for (int half = 0; half < 2; half++) {
@@ -240,20 +249,42 @@ __global__ void __launch_bounds__(TF_THREADS, 1) rmsd_tf32_kernel(const TfParams
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&t_empty[acc]);
                         }
+                        double lam[8];
+                        uint32_t near = 0;            // pairs the FP32 bound cannot exclude
 #pragma unroll
                         for (int c = 0; c < 8; c++) {
-                            const int64_t j = j0 + half * 8 + c;
-                            if (j > i && j < p.N && i < p.N) {
+                            const double Gj = __shfl_sync(0xffffffffu, gv, half * 8 + c);
+                            const double sGj = __shfl_sync(0xffffffffu, gv, 16 + half * 8 + c);
+                            lam[c] = fma(ci, sGj, fma(hs, Gj, hi));
+                            float f = 0.f;
+#pragma unroll
+                            for (int q = 0; q < 9; q++) { const float v = __uint_as_float(r[q * 8 + c]); f = fmaf(v, v, f); }
+                            const float lf = __double2float_rd(lam[c]) * 0.999999f;        // rounded towards -inf, then lowered
+                            const bool far = (lf > 0.f) && (3.00003f * f <= lf * lf);
+                            near |= (far ? 0u : 1u) << c;
+                        }
+                        if (__any_sync(0xffffffffu, near != 0u)) {
+#pragma unroll
+                            for (int c = 0; c < 8; c++) {
                                 double S[9];
 #pragma unroll
                                 for (int q = 0; q < 9; q++) S[q] = (double)__uint_as_float(r[q * 8 + c]);
-                                const double Gs = Gi + p.G[j];
-                                const double pad = fma(1e-10, Gs, p.e_thr) + (2.0 * 1.7320508075688772 * TF_EPS) * sGi * p.sG[j];
-                                if (screen_candidate(S, Gs, pad)) bits |= 1u << (half * 8 + c);
+                                double c2, c1, c0;
+                                key_charpoly(S, c2, c1, c0);
+                                const double l1 = lam[c], l2 = l1 * l1;
+                                const double p2 = fma(12.0, l2, 2.0 * c2);
+                                const double p1 = fma(fma(4.0, l2, 2.0 * c2), l1, c1);
+                                const double p0 = fma(fma(l2 + c2, l1, c1), l1, c0);
+                                const bool excluded = (l1 > 0.0) & (p0 > 0.0) & (p1 > 0.0) & (p2 > 0.0);
+                                if (!excluded && ((near >> c) & 1u)) bits |= 1u << (half * 8 + c);
                             }
                         }
                     }
-                    if (i < p.N && (j0 >> 4) < 2 * p.W) out_row[j0 >> 4] = (uint16_t)bits;
+                    // validity mask: j > i, j < N   (rows i >= N are not stored)
+                    uint32_t valid = 0xffffu;
+                    if (j0 + 15 >= p.N) valid = (j0 >= p.N) ? 0u : (0xffffu >> (j0 + 16 - p.N));
+                    if (j0 <= i) valid &= (i - j0 >= 15) ? 0u : (0xffffu << (i - j0 + 1));
+                    if (i < p.N && (j0 >> 4) < 2 * p.W) out_row[j0 >> 4] = (uint16_t)(bits & valid);
                 }
                 if (++acc == TF_NACC) { acc = 0; tph ^= 1u; }
             }
