@@ -404,7 +404,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--variant", default="dmma", choices=["dmma", "fma", "tf32"])
+    ap.add_argument("--variant", default="tf32", choices=["dmma", "fma", "tf32"])
     ap.add_argument("--n-conformers", type=int, default=0, help="override N (testing only; invalid as a bench value)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--lazy-n", type=int, default=10000)
