@@ -41,9 +41,9 @@ constexpr int TF_ACC_COLS = 3 * TF_N;          // 144 TMEM columns per accumulat
 constexpr int TF_NACC = 3;                     // accumulator buffers (432 of 512 columns)
 constexpr int TF_TMEM_COLS = 512;
 constexpr int TF_MAX_BSTAGES = 6;
-constexpr int TF_THREADS = 320;
+constexpr int TF_MAX_GROUPS = 3;               // epilogue groups of 4 warps
 constexpr double TF_EPS = 1.05e-3;             // see header
-constexpr int TF_CHUNK_TILES = 128;            // j tiles per work item
+constexpr int TF_DEFAULT_CFG = 1;              // see tsc_rmsd_sim_tf32
 
 struct TfParams {
     const float* PA;          // [panel][a][kc][128][4]
@@ -102,6 +102,16 @@ __device__ __forceinline__ void tmem_ld_x8_raw(uint32_t taddr, uint32_t* r) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld_x4_raw(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_bind12(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11])::"memory");
+}
 // tcgen05.wait::ld carrying 24 registers as in/out operands so that no use can be hoisted above it
 __device__ __forceinline__ void tmem_wait_bind24(uint32_t* r) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
@@ -111,7 +121,8 @@ __device__ __forceinline__ void tmem_wait_bind24(uint32_t* r) {
                    "+r"(r[22]), "+r"(r[23])::"memory");
 }
 
-__global__ void __launch_bounds__(TF_THREADS, 1) rmsd_tf32_kernel(const TfParams p) {
+template <int NGROUPS, int STEP>   // NGROUPS epilogue groups of 4 warps; STEP columns per TMEM load round (4 or 8)
+__global__ void __launch_bounds__((2 + 4 * NGROUPS) * 32, 1) rmsd_tf32_kernel(const TfParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int nkc = p.Mp / 4;
     const uint32_t a_bytes = 3u * nkc * TF_ROWS * 16u;        // 1536 * Mp
@@ -132,7 +143,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) rmsd_tf32_kernel(const TfParams
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
         for (int s = 0; s < p.nb_stages; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int t = 0; t < TF_NACC; t++) { mbar_init(&t_full[t], 1); mbar_init(&t_empty[t], 4); }
+        for (int t = 0; t < TF_NACC; t++) { mbar_init(&t_full[t], 1); mbar_init(&t_empty[t], 4); }   // 4 warps per group
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TF_TMEM_COLS);
@@ -208,8 +219,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) rmsd_tf32_kernel(const TfParams
         //   fast path (FP32, no conversion): Samuelson's bound lambda_max <= sqrt(3) ||S~||_F, i.e. the
         //     pair is excluded if 3 * sum(S~^2) <= lam^2  — decided per half-tile with one warp vote;
         //   full path (FP64, branch-free): Budan-Fourier sign test on the key-matrix quartic at lam.
-        const int ew = warp - 2;                      // 0..7
-        const int grp = ew >> 2;                      // tiles with (tile index & 1) == grp
+        const int ew = warp - 2;                      // 0 .. 4*NGROUPS-1
+        const int grp = ew >> 2;                      // this group takes tiles with tile index % NGROUPS == grp
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
         const int row_in_panel = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
@@ -224,7 +235,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) rmsd_tf32_kernel(const TfParams
             const double hi = fma(hs, Gi, -0.5 * p.e_thr), ci = -cc * p.sG[i];
             uint16_t* out_row = p.sim_bits16 + ((int64_t)w.w * CB + row_in_panel) * (2 * p.W);
             for (int t = 0; t < w.z; t++, tile_seq++) {
-                const bool mine = ((tile_seq & 1) == grp);
+                const bool mine = ((int)(tile_seq % NGROUPS) == grp);
                 if (mine) {
                     const int64_t j0 = (int64_t)(w.y + t) * TF_J;
                     // lanes 0..15 fetch G[j0+lane], lanes 16..31 sqrt(G)[j0+lane-16]; broadcast by shuffle later
@@ -234,41 +245,43 @@ __global__ void __launch_bounds__(TF_THREADS, 1) rmsd_tf32_kernel(const TfParams
                     const uint32_t d0 = tmem_base + lane_addr + (uint32_t)acc * TF_ACC_COLS;
                     uint32_t bits = 0;
 #pragma unroll
-                    for (int half = 0; half < 2; half++) {
-                        uint32_t r[72];
+                    for (int st = 0; st < TF_J / STEP; st++) {
+                        uint32_t r[9 * STEP];
 #pragma unroll
                         for (int a = 0; a < 3; a++)
 #pragma unroll
-                            for (int b = 0; b < 3; b++)
-                                tmem_ld_x8_raw(d0 + (uint32_t)(a * TF_N + b * TF_J + half * 8), &r[(3 * a + b) * 8]);
-                        tmem_wait_bind24(&r[0]);
-                        tmem_wait_bind24(&r[24]);
-                        tmem_wait_bind24(&r[48]);
-                        if (half == 1) {              // every value of this buffer is now in registers
+                            for (int b = 0; b < 3; b++) {
+                                const uint32_t ta = d0 + (uint32_t)(a * TF_N + b * TF_J + st * STEP);
+                                if (STEP == 8) tmem_ld_x8_raw(ta, &r[(3 * a + b) * STEP]);
+                                else tmem_ld_x4_raw(ta, &r[(3 * a + b) * STEP]);
+                            }
+                        if (STEP == 8) { tmem_wait_bind24(&r[0]); tmem_wait_bind24(&r[24]); tmem_wait_bind24(&r[48]); }
+                        else { tmem_wait_bind12(&r[0]); tmem_wait_bind12(&r[12]); tmem_wait_bind12(&r[24]); }
+                        if (st == TF_J / STEP - 1) {  // every value of this buffer is now in registers
                             tcgen05_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&t_empty[acc]);
                         }
-                        double lam[8];
+                        double lam[STEP];
                         uint32_t near = 0;            // pairs the FP32 bound cannot exclude
 #pragma unroll
-                        for (int c = 0; c < 8; c++) {
-                            const double Gj = __shfl_sync(0xffffffffu, gv, half * 8 + c);
-                            const double sGj = __shfl_sync(0xffffffffu, gv, 16 + half * 8 + c);
+                        for (int c = 0; c < STEP; c++) {
+                            const double Gj = __shfl_sync(0xffffffffu, gv, st * STEP + c);
+                            const double sGj = __shfl_sync(0xffffffffu, gv, 16 + st * STEP + c);
                             lam[c] = fma(ci, sGj, fma(hs, Gj, hi));
                             float f = 0.f;
 #pragma unroll
-                            for (int q = 0; q < 9; q++) { const float v = __uint_as_float(r[q * 8 + c]); f = fmaf(v, v, f); }
+                            for (int q = 0; q < 9; q++) { const float v = __uint_as_float(r[q * STEP + c]); f = fmaf(v, v, f); }
                             const float lf = __double2float_rd(lam[c]) * 0.999999f;        // rounded towards -inf, then lowered
                             const bool far = (lf > 0.f) && (3.00003f * f <= lf * lf);
                             near |= (far ? 0u : 1u) << c;
                         }
                         if (__any_sync(0xffffffffu, near != 0u)) {
 #pragma unroll
-                            for (int c = 0; c < 8; c++) {
+                            for (int c = 0; c < STEP; c++) {
                                 double S[9];
 #pragma unroll
-                                for (int q = 0; q < 9; q++) S[q] = (double)__uint_as_float(r[q * 8 + c]);
+                                for (int q = 0; q < 9; q++) S[q] = (double)__uint_as_float(r[q * STEP + c]);
                                 double c2, c1, c0;
                                 key_charpoly(S, c2, c1, c0);
                                 const double l1 = lam[c], l2 = l1 * l1;
@@ -276,7 +289,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) rmsd_tf32_kernel(const TfParams
                                 const double p1 = fma(fma(4.0, l2, 2.0 * c2), l1, c1);
                                 const double p0 = fma(fma(l2 + c2, l1, c1), l1, c0);
                                 const bool excluded = (l1 > 0.0) & (p0 > 0.0) & (p1 > 0.0) & (p2 > 0.0);
-                                if (!excluded && ((near >> c) & 1u)) bits |= 1u << (half * 8 + c);
+                                if (!excluded && ((near >> c) & 1u)) bits |= 1u << (st * STEP + c);
                             }
                         }
                     }
@@ -341,14 +354,20 @@ extern "C" int tsc_rmsd_sim_tf32(const float* PA, const float* PB, const double*
     if (nb > TF_MAX_BSTAGES) nb = TF_MAX_BSTAGES;
     p.nb_stages = nb;
     const size_t smem = a_bytes + nb * b_bytes + 512;
-    cudaError_t e = cudaFuncSetAttribute(rmsd_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // grid_ctas < 0 selects an alternative epilogue configuration (tuning aid): -1 = 2 groups x 8
+    // columns, -2 = 3 groups x 4 columns, -3 = 2 groups x 4 columns; default (>= 0) = TF_DEFAULT_CFG
+    const int cfg = grid_ctas < 0 ? -grid_ctas : TF_DEFAULT_CFG;
+    if (grid_ctas < 0) grid_ctas = 0;
+    auto kern = cfg == 1 ? rmsd_tf32_kernel<2, 8> : cfg == 2 ? rmsd_tf32_kernel<3, 4> : rmsd_tf32_kernel<2, 4>;
+    const int threads = cfg == 2 ? 448 : 320;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid = grid_ctas > 0 ? grid_ctas : sms;
     if (grid > n_items) grid = n_items;
-    rmsd_tf32_kernel<<<grid, TF_THREADS, smem, (cudaStream_t)stream>>>(p);
+    kern<<<grid, threads, smem, (cudaStream_t)stream>>>(p);
     TSC_CHECK_LAUNCH();
     return 0;
 }
