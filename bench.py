@@ -337,8 +337,12 @@ def run_b200(args):
         psrc = ("self-measured FP64 ceiling on this GPU in this run (tsc_bench_fp64: register-resident "
                 f"DMMA.8x8x4 {peaks['dmma']} / DFMA {peaks['dfma']} / both {peaks['mixed']} TFLOP/s); "
                 f"MEASURED_PEAKS.json ({mp_src}) has no FP64 entry")
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp) and world == 1 and not args.n_conformers:
+        traffic = json.load(open(tp)).get(kname)
     roofline = {"bound": "tensor", "kernel": kname,
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": psrc,
                 "algorithmic_flop_per_pair": 18 * M, "kernel_ms": screen_ms,
                 "kernel_share_of_step": screen_ms / step_ms}
@@ -391,7 +395,7 @@ def run_b200(args):
                        "matches_reference": (mask_digest(mask_np) == cfg["digest"]) if cfg["digest"] else None,
                        **pr.stats_dict()},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clash": clash,
-            "gpu_launches": args.steps * (4 + 3 * rounds), "clocks": clocks,
+            "gpu_launches": args.steps * ((5 if args.variant == "tf32" else 4) + 3 * rounds), "clocks": clocks,
             "fp64_peaks_tflops": peaks}
     print(json.dumps(line), flush=True)
     if world > 1:

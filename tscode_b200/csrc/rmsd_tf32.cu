@@ -43,7 +43,7 @@ constexpr int TF_TMEM_COLS = 512;
 constexpr int TF_MAX_BSTAGES = 6;
 constexpr int TF_MAX_GROUPS = 3;               // epilogue groups of 4 warps
 constexpr double TF_EPS = 1.05e-3;             // see header
-constexpr int TF_DEFAULT_CFG = 1;              // see tsc_rmsd_sim_tf32
+constexpr int TF_DEFAULT_CFG = 3;              // see tsc_rmsd_sim_tf32
 
 struct TfParams {
     const float* PA;          // [panel][a][kc][128][4]
