@@ -89,18 +89,25 @@ int tsc_rmsd_pairs(const double* P, const double* Q, int64_t n, int32_t M, int32
                    double* rmsd, double* maxdev, void* stream);
 
 /* One ladder round (rmsd_pruning.py:123-162) in three steps; cs = int(N // k) (:136).
+ *   gate (device, 1 int32, or NULL): number of active structures BEFORE this round.  When given,
+ *   every kernel first evaluates the reference's gate `k == 1 or 20*k < active` (:192) and does
+ *   nothing if it is closed — the host can enqueue every candidate round without a readback.
  *   cachebits ((N+31)/32 words): bit s set iff key (first, s) is cached and `first` starts a
  *   chunk of this round;   key_first/key_second (N) int32 + n_keys (1) int32: the cache (:183,:204). */
 int tsc_elim_cachebits(const int32_t* key_first, const int32_t* key_second, const int32_t* n_keys,
-                       int64_t N, int64_t cs, int64_t k, uint32_t* cachebits, void* stream);
-/*   out_mask (N) uint8 and out_key_second (N) int32 (-1 = none) are written for owned rows only. */
+                       int64_t N, int64_t cs, int64_t k, uint32_t* cachebits, const int32_t* gate,
+                       void* stream);
+/*   row_state (N) int32, written for owned rows only: -2 inactive, -1 kept, >= 0 dropped (value =
+ *   second element of the emitted cache key, first + j - i). */
 int tsc_elim_round(const uint32_t* sim_bits, const int32_t* row_blocks, int32_t n_rb,
                    const uint32_t* active_words, const uint32_t* cachebits, int64_t N, int64_t cs,
-                   int64_t k, uint8_t* out_mask, int32_t* out_key_second, void* stream);
-/*   mask bytes -> active words (+ n_active), emitted keys appended to the cache. */
-int tsc_elim_commit(const uint8_t* mask, const int32_t* key_second_per_row, int64_t N, int64_t cs,
-                    int64_t k, uint32_t* active_words_out, int32_t* key_first, int32_t* key_second,
-                    int32_t* n_keys, int32_t* n_active, void* stream);
+                   int64_t k, int32_t* row_state, const int32_t* gate, void* stream);
+/*   row_state -> active words, byte mask, emitted keys appended to the cache; n_active_out (must be
+ *   zero on entry) receives the new active count, or a copy of *gate when the round was skipped. */
+int tsc_elim_commit(const int32_t* row_state, int64_t N, int64_t cs, int64_t k,
+                    uint32_t* active_words_out, uint8_t* mask_out, int32_t* key_first,
+                    int32_t* key_second, int32_t* n_keys, const int32_t* gate, int32_t* n_active_out,
+                    void* stream);
 
 /* ---- compenetration_check / get_embed -------------------------------------------------- */
 /* Fused pose transform + clash screen (embeds.py:116-118 / 713-714 / 841-842).

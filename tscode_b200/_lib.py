@@ -30,9 +30,9 @@ SIGNATURES = {
     "tsc_rmsd_sim_tf32": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _i32, _vp]),
     "tsc_rmsd_verify": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp]),
     "tsc_rmsd_pairs": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
-    "tsc_elim_cachebits": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "tsc_elim_cachebits": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "tsc_elim_round": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
-    "tsc_elim_commit": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tsc_elim_commit": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tsc_embed_clash": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _f64, _f64, _i64, _vp, _vp, _vp]),
     "tsc_clash_structs": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _f64, _f64, _f64, _i64, _vp, _vp, _vp]),
     "tsc_rotcorr_pairs": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f64,

@@ -14,11 +14,21 @@
 //   tsc_elim_cachebits : key list -> N-bit map for this round's chunking (bit s set iff
 //                        (first, s) is cached and `first` is a chunk start of this round)
 //   tsc_elim_round     : one warp per row, 32 words per step, early exit on first hit
-//   tsc_elim_commit    : byte mask -> active words, active count, key-list append
+//   tsc_elim_commit    : per-row state -> active words, byte mask, active count, key-list append
 // Latency-bound (a few hundred kB per round); reported as time, not against a roofline.
+//
+// Device-side gating.  Whether a round of the ladder runs depends on the number of structures
+// still active (`k == 1 or 20*k < count_nonzero(mask)`, rmsd_pruning.py:192).  Every kernel takes
+// a pointer to that count as it stood BEFORE the round and returns immediately when the gate is
+// closed, so the host can enqueue every candidate round without reading anything back (no
+// synchronisation until the final mask) and all ranks of a multi-GPU run take the same decision.
 #include "tsc_common.cuh"
 
 namespace tsc {
+
+__device__ __forceinline__ bool gate_open(const int32_t* gate, int64_t k) {
+    return gate == nullptr || k == 1 || 20 * k < (int64_t)*gate;
+}
 
 __device__ __forceinline__ void chunk_of(int64_t i, int64_t N, int64_t cs, int64_t k, int64_t& first,
                                          int64_t& last) {
@@ -31,7 +41,8 @@ __device__ __forceinline__ void chunk_of(int64_t i, int64_t N, int64_t cs, int64
 
 __global__ void elim_cachebits_kernel(const int32_t* __restrict__ key_first, const int32_t* __restrict__ key_second,
                                       const int32_t* __restrict__ n_keys, int64_t N, int64_t cs, int64_t k,
-                                      uint32_t* cachebits) {
+                                      uint32_t* cachebits, const int32_t* __restrict__ gate) {
+    if (!gate_open(gate, k)) return;
     const int n = *n_keys;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
         const int64_t f = key_first[t], s = key_second[t];
@@ -53,8 +64,9 @@ __global__ void __launch_bounds__(256) elim_round_kernel(const uint32_t* __restr
                                                          const int32_t* __restrict__ row_blocks, int n_rb,
                                                          const uint32_t* __restrict__ active,
                                                          const uint32_t* __restrict__ cachebits, int64_t N,
-                                                         int64_t cs, int64_t k, uint8_t* __restrict__ out_mask,
-                                                         int32_t* __restrict__ out_key) {
+                                                         int64_t cs, int64_t k, int32_t* __restrict__ row_state,
+                                                         const int32_t* __restrict__ gate) {
+    if (!gate_open(gate, k)) return;
     const int lane = threadIdx.x & 31;
     const int64_t warp_g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -63,7 +75,7 @@ __global__ void __launch_bounds__(256) elim_round_kernel(const uint32_t* __restr
         const int64_t i = (int64_t)row_blocks[row / CB] * CB + (row % CB);
         if (i >= N) continue;
         if (!((active[i >> 5] >> (i & 31)) & 1u)) {
-            if (lane == 0) { out_mask[i] = 0; out_key[i] = -1; }
+            if (lane == 0) row_state[i] = -2;                    // inactive
             continue;
         }
         int64_t first, last;
@@ -106,33 +118,38 @@ __global__ void __launch_bounds__(256) elim_round_kernel(const uint32_t* __restr
                 }
             }
         }
-        if (lane == 0) { out_mask[i] = (uint8_t)keep; out_key[i] = key; }
+        if (lane == 0) row_state[i] = keep ? -1 : key;          // -1 kept, >= 0 dropped with this cache key
     }
 }
 
-__global__ void __launch_bounds__(256) elim_commit_kernel(const uint8_t* __restrict__ mask,
-                                                          const int32_t* __restrict__ keys, int64_t N, int64_t cs,
+__global__ void __launch_bounds__(256) elim_commit_kernel(const int32_t* __restrict__ row_state, int64_t N, int64_t cs,
                                                           int64_t k, uint32_t* __restrict__ active_out,
-                                                          int32_t* key_first, int32_t* key_second, int32_t* n_keys,
-                                                          int32_t* n_active) {
+                                                          uint8_t* __restrict__ mask_out, int32_t* key_first,
+                                                          int32_t* key_second, int32_t* n_keys,
+                                                          const int32_t* __restrict__ gate, int32_t* n_active_out) {
+    if (!gate_open(gate, k)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *n_active_out = *gate;     // round skipped: count carries over
+        return;
+    }
     const int lane = threadIdx.x & 31;
     const int64_t Npad = (N + 31) & ~int64_t(31);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Npad; i += (int64_t)gridDim.x * blockDim.x) {
         const bool live = i < N;
-        const bool m = live && mask[i] != 0;
+        const int32_t st = live ? row_state[i] : -2;
+        const bool m = st == -1;
         const uint32_t word = __ballot_sync(0xffffffffu, m);
         if (lane == 0) {
             active_out[i >> 5] = word;
-            if (word) atomicAdd(n_active, __popc(word));
+            if (word) atomicAdd(n_active_out, __popc(word));
         }
         if (live) {
-            const int32_t s = keys[i];
-            if (s >= 0) {
+            mask_out[i] = (uint8_t)m;
+            if (st >= 0) {
                 int64_t first, last;
                 chunk_of(i, N, cs, k, first, last);
                 const int slot = atomicAdd(n_keys, 1);
                 key_first[slot] = (int32_t)first;
-                key_second[slot] = s;
+                key_second[slot] = st;
             }
         }
     }
@@ -141,41 +158,40 @@ __global__ void __launch_bounds__(256) elim_commit_kernel(const uint8_t* __restr
 }  // namespace tsc
 
 extern "C" int tsc_elim_cachebits(const int32_t* key_first, const int32_t* key_second, const int32_t* n_keys,
-                                  int64_t N, int64_t cs, int64_t k, uint32_t* cachebits, void* stream) {
+                                  int64_t N, int64_t cs, int64_t k, uint32_t* cachebits, const int32_t* gate,
+                                  void* stream) {
     if (N <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(cachebits, 0, (size_t)((N + 31) / 32) * 4, st);
     if (e != cudaSuccess) return (int)e;
-    tsc::elim_cachebits_kernel<<<148, 256, 0, st>>>(key_first, key_second, n_keys, N, cs, k, cachebits);
+    tsc::elim_cachebits_kernel<<<148, 256, 0, st>>>(key_first, key_second, n_keys, N, cs, k, cachebits, gate);
     TSC_CHECK_LAUNCH();
     return 0;
 }
 
 extern "C" int tsc_elim_round(const uint32_t* sim_bits, const int32_t* row_blocks, int32_t n_rb,
                               const uint32_t* active_words, const uint32_t* cachebits, int64_t N, int64_t cs,
-                              int64_t k, uint8_t* out_mask, int32_t* out_key_second, void* stream) {
+                              int64_t k, int32_t* row_state, const int32_t* gate, void* stream) {
     if (N <= 0 || n_rb <= 0) return 0;
     const int64_t W = tsc::num_blocks_padded(N);
     int64_t rows = (int64_t)n_rb * tsc::CB;
     int64_t blocks = (rows + 7) / 8;
     if (blocks > 148 * 64) blocks = 148 * 64;
     tsc::elim_round_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        sim_bits, W, row_blocks, n_rb, active_words, cachebits, N, cs, k, out_mask, out_key_second);
+        sim_bits, W, row_blocks, n_rb, active_words, cachebits, N, cs, k, row_state, gate);
     TSC_CHECK_LAUNCH();
     return 0;
 }
 
-extern "C" int tsc_elim_commit(const uint8_t* mask, const int32_t* key_second_per_row, int64_t N, int64_t cs,
-                               int64_t k, uint32_t* active_words_out, int32_t* key_first, int32_t* key_second,
-                               int32_t* n_keys, int32_t* n_active, void* stream) {
+extern "C" int tsc_elim_commit(const int32_t* row_state, int64_t N, int64_t cs, int64_t k,
+                               uint32_t* active_words_out, uint8_t* mask_out, int32_t* key_first,
+                               int32_t* key_second, int32_t* n_keys, const int32_t* gate, int32_t* n_active_out,
+                               void* stream) {
     if (N <= 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(n_active, 0, 4, st);
-    if (e != cudaSuccess) return (int)e;
     int64_t blocks = (N + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    tsc::elim_commit_kernel<<<(unsigned)blocks, 256, 0, st>>>(mask, key_second_per_row, N, cs, k, active_words_out,
-                                                             key_first, key_second, n_keys, n_active);
+    tsc::elim_commit_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        row_state, N, cs, k, active_words_out, mask_out, key_first, key_second, n_keys, gate, n_active_out);
     TSC_CHECK_LAUNCH();
     return 0;
 }

@@ -105,14 +105,14 @@ class RmsdPruner:
             self.active = torch.empty(max(nw, 1), dtype=torch.int32, device=dev)
             self.cachebits = torch.empty(max(nw, 1), dtype=torch.int32, device=dev)
             self.mask_bytes = torch.ones(rows_pad, dtype=torch.uint8, device=dev)
-            self.row_keys = torch.full((rows_pad,), -1, dtype=torch.int32, device=dev)
+            self.row_state = torch.full((rows_pad,), -1, dtype=torch.int32, device=dev)
+            self.hist = torch.zeros(len(_host.LADDER) + 2, dtype=torch.int32, device=dev)   # active count per round
             self.key_first = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
             self.key_second = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
             self.n_keys = torch.zeros(1, dtype=torch.int32, device=dev)
-            self.n_active = torch.zeros(1, dtype=torch.int32, device=dev)
             if self.world > 1:
                 self._init_shards()
-        self.rounds = []
+        self._cands = []
         self.packed_ready = False
 
     # ---- multi-GPU plumbing -------------------------------------------------------------------
@@ -129,28 +129,19 @@ class RmsdPruner:
         dev = self.device
         self.gather_index = torch.from_numpy(gidx.reshape(-1)).to(dev)
         self.my_rows = torch.from_numpy(np.minimum(gidx[self.rank], rows_pad - 1)).to(dev)
-        self.loc_mask = torch.zeros(L, dtype=torch.uint8, device=dev)
-        self.loc_keys = torch.full((L,), -1, dtype=torch.int32, device=dev)
-        self.all_mask = torch.empty(self.world * L, dtype=torch.uint8, device=dev)
-        self.all_keys = torch.empty(self.world * L, dtype=torch.int32, device=dev)
-        self.mask_scratch = torch.ones(rows_pad + 1, dtype=torch.uint8, device=dev)
-        self.keys_scratch = torch.full((rows_pad + 1,), -1, dtype=torch.int32, device=dev)
+        self.loc_state = torch.full((L,), -2, dtype=torch.int32, device=dev)
+        self.all_state = torch.empty(self.world * L, dtype=torch.int32, device=dev)
+        self.state_scratch = torch.full((rows_pad + 1,), -2, dtype=torch.int32, device=dev)
 
     def _exchange_round(self):
-        """All-gather this round's per-row verdicts and emitted keys (NCCL over NVLink)."""
+        """All-gather this round's per-row states (verdict + emitted key in one int32) — NCCL over NVLink."""
         import torch.distributed as dist
-        torch = self.torch
-        L = self.n_rb_max * _host.CB
         n_mine = self.n_rb * _host.CB
-        self.loc_mask[:n_mine] = self.mask_bytes[self.my_rows[:n_mine]]
-        self.loc_keys[:n_mine] = self.row_keys[self.my_rows[:n_mine]]
-        dist.all_gather_into_tensor(self.all_mask, self.loc_mask, group=self.group)
-        dist.all_gather_into_tensor(self.all_keys, self.loc_keys, group=self.group)
-        self.mask_scratch.index_copy_(0, self.gather_index, self.all_mask)
-        self.keys_scratch.index_copy_(0, self.gather_index, self.all_keys)
         rows_pad = self.nb_pad * _host.CB
-        self.mask_bytes.copy_(self.mask_scratch[:rows_pad])
-        self.row_keys.copy_(self.keys_scratch[:rows_pad])
+        self.loc_state[:n_mine] = self.row_state[self.my_rows[:n_mine]]
+        dist.all_gather_into_tensor(self.all_state, self.loc_state, group=self.group)
+        self.state_scratch.index_copy_(0, self.gather_index, self.all_state)
+        self.row_state.copy_(self.state_scratch[:rows_pad])
 
     # ---- phases -------------------------------------------------------------------------------
     def pack(self):
@@ -196,42 +187,53 @@ class RmsdPruner:
         self.screen()
         self.verify()
 
-    def _round(self, k: int, cs: int) -> int:
-        L = lib()
-        N = self.N
-        st = stream_ptr()
-        check(L.tsc_elim_cachebits(ptr(self.key_first), ptr(self.key_second), ptr(self.n_keys), N, cs, k,
-                                   ptr(self.cachebits), st), "tsc_elim_cachebits")
-        if self.n_rb:
-            check(L.tsc_elim_round(ptr(self.sim_bits), ptr(self.row_blocks), self.n_rb, ptr(self.active),
-                                   ptr(self.cachebits), N, cs, k, ptr(self.mask_bytes), ptr(self.row_keys), st),
-                  "tsc_elim_round")
-        if self.world > 1:
-            self._exchange_round()
-        check(L.tsc_elim_commit(ptr(self.mask_bytes), ptr(self.row_keys), N, cs, k, ptr(self.active),
-                                ptr(self.key_first), ptr(self.key_second), ptr(self.n_keys), ptr(self.n_active), st),
-              "tsc_elim_commit")
-        return int(self.n_active.item())
+    def _gate_ptr(self, r):
+        import ctypes
+        return ctypes.c_void_p(self.hist.data_ptr() + 4 * r)
 
     def eliminate(self):
-        """The k-ladder (rmsd_pruning.py:186-204).  Returns the boolean mask as a device tensor."""
+        """The k-ladder (rmsd_pruning.py:186-204).  Every candidate round is enqueued without reading
+        anything back; each kernel evaluates the reference's gate on the device (eliminate.cu).
+        Returns the boolean mask as a device tensor."""
         torch = self.torch
         N = self.N
         if N == 0:
             return torch.zeros(0, dtype=torch.bool, device=self.device)
+        if self.M == 0:
+            raise ValueError("prune_conformers_rmsd needs at least one non-hydrogen atom")
+        L = lib()
         with torch.cuda.device(self.device):
-            self.mask_bytes.fill_(1)
-            self.row_keys.fill_(-1)
+            st = stream_ptr()
+            self.row_state.fill_(-1)
             self.n_keys.zero_()
-            if self.M == 0:
-                # no heavy atoms: every covariance is empty -> rmsd 0 for all pairs in the reference
-                raise ValueError("prune_conformers_rmsd needs at least one non-hydrogen atom")
-            # active words from an all-ones mask (k/cs irrelevant: no keys emitted)
-            check(lib().tsc_elim_commit(ptr(self.mask_bytes), ptr(self.row_keys), N, N, 1, ptr(self.active),
-                                        ptr(self.key_first), ptr(self.key_second), ptr(self.n_keys),
-                                        ptr(self.n_active), stream_ptr()), "tsc_elim_commit(init)")
-            self.rounds = _host.run_ladder(N, self._round)
+            self.hist.zero_()
+            # all structures active: active words + hist[0] = N  (no gate, no keys emitted)
+            check(L.tsc_elim_commit(ptr(self.row_state), N, N, 1, ptr(self.active), ptr(self.mask_bytes),
+                                    ptr(self.key_first), ptr(self.key_second), ptr(self.n_keys), None,
+                                    self._gate_ptr(0), st), "tsc_elim_commit(init)")
+            self._cands = [int(k) for k in _host.LADDER if _host.ladder_gate(k, N)]     # n_active <= N
+            for r, k in enumerate(self._cands):
+                cs = _host.chunk_size(N, k)
+                gate, out = self._gate_ptr(r), self._gate_ptr(r + 1)
+                check(L.tsc_elim_cachebits(ptr(self.key_first), ptr(self.key_second), ptr(self.n_keys), N, cs, k,
+                                           ptr(self.cachebits), gate, st), "tsc_elim_cachebits")
+                if self.n_rb:
+                    check(L.tsc_elim_round(ptr(self.sim_bits), ptr(self.row_blocks), self.n_rb, ptr(self.active),
+                                           ptr(self.cachebits), N, cs, k, ptr(self.row_state), gate, st),
+                          "tsc_elim_round")
+                if self.world > 1:
+                    self._exchange_round()
+                check(L.tsc_elim_commit(ptr(self.row_state), N, cs, k, ptr(self.active), ptr(self.mask_bytes),
+                                        ptr(self.key_first), ptr(self.key_second), ptr(self.n_keys), gate, out, st),
+                      "tsc_elim_commit")
             return self.mask_bytes[:N].to(torch.bool)
+
+    @property
+    def rounds(self):
+        """k of every round that actually ran (data dependent) — reads the per-round
+        active counts back from the device."""
+        h = self.hist.tolist()
+        return [k for r, k in enumerate(self._cands) if _host.ladder_gate(k, h[r])]
 
     def run(self):
         self.pack()
