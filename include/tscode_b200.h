@@ -69,8 +69,15 @@ int tsc_rmsd_sim_tiles(const double* packed, const double* G, int64_t N, int32_t
  *   use variant 0 then. */
 int64_t tsc_tf32_pa_floats(int64_t N, int32_t M);
 int64_t tsc_tf32_pb_floats(int64_t N, int32_t M);
+int64_t tsc_tf32_pr_floats(int64_t N, int32_t M);   /* PR: row-major [row][xyz][M] image, rows padded to 128 */
 int tsc_pack_tf32(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M, float* PA,
-                  float* PB, double* G, double* sG, void* stream);
+                  float* PB, float* PR, double* G, double* sG, void* stream);
+/* Same screen with the stationary 128-conformer operand held in TENSOR MEMORY (written once per
+ * work item with tcgen05.st, read by tcgen05.mma [d], [a_tmem], b_desc): removes ~3/4 of the
+ * shared-memory operand traffic that bounded tsc_rmsd_sim_tf32.  Default for variant "tf32". */
+int tsc_rmsd_sim_tf32ts(const float* PA, const float* PB, const float* PR, const double* G,
+                        const double* sG, int64_t N, int32_t M, const int32_t* items, int32_t n_items,
+                        double thr, uint32_t* sim_bits, int32_t grid_ctas, void* stream);
 int tsc_rmsd_sim_tf32(const float* PA, const float* PB, const double* G, const double* sG, int64_t N,
                       int32_t M, const int32_t* items, int32_t n_items, double thr, uint32_t* sim_bits,
                       int32_t grid_ctas, void* stream);

@@ -93,7 +93,7 @@ def test_rmsd_similarity_vs_reference(gpu):
 # ------------------------------------------------------------------------------------------
 # similarity bits (screen + verify) vs oracle, both contraction variants
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("variant", ["dmma", "fma", "tf32"])
+@pytest.mark.parametrize("variant", ["dmma", "fma", "tf32", "tf32ss"])
 @pytest.mark.parametrize("seed,N,M,nc,noise,thr", [
     (0, 1000, 40, 100, 0.05, 0.5),
     (5, 777, 29, 60, 0.05, 0.25),
@@ -103,6 +103,9 @@ def test_rmsd_similarity_vs_reference(gpu):
     (13, 65, 80, 3, 0.2, 0.5),
     (14, 31, 1, 2, 0.05, 0.5),         # single heavy atom
     (15, 130, 20, 4, 0.3, 0.5),
+    (16, 300, 72, 10, 0.15, 0.5),      # exactly nine K blocks: the whole operand lives in TMEM
+    (17, 260, 100, 8, 0.2, 0.5),       # 13 K blocks: nine in TMEM, four from shared memory
+    (18, 140, 7, 5, 0.1, 0.5),         # a single, zero-padded K block
 ])
 def test_sim_bits_vs_oracle(gpu, variant, seed, N, M, nc, noise, thr):
     from oracle import oracle_c

@@ -31,7 +31,7 @@ for seed, N, M, nc, noise, thr in ((0, 257, 40, 20, 0.05, 0.5), (0, 1000, 40, 10
     assert lost == 0
 
 S = gen_ensemble(3, 50000, 80, 5000)
-for variant in ("tf32", "dmma"):
+for variant in ("tf32", "tf32ss", "dmma"):
     pr = RmsdPruner(S, np.full(80, 6), 0.5, variant=variant)
     pr.pack()
     for _ in range(2):

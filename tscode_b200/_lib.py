@@ -26,7 +26,9 @@ SIGNATURES = {
     "tsc_rmsd_sim_tiles": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i64, _f64, _vp, _i32, _i32, _vp]),
     "tsc_tf32_pa_floats": (_i64, [_i64, _i32]),
     "tsc_tf32_pb_floats": (_i64, [_i64, _i32]),
-    "tsc_pack_tf32": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "tsc_tf32_pr_floats": (_i64, [_i64, _i32]),
+    "tsc_pack_tf32": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tsc_rmsd_sim_tf32ts": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _i32, _vp]),
     "tsc_rmsd_sim_tf32": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _i32, _vp]),
     "tsc_rmsd_verify": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp]),
     "tsc_rmsd_pairs": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),

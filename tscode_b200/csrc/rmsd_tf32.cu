@@ -29,43 +29,16 @@
 //                   accumulators of their row, release the TMEM buffer, run the FP64 screen,
 //                   store 16 bits per row
 // Pipelines: A full/empty, B ring full/empty, 3 TMEM accumulator buffers full/empty.
-#include "tsc_common.cuh"
-#include "tsc_math.cuh"
+#include "tf32_common.cuh"
 
 namespace tsc {
-
-constexpr int TF_ROWS = 128;                   // conformers per A panel  (UMMA M)
-constexpr int TF_J = 16;                       // conformers per B tile
-constexpr int TF_N = 3 * TF_J;                 // UMMA N = 48
-constexpr int TF_ACC_COLS = 3 * TF_N;          // 144 TMEM columns per accumulator buffer
-constexpr int TF_NACC = 3;                     // accumulator buffers (432 of 512 columns)
-constexpr int TF_TMEM_COLS = 512;
-constexpr int TF_MAX_BSTAGES = 6;
-constexpr int TF_MAX_GROUPS = 3;               // epilogue groups of 4 warps
-constexpr double TF_EPS = 1.05e-3;             // see header
-constexpr int TF_DEFAULT_CFG = 3;              // see tsc_rmsd_sim_tf32
-
-struct TfParams {
-    const float* PA;          // [panel][a][kc][128][4]
-    const float* PB;          // [jtile][kc][48][4]
-    const double* G;          // (>= njt*16) squared norms, exact FP64
-    const double* sG;         // sqrt(G)
-    const int4* items;        // (panel, jt_begin, jt_count, local_row_block_of_panel)
-    int n_items;
-    int64_t N;
-    int Mp;                   // atoms padded to a multiple of 8
-    int nb_stages;
-    double e_thr;             // M thr^2 (1 + 1e-6)
-    uint16_t* sim_bits16;
-    int64_t W;                // words per sim row
-};
 
 // pack: FP64 AoS -> TF32-rounded FP32 operand images + exact G, sqrt(G)
 __global__ void __launch_bounds__(256) pack_tf32_kernel(const double* __restrict__ S, int64_t N, int A,
                                                         const int32_t* __restrict__ heavy_idx, int M, int Mp,
                                                         int64_t n_rows_pad, float* __restrict__ PA,
-                                                        float* __restrict__ PB, double* __restrict__ G,
-                                                        double* __restrict__ sG) {
+                                                        float* __restrict__ PB, float* __restrict__ PR,
+                                                        double* __restrict__ G, double* __restrict__ sG) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t i = (int64_t)blockIdx.x * 8 + warp;          // one warp per conformer (incl. padding rows)
     if (i >= n_rows_pad) return;
@@ -92,33 +65,13 @@ __global__ void __launch_bounds__(256) pack_tf32_kernel(const double* __restrict
         pb[0] = fx;
         pb[TF_J * 4] = fy;
         pb[2 * TF_J * 4] = fz;
+        float* pr = PR + (size_t)i * 3 * Mp + m;          // row-major image for the TMEM-resident operand
+        pr[0] = fx;
+        pr[Mp] = fy;
+        pr[2 * Mp] = fz;
     }
     g = warp_sum(g);
     if (lane == 0) { G[i] = g; sG[i] = sqrt(g); }
-}
-
-__device__ __forceinline__ void tmem_ld_x8_raw(uint32_t taddr, uint32_t* r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_x4_raw(uint32_t taddr, uint32_t* r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_wait_bind12(uint32_t* r) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11])::"memory");
-}
-// tcgen05.wait::ld carrying 24 registers as in/out operands so that no use can be hoisted above it
-__device__ __forceinline__ void tmem_wait_bind24(uint32_t* r) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
-                   "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),
-                   "+r"(r[22]), "+r"(r[23])::"memory");
 }
 
 template <int NGROUPS, int STEP>   // NGROUPS epilogue groups of 4 warps; STEP columns per TMEM load round (4 or 8)
@@ -243,61 +196,8 @@ __global__ void __launch_bounds__((2 + 4 * NGROUPS) * 32, 1) rmsd_tf32_kernel(co
                     mbar_wait(&t_full[acc], tph);
                     tcgen05_fence_after();
                     const uint32_t d0 = tmem_base + lane_addr + (uint32_t)acc * TF_ACC_COLS;
-                    uint32_t bits = 0;
-#pragma unroll
-                    for (int st = 0; st < TF_J / STEP; st++) {
-                        uint32_t r[9 * STEP];
-#pragma unroll
-                        for (int a = 0; a < 3; a++)
-#pragma unroll
-                            for (int b = 0; b < 3; b++) {
-                                const uint32_t ta = d0 + (uint32_t)(a * TF_N + b * TF_J + st * STEP);
-                                if (STEP == 8) tmem_ld_x8_raw(ta, &r[(3 * a + b) * STEP]);
-                                else tmem_ld_x4_raw(ta, &r[(3 * a + b) * STEP]);
-                            }
-                        if (STEP == 8) { tmem_wait_bind24(&r[0]); tmem_wait_bind24(&r[24]); tmem_wait_bind24(&r[48]); }
-                        else { tmem_wait_bind12(&r[0]); tmem_wait_bind12(&r[12]); tmem_wait_bind12(&r[24]); }
-                        if (st == TF_J / STEP - 1) {  // every value of this buffer is now in registers
-                            tcgen05_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&t_empty[acc]);
-                        }
-                        double lam[STEP];
-                        uint32_t near = 0;            // pairs the FP32 bound cannot exclude
-#pragma unroll
-                        for (int c = 0; c < STEP; c++) {
-                            const double Gj = __shfl_sync(0xffffffffu, gv, st * STEP + c);
-                            const double sGj = __shfl_sync(0xffffffffu, gv, 16 + st * STEP + c);
-                            lam[c] = fma(ci, sGj, fma(hs, Gj, hi));
-                            float f = 0.f;
-#pragma unroll
-                            for (int q = 0; q < 9; q++) { const float v = __uint_as_float(r[q * STEP + c]); f = fmaf(v, v, f); }
-                            const float lf = __double2float_rd(lam[c]) * 0.999999f;        // rounded towards -inf, then lowered
-                            const bool far = (lf > 0.f) && (3.00003f * f <= lf * lf);
-                            near |= (far ? 0u : 1u) << c;
-                        }
-                        if (__any_sync(0xffffffffu, near != 0u)) {
-#pragma unroll
-                            for (int c = 0; c < STEP; c++) {
-                                double S[9];
-#pragma unroll
-                                for (int q = 0; q < 9; q++) S[q] = (double)__uint_as_float(r[q * STEP + c]);
-                                double c2, c1, c0;
-                                key_charpoly(S, c2, c1, c0);
-                                const double l1 = lam[c], l2 = l1 * l1;
-                                const double p2 = fma(12.0, l2, 2.0 * c2);
-                                const double p1 = fma(fma(4.0, l2, 2.0 * c2), l1, c1);
-                                const double p0 = fma(fma(l2 + c2, l1, c1), l1, c0);
-                                const bool excluded = (l1 > 0.0) & (p0 > 0.0) & (p1 > 0.0) & (p2 > 0.0);
-                                if (!excluded && ((near >> c) & 1u)) bits |= 1u << (st * STEP + c);
-                            }
-                        }
-                    }
-                    // validity mask: j > i, j < N   (rows i >= N are not stored)
-                    uint32_t valid = 0xffffu;
-                    if (j0 + 15 >= p.N) valid = (j0 >= p.N) ? 0u : (0xffffu >> (j0 + 16 - p.N));
-                    if (j0 <= i) valid &= (i - j0 >= 15) ? 0u : (0xffffu << (i - j0 + 1));
-                    if (i < p.N && (j0 >> 4) < 2 * p.W) out_row[j0 >> 4] = (uint16_t)(bits & valid);
+                    const uint32_t bits = tf32_epilogue_tile<STEP>(d0, gv, hi, ci, hs, i, j0, p.N, lane, &t_empty[acc]);
+                    if (i < p.N && (j0 >> 4) < 2 * p.W) out_row[j0 >> 4] = (uint16_t)bits;
                 }
                 if (++acc == TF_NACC) { acc = 0; tph ^= 1u; }
             }
@@ -320,13 +220,13 @@ extern "C" int64_t tsc_tf32_pb_floats(int64_t N, int32_t M) {
 }
 
 extern "C" int tsc_pack_tf32(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M, float* PA,
-                             float* PB, double* G, double* sG, void* stream) {
+                             float* PB, float* PR, double* G, double* sG, void* stream) {
     using namespace tsc;
     if (N <= 0 || M <= 0) return 0;
     const int Mp = (M + 7) / 8 * 8;
     const int64_t rows_pad = (N + TF_ROWS - 1) / TF_ROWS * TF_ROWS;
     pack_tf32_kernel<<<(unsigned)((rows_pad + 7) / 8), 256, 0, (cudaStream_t)stream>>>(S, N, A, heavy_idx, M, Mp,
-                                                                                     rows_pad, PA, PB, G, sG);
+                                                                                     rows_pad, PA, PB, PR, G, sG);
     TSC_CHECK_LAUNCH();
     return 0;
 }

@@ -1,0 +1,248 @@
+// rmsd_tf32ts.cu — tcgen05 pre-screen with the stationary operand in TENSOR MEMORY (variant 2, default).
+//
+// Same mathematics and same output contract as rmsd_tf32.cu (read its header first).  What changed,
+// and why: ncu on rmsd_tf32_kernel showed the tensor pipe "busy" 68 % of the time with only 26 % of
+// it doing math — every 128x48x8 MMA re-read its whole 4 KB A block from shared memory (8.7 MAC per
+// operand byte; 16 are needed to stay compute-bound) and the epilogue warps sat waiting for
+// accumulators.  The A panel (128 conformers) is the same for every tile of a work item, so it is
+// now written ONCE per item into TMEM (tcgen05.st, one row per thread) and the MMAs take it from
+// there (tcgen05.mma [d], [a_tmem], b_desc): shared-memory operand traffic drops to the 1.5 KB B
+// block per MMA.
+//
+// TMEM map (512 columns x 128 lanes x 32 bit):
+//   [0, 216)        A: component a, atom k  at column a*8*KT + k      (KT = min(Mp/8, 9) K blocks)
+//   [216, 504)      two accumulator buffers of 144 columns (D_x | D_y | D_z, each 3*16 wide)
+// With M > 72 heavy atoms the K blocks beyond the ninth do not fit next to two accumulator buffers;
+// their A blocks stay in shared memory (bulk-TMA of the tail of the rmsd_tf32.cu panel image) and
+// are multiplied with the shared-memory form of the instruction.
+//
+// Roles (one persistent CTA per SM, 10 warps): warp 0 lane 0 producer (A tail + ring of B tiles),
+// warp 1 TMEM allocation + MMA issue, warps 2..9 epilogue: at the start of a work item they load
+// their rows of the A panel (global -> registers -> tcgen05.st), then alternate over tiles
+// (group g takes accumulator buffer g).
+#include "tf32_common.cuh"
+
+namespace tsc {
+
+constexpr int TS_KT_MAX = 9;                   // K blocks (of 8 atoms) held in TMEM
+constexpr int TS_ACC0 = 3 * 8 * TS_KT_MAX;     // 216: first accumulator column
+constexpr int TS_NACC = 2;
+constexpr int TS_MAX_BSTAGES = 12;
+constexpr int TS_THREADS = 320;
+
+struct TsParams {
+    const float* PA;          // [panel][a][kc][128][4]    (only chunks kc >= 2*KT are read)
+    const float* PB;          // [jtile][kc][48][4]
+    const float* PR;          // [row][a][Mp]              row-major TF32 image for the TMEM part
+    const double* G;
+    const double* sG;
+    const int4* items;        // (panel, jt_begin, jt_count, local_row_block_of_panel)
+    int n_items;
+    int64_t N;
+    int Mp;
+    int nb_stages;
+    double e_thr;
+    uint16_t* sim_bits16;
+    int64_t W;
+};
+
+template <int STEP>
+__global__ void __launch_bounds__(TS_THREADS, 1) rmsd_tf32ts_kernel(const TsParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int nkc = p.Mp / 4;                                  // 16-byte K chunks
+    const int nkb = p.Mp / 8;                                  // K blocks per tile
+    const int KT = nkb < TS_KT_MAX ? nkb : TS_KT_MAX;          // K blocks with A in TMEM
+    const int tail_kc = nkc - 2 * KT;                          // chunks of A kept in shared memory
+    const uint32_t tail_bytes = (uint32_t)tail_kc * TF_ROWS * 16u;      // per component
+    const uint32_t b_bytes = (uint32_t)nkc * TF_N * 16u;
+    unsigned char* smA = smem_raw;                             // [a][tail_kc][128][4]
+    unsigned char* smB = smem_raw + 3u * tail_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + (size_t)p.nb_stages * b_bytes);
+    uint64_t* at_full = bars;                  // A tail landed (TMA)
+    uint64_t* am_full = bars + 1;              // A rows stored to TMEM (8 epilogue warps)
+    uint64_t* a_empty = bars + 2;              // all MMAs of the item retired
+    uint64_t* b_full = bars + 3;
+    uint64_t* b_empty = b_full + TS_MAX_BSTAGES;
+    uint64_t* t_full = b_empty + TS_MAX_BSTAGES;
+    uint64_t* t_empty = t_full + TS_NACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + TS_NACC);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(at_full, 1);
+        mbar_init(am_full, 8);
+        mbar_init(a_empty, 1);
+        for (int s = 0; s < p.nb_stages; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int t = 0; t < TS_NACC; t++) { mbar_init(&t_full[t], 1); mbar_init(&t_empty[t], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TF_TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== producer =====================
+        if (lane == 0) {
+            int bs = 0; uint32_t bph = 0, aph = 0;
+            for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+                const int4 w = p.items[it];
+                if (tail_kc > 0) {
+                    mbar_wait(a_empty, aph ^ 1u);
+                    mbar_arrive_expect_tx(at_full, 3u * tail_bytes);
+                    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.PA) +
+                                               (size_t)w.x * 3u * nkc * TF_ROWS * 16u;
+                    for (int a = 0; a < 3; a++)
+                        bulk_g2s(smA + (size_t)a * tail_bytes,
+                                 src + ((size_t)a * nkc + 2 * KT) * TF_ROWS * 16u, tail_bytes, at_full);
+                    aph ^= 1u;
+                }
+                for (int t = 0; t < w.z; t++) {
+                    mbar_wait(&b_empty[bs], bph ^ 1u);
+                    mbar_arrive_expect_tx(&b_full[bs], b_bytes);
+                    bulk_g2s(smB + (size_t)bs * b_bytes,
+                             reinterpret_cast<const unsigned char*>(p.PB) + (size_t)(w.y + t) * b_bytes, b_bytes,
+                             &b_full[bs]);
+                    if (++bs == p.nb_stages) { bs = 0; bph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(TF_ROWS, TF_N);
+            const uint32_t a_addr = smem_u32(smA);
+            const uint32_t a_lbo = TF_ROWS * 16u, b_lbo = TF_N * 16u;
+            int bs = 0, acc = 0; uint32_t bph = 0, aph = 0, tph = 0;
+            for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+                const int4 w = p.items[it];
+                mbar_wait(am_full, aph);
+                if (tail_kc > 0) mbar_wait(at_full, aph);
+                aph ^= 1u;
+                for (int t = 0; t < w.z; t++) {
+                    mbar_wait(&b_full[bs], bph);
+                    mbar_wait(&t_empty[acc], tph ^ 1u);
+                    tcgen05_fence_after();
+                    const uint32_t b_addr = smem_u32(smB + (size_t)bs * b_bytes);
+                    const uint32_t d0 = tmem_base + TS_ACC0 + (uint32_t)acc * TF_ACC_COLS;
+                    for (int kb = 0; kb < nkb; kb++) {
+                        const uint64_t bd = umma_desc_kmajor(b_addr + (uint32_t)kb * 2u * b_lbo, b_lbo, 128u);
+                        if (kb < KT) {
+#pragma unroll
+                            for (int a = 0; a < 3; a++)
+                                umma_tf32_ts(d0 + (uint32_t)a * TF_N, tmem_base + (uint32_t)(a * 8 * KT + kb * 8), bd,
+                                             idesc, kb > 0 ? 1u : 0u);
+                        } else {
+#pragma unroll
+                            for (int a = 0; a < 3; a++) {
+                                const uint64_t ad = umma_desc_kmajor(
+                                    a_addr + (uint32_t)a * tail_bytes + (uint32_t)(kb - KT) * 2u * a_lbo, a_lbo, 128u);
+                                umma_tf32_ss(d0 + (uint32_t)a * TF_N, ad, bd, idesc, 1u);
+                            }
+                        }
+                    }
+                    umma_commit(&b_empty[bs]);
+                    umma_commit(&t_full[acc]);
+                    if (++bs == p.nb_stages) { bs = 0; bph ^= 1u; }
+                    if (++acc == TS_NACC) { acc = 0; tph ^= 1u; }
+                }
+                umma_commit(a_empty);
+            }
+        }
+    } else {
+        // ===================== epilogue (8 warps = 2 groups; group g owns accumulator buffer g) =====================
+        const int ew = warp - 2;
+        const int grp = ew >> 2;
+        const int quad = warp & 3;
+        const int row_in_panel = quad * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        const double cc = 1.7320508075688772 * TF_EPS;
+        const double hs = 0.5 * (1.0 - 1e-10);
+        uint32_t tph = 0, eph = 0;
+        int64_t tile_seq = 0;
+        for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+            const int4 w = p.items[it];
+            const int64_t i = (int64_t)w.x * TF_ROWS + row_in_panel;
+            // ---- this thread's row of the A panel -> TMEM (group g: atoms [g*4*KT, (g+1)*4*KT) of every component)
+            mbar_wait(a_empty, eph ^ 1u);
+            eph ^= 1u;
+            tcgen05_fence_after();
+            {
+                const float4* src = reinterpret_cast<const float4*>(p.PR + (size_t)i * 3 * p.Mp);
+                for (int a = 0; a < 3; a++)
+                    for (int q = 0; q < KT; q++) {
+                        const float4 v = src[(a * p.Mp + grp * 4 * KT) / 4 + q];
+                        tmem_st_x4(tmem_base + lane_addr + (uint32_t)(a * 8 * KT + grp * 4 * KT + 4 * q),
+                                   __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+                    }
+                tmem_st_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(am_full);
+            }
+            const double Gi = p.G[i];
+            const double hi = fma(hs, Gi, -0.5 * p.e_thr), ci = -cc * p.sG[i];
+            uint16_t* out_row = p.sim_bits16 + ((int64_t)w.w * CB + row_in_panel) * (2 * p.W);
+            for (int t = 0; t < w.z; t++, tile_seq++) {
+                if ((int)(tile_seq & 1) == grp) {
+                    const int64_t j0 = (int64_t)(w.y + t) * TF_J;
+                    const double gv = (lane < 16) ? p.G[j0 + lane] : p.sG[j0 + lane - 16];
+                    mbar_wait(&t_full[grp], tph);
+                    tph ^= 1u;
+                    tcgen05_fence_after();
+                    const uint32_t d0 = tmem_base + lane_addr + TS_ACC0 + (uint32_t)grp * TF_ACC_COLS;
+                    const uint32_t bits = tf32_epilogue_tile<STEP>(d0, gv, hi, ci, hs, i, j0, p.N, lane, &t_empty[grp]);
+                    if (i < p.N && (j0 >> 4) < 2 * p.W) out_row[j0 >> 4] = (uint16_t)bits;
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TF_TMEM_COLS);
+}
+
+}  // namespace tsc
+
+extern "C" int64_t tsc_tf32_pr_floats(int64_t N, int32_t M) {
+    const int64_t Mp = (M + 7) / 8 * 8, rows = (N + tsc::TF_ROWS - 1) / tsc::TF_ROWS * tsc::TF_ROWS;
+    return rows * 3 * Mp;
+}
+
+extern "C" int tsc_rmsd_sim_tf32ts(const float* PA, const float* PB, const float* PR, const double* G,
+                                   const double* sG, int64_t N, int32_t M, const int32_t* items, int32_t n_items,
+                                   double thr, uint32_t* sim_bits, int32_t grid_ctas, void* stream) {
+    using namespace tsc;
+    if (n_items <= 0 || N <= 0) return 0;
+    TsParams p;
+    p.PA = PA; p.PB = PB; p.PR = PR; p.G = G; p.sG = sG;
+    p.items = reinterpret_cast<const int4*>(items);
+    p.n_items = n_items;
+    p.N = N;
+    p.Mp = (M + 7) / 8 * 8;
+    p.e_thr = (double)M * thr * thr * (1.0 + 1e-6);
+    p.sim_bits16 = reinterpret_cast<uint16_t*>(sim_bits);
+    p.W = num_blocks_padded(N);
+    const int nkb = p.Mp / 8, KT = nkb < TS_KT_MAX ? nkb : TS_KT_MAX;
+    const size_t a_bytes = (size_t)3 * (p.Mp / 4 - 2 * KT) * TF_ROWS * 16, b_bytes = (size_t)192 * p.Mp;
+    const size_t budget = 227 * 1024 - 512;
+    if (a_bytes + 2 * b_bytes > budget) return (int)cudaErrorInvalidValue;
+    int nb = (int)((budget - a_bytes) / b_bytes);
+    if (nb > TS_MAX_BSTAGES) nb = TS_MAX_BSTAGES;
+    p.nb_stages = nb;
+    const size_t smem = a_bytes + nb * b_bytes + 512;
+    const bool step8 = grid_ctas == -1;
+    if (grid_ctas < 0) grid_ctas = 0;
+    auto kern = step8 ? rmsd_tf32ts_kernel<8> : rmsd_tf32ts_kernel<4>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int grid = grid_ctas > 0 ? grid_ctas : sms;
+    if (grid > n_items) grid = n_items;
+    kern<<<grid, TS_THREADS, smem, (cudaStream_t)stream>>>(p);
+    TSC_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,147 @@
+// tf32_common.cuh — pieces shared by the two tcgen05 pre-screen kernels (rmsd_tf32.cu: both MMA
+// operands from shared memory; rmsd_tf32ts.cu: the stationary operand held in TMEM).
+#pragma once
+#include "tsc_common.cuh"
+#include "tsc_math.cuh"
+
+namespace tsc {
+
+constexpr int TF_ROWS = 128;                   // conformers per A panel  (UMMA M)
+constexpr int TF_J = 16;                       // conformers per B tile
+constexpr int TF_N = 3 * TF_J;                 // UMMA N = 48
+constexpr int TF_ACC_COLS = 3 * TF_N;          // 144 TMEM columns per accumulator buffer
+constexpr int TF_NACC = 3;                     // accumulator buffers of rmsd_tf32.cu (432 of 512 columns)
+constexpr int TF_TMEM_COLS = 512;
+constexpr int TF_MAX_BSTAGES = 6;
+constexpr int TF_MAX_GROUPS = 3;               // epilogue groups of 4 warps
+constexpr double TF_EPS = 1.05e-3;             // see header
+constexpr int TF_DEFAULT_CFG = 3;              // see tsc_rmsd_sim_tf32
+
+struct TfParams {
+    const float* PA;          // [panel][a][kc][128][4]
+    const float* PB;          // [jtile][kc][48][4]
+    const double* G;          // (>= njt*16) squared norms, exact FP64
+    const double* sG;         // sqrt(G)
+    const int4* items;        // (panel, jt_begin, jt_count, local_row_block_of_panel)
+    int n_items;
+    int64_t N;
+    int Mp;                   // atoms padded to a multiple of 8
+    int nb_stages;
+    double e_thr;             // M thr^2 (1 + 1e-6)
+    uint16_t* sim_bits16;
+    int64_t W;                // words per sim row
+};
+
+__device__ __forceinline__ void tmem_ld_x8_raw(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_x4_raw(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_bind12(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11])::"memory");
+}
+// tcgen05.wait::ld carrying 24 registers as in/out operands so that no use can be hoisted above it
+__device__ __forceinline__ void tmem_wait_bind24(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                   "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),
+                   "+r"(r[22]), "+r"(r[23])::"memory");
+}
+
+__device__ __forceinline__ void tmem_st_x4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]^T : the stationary operand read from tensor memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// One 128 x 16 tile of the epilogue for the thread owning row i: read the 16 x 9 accumulators of
+// this row from TMEM (base address d0, lane already selected), release the buffer (t_empty) once
+// they are in registers, screen the 16 pairs and return the 16 result bits (validity-masked).
+//   gv : lanes 0..15 hold G[j0+lane], lanes 16..31 sqrt(G)[j0+lane-16]   (fetched before the wait)
+//   hi = 0.5 (1-1e-10) G_i - 0.5 e_thr,  ci = -sqrt(3) eps sqrt(G_i),  hs = 0.5 (1-1e-10)
+// Per pair:  lam = threshold eigenvalue lowered by the TF32 error bound (3 FP64 ops);
+//   fast path (FP32, no conversion): Samuelson's bound lambda_max <= sqrt(3) ||S~||_F, i.e. the pair
+//     is excluded if 3 * sum(S~^2) <= lam^2  — decided per STEP columns with one warp vote;
+//   full path (FP64, branch-free): Budan-Fourier sign test on the key-matrix quartic at lam.
+template <int STEP>
+__device__ __forceinline__ uint32_t tf32_epilogue_tile(uint32_t d0, double gv, double hi, double ci, double hs,
+                                                       int64_t i, int64_t j0, int64_t N, int lane,
+                                                       uint64_t* t_empty_bar) {
+    uint32_t bits = 0;
+#pragma unroll
+    for (int st = 0; st < TF_J / STEP; st++) {
+        uint32_t r[9 * STEP];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                const uint32_t ta = d0 + (uint32_t)(a * TF_N + b * TF_J + st * STEP);
+                if (STEP == 8) tmem_ld_x8_raw(ta, &r[(3 * a + b) * STEP]);
+                else tmem_ld_x4_raw(ta, &r[(3 * a + b) * STEP]);
+            }
+        if (STEP == 8) { tmem_wait_bind24(&r[0]); tmem_wait_bind24(&r[24]); tmem_wait_bind24(&r[48]); }
+        else { tmem_wait_bind12(&r[0]); tmem_wait_bind12(&r[12]); tmem_wait_bind12(&r[24]); }
+        if (st == TF_J / STEP - 1) {      // every value of this buffer is now in registers
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty_bar);
+        }
+        double lam[STEP];
+        uint32_t near = 0;                // pairs the FP32 bound cannot exclude
+#pragma unroll
+        for (int c = 0; c < STEP; c++) {
+            const double Gj = __shfl_sync(0xffffffffu, gv, st * STEP + c);
+            const double sGj = __shfl_sync(0xffffffffu, gv, 16 + st * STEP + c);
+            lam[c] = fma(ci, sGj, fma(hs, Gj, hi));
+            float f = 0.f;
+#pragma unroll
+            for (int q = 0; q < 9; q++) { const float v = __uint_as_float(r[q * STEP + c]); f = fmaf(v, v, f); }
+            const float lf = __double2float_rd(lam[c]) * 0.999999f;        // rounded towards -inf, then lowered
+            const bool far = (lf > 0.f) && (3.00003f * f <= lf * lf);
+            near |= (far ? 0u : 1u) << c;
+        }
+        if (__any_sync(0xffffffffu, near != 0u)) {
+#pragma unroll
+            for (int c = 0; c < STEP; c++) {
+                double S[9];
+#pragma unroll
+                for (int q = 0; q < 9; q++) S[q] = (double)__uint_as_float(r[q * STEP + c]);
+                double c2, c1, c0;
+                key_charpoly(S, c2, c1, c0);
+                const double l1 = lam[c], l2 = l1 * l1;
+                const double p2 = fma(12.0, l2, 2.0 * c2);
+                const double p1 = fma(fma(4.0, l2, 2.0 * c2), l1, c1);
+                const double p0 = fma(fma(l2 + c2, l1, c1), l1, c0);
+                const bool excluded = (l1 > 0.0) & (p0 > 0.0) & (p1 > 0.0) & (p2 > 0.0);
+                if (!excluded && ((near >> c) & 1u)) bits |= 1u << (st * STEP + c);
+            }
+        }
+    }
+    // validity mask: j > i, j < N   (rows i >= N are not stored by the caller)
+    uint32_t valid = 0xffffu;
+    if (j0 + 15 >= N) valid = (j0 >= N) ? 0u : (0xffffu >> (j0 + 16 - N));
+    if (j0 <= i) valid &= (i - j0 >= 15) ? 0u : (0xffffu << (i - j0 + 1));
+    return bits & valid;
+}
+
+}  // namespace tsc

@@ -20,7 +20,7 @@ from ._lib import check, lib, ptr, require_cuda, stream_ptr
 
 import functools
 
-VARIANTS = {"dmma": 0, "fma": 1, "tf32": 2}
+VARIANTS = {"dmma": 0, "fma": 1, "tf32": 2, "tf32ss": 3}     # tf32 = A operand in TMEM; tf32ss = both from smem
 
 
 @functools.lru_cache(maxsize=8)
@@ -31,7 +31,7 @@ def _work_lists(N, rank, world, variant, device_str):
     dev = torch.device(device_str)
     rb = _host.owned_row_blocks(N, rank, world)
     out = {"row_blocks_np": rb, "row_blocks": torch.from_numpy(rb).to(dev)}
-    if variant == 2:
+    if variant in (2, 3):
         items = np.ascontiguousarray(_host.build_tf32_items(N, rb))
         out["n_items"], out["items"] = int(items.shape[0]), torch.from_numpy(items).to(dev)
     else:
@@ -80,7 +80,7 @@ class RmsdPruner:
         N, M = self.N, self.M
         self.nb_pad = _host.num_blocks_padded(N)
         self.W = self.nb_pad
-        if self.variant == 2 and M > TF32_MAX_M:
+        if self.variant in (2, 3) and M > TF32_MAX_M:
             self.variant = 0             # documented fallback: FP64 tensor cores (include/tscode_b200.h)
         with torch.cuda.device(self.device):
             dev = self.device
@@ -93,8 +93,9 @@ class RmsdPruner:
             self.packed = torch.empty(max(_host.packed_doubles(N, max(M, 1)), 1), dtype=torch.float64, device=dev)
             n_g = max(self.nb_pad * _host.CB, _host.tf32_rows_padded(N))
             self.G = torch.empty(n_g, dtype=torch.float64, device=dev)
-            if self.variant == 2:
+            if self.variant in (2, 3):
                 L = lib()
+                self.PR = torch.empty(max(L.tsc_tf32_pr_floats(N, max(M, 1)), 1), dtype=torch.float32, device=dev)
                 self.sG = torch.empty(n_g, dtype=torch.float64, device=dev)
                 self.PA = torch.empty(max(L.tsc_tf32_pa_floats(N, max(M, 1)), 1), dtype=torch.float32, device=dev)
                 self.PB = torch.empty(max(L.tsc_tf32_pb_floats(N, max(M, 1)), 1), dtype=torch.float32, device=dev)
@@ -151,9 +152,10 @@ class RmsdPruner:
         with self.torch.cuda.device(self.device):
             check(L.tsc_pack(ptr(self.S), self.N, self.A, ptr(self.heavy_idx), self.M, ptr(self.packed),
                              ptr(self.G), stream_ptr()), "tsc_pack")
-            if self.variant == 2:
+            if self.variant in (2, 3):
                 check(L.tsc_pack_tf32(ptr(self.S), self.N, self.A, ptr(self.heavy_idx), self.M, ptr(self.PA),
-                                      ptr(self.PB), ptr(self.G), ptr(self.sG), stream_ptr()), "tsc_pack_tf32")
+                                      ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG), stream_ptr()),
+                      "tsc_pack_tf32")
         self.packed_ready = True
 
     def screen(self):
@@ -166,6 +168,10 @@ class RmsdPruner:
         with self.torch.cuda.device(self.device):
             self.stats.zero_()
             if self.variant == 2:
+                check(L.tsc_rmsd_sim_tf32ts(ptr(self.PA), ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG), self.N,
+                                            self.M, ptr(self.items), self.n_items, self.thr, ptr(self.sim_bits),
+                                            self.grid_ctas, stream_ptr()), "tsc_rmsd_sim_tf32ts")
+            elif self.variant == 3:
                 check(L.tsc_rmsd_sim_tf32(ptr(self.PA), ptr(self.PB), ptr(self.G), ptr(self.sG), self.N, self.M,
                                           ptr(self.items), self.n_items, self.thr, ptr(self.sim_bits),
                                           self.grid_ctas, stream_ptr()), "tsc_rmsd_sim_tf32")
