@@ -181,6 +181,10 @@ int tsc_rotcorr_apply(const double* Sc, int64_t n, int32_t A, const int64_t* idx
 /* Self-measured FP64 ceilings: kind 0 = DFMA, 1 = DMMA.8x8x4, 2 = both at once (even warps
  * DMMA, odd warps DFMA).  SYNCHRONOUS: times one launch with CUDA events on `stream`.
  *   scratch: >= 1 double (device); flops_out [host] (2): {tensor flop, FMA flop}; ms_out [host]. */
+/* tcgen05.mma issue-rate probe: cycles (SM 0) for reps*nsets*3 kind::tf32 MMAs of 128 x N x 8, each
+ * of the nsets*3 accumulators in its own TMEM region; a_in_tmem selects the TS form. */
+int tsc_bench_umma(int32_t N, int32_t nsets, int32_t reps, int32_t a_in_tmem, long long* cycles_dev,
+                   void* stream);
 int tsc_bench_fp64(int32_t kind, int32_t iters, int32_t ctas_per_sm, int32_t threads, double* scratch,
                    double* flops_out, float* ms_out, void* stream);
 

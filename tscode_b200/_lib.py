@@ -43,6 +43,7 @@ SIGNATURES = {
                                   _vp, _vp, _vp, _vp]),
     "tsc_rotcorr_commit": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "tsc_rotcorr_apply": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tsc_bench_umma": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp]),
     "tsc_bench_fp64": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "tsc_embed_gather": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
 }

@@ -3,7 +3,7 @@
 // MEASURED_PEAKS.json carries HBM and bf16 numbers only; the RMSD kernel is bounded by the FP64
 // pipes, so bench.py measures their ceiling on the same GPU in the same run and quotes
 // fractions "of self-measured FP64 peak" (SURVEY 8(d)).  Not on the product path.
-#include "tsc_common.cuh"
+#include "tf32_common.cuh"
 
 namespace tsc {
 
@@ -106,6 +106,71 @@ extern "C" int tsc_bench_fp64(int32_t kind, int32_t iters, int32_t ctas_per_sm, 
     if (kind == 0) { flops_out[0] = 0; flops_out[1] = nthreads * per * 2.0; }
     else if (kind == 1) { flops_out[0] = nwarps * per * 512.0; flops_out[1] = 0; }
     else { flops_out[0] = (nwarps / 2) * per * 512.0; flops_out[1] = (nthreads / 2) * per * 2.0; }
+    TSC_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---- tcgen05.mma issue-rate probe (measurement aid) -------------------------------------------------
+// One CTA per SM; one thread issues `reps` rounds of (nsets x 3) kind::tf32 MMAs of shape 128 x N x 8,
+// each set accumulating into its own TMEM region, operands from (zeroed) shared memory or TMEM.
+// Answers: how many cycles does one such MMA cost as a function of N and of the distance between
+// MMAs that accumulate into the same region?
+namespace tsc {
+__global__ void __launch_bounds__(128, 1) umma_probe_kernel(int N, int nsets, int reps, int a_in_tmem,
+                                                            long long* cycles_out) {
+    extern __shared__ __align__(1024) unsigned char sm[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (128 * 32 + 256 * 32) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(&slot, 512);
+    fence_proxy_async();
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tb = slot;
+    if (warp == 1 && lane == 0) {
+        const uint32_t idesc = umma_idesc_tf32(128, N);
+        const uint64_t ad = umma_desc_kmajor(smem_u32(sm), 128 * 16, 128);
+        const uint64_t bd = umma_desc_kmajor(smem_u32(sm + 128 * 32), (uint32_t)N * 16, 128);
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; r++)
+            for (int s = 0; s < nsets; s++)
+                for (int a = 0; a < 3; a++) {
+                    const uint32_t d = tb + 64 + (uint32_t)((s * 3 + a) * N);
+                    if (a_in_tmem) {
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
+                                     "r"(tb + (uint32_t)(a * 8)), "l"(bd), "r"(idesc), "r"(1u)
+                                     : "memory");
+                    } else {
+                        umma_tf32_ss(d, ad, bd, idesc, 1u);
+                    }
+                }
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+        const long long t1 = clock64();
+        if (blockIdx.x == 0) cycles_out[0] = t1 - t0;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tb, 512);
+}
+}  // namespace tsc
+
+// cycles for reps * nsets * 3 MMAs (SM 0), N in {16..256}, nsets*3*N + 64 <= 512
+extern "C" int tsc_bench_umma(int32_t N, int32_t nsets, int32_t reps, int32_t a_in_tmem, long long* cycles_dev,
+                              void* stream) {
+    using namespace tsc;
+    if (N % 16 || N < 16 || N > 256 || nsets < 1 || 64 + nsets * 3 * N > 512) return (int)cudaErrorInvalidValue;
+    const size_t smem = 128 * 32 + 256 * 32 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    umma_probe_kernel<<<sms, 128, smem, (cudaStream_t)stream>>>(N, nsets, reps, a_in_tmem, cycles_dev);
     TSC_CHECK_LAUNCH();
     return 0;
 }

@@ -112,8 +112,11 @@ __global__ void __launch_bounds__(TS_THREADS, 1) rmsd_tf32ts_kernel(const TsPara
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(TF_ROWS, TF_N);
-            const uint32_t a_addr = smem_u32(smA);
             const uint32_t a_lbo = TF_ROWS * 16u, b_lbo = TF_N * 16u;
+            const uint64_t bd0 = umma_desc_kmajor(smem_u32(smB), b_lbo, 128u);       // stage 0, K block 0
+            const uint64_t ad0 = umma_desc_kmajor(smem_u32(smA), a_lbo, 128u);       // A tail, component x
+            const uint64_t bd_step = (2u * b_lbo) >> 4, ad_step = (2u * a_lbo) >> 4; // start-address field, 16-byte units
+            const uint32_t a_stride = 8u * KT;                                       // TMEM columns per component
             int bs = 0, acc = 0; uint32_t bph = 0, aph = 0, tph = 0;
             for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
                 const int4 w = p.items[it];
@@ -124,23 +127,29 @@ __global__ void __launch_bounds__(TS_THREADS, 1) rmsd_tf32ts_kernel(const TsPara
                     mbar_wait(&b_full[bs], bph);
                     mbar_wait(&t_empty[acc], tph ^ 1u);
                     tcgen05_fence_after();
-                    const uint32_t b_addr = smem_u32(smB + (size_t)bs * b_bytes);
                     const uint32_t d0 = tmem_base + TS_ACC0 + (uint32_t)acc * TF_ACC_COLS;
-                    for (int kb = 0; kb < nkb; kb++) {
-                        const uint64_t bd = umma_desc_kmajor(b_addr + (uint32_t)kb * 2u * b_lbo, b_lbo, 128u);
-                        if (kb < KT) {
-#pragma unroll
-                            for (int a = 0; a < 3; a++)
-                                umma_tf32_ts(d0 + (uint32_t)a * TF_N, tmem_base + (uint32_t)(a * 8 * KT + kb * 8), bd,
-                                             idesc, kb > 0 ? 1u : 0u);
-                        } else {
-#pragma unroll
-                            for (int a = 0; a < 3; a++) {
-                                const uint64_t ad = umma_desc_kmajor(
-                                    a_addr + (uint32_t)a * tail_bytes + (uint32_t)(kb - KT) * 2u * a_lbo, a_lbo, 128u);
-                                umma_tf32_ss(d0 + (uint32_t)a * TF_N, ad, bd, idesc, 1u);
-                            }
-                        }
+                    // descriptors advance by one add per K block (two 16-byte chunks = 2*LBO bytes)
+                    uint64_t bd = bd0 + (uint64_t)((uint32_t)bs * (b_bytes >> 4));
+                    uint32_t at = tmem_base;
+                    // K block 0 overwrites the accumulators, the others accumulate
+                    umma_tf32_ts_c<false>(d0, at, bd, idesc);
+                    umma_tf32_ts_c<false>(d0 + TF_N, at + a_stride, bd, idesc);
+                    umma_tf32_ts_c<false>(d0 + 2 * TF_N, at + 2 * a_stride, bd, idesc);
+#pragma unroll 4
+                    for (int kb = 1; kb < KT; kb++) {
+                        bd += bd_step;
+                        at += 8;
+                        umma_tf32_ts_c<true>(d0, at, bd, idesc);
+                        umma_tf32_ts_c<true>(d0 + TF_N, at + a_stride, bd, idesc);
+                        umma_tf32_ts_c<true>(d0 + 2 * TF_N, at + 2 * a_stride, bd, idesc);
+                    }
+                    uint64_t ad = ad0;
+                    for (int kb = KT; kb < nkb; kb++) {       // K blocks whose A block stayed in shared memory
+                        bd += bd_step;
+                        umma_tf32_ss_c<true>(d0, ad, bd, idesc);
+                        umma_tf32_ss_c<true>(d0 + TF_N, ad + (tail_bytes >> 4), bd, idesc);
+                        umma_tf32_ss_c<true>(d0 + 2 * TF_N, ad + 2 * (tail_bytes >> 4), bd, idesc);
+                        ad += ad_step;
                     }
                     umma_commit(&b_empty[bs]);
                     umma_commit(&t_full[acc]);

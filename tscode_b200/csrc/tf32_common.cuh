@@ -74,6 +74,34 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
         : "memory");
 }
 
+// Lean issue forms for the MMA loop.  A single thread issues every MMA of the CTA, and a 128x48x8
+// tf32 MMA only occupies the tensor pipe for ~24 cycles, so the instruction stream between two
+// MMAs must stay below that: the accumulate flag is a compile-time constant (ptxas folds the
+// predicate), descriptors are advanced with one integer add (tools/umma_probe.py: a loop that
+// rebuilds descriptors and predicates per MMA issues one MMA every ~130 cycles whatever N is).
+template <bool ACC>
+__device__ __forceinline__ void umma_tf32_ts_c(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "n"(ACC ? 1 : 0)
+        : "memory");
+}
+template <bool ACC>
+__device__ __forceinline__ void umma_tf32_ss_c(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "n"(ACC ? 1 : 0)
+        : "memory");
+}
+
 // One 128 x 16 tile of the epilogue for the thread owning row i: read the 16 x 9 accumulators of
 // this row from TMEM (base address d0, lane already selected), release the buffer (t_empty) once
 // they are in registers, screen the 16 pairs and return the 16 result bits (validity-masked).
