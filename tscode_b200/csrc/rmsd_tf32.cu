@@ -177,26 +177,23 @@ __global__ void __launch_bounds__((2 + 4 * NGROUPS) * 32, 1) rmsd_tf32_kernel(co
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
         const int row_in_panel = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        const double cc = 1.7320508075688772 * TF_EPS;
-        const double hs = 0.5 * (1.0 - 1e-10);
         int acc = 0; uint32_t tph = 0;
         int64_t tile_seq = 0;                         // running tile counter of this CTA
         for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
             const int4 w = p.items[it];
             const int64_t i = (int64_t)w.x * TF_ROWS + row_in_panel;
-            const double Gi = p.G[i];
-            const double hi = fma(hs, Gi, -0.5 * p.e_thr), ci = -cc * p.sG[i];
+            const TfRow row = tf32_row_consts(p.G[i], p.sG[i], p.e_thr);
             uint16_t* out_row = p.sim_bits16 + ((int64_t)w.w * CB + row_in_panel) * (2 * p.W);
             for (int t = 0; t < w.z; t++, tile_seq++) {
                 const bool mine = ((int)(tile_seq % NGROUPS) == grp);
                 if (mine) {
                     const int64_t j0 = (int64_t)(w.y + t) * TF_J;
                     // lanes 0..15 fetch G[j0+lane], lanes 16..31 sqrt(G)[j0+lane-16]; broadcast by shuffle later
-                    const double gv = (lane < 16) ? p.G[j0 + lane] : p.sG[j0 + lane - 16];
+                    const float gvf = tf32_col_term(p.G, p.sG, j0, lane);
                     mbar_wait(&t_full[acc], tph);
                     tcgen05_fence_after();
                     const uint32_t d0 = tmem_base + lane_addr + (uint32_t)acc * TF_ACC_COLS;
-                    const uint32_t bits = tf32_epilogue_tile<STEP>(d0, gv, hi, ci, hs, i, j0, p.N, lane, &t_empty[acc]);
+                    const uint32_t bits = tf32_epilogue_tile<STEP>(d0, gvf, row, p.G, p.sG, i, j0, p.N, lane, &t_empty[acc]);
                     if (i < p.N && (j0 >> 4) < 2 * p.W) out_row[j0 >> 4] = (uint16_t)bits;
                 }
                 if (++acc == TF_NACC) { acc = 0; tph ^= 1u; }

@@ -16,10 +16,10 @@
 // their A blocks stay in shared memory (bulk-TMA of the tail of the rmsd_tf32.cu panel image) and
 // are multiplied with the shared-memory form of the instruction.
 //
-// Roles (one persistent CTA per SM, 10 warps): warp 0 lane 0 producer (A tail + ring of B tiles),
-// warp 1 TMEM allocation + MMA issue, warps 2..9 epilogue: at the start of a work item they load
-// their rows of the A panel (global -> registers -> tcgen05.st), then alternate over tiles
-// (group g takes accumulator buffer g).
+// Roles (one persistent CTA per SM, 2 + 4*NG warps): warp 0 lane 0 producer (A tail + ring of B
+// tiles), warp 1 TMEM allocation + MMA issue, the rest epilogue in NG groups of 4 warps: at the
+// start of a work item they load their rows of the A panel (global -> registers -> tcgen05.st),
+// then group g takes the tiles with index % NG == g (accumulator buffer = tile index % 2).
 #include "tf32_common.cuh"
 
 namespace tsc {
@@ -28,7 +28,7 @@ constexpr int TS_KT_MAX = 9;                   // K blocks (of 8 atoms) held in 
 constexpr int TS_ACC0 = 3 * 8 * TS_KT_MAX;     // 216: first accumulator column
 constexpr int TS_NACC = 2;
 constexpr int TS_MAX_BSTAGES = 12;
-constexpr int TS_THREADS = 320;
+constexpr int TS_DEFAULT_CFG = 2;
 
 struct TsParams {
     const float* PA;          // [panel][a][kc][128][4]    (only chunks kc >= 2*KT are read)
@@ -46,8 +46,8 @@ struct TsParams {
     int64_t W;
 };
 
-template <int STEP>
-__global__ void __launch_bounds__(TS_THREADS, 1) rmsd_tf32ts_kernel(const TsParams p) {
+template <int NG, int STEP>      // NG epilogue groups of 4 warps; STEP columns per TMEM load round
+__global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) rmsd_tf32ts_kernel(const TsParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int nkc = p.Mp / 4;                                  // 16-byte K chunks
     const int nkb = p.Mp / 8;                                  // K blocks per tile
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) rmsd_tf32ts_kernel(const TsPara
 
     if (threadIdx.x == 0) {
         mbar_init(at_full, 1);
-        mbar_init(am_full, 8);
+        mbar_init(am_full, 4 * NG);
         mbar_init(a_empty, 1);
         for (int s = 0; s < p.nb_stages; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int t = 0; t < TS_NACC; t++) { mbar_init(&t_full[t], 1); mbar_init(&t_empty[t], 4); }
@@ -160,48 +160,47 @@ __global__ void __launch_bounds__(TS_THREADS, 1) rmsd_tf32ts_kernel(const TsPara
             }
         }
     } else {
-        // ===================== epilogue (8 warps = 2 groups; group g owns accumulator buffer g) =====================
+        // ===================== epilogue: NG groups of 4 warps, group g takes tiles with index % NG == g =====================
         const int ew = warp - 2;
         const int grp = ew >> 2;
         const int quad = warp & 3;
         const int row_in_panel = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        const double cc = 1.7320508075688772 * TF_EPS;
-        const double hs = 0.5 * (1.0 - 1e-10);
-        uint32_t tph = 0, eph = 0;
+        uint32_t eph = 0;
         int64_t tile_seq = 0;
         for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
             const int4 w = p.items[it];
             const int64_t i = (int64_t)w.x * TF_ROWS + row_in_panel;
-            // ---- this thread's row of the A panel -> TMEM (group g: atoms [g*4*KT, (g+1)*4*KT) of every component)
+            // ---- this thread's row of the A panel -> TMEM; the row's 3*2*KT float4 are dealt round-robin to the groups
             mbar_wait(a_empty, eph ^ 1u);
             eph ^= 1u;
             tcgen05_fence_after();
             {
                 const float4* src = reinterpret_cast<const float4*>(p.PR + (size_t)i * 3 * p.Mp);
-                for (int a = 0; a < 3; a++)
-                    for (int q = 0; q < KT; q++) {
-                        const float4 v = src[(a * p.Mp + grp * 4 * KT) / 4 + q];
-                        tmem_st_x4(tmem_base + lane_addr + (uint32_t)(a * 8 * KT + grp * 4 * KT + 4 * q),
-                                   __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
-                    }
+                for (int q = grp; q < 3 * 2 * KT; q += NG) {
+                    const int a = q / (2 * KT), wi = q - a * 2 * KT;
+                    const float4 v = src[a * (p.Mp / 4) + wi];
+                    tmem_st_x4(tmem_base + lane_addr + (uint32_t)(a * 8 * KT + 4 * wi), __float_as_uint(v.x),
+                               __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+                }
                 tmem_st_wait();
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(am_full);
             }
-            const double Gi = p.G[i];
-            const double hi = fma(hs, Gi, -0.5 * p.e_thr), ci = -cc * p.sG[i];
+            const TfRow row = tf32_row_consts(p.G[i], p.sG[i], p.e_thr);
             uint16_t* out_row = p.sim_bits16 + ((int64_t)w.w * CB + row_in_panel) * (2 * p.W);
             for (int t = 0; t < w.z; t++, tile_seq++) {
-                if ((int)(tile_seq & 1) == grp) {
+                if ((int)(tile_seq % NG) == grp) {
+                    const int acc = (int)(tile_seq & 1);                       // accumulator buffer of this tile
+                    const uint32_t par = (uint32_t)((tile_seq >> 1) & 1);      // parity of that buffer's use count
                     const int64_t j0 = (int64_t)(w.y + t) * TF_J;
-                    const double gv = (lane < 16) ? p.G[j0 + lane] : p.sG[j0 + lane - 16];
-                    mbar_wait(&t_full[grp], tph);
-                    tph ^= 1u;
+                    const float gvf = tf32_col_term(p.G, p.sG, j0, lane);
+                    mbar_wait(&t_full[acc], par);
                     tcgen05_fence_after();
-                    const uint32_t d0 = tmem_base + lane_addr + TS_ACC0 + (uint32_t)grp * TF_ACC_COLS;
-                    const uint32_t bits = tf32_epilogue_tile<STEP>(d0, gv, hi, ci, hs, i, j0, p.N, lane, &t_empty[grp]);
+                    const uint32_t d0 = tmem_base + lane_addr + TS_ACC0 + (uint32_t)acc * TF_ACC_COLS;
+                    const uint32_t bits =
+                        tf32_epilogue_tile<STEP>(d0, gvf, row, p.G, p.sG, i, j0, p.N, lane, &t_empty[acc]);
                     if (i < p.N && (j0 >> 4) < 2 * p.W) out_row[j0 >> 4] = (uint16_t)bits;
                 }
             }
@@ -241,9 +240,13 @@ extern "C" int tsc_rmsd_sim_tf32ts(const float* PA, const float* PB, const float
     if (nb > TS_MAX_BSTAGES) nb = TS_MAX_BSTAGES;
     p.nb_stages = nb;
     const size_t smem = a_bytes + nb * b_bytes + 512;
-    const bool step8 = grid_ctas == -1;
+    // grid_ctas < 0 selects an alternative epilogue configuration (tuning aid): -1 = 2 groups x 8 columns,
+    // -2 = 2 groups x 4, -3 = 3 groups x 4, -4 = 4 groups x 4; default = TS_DEFAULT_CFG
+    const int cfg = grid_ctas < 0 ? -grid_ctas : TS_DEFAULT_CFG;
     if (grid_ctas < 0) grid_ctas = 0;
-    auto kern = step8 ? rmsd_tf32ts_kernel<8> : rmsd_tf32ts_kernel<4>;
+    auto kern = cfg == 1 ? rmsd_tf32ts_kernel<2, 8> : cfg == 2 ? rmsd_tf32ts_kernel<2, 4>
+                : cfg == 3 ? rmsd_tf32ts_kernel<3, 4> : rmsd_tf32ts_kernel<4, 4>;
+    const int threads = (2 + 4 * (cfg <= 2 ? 2 : cfg)) * 32;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;
@@ -251,7 +254,7 @@ extern "C" int tsc_rmsd_sim_tf32ts(const float* PA, const float* PB, const float
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid = grid_ctas > 0 ? grid_ctas : sms;
     if (grid > n_items) grid = n_items;
-    kern<<<grid, TS_THREADS, smem, (cudaStream_t)stream>>>(p);
+    kern<<<grid, threads, smem, (cudaStream_t)stream>>>(p);
     TSC_CHECK_LAUNCH();
     return 0;
 }

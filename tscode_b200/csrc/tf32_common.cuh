@@ -105,14 +105,38 @@ __device__ __forceinline__ void umma_tf32_ss_c(uint32_t d_tmem, uint64_t a_desc,
 // One 128 x 16 tile of the epilogue for the thread owning row i: read the 16 x 9 accumulators of
 // this row from TMEM (base address d0, lane already selected), release the buffer (t_empty) once
 // they are in registers, screen the 16 pairs and return the 16 result bits (validity-masked).
-//   gv : lanes 0..15 hold G[j0+lane], lanes 16..31 sqrt(G)[j0+lane-16]   (fetched before the wait)
-//   hi = 0.5 (1-1e-10) G_i - 0.5 e_thr,  ci = -sqrt(3) eps sqrt(G_i),  hs = 0.5 (1-1e-10)
-// Per pair:  lam = threshold eigenvalue lowered by the TF32 error bound (3 FP64 ops);
-//   fast path (FP32, no conversion): Samuelson's bound lambda_max <= sqrt(3) ||S~||_F, i.e. the pair
-//     is excluded if 3 * sum(S~^2) <= lam^2  — decided per STEP columns with one warp vote;
-//   full path (FP64, branch-free): Budan-Fourier sign test on the key-matrix quartic at lam.
+//
+// Per pair the threshold eigenvalue, lowered by the TF32 error bound, is
+//     lam = 0.5 (1-1e-10) (G_i + G_j) - 0.5 e_thr - sqrt(3) eps sqrt(G_i) sqrt(G_j).
+//   fast path (FP32 only): a guaranteed LOWER bound lf of lam from directed-rounded per-conformer
+//     terms (A_i + B_j - C_i D_j, then scaled by 1 - 1e-6 to cover the two FP32 roundings), and
+//     Samuelson's bound lambda_max <= sqrt(3) ||S~||_F: the pair is excluded if 3.00003 f <= lf^2
+//     with f = sum S~^2 (relative rounding error of f <= 9 * 2^-24) — one warp vote per STEP columns;
+//   full path (FP64, branch-free, taken when some lane of the warp could not exclude a pair):
+//     Budan-Fourier sign test on the key-matrix quartic at lam.
+//   gvf: lanes 0..15 hold B_j = float_rd(hs G[j0+lane]), lanes 16..31 D_j = float_ru(sqrt(G)[j0+lane-16]).
+struct TfRow {                 // per-thread (row i) constants
+    float Af, Cf;              // A_i = float_rd(hs G_i - 0.5 e_thr),  C_i = float_ru(sqrt(3) eps sqrt(G_i))
+    double hi, ci;             // the same in FP64: hi = hs G_i - 0.5 e_thr,  ci = -sqrt(3) eps sqrt(G_i)
+};
+__device__ __forceinline__ TfRow tf32_row_consts(double Gi, double sGi, double e_thr) {
+    const double hs = 0.5 * (1.0 - 1e-10), cc = 1.7320508075688772 * TF_EPS;
+    TfRow r;
+    r.hi = fma(hs, Gi, -0.5 * e_thr);
+    r.ci = -cc * sGi;
+    r.Af = __double2float_rd(r.hi);
+    r.Cf = __double2float_ru(cc * sGi);
+    return r;
+}
+__device__ __forceinline__ float tf32_col_term(const double* __restrict__ G, const double* __restrict__ sG,
+                                               int64_t j0, int lane) {
+    const double hs = 0.5 * (1.0 - 1e-10);
+    return (lane < 16) ? __double2float_rd(hs * G[j0 + lane]) : __double2float_ru(sG[j0 + lane - 16]);
+}
+
 template <int STEP>
-__device__ __forceinline__ uint32_t tf32_epilogue_tile(uint32_t d0, double gv, double hi, double ci, double hs,
+__device__ __forceinline__ uint32_t tf32_epilogue_tile(uint32_t d0, float gvf, const TfRow& row,
+                                                       const double* __restrict__ G, const double* __restrict__ sG,
                                                        int64_t i, int64_t j0, int64_t N, int lane,
                                                        uint64_t* t_empty_bar) {
     uint32_t bits = 0;
@@ -134,29 +158,29 @@ __device__ __forceinline__ uint32_t tf32_epilogue_tile(uint32_t d0, double gv, d
             __syncwarp();
             if (lane == 0) mbar_arrive(t_empty_bar);
         }
-        double lam[STEP];
         uint32_t near = 0;                // pairs the FP32 bound cannot exclude
 #pragma unroll
         for (int c = 0; c < STEP; c++) {
-            const double Gj = __shfl_sync(0xffffffffu, gv, st * STEP + c);
-            const double sGj = __shfl_sync(0xffffffffu, gv, 16 + st * STEP + c);
-            lam[c] = fma(ci, sGj, fma(hs, Gj, hi));
+            const float Bj = __shfl_sync(0xffffffffu, gvf, st * STEP + c);
+            const float Dj = __shfl_sync(0xffffffffu, gvf, 16 + st * STEP + c);
+            const float lf = fmaf(-row.Cf, Dj, row.Af + Bj) * 0.999999f;
             float f = 0.f;
 #pragma unroll
             for (int q = 0; q < 9; q++) { const float v = __uint_as_float(r[q * STEP + c]); f = fmaf(v, v, f); }
-            const float lf = __double2float_rd(lam[c]) * 0.999999f;        // rounded towards -inf, then lowered
             const bool far = (lf > 0.f) && (3.00003f * f <= lf * lf);
             near |= (far ? 0u : 1u) << c;
         }
         if (__any_sync(0xffffffffu, near != 0u)) {
+            const double hs = 0.5 * (1.0 - 1e-10);
 #pragma unroll
             for (int c = 0; c < STEP; c++) {
+                const int64_t j = j0 + st * STEP + c;
                 double S[9];
 #pragma unroll
                 for (int q = 0; q < 9; q++) S[q] = (double)__uint_as_float(r[q * STEP + c]);
                 double c2, c1, c0;
                 key_charpoly(S, c2, c1, c0);
-                const double l1 = lam[c], l2 = l1 * l1;
+                const double l1 = fma(row.ci, sG[j], fma(hs, G[j], row.hi)), l2 = l1 * l1;
                 const double p2 = fma(12.0, l2, 2.0 * c2);
                 const double p1 = fma(fma(4.0, l2, 2.0 * c2), l1, c1);
                 const double p0 = fma(fma(l2 + c2, l1, c1), l1, c0);
