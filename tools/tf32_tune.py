@@ -6,8 +6,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tscode_b200.rmsd_pruning import RmsdPruner
 from tscode_b200.synth import gen_ensemble, mask_digest
 S = gen_ensemble(3, 50000, 80, 5000)
-for variant, cfg, name in (("tf32", -1, "A in TMEM, 2 groups x8"), ("tf32", -2, "A in TMEM, 2 groups x4"), ("tf32", -3, "A in TMEM, 3 groups x4"),
-                           ("tf32", -4, "A in TMEM, 4 groups x4"), ("tf32ss", -3, "A in smem, 2 groups x4")):
+for variant, cfg, name in (("tf32", -1, "A in TMEM, 2 groups x8"), ("tf32", -2, "A in TMEM, 2 groups x4"), ("tf32", -3, "A in TMEM, 4 groups (column halves) x4"),
+                           ("tf32ss", -3, "A in smem, 2 groups x4")):
     pr = RmsdPruner(S, np.full(80, 6), 0.5, variant=variant, grid_ctas=cfg)
     pr.pack()
     for _ in range(2):

@@ -16,10 +16,10 @@
 // their A blocks stay in shared memory (bulk-TMA of the tail of the rmsd_tf32.cu panel image) and
 // are multiplied with the shared-memory form of the instruction.
 //
-// Roles (one persistent CTA per SM, 2 + 4*NG warps): warp 0 lane 0 producer (A tail + ring of B
-// tiles), warp 1 TMEM allocation + MMA issue, the rest epilogue in NG groups of 4 warps: at the
+// Roles (one persistent CTA per SM, 2 + 8*CH warps): warp 0 lane 0 producer (A tail + ring of B
+// tiles), warp 1 TMEM allocation + MMA issue, the rest epilogue in 2*CH groups of 4 warps: at the
 // start of a work item they load their rows of the A panel (global -> registers -> tcgen05.st),
-// then group g takes the tiles with index % NG == g (accumulator buffer = tile index % 2).
+// then group g takes accumulator buffer g / CH and column part g % CH of its tiles.
 #include "tf32_common.cuh"
 
 namespace tsc {
@@ -46,8 +46,9 @@ struct TsParams {
     int64_t W;
 };
 
-template <int NG, int STEP>      // NG epilogue groups of 4 warps; STEP columns per TMEM load round
-__global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) rmsd_tf32ts_kernel(const TsParams p) {
+template <int CH, int STEP>      // 2*CH epilogue groups of 4 warps (CH column parts per tile); STEP columns per TMEM load round
+__global__ void __launch_bounds__((2 + 8 * CH) * 32, 1) rmsd_tf32ts_kernel(const TsParams p) {
+    constexpr int NG = 2 * CH;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int nkc = p.Mp / 4;                                  // 16-byte K chunks
     const int nkb = p.Mp / 8;                                  // K blocks per tile
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) rmsd_tf32ts_kernel(const
         mbar_init(am_full, 4 * NG);
         mbar_init(a_empty, 1);
         for (int s = 0; s < p.nb_stages; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int t = 0; t < TS_NACC; t++) { mbar_init(&t_full[t], 1); mbar_init(&t_empty[t], 4); }
+        for (int t = 0; t < TS_NACC; t++) { mbar_init(&t_full[t], 1); mbar_init(&t_empty[t], 4 * CH); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TF_TMEM_COLS);
@@ -160,13 +161,17 @@ __global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) rmsd_tf32ts_kernel(const
             }
         }
     } else {
-        // ===================== epilogue: NG groups of 4 warps, group g takes tiles with index % NG == g =====================
+        // ===================== epilogue: 2*CH groups of 4 warps =====================
+        // group g works on accumulator buffer g / CH (the tiles with index % 2 == g / CH) and, inside a
+        // tile, on the 16/CH columns of part g % CH.  Every group therefore waits on EVERY use of its
+        // buffer's barrier, which mbarrier parity waits require (a waiter may never fall two phases behind).
         const int ew = warp - 2;
         const int grp = ew >> 2;
+        const int buf = grp / CH, part = grp % CH;
         const int quad = warp & 3;
         const int row_in_panel = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        uint32_t eph = 0;
+        uint32_t eph = 0, tph = 0;
         int64_t tile_seq = 0;
         for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
             const int4 w = p.items[it];
@@ -189,19 +194,21 @@ __global__ void __launch_bounds__((2 + 4 * NG) * 32, 1) rmsd_tf32ts_kernel(const
                 if (lane == 0) mbar_arrive(am_full);
             }
             const TfRow row = tf32_row_consts(p.G[i], p.sG[i], p.e_thr);
-            uint16_t* out_row = p.sim_bits16 + ((int64_t)w.w * CB + row_in_panel) * (2 * p.W);
+            uint8_t* out_row = reinterpret_cast<uint8_t*>(p.sim_bits16) + ((int64_t)w.w * CB + row_in_panel) * (4 * p.W);
             for (int t = 0; t < w.z; t++, tile_seq++) {
-                if ((int)(tile_seq % NG) == grp) {
-                    const int acc = (int)(tile_seq & 1);                       // accumulator buffer of this tile
-                    const uint32_t par = (uint32_t)((tile_seq >> 1) & 1);      // parity of that buffer's use count
+                if ((int)(tile_seq & 1) == buf) {
                     const int64_t j0 = (int64_t)(w.y + t) * TF_J;
                     const float gvf = tf32_col_term(p.G, p.sG, j0, lane);
-                    mbar_wait(&t_full[acc], par);
+                    mbar_wait(&t_full[buf], tph);
+                    tph ^= 1u;
                     tcgen05_fence_after();
-                    const uint32_t d0 = tmem_base + lane_addr + TS_ACC0 + (uint32_t)acc * TF_ACC_COLS;
-                    const uint32_t bits =
-                        tf32_epilogue_tile<STEP>(d0, gvf, row, p.G, p.sG, i, j0, p.N, lane, &t_empty[acc]);
-                    if (i < p.N && (j0 >> 4) < 2 * p.W) out_row[j0 >> 4] = (uint16_t)bits;
+                    const uint32_t d0 = tmem_base + lane_addr + TS_ACC0 + (uint32_t)buf * TF_ACC_COLS;
+                    const uint32_t bits = tf32_epilogue_tile<STEP, TF_J / CH>(d0, gvf, row, p.G, p.sG, i, j0, p.N, lane,
+                                                                            &t_empty[buf], part * (TF_J / CH));
+                    if (i < p.N && (j0 >> 4) < 2 * p.W) {
+                        if (CH == 1) *reinterpret_cast<uint16_t*>(out_row + (j0 >> 3)) = (uint16_t)bits;
+                        else out_row[(j0 >> 3) + part] = (uint8_t)(bits >> (8 * part));
+                    }
                 }
             }
         }
@@ -240,13 +247,13 @@ extern "C" int tsc_rmsd_sim_tf32ts(const float* PA, const float* PB, const float
     if (nb > TS_MAX_BSTAGES) nb = TS_MAX_BSTAGES;
     p.nb_stages = nb;
     const size_t smem = a_bytes + nb * b_bytes + 512;
-    // grid_ctas < 0 selects an alternative epilogue configuration (tuning aid): -1 = 2 groups x 8 columns,
-    // -2 = 2 groups x 4, -3 = 3 groups x 4, -4 = 4 groups x 4; default = TS_DEFAULT_CFG
+    // grid_ctas < 0 selects an alternative epilogue configuration (tuning aid): -1 = 2 groups, 8 columns
+    // per TMEM load round; -2 = 2 groups x 4; -3 = 4 groups (two column halves per tile) x 4;
+    // default = TS_DEFAULT_CFG
     const int cfg = grid_ctas < 0 ? -grid_ctas : TS_DEFAULT_CFG;
     if (grid_ctas < 0) grid_ctas = 0;
-    auto kern = cfg == 1 ? rmsd_tf32ts_kernel<2, 8> : cfg == 2 ? rmsd_tf32ts_kernel<2, 4>
-                : cfg == 3 ? rmsd_tf32ts_kernel<3, 4> : rmsd_tf32ts_kernel<4, 4>;
-    const int threads = (2 + 4 * (cfg <= 2 ? 2 : cfg)) * 32;
+    auto kern = cfg == 1 ? rmsd_tf32ts_kernel<1, 8> : cfg == 2 ? rmsd_tf32ts_kernel<1, 4> : rmsd_tf32ts_kernel<2, 4>;
+    const int threads = (2 + 8 * (cfg <= 2 ? 1 : 2)) * 32;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;

@@ -134,14 +134,16 @@ __device__ __forceinline__ float tf32_col_term(const double* __restrict__ G, con
     return (lane < 16) ? __double2float_rd(hs * G[j0 + lane]) : __double2float_ru(sG[j0 + lane - 16]);
 }
 
-template <int STEP>
+// NCOL columns starting at column C0 of the tile are handled by this thread (NCOL = 16: whole tile).
+template <int STEP, int NCOL = TF_J>
 __device__ __forceinline__ uint32_t tf32_epilogue_tile(uint32_t d0, float gvf, const TfRow& row,
                                                        const double* __restrict__ G, const double* __restrict__ sG,
                                                        int64_t i, int64_t j0, int64_t N, int lane,
-                                                       uint64_t* t_empty_bar) {
+                                                       uint64_t* t_empty_bar, int C0 = 0) {
     uint32_t bits = 0;
 #pragma unroll
-    for (int st = 0; st < TF_J / STEP; st++) {
+    for (int st0 = 0; st0 < NCOL / STEP; st0++) {
+        const int st = st0 + C0 / STEP;
         uint32_t r[9 * STEP];
 #pragma unroll
         for (int a = 0; a < 3; a++)
@@ -153,7 +155,7 @@ __device__ __forceinline__ uint32_t tf32_epilogue_tile(uint32_t d0, float gvf, c
             }
         if (STEP == 8) { tmem_wait_bind24(&r[0]); tmem_wait_bind24(&r[24]); tmem_wait_bind24(&r[48]); }
         else { tmem_wait_bind12(&r[0]); tmem_wait_bind12(&r[12]); tmem_wait_bind12(&r[24]); }
-        if (st == TF_J / STEP - 1) {      // every value of this buffer is now in registers
+        if (st0 == NCOL / STEP - 1) {     // every value this thread needs from the buffer is now in registers
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(t_empty_bar);
