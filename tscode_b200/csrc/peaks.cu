@@ -135,9 +135,11 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int N, int nsets, in
         const uint64_t ad = umma_desc_kmajor(smem_u32(sm), 128 * 16, 128);
         const uint64_t bd = umma_desc_kmajor(smem_u32(sm + 128 * 32), (uint32_t)N * 16, 128);
         const long long t0 = clock64();
+        // nsets < 0: |nsets| accumulators in total (instead of nsets * 3)
+        const int nacc = nsets < 0 ? -nsets : nsets * 3;
         for (int r = 0; r < reps; r++)
-            for (int s = 0; s < nsets; s++)
-                for (int a = 0; a < 3; a++) {
+            for (int s = 0; s < (nsets < 0 ? 1 : nsets); s++)
+                for (int a = 0; a < (nsets < 0 ? nacc : 3); a++) {
                     const uint32_t d = tb + 64 + (uint32_t)((s * 3 + a) * N);
                     if (a_in_tmem) {
                         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -163,7 +165,8 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int N, int nsets, in
 extern "C" int tsc_bench_umma(int32_t N, int32_t nsets, int32_t reps, int32_t a_in_tmem, long long* cycles_dev,
                               void* stream) {
     using namespace tsc;
-    if (N % 16 || N < 16 || N > 256 || nsets < 1 || 64 + nsets * 3 * N > 512) return (int)cudaErrorInvalidValue;
+    if (N % 16 || N < 16 || N > 256 || nsets == 0 || 64 + (nsets < 0 ? -nsets : nsets * 3) * N > 512)
+        return (int)cudaErrorInvalidValue;
     const size_t smem = 128 * 32 + 256 * 32 + 1024;
     cudaError_t e = cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

@@ -84,34 +84,40 @@ __global__ void __launch_bounds__((2 + 8 * CH) * 32, 1) rmsd_tf32ts_kernel(const
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== producer =====================
-        if (lane == 0) {
+        // ===================== producer: warp-uniform control flow, one elected lane issues the copies =====================
+        {
             int bs = 0; uint32_t bph = 0, aph = 0;
             for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
                 const int4 w = p.items[it];
                 if (tail_kc > 0) {
                     mbar_wait(a_empty, aph ^ 1u);
-                    mbar_arrive_expect_tx(at_full, 3u * tail_bytes);
-                    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.PA) +
-                                               (size_t)w.x * 3u * nkc * TF_ROWS * 16u;
-                    for (int a = 0; a < 3; a++)
-                        bulk_g2s(smA + (size_t)a * tail_bytes,
-                                 src + ((size_t)a * nkc + 2 * KT) * TF_ROWS * 16u, tail_bytes, at_full);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(at_full, 3u * tail_bytes);
+                        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.PA) +
+                                                   (size_t)w.x * 3u * nkc * TF_ROWS * 16u;
+                        for (int a = 0; a < 3; a++)
+                            bulk_g2s(smA + (size_t)a * tail_bytes,
+                                     src + ((size_t)a * nkc + 2 * KT) * TF_ROWS * 16u, tail_bytes, at_full);
+                    }
+                    __syncwarp();
                     aph ^= 1u;
                 }
                 for (int t = 0; t < w.z; t++) {
                     mbar_wait(&b_empty[bs], bph ^ 1u);
-                    mbar_arrive_expect_tx(&b_full[bs], b_bytes);
-                    bulk_g2s(smB + (size_t)bs * b_bytes,
-                             reinterpret_cast<const unsigned char*>(p.PB) + (size_t)(w.y + t) * b_bytes, b_bytes,
-                             &b_full[bs]);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&b_full[bs], b_bytes);
+                        bulk_g2s(smB + (size_t)bs * b_bytes,
+                                 reinterpret_cast<const unsigned char*>(p.PB) + (size_t)(w.y + t) * b_bytes, b_bytes,
+                                 &b_full[bs]);
+                    }
+                    __syncwarp();
                     if (++bs == p.nb_stages) { bs = 0; bph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer: the whole warp runs the control flow, one elected lane issues =====================
+        {
             const uint32_t idesc = umma_idesc_tf32(TF_ROWS, TF_N);
             const uint32_t a_lbo = TF_ROWS * 16u, b_lbo = TF_N * 16u;
             const uint64_t bd0 = umma_desc_kmajor(smem_u32(smB), b_lbo, 128u);       // stage 0, K block 0
@@ -128,6 +134,7 @@ __global__ void __launch_bounds__((2 + 8 * CH) * 32, 1) rmsd_tf32ts_kernel(const
                     mbar_wait(&b_full[bs], bph);
                     mbar_wait(&t_empty[acc], tph ^ 1u);
                     tcgen05_fence_after();
+                    if (elect_one()) {
                     const uint32_t d0 = tmem_base + TS_ACC0 + (uint32_t)acc * TF_ACC_COLS;
                     // descriptors advance by one add per K block (two 16-byte chunks = 2*LBO bytes)
                     uint64_t bd = bd0 + (uint64_t)((uint32_t)bs * (b_bytes >> 4));
@@ -154,10 +161,13 @@ __global__ void __launch_bounds__((2 + 8 * CH) * 32, 1) rmsd_tf32ts_kernel(const
                     }
                     umma_commit(&b_empty[bs]);
                     umma_commit(&t_full[acc]);
+                    }
+                    __syncwarp();
                     if (++bs == p.nb_stages) { bs = 0; bph ^= 1u; }
                     if (++acc == TS_NACC) { acc = 0; tph ^= 1u; }
                 }
-                umma_commit(a_empty);
+                if (elect_one()) umma_commit(a_empty);
+                __syncwarp();
             }
         }
     } else {

@@ -87,6 +87,23 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
+// One elected lane of a fully converged warp.  tcgen05.mma / tcgen05.commit / cp.async.bulk are
+// issued through the uniform datapath: inside a plain `if (lane == 0)` region ptxas cannot prove
+// uniformity and wraps EVERY such instruction in an ELECT / BRA.U.ANY retry loop (~90 cycles per
+// MMA measured); a region guarded by elect.sync compiles to straight-line code.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rx;\n\t"
+        ".reg .pred px;\n\t"
+        "elect.sync rx|px, %1;\n\t"
+        "@px mov.s32 %0, 1;\n\t"
+        "}"
+        : "+r"(pred)
+        : "r"(0xffffffffu));
+    return pred != 0;
+}
 // ---- tcgen05 (5th-gen tensor cores, accumulators in TMEM) ------------------------------------
 // Shared-memory matrix descriptor, K-major, no swizzle ("interleave"): 8-row x 16-byte core
 // matrices stored contiguously (128 B); SBO = byte distance between core matrices along M/N,
