@@ -328,7 +328,7 @@ def run_b200(args):
     achieved = flops / (screen_ms * 1e-3) / 1e12
     if args.variant == "tf32":
         peak = mp["bf16_tflops"] / 2.0
-        kname = "rmsd_tf32_kernel"
+        kname = "rmsd_tf32ts_kernel"
         psrc = (f"TF32 dense = half of the {mp_src} cuBLAS bf16 burst figure in MEASURED_PEAKS.json "
                 f"({mp['bf16_tflops']} TFLOP/s); the kernel is epilogue- (FP64 screen) not MMA-bound, see DESIGN.md")
     else:

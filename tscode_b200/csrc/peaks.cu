@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int N, int nsets, in
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tb = slot;
-    if (warp == 1 && lane == 0) {
+    if (warp == 1) {
         const uint32_t idesc = umma_idesc_tf32(128, N);
         const uint64_t ad = umma_desc_kmajor(smem_u32(sm), 128 * 16, 128);
         const uint64_t bd = umma_desc_kmajor(smem_u32(sm + 128 * 32), (uint32_t)N * 16, 128);
@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int N, int nsets, in
             for (int s = 0; s < (nsets < 0 ? 1 : nsets); s++)
                 for (int a = 0; a < (nsets < 0 ? nacc : 3); a++) {
                     const uint32_t d = tb + 64 + (uint32_t)((s * 3 + a) * N);
+                    if (!elect_one()) continue;
                     if (a_in_tmem) {
                         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                                      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
@@ -150,10 +151,11 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int N, int nsets, in
                         umma_tf32_ss(d, ad, bd, idesc, 1u);
                     }
                 }
-        umma_commit(&bar);
+        if (elect_one()) umma_commit(&bar);
+        __syncwarp();
         mbar_wait(&bar, 0);
         const long long t1 = clock64();
-        if (blockIdx.x == 0) cycles_out[0] = t1 - t0;
+        if (blockIdx.x == 0 && lane == 0) cycles_out[0] = t1 - t0;
     }
     tcgen05_fence_before();
     __syncthreads();
