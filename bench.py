@@ -227,7 +227,7 @@ def run_b200(args):
     pinned.copy_(torch.from_numpy(S_host))
     S_pinned_np = pinned.numpy()
     S_dev = pinned.to(dev)
-    pr = RmsdPruner(S_dev, atomnos, thr, variant=args.variant, rank=rank, world=world, device=dev)
+    pr = RmsdPruner(S_dev, atomnos, thr, variant=args.variant, rank=rank, world=world, device=dev, ladder=args.ladder)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -304,7 +304,8 @@ def run_b200(args):
         for it in range(2 + max(2, min(args.steps, 5))):
             barrier()
             t0 = time.perf_counter()
-            p2 = RmsdPruner(pinned, atomnos, thr, variant=args.variant, rank=rank, world=world, device=dev)
+            p2 = RmsdPruner(pinned, atomnos, thr, variant=args.variant, rank=rank, world=world, device=dev,
+                            ladder=args.ladder)
             m2 = p2.run().cpu().numpy()
             torch.cuda.synchronize()
             dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
@@ -326,11 +327,17 @@ def run_b200(args):
     mp, mp_src = measured_peaks()
     flops = 18.0 * M * pairs / world
     achieved = flops / (screen_ms * 1e-3) / 1e12
-    if args.variant == "tf32":
+    if args.variant == "f16":
+        peak = float(mp["bf16_tflops"])
+        kname = "rmsd_ts_kernel<1,4,true>"
+        psrc = (f"16-bit dense tensor peak = the {mp_src} cuBLAS bf16 burst figure in MEASURED_PEAKS.json "
+                f"({mp['bf16_tflops']} TFLOP/s); the kernel issues kind::f16 MMAs of shape 128x48x16, which the "
+                "tensor pipe executes at a fixed ~35-44 cycles each (tools/umma_probe.py), see DESIGN.md")
+    elif args.variant == "tf32":
         peak = mp["bf16_tflops"] / 2.0
-        kname = "rmsd_tf32ts_kernel"
+        kname = "rmsd_ts_kernel<1,4,false>"
         psrc = (f"TF32 dense = half of the {mp_src} cuBLAS bf16 burst figure in MEASURED_PEAKS.json "
-                f"({mp['bf16_tflops']} TFLOP/s); the kernel is epilogue- (FP64 screen) not MMA-bound, see DESIGN.md")
+                f"({mp['bf16_tflops']} TFLOP/s)")
     else:
         peak = max(peaks["dmma"], peaks["dfma"])
         kname = f"rmsd_sim_kernel<{'ConsumerDMMA' if args.variant == 'dmma' else 'ConsumerFMA'}>"
@@ -388,14 +395,15 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(cfg, args, extra={
-                "variant": args.variant, "ladder_rounds": pr.rounds}),
+                "variant": args.variant, "ladder": pr.ladder_used, "ladder_rounds": pr.rounds}),
             "wall_ms_total": wall_ms,
             "phase_ms": {k: statistics.mean(v) for k, v in phase_ms.items()},
             "parity": {"survivors": int(mask_np.sum()), "digest": mask_digest(mask_np),
                        "matches_reference": (mask_digest(mask_np) == cfg["digest"]) if cfg["digest"] else None,
                        **pr.stats_dict()},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clash": clash,
-            "gpu_launches": args.steps * ((5 if args.variant == "tf32" else 4) + 3 * rounds), "clocks": clocks,
+            "gpu_launches": args.steps * ((5 if args.variant in ("tf32", "f16") else 4) +
+                                          (1 if pr.ladder_used == "fused" else 3 * rounds)), "clocks": clocks,
             "fp64_peaks_tflops": peaks}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -408,7 +416,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--variant", default="tf32", choices=["dmma", "fma", "tf32"])
+    ap.add_argument("--variant", default="f16", choices=["dmma", "fma", "tf32", "f16"])
+    ap.add_argument("--ladder", default="fused", choices=["fused", "bitrows"])
     ap.add_argument("--n-conformers", type=int, default=0, help="override N (testing only; invalid as a bench value)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--lazy-n", type=int, default=10000)

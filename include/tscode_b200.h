@@ -70,14 +70,27 @@ int tsc_rmsd_sim_tiles(const double* packed, const double* G, int64_t N, int32_t
 int64_t tsc_tf32_pa_floats(int64_t N, int32_t M);
 int64_t tsc_tf32_pb_floats(int64_t N, int32_t M);
 int64_t tsc_tf32_pr_floats(int64_t N, int32_t M);   /* PR: row-major [row][xyz][M] image, rows padded to 128 */
+int64_t tsc_tf32_ct_floats(int64_t N);               /* CT: [j tile][32] FP32 column terms of the fast path */
 int tsc_pack_tf32(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M, float* PA,
-                  float* PB, float* PR, double* G, double* sG, void* stream);
+                  float* PB, float* PR, double* G, double* sG, float* CT, void* stream);
 /* Same screen with the stationary 128-conformer operand held in TENSOR MEMORY (written once per
  * work item with tcgen05.st, read by tcgen05.mma [d], [a_tmem], b_desc): removes ~3/4 of the
  * shared-memory operand traffic that bounded tsc_rmsd_sim_tf32.  Default for variant "tf32". */
 int tsc_rmsd_sim_tf32ts(const float* PA, const float* PB, const float* PR, const double* G,
-                        const double* sG, int64_t N, int32_t M, const int32_t* items, int32_t n_items,
-                        double thr, uint32_t* sim_bits, int32_t grid_ctas, void* stream);
+                        const double* sG, const float* CT, int64_t N, int32_t M, const int32_t* items,
+                        int32_t n_items, double thr, uint32_t* sim_bits, int32_t grid_ctas, void* stream);
+/* FP16-operand form of the same screen (kind::f16, K = 16 atoms per MMA; FP16 has TF32's 10-bit mantissa,
+ * so the same error bound holds; tsc_pack_f16 zeroes |x| < 2^-14 and widens sqrt(G) accordingly).  Half as
+ * many MMA instructions per tile: default screen of prune_conformers_rmsd for M <= 320 heavy atoms.
+ *   PA, PB, PR: tsc_f16_operand_bytes(N, M) bytes each (atoms padded to a multiple of 16). */
+int64_t tsc_f16_operand_bytes(int64_t N, int32_t M);
+int tsc_pack_f16(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M, void* PA,
+                 void* PB, void* PR, double* G, double* sG, float* CT, void* stream);
+int tsc_rmsd_sim_f16ts(const void* PA, const void* PB, const void* PR, const double* G,
+                       const double* sG, const float* CT, int64_t N, int32_t M, const int32_t* items,
+                       int32_t n_items, double thr, uint32_t* sim_bits, int32_t grid_ctas, void* stream);
+/* Measurement aid: 8*96 int64 of clock64 stamps from the first work item of CTA 0 (NULL = off). */
+void tsc_set_trace_buffer(void* dev_ptr);
 int tsc_rmsd_sim_tf32(const float* PA, const float* PB, const double* G, const double* sG, int64_t N,
                       int32_t M, const int32_t* items, int32_t n_items, double thr, uint32_t* sim_bits,
                       int32_t grid_ctas, void* stream);
@@ -86,9 +99,14 @@ int tsc_rmsd_sim_tf32(const float* PA, const float* PB, const double* G, const d
  * afterwards bit (i,j) == (rmsd < thr and maxdev < 2*thr)  (:75, :95).
  *   row_blocks (n_rb) int32: global block index of each local row block.
  *   stats (4) uint64, accumulated: candidates, confirmed, within 1e-6 A of a threshold,
- *   degenerate optimal rotation. */
+ *   degenerate optimal rotation.
+ *   pair_list (may be NULL): a block of `pair_stride` int32 pairs; element 0 is a header whose
+ *   first int32 is the running pair count (zero it before the first call), confirmed pairs (i, j)
+ *   are appended from element 1 (unordered).  A count > pair_stride - 1 means the list overflowed
+ *   (pairs beyond the capacity are dropped; the bit rows stay complete). */
 int tsc_rmsd_verify(const double* packed, int64_t N, int32_t M, const int32_t* row_blocks,
-                    int32_t n_rb, double thr, uint32_t* sim_bits, uint64_t* stats, void* stream);
+                    int32_t n_rb, double thr, uint32_t* sim_bits, uint64_t* stats, int32_t* pair_list,
+                    int64_t pair_stride, void* stream);
 
 /* Batched rmsd_and_max_numba on explicit pairs: P, Q (n, M, 3) -> rmsd (n), maxdev (n).
  * broadcast_p = 1 compares P[0] with every Q[k] (_rmsd_similarity, rmsd_pruning.py:208-224). */
@@ -115,6 +133,20 @@ int tsc_elim_commit(const int32_t* row_state, int64_t N, int64_t cs, int64_t k,
                     uint32_t* active_words_out, uint8_t* mask_out, int32_t* key_first,
                     int32_t* key_second, int32_t* n_keys, const int32_t* gate, int32_t* n_active_out,
                     void* stream);
+
+/* The whole k-ladder in ONE persistent cooperative launch on the pair lists tsc_rmsd_verify emits
+ * (rmsd_pruning.py:186-204; same masks as the tsc_elim_cachebits/round/commit path).
+ *   lists: n_lists blocks of `stride` int32 pairs laid out as tsc_rmsd_verify writes them (one block
+ *   per rank after an all-gather; every rank runs the kernel on the complete set);
+ *   gate: 20 (rmsd_pruning.py:192);  ws: tsc_elim_fused_ws_words(N) int32 of scratch;
+ *   out: tsc_elim_fused_out_bytes(N) bytes = N mask bytes, padded to a multiple of 4, then 64 int32:
+ *   [0] status (0 done, 1 a pair list overflowed -> use the bit-row kernels, -1 aborted),
+ *   [1] rounds run, [2] survivors, [3] cache keys emitted, [8..8+rounds) the k of every round run.
+ *   Returns cudaErrorInvalidValue for N > ~800 000 (bitmaps are staged in shared memory). */
+int64_t tsc_elim_fused_ws_words(int64_t N);
+int64_t tsc_elim_fused_out_bytes(int64_t N);
+int tsc_elim_fused(const int32_t* lists, int32_t n_lists, int64_t stride, int64_t N, int32_t gate,
+                   int32_t* ws, uint8_t* out, void* stream);
 
 /* ---- compenetration_check / get_embed -------------------------------------------------- */
 /* Fused pose transform + clash screen (embeds.py:116-118 / 713-714 / 841-842).

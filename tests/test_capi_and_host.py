@@ -125,3 +125,19 @@ def test_sqrt_threshold_image(thr):
     rng = np.random.default_rng(0)
     x = thr * thr * (1 + (rng.random(20000) - 0.5) * 1e-14)
     assert np.array_equal(np.sqrt(x) < thr, x < t2)
+
+
+@pytest.mark.parametrize("N,density,seed", [(64, 0.05, 1), (777, 0.002, 2), (1037, 0.01, 3), (2500, 0.0005, 4),
+                                            (45, 0.3, 6), (300, 0.0, 7), (33, 1.0, 8), (1, 0.0, 9), (2, 1.0, 10)])
+def test_pairlist_ladder_model_matches_oracle(N, density, seed):
+    """The pair-list formulation the fused ladder kernel implements (first similar active partner per
+    row by atomicMin, cache bitmap scanned up to it) is the reference ladder."""
+    from oracle import oracle_c
+    rng = np.random.default_rng(seed)
+    sim = np.triu(rng.random((N, N)) < density, 1)
+    ref, _, rounds = oracle_c.prune_heavy(np.zeros((N, 1, 3)), 0.5, sim_bytes=sim.astype(np.uint8))
+    pairs = np.argwhere(sim)
+    rng.shuffle(pairs)
+    mask, ran = _host.ladder_pairlist_model(pairs, N)
+    assert ran == [int(k) for k in rounds]
+    assert np.array_equal(mask, ref)

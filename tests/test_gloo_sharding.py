@@ -103,3 +103,54 @@ def test_two_rank_ladder_matches_single(N, seed):
     ref, _, rounds = oracle_c.prune_heavy(np.zeros((N, 1, 3)), 0.5, sim_bytes=sim.astype(np.uint8))
     assert ran == [int(k) for k in rounds]
     assert np.array_equal(mask, ref)
+
+
+def _worker_pairs(rank, world, port, N, seed, q):
+    """The fused-ladder exchange: every rank emits the similar pairs of the rows it owns into a
+    fixed-capacity block (header = count), ONE all-gather, then the whole ladder runs redundantly
+    on the complete list (host model of elim_fused_kernel)."""
+    sys.path.insert(0, ROOT)
+    from tscode_b200 import _host
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(seed)
+    sim = np.triu(rng.random((N, N)) < 0.004, 1)
+    my_rows = _host.global_rows_of(_host.owned_row_blocks(N, rank, world))
+    my_rows = my_rows[my_rows < N]
+    mine = np.argwhere(sim[my_rows])
+    mine[:, 0] = my_rows[mine[:, 0]]
+    stride = 32 * N // world + 4096 + 1
+    block = torch.zeros((stride, 2), dtype=torch.int32)
+    block[0, 0] = mine.shape[0]
+    block[1:1 + mine.shape[0]] = torch.from_numpy(mine.astype(np.int32))
+    gathered = torch.empty((world * stride, 2), dtype=torch.int32)
+    dist.all_gather_into_tensor(gathered, block)
+    g = gathered.numpy().reshape(world, stride, 2)
+    pairs = np.concatenate([g[r, 1:1 + g[r, 0, 0]] for r in range(world)])
+    assert pairs.shape[0] == int(sim.sum())
+    mask, ran = _host.ladder_pairlist_model(pairs, N)
+    if rank == 0:
+        q.put((mask, ran))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("N,seed", [(700, 3), (1037, 4)])
+def test_two_rank_pair_list_exchange_matches_single(N, seed):
+    from oracle import oracle_c
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + seed
+    procs = [ctx.Process(target=_worker_pairs, args=(r, 2, port, N, seed, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    mask, ran = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(seed)
+    sim = np.triu(rng.random((N, N)) < 0.004, 1)
+    ref, _, rounds = oracle_c.prune_heavy(np.zeros((N, 1, 3)), 0.5, sim_bytes=sim.astype(np.uint8))
+    assert ran == [int(k) for k in rounds]
+    assert np.array_equal(mask, ref)

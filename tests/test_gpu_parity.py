@@ -93,7 +93,7 @@ def test_rmsd_similarity_vs_reference(gpu):
 # ------------------------------------------------------------------------------------------
 # similarity bits (screen + verify) vs oracle, both contraction variants
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("variant", ["dmma", "fma", "tf32", "tf32ss"])
+@pytest.mark.parametrize("variant", ["dmma", "fma", "tf32", "tf32ss", "f16"])
 @pytest.mark.parametrize("seed,N,M,nc,noise,thr", [
     (0, 1000, 40, 100, 0.05, 0.5),
     (5, 777, 29, 60, 0.05, 0.25),
@@ -157,6 +157,52 @@ def test_elimination_vs_oracle_on_random_bits(gpu, N, density, seed):
     assert np.array_equal(mask, ref), (mask.sum(), ref.sum())
 
 
+@pytest.mark.parametrize("N,density,seed", [(64, 0.05, 1), (777, 0.002, 2), (1037, 0.01, 3), (2500, 0.0005, 4),
+                                            (3001, 0.003, 5), (45, 0.3, 6), (1000, 0.0, 7), (33, 1.0, 8), (1, 0.0, 9),
+                                            (2, 1.0, 10), (20011, 0.0002, 11)])
+def test_fused_ladder_vs_oracle_on_random_pairs(gpu, N, density, seed):
+    """elim_fused_kernel (one cooperative launch, pair lists) against the oracle ladder."""
+    from oracle import oracle_c
+    from tscode_b200.rmsd_pruning import RmsdPruner
+    rng = np.random.default_rng(seed)
+    sim = np.triu(rng.random((N, N)) < density, 1)
+    pairs = np.argwhere(sim)
+    rng.shuffle(pairs)
+    pr = RmsdPruner(rng.normal(size=(N, 4, 3)), np.full(4, 6), 0.5, pair_cap=max(pairs.shape[0], 1))
+    pr.set_pairs(pairs)
+    mask = pr.eliminate().cpu().numpy()
+    assert pr.ladder_used == "fused"
+    ref, _, rounds = oracle_c.prune_heavy(np.zeros((N, 1, 3)), 0.5, sim_bytes=sim.astype(np.uint8))
+    assert pr.rounds == [int(k) for k in rounds]
+    assert np.array_equal(mask, ref), (mask.sum(), ref.sum())
+
+
+def test_fused_ladder_overflow_falls_back_to_bitrows(gpu):
+    """A pair list that overflows its capacity must not change the result: the bit rows take over."""
+    from oracle import oracle_c
+    from tscode_b200.rmsd_pruning import RmsdPruner
+    from tscode_b200.synth import gen_ensemble
+    S = gen_ensemble(5, 1500, 30, 20)                     # 20 clusters -> ~56k similar pairs
+    at = np.full(30, 6)
+    ref_out, ref = oracle_c.prune_conformers_rmsd(S, at, 0.5)
+    small = RmsdPruner(S, at, 0.5, pair_cap=100)
+    m1 = small.run().cpu().numpy()
+    assert small.ladder_used == "bitrows" and small.stats_dict()["confirmed"] > 100
+    big = RmsdPruner(S, at, 0.5, pair_cap=200_000)
+    m2 = big.run().cpu().numpy()
+    assert big.ladder_used == "fused"
+    forced = RmsdPruner(S, at, 0.5, ladder="bitrows")
+    m3 = forced.run().cpu().numpy()
+    assert np.array_equal(m1, ref) and np.array_equal(m2, ref) and np.array_equal(m3, ref)
+    assert small.rounds == big.rounds == forced.rounds
+    # the emitted list is exactly the set bits of the verified rows
+    n = int(big.pair_list[0, 0])
+    got = set(map(tuple, big.pair_list[1:1 + n].cpu().numpy().tolist()))
+    rows, dense = big.sim_rows_dense()
+    want = set((int(rows[a]), int(b)) for a, b in np.argwhere(dense) if rows[a] < big.N)
+    assert got == want and n == big.stats_dict()["confirmed"]
+
+
 # ------------------------------------------------------------------------------------------
 # prune_conformers_rmsd end to end vs the live reference's masks
 # ------------------------------------------------------------------------------------------
@@ -181,7 +227,7 @@ _big = json.load(open(os.path.join(GOLDEN, "prune_masks_big.json")))["rows"]
 
 
 @pytest.mark.parametrize("r", _big, ids=[f"N{r['N']}" for r in _big])
-@pytest.mark.parametrize("variant", ["dmma", "fma", "tf32"])
+@pytest.mark.parametrize("variant", ["dmma", "fma", "tf32", "f16"])
 def test_prune_big_digest_vs_reference(gpu, r, variant):
     """BASELINE configs[2] at full size: the 50k x 80 mask must equal the live reference's."""
     from tscode_b200.rmsd_pruning import RmsdPruner

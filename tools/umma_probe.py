@@ -6,8 +6,8 @@ from tscode_b200._lib import lib, check, ptr, stream_ptr
 out = torch.zeros(2, dtype=torch.int64, device="cuda")
 reps = 2000
 for tm in (0, 1):
-    for N, nsets in ((16, -1), (16, -2), (16, -8), (48, -1), (48, -3), (48, -9), (96, -1), (96, -2), (96, -4), (144, -1), (144, -3),
-                     (192, -1), (192, -2), (256, -1)):
+    for N, nsets in ((16, -3), (32, -3), (48, -1), (48, -3), (48, -6), (48, -9), (64, -3), (64, -6), (80, -3), (96, -3), (128, -3),
+                     (144, -3), (192, -2), (256, -1)):
         check(lib().tsc_bench_umma(N, nsets, reps, tm, ptr(out), stream_ptr()), "umma"); torch.cuda.synchronize()
         check(lib().tsc_bench_umma(N, nsets, reps, tm, ptr(out), stream_ptr()), "umma"); torch.cuda.synchronize()
         cyc = int(out[0].item()); n = reps * (-nsets if nsets < 0 else nsets * 3)

@@ -132,3 +132,63 @@ def sqrt_threshold_image(thresh: float) -> float:
     while math.sqrt(x) < thresh:
         x = math.nextafter(x, math.inf)
     return x
+
+
+def ladder_pairlist_model(pairs, N: int, gate: int = 20):
+    """Host model of the fused ladder kernel (eliminate.cu, elim_fused_kernel): the k-ladder of
+    rmsd_pruning.py:186-204 driven by an unordered list of similar pairs (i < j) instead of a
+    similarity matrix.  Same phases as the kernel; used by the CPU tests to pin the formulation
+    against the oracle.  Returns (mask, rounds_run)."""
+    pairs = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
+    INF = np.iinfo(np.int64).max
+    active = np.ones(N, bool)
+    keys_f, keys_s = np.zeros(0, np.int64), np.zeros(0, np.int64)
+    rounds = []
+    idx = np.arange(N, dtype=np.int64)
+    for k in LADDER:
+        n_active = int(active.sum())
+        if not ladder_gate(k, n_active, gate):
+            continue
+        k = int(k)
+        cs = chunk_size(N, k)
+        if cs > 0:
+            c = np.minimum(idx // cs, k - 1)
+            first = c * cs
+            last = np.where(c == k - 1, N, first + cs)
+        else:
+            first = np.zeros(N, np.int64)
+            last = np.full(N, N, np.int64)
+        # phase A: cache bitmap of this round's chunking, first similar active partner inside the chunk
+        cb = np.zeros(N + 64, bool)
+        if keys_f.size:
+            if cs > 0:
+                ok = (keys_f % cs == 0) & (keys_f // cs < k)
+                kl = np.where(keys_f // cs == k - 1, N, keys_f + cs)
+            else:
+                ok = keys_f == 0
+                kl = np.full(keys_f.shape, N)
+            ok &= keys_s < kl
+            cb[keys_s[ok]] = True
+        first_sim = np.full(N, INF)
+        if pairs.size:
+            i, j = pairs[:, 0], pairs[:, 1]
+            ok = active[i] & active[j] & (j < last[i])
+            np.minimum.at(first_sim, i[ok], j[ok])
+        # phase B
+        new_active = active.copy()
+        nf, ns = [], []
+        for r in np.flatnonzero(active):
+            js = first_sim[r]
+            limit = js if js != INF else last[r] - 1          # inclusive
+            hit = False
+            if cb.any() and r + 1 <= limit:
+                jj = np.arange(r + 1, limit + 1)
+                hit = bool(np.any(active[jj] & cb[first[r] + jj - r]))
+            if not hit and js != INF:
+                new_active[r] = False
+                nf.append(first[r]); ns.append(first[r] + js - r)
+        keys_f = np.concatenate([keys_f, np.asarray(nf, np.int64)])
+        keys_s = np.concatenate([keys_s, np.asarray(ns, np.int64)])
+        active = new_active
+        rounds.append(k)
+    return active, rounds

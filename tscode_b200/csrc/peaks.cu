@@ -134,24 +134,28 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int N, int nsets, in
         const uint32_t idesc = umma_idesc_tf32(128, N);
         const uint64_t ad = umma_desc_kmajor(smem_u32(sm), 128 * 16, 128);
         const uint64_t bd = umma_desc_kmajor(smem_u32(sm + 128 * 32), (uint32_t)N * 16, 128);
-        const long long t0 = clock64();
         // nsets < 0: |nsets| accumulators in total (instead of nsets * 3)
         const int nacc = nsets < 0 ? -nsets : nsets * 3;
-        for (int r = 0; r < reps; r++)
-            for (int s = 0; s < (nsets < 0 ? 1 : nsets); s++)
-                for (int a = 0; a < (nsets < 0 ? nacc : 3); a++) {
-                    const uint32_t d = tb + 64 + (uint32_t)((s * 3 + a) * N);
-                    if (!elect_one()) continue;
+        const long long t0 = clock64();
+        if (elect_one()) {
+            // straight-line issue, like the screen kernel: groups of `nacc` MMAs into distinct accumulators
+            for (int r = 0; r < reps; r++) {
+#pragma unroll 1
+                for (int a0 = 0; a0 < nacc; a0 += 3) {
+                    const uint32_t d = tb + 64 + (uint32_t)(a0 * N);
                     if (a_in_tmem) {
-                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
-                                     "r"(tb + (uint32_t)(a * 8)), "l"(bd), "r"(idesc), "r"(1u)
-                                     : "memory");
+                        umma_tf32_ts_c<true>(d, tb, bd, idesc);
+                        if (a0 + 1 < nacc) umma_tf32_ts_c<true>(d + N, tb + 8, bd, idesc);
+                        if (a0 + 2 < nacc) umma_tf32_ts_c<true>(d + 2 * N, tb + 16, bd, idesc);
                     } else {
-                        umma_tf32_ss(d, ad, bd, idesc, 1u);
+                        umma_tf32_ss_c<true>(d, ad, bd, idesc);
+                        if (a0 + 1 < nacc) umma_tf32_ss_c<true>(d + N, ad, bd, idesc);
+                        if (a0 + 2 < nacc) umma_tf32_ss_c<true>(d + 2 * N, ad, bd, idesc);
                     }
                 }
-        if (elect_one()) umma_commit(&bar);
+            }
+            umma_commit(&bar);
+        }
         __syncwarp();
         mbar_wait(&bar, 0);
         const long long t1 = clock64();

@@ -29,6 +29,7 @@
 //                   accumulators of their row, release the TMEM buffer, run the FP64 screen,
 //                   store 16 bits per row
 // Pipelines: A full/empty, B ring full/empty, 3 TMEM accumulator buffers full/empty.
+#include <cuda_fp16.h>
 #include "tf32_common.cuh"
 
 namespace tsc {
@@ -38,7 +39,8 @@ __global__ void __launch_bounds__(256) pack_tf32_kernel(const double* __restrict
                                                         const int32_t* __restrict__ heavy_idx, int M, int Mp,
                                                         int64_t n_rows_pad, float* __restrict__ PA,
                                                         float* __restrict__ PB, float* __restrict__ PR,
-                                                        double* __restrict__ G, double* __restrict__ sG) {
+                                                        double* __restrict__ G, double* __restrict__ sG,
+                                                        float* __restrict__ CT) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t i = (int64_t)blockIdx.x * 8 + warp;          // one warp per conformer (incl. padding rows)
     if (i >= n_rows_pad) return;
@@ -71,7 +73,78 @@ __global__ void __launch_bounds__(256) pack_tf32_kernel(const double* __restrict
         pr[2 * Mp] = fz;
     }
     g = warp_sum(g);
-    if (lane == 0) { G[i] = g; sG[i] = sqrt(g); }
+    if (lane == 0) {
+        const double sg = sqrt(g);
+        G[i] = g; sG[i] = sg;
+        if (CT) {       // FP32 column terms of the Samuelson fast path, directed roundings (tf32_common.cuh)
+            CT[jt * 32 + jj] = __double2float_rd(0.5 * (1.0 - 1e-10) * g);
+            CT[jt * 32 + 16 + jj] = __double2float_ru(sg);
+        }
+    }
+}
+
+// pack, FP16 form: the same three images with 8 FP16 values per 16-byte K chunk (kind::f16, K = 16 per MMA;
+// atoms padded to a multiple of 16).  FP16 keeps TF32's 10-bit mantissa (relative rounding error 2^-11) but
+// has a 5-bit exponent: |x| >= 65520 becomes inf (the pair then fails every exclusion test, becomes a
+// candidate and is decided exactly by the verify kernel), and values below the smallest normal 2^-14 are
+// set to ZERO here, explicitly, so that no subnormal ever reaches the tensor core; their absolute error
+// (<= 2^-14 each) enters the bound through sqrt(G)' = sqrt(G) + alpha sqrt(T), T = number of zeroed
+// coordinates of the conformer, alpha = 2^-14 (1 + 2^-10) / eps:
+//   ||S~ - S||_F <= 2 * 2^-11 (1 + 2^-11) sqrt(G_i G_j) + 2^-14 (1 + 2^-11) (sqrt(T_i G_j) + sqrt(G_i T_j))
+//                <= eps sqrt(G_i)' sqrt(G_j)'                      (eps = 1.05e-3 as for TF32)
+__global__ void __launch_bounds__(256) pack_f16_kernel(const double* __restrict__ S, int64_t N, int A,
+                                                       const int32_t* __restrict__ heavy_idx, int M, int Mp,
+                                                       int64_t n_rows_pad, __half* __restrict__ PA,
+                                                       __half* __restrict__ PB, __half* __restrict__ PR,
+                                                       double* __restrict__ G, double* __restrict__ sG,
+                                                       float* __restrict__ CT) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * 8 + warp;          // one warp per conformer (incl. padding rows)
+    if (i >= n_rows_pad) return;
+    const bool live = i < N;
+    const double* src = S + (live ? i : 0) * (int64_t)A * 3;
+    const int nkc = Mp / 8;
+    const int64_t panel = i / TF_ROWS, r = i % TF_ROWS;
+    const int64_t jt = i / TF_J, jj = i % TF_J;
+    double g = 0.0;
+    int tiny = 0;
+    const double fmin_normal = 6.103515625e-05;                 // 2^-14
+    for (int m = lane; m < Mp; m += 32) {
+        double x = 0.0, y = 0.0, z = 0.0;
+        if (live && m < M) {
+            const double* a = src + (int64_t)heavy_idx[m] * 3;
+            x = a[0]; y = a[1]; z = a[2];
+            g = fma(x, x, fma(y, y, fma(z, z, g)));
+        }
+        tiny += (x != 0.0 && fabs(x) < fmin_normal) + (y != 0.0 && fabs(y) < fmin_normal) +
+                (z != 0.0 && fabs(z) < fmin_normal);
+        const __half hx = fabs(x) < fmin_normal ? __float2half_rn(0.f) : __double2half(x);
+        const __half hy = fabs(y) < fmin_normal ? __float2half_rn(0.f) : __double2half(y);
+        const __half hz = fabs(z) < fmin_normal ? __float2half_rn(0.f) : __double2half(z);
+        const int kc = m >> 3, e = m & 7;
+        __half* pa = PA + (((panel * 3) * nkc + kc) * TF_ROWS + r) * 8 + e;
+        pa[0] = hx;
+        pa[(int64_t)nkc * TF_ROWS * 8] = hy;
+        pa[(int64_t)2 * nkc * TF_ROWS * 8] = hz;
+        __half* pb = PB + ((jt * nkc + kc) * TF_N + jj) * 8 + e;
+        pb[0] = hx;
+        pb[TF_J * 8] = hy;
+        pb[2 * TF_J * 8] = hz;
+        __half* pr = PR + (size_t)i * 3 * Mp + m;           // row-major image for the TMEM-resident operand
+        pr[0] = hx;
+        pr[Mp] = hy;
+        pr[2 * Mp] = hz;
+    }
+    g = warp_sum(g);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tiny += __shfl_xor_sync(0xffffffffu, tiny, o);
+    if (lane == 0) {
+        const double alpha = 6.103515625e-05 * (1.0 + 9.765625e-4) / TF_EPS;
+        const double sg = sqrt(g) + alpha * sqrt((double)tiny);
+        G[i] = g; sG[i] = sg;
+        CT[jt * 32 + jj] = __double2float_rd(0.5 * (1.0 - 1e-10) * g);
+        CT[jt * 32 + 16 + jj] = __double2float_ru(sg);
+    }
 }
 
 template <int NGROUPS, int STEP>   // NGROUPS epilogue groups of 4 warps; STEP columns per TMEM load round (4 or 8)
@@ -217,13 +290,31 @@ extern "C" int64_t tsc_tf32_pb_floats(int64_t N, int32_t M) {
 }
 
 extern "C" int tsc_pack_tf32(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M, float* PA,
-                             float* PB, float* PR, double* G, double* sG, void* stream) {
+                             float* PB, float* PR, double* G, double* sG, float* CT, void* stream) {
     using namespace tsc;
     if (N <= 0 || M <= 0) return 0;
     const int Mp = (M + 7) / 8 * 8;
     const int64_t rows_pad = (N + TF_ROWS - 1) / TF_ROWS * TF_ROWS;
     pack_tf32_kernel<<<(unsigned)((rows_pad + 7) / 8), 256, 0, (cudaStream_t)stream>>>(S, N, A, heavy_idx, M, Mp,
-                                                                                     rows_pad, PA, PB, PR, G, sG);
+                                                                                     rows_pad, PA, PB, PR, G, sG, CT);
+    TSC_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int64_t tsc_f16_operand_bytes(int64_t N, int32_t M) {       // size of each of PA, PB, PR
+    const int64_t Mp = (M + 15) / 16 * 16, rows = (N + tsc::TF_ROWS - 1) / tsc::TF_ROWS * tsc::TF_ROWS;
+    return rows * 3 * Mp * 2;
+}
+
+extern "C" int tsc_pack_f16(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M, void* PA,
+                            void* PB, void* PR, double* G, double* sG, float* CT, void* stream) {
+    using namespace tsc;
+    if (N <= 0 || M <= 0) return 0;
+    const int Mp = (M + 15) / 16 * 16;
+    const int64_t rows_pad = (N + TF_ROWS - 1) / TF_ROWS * TF_ROWS;
+    pack_f16_kernel<<<(unsigned)((rows_pad + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        S, N, A, heavy_idx, M, Mp, rows_pad, reinterpret_cast<__half*>(PA), reinterpret_cast<__half*>(PB),
+        reinterpret_cast<__half*>(PR), G, sG, CT);
     TSC_CHECK_LAUNCH();
     return 0;
 }

@@ -30,28 +30,37 @@ constexpr int TS_NACC = 2;
 constexpr int TS_MAX_BSTAGES = 12;
 constexpr int TS_DEFAULT_CFG = 2;
 
+// Operand images are addressed in 16-byte K chunks: 4 TF32 values (kind::tf32, K = 8 per MMA) or
+// 8 FP16 values (kind::f16, K = 16 per MMA).  FP16 has the same 10-bit mantissa as TF32, so the error
+// bound of rmsd_tf32.cu carries over (pack zeroes |x| < 2^-14 itself and widens sqrt(G) for it), while
+// every instruction covers twice as many atoms: the MMA warp, which a clock64 trace showed to be the
+// limit (35-44 cycles per 128x48 MMA whatever K is, tools/umma_probe.py), issues half as many.
 struct TsParams {
-    const float* PA;          // [panel][a][kc][128][4]    (only chunks kc >= 2*KT are read)
-    const float* PB;          // [jtile][kc][48][4]
-    const float* PR;          // [row][a][Mp]              row-major TF32 image for the TMEM part
+    const unsigned char* PA;  // [panel][a][kc][128][16 B]    (only chunks kc >= 2*KT are read)
+    const unsigned char* PB;  // [jtile][kc][48][16 B]
+    const unsigned char* PR;  // [row][a][nkc][16 B]          row-major image for the TMEM part
     const double* G;
     const double* sG;
+    const float* CT;          // [jtile][32]: 16 x float_rd(hs G_j), 16 x float_ru(sqrt(G_j))  (pack_tf32)
     const int4* items;        // (panel, jt_begin, jt_count, local_row_block_of_panel)
     int n_items;
     int64_t N;
-    int Mp;
+    int nkc;                  // 16-byte K chunks per conformer and component
     int nb_stages;
     double e_thr;
     uint16_t* sim_bits16;
     int64_t W;
+    long long* trace;         // measurement aid (tsc_set_trace_buffer): clock64 stamps of CTA 0's first item, or NULL
 };
 
-template <int CH, int STEP>      // 2*CH epilogue groups of 4 warps (CH column parts per tile); STEP columns per TMEM load round
-__global__ void __launch_bounds__((2 + 8 * CH) * 32, 1) rmsd_tf32ts_kernel(const TsParams p) {
+constexpr int TS_TRACE_TILES = 96;    // tiles of the first item that are stamped (8 slots each)
+
+template <int CH, int STEP, bool F16>   // 2*CH epilogue groups of 4 warps (CH column parts per tile); STEP columns per TMEM load round
+__global__ void __launch_bounds__((2 + 8 * CH) * 32, 1) rmsd_ts_kernel(const TsParams p) {
     constexpr int NG = 2 * CH;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const int nkc = p.Mp / 4;                                  // 16-byte K chunks
-    const int nkb = p.Mp / 8;                                  // K blocks per tile
+    const int nkc = p.nkc;                                     // 16-byte K chunks
+    const int nkb = nkc / 2;                                   // K blocks (one MMA each) per tile
     const int KT = nkb < TS_KT_MAX ? nkb : TS_KT_MAX;          // K blocks with A in TMEM
     const int tail_kc = nkc - 2 * KT;                          // chunks of A kept in shared memory
     const uint32_t tail_bytes = (uint32_t)tail_kc * TF_ROWS * 16u;      // per component
@@ -93,8 +102,7 @@ __global__ void __launch_bounds__((2 + 8 * CH) * 32, 1) rmsd_tf32ts_kernel(const
                     mbar_wait(a_empty, aph ^ 1u);
                     if (elect_one()) {
                         mbar_arrive_expect_tx(at_full, 3u * tail_bytes);
-                        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.PA) +
-                                                   (size_t)w.x * 3u * nkc * TF_ROWS * 16u;
+                        const unsigned char* src = p.PA + (size_t)w.x * 3u * nkc * TF_ROWS * 16u;
                         for (int a = 0; a < 3; a++)
                             bulk_g2s(smA + (size_t)a * tail_bytes,
                                      src + ((size_t)a * nkc + 2 * KT) * TF_ROWS * 16u, tail_bytes, at_full);
@@ -107,7 +115,7 @@ __global__ void __launch_bounds__((2 + 8 * CH) * 32, 1) rmsd_tf32ts_kernel(const
                     if (elect_one()) {
                         mbar_arrive_expect_tx(&b_full[bs], b_bytes);
                         bulk_g2s(smB + (size_t)bs * b_bytes,
-                                 reinterpret_cast<const unsigned char*>(p.PB) + (size_t)(w.y + t) * b_bytes, b_bytes,
+                                 p.PB + (size_t)(w.y + t) * b_bytes, b_bytes,
                                  &b_full[bs]);
                     }
                     __syncwarp();
@@ -118,7 +126,7 @@ __global__ void __launch_bounds__((2 + 8 * CH) * 32, 1) rmsd_tf32ts_kernel(const
     } else if (warp == 1) {
         // ===================== MMA issuer: the whole warp runs the control flow, one elected lane issues =====================
         {
-            const uint32_t idesc = umma_idesc_tf32(TF_ROWS, TF_N);
+            const uint32_t idesc = F16 ? umma_idesc_f16(TF_ROWS, TF_N) : umma_idesc_tf32(TF_ROWS, TF_N);
             const uint32_t a_lbo = TF_ROWS * 16u, b_lbo = TF_N * 16u;
             const uint64_t bd0 = umma_desc_kmajor(smem_u32(smB), b_lbo, 128u);       // stage 0, K block 0
             const uint64_t ad0 = umma_desc_kmajor(smem_u32(smA), a_lbo, 128u);       // A tail, component x
@@ -131,8 +139,12 @@ __global__ void __launch_bounds__((2 + 8 * CH) * 32, 1) rmsd_tf32ts_kernel(const
                 if (tail_kc > 0) mbar_wait(at_full, aph);
                 aph ^= 1u;
                 for (int t = 0; t < w.z; t++) {
+                    const bool tr = p.trace && it == 0 && t < TS_TRACE_TILES && lane == 0;
+                    if (tr) p.trace[t * 8 + 0] = clock64();
                     mbar_wait(&b_full[bs], bph);
+                    if (tr) p.trace[t * 8 + 1] = clock64();
                     mbar_wait(&t_empty[acc], tph ^ 1u);
+                    if (tr) p.trace[t * 8 + 2] = clock64();
                     tcgen05_fence_after();
                     if (elect_one()) {
                     const uint32_t d0 = tmem_base + TS_ACC0 + (uint32_t)acc * TF_ACC_COLS;
@@ -140,29 +152,30 @@ __global__ void __launch_bounds__((2 + 8 * CH) * 32, 1) rmsd_tf32ts_kernel(const
                     uint64_t bd = bd0 + (uint64_t)((uint32_t)bs * (b_bytes >> 4));
                     uint32_t at = tmem_base;
                     // K block 0 overwrites the accumulators, the others accumulate
-                    umma_tf32_ts_c<false>(d0, at, bd, idesc);
-                    umma_tf32_ts_c<false>(d0 + TF_N, at + a_stride, bd, idesc);
-                    umma_tf32_ts_c<false>(d0 + 2 * TF_N, at + 2 * a_stride, bd, idesc);
+                    umma_tf32_ts_c<false, F16>(d0, at, bd, idesc);
+                    umma_tf32_ts_c<false, F16>(d0 + TF_N, at + a_stride, bd, idesc);
+                    umma_tf32_ts_c<false, F16>(d0 + 2 * TF_N, at + 2 * a_stride, bd, idesc);
 #pragma unroll 4
                     for (int kb = 1; kb < KT; kb++) {
                         bd += bd_step;
                         at += 8;
-                        umma_tf32_ts_c<true>(d0, at, bd, idesc);
-                        umma_tf32_ts_c<true>(d0 + TF_N, at + a_stride, bd, idesc);
-                        umma_tf32_ts_c<true>(d0 + 2 * TF_N, at + 2 * a_stride, bd, idesc);
+                        umma_tf32_ts_c<true, F16>(d0, at, bd, idesc);
+                        umma_tf32_ts_c<true, F16>(d0 + TF_N, at + a_stride, bd, idesc);
+                        umma_tf32_ts_c<true, F16>(d0 + 2 * TF_N, at + 2 * a_stride, bd, idesc);
                     }
                     uint64_t ad = ad0;
                     for (int kb = KT; kb < nkb; kb++) {       // K blocks whose A block stayed in shared memory
                         bd += bd_step;
-                        umma_tf32_ss_c<true>(d0, ad, bd, idesc);
-                        umma_tf32_ss_c<true>(d0 + TF_N, ad + (tail_bytes >> 4), bd, idesc);
-                        umma_tf32_ss_c<true>(d0 + 2 * TF_N, ad + 2 * (tail_bytes >> 4), bd, idesc);
+                        umma_tf32_ss_c<true, F16>(d0, ad, bd, idesc);
+                        umma_tf32_ss_c<true, F16>(d0 + TF_N, ad + (tail_bytes >> 4), bd, idesc);
+                        umma_tf32_ss_c<true, F16>(d0 + 2 * TF_N, ad + 2 * (tail_bytes >> 4), bd, idesc);
                         ad += ad_step;
                     }
                     umma_commit(&b_empty[bs]);
                     umma_commit(&t_full[acc]);
                     }
                     __syncwarp();
+                    if (tr) p.trace[t * 8 + 3] = clock64();
                     if (++bs == p.nb_stages) { bs = 0; bph ^= 1u; }
                     if (++acc == TS_NACC) { acc = 0; tph ^= 1u; }
                 }
@@ -191,10 +204,10 @@ __global__ void __launch_bounds__((2 + 8 * CH) * 32, 1) rmsd_tf32ts_kernel(const
             eph ^= 1u;
             tcgen05_fence_after();
             {
-                const float4* src = reinterpret_cast<const float4*>(p.PR + (size_t)i * 3 * p.Mp);
+                const float4* src = reinterpret_cast<const float4*>(p.PR + (size_t)i * 3 * nkc * 16);
                 for (int q = grp; q < 3 * 2 * KT; q += NG) {
                     const int a = q / (2 * KT), wi = q - a * 2 * KT;
-                    const float4 v = src[a * (p.Mp / 4) + wi];
+                    const float4 v = src[a * nkc + wi];
                     tmem_st_x4(tmem_base + lane_addr + (uint32_t)(a * 8 * KT + 4 * wi), __float_as_uint(v.x),
                                __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
                 }
@@ -205,16 +218,30 @@ __global__ void __launch_bounds__((2 + 8 * CH) * 32, 1) rmsd_tf32ts_kernel(const
             }
             const TfRow row = tf32_row_consts(p.G[i], p.sG[i], p.e_thr);
             uint8_t* out_row = reinterpret_cast<uint8_t*>(p.sim_bits16) + ((int64_t)w.w * CB + row_in_panel) * (4 * p.W);
+            float gv_next = 0.f;
+            bool have_next = false;
             for (int t = 0; t < w.z; t++, tile_seq++) {
                 if ((int)(tile_seq & 1) == buf) {
                     const int64_t j0 = (int64_t)(w.y + t) * TF_J;
-                    const float gvf = tf32_col_term(p.G, p.sG, j0, lane);
+                    // column terms: prefetched one of this group's tiles ahead (the first of an item is a direct load)
+                    const float gvf = have_next ? gv_next : __ldg(&p.CT[(int64_t)(w.y + t) * 32 + lane]);
+                    have_next = t + 2 < w.z;
+                    if (have_next) gv_next = __ldg(&p.CT[(int64_t)(w.y + t + 2) * 32 + lane]);
+                    const bool tr = p.trace && it == 0 && t < TS_TRACE_TILES && lane == 0 && quad == 0 && part == 0;
+                    if (tr) p.trace[t * 8 + 4] = clock64();
                     mbar_wait(&t_full[buf], tph);
+                    if (tr) p.trace[t * 8 + 5] = clock64();
                     tph ^= 1u;
                     tcgen05_fence_after();
                     const uint32_t d0 = tmem_base + lane_addr + TS_ACC0 + (uint32_t)buf * TF_ACC_COLS;
-                    const uint32_t bits = tf32_epilogue_tile<STEP, TF_J / CH>(d0, gvf, row, p.G, p.sG, i, j0, p.N, lane,
-                                                                            &t_empty[buf], part * (TF_J / CH));
+                    uint32_t bits;
+                    if (STEP == 4)
+                        bits = tf32_epilogue_tile_v4<TF_J / CH>(d0, gvf, row, p.G, p.sG, i, j0, p.N, lane, &t_empty[buf],
+                                                                part * (TF_J / CH));
+                    else
+                        bits = tf32_epilogue_tile<STEP, TF_J / CH>(d0, gvf, row, p.G, p.sG, i, j0, p.N, lane,
+                                                                   &t_empty[buf], part * (TF_J / CH));
+                    if (tr) p.trace[t * 8 + 6] = clock64();
                     if (i < p.N && (j0 >> 4) < 2 * p.W) {
                         if (CH == 1) *reinterpret_cast<uint16_t*>(out_row + (j0 >> 3)) = (uint16_t)bits;
                         else out_row[(j0 >> 3) + part] = (uint8_t)(bits >> (8 * part));
@@ -235,22 +262,37 @@ extern "C" int64_t tsc_tf32_pr_floats(int64_t N, int32_t M) {
     return rows * 3 * Mp;
 }
 
-extern "C" int tsc_rmsd_sim_tf32ts(const float* PA, const float* PB, const float* PR, const double* G,
-                                   const double* sG, int64_t N, int32_t M, const int32_t* items, int32_t n_items,
-                                   double thr, uint32_t* sim_bits, int32_t grid_ctas, void* stream) {
-    using namespace tsc;
+static long long* g_ts_trace = nullptr;
+// Measurement aid: a device buffer of 8 * 96 int64 that receives clock64 stamps of the first work item
+// of CTA 0 (MMA warp: start, operands landed, accumulator free, issued; epilogue: start, accumulator
+// full, tile done).  NULL (default) disables it.
+extern "C" void tsc_set_trace_buffer(void* dev_ptr) { g_ts_trace = reinterpret_cast<long long*>(dev_ptr); }
+
+extern "C" int64_t tsc_tf32_ct_floats(int64_t N) {
+    return (N + tsc::TF_ROWS - 1) / tsc::TF_ROWS * tsc::TF_ROWS * 2;
+}
+
+namespace tsc {
+template <bool F16>
+static int launch_ts(const void* PA, const void* PB, const void* PR, const double* G, const double* sG, const float* CT,
+                     int64_t N, int32_t M, const int32_t* items, int32_t n_items, double thr, uint32_t* sim_bits,
+                     int32_t grid_ctas, void* stream) {
     if (n_items <= 0 || N <= 0) return 0;
     TsParams p;
-    p.PA = PA; p.PB = PB; p.PR = PR; p.G = G; p.sG = sG;
+    p.PA = reinterpret_cast<const unsigned char*>(PA);
+    p.PB = reinterpret_cast<const unsigned char*>(PB);
+    p.PR = reinterpret_cast<const unsigned char*>(PR);
+    p.G = G; p.sG = sG; p.CT = CT;
+    p.trace = g_ts_trace;
     p.items = reinterpret_cast<const int4*>(items);
     p.n_items = n_items;
     p.N = N;
-    p.Mp = (M + 7) / 8 * 8;
+    p.nkc = F16 ? (M + 15) / 16 * 2 : (M + 7) / 8 * 2;         // atoms padded to whole K blocks
     p.e_thr = (double)M * thr * thr * (1.0 + 1e-6);
     p.sim_bits16 = reinterpret_cast<uint16_t*>(sim_bits);
     p.W = num_blocks_padded(N);
-    const int nkb = p.Mp / 8, KT = nkb < TS_KT_MAX ? nkb : TS_KT_MAX;
-    const size_t a_bytes = (size_t)3 * (p.Mp / 4 - 2 * KT) * TF_ROWS * 16, b_bytes = (size_t)192 * p.Mp;
+    const int nkb = p.nkc / 2, KT = nkb < TS_KT_MAX ? nkb : TS_KT_MAX;
+    const size_t a_bytes = (size_t)3 * (p.nkc - 2 * KT) * TF_ROWS * 16, b_bytes = (size_t)p.nkc * TF_N * 16;
     const size_t budget = 227 * 1024 - 512;
     if (a_bytes + 2 * b_bytes > budget) return (int)cudaErrorInvalidValue;
     int nb = (int)((budget - a_bytes) / b_bytes);
@@ -262,7 +304,7 @@ extern "C" int tsc_rmsd_sim_tf32ts(const float* PA, const float* PB, const float
     // default = TS_DEFAULT_CFG
     const int cfg = grid_ctas < 0 ? -grid_ctas : TS_DEFAULT_CFG;
     if (grid_ctas < 0) grid_ctas = 0;
-    auto kern = cfg == 1 ? rmsd_tf32ts_kernel<1, 8> : cfg == 2 ? rmsd_tf32ts_kernel<1, 4> : rmsd_tf32ts_kernel<2, 4>;
+    auto kern = cfg == 1 ? rmsd_ts_kernel<1, 8, F16> : cfg == 2 ? rmsd_ts_kernel<1, 4, F16> : rmsd_ts_kernel<2, 4, F16>;
     const int threads = (2 + 8 * (cfg <= 2 ? 1 : 2)) * 32;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -274,4 +316,18 @@ extern "C" int tsc_rmsd_sim_tf32ts(const float* PA, const float* PB, const float
     kern<<<grid, threads, smem, (cudaStream_t)stream>>>(p);
     TSC_CHECK_LAUNCH();
     return 0;
+}
+}  // namespace tsc
+
+extern "C" int tsc_rmsd_sim_tf32ts(const float* PA, const float* PB, const float* PR, const double* G,
+                                   const double* sG, const float* CT, int64_t N, int32_t M, const int32_t* items,
+                                   int32_t n_items, double thr, uint32_t* sim_bits, int32_t grid_ctas, void* stream) {
+    return tsc::launch_ts<false>(PA, PB, PR, G, sG, CT, N, M, items, n_items, thr, sim_bits, grid_ctas, stream);
+}
+
+// FP16-operand form (default): PA / PB / PR are the images tsc_pack_f16 writes.
+extern "C" int tsc_rmsd_sim_f16ts(const void* PA, const void* PB, const void* PR, const double* G,
+                                  const double* sG, const float* CT, int64_t N, int32_t M, const int32_t* items,
+                                  int32_t n_items, double thr, uint32_t* sim_bits, int32_t grid_ctas, void* stream) {
+    return tsc::launch_ts<true>(PA, PB, PR, G, sG, CT, N, M, items, n_items, thr, sim_bits, grid_ctas, stream);
 }

@@ -123,7 +123,8 @@ constexpr int VF_WARPS = 8;
 __global__ void __launch_bounds__(VF_WARPS * 32) rmsd_verify_kernel(const double* __restrict__ packed, int64_t N, int M,
                                                                    int64_t nb_pad, const int32_t* __restrict__ row_blocks,
                                                                    int n_rb, double thr, uint32_t* sim_bits, int64_t W,
-                                                                   unsigned long long* stats) {
+                                                                   unsigned long long* stats, int2* pair_list,
+                                                                   int64_t pair_stride) {
     __shared__ int32_t s_row[VF_WARPS][32], s_i[VF_WARPS][32], s_j[VF_WARPS][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t warp_g = (int64_t)blockIdx.x * VF_WARPS + warp;
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(VF_WARPS * 32) rmsd_verify_kernel(const double
         double Rk[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, lam = 1.0, gap = 1.0;
         if (lane < count) kabsch_rot_from_cov(Sk, Rk, &lam, &gap);          // phase B: one solve per lane
         __syncwarp();
+        uint32_t okmask = 0;
         for (int k = 0; k < count; k++) {                       // phase C
             double R[9];
 #pragma unroll
@@ -162,6 +164,16 @@ __global__ void __launch_bounds__(VF_WARPS * 32) rmsd_verify_kernel(const double
             n_near += (fabs(rmsd - thr) < 1e-6) || ((rmsd < thr) && fabs(maxdev - thr2) < 1e-6);
             n_deg += ok && (gk < 1e-9 * fabs(lk));
             if (!ok && lane == 0) atomicAnd(&sim_bits[(int64_t)s_row[warp][k] * W + (j >> 5)], ~(1u << (j & 31)));
+            okmask |= (ok ? 1u : 0u) << k;
+        }
+        if (pair_list && okmask) {           // confirmed pairs of the batch -> (i, j) list, one atomic per batch
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&pair_list[0].x, __popc(okmask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if ((okmask >> lane) & 1u) {
+                const int64_t slot = (int64_t)base + __popc(okmask & ((1u << lane) - 1u));
+                if (slot < pair_stride - 1) pair_list[1 + slot] = make_int2(s_i[warp][lane], s_j[warp][lane]);
+            }
         }
         count = 0;
         __syncwarp();
@@ -220,7 +232,8 @@ __global__ void __launch_bounds__(256) rmsd_pairs_kernel(const double* __restric
 }  // namespace tsc
 
 extern "C" int tsc_rmsd_verify(const double* packed, int64_t N, int32_t M, const int32_t* row_blocks,
-                               int32_t n_rb, double thr, uint32_t* sim_bits, uint64_t* stats, void* stream) {
+                               int32_t n_rb, double thr, uint32_t* sim_bits, uint64_t* stats, int32_t* pair_list,
+                               int64_t pair_stride, void* stream) {
     using namespace tsc;
     if (N <= 0 || n_rb <= 0) return 0;
     const int64_t nb_pad = num_blocks_padded(N);
@@ -229,7 +242,8 @@ extern "C" int tsc_rmsd_verify(const double* packed, int64_t N, int32_t M, const
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
     rmsd_verify_kernel<<<(unsigned)blocks, VF_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        packed, N, M, nb_pad, row_blocks, n_rb, thr, sim_bits, nb_pad, reinterpret_cast<unsigned long long*>(stats));
+        packed, N, M, nb_pad, row_blocks, n_rb, thr, sim_bits, nb_pad, reinterpret_cast<unsigned long long*>(stats),
+        reinterpret_cast<int2*>(pair_list), pair_stride);
     TSC_CHECK_LAUNCH();
     return 0;
 }

@@ -79,27 +79,47 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
 // MMAs must stay below that: the accumulate flag is a compile-time constant (ptxas folds the
 // predicate), descriptors are advanced with one integer add (tools/umma_probe.py: a loop that
 // rebuilds descriptors and predicates per MMA issues one MMA every ~130 cycles whatever N is).
-template <bool ACC>
+template <bool ACC, bool F16 = false>
 __device__ __forceinline__ void umma_tf32_ts_c(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "n"(ACC ? 1 : 0)
-        : "memory");
+    if (F16)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+            "}" ::"r"(d_tmem),
+            "r"(a_tmem), "l"(b_desc), "r"(idesc), "n"(ACC ? 1 : 0)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+            "}" ::"r"(d_tmem),
+            "r"(a_tmem), "l"(b_desc), "r"(idesc), "n"(ACC ? 1 : 0)
+            : "memory");
 }
-template <bool ACC>
+template <bool ACC, bool F16 = false>
 __device__ __forceinline__ void umma_tf32_ss_c(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "n"(ACC ? 1 : 0)
-        : "memory");
+    if (F16)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(d_tmem),
+            "l"(a_desc), "l"(b_desc), "r"(idesc), "n"(ACC ? 1 : 0)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(d_tmem),
+            "l"(a_desc), "l"(b_desc), "r"(idesc), "n"(ACC ? 1 : 0)
+            : "memory");
 }
 
 // One 128 x 16 tile of the epilogue for the thread owning row i: read the 16 x 9 accumulators of
@@ -135,27 +155,44 @@ __device__ __forceinline__ float tf32_col_term(const double* __restrict__ G, con
 }
 
 // NCOL columns starting at column C0 of the tile are handled by this thread (NCOL = 16: whole tile).
+// The TMEM reads are software-pipelined: the loads of column group s+1 are in flight while group s
+// is screened (ncu on the first version: the epilogue warps issued 570 instructions per tile but
+// needed ~3800 cycles for them, almost all of it exposed tcgen05.ld latency — four load/wait/compute
+// rounds per tile — while the tensor pipe idled 56 % of the time waiting for a free accumulator).
+template <int STEP>
+__device__ __forceinline__ void tf32_ld_cols(uint32_t d0, int st, uint32_t* r) {
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            const uint32_t ta = d0 + (uint32_t)(a * TF_N + b * TF_J + st * STEP);
+            if (STEP == 8) tmem_ld_x8_raw(ta, &r[(3 * a + b) * STEP]);
+            else tmem_ld_x4_raw(ta, &r[(3 * a + b) * STEP]);
+        }
+}
+template <int STEP>
+__device__ __forceinline__ void tf32_ld_wait(uint32_t* r) {
+    if (STEP == 8) { tmem_wait_bind24(&r[0]); tmem_wait_bind24(&r[24]); tmem_wait_bind24(&r[48]); }
+    else { tmem_wait_bind12(&r[0]); tmem_wait_bind12(&r[12]); tmem_wait_bind12(&r[24]); }
+}
+
 template <int STEP, int NCOL = TF_J>
 __device__ __forceinline__ uint32_t tf32_epilogue_tile(uint32_t d0, float gvf, const TfRow& row,
                                                        const double* __restrict__ G, const double* __restrict__ sG,
                                                        int64_t i, int64_t j0, int64_t N, int lane,
                                                        uint64_t* t_empty_bar, int C0 = 0) {
+    constexpr int NST = NCOL / STEP;
     uint32_t bits = 0;
+    uint32_t rr[2][9 * STEP];
+    tf32_ld_cols<STEP>(d0, C0 / STEP, rr[0]);
+    tf32_ld_wait<STEP>(rr[0]);
 #pragma unroll
-    for (int st0 = 0; st0 < NCOL / STEP; st0++) {
+    for (int st0 = 0; st0 < NST; st0++) {
         const int st = st0 + C0 / STEP;
-        uint32_t r[9 * STEP];
-#pragma unroll
-        for (int a = 0; a < 3; a++)
-#pragma unroll
-            for (int b = 0; b < 3; b++) {
-                const uint32_t ta = d0 + (uint32_t)(a * TF_N + b * TF_J + st * STEP);
-                if (STEP == 8) tmem_ld_x8_raw(ta, &r[(3 * a + b) * STEP]);
-                else tmem_ld_x4_raw(ta, &r[(3 * a + b) * STEP]);
-            }
-        if (STEP == 8) { tmem_wait_bind24(&r[0]); tmem_wait_bind24(&r[24]); tmem_wait_bind24(&r[48]); }
-        else { tmem_wait_bind12(&r[0]); tmem_wait_bind12(&r[12]); tmem_wait_bind12(&r[24]); }
-        if (st0 == NCOL / STEP - 1) {     // every value this thread needs from the buffer is now in registers
+        uint32_t* r = rr[st0 & 1];
+        if (st0 + 1 < NST) {
+            tf32_ld_cols<STEP>(d0, st + 1, rr[(st0 + 1) & 1]);       // in flight while this group is screened
+        } else {                          // every value this thread needs from the buffer is now in registers
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(t_empty_bar);
@@ -190,8 +227,126 @@ __device__ __forceinline__ uint32_t tf32_epilogue_tile(uint32_t d0, float gvf, c
                 if (!excluded && ((near >> c) & 1u)) bits |= 1u << (st * STEP + c);
             }
         }
+        if (st0 + 1 < NST) tf32_ld_wait<STEP>(rr[(st0 + 1) & 1]);
     }
     // validity mask: j > i, j < N   (rows i >= N are not stored by the caller)
+    uint32_t valid = 0xffffu;
+    if (j0 + 15 >= N) valid = (j0 >= N) ? 0u : (0xffffu >> (j0 + 16 - N));
+    if (j0 <= i) valid &= (i - j0 >= 15) ? 0u : (0xffffu << (i - j0 + 1));
+    return bits & valid;
+}
+
+
+// Release-early form of the tile epilogue (16 columns, 4 per TMEM load round) used by the default
+// TMEM-operand kernel.  A clock64 trace of the previous form (tools/trace_probe.py) showed the MMA warp
+// needs ~1100 cycles to issue a tile and most tiles hand over in ~1400, but every tile in which some
+// warp took the FP64 path (one in three on C3: a single undecided pair drags 4 columns x 32 rows
+// through ~80 FP64 instructions each, behind two dependent global loads) held its accumulator buffer
+// for 3000-5000 cycles.  Here
+//   pass 1  reads the buffer once (loads of round s+1 in flight while round s is reduced) and keeps only
+//           f = ||S~||_F^2 per pair (16 registers), then takes the FP32 Samuelson decision for all 16;
+//   stash   the COLUMNS in which some lane is undecided (one REDUX over the warp) are re-read from TMEM,
+//           one 32x32b.x1 load per covariance entry: the first two into registers, any further ones are
+//           screened on the spot (rare);
+//   release the buffer goes back to the MMA warp;
+//   pass 2  the FP64 quartic sign test runs on the stashed columns, after the release.
+// gvf holds the column terms of the tile (lanes 0..15 B_j, 16..31 D_j), prefetched by the caller.
+__device__ __forceinline__ void tmem_ld_col9(uint32_t d0, int c, uint32_t* r) {
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++)
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];"
+                         : "=r"(r[3 * a + b])
+                         : "r"(d0 + (uint32_t)(a * TF_N + b * TF_J + c)));
+}
+__device__ __forceinline__ void tmem_wait_bind9(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8])::"memory");
+}
+// FP64 Budan-Fourier test of one pair on the TF32 covariance: true = provably not similar
+__device__ __forceinline__ bool tf32_quartic_excluded(const uint32_t* r, const TfRow& row, double Gj, double sGj) {
+    const double hs = 0.5 * (1.0 - 1e-10);
+    double S[9];
+#pragma unroll
+    for (int q = 0; q < 9; q++) S[q] = (double)__uint_as_float(r[q]);
+    double c2, c1, c0;
+    key_charpoly(S, c2, c1, c0);
+    const double l1 = fma(row.ci, sGj, fma(hs, Gj, row.hi)), l2 = l1 * l1;
+    const double p2 = fma(12.0, l2, 2.0 * c2);
+    const double p1 = fma(fma(4.0, l2, 2.0 * c2), l1, c1);
+    const double p0 = fma(fma(l2 + c2, l1, c1), l1, c0);
+    return (l1 > 0.0) & (p0 > 0.0) & (p1 > 0.0) & (p2 > 0.0);
+}
+
+// NCOL (16 or 8) columns starting at column C0 of the tile are handled by the calling thread.
+template <int NCOL>
+__device__ __forceinline__ uint32_t tf32_epilogue_tile_v4(uint32_t d0, float gvf, const TfRow& row,
+                                                          const double* __restrict__ G, const double* __restrict__ sG,
+                                                          int64_t i, int64_t j0, int64_t N, int lane,
+                                                          uint64_t* t_empty_bar, int C0) {
+    constexpr int NST = NCOL / 4;
+    float f[NCOL];
+    {
+        uint32_t rr[2][36];
+        tf32_ld_cols<4>(d0, C0 / 4, rr[0]);
+        tf32_ld_wait<4>(rr[0]);
+#pragma unroll
+        for (int st = 0; st < NST; st++) {
+            const uint32_t* r = rr[st & 1];
+            if (st + 1 < NST) tf32_ld_cols<4>(d0, C0 / 4 + st + 1, rr[(st + 1) & 1]);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                float acc = 0.f;
+#pragma unroll
+                for (int q = 0; q < 9; q++) { const float v = __uint_as_float(r[q * 4 + c]); acc = fmaf(v, v, acc); }
+                f[st * 4 + c] = acc;
+            }
+            if (st + 1 < NST) tf32_ld_wait<4>(rr[(st + 1) & 1]);
+        }
+    }
+    uint32_t near = 0;                    // pairs the FP32 bound cannot exclude (bit = column of the tile)
+#pragma unroll
+    for (int c = 0; c < NCOL; c++) {
+        const float Bj = __shfl_sync(0xffffffffu, gvf, C0 + c);
+        const float Dj = __shfl_sync(0xffffffffu, gvf, 16 + C0 + c);
+        const float lf = fmaf(-row.Cf, Dj, row.Af + Bj) * 0.999999f;
+        const bool far = (lf > 0.f) && (3.00003f * f[c] <= lf * lf);
+        near |= (far ? 0u : 1u) << (C0 + c);
+    }
+    uint32_t bits = 0;
+    uint32_t cols = __reduce_or_sync(0xffffffffu, near);      // columns with an undecided pair in some lane
+    uint32_t sa[9], sb[9];
+    int ca = -1, cb = -1;
+    if (cols) {
+        ca = __ffs(cols) - 1; cols &= cols - 1;
+        if (cols) { cb = __ffs(cols) - 1; cols &= cols - 1; }
+        while (cols) {                    // third and further undecided columns of a tile: screened before the release
+            const int c = __ffs(cols) - 1;
+            cols &= cols - 1;
+            uint32_t r[9];
+            tmem_ld_col9(d0, c, r);
+            tmem_wait_bind9(r);
+            const int64_t j = j0 + c;
+            if (((near >> c) & 1u) && !tf32_quartic_excluded(r, row, G[j], sG[j])) bits |= 1u << c;
+        }
+        tmem_ld_col9(d0, ca, sa);
+        if (cb >= 0) tmem_ld_col9(d0, cb, sb);
+        tmem_wait_bind9(sa);
+        if (cb >= 0) tmem_wait_bind9(sb);
+    }
+    tcgen05_fence_before();               // every value needed from the buffer has been read
+    __syncwarp();
+    if (lane == 0) mbar_arrive(t_empty_bar);
+    if (ca >= 0) {
+        const int64_t j = j0 + ca;
+        if (((near >> ca) & 1u) && !tf32_quartic_excluded(sa, row, G[j], sG[j])) bits |= 1u << ca;
+        if (cb >= 0) {
+            const int64_t jb = j0 + cb;
+            if (((near >> cb) & 1u) && !tf32_quartic_excluded(sb, row, G[jb], sG[jb])) bits |= 1u << cb;
+        }
+    }
     uint32_t valid = 0xffffu;
     if (j0 + 15 >= N) valid = (j0 >= N) ? 0u : (0xffffu >> (j0 + 16 - N));
     if (j0 <= i) valid &= (i - j0 >= 15) ? 0u : (0xffffu << (i - j0 + 1));

@@ -20,7 +20,9 @@ from ._lib import check, lib, ptr, require_cuda, stream_ptr
 
 import functools
 
-VARIANTS = {"dmma": 0, "fma": 1, "tf32": 2, "tf32ss": 3}     # tf32 = A operand in TMEM; tf32ss = both from smem
+# f16 / tf32 = tcgen05 pre-screen with the stationary operand in TMEM (FP16 or TF32 operands);
+# tf32ss = both operands from shared memory; dmma / fma = FP64 tensor cores / FMA pipe
+VARIANTS = {"dmma": 0, "fma": 1, "tf32": 2, "tf32ss": 3, "f16": 4}
 
 
 @functools.lru_cache(maxsize=8)
@@ -31,7 +33,7 @@ def _work_lists(N, rank, world, variant, device_str):
     dev = torch.device(device_str)
     rb = _host.owned_row_blocks(N, rank, world)
     out = {"row_blocks_np": rb, "row_blocks": torch.from_numpy(rb).to(dev)}
-    if variant in (2, 3):
+    if variant in (2, 3, 4):
         items = np.ascontiguousarray(_host.build_tf32_items(N, rb))
         out["n_items"], out["items"] = int(items.shape[0]), torch.from_numpy(items).to(dev)
     else:
@@ -40,6 +42,7 @@ def _work_lists(N, rank, world, variant, device_str):
     return out
 
 TF32_MAX_M = 120        # stationary A panel + 2 B stages must fit in shared memory
+F16_MAX_M = 320         # FP16 operands: 144 atoms of the panel in TMEM, the rest + 2 B stages in shared memory
 
 
 class RmsdPruner:
@@ -47,18 +50,19 @@ class RmsdPruner:
 
     structures : (N, A, 3) float64, numpy array or torch tensor (host or device)
     atomnos    : (A,) ints; hydrogens (== 1) are ignored        (rmsd_pruning.py:178-179)
-    variant    : "tf32" (default) = tcgen05/TMEM TF32 pre-screen with a rigorous error bound, exact
-                 FP64 verification of everything it cannot exclude (falls back to "dmma" when the
-                 molecule has more than 120 heavy atoms); "dmma" = FP64 tensor cores; "fma" = FP64
-                 FMA pipe.  All three give identical final similarity bits and masks.
+    variant    : "f16" (default) = tcgen05/TMEM pre-screen on FP16 operands (10-bit mantissa, K = 16
+                 atoms per MMA) with a rigorous error bound, exact FP64 verification of everything
+                 it cannot exclude (falls back to "dmma" above 320 heavy atoms); "tf32" = the same
+                 with TF32 operands (<= 120 heavy atoms); "dmma" = FP64 tensor cores; "fma" = FP64
+                 FMA pipe.  All give identical final similarity bits and masks.
     rank/world/group : row-block sharding over one process per GPU (block-cyclic, SURVEY 8(e));
                  every rank holds the whole packed ensemble, computes the similarity rows it
                  owns, and per elimination round contributes its rows' verdicts to an NCCL
                  all-gather.
     """
 
-    def __init__(self, structures, atomnos, rmsd_thr=0.5, *, variant="tf32", device=None,
-                 rank=0, world=1, group=None, grid_ctas=0):
+    def __init__(self, structures, atomnos, rmsd_thr=0.5, *, variant="f16", device=None,
+                 rank=0, world=1, group=None, grid_ctas=0, ladder="fused", pair_cap=None):
         torch = require_cuda()
         self.torch = torch
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -67,6 +71,9 @@ class RmsdPruner:
         self.variant_requested = self.variant
         self.rank, self.world, self.group = int(rank), int(world), group
         self.grid_ctas = int(grid_ctas)
+        if ladder not in ("fused", "bitrows"):
+            raise ValueError("ladder must be 'fused' or 'bitrows'")
+        self.ladder = ladder
         atomnos = np.asarray(atomnos)
         heavy = np.flatnonzero(atomnos != 1).astype(np.int32)
         if torch.is_tensor(structures):
@@ -80,7 +87,7 @@ class RmsdPruner:
         N, M = self.N, self.M
         self.nb_pad = _host.num_blocks_padded(N)
         self.W = self.nb_pad
-        if self.variant in (2, 3) and M > TF32_MAX_M:
+        if (self.variant in (2, 3) and M > TF32_MAX_M) or (self.variant == 4 and M > F16_MAX_M):
             self.variant = 0             # documented fallback: FP64 tensor cores (include/tscode_b200.h)
         with torch.cuda.device(self.device):
             dev = self.device
@@ -93,12 +100,21 @@ class RmsdPruner:
             self.packed = torch.empty(max(_host.packed_doubles(N, max(M, 1)), 1), dtype=torch.float64, device=dev)
             n_g = max(self.nb_pad * _host.CB, _host.tf32_rows_padded(N))
             self.G = torch.empty(n_g, dtype=torch.float64, device=dev)
+            if self.variant == 4:
+                L = lib()
+                nbytes = max(int(L.tsc_f16_operand_bytes(N, max(M, 1))), 16)
+                self.PA = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                self.PB = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                self.PR = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                self.sG = torch.empty(n_g, dtype=torch.float64, device=dev)
+                self.CT = torch.empty(max(L.tsc_tf32_ct_floats(N), 1), dtype=torch.float32, device=dev)
             if self.variant in (2, 3):
                 L = lib()
                 self.PR = torch.empty(max(L.tsc_tf32_pr_floats(N, max(M, 1)), 1), dtype=torch.float32, device=dev)
                 self.sG = torch.empty(n_g, dtype=torch.float64, device=dev)
                 self.PA = torch.empty(max(L.tsc_tf32_pa_floats(N, max(M, 1)), 1), dtype=torch.float32, device=dev)
                 self.PB = torch.empty(max(L.tsc_tf32_pb_floats(N, max(M, 1)), 1), dtype=torch.float32, device=dev)
+                self.CT = torch.empty(max(L.tsc_tf32_ct_floats(N), 1), dtype=torch.float32, device=dev)
             self.sim_bits = torch.empty((max(self.n_rb, 1) * _host.CB, self.W), dtype=torch.int32, device=dev)
             self.stats = torch.zeros(4, dtype=torch.int64, device=dev)
             nw = (N + 31) // 32
@@ -111,9 +127,23 @@ class RmsdPruner:
             self.key_first = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
             self.key_second = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
             self.n_keys = torch.zeros(1, dtype=torch.int32, device=dev)
+            # confirmed-pair list of this rank (header + capacity pairs) and, with several ranks, the
+            # gathered lists of all of them; consumed by the fused ladder (eliminate.cu)
+            cap = int(pair_cap) if pair_cap is not None else 32 * N // self.world + 4096
+            self.pair_stride = cap + 1
+            self.pair_list = torch.zeros((self.pair_stride, 2), dtype=torch.int32, device=dev)
+            self.pair_all = (torch.zeros((self.world * self.pair_stride, 2), dtype=torch.int32, device=dev)
+                             if self.world > 1 else self.pair_list)
+            L = lib()
+            self.fused_ws = torch.empty(int(L.tsc_elim_fused_ws_words(N)), dtype=torch.int32, device=dev)
+            self.fused_out = torch.zeros(int(L.tsc_elim_fused_out_bytes(N)), dtype=torch.uint8, device=dev)
+            self._info_off = (N + 3) // 4 * 4
             if self.world > 1:
                 self._init_shards()
         self._cands = []
+        self._pairs_ready = False
+        self._rounds_fused = None
+        self.ladder_used = None
         self.packed_ready = False
 
     # ---- multi-GPU plumbing -------------------------------------------------------------------
@@ -152,9 +182,13 @@ class RmsdPruner:
         with self.torch.cuda.device(self.device):
             check(L.tsc_pack(ptr(self.S), self.N, self.A, ptr(self.heavy_idx), self.M, ptr(self.packed),
                              ptr(self.G), stream_ptr()), "tsc_pack")
+            if self.variant == 4:
+                check(L.tsc_pack_f16(ptr(self.S), self.N, self.A, ptr(self.heavy_idx), self.M, ptr(self.PA),
+                                     ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG), ptr(self.CT), stream_ptr()),
+                      "tsc_pack_f16")
             if self.variant in (2, 3):
                 check(L.tsc_pack_tf32(ptr(self.S), self.N, self.A, ptr(self.heavy_idx), self.M, ptr(self.PA),
-                                      ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG), stream_ptr()),
+                                      ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG), ptr(self.CT), stream_ptr()),
                       "tsc_pack_tf32")
         self.packed_ready = True
 
@@ -164,13 +198,18 @@ class RmsdPruner:
             return
         if not self.packed_ready:
             self.pack()
+        self._pairs_ready = False
         L = lib()
         with self.torch.cuda.device(self.device):
             self.stats.zero_()
-            if self.variant == 2:
-                check(L.tsc_rmsd_sim_tf32ts(ptr(self.PA), ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG), self.N,
-                                            self.M, ptr(self.items), self.n_items, self.thr, ptr(self.sim_bits),
-                                            self.grid_ctas, stream_ptr()), "tsc_rmsd_sim_tf32ts")
+            if self.variant == 4:
+                check(L.tsc_rmsd_sim_f16ts(ptr(self.PA), ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG),
+                                           ptr(self.CT), self.N, self.M, ptr(self.items), self.n_items, self.thr,
+                                           ptr(self.sim_bits), self.grid_ctas, stream_ptr()), "tsc_rmsd_sim_f16ts")
+            elif self.variant == 2:
+                check(L.tsc_rmsd_sim_tf32ts(ptr(self.PA), ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG),
+                                            ptr(self.CT), self.N, self.M, ptr(self.items), self.n_items, self.thr,
+                                            ptr(self.sim_bits), self.grid_ctas, stream_ptr()), "tsc_rmsd_sim_tf32ts")
             elif self.variant == 3:
                 check(L.tsc_rmsd_sim_tf32(ptr(self.PA), ptr(self.PB), ptr(self.G), ptr(self.sG), self.N, self.M,
                                           ptr(self.items), self.n_items, self.thr, ptr(self.sim_bits),
@@ -181,13 +220,16 @@ class RmsdPruner:
                                            stream_ptr()), "tsc_rmsd_sim_tiles")
 
     def verify(self):
-        """Exact re-evaluation of screened pairs; afterwards sim_bits are final."""
-        if self.n_rb == 0 or self.M == 0:
-            return
+        """Exact re-evaluation of screened pairs; afterwards sim_bits are final and the confirmed
+        pairs of the owned rows are also available as an (i, j) list (pair_list)."""
         L = lib()
         with self.torch.cuda.device(self.device):
-            check(L.tsc_rmsd_verify(ptr(self.packed), self.N, self.M, ptr(self.row_blocks), self.n_rb, self.thr,
-                                    ptr(self.sim_bits), ptr(self.stats), stream_ptr()), "tsc_rmsd_verify")
+            self.pair_list[0].zero_()
+            if self.n_rb and self.M:
+                check(L.tsc_rmsd_verify(ptr(self.packed), self.N, self.M, ptr(self.row_blocks), self.n_rb, self.thr,
+                                        ptr(self.sim_bits), ptr(self.stats), ptr(self.pair_list), self.pair_stride,
+                                        stream_ptr()), "tsc_rmsd_verify")
+        self._pairs_ready = True
 
     def similarity(self):
         self.screen()
@@ -198,15 +240,51 @@ class RmsdPruner:
         return ctypes.c_void_p(self.hist.data_ptr() + 4 * r)
 
     def eliminate(self):
-        """The k-ladder (rmsd_pruning.py:186-204).  Every candidate round is enqueued without reading
-        anything back; each kernel evaluates the reference's gate on the device (eliminate.cu).
-        Returns the boolean mask as a device tensor."""
+        """The k-ladder (rmsd_pruning.py:186-204); returns the boolean mask as a device tensor.
+
+        Default: ONE persistent cooperative kernel over the confirmed-pair lists verify() emitted
+        (all-gathered once when several ranks share the rows).  If a list overflowed its capacity
+        (a very redundant ensemble), or the pruner was built with ladder="bitrows", the bit-row
+        kernels run instead: three launches and, on several ranks, one all-gather per round.
+        Both give the same mask (tests/test_gpu_parity.py)."""
         torch = self.torch
         N = self.N
         if N == 0:
             return torch.zeros(0, dtype=torch.bool, device=self.device)
         if self.M == 0:
             raise ValueError("prune_conformers_rmsd needs at least one non-hydrogen atom")
+        if self.ladder == "fused" and self._pairs_ready:
+            mask = self._eliminate_fused()
+            if mask is not None:
+                return mask
+        return self._eliminate_bitrows()
+
+    def _eliminate_fused(self):
+        torch = self.torch
+        N = self.N
+        L = lib()
+        with torch.cuda.device(self.device):
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_gather_into_tensor(self.pair_all, self.pair_list, group=self.group)
+            check(L.tsc_elim_fused(ptr(self.pair_all), self.world, self.pair_stride, N, 20, ptr(self.fused_ws),
+                                   ptr(self.fused_out), stream_ptr()), "tsc_elim_fused")
+            info = self.fused_out[self._info_off:self._info_off + 128].view(torch.int32).tolist()   # sync
+        if info[0] == 1:
+            return None                                   # pair list overflow -> bit rows (same on every rank)
+        if info[0] != 0:
+            raise RuntimeError(f"tsc_elim_fused did not complete (status {info[0]})")
+        self._rounds_fused = [int(k) for k in info[8:8 + info[1]]]
+        self.ladder_used = "fused"
+        return self.fused_out[:N].to(torch.bool)
+
+    def _eliminate_bitrows(self):
+        """Bit-row ladder: every candidate round is enqueued without reading anything back; each kernel
+        evaluates the reference's gate on the device (eliminate.cu)."""
+        torch = self.torch
+        N = self.N
+        self._rounds_fused = None
+        self.ladder_used = "bitrows"
         L = lib()
         with torch.cuda.device(self.device):
             st = stream_ptr()
@@ -238,6 +316,8 @@ class RmsdPruner:
     def rounds(self):
         """k of every round that actually ran (data dependent) — reads the per-round
         active counts back from the device."""
+        if self._rounds_fused is not None:
+            return list(self._rounds_fused)
         h = self.hist.tolist()
         return [k for r, k in enumerate(self._cands) if _host.ladder_gate(k, h[r])]
 
@@ -245,6 +325,17 @@ class RmsdPruner:
         self.pack()
         self.similarity()
         return self.eliminate()
+
+    def set_pairs(self, pairs):
+        """Replace this rank's confirmed-pair list by explicit (i, j) rows, i < j (tests)."""
+        torch = self.torch
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        n = pairs.shape[0]
+        self.pair_list[0, 0] = n
+        m = min(n, self.pair_stride - 1)
+        if m:
+            self.pair_list[1:1 + m].copy_(torch.from_numpy(pairs[:m]).to(self.device))
+        self._pairs_ready = True
 
     # ---- introspection ------------------------------------------------------------------------
     def stats_dict(self):
