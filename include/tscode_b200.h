@@ -76,9 +76,13 @@ int tsc_pack_tf32(const double* S, int64_t N, int32_t A, const int32_t* heavy_id
 /* Same screen with the stationary 128-conformer operand held in TENSOR MEMORY (written once per
  * work item with tcgen05.st, read by tcgen05.mma [d], [a_tmem], b_desc): removes ~3/4 of the
  * shared-memory operand traffic that bounded tsc_rmsd_sim_tf32.  Default for variant "tf32". */
+/*   cand_list (may be NULL): block of cand_stride int32 pairs, element 0 = header whose first int32 is the
+ *   running count (zero it first); (local row, j) of every bit the screen sets is appended from element 1.
+ *   tsc_rmsd_verify works from this list when it did not overflow. */
 int tsc_rmsd_sim_tf32ts(const float* PA, const float* PB, const float* PR, const double* G,
                         const double* sG, const float* CT, int64_t N, int32_t M, const int32_t* items,
-                        int32_t n_items, double thr, uint32_t* sim_bits, int32_t grid_ctas, void* stream);
+                        int32_t n_items, double thr, uint32_t* sim_bits, int32_t* cand_list,
+                        int64_t cand_stride, int32_t grid_ctas, void* stream);
 /* FP16-operand form of the same screen (kind::f16, K = 16 atoms per MMA; FP16 has TF32's 10-bit mantissa,
  * so the same error bound holds; tsc_pack_f16 zeroes |x| < 2^-14 and widens sqrt(G) accordingly).  Half as
  * many MMA instructions per tile: default screen of prune_conformers_rmsd for M <= 320 heavy atoms.
@@ -88,7 +92,8 @@ int tsc_pack_f16(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx
                  void* PB, void* PR, double* G, double* sG, float* CT, void* stream);
 int tsc_rmsd_sim_f16ts(const void* PA, const void* PB, const void* PR, const double* G,
                        const double* sG, const float* CT, int64_t N, int32_t M, const int32_t* items,
-                       int32_t n_items, double thr, uint32_t* sim_bits, int32_t grid_ctas, void* stream);
+                       int32_t n_items, double thr, uint32_t* sim_bits, int32_t* cand_list,
+                       int64_t cand_stride, int32_t grid_ctas, void* stream);
 /* Measurement aid: 8*96 int64 of clock64 stamps from the first work item of CTA 0 (NULL = off). */
 void tsc_set_trace_buffer(void* dev_ptr);
 int tsc_rmsd_sim_tf32(const float* PA, const float* PB, const double* G, const double* sG, int64_t N,
@@ -103,10 +108,13 @@ int tsc_rmsd_sim_tf32(const float* PA, const float* PB, const double* G, const d
  *   pair_list (may be NULL): a block of `pair_stride` int32 pairs; element 0 is a header whose
  *   first int32 is the running pair count (zero it before the first call), confirmed pairs (i, j)
  *   are appended from element 1 (unordered).  A count > pair_stride - 1 means the list overflowed
- *   (pairs beyond the capacity are dropped; the bit rows stay complete). */
+ *   (pairs beyond the capacity are dropped; the bit rows stay complete).
+ *   cand_list (may be NULL): the candidate list a tcgen05 screen wrote.  If its count is within the
+ *   capacity the candidates are verified straight from the list (32 per warp), else — or with NULL, or a
+ *   negative count — every set bit of the owned rows is found by scanning the bit rows. */
 int tsc_rmsd_verify(const double* packed, int64_t N, int32_t M, const int32_t* row_blocks,
                     int32_t n_rb, double thr, uint32_t* sim_bits, uint64_t* stats, int32_t* pair_list,
-                    int64_t pair_stride, void* stream);
+                    int64_t pair_stride, const int32_t* cand_list, int64_t cand_stride, void* stream);
 
 /* Batched rmsd_and_max_numba on explicit pairs: P, Q (n, M, 3) -> rmsd (n), maxdev (n).
  * broadcast_p = 1 compares P[0] with every Q[k] (_rmsd_similarity, rmsd_pruning.py:208-224). */

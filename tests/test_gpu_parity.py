@@ -191,8 +191,9 @@ def test_fused_ladder_overflow_falls_back_to_bitrows(gpu):
     big = RmsdPruner(S, at, 0.5, pair_cap=200_000)
     m2 = big.run().cpu().numpy()
     assert big.ladder_used == "fused"
-    forced = RmsdPruner(S, at, 0.5, ladder="bitrows")
+    forced = RmsdPruner(S, at, 0.5, ladder="bitrows", cand_cap=50)     # candidate list overflows too: bit-row verify
     m3 = forced.run().cpu().numpy()
+    assert int(forced.cand_list[0, 0]) > 50 and forced.stats_dict() == big.stats_dict()
     assert np.array_equal(m1, ref) and np.array_equal(m2, ref) and np.array_equal(m3, ref)
     assert small.rounds == big.rounds == forced.rounds
     # the emitted list is exactly the set bits of the verified rows

@@ -8,7 +8,8 @@ from tscode_b200._lib import lib, ptr
 from tscode_b200.rmsd_pruning import RmsdPruner
 from tscode_b200.synth import gen_ensemble
 S = gen_ensemble(3, 50000, 80, 5000)
-pr = RmsdPruner(S, np.full(80, 6), 0.5, variant=(sys.argv[1] if len(sys.argv) > 1 else "f16"))
+pr = RmsdPruner(S, np.full(80, 6), 0.5, variant=(sys.argv[1] if len(sys.argv) > 1 else "f16"),
+                grid_ctas=(int(sys.argv[2]) if len(sys.argv) > 2 else 0))
 trace = torch.zeros(8 * 96, dtype=torch.int64, device="cuda")
 pr.run(); torch.cuda.synchronize()
 lib().tsc_set_trace_buffer(ptr(trace))

@@ -31,11 +31,11 @@ SIGNATURES = {
     "tsc_set_trace_buffer": (None, [_vp]),
     "tsc_f16_operand_bytes": (_i64, [_i64, _i32]),
     "tsc_pack_f16": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "tsc_rmsd_sim_f16ts": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _i32, _vp]),
+    "tsc_rmsd_sim_f16ts": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _i64, _i32, _vp]),
     "tsc_pack_tf32": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "tsc_rmsd_sim_tf32ts": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _i32, _vp]),
+    "tsc_rmsd_sim_tf32ts": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _i64, _i32, _vp]),
     "tsc_rmsd_sim_tf32": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _i32, _vp]),
-    "tsc_rmsd_verify": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp, _i64, _vp]),
+    "tsc_rmsd_verify": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "tsc_elim_fused_ws_words": (_i64, [_i64]),
     "tsc_elim_fused_out_bytes": (_i64, [_i64]),
     "tsc_elim_fused": (C.c_int, [_vp, _i32, _i64, _i64, _i32, _vp, _vp, _vp]),

@@ -24,9 +24,14 @@
 
 namespace tsc {
 
-constexpr int TS_KT_MAX = 9;                   // K blocks (of 8 atoms) held in TMEM
-constexpr int TS_ACC0 = 3 * 8 * TS_KT_MAX;     // 216: first accumulator column
-constexpr int TS_NACC = 2;
+// Two TMEM budgets (template parameter NACC):
+//   NACC = 2: up to 9 K blocks of the A panel in TMEM (216 columns) + 2 accumulator buffers (288);
+//   NACC = 3: the whole A panel stays in shared memory (SS-form MMAs) and TMEM holds 3 accumulator buffers
+//             (432 columns), one per epilogue group: the MMA warp can run two tiles ahead of the epilogue.
+//             With FP16 operands an MMA reads 4 KB (A) + 1.5 KB (B) of shared memory = 43 cycles at 128 B/clk,
+//             about the ~40 cycles the tensor pipe needs for a 128x48 instruction anyway.
+constexpr int TS_KT_MAX = 9;                   // K blocks held in TMEM (NACC = 2)
+constexpr int TS_MAX_NACC = 3;
 constexpr int TS_MAX_BSTAGES = 12;
 constexpr int TS_DEFAULT_CFG = 2;
 
@@ -50,18 +55,25 @@ struct TsParams {
     double e_thr;
     uint16_t* sim_bits16;
     int64_t W;
+    int2* cand;               // candidate list (header + capacity entries (local row, j)), or NULL
+    int64_t cand_stride;
     long long* trace;         // measurement aid (tsc_set_trace_buffer): clock64 stamps of CTA 0's first item, or NULL
 };
 
+constexpr int TS_Q = 128;              // candidate queue entries per epilogue warp (shared memory)
 constexpr int TS_TRACE_TILES = 96;    // tiles of the first item that are stamped (8 slots each)
 
-template <int CH, int STEP, bool F16>   // 2*CH epilogue groups of 4 warps (CH column parts per tile); STEP columns per TMEM load round
-__global__ void __launch_bounds__((2 + 8 * CH) * 32, 1) rmsd_ts_kernel(const TsParams p) {
-    constexpr int NG = 2 * CH;
+// NACC*CH epilogue groups of 4 warps (CH column parts per tile); STEP columns per TMEM load round
+template <int CH, int STEP, bool F16, int NACC>
+__global__ void __launch_bounds__((2 + 4 * NACC * CH) * 32, 1) rmsd_ts_kernel(const TsParams p) {
+    constexpr int NG = NACC * CH;
+    constexpr int TS_NACC = NACC;
+    constexpr int KT_MAX = NACC == 2 ? TS_KT_MAX : 0;
+    constexpr int TS_ACC0 = 3 * 8 * KT_MAX;        // first accumulator column
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int nkc = p.nkc;                                     // 16-byte K chunks
     const int nkb = nkc / 2;                                   // K blocks (one MMA each) per tile
-    const int KT = nkb < TS_KT_MAX ? nkb : TS_KT_MAX;          // K blocks with A in TMEM
+    const int KT = nkb < KT_MAX ? nkb : KT_MAX;                // K blocks with A in TMEM
     const int tail_kc = nkc - 2 * KT;                          // chunks of A kept in shared memory
     const uint32_t tail_bytes = (uint32_t)tail_kc * TF_ROWS * 16u;      // per component
     const uint32_t b_bytes = (uint32_t)nkc * TF_N * 16u;
@@ -74,8 +86,9 @@ __global__ void __launch_bounds__((2 + 8 * CH) * 32, 1) rmsd_ts_kernel(const TsP
     uint64_t* b_full = bars + 3;
     uint64_t* b_empty = b_full + TS_MAX_BSTAGES;
     uint64_t* t_full = b_empty + TS_MAX_BSTAGES;
-    uint64_t* t_empty = t_full + TS_NACC;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + TS_NACC);
+    uint64_t* t_empty = t_full + TS_MAX_NACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + TS_MAX_NACC);
+    int2* cand_q = reinterpret_cast<int2*>(reinterpret_cast<unsigned char*>(bars) + 512);     // [epilogue warp][TS_Q]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -150,21 +163,29 @@ __global__ void __launch_bounds__((2 + 8 * CH) * 32, 1) rmsd_ts_kernel(const TsP
                     const uint32_t d0 = tmem_base + TS_ACC0 + (uint32_t)acc * TF_ACC_COLS;
                     // descriptors advance by one add per K block (two 16-byte chunks = 2*LBO bytes)
                     uint64_t bd = bd0 + (uint64_t)((uint32_t)bs * (b_bytes >> 4));
-                    uint32_t at = tmem_base;
-                    // K block 0 overwrites the accumulators, the others accumulate
-                    umma_tf32_ts_c<false, F16>(d0, at, bd, idesc);
-                    umma_tf32_ts_c<false, F16>(d0 + TF_N, at + a_stride, bd, idesc);
-                    umma_tf32_ts_c<false, F16>(d0 + 2 * TF_N, at + 2 * a_stride, bd, idesc);
-#pragma unroll 4
-                    for (int kb = 1; kb < KT; kb++) {
-                        bd += bd_step;
-                        at += 8;
-                        umma_tf32_ts_c<true, F16>(d0, at, bd, idesc);
-                        umma_tf32_ts_c<true, F16>(d0 + TF_N, at + a_stride, bd, idesc);
-                        umma_tf32_ts_c<true, F16>(d0 + 2 * TF_N, at + 2 * a_stride, bd, idesc);
-                    }
                     uint64_t ad = ad0;
-                    for (int kb = KT; kb < nkb; kb++) {       // K blocks whose A block stayed in shared memory
+                    if (KT_MAX > 0) {
+                        uint32_t at = tmem_base;
+                        // K block 0 overwrites the accumulators, the others accumulate
+                        umma_tf32_ts_c<false, F16>(d0, at, bd, idesc);
+                        umma_tf32_ts_c<false, F16>(d0 + TF_N, at + a_stride, bd, idesc);
+                        umma_tf32_ts_c<false, F16>(d0 + 2 * TF_N, at + 2 * a_stride, bd, idesc);
+#pragma unroll 4
+                        for (int kb = 1; kb < KT; kb++) {
+                            bd += bd_step;
+                            at += 8;
+                            umma_tf32_ts_c<true, F16>(d0, at, bd, idesc);
+                            umma_tf32_ts_c<true, F16>(d0 + TF_N, at + a_stride, bd, idesc);
+                            umma_tf32_ts_c<true, F16>(d0 + 2 * TF_N, at + 2 * a_stride, bd, idesc);
+                        }
+                    } else {                                      // whole panel in shared memory
+                        umma_tf32_ss_c<false, F16>(d0, ad, bd, idesc);
+                        umma_tf32_ss_c<false, F16>(d0 + TF_N, ad + (tail_bytes >> 4), bd, idesc);
+                        umma_tf32_ss_c<false, F16>(d0 + 2 * TF_N, ad + 2 * (tail_bytes >> 4), bd, idesc);
+                        ad += ad_step;
+                    }
+#pragma unroll 4
+                    for (int kb = (KT_MAX > 0 ? KT : 1); kb < nkb; kb++) {       // K blocks whose A block is in shared memory
                         bd += bd_step;
                         umma_tf32_ss_c<true, F16>(d0, ad, bd, idesc);
                         umma_tf32_ss_c<true, F16>(d0 + TF_N, ad + (tail_bytes >> 4), bd, idesc);
@@ -196,6 +217,21 @@ __global__ void __launch_bounds__((2 + 8 * CH) * 32, 1) rmsd_ts_kernel(const TsP
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         uint32_t eph = 0, tph = 0;
         int64_t tile_seq = 0;
+        // Candidates (rare: ~1 per 5000 pairs) go to a per-warp queue in shared memory and reach the global
+        // list in bursts with ONE atomic per burst: a global atomic per candidate (~1 us round trip inside
+        // the tile loop) had cost 0.35 ms on C3.
+        int2* my_q = cand_q + (size_t)ew * TS_Q;
+        int qn = 0;
+        auto flush_q = [&]() {
+            __syncwarp();
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&p.cand[0].x, qn);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            for (int k = lane; k < qn; k += 32)
+                if ((int64_t)base + k < p.cand_stride - 1) p.cand[1 + base + k] = my_q[k];
+            __syncwarp();
+            qn = 0;
+        };
         for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
             const int4 w = p.items[it];
             const int64_t i = (int64_t)w.x * TF_ROWS + row_in_panel;
@@ -221,12 +257,12 @@ __global__ void __launch_bounds__((2 + 8 * CH) * 32, 1) rmsd_ts_kernel(const TsP
             float gv_next = 0.f;
             bool have_next = false;
             for (int t = 0; t < w.z; t++, tile_seq++) {
-                if ((int)(tile_seq & 1) == buf) {
+                if ((int)(tile_seq % NACC) == buf) {
                     const int64_t j0 = (int64_t)(w.y + t) * TF_J;
                     // column terms: prefetched one of this group's tiles ahead (the first of an item is a direct load)
                     const float gvf = have_next ? gv_next : __ldg(&p.CT[(int64_t)(w.y + t) * 32 + lane]);
-                    have_next = t + 2 < w.z;
-                    if (have_next) gv_next = __ldg(&p.CT[(int64_t)(w.y + t + 2) * 32 + lane]);
+                    have_next = t + NACC < w.z;
+                    if (have_next) gv_next = __ldg(&p.CT[(int64_t)(w.y + t + NACC) * 32 + lane]);
                     const bool tr = p.trace && it == 0 && t < TS_TRACE_TILES && lane == 0 && quad == 0 && part == 0;
                     if (tr) p.trace[t * 8 + 4] = clock64();
                     mbar_wait(&t_full[buf], tph);
@@ -242,6 +278,41 @@ __global__ void __launch_bounds__((2 + 8 * CH) * 32, 1) rmsd_ts_kernel(const TsP
                         bits = tf32_epilogue_tile<STEP, TF_J / CH>(d0, gvf, row, p.G, p.sG, i, j0, p.N, lane,
                                                                    &t_empty[buf], part * (TF_J / CH));
                     if (tr) p.trace[t * 8 + 6] = clock64();
+                    if (p.cand) {
+                        uint32_t bb = (i < p.N) ? (CH == 1 ? bits : (bits & (0xffu << (8 * part)))) : 0u;
+                        if (__any_sync(0xffffffffu, bb != 0u)) {      // append (local row, j) of every bit set
+                            const int cnt = __popc(bb);
+                            int pre = cnt;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const int v = __shfl_up_sync(0xffffffffu, pre, o);
+                                if (lane >= o) pre += v;
+                            }
+                            const int total = __shfl_sync(0xffffffffu, pre, 31);
+                            int at = pre - cnt;
+                            const int32_t lrow = w.w * CB + row_in_panel;
+                            if (qn + total > TS_Q) flush_q();
+                            if (total > TS_Q) {                       // a dense tile: straight to the global list
+                                int base = 0;
+                                if (lane == 0) base = atomicAdd(&p.cand[0].x, total);
+                                base = __shfl_sync(0xffffffffu, base, 0);
+                                while (bb) {
+                                    const int b = __ffs(bb) - 1;
+                                    bb &= bb - 1;
+                                    if ((int64_t)base + at < p.cand_stride - 1)
+                                        p.cand[1 + base + at] = make_int2(lrow, (int32_t)(j0 + b));
+                                    at++;
+                                }
+                            } else {
+                                while (bb) {
+                                    const int b = __ffs(bb) - 1;
+                                    bb &= bb - 1;
+                                    my_q[qn + at++] = make_int2(lrow, (int32_t)(j0 + b));
+                                }
+                                qn += total;
+                            }
+                        }
+                    }
                     if (i < p.N && (j0 >> 4) < 2 * p.W) {
                         if (CH == 1) *reinterpret_cast<uint16_t*>(out_row + (j0 >> 3)) = (uint16_t)bits;
                         else out_row[(j0 >> 3) + part] = (uint8_t)(bits >> (8 * part));
@@ -249,6 +320,7 @@ __global__ void __launch_bounds__((2 + 8 * CH) * 32, 1) rmsd_ts_kernel(const TsP
                 }
             }
         }
+        if (p.cand && qn) flush_q();
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -276,9 +348,11 @@ namespace tsc {
 template <bool F16>
 static int launch_ts(const void* PA, const void* PB, const void* PR, const double* G, const double* sG, const float* CT,
                      int64_t N, int32_t M, const int32_t* items, int32_t n_items, double thr, uint32_t* sim_bits,
-                     int32_t grid_ctas, void* stream) {
+                     int32_t* cand_list, int64_t cand_stride, int32_t grid_ctas, void* stream) {
     if (n_items <= 0 || N <= 0) return 0;
     TsParams p;
+    p.cand = reinterpret_cast<int2*>(cand_list);
+    p.cand_stride = cand_stride;
     p.PA = reinterpret_cast<const unsigned char*>(PA);
     p.PB = reinterpret_cast<const unsigned char*>(PB);
     p.PR = reinterpret_cast<const unsigned char*>(PR);
@@ -291,21 +365,24 @@ static int launch_ts(const void* PA, const void* PB, const void* PR, const doubl
     p.e_thr = (double)M * thr * thr * (1.0 + 1e-6);
     p.sim_bits16 = reinterpret_cast<uint16_t*>(sim_bits);
     p.W = num_blocks_padded(N);
-    const int nkb = p.nkc / 2, KT = nkb < TS_KT_MAX ? nkb : TS_KT_MAX;
+    // grid_ctas < 0 selects an alternative configuration (tuning aid): -1 = A in TMEM, 2 groups, 8 columns per
+    // TMEM load round; -2 = A in TMEM, 2 groups x 4; -3 = A in TMEM, 4 groups (two column halves per tile) x 4;
+    // -4 = A in shared memory, 3 accumulator buffers, 3 groups x 4;  default = TS_DEFAULT_CFG
+    const int cfg = grid_ctas < 0 ? -grid_ctas : TS_DEFAULT_CFG;
+    if (grid_ctas < 0) grid_ctas = 0;
+    const int kt_max = cfg == 4 ? 0 : TS_KT_MAX;
+    const int nkb = p.nkc / 2, KT = nkb < kt_max ? nkb : kt_max;
     const size_t a_bytes = (size_t)3 * (p.nkc - 2 * KT) * TF_ROWS * 16, b_bytes = (size_t)p.nkc * TF_N * 16;
-    const size_t budget = 227 * 1024 - 512;
+    const size_t q_bytes = (size_t)16 * TS_Q * sizeof(int2);            // candidate queues of up to 16 epilogue warps
+    const size_t budget = 227 * 1024 - 512 - q_bytes;
     if (a_bytes + 2 * b_bytes > budget) return (int)cudaErrorInvalidValue;
     int nb = (int)((budget - a_bytes) / b_bytes);
     if (nb > TS_MAX_BSTAGES) nb = TS_MAX_BSTAGES;
     p.nb_stages = nb;
-    const size_t smem = a_bytes + nb * b_bytes + 512;
-    // grid_ctas < 0 selects an alternative epilogue configuration (tuning aid): -1 = 2 groups, 8 columns
-    // per TMEM load round; -2 = 2 groups x 4; -3 = 4 groups (two column halves per tile) x 4;
-    // default = TS_DEFAULT_CFG
-    const int cfg = grid_ctas < 0 ? -grid_ctas : TS_DEFAULT_CFG;
-    if (grid_ctas < 0) grid_ctas = 0;
-    auto kern = cfg == 1 ? rmsd_ts_kernel<1, 8, F16> : cfg == 2 ? rmsd_ts_kernel<1, 4, F16> : rmsd_ts_kernel<2, 4, F16>;
-    const int threads = (2 + 8 * (cfg <= 2 ? 1 : 2)) * 32;
+    const size_t smem = a_bytes + nb * b_bytes + 512 + q_bytes;
+    auto kern = cfg == 1 ? rmsd_ts_kernel<1, 8, F16, 2> : cfg == 2 ? rmsd_ts_kernel<1, 4, F16, 2>
+              : cfg == 3 ? rmsd_ts_kernel<2, 4, F16, 2> : rmsd_ts_kernel<1, 4, F16, 3>;
+    const int threads = cfg <= 2 ? 320 : cfg == 3 ? 576 : 448;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;
@@ -321,13 +398,17 @@ static int launch_ts(const void* PA, const void* PB, const void* PR, const doubl
 
 extern "C" int tsc_rmsd_sim_tf32ts(const float* PA, const float* PB, const float* PR, const double* G,
                                    const double* sG, const float* CT, int64_t N, int32_t M, const int32_t* items,
-                                   int32_t n_items, double thr, uint32_t* sim_bits, int32_t grid_ctas, void* stream) {
-    return tsc::launch_ts<false>(PA, PB, PR, G, sG, CT, N, M, items, n_items, thr, sim_bits, grid_ctas, stream);
+                                   int32_t n_items, double thr, uint32_t* sim_bits, int32_t* cand_list,
+                                   int64_t cand_stride, int32_t grid_ctas, void* stream) {
+    return tsc::launch_ts<false>(PA, PB, PR, G, sG, CT, N, M, items, n_items, thr, sim_bits, cand_list, cand_stride,
+                                 grid_ctas, stream);
 }
 
 // FP16-operand form (default): PA / PB / PR are the images tsc_pack_f16 writes.
 extern "C" int tsc_rmsd_sim_f16ts(const void* PA, const void* PB, const void* PR, const double* G,
                                   const double* sG, const float* CT, int64_t N, int32_t M, const int32_t* items,
-                                  int32_t n_items, double thr, uint32_t* sim_bits, int32_t grid_ctas, void* stream) {
-    return tsc::launch_ts<true>(PA, PB, PR, G, sG, CT, N, M, items, n_items, thr, sim_bits, grid_ctas, stream);
+                                  int32_t n_items, double thr, uint32_t* sim_bits, int32_t* cand_list,
+                                  int64_t cand_stride, int32_t grid_ctas, void* stream) {
+    return tsc::launch_ts<true>(PA, PB, PR, G, sG, CT, N, M, items, n_items, thr, sim_bits, cand_list, cand_stride,
+                                grid_ctas, stream);
 }

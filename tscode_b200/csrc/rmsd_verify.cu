@@ -17,6 +17,12 @@
 
 namespace tsc {
 
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 struct PairEval {
     double rmsd, maxdev, gap, lam;
 };
@@ -124,7 +130,10 @@ __global__ void __launch_bounds__(VF_WARPS * 32) rmsd_verify_kernel(const double
                                                                    int64_t nb_pad, const int32_t* __restrict__ row_blocks,
                                                                    int n_rb, double thr, uint32_t* sim_bits, int64_t W,
                                                                    unsigned long long* stats, int2* pair_list,
-                                                                   int64_t pair_stride) {
+                                                                   int64_t pair_stride, const int2* cand,
+                                                                   int64_t cand_stride) {
+    // a valid candidate list means rmsd_verify_list_kernel has done the work already
+    if (cand && cand[0].x >= 0 && (int64_t)cand[0].x <= cand_stride - 1) return;
     __shared__ int32_t s_row[VF_WARPS][32], s_i[VF_WARPS][32], s_j[VF_WARPS][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t warp_g = (int64_t)blockIdx.x * VF_WARPS + warp;
@@ -214,6 +223,192 @@ __global__ void __launch_bounds__(VF_WARPS * 32) rmsd_verify_kernel(const double
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Verification from a CANDIDATE LIST (the tcgen05 screens append (local row, j) of every bit they
+// set).  The bit-row scan above costs a dependent L2 round trip per 32 words of a 1564-word row and
+// leaves most lanes idle during the eigen-solves (a row has ~5 candidates); here a warp takes 32
+// list entries at a time: covariances and explicit differences are computed 8 candidates per pass by
+// groups of 4 lanes (one 20-atom slab of the packed layout per lane and step, 16-byte loads of
+// contiguous runs), the 32 eigen-solves run one per lane.  Same arithmetic per pair as eval_pair up
+// to the order of the atom sums.  Runs only if the list did not overflow (header count <= capacity);
+// otherwise rmsd_verify_kernel does the work from the bit rows.
+// ------------------------------------------------------------------------------------------
+// FULL: a whole 20-atom slab with the loop unrolled, so that the 60 (cov) / 120 (diff) loads of the slab are
+// independent instructions the scheduler can keep in flight together (the rolled loop paid one L2 round trip
+// per two atoms).
+template <bool FULL>
+__device__ __forceinline__ void slab_cov(const double* __restrict__ P, const double* __restrict__ Q, int n, double S[9]) {
+    // P, Q: x run of this conformer's slab; y at + CB*KS, z at + 2*CB*KS
+    const int nn = FULL ? KS : n;
+#pragma unroll
+    for (int k = 0; k < (FULL ? KS : 1); k += 2) {
+        if (!FULL) {
+#pragma unroll 1
+            for (int kk = 0; kk < nn; kk += 2) {
+                const double2 px = *reinterpret_cast<const double2*>(P + kk), py = *reinterpret_cast<const double2*>(P + CB * KS + kk),
+                              pz = *reinterpret_cast<const double2*>(P + 2 * CB * KS + kk);
+                const double2 qx = *reinterpret_cast<const double2*>(Q + kk), qy = *reinterpret_cast<const double2*>(Q + CB * KS + kk),
+                              qz = *reinterpret_cast<const double2*>(Q + 2 * CB * KS + kk);
+                S[0] = fma(px.x, qx.x, S[0]); S[1] = fma(px.x, qy.x, S[1]); S[2] = fma(px.x, qz.x, S[2]);
+                S[3] = fma(py.x, qx.x, S[3]); S[4] = fma(py.x, qy.x, S[4]); S[5] = fma(py.x, qz.x, S[5]);
+                S[6] = fma(pz.x, qx.x, S[6]); S[7] = fma(pz.x, qy.x, S[7]); S[8] = fma(pz.x, qz.x, S[8]);
+                S[0] = fma(px.y, qx.y, S[0]); S[1] = fma(px.y, qy.y, S[1]); S[2] = fma(px.y, qz.y, S[2]);
+                S[3] = fma(py.y, qx.y, S[3]); S[4] = fma(py.y, qy.y, S[4]); S[5] = fma(py.y, qz.y, S[5]);
+                S[6] = fma(pz.y, qx.y, S[6]); S[7] = fma(pz.y, qy.y, S[7]); S[8] = fma(pz.y, qz.y, S[8]);
+            }
+        } else {
+            const double2 px = *reinterpret_cast<const double2*>(P + k), py = *reinterpret_cast<const double2*>(P + CB * KS + k),
+                          pz = *reinterpret_cast<const double2*>(P + 2 * CB * KS + k);
+            const double2 qx = *reinterpret_cast<const double2*>(Q + k), qy = *reinterpret_cast<const double2*>(Q + CB * KS + k),
+                          qz = *reinterpret_cast<const double2*>(Q + 2 * CB * KS + k);
+            S[0] = fma(px.x, qx.x, S[0]); S[1] = fma(px.x, qy.x, S[1]); S[2] = fma(px.x, qz.x, S[2]);
+            S[3] = fma(py.x, qx.x, S[3]); S[4] = fma(py.x, qy.x, S[4]); S[5] = fma(py.x, qz.x, S[5]);
+            S[6] = fma(pz.x, qx.x, S[6]); S[7] = fma(pz.x, qy.x, S[7]); S[8] = fma(pz.x, qz.x, S[8]);
+            S[0] = fma(px.y, qx.y, S[0]); S[1] = fma(px.y, qy.y, S[1]); S[2] = fma(px.y, qz.y, S[2]);
+            S[3] = fma(py.y, qx.y, S[3]); S[4] = fma(py.y, qy.y, S[4]); S[5] = fma(py.y, qz.y, S[5]);
+            S[6] = fma(pz.y, qx.y, S[6]); S[7] = fma(pz.y, qy.y, S[7]); S[8] = fma(pz.y, qz.y, S[8]);
+        }
+    }
+}
+template <bool FULL>
+__device__ __forceinline__ void slab_diff(const double* __restrict__ P, const double* __restrict__ Q, int n,
+                                          const double R[9], double& ss, double& mx) {
+    if (FULL) {
+#pragma unroll
+        for (int k = 0; k < KS; k += 2) {
+            const double2 px = *reinterpret_cast<const double2*>(P + k), py = *reinterpret_cast<const double2*>(P + CB * KS + k),
+                          pz = *reinterpret_cast<const double2*>(P + 2 * CB * KS + k);
+            const double2 qx = *reinterpret_cast<const double2*>(Q + k), qy = *reinterpret_cast<const double2*>(Q + CB * KS + k),
+                          qz = *reinterpret_cast<const double2*>(Q + 2 * CB * KS + k);
+            {
+                const double dx = fma(R[0], px.x, fma(R[1], py.x, R[2] * pz.x)) - qx.x;
+                const double dy = fma(R[3], px.x, fma(R[4], py.x, R[5] * pz.x)) - qy.x;
+                const double dz = fma(R[6], px.x, fma(R[7], py.x, R[8] * pz.x)) - qz.x;
+                const double d2 = fma(dx, dx, fma(dy, dy, dz * dz));
+                ss += d2; mx = fmax(mx, d2);
+            }
+            {
+                const double dx = fma(R[0], px.y, fma(R[1], py.y, R[2] * pz.y)) - qx.y;
+                const double dy = fma(R[3], px.y, fma(R[4], py.y, R[5] * pz.y)) - qy.y;
+                const double dz = fma(R[6], px.y, fma(R[7], py.y, R[8] * pz.y)) - qz.y;
+                const double d2 = fma(dx, dx, fma(dy, dy, dz * dz));
+                ss += d2; mx = fmax(mx, d2);
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int k = 0; k < n; k++) {
+            const double px = P[k], py = P[CB * KS + k], pz = P[2 * CB * KS + k];
+            const double dx = fma(R[0], px, fma(R[1], py, R[2] * pz)) - Q[k];
+            const double dy = fma(R[3], px, fma(R[4], py, R[5] * pz)) - Q[CB * KS + k];
+            const double dz = fma(R[6], px, fma(R[7], py, R[8] * pz)) - Q[2 * CB * KS + k];
+            const double d2 = fma(dx, dx, fma(dy, dy, dz * dz));
+            ss += d2;
+            mx = fmax(mx, d2);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(VF_WARPS * 32) rmsd_verify_list_kernel(
+    const double* __restrict__ packed, int64_t N, int M, int64_t nb_pad, const int32_t* __restrict__ row_blocks,
+    double thr, uint32_t* sim_bits, int64_t W, unsigned long long* stats, const int2* __restrict__ cand,
+    int64_t cand_stride, int2* pair_list, int64_t pair_stride) {
+    const int64_t n = cand[0].x;
+    if (n <= 0 || n > cand_stride - 1) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int nslab = num_slabs(M);
+    const int grp = lane >> 2, sub = lane & 3;
+    const double thr2 = 2.0 * thr;
+    unsigned long long n_cand = 0, n_ok = 0, n_near = 0, n_deg = 0;
+    for (int64_t b0 = gwarp * 32; b0 < n; b0 += nwarps * 32) {
+        const int count = (int)((n - b0 < 32) ? n - b0 : 32);
+        int32_t lrow = 0, j = 0, i = 0;
+        if (lane < count) {
+            const int2 e = cand[1 + b0 + lane];
+            lrow = e.x; j = e.y;
+            i = row_blocks[lrow / CB] * CB + (lrow % CB);
+        }
+        // ---- phase A: covariances, 8 candidates per pass, 4 lanes (slabs) per candidate ----
+        double Sk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int pass = 0; pass * 8 < count; pass++) {
+            const int c = pass * 8 + grp;
+            const int64_t ci = __shfl_sync(0xffffffffu, i, c), cj = __shfl_sync(0xffffffffu, j, c);
+            double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            if (c < count)
+                for (int sl = sub; sl < nslab; sl += 4) {
+                    const int na = (M - sl * KS < KS) ? M - sl * KS : KS;
+                    const double* P = packed + packed_index(ci, sl * KS, 0, nb_pad);
+                    const double* Q = packed + packed_index(cj, sl * KS, 0, nb_pad);
+                    if (na == KS) slab_cov<true>(P, Q, KS, S);
+                    else slab_cov<false>(P, Q, (na + 1) & ~1, S);      // padding atoms are zero
+                }
+#pragma unroll
+            for (int q = 0; q < 9; q++) {
+                S[q] += __shfl_xor_sync(0xffffffffu, S[q], 1);
+                S[q] += __shfl_xor_sync(0xffffffffu, S[q], 2);
+                const double v = __shfl_sync(0xffffffffu, S[q], 4 * (lane & 7));
+                if ((lane >> 3) == pass) Sk[q] = v;
+            }
+        }
+        // ---- phase B: one eigen-solve per lane ----
+        double Rk[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, lam = 1.0, gap = 1.0;
+        if (lane < count) kabsch_rot_from_cov(Sk, Rk, &lam, &gap);
+        // ---- phase C: explicit rotation + differences ----
+        uint32_t okmask = 0;
+        for (int pass = 0; pass * 8 < count; pass++) {
+            const int c = pass * 8 + grp;
+            const int64_t ci = __shfl_sync(0xffffffffu, i, c), cj = __shfl_sync(0xffffffffu, j, c);
+            const int32_t crow = __shfl_sync(0xffffffffu, lrow, c);
+            double R[9];
+#pragma unroll
+            for (int q = 0; q < 9; q++) R[q] = __shfl_sync(0xffffffffu, Rk[q], c);
+            const double lk = __shfl_sync(0xffffffffu, lam, c), gk = __shfl_sync(0xffffffffu, gap, c);
+            double ss = 0.0, mx = 0.0;
+            if (c < count)
+                for (int sl = sub; sl < nslab; sl += 4) {
+                    const int na = (M - sl * KS < KS) ? M - sl * KS : KS;
+                    const double* P = packed + packed_index(ci, sl * KS, 0, nb_pad);
+                    const double* Q = packed + packed_index(cj, sl * KS, 0, nb_pad);
+                    if (na == KS) slab_diff<true>(P, Q, KS, R, ss, mx);
+                    else slab_diff<false>(P, Q, na, R, ss, mx);
+                }
+            ss += __shfl_xor_sync(0xffffffffu, ss, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1)); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            const double rmsd = sqrt(ss / (double)M), maxdev = sqrt(mx);
+            const bool ok = (rmsd < thr) && (maxdev < thr2);
+            const bool mine = (c < count) && sub == 0;
+            if (mine) {
+                n_cand++;
+                n_ok += ok;
+                n_near += (fabs(rmsd - thr) < 1e-6) || ((rmsd < thr) && fabs(maxdev - thr2) < 1e-6);
+                n_deg += ok && (gk < 1e-9 * fabs(lk));
+                if (!ok) atomicAnd(&sim_bits[(int64_t)crow * W + (cj >> 5)], ~(1u << (cj & 31)));
+            }
+            const uint32_t okb = __ballot_sync(0xffffffffu, mine && ok);      // bit 4g set <=> candidate pass*8+g confirmed
+#pragma unroll
+            for (int g = 0; g < 8; g++) okmask |= ((okb >> (4 * g)) & 1u) << (pass * 8 + g);
+        }
+        if (pair_list && okmask) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&pair_list[0].x, __popc(okmask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if ((okmask >> lane) & 1u) {
+                const int64_t slot = (int64_t)base + __popc(okmask & ((1u << lane) - 1u));
+                if (slot < pair_stride - 1) pair_list[1 + slot] = make_int2(i, j);
+            }
+        }
+    }
+    n_cand = warp_sum_u64(n_cand); n_ok = warp_sum_u64(n_ok); n_near = warp_sum_u64(n_near); n_deg = warp_sum_u64(n_deg);
+    if (lane == 0 && stats) {
+        if (n_cand) atomicAdd(&stats[0], n_cand);
+        if (n_ok) atomicAdd(&stats[1], n_ok);
+        if (n_near) atomicAdd(&stats[2], n_near);
+        if (n_deg) atomicAdd(&stats[3], n_deg);
+    }
+}
+
 // Batched rmsd_and_max_numba on explicit AoS pairs: P, Q are (n, M, 3); one warp per pair.
 __global__ void __launch_bounds__(256) rmsd_pairs_kernel(const double* __restrict__ P, const double* __restrict__ Q,
                                                          int64_t n, int M, int64_t q_stride_is_zero,
@@ -233,17 +428,26 @@ __global__ void __launch_bounds__(256) rmsd_pairs_kernel(const double* __restric
 
 extern "C" int tsc_rmsd_verify(const double* packed, int64_t N, int32_t M, const int32_t* row_blocks,
                                int32_t n_rb, double thr, uint32_t* sim_bits, uint64_t* stats, int32_t* pair_list,
-                               int64_t pair_stride, void* stream) {
+                               int64_t pair_stride, const int32_t* cand_list, int64_t cand_stride, void* stream) {
     using namespace tsc;
     if (N <= 0 || n_rb <= 0) return 0;
     const int64_t nb_pad = num_blocks_padded(N);
+    if (cand_list) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        rmsd_verify_list_kernel<<<sms * 4, VF_WARPS * 32, 0, (cudaStream_t)stream>>>(
+            packed, N, M, nb_pad, row_blocks, thr, sim_bits, nb_pad, reinterpret_cast<unsigned long long*>(stats),
+            reinterpret_cast<const int2*>(cand_list), cand_stride, reinterpret_cast<int2*>(pair_list), pair_stride);
+        TSC_CHECK_LAUNCH();
+    }
     int64_t rows = (int64_t)n_rb * CB;
     int64_t blocks = (rows + 4 * VF_WARPS - 1) / (4 * VF_WARPS);       // ~4 rows per warp: fuller batches
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
     rmsd_verify_kernel<<<(unsigned)blocks, VF_WARPS * 32, 0, (cudaStream_t)stream>>>(
         packed, N, M, nb_pad, row_blocks, n_rb, thr, sim_bits, nb_pad, reinterpret_cast<unsigned long long*>(stats),
-        reinterpret_cast<int2*>(pair_list), pair_stride);
+        reinterpret_cast<int2*>(pair_list), pair_stride, reinterpret_cast<const int2*>(cand_list), cand_stride);
     TSC_CHECK_LAUNCH();
     return 0;
 }

@@ -62,7 +62,7 @@ class RmsdPruner:
     """
 
     def __init__(self, structures, atomnos, rmsd_thr=0.5, *, variant="f16", device=None,
-                 rank=0, world=1, group=None, grid_ctas=0, ladder="fused", pair_cap=None):
+                 rank=0, world=1, group=None, grid_ctas=0, ladder="fused", pair_cap=None, cand_cap=None):
         torch = require_cuda()
         self.torch = torch
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -134,6 +134,9 @@ class RmsdPruner:
             self.pair_list = torch.zeros((self.pair_stride, 2), dtype=torch.int32, device=dev)
             self.pair_all = (torch.zeros((self.world * self.pair_stride, 2), dtype=torch.int32, device=dev)
                              if self.world > 1 else self.pair_list)
+            # candidate list the tcgen05 screens append to (local row, j); verify works from it
+            self.cand_stride = (int(cand_cap) if cand_cap is not None else 64 * N // self.world + 8192) + 1
+            self.cand_list = torch.zeros((self.cand_stride, 2), dtype=torch.int32, device=dev)
             L = lib()
             self.fused_ws = torch.empty(int(L.tsc_elim_fused_ws_words(N)), dtype=torch.int32, device=dev)
             self.fused_out = torch.zeros(int(L.tsc_elim_fused_out_bytes(N)), dtype=torch.uint8, device=dev)
@@ -202,14 +205,17 @@ class RmsdPruner:
         L = lib()
         with self.torch.cuda.device(self.device):
             self.stats.zero_()
+            self.cand_list[0].fill_(0 if self.variant in (2, 4) else -1)      # -1: this screen writes no list
             if self.variant == 4:
                 check(L.tsc_rmsd_sim_f16ts(ptr(self.PA), ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG),
                                            ptr(self.CT), self.N, self.M, ptr(self.items), self.n_items, self.thr,
-                                           ptr(self.sim_bits), self.grid_ctas, stream_ptr()), "tsc_rmsd_sim_f16ts")
+                                           ptr(self.sim_bits), ptr(self.cand_list), self.cand_stride, self.grid_ctas,
+                                           stream_ptr()), "tsc_rmsd_sim_f16ts")
             elif self.variant == 2:
                 check(L.tsc_rmsd_sim_tf32ts(ptr(self.PA), ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG),
                                             ptr(self.CT), self.N, self.M, ptr(self.items), self.n_items, self.thr,
-                                            ptr(self.sim_bits), self.grid_ctas, stream_ptr()), "tsc_rmsd_sim_tf32ts")
+                                            ptr(self.sim_bits), ptr(self.cand_list), self.cand_stride, self.grid_ctas,
+                                            stream_ptr()), "tsc_rmsd_sim_tf32ts")
             elif self.variant == 3:
                 check(L.tsc_rmsd_sim_tf32(ptr(self.PA), ptr(self.PB), ptr(self.G), ptr(self.sG), self.N, self.M,
                                           ptr(self.items), self.n_items, self.thr, ptr(self.sim_bits),
@@ -228,7 +234,7 @@ class RmsdPruner:
             if self.n_rb and self.M:
                 check(L.tsc_rmsd_verify(ptr(self.packed), self.N, self.M, ptr(self.row_blocks), self.n_rb, self.thr,
                                         ptr(self.sim_bits), ptr(self.stats), ptr(self.pair_list), self.pair_stride,
-                                        stream_ptr()), "tsc_rmsd_verify")
+                                        ptr(self.cand_list), self.cand_stride, stream_ptr()), "tsc_rmsd_verify")
         self._pairs_ready = True
 
     def similarity(self):
