@@ -17,6 +17,6 @@ $CMD > $OUT/plain.json 2> $OUT/plain.err && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/launches.csv $CMD > $OUT/ncu_launches.log 2>&1
 echo "launch list rc=$?" | tee -a $OUT/rc.txt
 $CMD > $OUT/plain2.json 2> $OUT/plain2.err && \
-ncu --set full --clock-control none --import-source on -k regex:rmsd_tf32 -s 3 -c 1 -o $OUT/prof_screen $CMD > $OUT/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:rmsd_ts_kernel -s 3 -c 1 -o $OUT/prof_screen $CMD > $OUT/ncu_full.log 2>&1
 echo "full capture rc=$?" | tee -a $OUT/rc.txt
 ls -la $OUT

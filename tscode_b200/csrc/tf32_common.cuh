@@ -296,12 +296,20 @@ __device__ __forceinline__ uint32_t tf32_epilogue_tile_v4(uint32_t d0, float gvf
         for (int st = 0; st < NST; st++) {
             const uint32_t* r = rr[st & 1];
             if (st + 1 < NST) tf32_ld_cols<4>(d0, C0 / 4 + st + 1, rr[(st + 1) & 1]);
+            // ||S~||_F^2 of two columns per instruction (fma.rn.f32x2 -> FFMA2; per-lane IEEE fma, same values)
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                float acc = 0.f;
+            for (int cp = 0; cp < 2; cp++) {
+                unsigned long long acc = 0ull;
 #pragma unroll
-                for (int q = 0; q < 9; q++) { const float v = __uint_as_float(r[q * 4 + c]); acc = fmaf(v, v, acc); }
-                f[st * 4 + c] = acc;
+                for (int q = 0; q < 9; q++) {
+                    unsigned long long v;
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(r[q * 4 + 2 * cp]), "r"(r[q * 4 + 2 * cp + 1]));
+                    asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(acc) : "l"(v));
+                }
+                uint32_t lo, hi;
+                asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(acc));
+                f[st * 4 + 2 * cp] = __uint_as_float(lo);
+                f[st * 4 + 2 * cp + 1] = __uint_as_float(hi);
             }
             if (st + 1 < NST) tf32_ld_wait<4>(rr[(st + 1) & 1]);
         }
@@ -311,8 +319,10 @@ __device__ __forceinline__ uint32_t tf32_epilogue_tile_v4(uint32_t d0, float gvf
     for (int c = 0; c < NCOL; c++) {
         const float Bj = __shfl_sync(0xffffffffu, gvf, C0 + c);
         const float Dj = __shfl_sync(0xffffffffu, gvf, 16 + C0 + c);
-        const float lf = fmaf(-row.Cf, Dj, row.Af + Bj) * 0.999999f;
-        const bool far = (lf > 0.f) && (3.00003f * f[c] <= lf * lf);
+        // lower bound of the threshold eigenvalue up to (1 - 1e-6); the factor is folded into the constant:
+        // 3 (1 + 9 2^-24) / (1 - 1e-6)^2 < 3.00004 also covers the roundings of the two products
+        const float lf = fmaf(-row.Cf, Dj, row.Af + Bj);
+        const bool far = (lf > 0.f) && (3.00004f * f[c] <= lf * lf);
         near |= (far ? 0u : 1u) << (C0 + c);
     }
     uint32_t bits = 0;
