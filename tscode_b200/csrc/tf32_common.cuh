@@ -314,17 +314,23 @@ __device__ __forceinline__ uint32_t tf32_epilogue_tile_v4(uint32_t d0, float gvf
             if (st + 1 < NST) tf32_ld_wait<4>(rr[(st + 1) & 1]);
         }
     }
-    uint32_t near = 0;                    // pairs the FP32 bound cannot exclude (bit = column of the tile)
+    // Samuelson decision per pair, branch- and select-free: with lf = A_i + B_j - C_i D_j (lower bound of the
+    // threshold eigenvalue up to a factor 1 - 1e-6, folded into the constant: 3 (1 + 9 2^-24) / (1 - 1e-6)^2 <
+    // 3.00004 also covers the roundings of the two products) the pair is excluded iff lf > 0 and
+    // t = 3.00004 f - lf^2 < 0, i.e. iff the sign bit of t is set and that of lf is clear (an FMA keeps the sign
+    // of the exact result; NaN / inf from an overflowed FP16 operand give t = +inf or the canonical NaN
+    // 0x7fffffff: not excluded).  The sign bits are funnel-shifted into a mask, one SHF per pair.
+    uint32_t farm = 0;                    // bit (NCOL-1-c) = pair of column C0 + c excluded
 #pragma unroll
     for (int c = 0; c < NCOL; c++) {
         const float Bj = __shfl_sync(0xffffffffu, gvf, C0 + c);
         const float Dj = __shfl_sync(0xffffffffu, gvf, 16 + C0 + c);
-        // lower bound of the threshold eigenvalue up to (1 - 1e-6); the factor is folded into the constant:
-        // 3 (1 + 9 2^-24) / (1 - 1e-6)^2 < 3.00004 also covers the roundings of the two products
         const float lf = fmaf(-row.Cf, Dj, row.Af + Bj);
-        const bool far = (lf > 0.f) && (3.00004f * f[c] <= lf * lf);
-        near |= (far ? 0u : 1u) << (C0 + c);
+        const float t = fmaf(3.00004f, f[c], -(lf * lf));
+        farm = __funnelshift_l(__float_as_uint(t) & ~__float_as_uint(lf), farm, 1);
     }
+    // pairs the FP32 bound cannot exclude (bit = column of the tile)
+    const uint32_t near = ((~__brev(farm)) >> (32 - NCOL)) << C0;
     uint32_t bits = 0;
     uint32_t cols = __reduce_or_sync(0xffffffffu, near);      // columns with an undecided pair in some lane
     uint32_t sa[9], sb[9];
