@@ -196,6 +196,25 @@ int tsc_rotcorr_pairs(const double* Sc, int64_t N, int32_t A, const uint8_t* hea
                       const uint8_t* node_mask, int64_t row_begin, int64_t row_end, double max_rmsd,
                       uint32_t* sim_bits, uint32_t* codes, double* rmsd_out, uint64_t* near_count,
                       void* stream);
+/* [host] Inner loop of the grouping replay for one chunk [base, hi) of a ladder round, driven by the forward
+ * scan's results (all pointers are HOST pointers): row i visits the columns (reach[i], min(first_hit[i], hi) - 1]
+ * and first_hit[i] if inside the chunk; state[j] = (best_angle(i, j) + state[i]) mod 360 for every visited j
+ * (torsion_module.py:1004-1008 as rotor-state algebra); matches are returned chunk-relative in the reference's
+ * insertion order.  compact[off[i] + k] = 3-bit-per-rotor code of pair (i, i + 1 + k); ang_table (T, 6). */
+int64_t tsc_host_rotcorr_chunk(int64_t base, int64_t hi, const int64_t* first_hit, int64_t* reach, double* state,
+                               int32_t T, const uint32_t* compact, const int64_t* off, const double* ang_table,
+                               int32_t* match_i, int32_t* match_j);
+/* Forward scan for the stateless mode at large N: first_hit[i] = min{ j > i : rmsd(i, j) < max_rmsd } (N if
+ * none) for rows [row_begin, row_end).  The grouping loop (torsion_module.py:1098-1125) stops at the first
+ * similar later structure and caches dissimilar pairs, so first_hit plus the best-angle codes of the pairs
+ * (i, j <= first_hit[i]) — written into the dense (N, N) codes / rmsd_out arrays, either may be NULL — is all
+ * it needs.  One CTA per row, 8 pairs at a time, early exit.  row_counter: one int32 of scratch. */
+int tsc_rotcorr_scan(const double* Sc, int64_t N, int32_t A, const uint8_t* heavy, int32_t T,
+                     const int32_t* tor_i2, const int32_t* tor_i3, const int32_t* n_ang,
+                     const double* sin_half, const double* cos_half, const uint8_t* rot_mask,
+                     const uint8_t* node_mask, int64_t row_begin, int64_t row_end, double max_rmsd,
+                     int32_t* first_hit, uint32_t* codes, double* rmsd_out, uint64_t* near_count,
+                     int32_t* row_counter, void* stream);
 /* Stateful mode — exact emulation of the reference's in-place mutation (utils.py:412 through
  * torsion_module.py:984-1008), one row of the grouping loop (:1101-1125) at a time:
  *   tsc_rotcorr_row evaluates (i, js[k]) for k < n from the CURRENT structures cur (N, A, 3) and stages

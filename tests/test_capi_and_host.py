@@ -141,3 +141,32 @@ def test_pairlist_ladder_model_matches_oracle(N, density, seed):
     mask, ran = _host.ladder_pairlist_model(pairs, N)
     assert ran == [int(k) for k in rounds]
     assert np.array_equal(mask, ref)
+
+
+@pytest.mark.parametrize("N,dens,seed", [(60, 0.05, 1), (300, 0.01, 2), (300, 0.2, 3), (777, 0.003, 4), (100, 0.0, 6),
+                                         (50, 1.0, 7)])
+def test_rotcorr_scan_replay_equals_dense_replay(N, dens, seed):
+    """The grouping loop of prune_conformers_rmsd_rot_corr driven by first hits (what the forward-scan
+    kernel returns) gives the same mask and the same rotor states as the replay on a full matrix —
+    both in its Python form and with the per-chunk inner loop in C (tsc_host_rotcorr_chunk)."""
+    from tscode_b200.torsion_module import ladder_replay, ladder_replay_scan
+    rng = np.random.default_rng(seed)
+    sim = np.triu(rng.random((N, N)) < dens, 1)
+    T = 3
+    table = np.zeros((T, 6)); table[:, :3] = [0, 120, 240]
+    codes = rng.integers(0, 3, size=(N, N, T))
+    ang = table[np.arange(T)[None, None, :], codes]
+    m1, s1 = ladder_replay(sim, N, ang)
+    first = np.array([(np.flatnonzero(sim[i])[0] if sim[i].any() else N) for i in range(N)])
+    lengths = np.maximum(np.minimum(first, N - 1) - np.arange(N), 0)
+    off = np.cumsum(lengths) - lengths
+    packed = (codes[..., 0] | (codes[..., 1] << 3) | (codes[..., 2] << 6)).astype(np.uint32)
+    compact = np.concatenate([packed[i, i + 1:i + 1 + lengths[i]] for i in range(N)]) if lengths.sum() else np.zeros(0, np.uint32)
+
+    def lookup(i, js):
+        cc = compact[off[i] + (np.asarray(js) - i - 1)]
+        return np.stack([table[t][(cc >> (3 * t)) & 7] for t in range(T)], axis=-1)
+    lookup.T, lookup.compact, lookup.off, lookup.table = T, compact, off.astype(np.int64), table
+    for native in (False, True):
+        m2, s2 = ladder_replay_scan(first, N, lookup, native=native)
+        assert np.array_equal(m1, m2) and np.array_equal(s1, s2), native

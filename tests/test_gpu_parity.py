@@ -408,6 +408,9 @@ def test_rot_corr_vs_reference(gpu, name):
           " heavy atoms =", np.abs(out2[:, heavy] - g["out"][:, heavy]).max())
     if not name.startswith("tritbu63"):          # noise-degenerate alkyne rotors: hydrogens may pick the other image
         assert np.abs(out2 - g["out"]).max() < 1e-9
+    out3, mask3 = prune_conformers_rmsd_rot_corr(S.copy(), atomnos, None, max_rmsd=f["thr"], torsion_info=info,
+                                                 mode="allpairs")       # every pair evaluated: same as the forward scan
+    assert np.array_equal(mask3, mask2) and np.abs(out3 - out2).max() < 1e-12
     # stateless pair values + the in-place mutation of the scalar entry point
     Sc = np.array([s - s.mean(axis=0) for s in S])
     pr = RotCorrPruner(Sc, atomnos, info, f["thr"], want_rmsd=True)

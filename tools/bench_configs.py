@@ -19,7 +19,7 @@ import rotor_molecules as rm  # noqa: E402
 from tscode_b200.numba_functions import PoseBatch  # noqa: E402
 from tscode_b200.rmsd_pruning import RmsdPruner, prune_conformers_rmsd  # noqa: E402
 from tscode_b200.synth import gen_ensemble, gen_poses, mask_digest  # noqa: E402
-from tscode_b200.torsion_module import (RotCorrPruner, TorsionInfo, ladder_replay,  # noqa: E402
+from tscode_b200.torsion_module import (RotCorrPruner, TorsionInfo, ladder_replay, ladder_replay_scan,  # noqa: E402
                                         prune_conformers_rmsd_rot_corr)
 
 out_path = sys.argv[1] if len(sys.argv) > 1 else None
@@ -74,25 +74,37 @@ emit({"config": "C4b rot_corr 750 x 63 (the reference's own size limit, torsion_
 N4 = int(os.environ.get("C4_N", "20000"))
 S20, _ = rm.ensemble_tritbu63(13, N4)
 Sc = S20 - S20.mean(axis=1, keepdims=True)
-pr4 = RotCorrPruner(Sc, atomnos63, info, 0.25, want_codes=True)
-t_pairs, _ = cuda_ms(pr4.similarity, reps=2)
-t0 = time.perf_counter(); sim = pr4.similar_matrix(); best = pr4.best_angles(); t_d2h = time.perf_counter() - t0
-t0 = time.perf_counter(); mask, state = ladder_replay(sim, N4, best); t_lad = time.perf_counter() - t0
+pr4 = RotCorrPruner(Sc, atomnos63, info, 0.25, want_codes=False)
+pr4.scan(); torch.cuda.synchronize()
+t0 = time.perf_counter(); first_hit, lookup = pr4.scan(); t_scan = time.perf_counter() - t0
+t0 = time.perf_counter(); mask, state = ladder_replay_scan(first_hit, N4, lookup); t_lad = time.perf_counter() - t0
+t0 = time.perf_counter(); out4, mask4 = prune_conformers_rmsd_rot_corr(S20, atomnos63, None, 0.25, torsion_info=info,
+                                                                      max_structures=None); t_api = time.perf_counter() - t0
 rng = np.random.default_rng(0)
-ii = rng.integers(0, N4 - 1, 300); jj = np.minimum(ii + 1 + rng.integers(0, 50, 300), N4 - 1)
+ii = rng.integers(0, N4 - 1, 300)
 bad = 0
-for a, b in zip(ii, jj):
-    if a < b:
-        r, _, _ = oracle_np.rotationally_corrected_rmsd(Sc[a], Sc[b], atomnos63 != 1, info.torsions, info.angles,
-                                                        info.rot_masks, [np.flatnonzero(n) for n in info.node_masks])
-        bad += int((r < 0.25) != bool(sim[a, b]))
+for a in ii:
+    b = int(min(first_hit[a], N4 - 1))
+    for bb in {b, min(a + 1, N4 - 1)}:
+        if a < bb:
+            r, _, _ = oracle_np.rotationally_corrected_rmsd(Sc[a], Sc[bb], atomnos63 != 1, info.torsions, info.angles,
+                                                            info.rot_masks, [np.flatnonzero(n) for n in info.node_masks])
+            bad += int((r < 0.25) != (bb == first_hit[a])) if bb <= first_hit[a] else 0
 npairs = N4 * (N4 - 1) // 2
-emit({"config": f"C4c rot_corr {N4} x 63 atoms, 6 rotors, guard lifted (beyond the reference's 750 limit)",
-      "pairs": npairs, "gpu_all_pairs_ms": t_pairs, "pairs_per_s": npairs / (t_pairs * 1e-3),
-      "d2h_decode_ms": t_d2h * 1e3, "host_ladder_ms": t_lad * 1e3, "survivors": int(mask.sum()),
+emit({"config": f"C4c rot_corr {N4} x 63 atoms, 6 rotors, guard lifted (beyond the reference's 750 limit), forward scan",
+      "pairs_total": npairs, "pairs_evaluated": int(pr4.pairs_evaluated), "scan_ms_incl_code_d2h": t_scan * 1e3,
+      "host_ladder_ms": t_lad * 1e3, "api_total_ms": t_api * 1e3, "survivors": int(mask.sum()),
+      "api_mask_equal": bool(np.array_equal(mask, mask4)),
       "near_threshold_pairs": int(pr4.near.item()), "sampled_pairs_vs_numpy_oracle_mismatches": bad,
       "local_rmsd_evals_per_pair": int(sum(len(a) for a in info.angles)) + 1})
-del pr4, sim, best
+if N4 <= 6000:      # all-pairs cross-check (O(N^2) whatever the data)
+    pr5 = RotCorrPruner(Sc, atomnos63, info, 0.25, want_codes=True)
+    t_pairs, _ = cuda_ms(pr5.similarity, reps=2)
+    m5, _ = ladder_replay(pr5.similar_matrix(), N4, pr5.best_angles())
+    emit({"config": f"C4c' all-pairs evaluation of the same {N4} structures", "gpu_all_pairs_ms": t_pairs,
+          "pairs_per_s": npairs / (t_pairs * 1e-3), "mask_equal_to_scan": bool(np.array_equal(m5, mask))})
+    del pr5
+del pr4
 torch.cuda.empty_cache()
 
 # ---- C5: 1M trimolecular poses -> clash -> gather -> prune (one GPU) ----------------------------------------

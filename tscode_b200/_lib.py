@@ -47,6 +47,9 @@ SIGNATURES = {
     "tsc_clash_structs": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _f64, _f64, _f64, _i64, _vp, _vp, _vp]),
     "tsc_rotcorr_pairs": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f64,
                                     _vp, _vp, _vp, _vp, _vp]),
+    "tsc_host_rotcorr_chunk": (_i64, [_i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "tsc_rotcorr_scan": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f64,
+                                   _vp, _vp, _vp, _vp, _vp, _vp]),
     "tsc_rotcorr_row": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32,
                                   _vp, _vp, _vp, _vp]),
     "tsc_rotcorr_commit": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),

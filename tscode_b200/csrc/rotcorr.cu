@@ -160,6 +160,190 @@ __device__ __forceinline__ double rotcorr_eval(const RotCorrParams& p, const dou
     return rmsd;
 }
 
+// Lane-parallel form of the search phase.  The (rotor, angle) combinations of a pair are independent, so
+// instead of running them one after the other with the 32 lanes splitting the atoms — which makes every
+// lane repeat each of the sum_t n_t eigen-solves (~2.5k FP64 instructions each: 94 % of the kernel) — lane c
+// takes combination c: it walks all atoms (shared-memory broadcast reads), rotates the moving ones of its
+// rotor by its angle, accumulates its own covariance and solves its own eigenproblem.  The best angle per
+// rotor is then a warp minimum over the lanes of that rotor (lowest angle index on exact ties, as the
+// reference's strict `<` in ascending order, torsion_module.py:994).  Apply phase and global RMSD unchanged.
+//   abits[a]: bit t = atom a moves with rotor t (rotation mask), bit 16 + t = atom a belongs to rotor t's
+//   heavy-atom sub-graph (staged in shared memory by the caller).
+__device__ __forceinline__ double rotcorr_eval2(const RotCorrParams& p, const uint32_t* __restrict__ abits,
+                                                const double* rx, const double* ry, const double* rz, double* cx,
+                                                double* cy, double* cz, int lane, uint32_t& code_out) {
+    const int A = p.A;
+    int best_idx[RC_MAX_T];
+#pragma unroll
+    for (int t = 0; t < RC_MAX_T; t++) best_idx[t] = 0;
+    // passes of whole rotors: as many consecutive rotors as fit in 32 lanes (n_ang <= 6, so at least five)
+    for (int t_begin = 0; t_begin < p.T;) {
+        int t_end = t_begin, ncomb = 0;
+        while (t_end < p.T && ncomb + p.n_ang[t_end] <= 32) ncomb += p.n_ang[t_end++];
+        int tc = -1, kc = 0;
+        {   // lane -> (rotor, angle) of this pass
+            int acc = 0;
+            for (int t = t_begin; t < t_end; t++) {
+                const int n = p.n_ang[t];
+                if (tc < 0 && lane < acc + n) { tc = t; kc = lane - acc; }
+                acc += n;
+            }
+        }
+        double local = 1e300;
+        if (tc >= 0) {
+            const int a2 = p.i2[tc], a3 = p.i3[tc];
+            const double ox = cx[a3], oy = cy[a3], oz = cz[a3];
+            double R[9];
+            rot_from_axis(cx[a2] - ox, cy[a2] - oy, cz[a2] - oz, p.sin_half[tc * RC_MAX_ANG + kc],
+                          p.cos_half[tc * RC_MAX_ANG + kc], R);
+            double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, G = 0.0, cnt = 0.0;
+            const uint32_t rbit = 1u << tc, nbit = 1u << (16 + tc);
+            for (int a = 0; a < A; a++) {
+                const uint32_t ab = abits[a];
+                if (!(ab & nbit)) continue;
+                const double px = rx[a], py = ry[a], pz = rz[a];
+                double qx = cx[a], qy = cy[a], qz = cz[a];
+                if (ab & rbit) rot_point(R, ox, oy, oz, qx, qy, qz);
+                S[0] = fma(px, qx, S[0]); S[1] = fma(px, qy, S[1]); S[2] = fma(px, qz, S[2]);
+                S[3] = fma(py, qx, S[3]); S[4] = fma(py, qy, S[4]); S[5] = fma(py, qz, S[5]);
+                S[6] = fma(pz, qx, S[6]); S[7] = fma(pz, qy, S[7]); S[8] = fma(pz, qz, S[8]);
+                G += px * px + py * py + pz * pz + qx * qx + qy * qy + qz * qz;
+                cnt += 1.0;
+            }
+            double q[4];
+            const double lam = key_top_eigen(key_matrix(S), q, nullptr);
+            local = sqrt(fmax(G - 2.0 * lam, 0.0) / cnt);
+        }
+        __syncwarp();
+        // per rotor: minimum over its lanes, lowest angle index on ties
+        for (int t = t_begin; t < t_end; t++) {
+            const double v = (tc == t) ? local : 1e300;
+            double m = v;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+            const uint32_t who = __ballot_sync(0xffffffffu, tc == t && v == m);
+            const int src = who ? __ffs(who) - 1 : 0;
+            const int kb = __shfl_sync(0xffffffffu, kc, src);
+            if (who) best_idx[t] = kb;
+        }
+        t_begin = t_end;
+    }
+    uint32_t code = 0;
+    for (int t = 0; t < p.T; t++) code |= (uint32_t)best_idx[t] << (3 * t);
+    // ---- apply phase: best rotations in torsion order, each about the CURRENT axis (:1004-1008) ----
+    for (int t = 0; t < p.T; t++) {
+        const int k = best_idx[t];
+        if (k == 0 && p.sin_half[t * RC_MAX_ANG] == 0.0) continue;      // angle 0: identity
+        const int a2 = p.i2[t], a3 = p.i3[t];
+        const double ox = cx[a3], oy = cy[a3], oz = cz[a3];
+        double R[9];
+        rot_from_axis(cx[a2] - ox, cy[a2] - oy, cz[a2] - oz, p.sin_half[t * RC_MAX_ANG + k],
+                      p.cos_half[t * RC_MAX_ANG + k], R);
+        __syncwarp();
+        for (int a = lane; a < A; a += 32)
+            if (abits[a] & (1u << t)) {
+                double x = cx[a], y = cy[a], z = cz[a];
+                rot_point(R, ox, oy, oz, x, y, z);
+                cx[a] = x; cy[a] = y; cz[a] = z;
+            }
+        __syncwarp();
+    }
+    // ---- global heavy-atom Kabsch RMSD, explicit rotation and differences (:1011) ----
+    double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, cnt = 0.0;
+    for (int a = lane; a < A; a += 32) {
+        if (!p.heavy[a]) continue;
+        const double px = rx[a], py = ry[a], pz = rz[a], qx = cx[a], qy = cy[a], qz = cz[a];
+        S[0] = fma(px, qx, S[0]); S[1] = fma(px, qy, S[1]); S[2] = fma(px, qz, S[2]);
+        S[3] = fma(py, qx, S[3]); S[4] = fma(py, qy, S[4]); S[5] = fma(py, qz, S[5]);
+        S[6] = fma(pz, qx, S[6]); S[7] = fma(pz, qy, S[7]); S[8] = fma(pz, qz, S[8]);
+        cnt += 1.0;
+    }
+#pragma unroll
+    for (int c = 0; c < 9; c++) S[c] = warp_sum(S[c]);
+    cnt = warp_sum(cnt);
+    double R[9];
+    kabsch_rot_from_cov(S, R, nullptr, nullptr);
+    double ss = 0.0;
+    for (int a = lane; a < A; a += 32) {
+        if (!p.heavy[a]) continue;
+        const double px = rx[a], py = ry[a], pz = rz[a];
+        const double dx = fma(R[0], px, fma(R[1], py, R[2] * pz)) - cx[a];
+        const double dy = fma(R[3], px, fma(R[4], py, R[5] * pz)) - cy[a];
+        const double dz = fma(R[6], px, fma(R[7], py, R[8] * pz)) - cz[a];
+        ss += fma(dx, dx, fma(dy, dy, dz * dz));
+    }
+    ss = warp_sum(ss);
+    code_out = code;
+    return sqrt(ss / cnt);
+}
+
+// rotation / sub-graph masks of every atom as one word (see rotcorr_eval2), into shared memory
+__device__ __forceinline__ void stage_abits(const RotCorrParams& p, uint32_t* abits) {
+    for (int a = threadIdx.x; a < p.A; a += blockDim.x) {
+        uint32_t w = 0;
+        for (int t = 0; t < p.T; t++) {
+            if (p.rot_mask[(size_t)t * p.A + a]) w |= 1u << t;
+            if (p.node_mask[(size_t)t * p.A + a]) w |= 1u << (16 + t);
+        }
+        abits[a] = w;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Forward scan (stateless mode, large N).  The grouping loop (torsion_module.py:1098-1125) walks, for
+// every first structure i, the later structures j in order and stops at the first similar one; pairs it
+// found dissimilar are cached and never looked at again.  With a stateless pair function the only facts
+// the loop ever uses about row i are therefore  first_hit[i] = min{ j > i : rmsd(i, j) < max_rmsd }  and
+// the best-angle codes of the pairs (i, j <= first_hit[i]) it mutates on the way.  One CTA per row
+// (rows handed out through an atomic counter), its 8 warps evaluating 8 consecutive j at a time until a
+// batch contains a hit: a redundant ensemble needs a few dozen pairs per row instead of N - i.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RC_WARPS * 32) rotcorr_scan_kernel(const RotCorrParams p, int32_t* __restrict__ first_hit,
+                                                                     int32_t* __restrict__ row_counter) {
+    extern __shared__ double smem[];
+    __shared__ int s_row, s_hit;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int A = p.A;
+    double* rx = smem;                                      // first structure, shared by the warps
+    double* ry = rx + A; double* rz = ry + A;
+    double* cx = rz + A + (size_t)warp * 3 * A;             // second structure, per warp
+    double* cy = cx + A; double* cz = cy + A;
+    uint32_t* abits = reinterpret_cast<uint32_t*>(smem + (size_t)(3 + 3 * RC_WARPS) * A);
+    stage_abits(p, abits);
+    unsigned long long near = 0;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) { s_row = atomicAdd(row_counter, 1); s_hit = 0x7fffffff; }
+        __syncthreads();
+        const int64_t i = p.row_begin + s_row;
+        if (i >= p.row_end) break;
+        const double* Pi = p.Sc + i * (int64_t)A * 3;
+        for (int a = threadIdx.x; a < A; a += blockDim.x) { rx[a] = Pi[3 * a]; ry[a] = Pi[3 * a + 1]; rz[a] = Pi[3 * a + 2]; }
+        __syncthreads();
+        for (int64_t j0 = i + 1; j0 < p.N; j0 += RC_WARPS) {
+            const int64_t j = j0 + warp;
+            if (j < p.N) {
+                const double* Pj = p.Sc + j * (int64_t)A * 3;
+                for (int a = lane; a < A; a += 32) { cx[a] = Pj[3 * a]; cy[a] = Pj[3 * a + 1]; cz[a] = Pj[3 * a + 2]; }
+                __syncwarp();
+                uint32_t code;
+                const double rmsd = rotcorr_eval2(p, abits, rx, ry, rz, cx, cy, cz, lane, code);
+                if (lane == 0) {
+                    if (p.codes) p.codes[i * p.N + j] = code;
+                    if (p.rmsd_out) p.rmsd_out[i * p.N + j] = rmsd;
+                    if (rmsd < p.max_rmsd) atomicMin(&s_hit, (int)j);
+                    near += fabs(rmsd - p.max_rmsd) < 1e-6;
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+            if (s_hit != 0x7fffffff) break;
+        }
+        if (threadIdx.x == 0) first_hit[i] = (s_hit == 0x7fffffff) ? (int32_t)p.N : s_hit;
+    }
+    if (lane == 0 && near && p.near_count) atomicAdd(p.near_count, near);
+}
+
 __global__ void __launch_bounds__(RC_WARPS * 32) rotcorr_pairs_kernel(const RotCorrParams p) {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -167,6 +351,9 @@ __global__ void __launch_bounds__(RC_WARPS * 32) rotcorr_pairs_kernel(const RotC
     double* rx = smem + (size_t)warp * 6 * A;
     double* ry = rx + A; double* rz = ry + A;
     double* cx = rz + A; double* cy = cx + A; double* cz = cy + A;
+    uint32_t* abits = reinterpret_cast<uint32_t*>(smem + (size_t)RC_WARPS * 6 * A);
+    stage_abits(p, abits);
+    __syncthreads();
     const int64_t warp_g = (int64_t)blockIdx.x * RC_WARPS + warp;
     const int64_t nwarps = (int64_t)gridDim.x * RC_WARPS;
     const int64_t nrows = p.row_end - p.row_begin;
@@ -183,7 +370,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) rotcorr_pairs_kernel(const RotC
         }
         __syncwarp();
         uint32_t code;
-        const double rmsd = rotcorr_eval(p, rx, ry, rz, cx, cy, cz, lane, code);
+        const double rmsd = rotcorr_eval2(p, abits, rx, ry, rz, cx, cy, cz, lane, code);
         if (lane == 0) {
             if (rmsd < p.max_rmsd) atomicOr(&p.sim_bits[i * p.Wb + (j >> 5)], 1u << (j & 31));
             if (p.codes) p.codes[i * p.N + j] = code;
@@ -291,7 +478,7 @@ extern "C" int tsc_rotcorr_pairs(const double* Sc, int64_t N, int32_t A, const u
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(sim_bits + row_begin * p.Wb, 0, (size_t)(row_end - row_begin) * p.Wb * 4, st);
     if (e != cudaSuccess) return (int)e;
-    const size_t smem = (size_t)RC_WARPS * 6 * A * sizeof(double);
+    const size_t smem = (size_t)RC_WARPS * 6 * A * sizeof(double) + (size_t)A * 4;
     if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
     e = cudaFuncSetAttribute(rotcorr_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -348,6 +535,34 @@ extern "C" int tsc_rotcorr_commit(double* cur, const double* staged, const int32
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     tsc::rotcorr_commit_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cur, staged, js, n_accept, A * 3);
+    TSC_CHECK_LAUNCH();
+    return 0;
+}
+
+// Forward scan of rows [row_begin, row_end): first_hit[i] = first j > i with rmsd(i, j) < max_rmsd (N if none);
+// codes / rmsd_out (dense (N, N), may be NULL) are written for the pairs evaluated on the way (at least every
+// j <= first_hit[i]).  row_counter: one int32 of scratch.
+extern "C" int tsc_rotcorr_scan(const double* Sc, int64_t N, int32_t A, const uint8_t* heavy, int32_t T,
+                                const int32_t* tor_i2, const int32_t* tor_i3, const int32_t* n_ang,
+                                const double* sin_half, const double* cos_half, const uint8_t* rot_mask,
+                                const uint8_t* node_mask, int64_t row_begin, int64_t row_end, double max_rmsd,
+                                int32_t* first_hit, uint32_t* codes, double* rmsd_out, uint64_t* near_count,
+                                int32_t* row_counter, void* stream) {
+    using namespace tsc;
+    if (N <= 0 || row_end <= row_begin) return 0;
+    if (T < 0 || T > RC_MAX_T) return (int)cudaErrorInvalidValue;
+    RotCorrParams p{Sc, N, A, heavy, T, tor_i2, tor_i3, n_ang, sin_half, cos_half, rot_mask, node_mask, row_begin,
+                    row_end, max_rmsd, nullptr, 0, codes, rmsd_out, reinterpret_cast<unsigned long long*>(near_count)};
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(row_counter, 0, 4, st);
+    if (e != cudaSuccess) return (int)e;
+    const size_t smem = (size_t)(3 + 3 * RC_WARPS) * A * sizeof(double) + (size_t)A * 4;
+    if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
+    e = cudaFuncSetAttribute(rotcorr_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int64_t blocks = row_end - row_begin;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    rotcorr_scan_kernel<<<(unsigned)blocks, RC_WARPS * 32, smem, st>>>(p, first_hit, row_counter);
     TSC_CHECK_LAUNCH();
     return 0;
 }

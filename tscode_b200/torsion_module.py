@@ -135,6 +135,44 @@ class RotCorrPruner:
                                       ptr(self.sim_bits), ptr(self.codes), ptr(self.rmsd), ptr(self.near),
                                       stream_ptr()), "tsc_rotcorr_pairs")
 
+    def scan(self):
+        """Forward scan (tsc_rotcorr_scan): returns (first_hit (N,) int64 numpy, lookup) where
+        first_hit[i] is the first j > i similar to i (N if none) and lookup(i, js) gives the best
+        rotor angles (len(js), T) of the pairs (i, j <= first_hit[i]) — all the grouping loop needs
+        in stateless mode.  The codes are compacted on the device before they cross PCIe."""
+        torch, N, T = self.torch, self.N, self.info.T
+        dev = self.dev
+        if self.codes is None:
+            self.codes = torch.zeros((N, N), dtype=torch.int32, device=dev)
+        first = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+        counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.near.zero_()
+        check(lib().tsc_rotcorr_scan(ptr(self.Sc), N, self.A, ptr(self.heavy), T, ptr(self.i2), ptr(self.i3),
+                                     ptr(self.n_ang), ptr(self.sin_half), ptr(self.cos_half), ptr(self.rot_mask),
+                                     ptr(self.node_mask), 0, N, self.max_rmsd, ptr(first), ptr(self.codes), ptr(self.rmsd),
+                                     ptr(self.near), ptr(counter), stream_ptr()), "tsc_rotcorr_scan")
+        rows = torch.arange(N, device=dev, dtype=torch.int64)
+        last = torch.clamp(first[:N].to(torch.int64), max=N - 1)               # last column the loop can visit
+        lengths = torch.clamp(last - rows, min=0)
+        offsets = torch.cumsum(lengths, 0) - lengths
+        total = int(lengths.sum().item())
+        if total:
+            r = torch.repeat_interleave(rows, lengths)
+            c = torch.arange(total, device=dev, dtype=torch.int64) - offsets[r] + r + 1
+            compact = self.codes.view(-1)[r * N + c].cpu().numpy().view(np.uint32)
+        else:
+            compact = np.zeros(0, np.uint32)
+        off = offsets.cpu().numpy()
+        table = self.ang_table
+
+        def lookup(i, js):
+            cc = compact[off[i] + (np.asarray(js) - i - 1)]
+            return np.stack([table[t][(cc >> (3 * t)) & 7] for t in range(T)], axis=-1)
+        lookup.T = T
+        lookup.compact, lookup.off, lookup.table = compact, np.ascontiguousarray(off, dtype=np.int64), table
+        self.pairs_evaluated = total
+        return first[:N].cpu().numpy().astype(np.int64), lookup
+
     def similar_matrix(self):
         """(N, N) bool, upper triangle, on the host."""
         bits = self.sim_bits.cpu().numpy().view(np.uint32)
@@ -291,14 +329,100 @@ def ladder_replay(similar, N, best_angles=None, verbose=False):
     return final_mask, state
 
 
+def ladder_replay_scan(first_hit, N, best_angles=None, verbose=False, native=None):
+    """The grouping loop (torsion_module.py:1076-1152) driven by first_hit[i] = first later structure
+    similar to i (N if none) instead of a similarity matrix.  Equivalent to ladder_replay: the pairs row
+    i has cached (visited and found dissimilar) always form a prefix (i, reach[i]] of its columns, so a
+    visit of row i in a chunk ending at `hi` touches the new columns (reach[i], min(first_hit, hi) - 1]
+    — cached from then on — plus first_hit[i] itself when it lies inside the chunk (similar pairs are
+    never cached: the reference re-evaluates and re-mutates them in every round).
+    The per-row part of a chunk runs in C on the host (tsc_host_rotcorr_chunk) when `best_angles` comes
+    from RotCorrPruner.scan(); the Python form below is the same loop and serves as its check.
+    Returns (final_mask, state (N, T) degrees)."""
+    import ctypes
+    import networkx as nx
+    first_hit = np.ascontiguousarray(first_hit, dtype=np.int64)
+    final_mask = np.ones(N, dtype=bool)
+    reach = np.arange(N, dtype=np.int64)
+    T = best_angles.T if best_angles is not None else 0
+    state = np.zeros((N, max(T, 0)))
+    if native is None:
+        native = best_angles is not None and hasattr(best_angles, "compact")
+    if native:
+        L = lib()
+        compact = np.ascontiguousarray(best_angles.compact, dtype=np.uint32)
+        if compact.size == 0:
+            compact = np.zeros(1, np.uint32)
+        off = best_angles.off
+        table = np.ascontiguousarray(best_angles.table, dtype=np.float64)
+        assert table.shape[1] == MAX_ANG
+        mi, mj = np.empty(max(N, 1), np.int32), np.empty(max(N, 1), np.int32)
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        p_first, p_reach, p_state, p_compact, p_off, p_table, p_mi, p_mj = (vp(a) for a in (
+            first_hit, reach, state, compact, off, table, mi, mj))           # the arrays never move
+    for k in _host.LADDER:
+        num_active = int(np.count_nonzero(final_mask))
+        if not (k == 1 or 5 * k < num_active):                                     # :1083
+            continue
+        if verbose:
+            print(f"Working on subgroups with k={k} ({num_active} candidates left) {' ' * 10}", end="\r")
+        d = int(N // k)
+        for step in range(int(k)):
+            if step == k - 1:
+                _l = len(range(d * step, num_active))                              # :1093-1094 (quirk kept)
+            else:
+                _l = len(range(d * step, int(d * (step + 1))))
+            if _l <= 1:
+                continue
+            base = d * step
+            hi = base + _l
+            matches = set()
+            if native:
+                n = int(L.tsc_host_rotcorr_chunk(base, hi, p_first, p_reach, p_state, T, p_compact, p_off, p_table,
+                                                 p_mi, p_mj))
+                for a, b in zip(mi[:n].tolist(), mj[:n].tolist()):                 # same insertion order (:1119-1120)
+                    matches.add((a, b))
+            else:
+                fh = first_hit[base:hi]
+                new_hi = np.minimum(fh - 1, hi - 1)
+                todo = np.flatnonzero((new_hi > reach[base:hi]) | (fh < hi))
+                for i_rel in todo.tolist():
+                    i = base + i_rel
+                    p = int(fh[i_rel])
+                    nh = int(new_hi[i_rel])
+                    lo = int(reach[i]) + 1
+                    hit = p < hi
+                    if nh >= lo:
+                        js = np.arange(lo, nh + 1)
+                        if hit:
+                            js = np.append(js, p)
+                        reach[i] = nh
+                    elif hit:
+                        js = np.array([p])
+                    else:
+                        continue
+                    if T:                                                           # in-place mutation (:1004-1008)
+                        state[js] = (best_angles(i, js) + state[i]) % 360.0
+                    if hit:
+                        matches.add((i_rel, p - base))                              # :1119-1120
+            if not matches:
+                continue
+            g = nx.Graph(matches)                                                  # :1136
+            groups = [tuple(g.subgraph(c).nodes) for c in nx.connected_components(g)]
+            for group in groups:                                                   # :1141-1152
+                for r in set(group) - {group[0]}:
+                    final_mask[r + base] = 0
+    return final_mask, state
+
+
 def prune_conformers_rmsd_rot_corr(structures, atomnos, graph, max_rmsd=0.25, verbose=False, logfunction=None,
                                    *, torsion_info: TorsionInfo | None = None, max_structures=750, mode=None):
     """Drop-in for tscode.torsion_module.prune_conformers_rmsd_rot_corr (:1013-1161).
 
     mode "exact" (default up to 2000 structures): row-by-row replay from the current, mutated
     coordinates — same visiting order, same mutations, same returned structures as the reference.
-    mode "stateless" (default above): all pairs at once from the centred input + host replay with
-    rotor-state algebra; masks agree with the reference on every fixture, but for rotors whose
+    mode "stateless" (default above): pairs evaluated from the centred input — a forward scan per row
+    up to its first similar partner (mode "allpairs": every pair) — + host replay with rotor-state algebra; masks agree with the reference on every fixture, but for rotors whose
     n-fold images differ only at noise level (e.g. a methyl-capped alkyne: the heavy atoms sit on
     the axis) the hydrogens of the returned structures may end up in another image."""
     structures = np.array([s - s.mean(axis=0) for s in np.asarray(structures, dtype=np.float64)])     # :1023
@@ -322,9 +446,14 @@ def prune_conformers_rmsd_rot_corr(structures, atomnos, graph, max_rmsd=0.25, ve
         pr = RotCorrPruner(structures, atomnos, info, max_rmsd, want_codes=False)
         out, mask, _ = pr.prune_stateful(verbose=verbose)
         return out, mask
-    pr = RotCorrPruner(structures, atomnos, info, max_rmsd)
-    pr.similarity()
-    mask, state = ladder_replay(pr.similar_matrix(), N, pr.best_angles(), verbose=verbose)
+    if mode == "allpairs":             # every pair evaluated (cross-check of the scan; O(N^2) whatever the data)
+        pr = RotCorrPruner(structures, atomnos, info, max_rmsd)
+        pr.similarity()
+        mask, state = ladder_replay(pr.similar_matrix(), N, pr.best_angles(), verbose=verbose)
+    else:
+        pr = RotCorrPruner(structures, atomnos, info, max_rmsd, want_codes=False)
+        first_hit, lookup = pr.scan()
+        mask, state = ladder_replay_scan(first_hit, N, lookup, verbose=verbose)
     keep = np.flatnonzero(mask)
     out = pr.apply_states(keep, state[keep])
     return out, mask
