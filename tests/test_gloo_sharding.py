@@ -154,3 +154,41 @@ def test_two_rank_pair_list_exchange_matches_single(N, seed):
     ref, _, rounds = oracle_c.prune_heavy(np.zeros((N, 1, 3)), 0.5, sim_bytes=sim.astype(np.uint8))
     assert ran == [int(k) for k in rounds]
     assert np.array_equal(mask, ref)
+
+
+def _worker_varlen(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    from tscode_b200.embeds import gather_varlen, pose_range
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P = 1003
+    lo, hi = pose_range(P, rank, world)
+    rng = np.random.default_rng(7)
+    verdict = rng.random(P) < 0.13                      # the clash screen's verdicts (same on every rank here)
+    poses = rng.normal(size=(P, 5, 3))
+    mine = torch.from_numpy(poses[lo:hi][verdict[lo:hi]])
+    got = gather_varlen(mine, world)
+    if rank == 0:
+        q.put((got.numpy(), poses[verdict]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_variable_length_survivor_gather_keeps_pose_order():
+    """Phase-1 -> phase-2 exchange of screen_and_prune: survivors of contiguous pose ranges, gathered with
+    counts first, come back in global pose order on every rank (also with an empty rank)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_varlen, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got, want = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(got, want)
+    from tscode_b200.embeds import pose_range
+    assert [pose_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert pose_range(2, 3, 4) == (2, 2)

@@ -439,3 +439,23 @@ def test_rot_corr_guard_and_no_rotors(gpu):
     # guard lifted: beyond the reference's own limit, checked against the oracle's literal model instead
     out2, mask2 = prune_conformers_rmsd_rot_corr(big, atomnos, None, torsion_info=info, max_structures=None)
     assert mask2.sum() < 20
+
+
+def test_screen_and_prune_pipeline_vs_oracle(gpu):
+    """embeds.screen_and_prune (clash screen -> survivors -> RMSD prune) against the oracle, one GPU."""
+    from oracle import oracle_c
+    from tscode_b200.embeds import screen_and_prune
+    from tscode_b200.synth import gen_poses
+    frags, conf, R, t = gen_poses(5, 30000, (20, 25, 15), n_conf=3)
+    atomnos = np.full(60, 6)
+    res = screen_and_prune(frags, conf, R, t, atomnos, 1.5, 0, 0.5)
+    v = res["verdict"].cpu().numpy()
+    ref_v = oracle_c.embed_clash_batch(frags, conf, R, t, 1.5, 0)
+    assert np.array_equal(v, ref_v) and 10 < v.sum() < 30000
+    keep = np.flatnonzero(ref_v)
+    assert np.array_equal(res["keep"].cpu().numpy(), keep)
+    poses = res["poses"].cpu().numpy()
+    ref_poses = np.stack([oracle_c.get_embed(frags, conf[p], R[p], t[p]) for p in keep[:50]])
+    assert np.abs(poses[:50] - ref_poses).max() < 1e-12
+    ref_mask, _, _ = oracle_c.prune_heavy(poses, 0.5)
+    assert np.array_equal(res["mask"].cpu().numpy(), ref_mask)
