@@ -121,6 +121,18 @@ int tsc_rmsd_verify(const double* packed, int64_t N, int32_t M, const int32_t* r
 int tsc_rmsd_pairs(const double* P, const double* Q, int64_t n, int32_t M, int32_t broadcast_p,
                    double* rmsd, double* maxdev, void* stream);
 
+/* Group-local de-duplication inside the cyclical embeds (embeds.py:714-718, 842-846): a pose that passed the clash
+ * test is kept iff _rmsd_similarity(pose, kept poses of its group, rmsd_thr) is False (rmsd_pruning.py:208-224,
+ * all atoms).  tsc_rmsd_pairs_idx evaluates the similarity of explicit index pairs (pi[k] = later pose = `ref`,
+ * pj[k] = earlier pose) of one pose array S (P, M, 3); tsc_group_greedy replays the sequential keep/append logic,
+ * one thread per group: members [g_begin[g], g_begin[g+1]) of `order` (pose indices in generation order), the
+ * pairs of member m stored at sim[pair_base[m] + r], r = rank of the earlier member inside the group.
+ * keep (P) uint8 must be zeroed first (non-members stay 0). */
+int tsc_rmsd_pairs_idx(const double* S, const int32_t* pi, const int32_t* pj, int64_t n, int32_t M, double thr,
+                       uint8_t* sim, void* stream);
+int tsc_group_greedy(const int32_t* g_begin, int32_t n_groups, const int32_t* order, const int64_t* pair_base,
+                     const uint8_t* sim, uint8_t* keep, void* stream);
+
 /* One ladder round (rmsd_pruning.py:123-162) in three steps; cs = int(N // k) (:136).
  *   gate (device, 1 int32, or NULL): number of active structures BEFORE this round.  When given,
  *   every kernel first evaluates the reference's gate `k == 1 or 20*k < active` (:192) and does
@@ -179,6 +191,19 @@ int tsc_clash_structs(const double* S, int64_t P, int32_t A, const int32_t* ids,
 int tsc_embed_gather(const double* frag_lib, const int64_t* frag_off, const int32_t* n_atoms, int32_t F,
                      int32_t A_total, const int32_t* conf, const double* R, const double* t,
                      const int64_t* keep_idx, int64_t n_keep, double* S_out, void* stream);
+
+/* Pose parameters of the string embed generated on the device (embeds.py:91-114):
+ *   mol2.rotation = rot_mat_from_pointer(ref_vec, angle) @ rotation_matrix_from_vectors(mol_vec, -ref_vec)
+ *   (first factor only for angle != 0; utils.py:183-208, algebra.py:325-344), mol2.position = p1 - rotation @ p2,
+ * for the whole pose space conformers (c1, c2) x reactive centres (ai1, ai2) x angles in the reference's loop
+ * order, P = n_conf1*n_conf2*n_c1*n_c2*n_ang.  centers1/vecs1 (n_conf1, n_c1, 3) = ra1.center / ra1.orb_vecs of
+ * every conformer of molecule 1, centers2/vecs2 likewise; sin_half/cos_half (n_ang) = sin, cos of angle/2 in
+ * radians evaluated on the host, nonzero (n_ang) uint8 = angle != 0; flip (9) = rot_mat_from_pointer([0,0,1], 180)
+ * evaluated on the host.  Out: conf (P, 2) int32, R (P, 2, 3, 3), t (P, 2, 3) as tsc_embed_clash reads them. */
+int tsc_string_embed_params(const double* centers1, const double* vecs1, const double* centers2,
+                            const double* vecs2, int32_t n_conf1, int32_t n_conf2, int32_t n_c1, int32_t n_c2,
+                            const double* sin_half, const double* cos_half, const uint8_t* nonzero,
+                            int32_t n_ang, const double* flip, int32_t* conf, double* R, double* t, void* stream);
 
 /* ---- prune_conformers_rmsd_rot_corr ---------------------------------------------------------- */
 /* Rotor-corrected RMSD of every pair (i in [row_begin,row_end), j > i), stateless from the centred

@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
 import ref_harness  # noqa: E402
-from tscode_b200.synth import gen_ensemble, gen_poses, materialise_poses, mask_digest  # noqa: E402
+from tscode_b200.synth import gen_ensemble, gen_poses, gen_pose_groups, materialise_poses, mask_digest  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 
@@ -106,6 +106,51 @@ def main():
         json.dump({"seed": 21, "N": 64, "M": 30, "n_clusters": 6, "sigma_noise": 0.2, "rmsd_thr": 1.0,
                    "window": 8, "out": out}, open(os.path.join(GOLD, "rmsd_similarity.json"), "w"))
         print("simlist:", sum(out), "of", len(out))
+
+    # ---- (f)-1: the clash test + group-local de-duplication of the cyclical embeds (embeds.py:713-718) ------
+    if want("dedup"):
+        rows = []
+        for r in (dict(seed=31, n_groups=60, steps=12, n_atoms=(30, 30), thresh=1.5, rmsd_thr=1.0),
+                  dict(seed=32, n_groups=25, steps=36, n_atoms=(20, 45), thresh=1.3, rmsd_thr=1.0),
+                  dict(seed=33, n_groups=40, steps=8, n_atoms=(12, 9), thresh=1.0, rmsd_thr=0.6)):
+            frags, conf, R, t, gid = gen_pose_groups(r["seed"], r["n_groups"], r["steps"], r["n_atoms"])
+            S = materialise_poses(frags, conf, R, t)
+            ids = np.array(r["n_atoms"])
+            keep, passed = np.zeros(len(S), np.uint8), np.zeros(len(S), np.uint8)
+            for g in range(r["n_groups"]):
+                angular_poses = []
+                for p in np.flatnonzero(gid == g):
+                    if compenetration_check(S[p], ids=ids, thresh=r["thresh"]):           # embeds.py:713
+                        passed[p] = 1
+                        if not _rmsd_similarity(S[p], angular_poses, rmsd_thr=r["rmsd_thr"]):   # :714
+                            angular_poses.append(S[p]); keep[p] = 1
+            rows.append(dict(r, passed=int(passed.sum()), kept=int(keep.sum()),
+                             passed_hex=np.packbits(passed).tobytes().hex(), keep_hex=np.packbits(keep).tobytes().hex()))
+            print("dedup:", {k: v for k, v in rows[-1].items() if not k.endswith("_hex")})
+        json.dump({"meta": meta, "rows": rows}, open(os.path.join(GOLD, "dedup_groups.json"), "w"), indent=1)
+
+    # ---- (f)-2: pose parameters of the string embed (embeds.py:91-114) with the reference's own builders ----
+    if want("stringembed"):
+        rng = np.random.default_rng(77)
+        n_conf1, n_conf2, n_c1, n_c2 = 3, 2, 2, 3
+        c1, c2 = rng.normal(size=(n_conf1, n_c1, 3)) * 2, rng.normal(size=(n_conf2, n_c2, 3)) * 2
+        v1, v2 = rng.normal(size=(n_conf1, n_c1, 3)), rng.normal(size=(n_conf2, n_c2, 3))
+        v2[0, 0] = -v1[0, 0] * 1.7            # mol_vec parallel to -ref_vec: identity branch (utils.py:207)
+        v2[1, 1] = v1[1, 0] * 0.4             # mol_vec antiparallel to -ref_vec: 180 degree flip (utils.py:203-205)
+        angles = [0, 30, 90, 120, 240, 345.5]
+        Rs, ts = [], []
+        for a in range(n_conf1):
+            for b in range(n_conf2):
+                for ai1 in range(n_c1):
+                    for ai2 in range(n_c2):
+                        for angle in angles:
+                            rot = rotation_matrix_from_vectors(v2[b, ai2], -v1[a, ai1])
+                            if angle != 0:
+                                rot = rot_mat_from_pointer(v1[a, ai1], angle) @ rot
+                            Rs.append(rot); ts.append(c1[a, ai1] - rot @ c2[b, ai2])
+        np.savez_compressed(os.path.join(GOLD, "string_embed_params.npz"), c1=c1, c2=c2, v1=v1, v2=v2,
+                            angles=np.array(angles), R=np.array(Rs), t=np.array(ts))
+        print("stringembed:", len(Rs), "poses")
 
     # ---- A7/A8: get_embed + compenetration_check ---------------------------------------------
     if want("clash"):

@@ -146,6 +146,24 @@ def rotation_matrix_from_vectors(vec1, vec2):
     return np.eye(3)
 
 
+def string_embed_params(centers, vecs, angles):
+    """Pose parameters of the string embed, embeds.py:91-114: loop order conformer pairs (cartesian_product:
+    first index major), centre pairs, angles.  Returns (conf (P, 2), R (P, 2, 3, 3), t (P, 2, 3))."""
+    (c1, c2), (v1, v2) = centers, vecs
+    conf, R, t = [], [], []
+    for a in range(c1.shape[0]):
+        for b in range(c2.shape[0]):
+            for ai1 in range(c1.shape[1]):
+                for ai2 in range(c2.shape[1]):
+                    for angle in angles:
+                        p1, p2, ref_vec, mol_vec = c1[a, ai1], c2[b, ai2], v1[a, ai1], v2[b, ai2]
+                        rot = rotation_matrix_from_vectors(mol_vec, -ref_vec)          # :103
+                        if angle != 0:                                                # :105-107
+                            rot = rot_mat_from_pointer(ref_vec, angle) @ rot
+                        conf.append((a, b)); R.append((np.eye(3), rot)); t.append((np.zeros(3), p1 - rot @ p2))   # :109
+    return np.array(conf), np.array(R), np.array(t)
+
+
 def align_vec_pair(ref, tgt):
     """algebra.py:258-282."""
     B = np.einsum("ji,jk->ik", np.asarray(ref, float), np.asarray(tgt, float))

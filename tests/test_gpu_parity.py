@@ -459,3 +459,49 @@ def test_screen_and_prune_pipeline_vs_oracle(gpu):
     assert np.abs(poses[:50] - ref_poses).max() < 1e-12
     ref_mask, _, _ = oracle_c.prune_heavy(poses, 0.5)
     assert np.array_equal(res["mask"].cpu().numpy(), ref_mask)
+
+
+def test_dedup_groups_vs_live_reference(gpu):
+    """(f)-1: fused clash screen + group-local de-duplication (embeds.dedup_groups) against the keep masks of the
+    live reference's sequential loop (embeds.py:713-718)."""
+    from tscode_b200.embeds import dedup_groups
+    from tscode_b200.numba_functions import PoseBatch
+    from tscode_b200.synth import gen_pose_groups
+    rows = json.load(open(os.path.join(GOLDEN, "dedup_groups.json")))["rows"]
+    for r in rows:
+        frags, conf, R, t, gid = gen_pose_groups(r["seed"], r["n_groups"], r["steps"], tuple(r["n_atoms"]))
+        P = conf.shape[0]
+        want_pass = np.unpackbits(np.frombuffer(bytes.fromhex(r["passed_hex"]), np.uint8))[:P]
+        want_keep = np.unpackbits(np.frombuffer(bytes.fromhex(r["keep_hex"]), np.uint8))[:P]
+        pb = PoseBatch(frags, conf, R, t)
+        passed = pb.clash(r["thresh"], 0)
+        assert np.array_equal(passed.cpu().numpy(), want_pass)
+        keep = dedup_groups(pb.gather(None, P), gid, passed.bool(), r["rmsd_thr"])
+        assert np.array_equal(keep.cpu().numpy().astype(np.uint8), want_keep), r["seed"]
+    # all-pass form and degenerate inputs
+    keep = dedup_groups(pb.gather(None, P), gid, None, 1e-9)
+    assert bool(keep.all())                                      # nothing is similar at a vanishing threshold
+    assert dedup_groups(np.zeros((0, 5, 3)), np.zeros(0, int)).numel() == 0
+    with pytest.raises(ValueError):
+        dedup_groups(np.zeros((3, 5, 3)), np.array([1, 0, 0]))
+
+
+def test_string_embed_params_on_device_vs_live_reference(gpu):
+    """(f)-2: tsc_string_embed_params against the R, t the live reference's builders produced; tolerance 1e-13 (the
+    3x3 products are evaluated in a different summation order than numpy's BLAS), then the generated PoseBatch
+    through the clash screen against the oracle."""
+    from oracle import oracle_c, oracle_np
+    from tscode_b200.embeds import string_embed_poses
+    g = np.load(os.path.join(GOLDEN, "string_embed_params.npz"))
+    rng = np.random.default_rng(3)
+    frags = [rng.normal(size=(3, 14, 3)) * 1.5, rng.normal(size=(2, 11, 3)) * 1.5]
+    pb = string_embed_poses(frags, (g["c1"], g["c2"]), (g["v1"], g["v2"]), list(g["angles"]))
+    assert pb.P == g["R"].shape[0]
+    R, t, conf = pb.R.cpu().numpy(), pb.t.cpu().numpy(), pb.conf.cpu().numpy()
+    assert np.abs(R[:, 1] - g["R"]).max() < 1e-13 and np.abs(t[:, 1] - g["t"]).max() < 1e-13
+    assert np.array_equal(R[:, 0], np.broadcast_to(np.eye(3), R[:, 0].shape)) and not t[:, 0].any()
+    oc, oR, ot = oracle_np.string_embed_params((g["c1"], g["c2"]), (g["v1"], g["v2"]), list(g["angles"]))
+    assert np.array_equal(conf, oc)
+    v = pb.clash(1.2, 0).cpu().numpy()
+    ref = oracle_c.embed_clash_batch(frags, oc, np.ascontiguousarray(R), np.ascontiguousarray(t), 1.2, 0)
+    assert np.array_equal(v, ref)

@@ -118,3 +118,35 @@ def test_get_embed_and_rotation_builders():
         assert np.abs(oracle_np.rotation_matrix_from_vectors(g["v1"][i], g["v2"][i]) - g["rmv"][i]).max() < 1e-12
         assert np.abs(oracle_np.rot_mat_from_pointer(g["v1"][i], g["ang"][i]) - g["rmp"][i]).max() < 1e-12
         assert np.abs(oracle_np.align_vec_pair(g["ref"][i], g["tgt"][i]) - g["avp"][i]).max() < 1e-10
+
+
+def test_oracle_dedup_groups_vs_live_reference():
+    """(f)-1: clash test + group-local `_rmsd_similarity` de-duplication of the cyclical embeds
+    (embeds.py:713-718), oracle loop against the masks the live reference produced."""
+    from tscode_b200.synth import gen_pose_groups, materialise_poses
+    rows = json.load(open(os.path.join(GOLDEN, "dedup_groups.json")))["rows"]
+    for r in rows:
+        frags, conf, R, t, gid = gen_pose_groups(r["seed"], r["n_groups"], r["steps"], tuple(r["n_atoms"]))
+        S = materialise_poses(frags, conf, R, t)
+        ids = np.array(r["n_atoms"])
+        want_pass = np.unpackbits(np.frombuffer(bytes.fromhex(r["passed_hex"]), np.uint8))[:len(S)]
+        want_keep = np.unpackbits(np.frombuffer(bytes.fromhex(r["keep_hex"]), np.uint8))[:len(S)]
+        keep, passed = np.zeros(len(S), np.uint8), np.zeros(len(S), np.uint8)
+        for g in range(r["n_groups"]):
+            kept = []
+            for p in np.flatnonzero(gid == g):
+                if oracle_c.compenetration_check(S[p], ids, r["thresh"], 0):
+                    passed[p] = 1
+                    if not oracle_c.rmsd_similarity(S[p], kept, r["rmsd_thr"]):
+                        kept.append(S[p]); keep[p] = 1
+        assert np.array_equal(passed, want_pass) and np.array_equal(keep, want_keep)
+
+
+def test_oracle_string_embed_params_vs_live_reference():
+    """(f)-2: pose parameters of the string embed (embeds.py:91-114), numpy oracle vs the live reference's builders,
+    including the parallel (identity) and antiparallel (180 degree flip) branches of rotation_matrix_from_vectors."""
+    g = np.load(os.path.join(GOLDEN, "string_embed_params.npz"))
+    conf, R, t = oracle_np.string_embed_params((g["c1"], g["c2"]), (g["v1"], g["v2"]), list(g["angles"]))
+    assert R.shape[0] == g["R"].shape[0] == 3 * 2 * 2 * 3 * 6
+    assert np.abs(R[:, 1] - g["R"]).max() < 1e-14 and np.abs(t[:, 1] - g["t"]).max() < 1e-13
+    assert np.array_equal(R[:, 0], np.broadcast_to(np.eye(3), R[:, 0].shape)) and not t[:, 0].any()

@@ -40,6 +40,8 @@ SIGNATURES = {
     "tsc_elim_fused_out_bytes": (_i64, [_i64]),
     "tsc_elim_fused": (C.c_int, [_vp, _i32, _i64, _i64, _i32, _vp, _vp, _vp]),
     "tsc_rmsd_pairs": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "tsc_rmsd_pairs_idx": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _f64, _vp, _vp]),
+    "tsc_group_greedy": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "tsc_elim_cachebits": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "tsc_elim_round": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "tsc_elim_commit": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -56,6 +58,8 @@ SIGNATURES = {
     "tsc_rotcorr_apply": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tsc_bench_umma": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp]),
     "tsc_bench_fp64": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "tsc_string_embed_params": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
+                                          _vp, _vp]),
     "tsc_embed_gather": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
 }
 

@@ -214,6 +214,93 @@ static int clash_grid(int64_t P) {
     return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
+// ------------------------------------------------------------------------------------------
+// On-device pose parameters of the string embed (tscode/embeds.py:91-114): the reference builds, per pose and on
+// the host, mol2.rotation = rot_mat_from_pointer(ref_vec, angle) @ rotation_matrix_from_vectors(mol_vec, -ref_vec)
+// (the first factor only if angle != 0) and mol2.position = p1 - rotation @ p2, 15-60 us of numpy small-array
+// overhead each, then ships nothing: it screens the pose immediately.  Here the whole pose space
+//   conformers (c1, c2) x reactive centres (ai1, ai2) x systematic angles, in the reference's loop order,
+// is generated by one kernel into the (conf, R, t) arrays the fused clash screen consumes, so that only the
+// small per-conformer tables of centres and orbital vectors cross PCIe.
+//   c1t/v1t: (n_conf1, n_c1, 3) centres / orbital vectors of molecule 1, c2t/v2t likewise for molecule 2;
+//   sin_half/cos_half/nonzero (n_ang): host-evaluated sin, cos of angle/2 (algebra.py:337-341) and angle != 0;
+//   flip (9): rot_mat_from_pointer([0,0,1], 180) as the host evaluates it (antiparallel case, utils.py:203-205).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mat3_mul(const double A[9], const double B[9], double C[9]) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+
+__global__ void __launch_bounds__(256) string_embed_params_kernel(
+    const double* __restrict__ c1t, const double* __restrict__ v1t, const double* __restrict__ c2t,
+    const double* __restrict__ v2t, int n_conf1, int n_conf2, int n_c1, int n_c2, const double* __restrict__ sin_half,
+    const double* __restrict__ cos_half, const uint8_t* __restrict__ nonzero, int n_ang, const double* __restrict__ flip,
+    int64_t P, int32_t* __restrict__ conf, double* __restrict__ R, double* __restrict__ t) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = p;
+        const int k = (int)(r % n_ang); r /= n_ang;
+        const int ai2 = (int)(r % n_c2); r /= n_c2;
+        const int ai1 = (int)(r % n_c1); r /= n_c1;
+        const int c2 = (int)(r % n_conf2); r /= n_conf2;
+        const int c1 = (int)r;
+        const double* p1 = c1t + ((int64_t)c1 * n_c1 + ai1) * 3;
+        const double* rv = v1t + ((int64_t)c1 * n_c1 + ai1) * 3;        // ref_vec
+        const double* p2 = c2t + ((int64_t)c2 * n_c2 + ai2) * 3;
+        const double* mv = v2t + ((int64_t)c2 * n_c2 + ai2) * 3;        // mol_vec
+        // rotation_matrix_from_vectors(mol_vec, -ref_vec)                (utils.py:183-208)
+        // norms and cross product with separately rounded multiplies and adds, as numba / numpy evaluate them: for
+        // (anti)parallel vectors the cross product is pure rounding noise that Rodrigues' formula then divides by,
+        // so an FMA-contracted cross product would give a different (equally arbitrary) matrix than the reference
+        const double na = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(mv[0], mv[0]), __dmul_rn(mv[1], mv[1])), __dmul_rn(mv[2], mv[2])));
+        const double nb = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(rv[0], rv[0]), __dmul_rn(rv[1], rv[1])), __dmul_rn(rv[2], rv[2])));
+        const double a0 = mv[0] / na, a1 = mv[1] / na, a2 = mv[2] / na;
+        const double b0 = -rv[0] / nb, b1 = -rv[1] / nb, b2 = -rv[2] / nb;
+        const double vx = __dsub_rn(__dmul_rn(a1, b2), __dmul_rn(a2, b1));
+        const double vy = __dsub_rn(__dmul_rn(a2, b0), __dmul_rn(a0, b2));
+        const double vz = __dsub_rn(__dmul_rn(a0, b1), __dmul_rn(a1, b0));
+        const double s = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz)));
+        double Rv[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        if (s != 0.0) {
+            const double c = a0 * b0 + a1 * b1 + a2 * b2;
+            const double f = (1.0 - c) / (s * s);
+            const double K[9] = {0, -vz, vy, vz, 0, -vx, -vy, vx, 0};
+            double K2[9];
+            mat3_mul(K, K, K2);
+#pragma unroll
+            for (int e = 0; e < 9; e++) Rv[e] = (Rv[e] + K[e]) + K2[e] * f;
+        } else {
+            const double sx = a0 + b0, sy = a1 + b1, sz = a2 + b2;
+            if (sqrt(__dadd_rn(__dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy)), __dmul_rn(sz, sz))) == 0.0) {
+#pragma unroll
+                for (int e = 0; e < 9; e++) Rv[e] = flip[e];
+            }
+        }
+        double R2[9];
+        if (nonzero[k]) {        // delta_rot = rot_mat_from_pointer(ref_vec, angle) (algebra.py:325-344)
+            const double u0 = rv[0] / nb, u1 = rv[1] / nb, u2 = rv[2] / nb;
+            const double q1 = sin_half[k] * u0, q2 = sin_half[k] * u1, q3 = sin_half[k] * u2, q0 = cos_half[k];
+            const double D[9] = {2 * (q0 * q0 + q1 * q1) - 1, 2 * (q1 * q2 - q0 * q3),     2 * (q1 * q3 + q0 * q2),
+                                 2 * (q1 * q2 + q0 * q3),     2 * (q0 * q0 + q2 * q2) - 1, 2 * (q2 * q3 - q0 * q1),
+                                 2 * (q1 * q3 - q0 * q2),     2 * (q2 * q3 + q0 * q1),     2 * (q0 * q0 + q3 * q3) - 1};
+            mat3_mul(D, Rv, R2);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 9; e++) R2[e] = Rv[e];
+        }
+        double* Ro = R + p * 18;
+        double* to = t + p * 6;
+#pragma unroll
+        for (int e = 0; e < 9; e++) { Ro[e] = (e % 4 == 0) ? 1.0 : 0.0; Ro[9 + e] = R2[e]; }
+        to[0] = 0.0; to[1] = 0.0; to[2] = 0.0;
+        to[3] = p1[0] - (R2[0] * p2[0] + R2[1] * p2[1] + R2[2] * p2[2]);
+        to[4] = p1[1] - (R2[3] * p2[0] + R2[4] * p2[1] + R2[5] * p2[2]);
+        to[5] = p1[2] - (R2[6] * p2[0] + R2[7] * p2[1] + R2[8] * p2[2]);
+        conf[2 * p] = c1; conf[2 * p + 1] = c2;
+    }
+}
+
 }  // namespace tsc
 
 extern "C" int tsc_embed_clash(const double* frag_lib, const int64_t* frag_off, const int32_t* n_atoms, int32_t F,
@@ -277,6 +364,25 @@ extern "C" int tsc_embed_gather(const double* frag_lib, const int64_t* frag_off,
     if (blocks > 148 * 16) blocks = 148 * 16;
     embed_gather_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(frag_lib, frag_off, n_atoms, F, conf, R,
                                                                            t, keep_idx, n_keep, A_total, S_out);
+    TSC_CHECK_LAUNCH();
+    return 0;
+}
+
+// Pose parameters of the whole string-embed pose space, P = n_conf1 * n_conf2 * n_c1 * n_c2 * n_ang poses in the
+// reference's loop order (embeds.py:91-114): conf (P, 2) int32, R (P, 2, 3, 3), t (P, 2, 3), ready for
+// tsc_embed_clash / tsc_embed_gather.
+extern "C" int tsc_string_embed_params(const double* centers1, const double* vecs1, const double* centers2,
+                                       const double* vecs2, int32_t n_conf1, int32_t n_conf2, int32_t n_c1, int32_t n_c2,
+                                       const double* sin_half, const double* cos_half, const uint8_t* nonzero,
+                                       int32_t n_ang, const double* flip, int32_t* conf, double* R, double* t,
+                                       void* stream) {
+    const int64_t P = (int64_t)n_conf1 * n_conf2 * n_c1 * n_c2 * n_ang;
+    if (P <= 0) return 0;
+    int64_t blocks = (P + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    tsc::string_embed_params_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        centers1, vecs1, centers2, vecs2, n_conf1, n_conf2, n_c1, n_c2, sin_half, cos_half, nonzero, n_ang, flip, P, conf,
+        R, t);
     TSC_CHECK_LAUNCH();
     return 0;
 }

@@ -424,6 +424,47 @@ __global__ void __launch_bounds__(256) rmsd_pairs_kernel(const double* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Group-local de-duplication of generated poses (the step right after the clash test inside the cyclical
+// embeds, tscode/embeds.py:714-718 / 842-846):
+//     if compenetration_check(pose): if not _rmsd_similarity(pose, angular_poses, rmsd_thr=1): keep, append
+// i.e. within one group (same conformers, pairing and orientation; <= (steps+1)^F poses) a pose is kept iff it
+// passed the clash test and is not similar (all atoms, rmsd < thr and max deviation < 2 thr,
+// rmsd_pruning.py:208-224) to any pose of the group kept BEFORE it.  Groups are independent; inside a group the
+// pair similarities do not depend on the greedy state, so they are computed for all pairs of clash-passing
+// poses at once (one warp per pair) and the greedy pass itself is a tiny sequential kernel, one thread per group.
+//   S (P, A, 3) poses;  pair k = (pi[k], pj[k]) with pj[k] earlier than pi[k] in the same group;  sim[k] out.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rmsd_pairs_idx_kernel(const double* __restrict__ S, const int32_t* __restrict__ pi,
+                                                             const int32_t* __restrict__ pj, int64_t n, int M, double thr,
+                                                             uint8_t* __restrict__ sim) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const AosView V{S, M};
+    for (int64_t k = warp_g; k < n; k += nwarps) {
+        // ref = the new pose (rotated onto the kept one), as _rmsd_similarity(ref=pose, structures=kept) does
+        const PairEval ev = eval_pair(V, pi[k], V, pj[k], M, lane);
+        if (lane == 0) sim[k] = (uint8_t)((ev.rmsd < thr) && (ev.maxdev < 2.0 * thr));
+    }
+}
+
+// one thread per group: members [g_begin[g], g_begin[g+1]) of `order` (pose indices of the clash-passing poses in
+// generation order); pair_base[m] = index of the first pair of member m, its pairs being (m, earlier member 0..r-1)
+__global__ void group_greedy_kernel(const int32_t* __restrict__ g_begin, int32_t n_groups, const int32_t* __restrict__ order,
+                                    const int64_t* __restrict__ pair_base, const uint8_t* __restrict__ sim,
+                                    uint8_t* __restrict__ keep) {
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += gridDim.x * blockDim.x) {
+        const int b = g_begin[g], e = g_begin[g + 1];
+        for (int m = b; m < e; m++) {
+            const uint8_t* row = sim + pair_base[m];
+            bool dup = false;
+            for (int q = b; q < m && !dup; q++) dup = row[q - b] && keep[order[q]];
+            keep[order[m]] = (uint8_t)!dup;
+        }
+    }
+}
+
 }  // namespace tsc
 
 extern "C" int tsc_rmsd_verify(const double* packed, int64_t N, int32_t M, const int32_t* row_blocks,
@@ -459,6 +500,31 @@ extern "C" int tsc_rmsd_pairs(const double* P, const double* Q, int64_t n, int32
     int64_t blocks = (n + 7) / 8;
     if (blocks > 148 * 32) blocks = 148 * 32;
     rmsd_pairs_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(P, Q, n, M, broadcast_p, rmsd, maxdev);
+    TSC_CHECK_LAUNCH();
+    return 0;
+}
+
+// Similarity of explicit index pairs of one pose array: sim[k] = rmsd_and_max(S[pi[k]], S[pj[k]]) passes
+// (rmsd < thr and maxdev < 2 thr), all M atoms.
+extern "C" int tsc_rmsd_pairs_idx(const double* S, const int32_t* pi, const int32_t* pj, int64_t n, int32_t M,
+                                  double thr, uint8_t* sim, void* stream) {
+    using namespace tsc;
+    if (n <= 0) return 0;
+    int64_t blocks = (n + 7) / 8;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    rmsd_pairs_idx_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(S, pi, pj, n, M, thr, sim);
+    TSC_CHECK_LAUNCH();
+    return 0;
+}
+
+// Greedy pass of the group-local de-duplication (embeds.py:714-718): keep[order[m]] = 1 iff member m is not similar
+// to an earlier KEPT member of its group.  keep must be zero for poses that are not members.
+extern "C" int tsc_group_greedy(const int32_t* g_begin, int32_t n_groups, const int32_t* order, const int64_t* pair_base,
+                                const uint8_t* sim, uint8_t* keep, void* stream) {
+    if (n_groups <= 0) return 0;
+    int blocks = (n_groups + 127) / 128;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    tsc::group_greedy_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(g_begin, n_groups, order, pair_base, sim, keep);
     TSC_CHECK_LAUNCH();
     return 0;
 }

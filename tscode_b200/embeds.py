@@ -31,6 +31,96 @@ def pose_range(P: int, rank: int, world: int):
     return lo, min(lo + per, P)
 
 
+def string_embed_poses(frags, centers, vecs, angles):
+    """The pose space of a string embed (embeds.py:91-114) generated ON THE DEVICE.
+
+    frags   : [atomcoords of mol1 (n_conf1, n_1, 3), atomcoords of mol2 (n_conf2, n_2, 3)]
+    centers : [ra1.center per conformer (n_conf1, n_c1, 3), ra2.center (n_conf2, n_c2, 3)]   (mol.get_r_atoms(c)[0].center)
+    vecs    : [ra1.orb_vecs per conformer (n_conf1, n_c1, 3), ra2.orb_vecs (n_conf2, n_c2, 3)]
+    angles  : embedder.systematic_angles (degrees)
+    Returns a PoseBatch of P = n_conf1*n_conf2*n_c1*n_c2*len(angles) poses in the reference's loop order
+    (conformer pairs, then centre pairs, then angles); `.clash()` screens them, `.gather(keep)` materialises
+    survivors.  Only the small centre / vector tables cross PCIe."""
+    torch = require_cuda()
+    from ._lib import check, lib, ptr, stream_ptr
+    dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+    c1, c2 = (np.ascontiguousarray(c, dtype=np.float64) for c in centers)
+    v1, v2 = (np.ascontiguousarray(v, dtype=np.float64) for v in vecs)
+    n_conf1, n_c1 = c1.shape[:2]
+    n_conf2, n_c2 = c2.shape[:2]
+    if v1.shape != c1.shape or v2.shape != c2.shape or frags[0].shape[0] != n_conf1 or frags[1].shape[0] != n_conf2:
+        raise ValueError("centers / vecs must be (n_conf, n_centres, 3) per molecule")
+    ang = np.asarray(angles, dtype=np.float64).reshape(-1)
+    half = ang * np.pi / 180 / 2                                    # `angle *= np.pi/180`, then angle/2 (algebra.py:337-341)
+    # rot_mat_from_pointer([0, 0, 1], 180) exactly as the reference evaluates it (utils.py:203-205)
+    q = np.array([0.0, 0.0, np.sin(np.pi / 2) * 1.0, np.cos(np.pi / 2)])
+    q0, q1, q2, q3 = q[3], q[0], q[1], q[2]
+    flip = np.array([2 * (q0 * q0 + q1 * q1) - 1, 2 * (q1 * q2 - q0 * q3), 2 * (q1 * q3 + q0 * q2),
+                     2 * (q1 * q2 + q0 * q3), 2 * (q0 * q0 + q2 * q2) - 1, 2 * (q2 * q3 - q0 * q1),
+                     2 * (q1 * q3 - q0 * q2), 2 * (q2 * q3 + q0 * q1), 2 * (q0 * q0 + q3 * q3) - 1])
+    P = n_conf1 * n_conf2 * n_c1 * n_c2 * ang.size
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_c1, d_v1, d_c2, d_v2 = up(c1), up(v1), up(c2), up(v2)
+    d_sin, d_cos, d_nz, d_flip = up(np.sin(half)), up(np.cos(half)), up((ang != 0).astype(np.uint8)), up(flip)
+    conf = torch.empty((max(P, 1), 2), dtype=torch.int32, device=dev)
+    R = torch.empty((max(P, 1), 2, 3, 3), dtype=torch.float64, device=dev)
+    t = torch.empty((max(P, 1), 2, 3), dtype=torch.float64, device=dev)
+    check(lib().tsc_string_embed_params(ptr(d_c1), ptr(d_v1), ptr(d_c2), ptr(d_v2), n_conf1, n_conf2, n_c1, n_c2,
+                                        ptr(d_sin), ptr(d_cos), ptr(d_nz), int(ang.size), ptr(d_flip), ptr(conf), ptr(R),
+                                        ptr(t), stream_ptr()), "tsc_string_embed_params")
+    return PoseBatch(frags, conf[:P], R[:P], t[:P])
+
+
+def dedup_groups(poses, group_id, passed=None, rmsd_thr=1.0):
+    """Group-local de-duplication of generated poses — the `_rmsd_similarity(pose, angular_poses, rmsd_thr=1)`
+    step of the cyclical embeds (embeds.py:714-718, 842-846), batched.
+
+    poses    : (P, A, 3) float64, numpy or device tensor, in generation order
+    group_id : (P,) ints, non-decreasing: poses of one (conformers, pairing, orientation) combination share an id
+    passed   : (P,) bool clash verdicts (compenetration_check); None = all passed
+    Returns keep (P,) bool device tensor: pose p is kept iff it passed and is not similar (all atoms, rmsd < thr and
+    max deviation < 2 thr) to any pose of its group kept before it — exactly the reference's sequential logic."""
+    torch = require_cuda()
+    from ._lib import check, lib, ptr, stream_ptr
+    dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+    S = poses.to(dev, dtype=torch.float64).contiguous() if torch.is_tensor(poses) else \
+        torch.as_tensor(np.ascontiguousarray(poses, dtype=np.float64)).to(dev)
+    P, A = int(S.shape[0]), int(S.shape[1])
+    gid = torch.as_tensor(np.asarray(group_id)).to(dev).to(torch.int64) if not torch.is_tensor(group_id) else group_id.to(dev).to(torch.int64)
+    ok = torch.ones(P, dtype=torch.bool, device=dev) if passed is None else \
+        (passed.to(dev) if torch.is_tensor(passed) else torch.as_tensor(np.asarray(passed)).to(dev)).to(torch.bool)
+    keep = torch.zeros(max(P, 1), dtype=torch.uint8, device=dev)
+    if P == 0:
+        return keep[:0].bool()
+    if P > 1 and bool((gid[1:] < gid[:-1]).any()):
+        raise ValueError("group_id must be non-decreasing (poses in generation order)")
+    order = ok.nonzero().squeeze(1)                                  # members, in generation order
+    n = int(order.numel())
+    if n == 0:
+        return keep[:P].bool()
+    g = gid[order]
+    new = torch.ones(n, dtype=torch.bool, device=dev)
+    new[1:] = g[1:] != g[:-1]
+    starts = new.nonzero().squeeze(1)                                # first member of every group
+    n_groups = int(starts.numel())
+    g_begin = torch.cat([starts, torch.tensor([n], device=dev)]).to(torch.int32)
+    gidx = torch.cumsum(new.to(torch.int64), 0) - 1                  # group index of every member
+    rank = torch.arange(n, device=dev) - starts[gidx]                # earlier members of the same group
+    pair_base = torch.cumsum(rank, 0) - rank
+    n_pairs = int(rank.sum().item())
+    sim = torch.zeros(max(n_pairs, 1), dtype=torch.uint8, device=dev)
+    if n_pairs:
+        m = torch.repeat_interleave(torch.arange(n, device=dev), rank)            # member of every pair ...
+        r = torch.arange(n_pairs, device=dev) - pair_base[m]                       # ... and rank of its earlier partner
+        pi = order[m].to(torch.int32)
+        pj = order[starts[gidx[m]] + r].to(torch.int32)
+        check(lib().tsc_rmsd_pairs_idx(ptr(S), ptr(pi), ptr(pj), n_pairs, A, float(rmsd_thr), ptr(sim), stream_ptr()),
+              "tsc_rmsd_pairs_idx")
+    check(lib().tsc_group_greedy(ptr(g_begin), n_groups, ptr(order.to(torch.int32)), ptr(pair_base), ptr(sim), ptr(keep),
+                                 stream_ptr()), "tsc_group_greedy")
+    return keep[:P].bool()
+
+
 def gather_varlen(x, world: int, group=None):
     """All-gather of per-rank tensors whose first dimension differs: counts first (one host readback:
     the sizes must be known to size the receive buffer), then one padded all-gather, then the ranks'

@@ -54,6 +54,39 @@ def gen_poses(seed, P, n_atoms=(50, 50), n_conf=4, blob=2.0, dmin=3.0, dmax=9.0)
     return frags, conf, np.ascontiguousarray(R), np.ascontiguousarray(t)
 
 
+def gen_pose_groups(seed, n_groups, steps=12, n_atoms=(30, 30), n_conf=3, blob=1.6, dist=(4.0, 7.0)):
+    """Poses as a cyclical embed generates them (embeds.py:657-718): per group (one combination of conformers,
+    pairing and orientation) the second fragment is stepped through `steps` angles about an axis through its own
+    reactive centre while the first stays put, so neighbouring angles of a group can be similar.
+    Returns (frags, conf (P, 2), R (P, 2, 3, 3), t (P, 2, 3), group_id (P,)) with P = n_groups * steps."""
+    rng = np.random.default_rng(seed)
+    frags = [rng.normal(size=(n_conf, n, 3)) * blob for n in n_atoms]
+    # make the stepped fragment elongated along its own z axis: rotations about an axis near z move it little
+    frags[1][..., :2] *= 0.35
+    P = n_groups * steps
+    conf = np.repeat(rng.integers(0, n_conf, size=(n_groups, 2)), steps, axis=0)
+    gid = np.repeat(np.arange(n_groups), steps)
+    R = np.zeros((P, 2, 3, 3)); t = np.zeros((P, 2, 3))
+    R[:, 0] = np.eye(3)
+    for g in range(n_groups):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        x, y, z, w = q
+        R0 = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                       [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                       [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        d = rng.normal(size=3); d /= np.linalg.norm(d)
+        pos = d * rng.uniform(*dist)
+        tilt = rng.normal(size=3) * 0.15
+        axis = R0 @ (np.array([0.0, 0.0, 1.0]) + tilt); axis /= np.linalg.norm(axis)
+        K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+        for k in range(steps):
+            a = 2 * np.pi * k / steps
+            Rs = np.eye(3) + np.sin(a) * K + (1 - np.cos(a)) * (K @ K)
+            R[g * steps + k, 1] = Rs @ R0
+            t[g * steps + k, 1] = pos
+    return frags, conf, np.ascontiguousarray(R), np.ascontiguousarray(t), gid
+
+
 def materialise_poses(frags, conf, R, t, sel=None):
     """Host-side (numpy) materialisation of poses: what embeds.get_embed does per pose,
     vectorised.  Only for building inputs of the 'already materialised' clash entry point
