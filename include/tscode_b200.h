@@ -168,6 +168,23 @@ int64_t tsc_elim_fused_out_bytes(int64_t N);
 int tsc_elim_fused(const int32_t* lists, int32_t n_lists, int64_t stride, int64_t N, int32_t gate,
                    int32_t* ws, uint8_t* out, void* stream);
 
+/* ---- prune_conformers_tfd / prune_by_moment_of_inertia (run right before the RMSD prune, embedder.py:1325-1352) */
+/* Torsion fingerprints (numba_functions.py:233-239, 258-268; dihedral of algebra.py:24-57): tf (N, Q) float32
+ * degrees for quadruplets quads (Q, 4) int32 of the structures S (N, A, 3). */
+int tsc_tfd_fingerprints(const double* S, int64_t N, int32_t A, const int32_t* quads, int32_t Q, float* tf,
+                         void* stream);
+/* first_hit[i] = first j > i with tfd_similarity(tf[i], tf[j], thresh) (numba_functions.py:241-256), N if none:
+ * all the grouping loop (numba_functions.py:155-231) needs.  near_count (may be NULL): pairs with
+ * |sum - thresh| < 1e-4 among those looked at. */
+int tsc_tfd_scan(const float* tf, int64_t N, int32_t Q, double thresh, int32_t* first_hit, uint64_t* near_count,
+                 void* stream);
+/* Principal moments of inertia of the heavy atoms (algebra.py:166-187): moments (N, 3), ascending. */
+int tsc_moi_moments(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M,
+                    const double* masses, double* moments, void* stream);
+/* first_hit[i] = first j > i with all(|I_i - I_j| / I_i < max_deviation) (algebra.py:189-203), N if none. */
+int tsc_moi_scan(const double* moments, int64_t N, double max_deviation, int32_t* first_hit, uint64_t* near_count,
+                 void* stream);
+
 /* ---- compenetration_check / get_embed -------------------------------------------------- */
 /* Fused pose transform + clash screen (embeds.py:116-118 / 713-714 / 841-842).
  *   frag_lib: all fragments' conformers back to back; frag_off (F) int64 = offset in doubles of

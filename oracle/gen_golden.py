@@ -152,6 +152,38 @@ def main():
                             angles=np.array(angles), R=np.array(Rs), t=np.array(ts))
         print("stringembed:", len(Rs), "poses")
 
+    # ---- (f)-3: prune_conformers_tfd and prune_by_moment_of_inertia (embedder.py:1325-1352) ------------------
+    if want("tfdmoi"):
+        from tscode.numba_functions import prune_conformers_tfd, _get_tf_mat
+        from tscode.optimization_methods import prune_by_moment_of_inertia
+        from tscode.algebra import get_inertia_moments
+        from tscode.pt import pt
+        rows = []
+        for r in (dict(seed=41, N=400, M=24, n_clusters=60, sigma_noise=0.02, Q=8, thresh=10),
+                  dict(seed=42, N=900, M=30, n_clusters=90, sigma_noise=0.03, Q=12, thresh=10),
+                  dict(seed=43, N=150, M=16, n_clusters=150, sigma_noise=0.05, Q=5, thresh=25)):
+            S = gen_ensemble(r["seed"], r["N"], r["M"], r["n_clusters"], sigma_noise=r["sigma_noise"])
+            rng = np.random.default_rng(r["seed"])
+            quads = np.array([rng.choice(r["M"], 4, replace=False) for _ in range(r["Q"])])
+            out, mask = prune_conformers_tfd(S.copy(), quads, thresh=r["thresh"])
+            tf = _get_tf_mat(S.copy(), quads)
+            rows.append(dict(r, kind="tfd", quads=quads.tolist(), survivors=int(mask.sum()), digest=mask_digest(mask),
+                             mask_hex=np.packbits(mask).tobytes().hex(), tf_row0=[float(x) for x in tf[0]]))
+            print("tfd:", {k: v for k, v in rows[-1].items() if k not in ("mask_hex", "quads", "tf_row0")})
+        for r in (dict(seed=51, N=300, M=20, n_clusters=40, sigma_noise=0.004, max_deviation=1e-2),
+                  dict(seed=52, N=700, M=33, n_clusters=500, sigma_noise=0.01, max_deviation=2e-2)):
+            S = gen_ensemble(r["seed"], r["N"], r["M"], r["n_clusters"], sigma_noise=r["sigma_noise"])
+            rng = np.random.default_rng(r["seed"])
+            atomnos = rng.choice([1, 6, 7, 8, 9, 16, 17], size=r["M"], p=[0.3, 0.4, 0.1, 0.1, 0.04, 0.03, 0.03])
+            masses = [float(pt[int(a)].mass) for a in atomnos]
+            out, mask = prune_by_moment_of_inertia(S.copy(), atomnos, max_deviation=r["max_deviation"])
+            mom0 = get_inertia_moments(S[0][atomnos != 1].copy(), np.array([m for m, a in zip(masses, atomnos) if a != 1]))
+            rows.append(dict(r, kind="moi", atomnos=[int(a) for a in atomnos], masses=masses, survivors=int(mask.sum()),
+                             digest=mask_digest(mask), mask_hex=np.packbits(mask).tobytes().hex(),
+                             moments_row0=[float(x) for x in mom0]))
+            print("moi:", {k: v for k, v in rows[-1].items() if k not in ("mask_hex", "atomnos", "masses")})
+        json.dump({"meta": meta, "rows": rows}, open(os.path.join(GOLD, "tfd_moi.json"), "w"), indent=1)
+
     # ---- A7/A8: get_embed + compenetration_check ---------------------------------------------
     if want("clash"):
         rows = [

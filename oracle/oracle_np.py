@@ -263,3 +263,74 @@ def rotcorr_ladder_model(similar, N, best_angles=None):
                     for i in set(group) - {group[0]}:
                         final_mask[i + d * step] = 0
     return final_mask, state
+
+
+# --- TFD and MOI pruning (numba_functions.py:142-268, optimization_methods.py:327-358, algebra.py:24-57, 166-203)
+def dihedral(p):
+    """algebra.py:24-57 (Praxeolitic formula), degrees."""
+    p0, p1, p2, p3 = (np.asarray(x, float) for x in p)
+    b0 = -1.0 * (p1 - p0); b1 = p2 - p1; b2 = p3 - p2
+    b1 = b1 / np.sqrt((b1 * b1).sum())
+    v = b0 - np.dot(b0, b1) * b1
+    w = b2 - np.dot(b2, b1) * b1
+    return np.degrees(np.arctan2(np.dot(np.cross(b1, v), w), np.dot(v, w)))
+
+
+def torsion_fingerprints(structures, quadruplets):
+    """_get_tf_mat / get_torsion_fingerprint (numba_functions.py:233-239, 258-268): (N, Q) float32."""
+    out = np.zeros((len(structures), len(quadruplets)), dtype=np.float32)
+    for i, s in enumerate(structures):
+        for k, q in enumerate(quadruplets):
+            out[i, k] = dihedral([s[q[0]], s[q[1]], s[q[2]], s[q[3]]])
+    return out
+
+
+def tfd_similarity(tfp1, tfp2, thresh=10):
+    """numba_functions.py:241-256: float32 difference, wrapped and summed in float64."""
+    deltas = np.abs(tfp1 - tfp2)
+    deltas = np.abs(deltas.astype(np.float64) - (deltas > 180) * 360)
+    return bool(np.sum(deltas) < thresh)
+
+
+def prune_conformers_tfd(structures, quadruplets, thresh=10):
+    """numba_functions.py:142-231: the grouping loop is the one of rot_corr (rotcorr_ladder_model) on the
+    TFD similarity matrix."""
+    structures = np.asarray(structures)
+    tf = torsion_fingerprints(structures, quadruplets)
+    N = len(structures)
+    d = np.abs(tf[:, None, :] - tf[None, :, :])
+    d = np.abs(d.astype(np.float64) - (d > 180) * 360).sum(axis=2)
+    mask, _ = rotcorr_ladder_model(np.triu(d < thresh, 1), N)
+    return structures[mask], mask
+
+
+def get_inertia_moments(coords, masses):
+    """algebra.py:166-187 (symmetric eigenvalues instead of eig + B^-1 A B: same values to rounding)."""
+    coords = np.asarray(coords, float)
+    c = coords - (coords * masses[:, None]).sum(axis=0) / masses.sum()
+    r2 = (c * c).sum(axis=1)
+    I = (masses * r2).sum() * np.eye(3) - np.einsum("n,ni,nj->ij", masses, c, c)
+    ev = np.linalg.eigvalsh(I)
+    return ev[np.argsort(np.abs(ev))]
+
+
+def prune_by_moment_of_inertia(structures, atomnos, masses, max_deviation=1e-2):
+    """optimization_methods.py:327-358 with get_moi_similarity_matches (algebra.py:189-203); `masses` per atom."""
+    import networkx as nx
+    structures = np.asarray(structures)
+    atomnos = np.asarray(atomnos)
+    heavy = atomnos != 1
+    mom = np.array([get_inertia_moments(s[heavy], np.asarray(masses, float)[heavy]) for s in structures])
+    matches = []
+    for i in range(len(structures)):
+        for j in range(i + 1, len(structures)):
+            if np.all(np.abs(mom[i] - mom[j]) / mom[i] < max_deviation):
+                matches.append((i, j))
+                break
+    G = nx.Graph(matches)
+    groups = [tuple(G.subgraph(c).nodes) for c in nx.connected_components(G)]
+    mask = np.ones(len(structures), dtype=bool)
+    for g in groups:
+        for i in set(g) - {g[0]}:
+            mask[i] = False
+    return structures[mask], mask

@@ -505,3 +505,30 @@ def test_string_embed_params_on_device_vs_live_reference(gpu):
     v = pb.clash(1.2, 0).cpu().numpy()
     ref = oracle_c.embed_clash_batch(frags, oc, np.ascontiguousarray(R), np.ascontiguousarray(t), 1.2, 0)
     assert np.array_equal(v, ref)
+
+
+_tm = json.load(open(os.path.join(GOLDEN, "tfd_moi.json")))["rows"]
+
+
+@pytest.mark.parametrize("r", _tm, ids=[f"{r['kind']}{r['seed']}" for r in _tm])
+def test_tfd_moi_pruning_vs_live_reference(gpu, r):
+    """(f)-3: the drop-ins for prune_conformers_tfd (numba_functions.py:142) and prune_by_moment_of_inertia
+    (optimization_methods.py:327) against the masks of the live reference."""
+    from tscode_b200.numba_functions import prune_conformers_tfd, torsion_fingerprints
+    from tscode_b200.optimization_methods import moments_of_inertia, prune_by_moment_of_inertia
+    from tscode_b200.synth import gen_ensemble, mask_digest
+    S = gen_ensemble(r["seed"], r["N"], r["M"], r["n_clusters"], sigma_noise=r["sigma_noise"])
+    want = np.unpackbits(np.frombuffer(bytes.fromhex(r["mask_hex"]), np.uint8))[:r["N"]].astype(bool)
+    if r["kind"] == "tfd":
+        tf = torsion_fingerprints(S[:3], r["quads"])
+        assert np.abs(tf[0] - np.array(r["tf_row0"], dtype=np.float32)).max() < 2e-5      # one float32 ulp at 180 degrees
+        out, mask = prune_conformers_tfd(S, np.array(r["quads"]), thresh=r["thresh"])
+        print("tfd near-threshold pairs:", prune_conformers_tfd.last_near_threshold)
+    else:
+        atomnos, masses = np.array(r["atomnos"]), np.array(r["masses"])
+        mom = moments_of_inertia(S[:2], atomnos, masses).cpu().numpy()
+        assert np.allclose(mom[0], r["moments_row0"], rtol=1e-11)
+        out, mask = prune_by_moment_of_inertia(S, atomnos, r["max_deviation"], masses=masses)
+        print("moi near-threshold pairs:", prune_by_moment_of_inertia.last_near_threshold)
+    assert mask.dtype == np.bool_ and np.array_equal(mask, want) and mask_digest(mask) == r["digest"]
+    assert np.array_equal(out, S[mask])

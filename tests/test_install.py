@@ -30,6 +30,13 @@ def test_install_rebinds_every_importer():
         assert emb._rmsd_similarity is rmsd_pruning._rmsd_similarity
         assert tm.prune_conformers_rmsd_rot_corr is torsion_module.prune_conformers_rmsd_rot_corr
         assert ("tscode.embeds", "compenetration_check") in patched
+        import tscode.optimization_methods as om
+        import tscode.operators as ops
+        from tscode_b200 import optimization_methods
+        assert nf.prune_conformers_tfd is numba_functions.prune_conformers_tfd
+        assert tm.prune_conformers_tfd is numba_functions.prune_conformers_tfd          # torsion_module.py:35
+        assert ops.prune_conformers_tfd is numba_functions.prune_conformers_tfd         # operators.py:38
+        assert om.prune_by_moment_of_inertia is optimization_methods.prune_by_moment_of_inertia
     finally:
         install.uninstall()
     assert rp.prune_conformers_rmsd is orig

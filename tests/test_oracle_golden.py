@@ -150,3 +150,23 @@ def test_oracle_string_embed_params_vs_live_reference():
     assert R.shape[0] == g["R"].shape[0] == 3 * 2 * 2 * 3 * 6
     assert np.abs(R[:, 1] - g["R"]).max() < 1e-14 and np.abs(t[:, 1] - g["t"]).max() < 1e-13
     assert np.array_equal(R[:, 0], np.broadcast_to(np.eye(3), R[:, 0].shape)) and not t[:, 0].any()
+
+
+_tm = json.load(open(os.path.join(GOLDEN, "tfd_moi.json")))["rows"]
+
+
+@pytest.mark.parametrize("r", _tm, ids=[f"{r['kind']}{r['seed']}" for r in _tm])
+def test_oracle_tfd_moi_pruning_vs_live_reference(r):
+    """(f)-3: prune_conformers_tfd / prune_by_moment_of_inertia, numpy oracle vs the live reference's masks."""
+    S = gen_ensemble(r["seed"], r["N"], r["M"], r["n_clusters"], sigma_noise=r["sigma_noise"])
+    want = np.unpackbits(np.frombuffer(bytes.fromhex(r["mask_hex"]), np.uint8))[:r["N"]].astype(bool)
+    if r["kind"] == "tfd":
+        tf = oracle_np.torsion_fingerprints(S[:1], r["quads"])
+        assert np.array_equal(tf[0], np.array(r["tf_row0"], dtype=np.float32))
+        _, mask = oracle_np.prune_conformers_tfd(S, r["quads"], r["thresh"])
+    else:
+        atomnos, masses = np.array(r["atomnos"]), np.array(r["masses"])
+        mom = oracle_np.get_inertia_moments(S[0][atomnos != 1], masses[atomnos != 1])
+        assert np.allclose(mom, r["moments_row0"], rtol=1e-12)
+        _, mask = oracle_np.prune_by_moment_of_inertia(S, atomnos, masses, r["max_deviation"])
+    assert mask_digest(mask) == r["digest"] and np.array_equal(mask, want)

@@ -27,7 +27,8 @@ extern "C" int32_t tsc_device_sm_count(void) {
 // flops per visit: plain C on the host.  All pointers are HOST pointers.
 //   compact / off: best-angle codes of row i's pairs (i, i + 1 + k) at compact[off[i] + k], 3 bits per
 //   rotor;  ang_table (T, 6) degrees;  match_i / match_j (capacity hi - base): chunk-relative matches
-//   in the order the reference adds them.  Returns the number of matches.
+//   in the order the reference adds them.  Returns the number of matches.  T = 0 (no rotor states: the TFD
+//   pruning, numba_functions.py:155-231, runs the same loop) ignores compact / off / ang_table / state.
 // ------------------------------------------------------------------------------------------
 #include <math.h>
 extern "C" int64_t tsc_host_rotcorr_chunk(int64_t base, int64_t hi, const int64_t* first_hit, int64_t* reach,
@@ -39,15 +40,15 @@ extern "C" int64_t tsc_host_rotcorr_chunk(int64_t base, int64_t hi, const int64_
         const int64_t new_hi = (p - 1 < hi - 1) ? p - 1 : hi - 1;
         const int64_t lo = reach[i] + 1;
         const double* si = state + i * T;
-        const uint32_t* ci = compact + off[i] - (i + 1);          // code of (i, j) at ci[j]
-        for (int64_t j = lo; j <= new_hi; j++) {
+        const uint32_t* ci = T > 0 ? compact + off[i] - (i + 1) : nullptr;      // code of (i, j) at ci[j]
+        for (int64_t j = lo; T > 0 && j <= new_hi; j++) {
             const uint32_t c = ci[j];
             double* sj = state + j * T;
             for (int t = 0; t < T; t++) sj[t] = fmod(ang_table[t * 6 + ((c >> (3 * t)) & 7u)] + si[t], 360.0);
         }
         if (new_hi >= lo) reach[i] = new_hi;
         if (p < hi) {
-            const uint32_t c = ci[p];
+            const uint32_t c = T > 0 ? ci[p] : 0u;
             double* sj = state + p * T;
             for (int t = 0; t < T; t++) sj[t] = fmod(ang_table[t * 6 + ((c >> (3 * t)) & 7u)] + si[t], 360.0);
             match_i[n_match] = (int32_t)(i - base);

@@ -116,8 +116,9 @@ def dedup_groups(poses, group_id, passed=None, rmsd_thr=1.0):
         pj = order[starts[gidx[m]] + r].to(torch.int32)
         check(lib().tsc_rmsd_pairs_idx(ptr(S), ptr(pi), ptr(pj), n_pairs, A, float(rmsd_thr), ptr(sim), stream_ptr()),
               "tsc_rmsd_pairs_idx")
-    check(lib().tsc_group_greedy(ptr(g_begin), n_groups, ptr(order.to(torch.int32)), ptr(pair_base), ptr(sim), ptr(keep),
-                                 stream_ptr()), "tsc_group_greedy")
+    order32 = order.to(torch.int32)
+    check(lib().tsc_group_greedy(ptr(g_begin), n_groups, ptr(order32), ptr(pair_base), ptr(sim), ptr(keep), stream_ptr()),
+          "tsc_group_greedy")
     return keep[:P].bool()
 
 

@@ -11,6 +11,7 @@ import importlib
 import sys
 
 from . import numba_functions as _nf
+from . import optimization_methods as _om
 from . import rmsd_pruning as _rp
 from . import torsion_module as _tm
 
@@ -23,6 +24,10 @@ _PATCHES = {
     },
     "tscode.numba_functions": {
         "compenetration_check": _nf.compenetration_check,
+        "prune_conformers_tfd": _nf.prune_conformers_tfd,
+    },
+    "tscode.optimization_methods": {
+        "prune_by_moment_of_inertia": _om.prune_by_moment_of_inertia,
     },
     "tscode.embeds": {
         "get_embed": _nf.get_embed,

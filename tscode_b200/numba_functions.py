@@ -155,3 +155,52 @@ def get_embed(mols, conf_ids):
                        np.stack([np.asarray(m.position, float), np.zeros(3)])[None])
         parts.append(pb.gather(None, 1)[0].cpu().numpy())
     return np.concatenate(parts)
+
+
+def prune_conformers_tfd(structures, quadruplets, thresh=10, verbose=False):
+    """Drop-in for tscode.numba_functions.prune_conformers_tfd (numba_functions.py:142-231): removes
+    structures whose torsion fingerprints (float32 dihedrals of `quadruplets`) differ from an earlier
+    one's by less than `thresh` degrees in total, with the reference's k-ladder, cache and
+    connected-component survivor choice.  Returns (structures[mask], mask).
+
+    Fingerprints and the pair test run on the GPU; the grouping loop stops at the first similar later
+    structure of every row and caches dissimilar pairs, so it only needs first_hit[i] (tsc_tfd_scan) and
+    is replayed on the host exactly as written (torsion_module.ladder_replay_scan, shared with rot_corr —
+    the two loops are the same code in the reference)."""
+    torch = require_cuda()
+    from .torsion_module import ladder_replay_scan
+    structures = np.asarray(structures)
+    N = structures.shape[0]
+    quads = np.ascontiguousarray(np.asarray(quadruplets, dtype=np.int32).reshape(-1, 4))
+    Q = quads.shape[0]
+    if N == 0:
+        return structures, np.ones(0, dtype=bool)
+    dev = _dev(torch)
+    S = torch.as_tensor(np.ascontiguousarray(structures, dtype=np.float64)).to(dev)
+    first = torch.full((N,), N, dtype=torch.int32, device=dev)
+    near = torch.zeros(1, dtype=torch.int64, device=dev)
+    tf = torch.zeros((N, max(Q, 1)), dtype=torch.float32, device=dev)
+    d_quads = torch.from_numpy(quads).to(dev)            # (kept alive until the end of the call: never pass temporaries)
+    if Q:
+        check(lib().tsc_tfd_fingerprints(ptr(S), N, int(S.shape[1]), ptr(d_quads), Q, ptr(tf), stream_ptr()),
+              "tsc_tfd_fingerprints")
+    # Q == 0: every sum is 0 < thresh, the scan handles it (row i hits i + 1)
+    check(lib().tsc_tfd_scan(ptr(tf), N, Q, float(thresh), ptr(first), ptr(near), stream_ptr()), "tsc_tfd_scan")
+    mask, _ = ladder_replay_scan(first.cpu().numpy().astype(np.int64), N, None, verbose=verbose)
+    prune_conformers_tfd.last_near_threshold = int(near.item())
+    return structures[mask], mask
+
+
+def torsion_fingerprints(structures, quadruplets):
+    """_get_tf_mat (numba_functions.py:233-239): (N, Q) float32 dihedrals in degrees, numpy."""
+    torch = require_cuda()
+    structures = np.ascontiguousarray(structures, dtype=np.float64)
+    quads = np.ascontiguousarray(np.asarray(quadruplets, dtype=np.int32).reshape(-1, 4))
+    N, Q = structures.shape[0], quads.shape[0]
+    dev = _dev(torch)
+    tf = torch.zeros((N, max(Q, 1)), dtype=torch.float32, device=dev)
+    d_S, d_quads = torch.from_numpy(structures).to(dev), torch.from_numpy(quads).to(dev)
+    if N and Q:
+        check(lib().tsc_tfd_fingerprints(ptr(d_S), N, structures.shape[1], ptr(d_quads), Q, ptr(tf), stream_ptr()),
+              "tsc_tfd_fingerprints")
+    return tf[:, :Q].cpu().numpy()

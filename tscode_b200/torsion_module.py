@@ -265,7 +265,8 @@ class RotCorrPruner:
         out = torch.empty((n, self.A, 3), dtype=torch.float64, device=self.dev)
         sh = torch.from_numpy(np.ascontiguousarray(np.sin(half))).to(self.dev)
         ch = torch.from_numpy(np.ascontiguousarray(np.cos(half))).to(self.dev)
-        check(lib().tsc_rotcorr_apply(ptr(self.Sc), n, self.A, ptr(torch.from_numpy(idx).to(self.dev)), T,
+        d_idx = torch.from_numpy(idx).to(self.dev)
+        check(lib().tsc_rotcorr_apply(ptr(self.Sc), n, self.A, ptr(d_idx), T,
                                       ptr(self.i2), ptr(self.i3), ptr(sh), ptr(ch), ptr(self.rot_mask), ptr(out),
                                       stream_ptr()), "tsc_rotcorr_apply")
         return out.cpu().numpy()
@@ -347,15 +348,18 @@ def ladder_replay_scan(first_hit, N, best_angles=None, verbose=False, native=Non
     T = best_angles.T if best_angles is not None else 0
     state = np.zeros((N, max(T, 0)))
     if native is None:
-        native = best_angles is not None and hasattr(best_angles, "compact")
+        native = best_angles is None or hasattr(best_angles, "compact")
     if native:
         L = lib()
-        compact = np.ascontiguousarray(best_angles.compact, dtype=np.uint32)
-        if compact.size == 0:
-            compact = np.zeros(1, np.uint32)
-        off = best_angles.off
-        table = np.ascontiguousarray(best_angles.table, dtype=np.float64)
-        assert table.shape[1] == MAX_ANG
+        if T:
+            compact = np.ascontiguousarray(best_angles.compact, dtype=np.uint32)
+            if compact.size == 0:
+                compact = np.zeros(1, np.uint32)
+            off = best_angles.off
+            table = np.ascontiguousarray(best_angles.table, dtype=np.float64)
+            assert table.shape[1] == MAX_ANG
+        else:                                   # no rotor states (the TFD pruning runs the same loop)
+            compact, off, table = np.zeros(1, np.uint32), np.zeros(max(N, 1), np.int64), np.zeros((1, MAX_ANG))
         mi, mj = np.empty(max(N, 1), np.int32), np.empty(max(N, 1), np.int32)
         vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
         p_first, p_reach, p_state, p_compact, p_off, p_table, p_mi, p_mj = (vp(a) for a in (
