@@ -289,6 +289,15 @@ int tsc_bench_umma(int32_t N, int32_t nsets, int32_t reps, int32_t a_in_tmem, lo
 int tsc_bench_fp64(int32_t kind, int32_t iters, int32_t ctas_per_sm, int32_t threads, double* scratch,
                    double* flops_out, float* ms_out, void* stream);
 
+/* ---- ensemble I/O ------------------------------------------------------------------------ */
+/* [host] Multi-frame XYZ text of n_frames structures (utils.py:114-126, write_xyz; embedder.py:996-1043): per frame
+ * "<A>\n<title>\n" and per atom '%s     % .6f % .6f % .6f\n', byte-identical to the reference's Python formatting.
+ * coords (n_frames, A, 3) HOST doubles; symbols: A zero-terminated strings at a stride of 4 bytes; titles: n_frames
+ * zero-terminated strings back to back, or NULL for "temp".  out == NULL returns the byte count; otherwise the
+ * text is written (cap bytes available; returns -needed if too small).  Frames are formatted by n_threads threads. */
+int64_t tsc_host_write_xyz(const double* coords, int64_t n_frames, int32_t A, const char* symbols, const char* titles,
+                           char* out, int64_t cap, int32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -170,3 +170,31 @@ def test_rotcorr_scan_replay_equals_dense_replay(N, dens, seed):
     for native in (False, True):
         m2, s2 = ladder_replay_scan(first, N, lookup, native=native)
         assert np.array_equal(m1, m2) and np.array_equal(s1, s2), native
+
+
+def test_native_xyz_text_is_byte_identical_to_reference_formatting():
+    """(f)-4: tsc_host_write_xyz against the reference's per-atom '%s     % .6f % .6f % .6f\\n' (utils.py:114-126),
+    including half-way decimals, negative zero, huge values, inf / nan, and per-frame titles."""
+    import io
+    from tscode_b200.utils import _SYMBOLS, write_xyz, xyz_text
+
+    def ref_write(coords, atomnos, title='temp'):                 # utils.py:114-126 verbatim (pt -> symbol table)
+        string = ''
+        string += str(len(coords))
+        string += f'\\n{title}\\n'
+        for i, atom in enumerate(coords):
+            string += '%s     % .6f % .6f % .6f\\n' % (_SYMBOLS[atomnos[i]], atom[0], atom[1], atom[2])
+        return string
+    rng = np.random.default_rng(0)
+    S = rng.normal(size=(300, 37, 3)) * np.array([1, 10, 1000])
+    S[0, 0] = [0.0, -0.0, -1e-9]; S[0, 1] = [0.5e-6, 1.5e-6, 2.5e-6]; S[0, 2] = [123456.7890125, -0.0000005, 1e15]
+    S[0, 3] = [np.inf, -np.inf, np.nan]; S[0, 4] = [1e300, -1e300, 1e-300]
+    S[1, :, 0] = np.round(S[1, :, 0], 6) + 0.5e-6
+    at = rng.choice([1, 6, 7, 8, 17, 35], size=37)
+    want = ''.join(ref_write(s, at, f"conf {k}") for k, s in enumerate(S)).encode()
+    for nt in (1, 3, 16):
+        assert xyz_text(S, at, [f"conf {k}" for k in range(len(S))], n_threads=nt) == want
+    assert xyz_text(S[:2], at) == ''.join(ref_write(s, at) for s in S[:2]).encode()
+    buf = io.StringIO()
+    write_xyz(S[5], at, buf, title='x')
+    assert buf.getvalue() == ref_write(S[5], at, 'x')
