@@ -181,9 +181,9 @@ def test_native_xyz_text_is_byte_identical_to_reference_formatting():
     def ref_write(coords, atomnos, title='temp'):                 # utils.py:114-126 verbatim (pt -> symbol table)
         string = ''
         string += str(len(coords))
-        string += f'\\n{title}\\n'
+        string += f'\n{title}\n'
         for i, atom in enumerate(coords):
-            string += '%s     % .6f % .6f % .6f\\n' % (_SYMBOLS[atomnos[i]], atom[0], atom[1], atom[2])
+            string += '%s     % .6f % .6f % .6f\n' % (_SYMBOLS[atomnos[i]], atom[0], atom[1], atom[2])
         return string
     rng = np.random.default_rng(0)
     S = rng.normal(size=(300, 37, 3)) * np.array([1, 10, 1000])
