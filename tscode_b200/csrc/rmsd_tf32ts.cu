@@ -64,8 +64,11 @@ constexpr int TS_Q = 128;              // candidate queue entries per epilogue w
 constexpr int TS_TRACE_TILES = 96;    // tiles of the first item that are stamped (8 slots each)
 
 // NACC*CH epilogue groups of 4 warps (CH column parts per tile); STEP columns per TMEM load round
-template <int CH, int STEP, bool F16, int NACC>
-__global__ void __launch_bounds__((2 + 4 * NACC * CH) * 32, 1) rmsd_ts_kernel(const TsParams p) {
+// NMMA MMA-issuing warps (tile t is issued by warp t % NMMA): while one of them goes through its per-tile
+// bookkeeping (two mbarrier waits, descriptor set-up, commits: ~460 cycles in the trace) the other keeps the
+// tensor pipe fed, and the MMAs of two tiles (six accumulator chains instead of three) interleave in the pipe.
+template <int CH, int STEP, bool F16, int NACC, int NMMA = 1>
+__global__ void __launch_bounds__((1 + NMMA + 4 * NACC * CH) * 32, 1) rmsd_ts_kernel(const TsParams p) {
     constexpr int NG = NACC * CH;
     constexpr int TS_NACC = NACC;
     constexpr int KT_MAX = NACC == 2 ? TS_KT_MAX : 0;
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__((2 + 4 * NACC * CH) * 32, 1) rmsd_ts_kernel(co
     if (threadIdx.x == 0) {
         mbar_init(at_full, 1);
         mbar_init(am_full, 4 * NG);
-        mbar_init(a_empty, 1);
+        mbar_init(a_empty, NMMA);
         for (int s = 0; s < p.nb_stages; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int t = 0; t < TS_NACC; t++) { mbar_init(&t_full[t], 1); mbar_init(&t_empty[t], 4 * CH); }
         fence_barrier_init();
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__((2 + 4 * NACC * CH) * 32, 1) rmsd_ts_kernel(co
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp <= NMMA) {
         // ===================== MMA issuer: the whole warp runs the control flow, one elected lane issues =====================
         {
             const uint32_t idesc = F16 ? umma_idesc_f16(TF_ROWS, TF_N) : umma_idesc_tf32(TF_ROWS, TF_N);
@@ -145,13 +148,16 @@ __global__ void __launch_bounds__((2 + 4 * NACC * CH) * 32, 1) rmsd_ts_kernel(co
             const uint64_t ad0 = umma_desc_kmajor(smem_u32(smA), a_lbo, 128u);       // A tail, component x
             const uint64_t bd_step = (2u * b_lbo) >> 4, ad_step = (2u * a_lbo) >> 4; // start-address field, 16-byte units
             const uint32_t a_stride = 8u * KT;                                       // TMEM columns per component
-            int bs = 0, acc = 0; uint32_t bph = 0, aph = 0, tph = 0;
+            const int mw = warp - 1;                                                 // this MMA warp's index
+            int bs = mw % p.nb_stages, acc = mw % TS_NACC; uint32_t bph = 0, aph = 0, tph = 0;
+            int64_t tseq = 0;                                                        // tiles of this CTA so far
             for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
                 const int4 w = p.items[it];
                 mbar_wait(am_full, aph);
                 if (tail_kc > 0) mbar_wait(at_full, aph);
                 aph ^= 1u;
-                for (int t = 0; t < w.z; t++) {
+                for (int t = 0; t < w.z; t++, tseq++) {
+                    if (NMMA > 1 && (int)(tseq % NMMA) != mw) continue;
                     const bool tr = p.trace && it == 0 && t < TS_TRACE_TILES && lane == 0;
                     if (tr) p.trace[t * 8 + 0] = clock64();
                     mbar_wait(&b_full[bs], bph);
@@ -197,8 +203,10 @@ __global__ void __launch_bounds__((2 + 4 * NACC * CH) * 32, 1) rmsd_ts_kernel(co
                     }
                     __syncwarp();
                     if (tr) p.trace[t * 8 + 3] = clock64();
-                    if (++bs == p.nb_stages) { bs = 0; bph ^= 1u; }
-                    if (++acc == TS_NACC) { acc = 0; tph ^= 1u; }
+                    bs += NMMA;
+                    if (bs >= p.nb_stages) { bs -= p.nb_stages; bph ^= 1u; }
+                    acc += NMMA;
+                    if (acc >= TS_NACC) { acc -= TS_NACC; tph ^= 1u; }
                 }
                 if (elect_one()) umma_commit(a_empty);
                 __syncwarp();
@@ -209,7 +217,7 @@ __global__ void __launch_bounds__((2 + 4 * NACC * CH) * 32, 1) rmsd_ts_kernel(co
         // group g works on accumulator buffer g / CH (the tiles with index % 2 == g / CH) and, inside a
         // tile, on the 16/CH columns of part g % CH.  Every group therefore waits on EVERY use of its
         // buffer's barrier, which mbarrier parity waits require (a waiter may never fall two phases behind).
-        const int ew = warp - 2;
+        const int ew = warp - (1 + NMMA);
         const int grp = ew >> 2;
         const int buf = grp / CH, part = grp % CH;
         const int quad = warp & 3;
@@ -367,7 +375,10 @@ static int launch_ts(const void* PA, const void* PB, const void* PR, const doubl
     p.W = num_blocks_padded(N);
     // grid_ctas < 0 selects an alternative configuration (tuning aid): -1 = A in TMEM, 2 groups, 8 columns per
     // TMEM load round; -2 = A in TMEM, 2 groups x 4; -3 = A in TMEM, 4 groups (two column halves per tile) x 4;
-    // -4 = A in shared memory, 3 accumulator buffers, 3 groups x 4;  default = TS_DEFAULT_CFG
+    // -4 = A in shared memory, 3 accumulator buffers, 3 groups x 4;  -5 = as -2 with two MMA warps;
+    // (measured on C3, FP16 operands: -2 2.72 ms, -3 3.08, -4 2.78, -5 2.88; reading the whole tile into 144
+    // registers and releasing before any arithmetic: 4.06)
+    // default = TS_DEFAULT_CFG
     const int cfg = grid_ctas < 0 ? -grid_ctas : TS_DEFAULT_CFG;
     if (grid_ctas < 0) grid_ctas = 0;
     const int kt_max = cfg == 4 ? 0 : TS_KT_MAX;
@@ -381,8 +392,9 @@ static int launch_ts(const void* PA, const void* PB, const void* PR, const doubl
     p.nb_stages = nb;
     const size_t smem = a_bytes + nb * b_bytes + 512 + q_bytes;
     auto kern = cfg == 1 ? rmsd_ts_kernel<1, 8, F16, 2> : cfg == 2 ? rmsd_ts_kernel<1, 4, F16, 2>
-              : cfg == 3 ? rmsd_ts_kernel<2, 4, F16, 2> : rmsd_ts_kernel<1, 4, F16, 3>;
-    const int threads = cfg <= 2 ? 320 : cfg == 3 ? 576 : 448;
+              : cfg == 3 ? rmsd_ts_kernel<2, 4, F16, 2> : cfg == 4 ? rmsd_ts_kernel<1, 4, F16, 3>
+              : rmsd_ts_kernel<1, 4, F16, 2, 2>;
+    const int threads = cfg <= 2 ? 320 : cfg == 3 ? 576 : cfg == 4 ? 448 : 352;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;
