@@ -532,3 +532,26 @@ def test_tfd_moi_pruning_vs_live_reference(gpu, r):
         print("moi near-threshold pairs:", prune_by_moment_of_inertia.last_near_threshold)
     assert mask.dtype == np.bool_ and np.array_equal(mask, want) and mask_digest(mask) == r["digest"]
     assert np.array_equal(out, S[mask])
+
+
+@pytest.mark.parametrize("scale,shift", [(1e-5, 0.0), (1.0, 7e4), (3e3, 0.0), (1.0, 0.0)])
+def test_f16_screen_extreme_coordinates(gpu, scale, shift):
+    """FP16 operands of the default screen: coordinates below the smallest normal half (zeroed by pack, bound
+    widened), beyond the largest finite half (inf -> the pair can never be excluded -> exact verify decides) and
+    large-but-finite ones must all give the oracle's mask; a mixed ensemble exercises every path at once."""
+    from oracle import oracle_c
+    from tscode_b200.rmsd_pruning import RmsdPruner
+    from tscode_b200.synth import gen_ensemble
+    S = gen_ensemble(11, 600, 24, 40, sigma_noise=0.05) * scale
+    S[:, :, 0] += shift
+    if scale == 1.0 and shift == 0.0:                 # mixed: a few structures with tiny / huge / zero coordinates
+        S[::7, 3] *= 1e-6
+        S[::11, 5, 1] = 8e4
+        S[::13] = 0.0
+    thr = 0.5 * (scale if scale < 1 else 1.0)
+    at = np.full(24, 6)
+    ref_out, ref = oracle_c.prune_conformers_rmsd(S, at, thr)
+    for variant in ("f16", "dmma"):
+        pr = RmsdPruner(S, at, thr, variant=variant)
+        m = pr.run().cpu().numpy()
+        assert np.array_equal(m, ref), (variant, scale, shift, int(m.sum()), int(ref.sum()), pr.stats_dict())

@@ -90,3 +90,20 @@ def test_screen_degenerate_inputs(hm):
     assert hm.hm_screen(p, q, 5, 0.5) == 1
     q2 = p.copy(); q2[:, 0] *= 3
     assert hm.hm_screen(p, q2, 5, 0.5) == 0
+
+
+def test_screen_far_from_origin_never_loses_a_pair(hm):
+    """Ensembles far from the origin (rotation-only Kabsch does not centre, rmsd_pruning.py:6-41) make two roots of
+    the key-matrix quartic nearly coincide at ~1e11: without the rounding guard of quartic_excluded the sign test
+    dropped true pairs."""
+    S = gen_ensemble(11, 120, 24, 8, sigma_noise=0.05)
+    lost = sim = 0
+    for shift in (7e4, 3e3, 1e6):
+        T = S.copy(); T[:, :, 0] += shift
+        for i in range(0, 120):
+            for j in range(i + 1, min(i + 25, 120)):
+                r, d = oracle_c.rmsd_and_max(T[i], T[j])
+                if r < 0.5:
+                    sim += 1
+                    lost += 1 - hm.hm_screen(T[i], T[j], 24, 0.5)
+    assert sim > 100 and lost == 0, (sim, lost)

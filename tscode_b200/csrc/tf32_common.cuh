@@ -219,11 +219,8 @@ __device__ __forceinline__ uint32_t tf32_epilogue_tile(uint32_t d0, float gvf, c
                 for (int q = 0; q < 9; q++) S[q] = (double)__uint_as_float(r[q * STEP + c]);
                 double c2, c1, c0;
                 key_charpoly(S, c2, c1, c0);
-                const double l1 = fma(row.ci, sG[j], fma(hs, G[j], row.hi)), l2 = l1 * l1;
-                const double p2 = fma(12.0, l2, 2.0 * c2);
-                const double p1 = fma(fma(4.0, l2, 2.0 * c2), l1, c1);
-                const double p0 = fma(fma(l2 + c2, l1, c1), l1, c0);
-                const bool excluded = (l1 > 0.0) & (p0 > 0.0) & (p1 > 0.0) & (p2 > 0.0);
+                const double l1 = fma(row.ci, sG[j], fma(hs, G[j], row.hi));
+                const bool excluded = quartic_excluded(l1, c2, c1, c0);
                 if (!excluded && ((near >> c) & 1u)) bits |= 1u << (st * STEP + c);
             }
         }
@@ -273,11 +270,8 @@ __device__ __forceinline__ bool tf32_quartic_excluded(const uint32_t* r, const T
     for (int q = 0; q < 9; q++) S[q] = (double)__uint_as_float(r[q]);
     double c2, c1, c0;
     key_charpoly(S, c2, c1, c0);
-    const double l1 = fma(row.ci, sGj, fma(hs, Gj, row.hi)), l2 = l1 * l1;
-    const double p2 = fma(12.0, l2, 2.0 * c2);
-    const double p1 = fma(fma(4.0, l2, 2.0 * c2), l1, c1);
-    const double p0 = fma(fma(l2 + c2, l1, c1), l1, c0);
-    return (l1 > 0.0) & (p0 > 0.0) & (p1 > 0.0) & (p2 > 0.0);
+    const double l1 = fma(row.ci, sGj, fma(hs, Gj, row.hi));
+    return quartic_excluded(l1, c2, c1, c0);
 }
 
 // NCOL (16 or 8) columns starting at column C0 of the tile are handled by the calling thread.

@@ -91,16 +91,32 @@ TSC_HD void key_charpoly(const double S[9], double& c2, double& c1, double& c0) 
 // only costs a few extra verifications and can never lose a true pair.
 // Returns true when the pair is a CANDIDATE (cannot be excluded).
 // ------------------------------------------------------------------------------------------
+// Rounding guard.  The sign test is only as good as the evaluated polynomial: for an ensemble far from the
+// origin (|centroid| ~ 7e4 A) two roots of P sit within ~1e3 of each other at ~1e11, P(lam_t) ~ 1e26 drowns in the
+// ~1e28 rounding noise of the coefficients, and the unguarded test LOST true pairs (caught by
+// test_f16_screen_extreme_coordinates).  Every root and lam_t are below r = lam_t + 2 ||S||_F, the evaluation
+// errors of P, P', P'' (coefficients through 2x2 minors + Horner) are below ~30 eps (r/2)^4-ish; a pair is
+// excluded only if the three values clear 4e-13 r^4, 16e-13 r^3, 48e-13 r^2 (with r^2 over-estimated by
+// 2 (lam_t^2 + 4 ||S||_F^2), which needs no square root) — for ordinary, centred ensembles
+// (r ~ 1e3..1e4) that is ~1e2 against values of 1e10 and more, so no screening power is lost.
+TSC_HD bool quartic_excluded(double lam, double c2, double c1, double c0) {
+    if (!(lam > 0.0)) return false;
+    const double l2 = lam * lam;
+    const double R2 = 2.0 * fma(-2.0, c2, l2);                 // 2 (lam^2 + 4 ||S||_F^2) >= r^2  (no square root)
+    const double tol = 4e-13;
+    const double p2 = fma(12.0, l2, 2.0 * c2);                 // P''
+    const double p1 = fma(fma(4.0, l2, 2.0 * c2), lam, c1);    // P'
+    const double p0 = fma(fma(l2 + c2, lam, c1), lam, c0);     // P
+    // P > tol r^4,  P' > 4 tol r^3 (compared through squares),  P'' > 12 tol r^2;  NaN -> not excluded
+    return (p0 > tol * R2 * R2) & (p1 > 0.0) & (p1 * p1 > 16.0 * tol * tol * R2 * R2 * R2) & (p2 > 12.0 * tol * R2);
+}
+
 TSC_HD bool screen_candidate(const double S[9], double G, double e_thr_pad) {
     double lam = 0.5 * (G - e_thr_pad);
     if (!(lam > 0.0)) return true;
     double c2, c1, c0;
     key_charpoly(S, c2, c1, c0);
-    double l2 = lam * lam;
-    double p2 = fma(12.0, l2, 2.0 * c2);                 // P''
-    double p1 = fma(fma(4.0, l2, 2.0 * c2), lam, c1);    // P'
-    double p0 = fma(fma(l2 + c2, lam, c1), lam, c0);     // P
-    return !((p0 > 0.0) && (p1 > 0.0) && (p2 > 0.0));
+    return !quartic_excluded(lam, c2, c1, c0);
 }
 
 // ------------------------------------------------------------------------------------------
