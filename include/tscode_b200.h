@@ -46,6 +46,10 @@ int64_t tsc_packed_doubles(int64_t N, int32_t M);
 int tsc_pack(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M,
              double* packed, double* G, void* stream);
 
+/* tsc_pack for the conformer blocks (32 rows) [block_begin, block_end) only — chunked upload pipelines. */
+int tsc_pack_blocks(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M,
+                    double* packed, double* G, int64_t block_begin, int64_t block_end, void* stream);
+
 /* All-pairs similarity screen over a list of 32 x 64 pair tiles.
  *   tiles (n_tiles, 4) int32: {ib, jp, lb, 0} = I block ib, J blocks 2jp and 2jp+1, rows written
  *   at local row block lb of sim_bits.  For every owned row block ib the caller lists jp from
@@ -90,6 +94,11 @@ int tsc_rmsd_sim_tf32ts(const float* PA, const float* PB, const float* PR, const
 int64_t tsc_f16_operand_bytes(int64_t N, int32_t M);
 int tsc_pack_f16(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M, void* PA,
                  void* PB, void* PR, double* G, double* sG, float* CT, void* stream);
+/* tsc_pack_f16 for conformers [row_begin, row_end) only (row_begin a multiple of 8; let the last chunk end at
+ * ceil(N/128)*128 so that the padding rows are written). */
+int tsc_pack_f16_rows(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M, void* PA,
+                      void* PB, void* PR, double* G, double* sG, float* CT, int64_t row_begin, int64_t row_end,
+                      void* stream);
 int tsc_rmsd_sim_f16ts(const void* PA, const void* PB, const void* PR, const double* G,
                        const double* sG, const float* CT, int64_t N, int32_t M, const int32_t* items,
                        int32_t n_items, double thr, uint32_t* sim_bits, int32_t* cand_list,

@@ -23,6 +23,7 @@ SIGNATURES = {
     "tsc_packed_doubles": (_i64, [_i64, _i32]),
     "tsc_device_sm_count": (_i32, []),
     "tsc_pack": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "tsc_pack_blocks": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _i64, _i64, _vp]),
     "tsc_rmsd_sim_tiles": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i64, _f64, _vp, _i32, _i32, _vp]),
     "tsc_tf32_pa_floats": (_i64, [_i64, _i32]),
     "tsc_tf32_pb_floats": (_i64, [_i64, _i32]),
@@ -31,6 +32,7 @@ SIGNATURES = {
     "tsc_set_trace_buffer": (None, [_vp]),
     "tsc_f16_operand_bytes": (_i64, [_i64, _i32]),
     "tsc_pack_f16": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tsc_pack_f16_rows": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "tsc_rmsd_sim_f16ts": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _i64, _i32, _vp]),
     "tsc_pack_tf32": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tsc_rmsd_sim_tf32ts": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _i64, _i32, _vp]),

@@ -12,8 +12,8 @@ namespace tsc {
 __global__ void __launch_bounds__(256) pack_kernel(const double* __restrict__ S, int64_t N, int A,
                                                    const int32_t* __restrict__ heavy_idx, int M, int nslab,
                                                    int64_t nb_pad, double* __restrict__ packed,
-                                                   double* __restrict__ G) {
-    const int b = blockIdx.x;                     // conformer block
+                                                   double* __restrict__ G, int block_begin) {
+    const int b = block_begin + blockIdx.x;       // conformer block
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Mp = nslab * KS;
     for (int c = warp; c < CB; c += 8) {
@@ -45,7 +45,20 @@ extern "C" int tsc_pack(const double* S, int64_t N, int32_t A, const int32_t* he
     if (N <= 0 || M <= 0) return 0;
     const int64_t nb_pad = tsc::num_blocks_padded(N);
     tsc::pack_kernel<<<(unsigned)nb_pad, 256, 0, (cudaStream_t)stream>>>(S, N, A, heavy_idx, M, tsc::num_slabs(M),
-                                                                         nb_pad, packed, G);
+                                                                         nb_pad, packed, G, 0);
+    TSC_CHECK_LAUNCH();
+    return 0;
+}
+
+// The same for the conformer blocks (32 rows each) [block_begin, block_end) only: lets the caller repack a chunk of
+// the ensemble as soon as its host-to-device copy has landed while later chunks are still in flight.
+extern "C" int tsc_pack_blocks(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M,
+                               double* packed, double* G, int64_t block_begin, int64_t block_end, void* stream) {
+    if (N <= 0 || M <= 0 || block_end <= block_begin) return 0;
+    const int64_t nb_pad = tsc::num_blocks_padded(N);
+    if (block_end > nb_pad) block_end = nb_pad;
+    tsc::pack_kernel<<<(unsigned)(block_end - block_begin), 256, 0, (cudaStream_t)stream>>>(
+        S, N, A, heavy_idx, M, tsc::num_slabs(M), nb_pad, packed, G, (int)block_begin);
     TSC_CHECK_LAUNCH();
     return 0;
 }

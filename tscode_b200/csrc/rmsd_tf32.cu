@@ -97,9 +97,9 @@ __global__ void __launch_bounds__(256) pack_f16_kernel(const double* __restrict_
                                                        int64_t n_rows_pad, __half* __restrict__ PA,
                                                        __half* __restrict__ PB, __half* __restrict__ PR,
                                                        double* __restrict__ G, double* __restrict__ sG,
-                                                       float* __restrict__ CT) {
+                                                       float* __restrict__ CT, int64_t row_begin) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t i = (int64_t)blockIdx.x * 8 + warp;          // one warp per conformer (incl. padding rows)
+    const int64_t i = row_begin + (int64_t)blockIdx.x * 8 + warp;      // one warp per conformer (incl. padding rows)
     if (i >= n_rows_pad) return;
     const bool live = i < N;
     const double* src = S + (live ? i : 0) * (int64_t)A * 3;
@@ -314,7 +314,24 @@ extern "C" int tsc_pack_f16(const double* S, int64_t N, int32_t A, const int32_t
     const int64_t rows_pad = (N + TF_ROWS - 1) / TF_ROWS * TF_ROWS;
     pack_f16_kernel<<<(unsigned)((rows_pad + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
         S, N, A, heavy_idx, M, Mp, rows_pad, reinterpret_cast<__half*>(PA), reinterpret_cast<__half*>(PB),
-        reinterpret_cast<__half*>(PR), G, sG, CT);
+        reinterpret_cast<__half*>(PR), G, sG, CT, 0);
+    TSC_CHECK_LAUNCH();
+    return 0;
+}
+
+// The same for conformers [row_begin, row_end) only (row_begin a multiple of 8; the last chunk should end at the
+// padded row count ceil(N/128)*128 so that the padding rows are written too).
+extern "C" int tsc_pack_f16_rows(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M, void* PA,
+                                 void* PB, void* PR, double* G, double* sG, float* CT, int64_t row_begin,
+                                 int64_t row_end, void* stream) {
+    using namespace tsc;
+    if (N <= 0 || M <= 0 || row_end <= row_begin) return 0;
+    const int Mp = (M + 15) / 16 * 16;
+    const int64_t rows_pad = (N + TF_ROWS - 1) / TF_ROWS * TF_ROWS;
+    if (row_end > rows_pad) row_end = rows_pad;
+    pack_f16_kernel<<<(unsigned)((row_end - row_begin + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        S, N, A, heavy_idx, M, Mp, row_end, reinterpret_cast<__half*>(PA), reinterpret_cast<__half*>(PB),
+        reinterpret_cast<__half*>(PR), G, sG, CT, row_begin);
     TSC_CHECK_LAUNCH();
     return 0;
 }

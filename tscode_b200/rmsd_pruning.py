@@ -18,11 +18,18 @@ import numpy as np
 from . import _host
 from ._lib import check, lib, ptr, require_cuda, stream_ptr
 
+import ctypes
 import functools
 
 # f16 / tf32 = tcgen05 pre-screen with the stationary operand in TMEM (FP16 or TF32 operands);
 # tf32ss = both operands from shared memory; dmma / fma = FP64 tensor cores / FMA pipe
 VARIANTS = {"dmma": 0, "fma": 1, "tf32": 2, "tf32ss": 3, "f16": 4}
+
+
+@functools.lru_cache(maxsize=8)
+def _copy_stream(device_str):
+    import torch
+    return torch.cuda.Stream(device=torch.device(device_str))
 
 
 @functools.lru_cache(maxsize=8)
@@ -35,7 +42,7 @@ def _work_lists(N, rank, world, variant, device_str):
     out = {"row_blocks_np": rb, "row_blocks": torch.from_numpy(rb).to(dev)}
     if variant in (2, 3, 4):
         items = np.ascontiguousarray(_host.build_tf32_items(N, rb))
-        out["n_items"], out["items"] = int(items.shape[0]), torch.from_numpy(items).to(dev)
+        out["n_items"], out["items"], out["items_np"] = int(items.shape[0]), torch.from_numpy(items).to(dev), items
     else:
         tiles = _host.build_tiles(N, rb)
         out["n_tiles"], out["tiles"] = int(tiles.shape[0]), torch.from_numpy(tiles).to(dev)
@@ -62,7 +69,8 @@ class RmsdPruner:
     """
 
     def __init__(self, structures, atomnos, rmsd_thr=0.5, *, variant="f16", device=None,
-                 rank=0, world=1, group=None, grid_ctas=0, ladder="fused", pair_cap=None, cand_cap=None):
+                 rank=0, world=1, group=None, grid_ctas=0, ladder="fused", pair_cap=None, cand_cap=None,
+                 pipeline_upload=True):
         torch = require_cuda()
         self.torch = torch
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -76,12 +84,20 @@ class RmsdPruner:
         self.ladder = ladder
         atomnos = np.asarray(atomnos)
         heavy = np.flatnonzero(atomnos != 1).astype(np.int32)
+        self._host = None
         if torch.is_tensor(structures):
-            S = structures.to(self.device, dtype=torch.float64).contiguous()
+            src = structures
         else:
-            S = torch.as_tensor(np.ascontiguousarray(structures, dtype=np.float64)).to(self.device)
-        if S.dim() != 3 or S.shape[2] != 3 or S.shape[1] != atomnos.shape[0]:
-            raise ValueError(f"structures must be (N, {atomnos.shape[0]}, 3), got {tuple(S.shape)}")
+            src = torch.as_tensor(np.ascontiguousarray(structures, dtype=np.float64))
+        if src.dim() != 3 or src.shape[2] != 3 or src.shape[1] != atomnos.shape[0]:
+            raise ValueError(f"structures must be (N, {atomnos.shape[0]}, 3), got {tuple(src.shape)}")
+        if (pipeline_upload and not src.is_cuda and src.dtype == torch.float64 and src.is_contiguous()
+                and src.is_pinned() and src.shape[0] >= 4096):
+            # pinned host input: the copy is issued in chunks by run(), overlapped with pack and screen
+            self._host = src
+            S = torch.empty(src.shape, dtype=torch.float64, device=self.device)
+        else:
+            S = src.to(self.device, dtype=torch.float64).contiguous()
         self.S = S
         self.N, self.A, self.M = int(S.shape[0]), int(S.shape[1]), int(heavy.size)
         N, M = self.N, self.M
@@ -265,16 +281,24 @@ class RmsdPruner:
                 return mask
         return self._eliminate_bitrows()
 
-    def _eliminate_fused(self):
+    def _enqueue_fused(self):
         torch = self.torch
-        N = self.N
         L = lib()
         with torch.cuda.device(self.device):
             if self.world > 1:
                 import torch.distributed as dist
                 dist.all_gather_into_tensor(self.pair_all, self.pair_list, group=self.group)
-            check(L.tsc_elim_fused(ptr(self.pair_all), self.world, self.pair_stride, N, 20, ptr(self.fused_ws),
+            check(L.tsc_elim_fused(ptr(self.pair_all), self.world, self.pair_stride, self.N, 20, ptr(self.fused_ws),
                                    ptr(self.fused_out), stream_ptr()), "tsc_elim_fused")
+        self._fused_enqueued = True
+
+    def _eliminate_fused(self):
+        torch = self.torch
+        N = self.N
+        if not getattr(self, "_fused_enqueued", False):
+            self._enqueue_fused()
+        self._fused_enqueued = False
+        with torch.cuda.device(self.device):
             info = self.fused_out[self._info_off:self._info_off + 128].view(torch.int32).tolist()   # sync
         if info[0] == 1:
             return None                                   # pair list overflow -> bit rows (same on every rank)
@@ -327,10 +351,89 @@ class RmsdPruner:
         h = self.hist.tolist()
         return [k for r, k in enumerate(self._cands) if _host.ladder_gate(k, h[r])]
 
+    def run_async(self):
+        """Enqueue the whole prune (upload if the input was pinned host memory, pack, screen, verify, fused
+        ladder) without waiting for anything; finish() returns the mask.  Lets the caller do host work — e.g.
+        allocating and first-touching the output array — while the GPU runs."""
+        if self.N == 0 or self.M == 0 or self.ladder != "fused":
+            return
+        if self._host is not None:
+            self._upload_pack_screen_pipelined()
+        else:
+            self.pack()
+            self.screen()
+        self.verify()
+        self._enqueue_fused()
+
+    def finish(self):
+        """Mask of a prune started with run_async() (or the whole prune if it was not)."""
+        if getattr(self, "_fused_enqueued", False):
+            return self.eliminate()
+        return self.run()
+
     def run(self):
+        if self._host is not None:
+            self._upload_pack_screen_pipelined()
+            self.verify()
+            return self.eliminate()
         self.pack()
         self.similarity()
         return self.eliminate()
+
+    def _upload_pack_screen_pipelined(self, n_chunks=8):
+        """Pinned host input: H2D copy, pack and screen overlapped.  A 128-row panel only needs the conformers
+        from its own first row to the end (rows i, columns j > i), so the ensemble is uploaded in chunks from the
+        LAST to the first on a copy stream, and as soon as a chunk has landed its rows are packed and the work
+        items of its panels are screened: when the final (first) chunk arrives only its own share of the pairs
+        (~2/n_chunks of them) is still to do."""
+        torch = self.torch
+        host, N = self._host, self.N
+        self._host = None                                # the next run() works from the device copy
+        if self.variant != 4 or N == 0 or self.M == 0:
+            self.S.copy_(host)
+            self.pack()
+            self.screen()
+            return
+        L = lib()
+        n_panels = (N + 127) // 128
+        n_chunks = max(1, min(n_chunks, n_panels))
+        bounds = [(n_panels * c // n_chunks) * 128 for c in range(n_chunks)] + [N]
+        items_np = _work_lists(N, self.rank, self.world, self.variant, str(self.device))["items_np"]
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream()
+            copy = _copy_stream(str(self.device))
+            copy.wait_stream(main)
+            events = []
+            with torch.cuda.stream(copy):
+                for c in reversed(range(n_chunks)):
+                    lo, hi = bounds[c], bounds[c + 1]
+                    self.S[lo:hi].copy_(host[lo:hi], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy)
+                    events.append((c, ev))
+            self.stats.zero_()
+            self.cand_list[0].fill_(0)
+            self._pairs_ready = False
+            rows_pad = n_panels * 128
+            st = stream_ptr()
+            for c, ev in events:
+                lo, hi = bounds[c], bounds[c + 1]
+                main.wait_event(ev)
+                hi_pad = rows_pad if c == n_chunks - 1 else hi
+                check(L.tsc_pack_blocks(ptr(self.S), N, self.A, ptr(self.heavy_idx), self.M, ptr(self.packed), ptr(self.G),
+                                        lo // 32, self.nb_pad if c == n_chunks - 1 else hi // 32, st), "tsc_pack_blocks")
+                check(L.tsc_pack_f16_rows(ptr(self.S), N, self.A, ptr(self.heavy_idx), self.M, ptr(self.PA), ptr(self.PB),
+                                          ptr(self.PR), ptr(self.G), ptr(self.sG), ptr(self.CT), lo, hi_pad, st),
+                      "tsc_pack_f16_rows")
+                i0 = int(np.searchsorted(items_np[:, 0], lo // 128, side="left"))
+                i1 = int(np.searchsorted(items_np[:, 0], (hi + 127) // 128, side="left"))
+                if i1 > i0:
+                    check(L.tsc_rmsd_sim_f16ts(ptr(self.PA), ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG),
+                                               ptr(self.CT), N, self.M,
+                                               ctypes.c_void_p(self.items.data_ptr() + 16 * i0), i1 - i0, self.thr,
+                                               ptr(self.sim_bits), ptr(self.cand_list), self.cand_stride, self.grid_ctas,
+                                               st), "tsc_rmsd_sim_f16ts")
+        self.packed_ready = True
 
     def set_pairs(self, pairs):
         """Replace this rank's confirmed-pair list by explicit (i, j) rows, i < j (tests)."""
@@ -371,7 +474,22 @@ def prune_conformers_rmsd(structures, atomnos, rmsd_thr=0.5):
     if N == 0:
         return structures[:0], np.zeros(0, dtype=np.bool_)
     pr = RmsdPruner(structures, atomnos, rmsd_thr)
-    mask = pr.run().cpu().numpy().astype(np.bool_)
+    pr.run_async()
+    big = (structures.flags.c_contiguous and structures.dtype == np.float64 and structures.nbytes > (1 << 22))
+    out_buf = None
+    if big:
+        # while the GPU works: allocate the output and first-touch its pages with all host threads (page faults on
+        # a fresh 100 MB array cost more than the copy into it)
+        import torch
+        out_buf = torch.empty(structures.shape, dtype=torch.float64)
+        out_buf.zero_()
+    mask = pr.finish().cpu().numpy().astype(np.bool_)
+    if out_buf is not None:
+        import torch
+        idx = torch.from_numpy(np.flatnonzero(mask))
+        out = out_buf[:idx.numel()]
+        torch.index_select(torch.from_numpy(structures), 0, idx, out=out)
+        return out.numpy(), mask
     return _take_rows(structures, mask), mask
 
 
