@@ -26,6 +26,20 @@ import functools
 VARIANTS = {"dmma": 0, "fma": 1, "tf32": 2, "tf32ss": 3, "f16": 4}
 
 
+_STAGING = {}
+
+
+def _staging_buffer(numel):
+    """One cached pinned float64 buffer per process, grown on demand (cudaHostAlloc costs tens of ms: paid once).
+    Calls are serialised by the caller's synchronisation at the end of every prune."""
+    import torch
+    buf = _STAGING.get("buf")
+    if buf is None or buf.numel() < numel:
+        buf = torch.empty(numel, dtype=torch.float64).pin_memory()
+        _STAGING["buf"] = buf
+    return buf[:numel]
+
+
 @functools.lru_cache(maxsize=8)
 def _copy_stream(device_str):
     import torch
@@ -91,10 +105,15 @@ class RmsdPruner:
             src = torch.as_tensor(np.ascontiguousarray(structures, dtype=np.float64))
         if src.dim() != 3 or src.shape[2] != 3 or src.shape[1] != atomnos.shape[0]:
             raise ValueError(f"structures must be (N, {atomnos.shape[0]}, 3), got {tuple(src.shape)}")
+        self._staging = None
         if (pipeline_upload and not src.is_cuda and src.dtype == torch.float64 and src.is_contiguous()
-                and src.is_pinned() and src.shape[0] >= 4096):
-            # pinned host input: the copy is issued in chunks by run(), overlapped with pack and screen
+                and src.shape[0] >= 4096):
+            # host input: the copy is issued in chunks by run(), overlapped with pack and screen.  Pageable memory
+            # (what the reference's callers hold: np.array(poses)) goes through a cached pinned staging buffer,
+            # chunk by chunk, so that the host memcpy of one chunk overlaps the DMA of the previous one.
             self._host = src
+            if not src.is_pinned():
+                self._staging = _staging_buffer(src.numel())
             S = torch.empty(src.shape, dtype=torch.float64, device=self.device)
         else:
             S = src.to(self.device, dtype=torch.float64).contiguous()
@@ -390,6 +409,7 @@ class RmsdPruner:
         host, N = self._host, self.N
         self._host = None                                # the next run() works from the device copy
         if self.variant != 4 or N == 0 or self.M == 0:
+            self._staging = None
             self.S.copy_(host)
             self.pack()
             self.screen()
@@ -404,10 +424,16 @@ class RmsdPruner:
             copy = _copy_stream(str(self.device))
             copy.wait_stream(main)
             events = []
+            stage = self._staging.view(host.shape) if self._staging is not None else None
+            self._staging = None
             with torch.cuda.stream(copy):
                 for c in reversed(range(n_chunks)):
                     lo, hi = bounds[c], bounds[c + 1]
-                    self.S[lo:hi].copy_(host[lo:hi], non_blocking=True)
+                    if stage is not None:
+                        stage[lo:hi].copy_(host[lo:hi])                  # host threads; the previous DMA is in flight
+                        self.S[lo:hi].copy_(stage[lo:hi], non_blocking=True)
+                    else:
+                        self.S[lo:hi].copy_(host[lo:hi], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(copy)
                     events.append((c, ev))
