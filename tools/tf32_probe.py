@@ -35,7 +35,7 @@ for seed, N, M, nc, noise, thr in ((0, 257, 40, 20, 0.05, 0.5), (0, 1000, 40, 10
         assert lost == 0
 
 S = gen_ensemble(3, 50000, 80, 5000)
-for variant, cfg in (("f16", -2), ("f16", -3), ("f16", -4), ("f16", -5), ("tf32", -2)):
+for variant, cfg in (("f16", -2), ("f16", -3), ("f16", -4), ("f16", -5), ("f16", -7), ("tf32", -2)):
     pr = RmsdPruner(S, np.full(80, 6), 0.5, variant=variant, grid_ctas=cfg)
     pr.pack()
     for _ in range(2):

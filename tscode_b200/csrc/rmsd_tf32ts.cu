@@ -67,9 +67,13 @@ constexpr int TS_TRACE_TILES = 96;    // tiles of the first item that are stampe
 // NMMA MMA-issuing warps (tile t is issued by warp t % NMMA): while one of them goes through its per-tile
 // bookkeeping (two mbarrier waits, descriptor set-up, commits: ~460 cycles in the trace) the other keeps the
 // tensor pipe fed, and the MMAs of two tiles (six accumulator chains instead of three) interleave in the pipe.
-template <int CH, int STEP, bool F16, int NACC, int NMMA = 1>
-__global__ void __launch_bounds__((1 + NMMA + 4 * NACC * CH) * 32, 1) rmsd_ts_kernel(const TsParams p) {
-    constexpr int NG = NACC * CH;
+// SPLIT: CH groups in total instead of NACC*CH — group g takes column part g of EVERY tile (both buffers in
+// turn), so all epilogue warps work on the tile that has just finished and the buffer is handed back after half
+// the per-warp work: the serial chain MMA -> completion -> epilogue-until-release -> MMA that bounds the tile
+// rate with two buffers gets shorter, at unchanged total epilogue work.
+template <int CH, int STEP, bool F16, int NACC, int NMMA = 1, bool SPLIT = false>
+__global__ void __launch_bounds__((1 + NMMA + 4 * (SPLIT ? CH : NACC * CH)) * 32, 1) rmsd_ts_kernel(const TsParams p) {
+    constexpr int NG = SPLIT ? CH : NACC * CH;
     constexpr int TS_NACC = NACC;
     constexpr int KT_MAX = NACC == 2 ? TS_KT_MAX : 0;
     constexpr int TS_ACC0 = 3 * 8 * KT_MAX;        // first accumulator column
@@ -219,7 +223,9 @@ __global__ void __launch_bounds__((1 + NMMA + 4 * NACC * CH) * 32, 1) rmsd_ts_ke
         // buffer's barrier, which mbarrier parity waits require (a waiter may never fall two phases behind).
         const int ew = warp - (1 + NMMA);
         const int grp = ew >> 2;
-        const int buf = grp / CH, part = grp % CH;
+        const int part = grp % CH;
+        int buf = SPLIT ? 0 : grp / CH;
+        uint32_t tph_b[TS_MAX_NACC] = {0, 0, 0};                 // SPLIT: one phase per buffer
         const int quad = warp & 3;
         const int row_in_panel = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
@@ -265,17 +271,26 @@ __global__ void __launch_bounds__((1 + NMMA + 4 * NACC * CH) * 32, 1) rmsd_ts_ke
             float gv_next = 0.f;
             bool have_next = false;
             for (int t = 0; t < w.z; t++, tile_seq++) {
-                if ((int)(tile_seq % NACC) == buf) {
+                if (SPLIT) buf = (int)(tile_seq % NACC);
+                if (SPLIT || (int)(tile_seq % NACC) == buf) {
+                    constexpr int AHEAD = SPLIT ? 1 : NACC;              // this group's next tile
                     const int64_t j0 = (int64_t)(w.y + t) * TF_J;
                     // column terms: prefetched one of this group's tiles ahead (the first of an item is a direct load)
                     const float gvf = have_next ? gv_next : __ldg(&p.CT[(int64_t)(w.y + t) * 32 + lane]);
-                    have_next = t + NACC < w.z;
-                    if (have_next) gv_next = __ldg(&p.CT[(int64_t)(w.y + t + NACC) * 32 + lane]);
+                    have_next = t + AHEAD < w.z;
+                    if (have_next) gv_next = __ldg(&p.CT[(int64_t)(w.y + t + AHEAD) * 32 + lane]);
                     const bool tr = p.trace && it == 0 && t < TS_TRACE_TILES && lane == 0 && quad == 0 && part == 0;
                     if (tr) p.trace[t * 8 + 4] = clock64();
-                    mbar_wait(&t_full[buf], tph);
+                    if (SPLIT) {
+                        // (static indexing keeps the phases in registers)
+                        const uint32_t ph = buf == 0 ? tph_b[0] : buf == 1 ? tph_b[1] : tph_b[2];
+                        mbar_wait(&t_full[buf], ph);
+                        if (buf == 0) tph_b[0] ^= 1u; else if (buf == 1) tph_b[1] ^= 1u; else tph_b[2] ^= 1u;
+                    } else {
+                        mbar_wait(&t_full[buf], tph);
+                        tph ^= 1u;
+                    }
                     if (tr) p.trace[t * 8 + 5] = clock64();
-                    tph ^= 1u;
                     tcgen05_fence_after();
                     const uint32_t d0 = tmem_base + lane_addr + TS_ACC0 + (uint32_t)buf * TF_ACC_COLS;
                     uint32_t bits;
@@ -376,7 +391,10 @@ static int launch_ts(const void* PA, const void* PB, const void* PR, const doubl
     // grid_ctas < 0 selects an alternative configuration (tuning aid): -1 = A in TMEM, 2 groups, 8 columns per
     // TMEM load round; -2 = A in TMEM, 2 groups x 4; -3 = A in TMEM, 4 groups (two column halves per tile) x 4;
     // -4 = A in shared memory, 3 accumulator buffers, 3 groups x 4;  -5 = as -2 with two MMA warps;
-    // (measured on C3, FP16 operands: -2 2.72 ms, -3 3.08, -4 2.78, -5 2.88; reading the whole tile into 144
+    // -7 = A in TMEM, 2 groups each taking one column half of EVERY tile (SPLIT);
+    // (measured on C3, FP16 operands: -2 2.72 ms, -3 3.08, -4 2.78, -5 2.88, -7 3.60 — an epilogue warp spends
+    // ~600 cycles per tile whatever the number of columns it handles, so fewer columns per warp-tile lose;
+    // reading the whole tile into 144
     // registers and releasing before any arithmetic: 4.06)
     // default = TS_DEFAULT_CFG
     const int cfg = grid_ctas < 0 ? -grid_ctas : TS_DEFAULT_CFG;
@@ -393,8 +411,8 @@ static int launch_ts(const void* PA, const void* PB, const void* PR, const doubl
     const size_t smem = a_bytes + nb * b_bytes + 512 + q_bytes;
     auto kern = cfg == 1 ? rmsd_ts_kernel<1, 8, F16, 2> : cfg == 2 ? rmsd_ts_kernel<1, 4, F16, 2>
               : cfg == 3 ? rmsd_ts_kernel<2, 4, F16, 2> : cfg == 4 ? rmsd_ts_kernel<1, 4, F16, 3>
-              : rmsd_ts_kernel<1, 4, F16, 2, 2>;
-    const int threads = cfg <= 2 ? 320 : cfg == 3 ? 576 : cfg == 4 ? 448 : 352;
+              : cfg == 5 ? rmsd_ts_kernel<1, 4, F16, 2, 2> : rmsd_ts_kernel<2, 4, F16, 2, 1, true>;
+    const int threads = cfg <= 2 ? 320 : cfg == 3 ? 576 : cfg == 4 ? 448 : cfg == 5 ? 352 : 320;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;

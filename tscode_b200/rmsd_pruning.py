@@ -214,6 +214,9 @@ class RmsdPruner:
 
     # ---- phases -------------------------------------------------------------------------------
     def pack(self):
+        if self._host is not None:                       # phases driven by hand: plain upload first
+            self.S.copy_(self._host)
+            self._host, self._staging = None, None
         if self.N == 0 or self.M == 0:
             return
         L = lib()
