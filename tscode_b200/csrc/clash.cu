@@ -46,8 +46,7 @@ __device__ __forceinline__ bool count_block(const double* xa, const double* ya, 
         // absent atoms sit at 1e200: d2 overflows to +inf, never below any threshold
         const double x1 = v1 ? xb[b1] : 1e200, y1 = v1 ? yb[b1] : 1e200, z1 = v1 ? zb[b1] : 1e200;
         const double x2 = v2 ? xb[b2] : 1e200, y2 = v2 ? yb[b2] : 1e200, z2 = v2 ? zb[b2] : 1e200;
-        int cnt = 0;
-        for (int a = 0; a < na; a++) {
+        auto pair2 = [&](int a, int& cnt) {
             const double ax = xa[a], ay = ya[a], az = za[a];
             {
                 const double dx = ax - x1, dy = ay - y1, dz = az - z1;
@@ -61,11 +60,20 @@ __device__ __forceinline__ bool count_block(const double* xa, const double* ya, 
                 cnt += d2 < th.t2;
                 if (REPORT) near += (d2 > th.near_lo2 && d2 < th.near_hi2);
             }
-            if ((a & 7) == 7 || a == na - 1) {
-                count += __reduce_add_sync(0xffffffffu, cnt);
-                cnt = 0;
-                if (!REPORT && count > max_clashes) return true;
-            }
+        };
+        int a = 0;
+        for (; a + 8 <= na; a += 8) {                 // 8 A atoms per early-exit check, no per-atom branches
+            int cnt = 0;
+#pragma unroll
+            for (int u = 0; u < 8; u++) pair2(a + u, cnt);
+            count += __reduce_add_sync(0xffffffffu, cnt);
+            if (!REPORT && count > max_clashes) return true;
+        }
+        if (a < na) {
+            int cnt = 0;
+            for (; a < na; a++) pair2(a, cnt);
+            count += __reduce_add_sync(0xffffffffu, cnt);
+            if (!REPORT && count > max_clashes) return true;
         }
     }
     return count > max_clashes;
@@ -112,10 +120,10 @@ __device__ __forceinline__ int verdict_intramolecular(const double* sx, const do
     return 1;
 }
 
-template <bool REPORT>
+template <bool REPORT, int F>       // F (2 or 3) is a template parameter: fragment loops unroll, offsets stay in registers
 __global__ void __launch_bounds__(CLASH_WARPS * 32) embed_clash_kernel(
     const double* __restrict__ frag_lib, const int64_t* __restrict__ frag_off, const int32_t* __restrict__ n_atoms,
-    int F, const int32_t* __restrict__ conf, const double* __restrict__ R, const double* __restrict__ t, int64_t P,
+    const int32_t* __restrict__ conf, const double* __restrict__ R, const double* __restrict__ t, int64_t P,
     int A_total, ClashThresh th, long long max_clashes, uint8_t* __restrict__ verdict, unsigned long long* near_out) {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -123,9 +131,11 @@ __global__ void __launch_bounds__(CLASH_WARPS * 32) embed_clash_kernel(
     double* sy = sx + A_total;
     double* sz = sy + A_total;
     int off[3] = {0, 0, 0}, n[3] = {0, 0, 0};
+    const double* Xbase[3] = {nullptr, nullptr, nullptr};
     {
         int o = 0;
-        for (int k = 0; k < F; k++) { n[k] = n_atoms[k]; off[k] = o; o += n[k]; }
+#pragma unroll
+        for (int k = 0; k < F; k++) { n[k] = n_atoms[k]; off[k] = o; o += n[k]; Xbase[k] = frag_lib + frag_off[k]; }
     }
     unsigned long long near = 0;
     const int64_t warp_g = (int64_t)blockIdx.x * CLASH_WARPS + warp;
@@ -133,8 +143,9 @@ __global__ void __launch_bounds__(CLASH_WARPS * 32) embed_clash_kernel(
     // (requesting the next pose's parameters ahead — lanes fetching R ++ t together, read back with shuffles — was
     // measured slower, 0.180 vs 0.166 ms on C2: the kernel is bound by issue slots, not by that round trip)
     for (int64_t p = warp_g; p < P; p += nwarps) {
+#pragma unroll
         for (int k = 0; k < F; k++) {
-            const double* X = frag_lib + frag_off[k] + (int64_t)conf[p * F + k] * 3 * n[k];
+            const double* X = Xbase[k] + (int64_t)conf[p * F + k] * 3 * n[k];
             const double* r = R + (p * F + k) * 9;
             const double* tt = t + (p * F + k) * 3;
             const double r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3], r4 = r[4], r5 = r[5], r6 = r[6], r7 = r[7],
@@ -333,16 +344,18 @@ extern "C" int tsc_embed_clash(const double* frag_lib, const int64_t* frag_off, 
     if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
     cudaError_t e;
     if (near_count) {
-        e = cudaFuncSetAttribute(embed_clash_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        auto kern = F == 2 ? embed_clash_kernel<true, 2> : embed_clash_kernel<true, 3>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        embed_clash_kernel<true><<<clash_grid(P), CLASH_WARPS * 32, smem, (cudaStream_t)stream>>>(
-            frag_lib, frag_off, n_atoms, F, conf, R, t, P, A_total, th, max_clashes, verdict,
+        kern<<<clash_grid(P), CLASH_WARPS * 32, smem, (cudaStream_t)stream>>>(
+            frag_lib, frag_off, n_atoms, conf, R, t, P, A_total, th, max_clashes, verdict,
             reinterpret_cast<unsigned long long*>(near_count));
     } else {
-        e = cudaFuncSetAttribute(embed_clash_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        auto kern = F == 2 ? embed_clash_kernel<false, 2> : embed_clash_kernel<false, 3>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        embed_clash_kernel<false><<<clash_grid(P), CLASH_WARPS * 32, smem, (cudaStream_t)stream>>>(
-            frag_lib, frag_off, n_atoms, F, conf, R, t, P, A_total, th, max_clashes, verdict, nullptr);
+        kern<<<clash_grid(P), CLASH_WARPS * 32, smem, (cudaStream_t)stream>>>(
+            frag_lib, frag_off, n_atoms, conf, R, t, P, A_total, th, max_clashes, verdict, nullptr);
     }
     TSC_CHECK_LAUNCH();
     return 0;
