@@ -231,6 +231,20 @@ int tsc_string_embed_params(const double* centers1, const double* vecs1, const d
                             const double* sin_half, const double* cos_half, const uint8_t* nonzero,
                             int32_t n_ang, const double* flip, int32_t* conf, double* R, double* t, void* stream);
 
+/* Pose parameters of the cyclical embeds generated on the device (embeds.py:657-709), G groups (combination of
+ * conformers, pivots and polygon orientation) x C angle combinations (embedder.systematic_angles) x F molecules:
+ *   A = align_vec_pair([end - start, direction], [pivot, mol_direction])   (algebra.py:258-282, once per group
+ *   and molecule), axis = A @ axis_src, Sr = rot_mat_from_pointer(axis, angle), rotation = Sr @ A,
+ *   position = A @ apm - Sr @ (A @ apm) + vmean - A @ pmean.
+ * (G, F, ...) inputs: ref2 (2,3), tgt2 (2,3), axis_src (3) = rc0 - rc1 or pivot, apm (3) = atomic_pivot_mean,
+ * vmean (3) = mean(vec_pair), pmean (3) = pivot.meanpoint, gconf int32 conformer index; combos (C, F) int32 index
+ * into the angle table; sin_half / cos_half = host-evaluated sin, cos of angle/2; scratch G*F*18 doubles.
+ * Out: conf (G*C, F) int32, R (G*C, F, 3, 3), t (G*C, F, 3); pose g*C + c. */
+int tsc_cyclical_embed_params(const double* ref2, const double* tgt2, const double* axis_src, const double* apm,
+                              const double* vmean, const double* pmean, const int32_t* gconf, int64_t G, int32_t F,
+                              const int32_t* combos, int64_t C, const double* sin_half, const double* cos_half,
+                              double* scratch, int32_t* conf, double* R, double* t, void* stream);
+
 /* ---- prune_conformers_rmsd_rot_corr ---------------------------------------------------------- */
 /* Rotor-corrected RMSD of every pair (i in [row_begin,row_end), j > i), stateless from the centred
  * structures Sc (N, A, 3)  (rotationally_corrected_rmsd, torsion_module.py:953-1011).

@@ -184,6 +184,30 @@ def main():
             print("moi:", {k: v for k, v in rows[-1].items() if k not in ("mask_hex", "atomnos", "masses")})
         json.dump({"meta": meta, "rows": rows}, open(os.path.join(GOLD, "tfd_moi.json"), "w"), indent=1)
 
+    # ---- (f)-2b: pose parameters of the cyclical embeds (embeds.py:657-709) with the reference's own builders ----
+    if want("cyclicalembed"):
+        rng = np.random.default_rng(88)
+        G, F = 7, 3
+        ref2, tgt2 = rng.normal(size=(G, F, 2, 3)), rng.normal(size=(G, F, 2, 3))
+        axis_src, apm = rng.normal(size=(G, F, 3)), rng.normal(size=(G, F, 3)) * 2
+        vmean, pmean = rng.normal(size=(G, F, 3)) * 3, rng.normal(size=(G, F, 3)) * 2
+        steps = [0, 120, 240]
+        sys_angles = np.array([(a, b, c) for a in steps for b in steps for c in steps], dtype=float)
+        Rs, ts = [], []
+        for g in range(G):
+            for angles in sys_angles:
+                Rg, tg = [], []
+                for i in range(F):
+                    A = align_vec_pair(ref2[g, i], tgt2[g, i])
+                    step = rot_mat_from_pointer(A @ axis_src[g, i], float(angles[i]))
+                    cor = A @ apm[g, i]
+                    pos = vmean[g, i] - A @ pmean[g, i]
+                    Rg.append(step @ A); tg.append(cor - step @ cor + pos)
+                Rs.append(Rg); ts.append(tg)
+        np.savez_compressed(os.path.join(GOLD, "cyclical_embed_params.npz"), ref2=ref2, tgt2=tgt2, axis_src=axis_src, apm=apm,
+                            vmean=vmean, pmean=pmean, sys_angles=sys_angles, R=np.array(Rs), t=np.array(ts))
+        print("cyclicalembed:", len(Rs), "poses")
+
     # ---- A7/A8: get_embed + compenetration_check ---------------------------------------------
     if want("clash"):
         rows = [

@@ -164,6 +164,26 @@ def string_embed_params(centers, vecs, angles):
     return np.array(conf), np.array(R), np.array(t)
 
 
+def cyclical_embed_params(ref2, tgt2, axis_src, apm, vec_mean, pivot_mean, systematic_angles):
+    """Pose parameters of the cyclical embeds, embeds.py:657-709, per group g and angle combination c:
+    (R (G*C, F, 3, 3), t (G*C, F, 3)), pose index g*C + c."""
+    ref2, tgt2 = np.asarray(ref2, float), np.asarray(tgt2, float)
+    G, F = ref2.shape[:2]
+    ang = np.asarray(systematic_angles, float).reshape(-1, F)
+    R, t = [], []
+    for g in range(G):
+        for angles in ang:
+            Rg, tg = [], []
+            for i in range(F):
+                A = align_vec_pair(ref2[g, i], tgt2[g, i])                       # :682
+                step = rot_mat_from_pointer(A @ axis_src[g][i], angles[i])       # :688-696
+                cor = A @ apm[g][i]                                              # :698
+                pos = vec_mean[g][i] - A @ pivot_mean[g][i]                      # :706
+                Rg.append(step @ A); tg.append(cor - step @ cor + pos)           # :703, :707
+            R.append(Rg); t.append(tg)
+    return np.array(R), np.array(t)
+
+
 def align_vec_pair(ref, tgt):
     """algebra.py:258-282."""
     B = np.einsum("ji,jk->ik", np.asarray(ref, float), np.asarray(tgt, float))

@@ -555,3 +555,20 @@ def test_f16_screen_extreme_coordinates(gpu, scale, shift):
         pr = RmsdPruner(S, at, thr, variant=variant)
         m = pr.run().cpu().numpy()
         assert np.array_equal(m, ref), (variant, scale, shift, int(m.sum()), int(ref.sum()), pr.stats_dict())
+
+
+def test_cyclical_embed_params_on_device_vs_live_reference(gpu):
+    """(f)-2: tsc_cyclical_embed_params (alignment by Horn's key matrix instead of the reference's SVD, step
+    rotation, positions) against the R, t of the live reference's builders; 1e-12."""
+    from tscode_b200.embeds import cyclical_embed_poses
+    g = np.load(os.path.join(GOLDEN, "cyclical_embed_params.npz"))
+    rng = np.random.default_rng(4)
+    frags = [rng.normal(size=(2, n, 3)) for n in (9, 12, 7)]
+    gconf = rng.integers(0, 2, size=(7, 3))
+    pb, gid = cyclical_embed_poses(frags, gconf, g["ref2"], g["tgt2"], g["axis_src"], g["apm"], g["vmean"], g["pmean"],
+                                   g["sys_angles"])
+    assert pb.P == 7 * 27 and np.array_equal(gid.cpu().numpy(), np.repeat(np.arange(7), 27))
+    R, t = pb.R.cpu().numpy(), pb.t.cpu().numpy()
+    assert np.abs(R - g["R"]).max() < 1e-12 and np.abs(t - g["t"]).max() < 1e-12
+    assert np.array_equal(pb.conf.cpu().numpy(), np.repeat(gconf, 27, axis=0))
+    assert pb.clash(1.0, 0).shape[0] == pb.P

@@ -170,3 +170,13 @@ def test_oracle_tfd_moi_pruning_vs_live_reference(r):
         assert np.allclose(mom, r["moments_row0"], rtol=1e-12)
         _, mask = oracle_np.prune_by_moment_of_inertia(S, atomnos, masses, r["max_deviation"])
     assert mask_digest(mask) == r["digest"] and np.array_equal(mask, want)
+
+
+def test_oracle_cyclical_embed_params_vs_live_reference():
+    """(f)-2: pose parameters of the cyclical embeds (embeds.py:657-709), numpy oracle vs the live reference's
+    align_vec_pair / rot_mat_from_pointer."""
+    g = np.load(os.path.join(GOLDEN, "cyclical_embed_params.npz"))
+    R, t = oracle_np.cyclical_embed_params(g["ref2"], g["tgt2"], g["axis_src"], g["apm"], g["vmean"], g["pmean"],
+                                           g["sys_angles"])
+    assert R.shape == g["R"].shape == (7 * 27, 3, 3, 3)
+    assert np.abs(R - g["R"]).max() < 1e-13 and np.abs(t - g["t"]).max() < 1e-12

@@ -67,6 +67,8 @@ SIGNATURES = {
     "tsc_bench_fp64": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "tsc_string_embed_params": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
                                           _vp, _vp]),
+    "tsc_cyclical_embed_params": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp,
+                                            _vp, _vp, _vp]),
     "tsc_embed_gather": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
 }
 

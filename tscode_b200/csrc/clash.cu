@@ -18,6 +18,7 @@
 //
 // Roofline: FP64 FMA pipe (6 FP64 instructions per atom pair); bytes are negligible.
 #include "tsc_common.cuh"
+#include "tsc_math.cuh"
 
 namespace tsc {
 
@@ -330,6 +331,78 @@ __global__ void __launch_bounds__(256) string_embed_params_kernel(
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// On-device pose parameters of the cyclical embeds (tscode/embeds.py:657-709).  For one group (a combination of
+// conformers, pivots and polygon orientation) and molecule i the reference computes, per pose,
+//     A   = align_vec_pair([end - start, direction_i], [pivot_i, mol_direction_i])        # 3x3 SVD, :682
+//     axis = A @ (rc0 - rc1)  or  A @ pivot_i;  Sr = rot_mat_from_pointer(axis, angle_i)   # :688-696
+//     rotation = Sr @ A;  position = A @ apm - Sr @ (A @ apm) + mean(vec_pair) - A @ meanpoint   # :698-708
+// Only Sr depends on the pose (its angle), so a first kernel does the per-(group, molecule) part once — the
+// alignment is the optimal rotation of a two-vector correlation, obtained here as the top eigenvector of Horn's
+// key matrix instead of an SVD with reflection fix (same rotation whenever it is unique) — and a second kernel
+// expands groups x angle combinations into the (R, t) arrays of the fused clash screen.
+// ------------------------------------------------------------------------------------------
+__global__ void cyclical_group_kernel(const double* __restrict__ ref2, const double* __restrict__ tgt2,
+                                      const double* __restrict__ axis_src, const double* __restrict__ apm,
+                                      const double* __restrict__ vmean, const double* __restrict__ pmean, int64_t n,
+                                      double* __restrict__ A_out, double* __restrict__ axis_out,
+                                      double* __restrict__ cor_out, double* __restrict__ pos_out) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const double* rf = ref2 + e * 6;
+        const double* tg = tgt2 + e * 6;
+        // cross-covariance taking tgt onto ref: S[a][b] = sum_j tgt[j][a] * ref[j][b]  (= B^T of algebra.py:266-272)
+        double S[9];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) S[3 * a + b] = tg[a] * rf[b] + tg[3 + a] * rf[3 + b];
+        double A[9];
+        kabsch_rot_from_cov(S, A, nullptr, nullptr);
+        const double* u = axis_src + e * 3, *c = apm + e * 3, *vm = vmean + e * 3, *pm = pmean + e * 3;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            axis_out[e * 3 + r] = A[3 * r] * u[0] + A[3 * r + 1] * u[1] + A[3 * r + 2] * u[2];
+            cor_out[e * 3 + r] = A[3 * r] * c[0] + A[3 * r + 1] * c[1] + A[3 * r + 2] * c[2];
+            pos_out[e * 3 + r] = vm[r] - (A[3 * r] * pm[0] + A[3 * r + 1] * pm[1] + A[3 * r + 2] * pm[2]);
+        }
+#pragma unroll
+        for (int q = 0; q < 9; q++) A_out[e * 9 + q] = A[q];
+    }
+}
+
+__global__ void __launch_bounds__(256) cyclical_pose_kernel(
+    const double* __restrict__ A, const double* __restrict__ axis, const double* __restrict__ cor,
+    const double* __restrict__ pos, const int32_t* __restrict__ gconf, const int32_t* __restrict__ combos,
+    const double* __restrict__ sin_half, const double* __restrict__ cos_half, int64_t G, int F, int64_t C,
+    int32_t* __restrict__ conf, double* __restrict__ R, double* __restrict__ t) {
+    const int64_t total = G * C * F;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e % F);
+        const int64_t pose = e / F, g = pose / C, c = pose % C;
+        const int64_t gi = g * F + i;
+        const int k = combos[c * F + i];
+        const double* ax = axis + gi * 3;
+        const double nrm = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);        // rot_mat_from_pointer, algebra.py:325-344
+        const double q1 = sin_half[k] * (ax[0] / nrm), q2 = sin_half[k] * (ax[1] / nrm), q3 = sin_half[k] * (ax[2] / nrm),
+                     q0 = cos_half[k];
+        const double Sr[9] = {2 * (q0 * q0 + q1 * q1) - 1, 2 * (q1 * q2 - q0 * q3),     2 * (q1 * q3 + q0 * q2),
+                              2 * (q1 * q2 + q0 * q3),     2 * (q0 * q0 + q2 * q2) - 1, 2 * (q2 * q3 - q0 * q1),
+                              2 * (q1 * q3 - q0 * q2),     2 * (q2 * q3 + q0 * q1),     2 * (q0 * q0 + q3 * q3) - 1};
+        double Rm[9];
+        mat3_mul(Sr, A + gi * 9, Rm);
+        const double* cr = cor + gi * 3;
+        const double* ps = pos + gi * 3;
+        double* Ro = R + e * 9;
+        double* to = t + e * 3;
+#pragma unroll
+        for (int q = 0; q < 9; q++) Ro[q] = Rm[q];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+            to[r] = (cr[r] - (Sr[3 * r] * cr[0] + Sr[3 * r + 1] * cr[1] + Sr[3 * r + 2] * cr[2])) + ps[r];
+        conf[e] = gconf[gi];
+    }
+}
+
 }  // namespace tsc
 
 extern "C" int tsc_embed_clash(const double* frag_lib, const int64_t* frag_off, const int32_t* n_atoms, int32_t F,
@@ -414,6 +487,33 @@ extern "C" int tsc_string_embed_params(const double* centers1, const double* vec
     tsc::string_embed_params_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         centers1, vecs1, centers2, vecs2, n_conf1, n_conf2, n_c1, n_c2, sin_half, cos_half, nonzero, n_ang, flip, P, conf,
         R, t);
+    TSC_CHECK_LAUNCH();
+    return 0;
+}
+
+// Pose parameters of cyclical embeds (embeds.py:657-709) for G groups x C angle combinations x F molecules.
+//   per (group, molecule), (G, F, ...) arrays: ref2 (2, 3) = [end - start, direction], tgt2 (2, 3) = [pivot,
+//   mol_direction], axis_src (3) = rc0 - rc1 or pivot, apm (3) = atomic_pivot_mean, vmean (3) = mean(vec_pair),
+//   pmean (3) = pivot.meanpoint, gconf int32 = conformer index;  combos (C, F) int32 = index of every molecule's
+//   angle in the table;  sin_half / cos_half: host-evaluated sin, cos of angle/2.
+//   scratch: G*F*18 doubles.  Out: conf (G*C, F) int32, R (G*C, F, 3, 3), t (G*C, F, 3); pose index = g*C + c.
+extern "C" int tsc_cyclical_embed_params(const double* ref2, const double* tgt2, const double* axis_src, const double* apm,
+                                         const double* vmean, const double* pmean, const int32_t* gconf, int64_t G,
+                                         int32_t F, const int32_t* combos, int64_t C, const double* sin_half,
+                                         const double* cos_half, double* scratch, int32_t* conf, double* R, double* t,
+                                         void* stream) {
+    using namespace tsc;
+    if (G <= 0 || C <= 0 || F <= 0) return 0;
+    const int64_t n = G * F;
+    double* A = scratch, *axis = A + n * 9, *cor = axis + n * 3, *pos = cor + n * 3;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t b1 = (n + 127) / 128;
+    if (b1 > 148 * 16) b1 = 148 * 16;
+    cyclical_group_kernel<<<(unsigned)b1, 128, 0, st>>>(ref2, tgt2, axis_src, apm, vmean, pmean, n, A, axis, cor, pos);
+    TSC_CHECK_LAUNCH();
+    int64_t b2 = (G * C * F + 255) / 256;
+    if (b2 > 148 * 32) b2 = 148 * 32;
+    cyclical_pose_kernel<<<(unsigned)b2, 256, 0, st>>>(A, axis, cor, pos, gconf, combos, sin_half, cos_half, G, F, C, conf, R, t);
     TSC_CHECK_LAUNCH();
     return 0;
 }

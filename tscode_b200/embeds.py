@@ -71,6 +71,46 @@ def string_embed_poses(frags, centers, vecs, angles):
     return PoseBatch(frags, conf[:P], R[:P], t[:P])
 
 
+def cyclical_embed_poses(frags, group_conf, ref2, tgt2, axis_src, atomic_pivot_mean, vec_mean, pivot_mean,
+                         systematic_angles):
+    """The pose space of a cyclical embed (embeds.py:657-718) generated ON THE DEVICE.
+
+    Per group g (one combination of conformers, pivots and polygon orientation) and molecule i the host supplies
+    what the reference's loop derives before touching the angles:
+      group_conf (G, F) conformer ids;  ref2 (G, F, 2, 3) = [end - start, directions[i]];
+      tgt2 (G, F, 2, 3) = [pivots[i].pivot, mol_direction];  axis_src (G, F, 3) = reactive_coords[0] -
+      reactive_coords[1] (two reactive atoms) or pivots[i].pivot;  atomic_pivot_mean (G, F, 3);
+      vec_mean (G, F, 3) = np.mean(vec_pair, axis=0);  pivot_mean (G, F, 3) = pivots[i].meanpoint;
+    systematic_angles: (C, F) degrees (embedder.systematic_angles).
+    Returns (PoseBatch of G*C poses in the reference's order — groups outermost, angles innermost —, group_id (G*C,)
+    device tensor for dedup_groups)."""
+    torch = require_cuda()
+    from ._lib import check, lib, ptr, stream_ptr
+    dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+    group_conf = np.ascontiguousarray(group_conf, dtype=np.int32)
+    G, F = group_conf.shape
+    ang = np.asarray(systematic_angles, dtype=np.float64).reshape(-1, F)
+    C = ang.shape[0]
+    table, inv = np.unique(ang, return_inverse=True)
+    combos = np.ascontiguousarray(inv.reshape(C, F).astype(np.int32))
+    half = table * np.pi / 180 / 2                                  # algebra.py:337-341
+    up = lambda a, dt=np.float64: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+    d_ref, d_tgt = up(np.reshape(ref2, (G, F, 2, 3))), up(np.reshape(tgt2, (G, F, 2, 3)))
+    d_axis, d_apm, d_vm, d_pm = (up(np.reshape(a, (G, F, 3))) for a in (axis_src, atomic_pivot_mean, vec_mean, pivot_mean))
+    d_gconf, d_combos = up(group_conf, np.int32), up(combos, np.int32)
+    d_sin, d_cos = up(np.sin(half)), up(np.cos(half))
+    P = G * C
+    scratch = torch.empty(max(G * F * 18, 1), dtype=torch.float64, device=dev)
+    conf = torch.empty((max(P, 1), F), dtype=torch.int32, device=dev)
+    R = torch.empty((max(P, 1), F, 3, 3), dtype=torch.float64, device=dev)
+    t = torch.empty((max(P, 1), F, 3), dtype=torch.float64, device=dev)
+    check(lib().tsc_cyclical_embed_params(ptr(d_ref), ptr(d_tgt), ptr(d_axis), ptr(d_apm), ptr(d_vm), ptr(d_pm),
+                                          ptr(d_gconf), G, F, ptr(d_combos), C, ptr(d_sin), ptr(d_cos), ptr(scratch),
+                                          ptr(conf), ptr(R), ptr(t), stream_ptr()), "tsc_cyclical_embed_params")
+    gid = torch.arange(G, device=dev).repeat_interleave(C)
+    return PoseBatch(frags, conf[:P], R[:P], t[:P]), gid
+
+
 def dedup_groups(poses, group_id, passed=None, rmsd_thr=1.0):
     """Group-local de-duplication of generated poses — the `_rmsd_similarity(pose, angular_poses, rmsd_thr=1)`
     step of the cyclical embeds (embeds.py:714-718, 842-846), batched.
