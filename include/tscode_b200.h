@@ -194,6 +194,13 @@ int tsc_moi_moments(const double* S, int64_t N, int32_t A, const int32_t* heavy_
 int tsc_moi_scan(const double* moments, int64_t N, double max_deviation, int32_t* first_hit, uint64_t* near_count,
                  void* stream);
 
+/* Distance-constraint scores of P structures: score_abs32 = _score_embed_poses (numba_functions.py:273-288, sum of
+ * |dist - target| accumulated in float32), error_signed = the error of fitness_check (optimization_methods.py:544-557,
+ * signed sum in float64; the verdict is error < threshold).  cons (K, 2) int32 / targets (K) shared by all structures
+ * (per_pose = 0) or (P, K, 2) / (P, K) (per_pose = 1); NaN target = no target (None).  Either output may be NULL. */
+int tsc_constraint_scores(const double* S, int64_t P, int32_t A, const int32_t* cons, const double* targets,
+                          int32_t K, int32_t per_pose, float* score_abs32, double* error_signed, void* stream);
+
 /* ---- compenetration_check / get_embed -------------------------------------------------- */
 /* Fused pose transform + clash screen (embeds.py:116-118 / 713-714 / 841-842).
  *   frag_lib: all fragments' conformers back to back; frag_off (F) int64 = offset in doubles of

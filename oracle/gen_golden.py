@@ -208,6 +208,22 @@ def main():
                             vmean=vmean, pmean=pmean, sys_angles=sys_angles, R=np.array(Rs), t=np.array(ts))
         print("cyclicalembed:", len(Rs), "poses")
 
+    # ---- _score_embed_poses / fitness_check ------------------------------------------------------------
+    if want("scores"):
+        from tscode.numba_functions import _score_embed_poses
+        from tscode.optimization_methods import fitness_check
+        S = gen_ensemble(61, 200, 30, 20, sigma_noise=0.3)
+        rng = np.random.default_rng(61)
+        cons = rng.integers(0, 30, size=(200, 3, 2)); cons[:, :, 1] = (cons[:, :, 0] + 1 + rng.integers(0, 28, size=(200, 3))) % 30
+        dists = rng.uniform(1.5, 6.0, size=(200, 3))
+        scores = _score_embed_poses(S, cons, dists)
+        targets = [[None if (p + k) % 5 == 0 else float(dists[p, k]) for k in range(3)] for p in range(200)]
+        fit = [bool(fitness_check(S[p], [tuple(c) for c in cons[p]], targets[p], 1.0)) for p in range(200)]
+        json.dump({"seed": 61, "N": 200, "M": 30, "n_clusters": 20, "sigma_noise": 0.3, "cons": cons.tolist(),
+                   "dists": dists.tolist(), "scores": [float(x) for x in scores], "fitness_threshold": 1.0,
+                   "fitness": fit}, open(os.path.join(GOLD, "constraint_scores.json"), "w"))
+        print("scores:", float(scores.sum()), sum(fit))
+
     # ---- A7/A8: get_embed + compenetration_check ---------------------------------------------
     if want("clash"):
         rows = [

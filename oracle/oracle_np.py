@@ -354,3 +354,24 @@ def prune_by_moment_of_inertia(structures, atomnos, masses, max_deviation=1e-2):
         for i in set(g) - {g[0]}:
             mask[i] = False
     return structures[mask], mask
+
+
+def score_embed_poses(structures, constrained_indices, constrained_distances):
+    """numba_functions.py:273-288: float32 accumulation of float64 terms."""
+    scores = np.zeros(len(structures), dtype=np.float32)
+    for j in range(len(structures)):
+        for i, (i1, i2) in enumerate(constrained_indices[j]):
+            v = structures[j][i1] - structures[j][i2]
+            dist = np.sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])
+            scores[j] += np.abs(dist - constrained_distances[j][i])
+    return scores
+
+
+def fitness_check(coords, constraints, targets, threshold):
+    """optimization_methods.py:544-557."""
+    error = 0
+    for (a, b), target in zip(constraints, targets):
+        if target is not None:
+            v = coords[a] - coords[b]
+            error += (np.sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) - target)
+    return error < threshold

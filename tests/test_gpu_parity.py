@@ -572,3 +572,19 @@ def test_cyclical_embed_params_on_device_vs_live_reference(gpu):
     assert np.abs(R - g["R"]).max() < 1e-12 and np.abs(t - g["t"]).max() < 1e-12
     assert np.array_equal(pb.conf.cpu().numpy(), np.repeat(gconf, 27, axis=0))
     assert pb.clash(1.0, 0).shape[0] == pb.P
+
+
+def test_constraint_scores_vs_live_reference(gpu):
+    """_score_embed_poses (float32 scores, bit-exact) and fitness_check verdicts against the live reference."""
+    from tscode_b200.numba_functions import _score_embed_poses
+    from tscode_b200.optimization_methods import constraint_scores, fitness_check
+    from tscode_b200.synth import gen_ensemble
+    g = json.load(open(os.path.join(GOLDEN, "constraint_scores.json")))
+    S = gen_ensemble(g["seed"], g["N"], g["M"], g["n_clusters"], sigma_noise=g["sigma_noise"])
+    cons, dists = np.array(g["cons"]), np.array(g["dists"])
+    sc = _score_embed_poses(S, cons, dists)
+    assert sc.dtype == np.float32 and np.array_equal(sc, np.array(g["scores"], dtype=np.float32))
+    targets = [[None if (p + k) % 5 == 0 else float(dists[p, k]) for k in range(3)] for p in range(g["N"])]
+    _, err = constraint_scores(S, cons, targets)
+    assert [bool(e < g["fitness_threshold"]) for e in err] == g["fitness"]
+    assert fitness_check(S[3], [tuple(c) for c in cons[3]], targets[3], g["fitness_threshold"]) == g["fitness"][3]

@@ -180,3 +180,14 @@ def test_oracle_cyclical_embed_params_vs_live_reference():
                                            g["sys_angles"])
     assert R.shape == g["R"].shape == (7 * 27, 3, 3, 3)
     assert np.abs(R - g["R"]).max() < 1e-13 and np.abs(t - g["t"]).max() < 1e-12
+
+
+def test_oracle_constraint_scores_vs_live_reference():
+    g = json.load(open(os.path.join(GOLDEN, "constraint_scores.json")))
+    S = gen_ensemble(g["seed"], g["N"], g["M"], g["n_clusters"], sigma_noise=g["sigma_noise"])
+    cons, dists = np.array(g["cons"]), np.array(g["dists"])
+    sc = oracle_np.score_embed_poses(S, cons, dists)
+    assert np.array_equal(sc, np.array(g["scores"], dtype=np.float32))
+    for p in range(g["N"]):
+        tg = [None if (p + k) % 5 == 0 else float(dists[p, k]) for k in range(3)]
+        assert bool(oracle_np.fitness_check(S[p], [tuple(c) for c in cons[p]], tg, g["fitness_threshold"])) == g["fitness"][p]

@@ -51,6 +51,7 @@ SIGNATURES = {
     "tsc_tfd_scan": (C.c_int, [_vp, _i64, _i32, _f64, _vp, _vp, _vp]),
     "tsc_moi_moments": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
     "tsc_moi_scan": (C.c_int, [_vp, _i64, _f64, _vp, _vp, _vp]),
+    "tsc_constraint_scores": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "tsc_embed_clash": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _f64, _f64, _i64, _vp, _vp, _vp]),
     "tsc_clash_structs": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _f64, _f64, _f64, _i64, _vp, _vp, _vp]),
     "tsc_rotcorr_pairs": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f64,

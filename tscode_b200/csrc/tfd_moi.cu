@@ -178,6 +178,36 @@ __global__ void __launch_bounds__(256) moi_scan_kernel(const double* __restrict_
     if (near_count && near) atomicAdd(near_count, near);
 }
 
+// ---- constraint scores of embedded poses -----------------------------------------------------------
+// _score_embed_poses (numba_functions.py:273-288): scores[j] = sum_i | |x_i1 - x_i2| - d_i |, accumulated in
+// float32;  fitness_check (optimization_methods.py:544-557): error = sum_i ( |x_a - x_b| - target_i ) over the
+// constraints whose target is not None (signed, float64), verdict error < threshold.  One thread per structure;
+// the norm is evaluated with separately rounded multiplies and adds like numba's norm_of (algebra.py:90-96).
+__global__ void __launch_bounds__(256) constraint_score_kernel(const double* __restrict__ S, int64_t P, int A,
+                                                               const int32_t* __restrict__ cons, const double* __restrict__ targets,
+                                                               int K, int per_pose, float* __restrict__ score_abs32,
+                                                               double* __restrict__ error_signed) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+        const double* X = S + p * (int64_t)A * 3;
+        const int32_t* c = cons + (per_pose ? p * K * 2 : 0);
+        const double* tg = targets + (per_pose ? p * K : 0);
+        float s32 = 0.0f;
+        double err = 0.0;
+        for (int k = 0; k < K; k++) {
+            const double t = tg[k];
+            const double* a = X + 3 * c[2 * k], *b = X + 3 * c[2 * k + 1];
+            const double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+            const double d = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+            if (t == t) {                       // NaN marks a constraint without target (None)
+                s32 = (float)((double)s32 + fabs(d - t));          // float32 accumulator += float64 term
+                err += d - t;
+            }
+        }
+        if (score_abs32) score_abs32[p] = s32;
+        if (error_signed) error_signed[p] = err;
+    }
+}
+
 }  // namespace tsc
 
 extern "C" int tsc_tfd_fingerprints(const double* S, int64_t N, int32_t A, const int32_t* quads, int32_t Q, float* tf,
@@ -218,6 +248,20 @@ extern "C" int tsc_moi_scan(const double* moments, int64_t N, double max_deviati
     if (blocks > 148 * 16) blocks = 148 * 16;
     tsc::moi_scan_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         moments, N, max_deviation, first_hit, reinterpret_cast<unsigned long long*>(near_count));
+    TSC_CHECK_LAUNCH();
+    return 0;
+}
+
+// scores of P structures S (P, A, 3) against K distance constraints: cons (K, 2) int32 atom pairs and targets (K)
+// shared by all structures (per_pose = 0) or (P, K, 2) / (P, K) per structure (per_pose = 1); a NaN target skips the
+// constraint.  score_abs32 (P) float32 = _score_embed_poses; error_signed (P) float64 = fitness_check's error.
+extern "C" int tsc_constraint_scores(const double* S, int64_t P, int32_t A, const int32_t* cons, const double* targets,
+                                     int32_t K, int32_t per_pose, float* score_abs32, double* error_signed, void* stream) {
+    if (P <= 0) return 0;
+    int64_t blocks = (P + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    tsc::constraint_score_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(S, P, A, cons, targets, K, per_pose,
+                                                                                   score_abs32, error_signed);
     TSC_CHECK_LAUNCH();
     return 0;
 }

@@ -25,9 +25,11 @@ _PATCHES = {
     "tscode.numba_functions": {
         "compenetration_check": _nf.compenetration_check,
         "prune_conformers_tfd": _nf.prune_conformers_tfd,
+        "_score_embed_poses": _nf._score_embed_poses,
     },
     "tscode.optimization_methods": {
         "prune_by_moment_of_inertia": _om.prune_by_moment_of_inertia,
+        "fitness_check": _om.fitness_check,
     },
     "tscode.embeds": {
         "get_embed": _nf.get_embed,

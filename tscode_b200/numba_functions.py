@@ -204,3 +204,11 @@ def torsion_fingerprints(structures, quadruplets):
         check(lib().tsc_tfd_fingerprints(ptr(d_S), N, structures.shape[1], ptr(d_quads), Q, ptr(tf), stream_ptr()),
               "tsc_tfd_fingerprints")
     return tf[:, :Q].cpu().numpy()
+
+
+def _score_embed_poses(structures, constrained_indices, constrained_distances):
+    """Drop-in for tscode.numba_functions._score_embed_poses (:273-288): float32 score per structure = sum of
+    |distance - desired distance| over that structure's constrained pairs."""
+    from .optimization_methods import constraint_scores
+    score, _ = constraint_scores(structures, np.asarray(constrained_indices), np.asarray(constrained_distances, dtype=np.float64))
+    return score

@@ -72,3 +72,36 @@ def prune_by_moment_of_inertia(structures, atomnos, max_deviation=1e-2, *, masse
             mask[i] = False
     prune_by_moment_of_inertia.last_near_threshold = int(near.item())
     return structures[mask], mask
+
+
+def constraint_scores(structures, constraints, targets):
+    """Batched distance-constraint scores: (score_abs float32 (P,), error_signed float64 (P,)) numpy.
+    constraints: (K, 2) shared by all structures or (P, K, 2) per structure; targets: (K,) or (P, K), None / NaN for a
+    constraint without target."""
+    torch = require_cuda()
+    S = np.ascontiguousarray(structures, dtype=np.float64)
+    P, A = S.shape[0], S.shape[1]
+    cons = np.ascontiguousarray(np.asarray(constraints, dtype=np.int32))
+    tg = np.array([[np.nan if v is None else v for v in row] for row in np.atleast_2d(np.asarray(targets, dtype=object))],
+                  dtype=np.float64)
+    per_pose = cons.ndim == 3
+    K = cons.shape[-2] if cons.size else 0
+    tg = np.ascontiguousarray(tg.reshape(P, K) if per_pose else tg.reshape(K))
+    dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+    d_S, d_c, d_t = torch.from_numpy(S).to(dev), torch.from_numpy(cons.reshape(-1)).to(dev), torch.from_numpy(tg.reshape(-1)).to(dev)
+    score = torch.zeros(max(P, 1), dtype=torch.float32, device=dev)
+    err = torch.zeros(max(P, 1), dtype=torch.float64, device=dev)
+    if P:
+        check(lib().tsc_constraint_scores(ptr(d_S), P, A, ptr(d_c), ptr(d_t), K, 1 if per_pose else 0, ptr(score), ptr(err),
+                                          stream_ptr()), "tsc_constraint_scores")
+    return score[:P].cpu().numpy(), err[:P].cpu().numpy()
+
+
+def fitness_check(coords, constraints, targets, threshold) -> bool:
+    """Drop-in for tscode.optimization_methods.fitness_check (:544-557): True if the signed sum of
+    (distance - target) over the constraints with a target is below `threshold`.  (One launch per call: use
+    constraint_scores for a whole ensemble, as Embedder.fitness_refining's loop should, embedder.py:1283-1290.)"""
+    if len(constraints) == 0:
+        return bool(0 < threshold)
+    _, err = constraint_scores(np.asarray(coords, dtype=np.float64)[None], np.asarray(constraints), list(targets))
+    return bool(err[0] < threshold)
