@@ -142,6 +142,7 @@ class RmsdPruner:
                 self.PB = torch.empty(nbytes, dtype=torch.uint8, device=dev)
                 self.PR = torch.empty(nbytes, dtype=torch.uint8, device=dev)
                 self.sG = torch.empty(n_g, dtype=torch.float64, device=dev)
+                self.G_side = torch.empty(n_g, dtype=torch.float64, device=dev)
                 self.CT = torch.empty(max(L.tsc_tf32_ct_floats(N), 1), dtype=torch.float32, device=dev)
             if self.variant in (2, 3):
                 L = lib()
@@ -169,6 +170,9 @@ class RmsdPruner:
             self.pair_list = torch.zeros((self.pair_stride, 2), dtype=torch.int32, device=dev)
             self.pair_all = (torch.zeros((self.world * self.pair_stride, 2), dtype=torch.int32, device=dev)
                              if self.world > 1 else self.pair_list)
+            self.pair_stride_small = min(self.pair_stride, 4 * N // self.world + 2048 + 1)
+            self.pair_all_small = (torch.zeros((self.world * self.pair_stride_small, 2), dtype=torch.int32, device=dev)
+                                   if self.world > 1 else self.pair_list)
             # candidate list the tcgen05 screens append to (local row, j); verify works from it
             self.cand_stride = (int(cand_cap) if cand_cap is not None else 64 * N // self.world + 8192) + 1
             self.cand_list = torch.zeros((self.cand_stride, 2), dtype=torch.int32, device=dev)
@@ -179,6 +183,8 @@ class RmsdPruner:
             if self.world > 1:
                 self._init_shards()
         self._cands = []
+        self._packed_event = None
+        self._fused_enqueued = None
         self._pairs_ready = False
         self._rounds_fused = None
         self.ladder_used = None
@@ -220,9 +226,21 @@ class RmsdPruner:
         if self.N == 0 or self.M == 0:
             return
         L = lib()
-        with self.torch.cuda.device(self.device):
-            check(L.tsc_pack(ptr(self.S), self.N, self.A, ptr(self.heavy_idx), self.M, ptr(self.packed),
-                             ptr(self.G), stream_ptr()), "tsc_pack")
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            if self.variant == 4:
+                # the FP64 tiled-SoA image is only read by verify: it is written on a side stream while the main
+                # stream goes on to the FP16 images and the screen (verify waits for the event)
+                main, side = torch.cuda.current_stream(), _copy_stream(str(self.device))
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    check(L.tsc_pack(ptr(self.S), self.N, self.A, ptr(self.heavy_idx), self.M, ptr(self.packed),
+                                     ptr(self.G_side), stream_ptr()), "tsc_pack")      # (G itself comes from pack_f16)
+                    self._packed_event = torch.cuda.Event()
+                    self._packed_event.record(side)
+            else:
+                check(L.tsc_pack(ptr(self.S), self.N, self.A, ptr(self.heavy_idx), self.M, ptr(self.packed),
+                                 ptr(self.G), stream_ptr()), "tsc_pack")
             if self.variant == 4:
                 check(L.tsc_pack_f16(ptr(self.S), self.N, self.A, ptr(self.heavy_idx), self.M, ptr(self.PA),
                                      ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG), ptr(self.CT), stream_ptr()),
@@ -268,6 +286,9 @@ class RmsdPruner:
         pairs of the owned rows are also available as an (i, j) list (pair_list)."""
         L = lib()
         with self.torch.cuda.device(self.device):
+            if self._packed_event is not None:           # FP64 image written on the side stream (pack())
+                self.torch.cuda.current_stream().wait_event(self._packed_event)
+                self._packed_event = None
             self.pair_list[0].zero_()
             if self.n_rb and self.M:
                 check(L.tsc_rmsd_verify(ptr(self.packed), self.N, self.M, ptr(self.row_blocks), self.n_rb, self.thr,
@@ -303,25 +324,44 @@ class RmsdPruner:
                 return mask
         return self._eliminate_bitrows()
 
-    def _enqueue_fused(self):
+    def _enqueue_fused(self, tier="small"):
+        """All-gather of the confirmed-pair lists (several ranks) + the fused ladder kernel, nothing read back.
+        Two tiers: the blocks have room for 32 N / world pairs, but a typical ensemble has a few per structure, so
+        first only a short prefix of every block (4 N / world + 2048 pairs) is gathered; if some rank's count does
+        not fit the prefix the kernel reports status 1 and the full blocks are gathered (same decision on every
+        rank: all see the same headers)."""
         torch = self.torch
         L = lib()
+        stride = self.pair_stride_small if (tier == "small" and self.world > 1) else self.pair_stride
         with torch.cuda.device(self.device):
             if self.world > 1:
                 import torch.distributed as dist
-                dist.all_gather_into_tensor(self.pair_all, self.pair_list, group=self.group)
-            check(L.tsc_elim_fused(ptr(self.pair_all), self.world, self.pair_stride, self.N, 20, ptr(self.fused_ws),
+                if stride == self.pair_stride:
+                    lists = self.pair_all
+                    dist.all_gather_into_tensor(lists, self.pair_list, group=self.group)
+                else:
+                    lists = self.pair_all_small
+                    dist.all_gather_into_tensor(lists, self.pair_list[:stride], group=self.group)
+            else:
+                lists = self.pair_list
+            check(L.tsc_elim_fused(ptr(lists), self.world, stride, self.N, 20, ptr(self.fused_ws),
                                    ptr(self.fused_out), stream_ptr()), "tsc_elim_fused")
-        self._fused_enqueued = True
+        self._fused_enqueued = tier if self.world > 1 else "full"
 
     def _eliminate_fused(self):
         torch = self.torch
         N = self.N
-        if not getattr(self, "_fused_enqueued", False):
+        if not self._fused_enqueued:
             self._enqueue_fused()
-        self._fused_enqueued = False
-        with torch.cuda.device(self.device):
-            info = self.fused_out[self._info_off:self._info_off + 128].view(torch.int32).tolist()   # sync
+        while True:
+            tier = self._fused_enqueued
+            self._fused_enqueued = None
+            with torch.cuda.device(self.device):
+                info = self.fused_out[self._info_off:self._info_off + 128].view(torch.int32).tolist()   # sync
+            if info[0] == 1 and tier == "small":
+                self._enqueue_fused("full")               # a list did not fit the short prefix
+                continue
+            break
         if info[0] == 1:
             return None                                   # pair list overflow -> bit rows (same on every rank)
         if info[0] != 0:
@@ -389,7 +429,7 @@ class RmsdPruner:
 
     def finish(self):
         """Mask of a prune started with run_async() (or the whole prune if it was not)."""
-        if getattr(self, "_fused_enqueued", False):
+        if self._fused_enqueued:
             return self.eliminate()
         return self.run()
 
