@@ -170,7 +170,7 @@ class RmsdPruner:
             self.pair_list = torch.zeros((self.pair_stride, 2), dtype=torch.int32, device=dev)
             self.pair_all = (torch.zeros((self.world * self.pair_stride, 2), dtype=torch.int32, device=dev)
                              if self.world > 1 else self.pair_list)
-            self.pair_stride_small = min(self.pair_stride, 4 * N // self.world + 2048 + 1)
+            self.pair_stride_small = min(self.pair_stride, 8 * N // self.world + 2048 + 1)
             self.pair_all_small = (torch.zeros((self.world * self.pair_stride_small, 2), dtype=torch.int32, device=dev)
                                    if self.world > 1 else self.pair_list)
             # candidate list the tcgen05 screens append to (local row, j); verify works from it
@@ -327,7 +327,7 @@ class RmsdPruner:
     def _enqueue_fused(self, tier="small"):
         """All-gather of the confirmed-pair lists (several ranks) + the fused ladder kernel, nothing read back.
         Two tiers: the blocks have room for 32 N / world pairs, but a typical ensemble has a few per structure, so
-        first only a short prefix of every block (4 N / world + 2048 pairs) is gathered; if some rank's count does
+        first only a short prefix of every block (8 N / world + 2048 pairs) is gathered; if some rank's count does
         not fit the prefix the kernel reports status 1 and the full blocks are gathered (same decision on every
         rank: all see the same headers)."""
         torch = self.torch
