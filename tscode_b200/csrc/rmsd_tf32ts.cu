@@ -1,4 +1,6 @@
-// rmsd_tf32ts.cu — tcgen05 pre-screen with the stationary operand in TENSOR MEMORY (variant 2, default).
+// rmsd_tf32ts.cu — tcgen05 pre-screen with the stationary operand in TENSOR MEMORY: rmsd_ts_kernel.
+// FP16 operands (kind::f16, tsc_rmsd_sim_f16ts) are the default screen of prune_conformers_rmsd; TF32 operands
+// (kind::tf32, tsc_rmsd_sim_tf32ts) are the same kernel with K = 8 per MMA.
 //
 // Same mathematics and same output contract as rmsd_tf32.cu (read its header first).  What changed,
 // and why: ncu on rmsd_tf32_kernel showed the tensor pipe "busy" 68 % of the time with only 26 % of
@@ -9,17 +11,19 @@
 // there (tcgen05.mma [d], [a_tmem], b_desc): shared-memory operand traffic drops to the 1.5 KB B
 // block per MMA.
 //
-// TMEM map (512 columns x 128 lanes x 32 bit):
-//   [0, 216)        A: component a, atom k  at column a*8*KT + k      (KT = min(Mp/8, 9) K blocks)
+// TMEM map (512 columns x 128 lanes x 32 bit), default configuration:
+//   [0, 216)        A: component a, K block kb at columns a*8*KT + 8*kb .. +8  (KT = min(K blocks, 9); a K block is
+//                   8 TF32 or 16 FP16 atoms = 32 bytes per row)
 //   [216, 504)      two accumulator buffers of 144 columns (D_x | D_y | D_z, each 3*16 wide)
-// With M > 72 heavy atoms the K blocks beyond the ninth do not fit next to two accumulator buffers;
-// their A blocks stay in shared memory (bulk-TMA of the tail of the rmsd_tf32.cu panel image) and
-// are multiplied with the shared-memory form of the instruction.
+// K blocks beyond the ninth (M > 72 heavy atoms with TF32, > 144 with FP16) do not fit next to two accumulator
+// buffers; their A blocks stay in shared memory (bulk-TMA of the tail of the panel image) and are multiplied with
+// the shared-memory form of the instruction.
 //
-// Roles (one persistent CTA per SM, 2 + 8*CH warps): warp 0 lane 0 producer (A tail + ring of B
-// tiles), warp 1 TMEM allocation + MMA issue, the rest epilogue in 2*CH groups of 4 warps: at the
-// start of a work item they load their rows of the A panel (global -> registers -> tcgen05.st),
-// then group g takes accumulator buffer g / CH and column part g % CH of its tiles.
+// Roles (one persistent CTA per SM): warp 0 producer (A tail + ring of B tiles), warp 1 TMEM allocation + MMA
+// issue, the rest epilogue in groups of 4 warps: at the start of a work item they load their rows of the A panel
+// (global -> registers -> tcgen05.st), then every group takes the tiles of its accumulator buffer.  Template
+// parameters select measured alternatives (see launch_ts): column-split groups, three buffers with the panel in
+// shared memory, two MMA warps.
 #include "tf32_common.cuh"
 
 namespace tsc {
