@@ -20,3 +20,4 @@ $CMD > $OUT/plain2.json 2> $OUT/plain2.err && \
 ncu --set full --clock-control none --import-source on -k regex:rmsd_ts_kernel -s 3 -c 1 -o $OUT/prof_screen $CMD > $OUT/ncu_full.log 2>&1
 echo "full capture rc=$?" | tee -a $OUT/rc.txt
 ls -la $OUT
+echo "== probes" ; timeout 120 python tools/umma_probe.py > $OUT/umma_probe.log 2>&1 ; timeout 120 python tools/trace_probe.py > $OUT/trace_probe.log 2>&1 ; timeout 120 python tools/clash_run.py > $OUT/clash_run.log 2>&1; tail -3 $OUT/clash_run.log
