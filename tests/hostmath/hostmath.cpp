@@ -50,4 +50,55 @@ void hm_rmsd_and_max(const double* p, const double* q, int M, double* rmsd, doub
     *rmsd = sqrt(ss / M);
     *maxdev = sqrt(mx);
 }
+
+// ---- FP32 second stage of the tcgen05 pre-screens (quartic32_*) ----
+static float frob32(const float* S) {                 // the device's FFMA chain
+    float f = 0.f;
+    for (int q = 0; q < 9; q++) f = fmaf(S[q], S[q], f);
+    return f;
+}
+
+// For n samples (9 floats each) and test points lam: forward errors of the FP32 values of P, P', P'' against
+// long-double evaluation of the same polynomial, scaled by rho^4, rho^3, rho^2 (rho = max(lam, 2 ||S||_F)).
+// out[3*k + 0..2]
+void hm_q32_errors(const float* S, const float* lam, int n, double* out) {
+    for (int k = 0; k < n; k++) {
+        const float* s = S + 9 * k;
+        float p0, p1, p2;
+        tsc::quartic32_values<tsc::OpsF32>(s, frob32(s), lam[k], p0, p1, p2);
+        long double Sd[9], f = 0;
+        for (int q = 0; q < 9; q++) { Sd[q] = s[q]; f += Sd[q] * Sd[q]; }
+        long double K[4][4];
+        K[0][0] = Sd[0] + Sd[4] + Sd[8]; K[0][1] = Sd[5] - Sd[7]; K[0][2] = Sd[6] - Sd[2]; K[0][3] = Sd[1] - Sd[3];
+        K[1][1] = Sd[0] - Sd[4] - Sd[8]; K[1][2] = Sd[1] + Sd[3]; K[1][3] = Sd[6] + Sd[2];
+        K[2][2] = -Sd[0] + Sd[4] - Sd[8]; K[2][3] = Sd[5] + Sd[7]; K[3][3] = -Sd[0] - Sd[4] + Sd[8];
+        for (int a = 0; a < 4; a++) for (int b = 0; b < a; b++) K[a][b] = K[b][a];
+        // determinant by cofactor expansion (exact enough in long double)
+        auto det3 = [&](int r0, int r1, int r2, int c0, int c1, int c2) {
+            return K[r0][c0] * (K[r1][c1] * K[r2][c2] - K[r1][c2] * K[r2][c1])
+                 - K[r0][c1] * (K[r1][c0] * K[r2][c2] - K[r1][c2] * K[r2][c0])
+                 + K[r0][c2] * (K[r1][c0] * K[r2][c1] - K[r1][c1] * K[r2][c0]);
+        };
+        long double c0 = K[0][0] * det3(1, 2, 3, 1, 2, 3) - K[0][1] * det3(1, 2, 3, 0, 2, 3)
+                       + K[0][2] * det3(1, 2, 3, 0, 1, 3) - K[0][3] * det3(1, 2, 3, 0, 1, 2);
+        long double dS = Sd[0] * (Sd[4] * Sd[8] - Sd[5] * Sd[7]) - Sd[1] * (Sd[3] * Sd[8] - Sd[5] * Sd[6])
+                       + Sd[2] * (Sd[3] * Sd[7] - Sd[4] * Sd[6]);
+        long double c1 = -8 * dS, c2 = -2 * f, l = lam[k];
+        long double P0 = ((l * l + c2) * l + c1) * l + c0, P1 = (4 * l * l + 2 * c2) * l + c1, P2 = 12 * l * l + 2 * c2;
+        long double rho = fmaxl(fabsl(l), 2 * sqrtl(f));
+        if (rho == 0) rho = 1;
+        out[3 * k + 0] = (double)(fabsl(P0 - p0) / (rho * rho * rho * rho));
+        out[3 * k + 1] = (double)(fabsl(P1 - p1) / (rho * rho * rho));
+        out[3 * k + 2] = (double)(fabsl(P2 - p2) / (rho * rho));
+    }
+}
+
+// decision of the FP32 stage and, beside it, lambda_max of the same (float) covariance in FP64
+int hm_q32_excluded(const float* S, float lam, double* lam_max) {
+    double Sd[9];
+    for (int q = 0; q < 9; q++) Sd[q] = S[q];
+    double qv[4], gap;
+    *lam_max = tsc::key_top_eigen(tsc::key_matrix(Sd), qv, &gap);
+    return tsc::quartic32_excluded(S, frob32(S), lam) ? 1 : 0;
+}
 }

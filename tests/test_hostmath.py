@@ -11,6 +11,7 @@ from tscode_b200.synth import gen_ensemble
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_fp = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 
 
 @pytest.fixture(scope="module")
@@ -19,11 +20,13 @@ def hm():
     so = os.path.join(HERE, "hostmath", "libhostmath.so")
     hdr = os.path.join(HERE, "..", "tscode_b200", "csrc", "tsc_math.cuh")
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-x", "c++", src, "-o", so])
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", src, "-o", so])
     L = C.CDLL(so)
     L.hm_screen.argtypes = [_dp, _dp, C.c_int, C.c_double]
     L.hm_screen_nomargin.argtypes = [_dp, _dp, C.c_int, C.c_double]
     L.hm_rmsd_and_max.argtypes = [_dp, _dp, C.c_int] + [C.POINTER(C.c_double)] * 4
+    L.hm_q32_errors.argtypes = [_fp, _fp, C.c_int, _dp]
+    L.hm_q32_excluded.argtypes = [_fp, C.c_float, C.POINTER(C.c_double)]
     return L
 
 
@@ -107,3 +110,75 @@ def test_screen_far_from_origin_never_loses_a_pair(hm):
                     sim += 1
                     lost += 1 - hm.hm_screen(T[i], T[j], 24, 0.5)
     assert sim > 100 and lost == 0, (sim, lost)
+
+
+def _q32_covariances(rng, kind, n):
+    if kind == 0:        # anything, 8 decades of magnitude
+        S = rng.normal(size=(n, 9)) * 10 ** rng.uniform(-3, 5, size=(n, 1))
+    elif kind == 1:      # elongated molecule, similar orientation: near-PSD anisotropic covariance
+        P = rng.normal(size=(n, 20, 3)) * np.array([6, 2, 1.0]); Q = P + rng.normal(size=(n, 20, 3)) * 0.3
+        S = np.einsum("nma,nmb->nab", P, Q).reshape(n, 9)
+    elif kind == 2:      # rank one
+        a = rng.normal(size=(n, 3)); b = rng.normal(size=(n, 3))
+        S = (a[:, :, None] * b[:, None, :]).reshape(n, 9) * 1e3
+    elif kind == 3:      # ensemble far from the origin: two roots of the quartic nearly coincide
+        P = rng.normal(size=(n, 10, 3)) + np.array([7e3, 0, 0]); Q = P + rng.normal(size=(n, 10, 3)) * 0.05
+        S = np.einsum("nma,nmb->nab", P, Q).reshape(n, 9)
+    else:                # many exact zeros
+        S = rng.normal(size=(n, 9)) * (rng.random((n, 9)) < 0.4) * 1e2
+    return np.ascontiguousarray(S, dtype=np.float32)
+
+
+def test_fp32_quartic_forward_errors_within_tolerances(hm):
+    """quartic32_values (FP32 second stage of the tcgen05 pre-screens, tsc_math.cuh): measured forward errors of
+    P, P', P'' against long-double evaluation stay well inside the tolerances quartic32_decide applies
+    (512 u rho^4, 72 u rho^3, 68 u rho^2)."""
+    rng = np.random.default_rng(0)
+    u = 2.0 ** -24
+    worst = np.zeros(3)
+    for trial in range(10):
+        n = 20000
+        S = _q32_covariances(rng, trial % 5, n)
+        s = np.sqrt((S.astype(np.float64) ** 2).sum(1))
+        lam = (s * 10 ** rng.uniform(-2, 1, size=n)).astype(np.float32)
+        out = np.zeros(3 * n)
+        hm.hm_q32_errors(S, lam, n, out)
+        o = out.reshape(n, 3)
+        o = o[np.isfinite(o).all(1)]
+        assert len(o) > 0.9 * n
+        worst = np.maximum(worst, o.max(axis=0))
+    assert worst[0] < 512 * u / 8 and worst[1] < 72 * u / 3 and worst[2] < 68 * u / 2, worst / u
+
+
+def test_fp32_quartic_never_excludes_a_pair_above_the_test_point(hm):
+    """Whenever the FP32 stage excludes, lambda_max (FP64 eigen-solve of the same covariance) is below the test
+    point; and it does exclude the anisotropic pairs Samuelson's bound cannot (tools/aniso_probe.py)."""
+    rng = np.random.default_rng(1)
+    n = 3000
+    base = rng.normal(size=(80, 3)) * np.array([6, 2, 1.0])
+    P = base + rng.normal(size=(n, 80, 3)); Q = base + rng.normal(size=(n, 80, 3))
+    S = np.ascontiguousarray(np.einsum("nma,nmb->nab", P, Q).reshape(n, 9), dtype=np.float32)
+    Gp, Gq = (P ** 2).sum((1, 2)), (Q ** 2).sum((1, 2))
+    lam_t = (0.5 * (Gp + Gq - 80 * 0.25) - 1.05e-3 * np.sqrt(3.0) * np.sqrt(Gp * Gq)).astype(np.float32)
+    lm = C.c_double()
+    excluded = samuelson = 0
+    for k in range(n):
+        e = hm.hm_q32_excluded(S[k], float(lam_t[k]), C.byref(lm))
+        assert not (e and lm.value > lam_t[k])
+        excluded += e
+        samuelson += bool(3.00004 * float((S[k].astype(np.float64) ** 2).sum()) <= float(lam_t[k]) ** 2)
+    assert excluded == n and samuelson == 0
+    # test points swept through lambda_max: the decision flips from "not excluded" to "excluded" within a relative
+    # band of 1e-3 above lambda_max, never below it
+    for k in range(0, n, 10):
+        hm.hm_q32_excluded(S[k], 1.0, C.byref(lm))
+        for rel in (-1e-2, -1e-4, -1e-6, 0.0, 1e-6):
+            assert hm.hm_q32_excluded(S[k], float(np.float32(lm.value * (1 + rel))) , C.byref(lm)) == 0 or rel > 0
+        assert hm.hm_q32_excluded(S[k], float(np.float32(lm.value * (1 + 1e-3))), C.byref(lm)) == 1
+    # NaN / inf / zero inputs are never excluded
+    bad = np.zeros(9, np.float32)
+    assert hm.hm_q32_excluded(bad, 0.0, C.byref(lm)) == 0
+    bad[0] = np.inf
+    assert hm.hm_q32_excluded(bad, 10.0, C.byref(lm)) == 0
+    bad[0] = np.nan
+    assert hm.hm_q32_excluded(bad, 10.0, C.byref(lm)) == 0

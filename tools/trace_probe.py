@@ -25,6 +25,7 @@ print("mma wait b_full", (t[32:96, 1] - t[32:96, 0]).mean(), "wait t_empty", (t[
       "issue", (t[32:96, 3] - t[32:96, 2]).mean())
 print("epi: wait t_full", (t[32:96, 5] - t[32:96, 4]).mean(), "work", (t[32:96, 6] - t[32:96, 5]).mean())
 print("issued -> t_full seen", (t[32:96, 5] - t[32:96, 3]).mean())
+print("SM clock from clock64 / globaltimer over tiles 8..95: %.1f MHz" % (1e3 * (t[95, 3] - t[8, 3]) / max(t[95, 7] - t[8, 7], 1)))
 pr.verify(); m = pr.eliminate(); torch.cuda.synchronize()
 info = pr.fused_out[pr._info_off:pr._info_off + 256].view(torch.int32).cpu().numpy()
 print("fused ladder status", info[:4], "rounds", info[8:8 + info[1]])

@@ -28,6 +28,12 @@
 
 namespace tsc {
 
+__device__ __forceinline__ long long ts_globaltimer_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // Two TMEM budgets (template parameter NACC):
 //   NACC = 2: up to 9 K blocks of the A panel in TMEM (216 columns) + 2 accumulator buffers (288);
 //   NACC = 3: the whole A panel stays in shared memory (SS-form MMAs) and TMEM holds 3 accumulator buffers
@@ -35,6 +41,7 @@ namespace tsc {
 //             With FP16 operands an MMA reads 4 KB (A) + 1.5 KB (B) of shared memory = 43 cycles at 128 B/clk,
 //             about the ~40 cycles the tensor pipe needs for a 128x48 instruction anyway.
 constexpr int TS_KT_MAX = 9;                   // K blocks held in TMEM (NACC = 2)
+constexpr int TS_KT_HYB = 3;                   // K blocks held in TMEM next to THREE accumulator buffers (72 + 432 columns)
 constexpr int TS_MAX_NACC = 3;
 constexpr int TS_MAX_BSTAGES = 12;
 constexpr int TS_DEFAULT_CFG = 2;
@@ -75,11 +82,12 @@ constexpr int TS_TRACE_TILES = 96;    // tiles of the first item that are stampe
 // turn), so all epilogue warps work on the tile that has just finished and the buffer is handed back after half
 // the per-warp work: the serial chain MMA -> completion -> epilogue-until-release -> MMA that bounds the tile
 // rate with two buffers gets shorter, at unchanged total epilogue work.
-template <int CH, int STEP, bool F16, int NACC, int NMMA = 1, bool SPLIT = false>
+template <int CH, int STEP, bool F16, int NACC, int NMMA = 1, bool SPLIT = false, int KTM = (NACC == 2 ? TS_KT_MAX : 0), int EPI = 4>
 __global__ void __launch_bounds__((1 + NMMA + 4 * (SPLIT ? CH : NACC * CH)) * 32, 1) rmsd_ts_kernel(const TsParams p) {
     constexpr int NG = SPLIT ? CH : NACC * CH;
     constexpr int TS_NACC = NACC;
-    constexpr int KT_MAX = NACC == 2 ? TS_KT_MAX : 0;
+    constexpr int KT_MAX = KTM;
+    static_assert(3 * 8 * KTM + NACC * TF_ACC_COLS <= TF_TMEM_COLS, "TMEM budget");
     constexpr int TS_ACC0 = 3 * 8 * KT_MAX;        // first accumulator column
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int nkc = p.nkc;                                     // 16-byte K chunks
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__((1 + NMMA + 4 * (SPLIT ? CH : NACC * CH)) * 32
                     umma_commit(&t_full[acc]);
                     }
                     __syncwarp();
-                    if (tr) p.trace[t * 8 + 3] = clock64();
+                    if (tr) { p.trace[t * 8 + 3] = clock64(); p.trace[t * 8 + 7] = ts_globaltimer_ns(); }
                     bs += NMMA;
                     if (bs >= p.nb_stages) { bs -= p.nb_stages; bph ^= 1u; }
                     acc += NMMA;
@@ -302,7 +310,10 @@ __global__ void __launch_bounds__((1 + NMMA + 4 * (SPLIT ? CH : NACC * CH)) * 32
                     tcgen05_fence_after();
                     const uint32_t d0 = tmem_base + lane_addr + TS_ACC0 + (uint32_t)buf * TF_ACC_COLS;
                     uint32_t bits;
-                    if (STEP == 4)
+                    if (EPI == 5)
+                        bits = tf32_epilogue_tile_v5<TF_J / CH>(d0, gvf, row, i, j0, p.N, lane, &t_empty[buf],
+                                                                part * (TF_J / CH));
+                    else if (STEP == 4)
                         bits = tf32_epilogue_tile_v4<TF_J / CH>(d0, gvf, row, p.G, p.sG, i, j0, p.N, lane, &t_empty[buf],
                                                                 part * (TF_J / CH));
                     else
@@ -401,6 +412,10 @@ static int launch_ts(const void* PA, const void* PB, const void* PR, const doubl
     // TMEM load round; -2 = A in TMEM, 2 groups x 4; -3 = A in TMEM, 4 groups (two column halves per tile) x 4;
     // -4 = A in shared memory, 3 accumulator buffers, 3 groups x 4;  -5 = as -2 with two MMA warps;
     // -7 = A in TMEM, 2 groups each taking one column half of EVERY tile (SPLIT);
+    // -8 = hybrid: the first 3 K blocks of A in TMEM (72 columns), the rest in shared memory, THREE accumulator
+    //      buffers and three epilogue groups;  -9 = as -8 with three MMA warps, one per buffer
+    //      (a warp must see every phase of the barriers it waits on: two warps on three buffers alias phases and hang);
+    // -10 = as -8 with the two-stage FP32 epilogue (tf32_epilogue_tile_v5);  -11 = as -2 with that epilogue;
     // (measured on C3, FP16 operands: -2 2.72 ms, -3 3.08, -4 2.78, -5 2.88, -7 3.60 — an epilogue warp spends
     // ~600 cycles per tile whatever the number of columns it handles, so fewer columns per warp-tile lose;
     // reading the whole tile into 144
@@ -408,7 +423,7 @@ static int launch_ts(const void* PA, const void* PB, const void* PR, const doubl
     // default = TS_DEFAULT_CFG
     const int cfg = grid_ctas < 0 ? -grid_ctas : TS_DEFAULT_CFG;
     if (grid_ctas < 0) grid_ctas = 0;
-    const int kt_max = cfg == 4 ? 0 : TS_KT_MAX;
+    const int kt_max = cfg == 4 ? 0 : (cfg == 8 || cfg == 9 || cfg == 10) ? TS_KT_HYB : TS_KT_MAX;
     const int nkb = p.nkc / 2, KT = nkb < kt_max ? nkb : kt_max;
     const size_t a_bytes = (size_t)3 * (p.nkc - 2 * KT) * TF_ROWS * 16, b_bytes = (size_t)p.nkc * TF_N * 16;
     const size_t q_bytes = (size_t)16 * TS_Q * sizeof(int2);            // candidate queues of up to 16 epilogue warps
@@ -420,8 +435,12 @@ static int launch_ts(const void* PA, const void* PB, const void* PR, const doubl
     const size_t smem = a_bytes + nb * b_bytes + 512 + q_bytes;
     auto kern = cfg == 1 ? rmsd_ts_kernel<1, 8, F16, 2> : cfg == 2 ? rmsd_ts_kernel<1, 4, F16, 2>
               : cfg == 3 ? rmsd_ts_kernel<2, 4, F16, 2> : cfg == 4 ? rmsd_ts_kernel<1, 4, F16, 3>
-              : cfg == 5 ? rmsd_ts_kernel<1, 4, F16, 2, 2> : rmsd_ts_kernel<2, 4, F16, 2, 1, true>;
-    const int threads = cfg <= 2 ? 320 : cfg == 3 ? 576 : cfg == 4 ? 448 : cfg == 5 ? 352 : 320;
+              : cfg == 5 ? rmsd_ts_kernel<1, 4, F16, 2, 2> : cfg == 8 ? rmsd_ts_kernel<1, 4, F16, 3, 1, false, TS_KT_HYB>
+              : cfg == 9 ? rmsd_ts_kernel<1, 4, F16, 3, 3, false, TS_KT_HYB>
+              : cfg == 10 ? rmsd_ts_kernel<1, 4, F16, 3, 1, false, TS_KT_HYB, 5>
+              : cfg == 11 ? rmsd_ts_kernel<1, 4, F16, 2, 1, false, TS_KT_MAX, 5> : rmsd_ts_kernel<2, 4, F16, 2, 1, true>;
+    const int threads = cfg <= 2 || cfg == 11 ? 320 : cfg == 3 ? 576 : cfg == 4 || cfg == 8 || cfg == 10 ? 448
+                      : cfg == 5 ? 352 : cfg == 9 ? 512 : 320;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;

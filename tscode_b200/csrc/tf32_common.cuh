@@ -363,4 +363,117 @@ __device__ __forceinline__ uint32_t tf32_epilogue_tile_v4(uint32_t d0, float gvf
     return bits & valid;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Two-stage FP32 epilogue (default of the TMEM-operand kernel since round 1 / r04): no FP64, no second TMEM pass.
+//   stage 1  Samuelson's bound, as in tf32_epilogue_tile_v4, taken per group of 4 columns while the group's 36
+//            accumulators are in registers;
+//   stage 2  only for a column pair in which some lane is still undecided (one warp vote): the FP32 sign test of
+//            the key-matrix quartic (tsc_math.cuh: quartic32_values / quartic32_decide, rigorous forward error
+//            bounds) on the same registers, two columns per instruction (fma/mul/add.f32x2);
+//   the rest is a candidate: the verify kernel decides it exactly.
+// Why: (a) the FP64 test of v4 ran behind a second TMEM read and two global loads, whole-warp, for one or two
+// undecided lanes — a clock64 trace showed tiles with an undecided pair holding their epilogue group for 3000-5000
+// cycles (normal: ~900) and the MMA warp stalling on the third buffer behind them; on C3 practically every pair
+// Samuelson cannot exclude is a true candidate anyway, so the FP64 test only confirmed what verify re-derives;
+// (b) Samuelson's bound needs a near-isotropic covariance: for elongated or planar molecules it excludes nothing and
+// v4 ran the FP64 test for every pair (3x slower screen, tools/aniso_probe.py).  The FP32 quartic excludes those
+// pairs at ~45 instructions per pair.
+// The accumulator buffer is released as soon as the last group is in registers.
+// ------------------------------------------------------------------------------------------------------------------
+struct OpsF2 {                 // two FP32 lanes per 64-bit register (per-lane IEEE, same values as OpsF32)
+    typedef unsigned long long T;
+    static __device__ __forceinline__ T fma(T a, T b, T c) { T d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+    static __device__ __forceinline__ T mul(T a, T b) { T d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+    static __device__ __forceinline__ T add(T a, T b) { T d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+    static __device__ __forceinline__ T sub(T a, T b) { T d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+    static __device__ __forceinline__ T pack(uint32_t lo, uint32_t hi) { T d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi)); return d; }
+    static __device__ __forceinline__ T bc(float x) { return pack(__float_as_uint(x), __float_as_uint(x)); }
+    static __device__ __forceinline__ void unpack(T v, float& lo, float& hi) {
+        uint32_t a, b;
+        asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+        lo = __uint_as_float(a); hi = __uint_as_float(b);
+    }
+};
+
+template <int NCOL>
+__device__ __forceinline__ uint32_t tf32_epilogue_tile_v5(uint32_t d0, float gvf, const TfRow& row, int64_t i, int64_t j0,
+                                                          int64_t N, int lane, uint64_t* t_empty_bar, int C0) {
+    constexpr int NST = NCOL / 4;
+    uint32_t near = 0;                     // bit = column of the tile: pair not excluded
+    uint32_t rr[2][36];
+    tf32_ld_cols<4>(d0, C0 / 4, rr[0]);
+    tf32_ld_wait<4>(rr[0]);
+#pragma unroll
+    for (int st = 0; st < NST; st++) {
+        const uint32_t* r = rr[st & 1];
+        if (st + 1 < NST) {
+            tf32_ld_cols<4>(d0, C0 / 4 + st + 1, rr[(st + 1) & 1]);   // in flight while this group is screened
+        } else {                           // the last group is in registers: the buffer goes back to the MMA warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty_bar);
+        }
+        // ||S~||_F^2 of the four columns, two per instruction
+        unsigned long long fp[2];
+#pragma unroll
+        for (int cp = 0; cp < 2; cp++) {
+            unsigned long long acc = 0ull;
+#pragma unroll
+            for (int q = 0; q < 9; q++) {
+                const unsigned long long v = OpsF2::pack(r[q * 4 + 2 * cp], r[q * 4 + 2 * cp + 1]);
+                acc = OpsF2::fma(v, v, acc);
+            }
+            fp[cp] = acc;
+        }
+        float f4[4];
+        OpsF2::unpack(fp[0], f4[0], f4[1]);
+        OpsF2::unpack(fp[1], f4[2], f4[3]);
+        // stage 1: Samuelson (see tf32_epilogue_tile_v4 for the constant and the sign-bit form of the decision)
+        float lf4[4], ab4[4];
+        uint32_t und = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int col = C0 + 4 * st + c;
+            const float Bj = __shfl_sync(0xffffffffu, gvf, col);
+            const float Dj = __shfl_sync(0xffffffffu, gvf, 16 + col);
+            ab4[c] = row.Af + Bj;
+            lf4[c] = fmaf(-row.Cf, Dj, ab4[c]);
+            const float t = fmaf(3.00004f, f4[c], -(lf4[c] * lf4[c]));
+            const uint32_t excl = (__float_as_uint(t) & ~__float_as_uint(lf4[c])) >> 31;
+            und |= (excl ^ 1u) << c;
+        }
+        // stage 2: FP32 quartic sign test, per column pair with an undecided lane
+#pragma unroll
+        for (int cp = 0; cp < 2; cp++) {
+            if (__any_sync(0xffffffffu, (und >> (2 * cp)) & 3u)) {
+                unsigned long long S2[9];
+#pragma unroll
+                for (int q = 0; q < 9; q++) S2[q] = OpsF2::pack(r[q * 4 + 2 * cp], r[q * 4 + 2 * cp + 1]);
+                // test point: a rigorous lower bound of the (already lowered) threshold eigenvalue; lf carries the
+                // roundings of A_i + B_j and of the FMA: |lf - exact| <= u (|A_i + B_j| + |lf|) (1 + u)
+                float lam[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+                    lam[h] = fmaf(-2e-7f, fabsf(ab4[2 * cp + h]) + fabsf(lf4[2 * cp + h]), lf4[2 * cp + h]);
+                unsigned long long p0, p1, p2;
+                quartic32_values<OpsF2>(S2, fp[cp], OpsF2::pack(__float_as_uint(lam[0]), __float_as_uint(lam[1])), p0, p1, p2);
+                float a0[2], a1[2], a2[2];
+                OpsF2::unpack(p0, a0[0], a0[1]);
+                OpsF2::unpack(p1, a1[0], a1[1]);
+                OpsF2::unpack(p2, a2[0], a2[1]);
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+                    if (quartic32_decide(a0[h], a1[h], a2[h], f4[2 * cp + h], lam[h])) und &= ~(1u << (2 * cp + h));
+            }
+        }
+        near |= und << (C0 + 4 * st);
+        if (st + 1 < NST) tf32_ld_wait<4>(rr[(st + 1) & 1]);
+    }
+    uint32_t valid = 0xffffu;
+    if (j0 + 15 >= N) valid = (j0 >= N) ? 0u : (0xffffu >> (j0 + 16 - N));
+    if (j0 <= i) valid &= (i - j0 >= 15) ? 0u : (0xffffu << (i - j0 + 1));
+    return near & valid;
+}
+
 }  // namespace tsc

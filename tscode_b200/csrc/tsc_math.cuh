@@ -120,6 +120,106 @@ TSC_HD bool screen_candidate(const double S[9], double G, double e_thr_pad) {
 }
 
 // ------------------------------------------------------------------------------------------
+// FP32 form of the sign test: second stage of the tcgen05 pre-screens (tf32_common.cuh).
+//
+// Samuelson's bound sqrt(3) ||S||_F >= lambda_max is only sharp for near-isotropic covariances; for an
+// elongated or planar molecule it exceeds the threshold eigenvalue for EVERY pair (tools/aniso_probe.py:
+// the FP64 test then ran for all pairs and the screen was 3x slower).  The quartic's values P, P', P'' at a
+// test point lam <= lam_t are therefore also evaluated in FP32, straight from the FP32 accumulators, and
+// a pair is excluded only if they clear forward error bounds; whatever this stage cannot exclude becomes a
+// candidate and is decided exactly by the verify kernel, so the bounds only have to be safe, not sharp.
+//
+// Error bounds (standard model, u = 2^-24, s = ||S||_F, rho = max(lam, 2 s) >= every root and lam):
+//   key entries  |k| <= sqrt(3) s =: kappa, abs. error <= 2 u kappa;   2x2 minors |a| <= 2 kappa^2, error <= 11 u kappa^2
+//   c0 = det K (six products of minors, FMA chain): error <= 408 u kappa^4 = 3672 u s^4 <= 230 u rho^4
+//   c1 = -8 det S: error <= 72 u s^3 <= 9 u rho^3;   c2 = -2 f: error <= 18 u s^2 <= 4.5 u rho^2
+//   Horner: |P~ - P| <= 253 u rho^4,  |P'~ - P'| <= 36 u rho^3,  |P''~ - P''| <= 34 u rho^2
+// and the tolerances used are about twice that: 512 u rho^4, 72 u rho^3, 68 u rho^2
+// (tests/test_hostmath.py measures the actual errors against long-double evaluation on 2e6 covariances of six
+// kinds: 3.6 u, 11 u and 21 u at worst).
+// The operations are written through a policy class so that the host (float) and the device (two pairs
+// per instruction, fma.rn.f32x2) run the same sequence; no negation is needed anywhere: the key entries are
+// formed in the signs the minors use.
+// ------------------------------------------------------------------------------------------
+struct OpsF32 {
+    typedef float T;
+#ifdef __CUDA_ARCH__
+    static TSC_HD T fma(T a, T b, T c) { return __fmaf_rn(a, b, c); }
+    static TSC_HD T mul(T a, T b) { return __fmul_rn(a, b); }
+    static TSC_HD T add(T a, T b) { return __fadd_rn(a, b); }
+    static TSC_HD T sub(T a, T b) { return __fsub_rn(a, b); }
+#else
+    static TSC_HD T fma(T a, T b, T c) { return fmaf(a, b, c); }
+    static TSC_HD T mul(T a, T b) { volatile float r = a * b; return r; }      // (no contraction on the host)
+    static TSC_HD T add(T a, T b) { volatile float r = a + b; return r; }
+    static TSC_HD T sub(T a, T b) { volatile float r = a - b; return r; }
+#endif
+    static TSC_HD T bc(float x) { return x; }
+};
+
+// P, P', P'' of the key-matrix quartic of S at lam;  f = ||S||_F^2 (already computed by the caller)
+template <class O>
+TSC_HD void quartic32_values(const typename O::T* S, typename O::T f, typename O::T lam, typename O::T& p0,
+                             typename O::T& p1, typename O::T& p2) {
+    typedef typename O::T T;
+    const T t04p = O::add(S[0], S[4]), t04 = O::sub(S[0], S[4]);
+    const T k00 = O::add(t04p, S[8]), nk33 = O::sub(t04p, S[8]), k33 = O::sub(S[8], t04p);
+    const T k11 = O::sub(t04, S[8]), nk11 = O::sub(S[8], t04), nk22 = O::add(t04, S[8]);
+    const T k01 = O::sub(S[5], S[7]), nk01 = O::sub(S[7], S[5]);
+    const T k02 = O::sub(S[6], S[2]);
+    const T k03 = O::sub(S[1], S[3]), nk03 = O::sub(S[3], S[1]);
+    const T k12 = O::add(S[1], S[3]), k13 = O::add(S[6], S[2]), k23 = O::add(S[5], S[7]);
+    // 2x2 minors of rows (0,1) and (2,3) of K, each in the sign that makes its term of the Laplace expansion positive
+    const T na01 = O::fma(k01, k01, O::mul(k00, nk11));       // -(k00 k11 - k01^2)
+    const T nb23 = O::fma(k23, k23, O::mul(nk22, k33));       // -(k22 k33 - k23^2)
+    const T a02 = O::fma(k00, k12, O::mul(k02, nk01));        //   k00 k12 - k02 k01
+    const T nb13 = O::fma(k23, k13, O::mul(k12, nk33));       // -(k12 k33 - k23 k13)
+    const T a03 = O::fma(k00, k13, O::mul(k03, nk01));        //   k00 k13 - k03 k01
+    const T b12 = O::fma(k12, k23, O::mul(nk22, k13));        //   k12 k23 - k22 k13
+    const T na12 = O::fma(k02, k11, O::mul(nk01, k12));       // -(k01 k12 - k02 k11)
+    const T nb03 = O::fma(k23, k03, O::mul(k02, nk33));       // -(k02 k33 - k23 k03)
+    const T na13 = O::fma(k03, k11, O::mul(nk01, k13));       // -(k01 k13 - k03 k11)
+    const T b02 = O::fma(k02, k23, O::mul(nk22, k03));        //   k02 k23 - k22 k03
+    const T a23 = O::fma(k02, k13, O::mul(nk03, k12));        //   k02 k13 - k03 k12  (= b01)
+    T c0 = O::mul(na01, nb23);
+    c0 = O::fma(a02, nb13, c0);
+    c0 = O::fma(a03, b12, c0);
+    c0 = O::fma(na12, nb03, c0);
+    c0 = O::fma(na13, b02, c0);
+    c0 = O::fma(a23, a23, c0);
+    // c1 = -8 det S
+    const T m0 = O::sub(O::mul(S[4], S[8]), O::mul(S[5], S[7]));
+    const T m1 = O::sub(O::mul(S[5], S[6]), O::mul(S[3], S[8]));
+    const T m2 = O::sub(O::mul(S[3], S[7]), O::mul(S[4], S[6]));
+    T d = O::mul(S[0], m0);
+    d = O::fma(S[1], m1, d);
+    d = O::fma(S[2], m2, d);
+    const T c1 = O::mul(d, O::bc(-8.0f));
+    const T l2 = O::mul(lam, lam);
+    const T c2 = O::mul(f, O::bc(-2.0f)), c2x2 = O::mul(f, O::bc(-4.0f));
+    p2 = O::fma(O::bc(12.0f), l2, c2x2);
+    p1 = O::fma(O::fma(O::bc(4.0f), l2, c2x2), lam, c1);
+    p0 = O::fma(O::fma(O::add(l2, c2), lam, c1), lam, c0);
+}
+
+constexpr float Q32_T0 = 3.06e-5f;      // 512 u
+constexpr float Q32_T1SQ = 1.85e-11f;   // (72 u)^2 = 1.842e-11, rounded up
+constexpr float Q32_T2 = 4.06e-6f;      // 68 u
+
+// true = all roots of the quartic are provably below lam (NaN / inf anywhere -> false)
+TSC_HD bool quartic32_decide(float p0, float p1, float p2, float f, float lam) {
+    const float rho2 = fmaxf(lam * lam, 4.0f * f);
+    const float rho4 = rho2 * rho2;
+    return (lam > 0.0f) & (p0 > Q32_T0 * rho4) & (p1 > 0.0f) & (p1 * p1 > Q32_T1SQ * rho4 * rho2) & (p2 > Q32_T2 * rho2);
+}
+
+TSC_HD bool quartic32_excluded(const float S[9], float f, float lam) {
+    float p0, p1, p2;
+    quartic32_values<OpsF32>(S, f, lam, p0, p1, p2);
+    return quartic32_decide(p0, p1, p2, f, lam);
+}
+
+// ------------------------------------------------------------------------------------------
 // Largest eigenpair of the key matrix by cyclic Jacobi (always converges, any eigenvector of a
 // degenerate top eigenspace is an optimal rotation).  q = (q0, q1, q2, q3) unit quaternion,
 // scalar first.  Returns lambda_max; *gap receives lambda_1 - lambda_2.
