@@ -271,6 +271,28 @@ def run_b200(args):
     barrier()
     wall_ms = (time.perf_counter() - w0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
+    if rank == 0 and world == 1 and not args.skip_extras:
+        # The timed region above lasts a few tens of ms: nvidia-smi (100 ms period) sees it once at best, usually
+        # between kernels.  Two untimed additions: (a) the same step back to back for ~0.6 s under a second sampler;
+        # (b) the SM clock the screen kernel itself ran at, from clock64 / globaltimer stamps of CTA 0's first work
+        # item (tsc_set_trace_buffer).  Neither enters any reported rate.
+        from tscode_b200._lib import lib as _lib, ptr as _ptr
+        s2 = ClockSampler(local)
+        s2.start()
+        t_end = time.perf_counter() + 0.6
+        while time.perf_counter() < t_end:
+            for _ in range(20):
+                step()
+            torch.cuda.synchronize()
+        clocks["sustained"] = s2.stop()
+        if args.variant in ("f16", "tf32"):
+            trace = torch.zeros(8 * 96, dtype=torch.int64, device=dev)
+            _lib().tsc_set_trace_buffer(_ptr(trace))
+            pr.screen(); torch.cuda.synchronize()
+            _lib().tsc_set_trace_buffer(None)
+            tr = trace.cpu().numpy().reshape(96, 8)
+            if tr[95, 7] > tr[8, 7] > 0:
+                clocks["sm_mhz_in_screen_kernel"] = round(1e3 * float(tr[95, 3] - tr[8, 3]) / float(tr[95, 7] - tr[8, 7]), 1)
     step_ms = sum(t_events) / len(t_events)
     t = torch.tensor([step_ms, statistics.mean(phase_ms["screen"])], dtype=torch.float64, device=dev)
     if world > 1:

@@ -93,6 +93,36 @@ def test_tiles_cover_upper_triangle(N, world):
                 assert (p, jt) not in seen
                 seen.add((p, jt))
     assert seen == {(p, jt) for p in range((N + 127) // 128) for jt in range(8 * p, njt)}
+    # the balanced form (one contiguous stretch per CTA, dealt round-robin): same coverage; empty items only at the
+    # end of a CTA's list (the kernel stops at the first one)
+    for n_ctas in (148, 5):
+        seen = set()
+        for rank in range(world):
+            rb = _host.owned_row_blocks(N, rank, world)
+            items = _host.build_tf32_items_balanced(N, rb, n_ctas)
+            g = min(n_ctas, len(items))
+            for b in range(g):
+                mine = items[b::g]
+                live = mine[:, 2] > 0
+                assert not live[np.argmin(live):].any() or live.all()
+            for p, j0, cnt, lb in items:
+                assert rb[lb] == 4 * p and cnt >= 0
+                for jt in range(j0, j0 + cnt):
+                    assert (p, jt) not in seen
+                    seen.add((p, jt))
+        assert seen == {(p, jt) for p in range((N + 127) // 128) for jt in range(8 * p, njt)}
+    # ... and restricted to panel ranges (the sub-launches of the pipelined upload) the pieces tile the whole
+    seen = set()
+    rb = _host.owned_row_blocks(N, 0, 1)
+    n_panels = (N + 127) // 128
+    cuts = sorted({0, n_panels // 3, n_panels // 2, n_panels})
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        for p, j0, cnt, lb in _host.build_tf32_items_balanced(N, rb, 148, panel_lo=lo, panel_hi=hi):
+            assert lo <= p < hi or cnt == 0
+            for jt in range(j0, j0 + cnt):
+                assert (p, jt) not in seen
+                seen.add((p, jt))
+    assert seen == {(p, jt) for p in range(n_panels) for jt in range(8 * p, njt)}
 
 
 def test_row_sharding_is_balanced():
@@ -101,6 +131,18 @@ def test_row_sharding_is_balanced():
     assert max(loads) / min(loads) < 1.005
     items = [_host.build_tf32_items(N, _host.owned_row_blocks(N, r, 8))[:, 2].sum() for r in range(8)]
     assert max(items) / min(items) < 1.005
+    # inside a rank: cost (tiles + 3 per item) per CTA of the persistent grid, full launch and upload sub-launches
+    def cta_loads(items, g=148):
+        return np.array([items[b::g, 2].sum() + 3.0 * (items[b::g, 2] > 0).sum() for b in range(g)])
+    for world in (1, 8):
+        rb = _host.owned_row_blocks(N, 0, world)
+        loads = cta_loads(_host.build_tf32_items_balanced(N, rb, 148))
+        assert loads.max() / loads.mean() < 1.01
+    rb = _host.owned_row_blocks(N, 0, 1)
+    n_panels = (N + 127) // 128
+    for c in range(8):
+        loads = cta_loads(_host.build_tf32_items_balanced(N, rb, 148, panel_lo=n_panels * c // 8, panel_hi=n_panels * (c + 1) // 8))
+        assert loads.max() / loads.mean() < 1.05
 
 
 def test_ladder_schedule_matches_reference_rule():

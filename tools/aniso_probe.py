@@ -14,11 +14,15 @@ from tscode_b200.synth import gen_ensemble, mask_digest  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 cfgs = [int(c) for c in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["0"])]
+M = int(sys.argv[3]) if len(sys.argv) > 3 else 80
+kinds = sys.argv[4].split(",") if len(sys.argv) > 4 else ["isotropic", "elongated", "planar"]
 for name, scale in (("isotropic", 3.0), ("elongated", np.array([6.0, 2.0, 1.0])), ("planar", np.array([4.0, 4.0, 0.5]))):
-    S = gen_ensemble(3, N, 80, N // 10, scale=scale)
+    if name not in kinds:
+        continue
+    S = gen_ensemble(3, N, M, N // 10, scale=scale)
     ref = None
     for variant, cfg in [("f16", c) for c in cfgs] + [("dmma", 0)]:
-        pr = RmsdPruner(S, np.full(80, 6), 0.5, variant=variant, grid_ctas=cfg)
+        pr = RmsdPruner(S, np.full(M, 6), 0.5, variant=variant, grid_ctas=cfg)
         pr.pack()
         pr.screen(); torch.cuda.synchronize()
         ts = []
@@ -29,5 +33,5 @@ for name, scale in (("isotropic", 3.0), ("elongated", np.array([6.0, 2.0, 1.0]))
         mask = pr.eliminate().cpu().numpy()
         d = mask_digest(mask)
         ref = ref or d
-        print(f"{name} N={N} {variant} cfg {cfg}: screen {min(ts):.3f} ms verify {e1.elapsed_time(e2):.3f} ms "
+        print(f"{name} N={N} M={M} {variant} cfg {cfg}: screen {min(ts):.3f} ms verify {e1.elapsed_time(e2):.3f} ms "
               f"digest {d} same={d == ref} {pr.stats_dict()}", flush=True)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Probe: screen time on C3 as a function of the work-item length (j tiles per item) and configuration —
-separates the per-item cost (pipeline drain + panel rows -> TMEM) from the per-tile cost."""
+"""Probe: screen time on C3 (or N given) as a function of how the (panel, j tile) pairs are cut into work items and
+dealt to the CTAs — separates the per-item cost, the tail imbalance and the effect of the order."""
 import os
 import sys
 
@@ -12,14 +12,32 @@ from tscode_b200 import _host  # noqa: E402
 from tscode_b200.rmsd_pruning import RmsdPruner  # noqa: E402
 from tscode_b200.synth import gen_ensemble, mask_digest  # noqa: E402
 
-S = gen_ensemble(3, 50000, 80, 5000)
-cfgs = [int(c) for c in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["-2", "-8"])]
-chunks = [int(c) for c in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["64", "128", "256", "512"])]
+cfgs = [int(c) for c in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["-10"])]
+modes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["chunk128", "linear", "linear128", "even", "evensnake"]
+N = int(sys.argv[3]) if len(sys.argv) > 3 else 50000
+S = gen_ensemble(3, N, 80, N // 10)
+
+
+def build(mode, pr):
+    rb = pr.row_blocks_np
+    if mode.startswith("chunk"):
+        return _host.build_tf32_items(pr.N, rb, chunk=int(mode[5:]))
+    if mode == "linear":
+        return _host.build_tf32_items_balanced(pr.N, rb, 148)
+    if mode.startswith("linear"):
+        return _host.build_tf32_items_balanced(pr.N, rb, 148, max_item=int(mode[6:]))
+    if mode == "even":
+        return _host.build_tf32_items_even(pr.N, rb, 148, snake=False)
+    if mode == "evensnake":
+        return _host.build_tf32_items_even(pr.N, rb, 148, snake=True)
+    raise ValueError(mode)
+
+
 for cfg in cfgs:
     pr = RmsdPruner(S, np.full(80, 6), 0.5, variant="f16", grid_ctas=cfg)
     pr.pack()
-    for chunk in chunks:
-        items = np.ascontiguousarray(_host.build_tf32_items(pr.N, pr.row_blocks_np, chunk=chunk))
+    for mode in modes:
+        items = np.ascontiguousarray(build(mode, pr))
         pr.items, pr.n_items = torch.from_numpy(items).to(pr.device), int(items.shape[0])
         for _ in range(2):
             pr.screen()
@@ -31,5 +49,5 @@ for cfg in cfgs:
             ts.append(e0.elapsed_time(e1))
         pr.verify()
         mask = pr.eliminate().cpu().numpy()
-        print(f"cfg {cfg} chunk {chunk}: items {pr.n_items} screen {min(ts):.3f} ms (median {sorted(ts)[len(ts)//2]:.3f}) "
+        print(f"cfg {cfg} {mode}: items {pr.n_items} screen {min(ts):.3f} ms (median {sorted(ts)[len(ts)//2]:.3f}) "
               f"digest {mask_digest(mask)} {pr.stats_dict()}", flush=True)

@@ -19,7 +19,7 @@ for seed, N, M, nc, noise, thr in ((0, 257, 40, 20, 0.05, 0.5), (0, 1000, 40, 10
     S = gen_ensemble(seed, N, M, nc, sigma_noise=noise)
     sim = oracle_c.sim_rows(S, thr, 0, N).astype(bool)
     ref, _, _ = oracle_c.prune_heavy(S, thr)
-    for vv, cfg in (("f16", -10), ("f16", -11), ("tf32", -10)):
+    for vv, cfg in (("f16", 0), ("f16", -11), ("tf32", 0)):
         if vv == "tf32" and M > 120:
             continue
         pr = RmsdPruner(S, np.full(M, 6), thr, variant=vv, grid_ctas=cfg)
@@ -35,7 +35,7 @@ for seed, N, M, nc, noise, thr in ((0, 257, 40, 20, 0.05, 0.5), (0, 1000, 40, 10
         assert lost == 0
 
 S = gen_ensemble(3, 50000, 80, 5000)
-for variant, cfg in (("f16", -8), ("f16", -10), ("f16", -11), ("tf32", -10)):
+for variant, cfg in (("f16", 0), ("f16", -11), ("tf32", 0)):
     pr = RmsdPruner(S, np.full(80, 6), 0.5, variant=variant, grid_ctas=cfg)
     pr.pack()
     for _ in range(2):

@@ -63,6 +63,103 @@ def build_tf32_items(N: int, row_blocks: np.ndarray, chunk: int = 128) -> np.nda
     return np.asarray(items, dtype=np.int32).reshape(-1, 4)
 
 
+def build_tf32_items_balanced(N: int, row_blocks: np.ndarray, n_ctas: int, panel_lo: int = 0,
+                              panel_hi: int | None = None, item_cost: float = 3.0, max_item: int = 0) -> np.ndarray:
+    """Work items of the tcgen05 pre-screen for a persistent grid of `n_ctas` CTAs, each of which takes the array
+    entries b, b + n_ctas, b + 2 n_ctas, ...  Same coverage as build_tf32_items (optionally only the panels in
+    [panel_lo, panel_hi)), but partitioned linearly: the (panel, j tile) pairs are laid out panel after panel and
+    every CTA gets one contiguous stretch of equal cost (tiles + `item_cost` tiles per item start: pipeline drain
+    and panel rows -> TMEM, measured ~2 400 cycles), i.e. one item per panel its stretch touches.  Plain
+    round-robin dealing of 128-tile chunks left the busiest CTA of C3 5 % above the mean, and 20 % in the eight
+    sub-launches of the pipelined upload.  CTAs whose stretch touches fewer panels than the longest list get
+    empty items (count 0, a valid panel) in the last rounds."""
+    rb = np.asarray(row_blocks, dtype=np.int64)
+    njt = ((N + 127) // 128) * 8
+    if panel_hi is None:
+        panel_hi = (N + 127) // 128
+    panels = [(int(ib // PANEL_BLOCKS), lb) for lb, ib in enumerate(rb)
+              if ib % PANEL_BLOCKS == 0 and panel_lo <= ib // PANEL_BLOCKS < panel_hi]
+    total = sum(njt - 8 * p for p, _ in panels)
+    if total == 0:
+        return np.zeros((0, 4), np.int32)
+    n_bins = max(1, min(n_ctas, total // 8))
+    bins = [[] for _ in range(n_bins)]
+    left = float(total + item_cost * (len(panels) + n_bins))      # cost still to hand out (upper estimate)
+    b, budget = 0, 0.0
+    budget = left / n_bins
+    for p, lb in panels:
+        j, end = 8 * p, njt
+        while j < end:
+            room = int(budget - item_cost)
+            if room < 4 and b + 1 < n_bins:                       # not worth starting an item here: next CTA
+                left -= max(budget, 0.0) if False else 0.0
+                b += 1
+                budget = left / (n_bins - b)
+                continue
+            take = end - j if b + 1 == n_bins else max(1, min(end - j, room))
+            bins[b].append((p, j, take, lb))
+            j += take
+            budget -= take + item_cost
+            left -= take + item_cost
+    bins = [x for x in bins if x]
+    if max_item > 0:                                 # (measurement aid) the same stretches, cut into short items
+        bins = [[(p, j + o, min(max_item, cnt - o), lb) for p, j, cnt, lb in x for o in range(0, cnt, max_item)] for x in bins]
+    rounds = max(len(x) for x in bins)
+    pad_p, pad_lb = panels[0]
+    items = []
+    for r in range(rounds):
+        last = max(q for q in range(len(bins)) if len(bins[q]) > r)
+        for q in range(len(bins) if r + 1 < rounds else last + 1):
+            items.append(bins[q][r] if len(bins[q]) > r else (pad_p, 8 * pad_p, 0, pad_lb))
+    return np.asarray(items, dtype=np.int32).reshape(-1, 4)
+
+
+def build_tf32_items_even(N: int, row_blocks: np.ndarray, n_ctas: int, chunk: int = 128, panel_lo: int = 0,
+                          panel_hi: int | None = None, snake: bool = True) -> np.ndarray:
+    """As build_tf32_items (panel-major order, dealt round-robin to the CTAs by the kernel), but the number of
+    items is an exact multiple of n_ctas and every panel's j range is cut into equal pieces of about
+    total / n_items tiles, so that every CTA gets the same number of near-equal items."""
+    rb = np.asarray(row_blocks, dtype=np.int64)
+    njt = ((N + 127) // 128) * 8
+    if panel_hi is None:
+        panel_hi = (N + 127) // 128
+    panels = [(int(ib // PANEL_BLOCKS), lb) for lb, ib in enumerate(rb)
+              if ib % PANEL_BLOCKS == 0 and panel_lo <= ib // PANEL_BLOCKS < panel_hi]
+    L = np.array([njt - 8 * p for p, _ in panels], dtype=np.int64)
+    total = int(L.sum())
+    if total == 0:
+        return np.zeros((0, 4), np.int32)
+    m = max(1, int(round(total / (n_ctas * chunk))))
+    if m < 4:                                        # few items per CTA: shorter pieces (>= 16 tiles) balance better
+        m = max(m, min(4, total // (n_ctas * 16)))
+    n_items = min(m * n_ctas, total // 8) if total >= 8 * n_ctas else max(1, total // 8)
+    n_items = max(n_items, len(panels))
+    c = total / n_items
+    n_p = np.maximum(1, np.rint(L / c).astype(np.int64))
+    n_p = np.minimum(n_p, L)
+    while n_p.sum() < n_items:                       # split where the pieces are longest
+        q = int(np.argmax(np.where(n_p < L, L / n_p, 0.0)))
+        if n_p[q] >= L[q]:
+            break
+        n_p[q] += 1
+    while n_p.sum() > n_items and (n_p > 1).any():   # merge where they are shortest
+        q = int(np.argmin(np.where(n_p > 1, L / np.maximum(n_p - 1, 1), np.inf)))
+        n_p[q] -= 1
+    items = []
+    for (p, lb), Lp, n in zip(panels, L, n_p):
+        cuts = [8 * p + (int(Lp) * q) // int(n) for q in range(int(n) + 1)]
+        items += [(p, cuts[q], cuts[q + 1] - cuts[q], lb) for q in range(int(n)) if cuts[q + 1] > cuts[q]]
+    if snake and len(items) > n_ctas:
+        # longest first (stable: pieces of a panel stay together), rounds dealt alternately forwards and backwards
+        items.sort(key=lambda t: -t[2])
+        out = []
+        for r in range(0, len(items), n_ctas):
+            row = items[r:r + n_ctas]
+            out += row if (r // n_ctas) % 2 == 0 else row[::-1]
+        items = out
+    return np.asarray(items, dtype=np.int32).reshape(-1, 4)
+
+
 def tf32_rows_padded(N: int) -> int:
     return ((N + 127) // 128) * 128
 

@@ -44,7 +44,6 @@ constexpr int TS_KT_MAX = 9;                   // K blocks held in TMEM (NACC = 
 constexpr int TS_KT_HYB = 3;                   // K blocks held in TMEM next to THREE accumulator buffers (72 + 432 columns)
 constexpr int TS_MAX_NACC = 3;
 constexpr int TS_MAX_BSTAGES = 12;
-constexpr int TS_DEFAULT_CFG = 2;
 
 // Operand images are addressed in 16-byte K chunks: 4 TF32 values (kind::tf32, K = 8 per MMA) or
 // 8 FP16 values (kind::f16, K = 16 per MMA).  FP16 has the same 10-bit mantissa as TF32, so the error
@@ -130,6 +129,7 @@ __global__ void __launch_bounds__((1 + NMMA + 4 * (SPLIT ? CH : NACC * CH)) * 32
             int bs = 0; uint32_t bph = 0, aph = 0;
             for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
                 const int4 w = p.items[it];
+                if (w.z == 0) break;              // empty item: this CTA's list is exhausted (_host.build_tf32_items_balanced)
                 if (tail_kc > 0) {
                     mbar_wait(a_empty, aph ^ 1u);
                     if (elect_one()) {
@@ -169,6 +169,7 @@ __global__ void __launch_bounds__((1 + NMMA + 4 * (SPLIT ? CH : NACC * CH)) * 32
             int64_t tseq = 0;                                                        // tiles of this CTA so far
             for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
                 const int4 w = p.items[it];
+                if (w.z == 0) break;
                 mbar_wait(am_full, aph);
                 if (tail_kc > 0) mbar_wait(at_full, aph);
                 aph ^= 1u;
@@ -260,6 +261,7 @@ __global__ void __launch_bounds__((1 + NMMA + 4 * (SPLIT ? CH : NACC * CH)) * 32
         };
         for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
             const int4 w = p.items[it];
+            if (w.z == 0) break;
             const int64_t i = (int64_t)w.x * TF_ROWS + row_in_panel;
             // ---- this thread's row of the A panel -> TMEM; the row's 3*2*KT float4 are dealt round-robin to the groups
             mbar_wait(a_empty, eph ^ 1u);
@@ -416,12 +418,19 @@ static int launch_ts(const void* PA, const void* PB, const void* PR, const doubl
     //      buffers and three epilogue groups;  -9 = as -8 with three MMA warps, one per buffer
     //      (a warp must see every phase of the barriers it waits on: two warps on three buffers alias phases and hang);
     // -10 = as -8 with the two-stage FP32 epilogue (tf32_epilogue_tile_v5);  -11 = as -2 with that epilogue;
+    // (measured and removed: issuing the second half of tile t's K blocks alternately with the first half of tile
+    //  t+1's — six accumulator chains in flight instead of three, 45 instead of 56 cycles per MMA in
+    //  tools/umma_probe.py — needs the NEXT tile's accumulator buffer before the current tile is committed, which
+    //  leaves the epilogue less than one tile time to hand a buffer back: C3 3.26 ms with three buffers, 3.78 with
+    //  two, against 2.31 / 2.32 without)
     // (measured on C3, FP16 operands: -2 2.72 ms, -3 3.08, -4 2.78, -5 2.88, -7 3.60 — an epilogue warp spends
     // ~600 cycles per tile whatever the number of columns it handles, so fewer columns per warp-tile lose;
     // reading the whole tile into 144
     // registers and releasing before any arithmetic: 4.06)
-    // default = TS_DEFAULT_CFG
-    const int cfg = grid_ctas < 0 ? -grid_ctas : TS_DEFAULT_CFG;
+    // default: two-stage FP32 epilogue; three accumulator buffers next to a 3-K-block TMEM panel while the part of the
+    // panel left in shared memory is small (<= 5 K blocks in all: M <= 80 with FP16 operands), otherwise the whole
+    // panel (up to 9 K blocks) in TMEM and two buffers (20 000 x 150 atoms: 0.64 against 0.73 ms; equal at 80 atoms)
+    const int cfg = grid_ctas < 0 ? -grid_ctas : (p.nkc / 2 <= 5 ? 10 : 11);
     if (grid_ctas < 0) grid_ctas = 0;
     const int kt_max = cfg == 4 ? 0 : (cfg == 8 || cfg == 9 || cfg == 10) ? TS_KT_HYB : TS_KT_MAX;
     const int nkb = p.nkc / 2, KT = nkb < kt_max ? nkb : kt_max;

@@ -378,7 +378,7 @@ __device__ __forceinline__ uint32_t tf32_epilogue_tile_v4(uint32_t d0, float gvf
 // Samuelson cannot exclude is a true candidate anyway, so the FP64 test only confirmed what verify re-derives;
 // (b) Samuelson's bound needs a near-isotropic covariance: for elongated or planar molecules it excludes nothing and
 // v4 ran the FP64 test for every pair (3x slower screen, tools/aniso_probe.py).  The FP32 quartic excludes those
-// pairs at ~45 instructions per pair.
+// pairs at ~36 instructions per pair.
 // The accumulator buffer is released as soon as the last group is in registers.
 // ------------------------------------------------------------------------------------------------------------------
 struct OpsF2 {                 // two FP32 lanes per 64-bit register (per-lane IEEE, same values as OpsF32)
@@ -456,15 +456,18 @@ __device__ __forceinline__ uint32_t tf32_epilogue_tile_v5(uint32_t d0, float gvf
 #pragma unroll
                 for (int h = 0; h < 2; h++)
                     lam[h] = fmaf(-2e-7f, fabsf(ab4[2 * cp + h]) + fabsf(lf4[2 * cp + h]), lf4[2 * cp + h]);
-                unsigned long long p0, p1, p2;
-                quartic32_values<OpsF2>(S2, fp[cp], OpsF2::pack(__float_as_uint(lam[0]), __float_as_uint(lam[1])), p0, p1, p2);
-                float a0[2], a1[2], a2[2];
-                OpsF2::unpack(p0, a0[0], a0[1]);
+                unsigned long long p0, p1, p2, m0, m1, m2;
+                const unsigned long long lam2 = OpsF2::pack(__float_as_uint(lam[0]), __float_as_uint(lam[1]));
+                quartic32_values<OpsF2>(S2, fp[cp], lam2, p0, p1, p2);
+                quartic32_margins<OpsF2>(p0, p1, p2, fp[cp], lam2, m0, m1, m2);
+                float a1[2], b0[2], b1[2], b2[2];
                 OpsF2::unpack(p1, a1[0], a1[1]);
-                OpsF2::unpack(p2, a2[0], a2[1]);
+                OpsF2::unpack(m0, b0[0], b0[1]);
+                OpsF2::unpack(m1, b1[0], b1[1]);
+                OpsF2::unpack(m2, b2[0], b2[1]);
 #pragma unroll
                 for (int h = 0; h < 2; h++)
-                    if (quartic32_decide(a0[h], a1[h], a2[h], f4[2 * cp + h], lam[h])) und &= ~(1u << (2 * cp + h));
+                    if (quartic32_decide(lam[h], a1[h], b0[h], b1[h], b2[h])) und &= ~(1u << (2 * cp + h));
             }
         }
         near |= und << (C0 + 4 * st);

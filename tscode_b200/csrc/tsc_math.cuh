@@ -129,17 +129,20 @@ TSC_HD bool screen_candidate(const double S[9], double G, double e_thr_pad) {
 // a pair is excluded only if they clear forward error bounds; whatever this stage cannot exclude becomes a
 // candidate and is decided exactly by the verify kernel, so the bounds only have to be safe, not sharp.
 //
+// Coefficients: c2 = -2 f (f = ||S||_F^2), c1 = -8 det S, and — the roots being the signed sums
+// +-s1 +-s2 +-s3 of the singular values — c0 = det K = sum s^4 - 2 sum s_i^2 s_j^2 = 2 ||S^T S||_F^2 - f^2,
+// which costs 28 operations through the six entries of S^T S instead of 44 through the 2x2 minors of K and
+// has a much smaller error bound.
 // Error bounds (standard model, u = 2^-24, s = ||S||_F, rho = max(lam, 2 s) >= every root and lam):
-//   key entries  |k| <= sqrt(3) s =: kappa, abs. error <= 2 u kappa;   2x2 minors |a| <= 2 kappa^2, error <= 11 u kappa^2
-//   c0 = det K (six products of minors, FMA chain): error <= 408 u kappa^4 = 3672 u s^4 <= 230 u rho^4
-//   c1 = -8 det S: error <= 72 u s^3 <= 9 u rho^3;   c2 = -2 f: error <= 18 u s^2 <= 4.5 u rho^2
-//   Horner: |P~ - P| <= 253 u rho^4,  |P'~ - P'| <= 36 u rho^3,  |P''~ - P''| <= 34 u rho^2
-// and the tolerances used are about twice that: 512 u rho^4, 72 u rho^3, 68 u rho^2
-// (tests/test_hostmath.py measures the actual errors against long-double evaluation on 2e6 covariances of six
-// kinds: 3.6 u, 11 u and 21 u at worst).
-// The operations are written through a policy class so that the host (float) and the device (two pairs
-// per instruction, fma.rn.f32x2) run the same sequence; no negation is needed anywhere: the key entries are
-// formed in the signs the minors use.
+//   T = S^T S: |T~_ab - T_ab| <= 3 u |col_a| |col_b|;  p4 = ||T||_F^2 <= f^2, error <= 13 u f^2;  f~ = f (1 + 9 u)
+//   c0: error <= 46 u s^4 <= 3 u rho^4;   c1 = -8 det S: error <= 72 u s^3 <= 9 u rho^3;   c2: error <= 4.5 u rho^2
+//   Horner: |P~ - P| <= 26 u rho^4,  |P'~ - P'| <= 36 u rho^3,  |P''~ - P''| <= 34 u rho^2
+// The tolerances are 64 u R^2, 72 u R^(3/2), 68 u R with R = lam^2 + 4 f in [rho^2, 2 rho^2] (no max, no square
+// root: P' is compared through squares): at least twice the bounds.  tests/test_hostmath.py measures the actual
+// errors against long-double evaluation on 2e5 covariances of five kinds (isotropic, elongated, rank one, far from
+// the origin, sparse): a few u.
+// The operations are written through a policy class so that the host (float) and the device (two pairs per
+// instruction, fma / mul / add / sub .f32x2) run the same sequence.
 // ------------------------------------------------------------------------------------------
 struct OpsF32 {
     typedef float T;
@@ -157,36 +160,26 @@ struct OpsF32 {
     static TSC_HD T bc(float x) { return x; }
 };
 
+constexpr float Q32_T0 = 3.82e-6f;      // 64 u
+constexpr float Q32_T1SQ = 1.85e-11f;   // (72 u)^2 = 1.842e-11, rounded up
+constexpr float Q32_T2 = 4.06e-6f;      // 68 u
+
 // P, P', P'' of the key-matrix quartic of S at lam;  f = ||S||_F^2 (already computed by the caller)
 template <class O>
 TSC_HD void quartic32_values(const typename O::T* S, typename O::T f, typename O::T lam, typename O::T& p0,
                              typename O::T& p1, typename O::T& p2) {
     typedef typename O::T T;
-    const T t04p = O::add(S[0], S[4]), t04 = O::sub(S[0], S[4]);
-    const T k00 = O::add(t04p, S[8]), nk33 = O::sub(t04p, S[8]), k33 = O::sub(S[8], t04p);
-    const T k11 = O::sub(t04, S[8]), nk11 = O::sub(S[8], t04), nk22 = O::add(t04, S[8]);
-    const T k01 = O::sub(S[5], S[7]), nk01 = O::sub(S[7], S[5]);
-    const T k02 = O::sub(S[6], S[2]);
-    const T k03 = O::sub(S[1], S[3]), nk03 = O::sub(S[3], S[1]);
-    const T k12 = O::add(S[1], S[3]), k13 = O::add(S[6], S[2]), k23 = O::add(S[5], S[7]);
-    // 2x2 minors of rows (0,1) and (2,3) of K, each in the sign that makes its term of the Laplace expansion positive
-    const T na01 = O::fma(k01, k01, O::mul(k00, nk11));       // -(k00 k11 - k01^2)
-    const T nb23 = O::fma(k23, k23, O::mul(nk22, k33));       // -(k22 k33 - k23^2)
-    const T a02 = O::fma(k00, k12, O::mul(k02, nk01));        //   k00 k12 - k02 k01
-    const T nb13 = O::fma(k23, k13, O::mul(k12, nk33));       // -(k12 k33 - k23 k13)
-    const T a03 = O::fma(k00, k13, O::mul(k03, nk01));        //   k00 k13 - k03 k01
-    const T b12 = O::fma(k12, k23, O::mul(nk22, k13));        //   k12 k23 - k22 k13
-    const T na12 = O::fma(k02, k11, O::mul(nk01, k12));       // -(k01 k12 - k02 k11)
-    const T nb03 = O::fma(k23, k03, O::mul(k02, nk33));       // -(k02 k33 - k23 k03)
-    const T na13 = O::fma(k03, k11, O::mul(nk01, k13));       // -(k01 k13 - k03 k11)
-    const T b02 = O::fma(k02, k23, O::mul(nk22, k03));        //   k02 k23 - k22 k03
-    const T a23 = O::fma(k02, k13, O::mul(nk03, k12));        //   k02 k13 - k03 k12  (= b01)
-    T c0 = O::mul(na01, nb23);
-    c0 = O::fma(a02, nb13, c0);
-    c0 = O::fma(a03, b12, c0);
-    c0 = O::fma(na12, nb03, c0);
-    c0 = O::fma(na13, b02, c0);
-    c0 = O::fma(a23, a23, c0);
+    // T = S^T S (S row-major: S[3 k + a])
+    const T t00 = O::fma(S[6], S[6], O::fma(S[3], S[3], O::mul(S[0], S[0])));
+    const T t11 = O::fma(S[7], S[7], O::fma(S[4], S[4], O::mul(S[1], S[1])));
+    const T t22 = O::fma(S[8], S[8], O::fma(S[5], S[5], O::mul(S[2], S[2])));
+    const T t01 = O::fma(S[6], S[7], O::fma(S[3], S[4], O::mul(S[0], S[1])));
+    const T t02 = O::fma(S[6], S[8], O::fma(S[3], S[5], O::mul(S[0], S[2])));
+    const T t12 = O::fma(S[7], S[8], O::fma(S[4], S[5], O::mul(S[1], S[2])));
+    const T dg = O::fma(t22, t22, O::fma(t11, t11, O::mul(t00, t00)));
+    const T og = O::fma(t12, t12, O::fma(t02, t02, O::mul(t01, t01)));
+    const T p4 = O::fma(og, O::bc(2.0f), dg);
+    const T c0 = O::sub(O::mul(p4, O::bc(2.0f)), O::mul(f, f));
     // c1 = -8 det S
     const T m0 = O::sub(O::mul(S[4], S[8]), O::mul(S[5], S[7]));
     const T m1 = O::sub(O::mul(S[5], S[6]), O::mul(S[3], S[8]));
@@ -202,21 +195,28 @@ TSC_HD void quartic32_values(const typename O::T* S, typename O::T f, typename O
     p0 = O::fma(O::fma(O::add(l2, c2), lam, c1), lam, c0);
 }
 
-constexpr float Q32_T0 = 3.06e-5f;      // 512 u
-constexpr float Q32_T1SQ = 1.85e-11f;   // (72 u)^2 = 1.842e-11, rounded up
-constexpr float Q32_T2 = 4.06e-6f;      // 68 u
+// margins of the three values over their tolerances: the pair is excluded iff lam, p1, m0, m1, m2 are all > 0
+template <class O>
+TSC_HD void quartic32_margins(typename O::T p0, typename O::T p1, typename O::T p2, typename O::T f, typename O::T lam,
+                              typename O::T& m0, typename O::T& m1, typename O::T& m2) {
+    typedef typename O::T T;
+    const T R = O::fma(f, O::bc(4.0f), O::mul(lam, lam));
+    const T R2 = O::mul(R, R);
+    m0 = O::fma(R2, O::bc(-Q32_T0), p0);
+    m2 = O::fma(R, O::bc(-Q32_T2), p2);
+    m1 = O::fma(O::mul(R2, R), O::bc(-Q32_T1SQ), O::mul(p1, p1));
+}
 
 // true = all roots of the quartic are provably below lam (NaN / inf anywhere -> false)
-TSC_HD bool quartic32_decide(float p0, float p1, float p2, float f, float lam) {
-    const float rho2 = fmaxf(lam * lam, 4.0f * f);
-    const float rho4 = rho2 * rho2;
-    return (lam > 0.0f) & (p0 > Q32_T0 * rho4) & (p1 > 0.0f) & (p1 * p1 > Q32_T1SQ * rho4 * rho2) & (p2 > Q32_T2 * rho2);
+TSC_HD bool quartic32_decide(float lam, float p1, float m0, float m1, float m2) {
+    return (lam > 0.0f) & (p1 > 0.0f) & (m0 > 0.0f) & (m1 > 0.0f) & (m2 > 0.0f);
 }
 
 TSC_HD bool quartic32_excluded(const float S[9], float f, float lam) {
-    float p0, p1, p2;
+    float p0, p1, p2, m0, m1, m2;
     quartic32_values<OpsF32>(S, f, lam, p0, p1, p2);
-    return quartic32_decide(p0, p1, p2, f, lam);
+    quartic32_margins<OpsF32>(p0, p1, p2, f, lam, m0, m1, m2);
+    return quartic32_decide(lam, p1, m0, m1, m2);
 }
 
 // ------------------------------------------------------------------------------------------

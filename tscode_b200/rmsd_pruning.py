@@ -46,15 +46,35 @@ def _copy_stream(device_str):
     return torch.cuda.Stream(device=torch.device(device_str))
 
 
+UPLOAD_CHUNKS = 8       # pieces a host ensemble is uploaded in (_upload_pack_screen_pipelined)
+
+
+def _upload_bounds(N, n_chunks=UPLOAD_CHUNKS):
+    """Panel boundaries of the upload chunks: chunk c = panels [b[c], b[c+1])."""
+    n_panels = (N + 127) // 128
+    n_chunks = max(1, min(n_chunks, n_panels))
+    return [n_panels * c // n_chunks for c in range(n_chunks)] + [n_panels]
+
+
 @functools.lru_cache(maxsize=8)
-def _work_lists(N, rank, world, variant, device_str):
+def _work_lists(N, rank, world, variant, device_str, n_ctas=0):
     """Device-resident work lists (owned row blocks, tile / item lists) — they depend only on the
     shape of the problem, so repeated prunes of same-sized ensembles reuse them."""
     import torch
     dev = torch.device(device_str)
     rb = _host.owned_row_blocks(N, rank, world)
     out = {"row_blocks_np": rb, "row_blocks": torch.from_numpy(rb).to(dev)}
-    if variant in (2, 3, 4):
+    if variant in (2, 4):
+        # TMEM-operand screens: one contiguous, equally expensive stretch of (panel, j tile) pairs per CTA of the
+        # persistent grid (the kernel deals array entries round-robin); plus the same per upload chunk
+        n_ctas = n_ctas if n_ctas > 0 else torch.cuda.get_device_properties(dev).multi_processor_count
+        items = np.ascontiguousarray(_host.build_tf32_items_balanced(N, rb, n_ctas))
+        out["n_items"], out["items"], out["items_np"] = int(items.shape[0]), torch.from_numpy(items).to(dev), items
+        bounds = _upload_bounds(N)
+        chunks = [np.ascontiguousarray(_host.build_tf32_items_balanced(N, rb, n_ctas, panel_lo=bounds[c], panel_hi=bounds[c + 1]))
+                  for c in range(len(bounds) - 1)]
+        out["chunk_items"] = [(torch.from_numpy(it).to(dev) if it.shape[0] else None, int(it.shape[0])) for it in chunks]
+    elif variant == 3:
         items = np.ascontiguousarray(_host.build_tf32_items(N, rb))
         out["n_items"], out["items"], out["items_np"] = int(items.shape[0]), torch.from_numpy(items).to(dev), items
     else:
@@ -127,7 +147,7 @@ class RmsdPruner:
         with torch.cuda.device(self.device):
             dev = self.device
             self.heavy_idx = torch.from_numpy(heavy).to(dev)
-            wl = _work_lists(N, self.rank, self.world, self.variant, str(dev))
+            wl = _work_lists(N, self.rank, self.world, self.variant, str(dev), max(self.grid_ctas, 0))
             self.row_blocks_np, self.row_blocks = wl["row_blocks_np"], wl["row_blocks"]
             self.n_rb = int(self.row_blocks_np.size)
             self.n_tiles, self.tiles = wl.get("n_tiles", 0), wl.get("tiles")
@@ -442,7 +462,7 @@ class RmsdPruner:
         self.similarity()
         return self.eliminate()
 
-    def _upload_pack_screen_pipelined(self, n_chunks=8):
+    def _upload_pack_screen_pipelined(self):
         """Pinned host input: H2D copy, pack and screen overlapped.  A 128-row panel only needs the conformers
         from its own first row to the end (rows i, columns j > i), so the ensemble is uploaded in chunks from the
         LAST to the first on a copy stream, and as soon as a chunk has landed its rows are packed and the work
@@ -459,9 +479,11 @@ class RmsdPruner:
             return
         L = lib()
         n_panels = (N + 127) // 128
-        n_chunks = max(1, min(n_chunks, n_panels))
-        bounds = [(n_panels * c // n_chunks) * 128 for c in range(n_chunks)] + [N]
-        items_np = _work_lists(N, self.rank, self.world, self.variant, str(self.device))["items_np"]
+        pb = _upload_bounds(N)
+        n_chunks = len(pb) - 1
+        bounds = [q * 128 for q in pb[:-1]] + [N]
+        chunk_items = _work_lists(N, self.rank, self.world, self.variant, str(self.device),
+                                  max(self.grid_ctas, 0))["chunk_items"]
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream()
             copy = _copy_stream(str(self.device))
@@ -494,12 +516,10 @@ class RmsdPruner:
                 check(L.tsc_pack_f16_rows(ptr(self.S), N, self.A, ptr(self.heavy_idx), self.M, ptr(self.PA), ptr(self.PB),
                                           ptr(self.PR), ptr(self.G), ptr(self.sG), ptr(self.CT), lo, hi_pad, st),
                       "tsc_pack_f16_rows")
-                i0 = int(np.searchsorted(items_np[:, 0], lo // 128, side="left"))
-                i1 = int(np.searchsorted(items_np[:, 0], (hi + 127) // 128, side="left"))
-                if i1 > i0:
+                it_dev, n_it = chunk_items[c]
+                if n_it:
                     check(L.tsc_rmsd_sim_f16ts(ptr(self.PA), ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG),
-                                               ptr(self.CT), N, self.M,
-                                               ctypes.c_void_p(self.items.data_ptr() + 16 * i0), i1 - i0, self.thr,
+                                               ptr(self.CT), N, self.M, ptr(it_dev), n_it, self.thr,
                                                ptr(self.sim_bits), ptr(self.cand_list), self.cand_stride, self.grid_ctas,
                                                st), "tsc_rmsd_sim_f16ts")
         self.packed_ready = True
