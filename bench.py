@@ -271,6 +271,7 @@ def run_b200(args):
     barrier()
     wall_ms = (time.perf_counter() - w0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
+    verify_stats = pr.stats_dict()          # counters of the last timed step (the extras below run more steps)
     if rank == 0 and world == 1 and not args.skip_extras:
         # The timed region above lasts a few tens of ms: nvidia-smi (100 ms period) sees it once at best, usually
         # between kernels.  Two untimed additions: (a) the same step back to back for ~0.6 s under a second sampler;
@@ -428,7 +429,7 @@ def run_b200(args):
             "phase_ms": {k: statistics.mean(v) for k, v in phase_ms.items()},
             "parity": {"survivors": int(mask_np.sum()), "digest": mask_digest(mask_np),
                        "matches_reference": (mask_digest(mask_np) == cfg["digest"]) if cfg["digest"] else None,
-                       **pr.stats_dict()},
+                       **verify_stats},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clash": clash,
             "gpu_launches": args.steps * ((5 if args.variant in ("tf32", "f16") else 4) +
                                           (1 if pr.ladder_used == "fused" else 3 * rounds)), "clocks": clocks,
