@@ -354,8 +354,9 @@ def run_b200(args):
         peak = float(mp["bf16_tflops"])
         kname = "rmsd_ts_kernel<1,4,true>"
         psrc = (f"16-bit dense tensor peak = the {mp_src} cuBLAS bf16 burst figure in MEASURED_PEAKS.json "
-                f"({mp['bf16_tflops']} TFLOP/s); the kernel issues kind::f16 MMAs of shape 128x48x16, which the "
-                "tensor pipe executes at a fixed ~35-44 cycles each (tools/umma_probe.py), see DESIGN.md")
+                f"({mp['bf16_tflops']} TFLOP/s); the kernel issues kind::f16 MMAs of shape 128x48x16 (math time 24 cycles), "
+                "which the tensor pipe executes at a fixed ~41-56 cycles each (tools/umma_probe.py; ncu: tensor pipe "
+                "38.5 % active), see DESIGN.md 4.1b and 7")
     elif args.variant == "tf32":
         peak = mp["bf16_tflops"] / 2.0
         kname = "rmsd_ts_kernel<1,4,false>"

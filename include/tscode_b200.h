@@ -80,7 +80,14 @@ int tsc_pack_tf32(const double* S, int64_t N, int32_t A, const int32_t* heavy_id
 /* Same screen with the stationary 128-conformer operand held in TENSOR MEMORY (written once per
  * work item with tcgen05.st, read by tcgen05.mma [d], [a_tmem], b_desc): removes ~3/4 of the
  * shared-memory operand traffic that bounded tsc_rmsd_sim_tf32.  Default for variant "tf32". */
-/*   cand_list (may be NULL): block of cand_stride int32 pairs, element 0 = header whose first int32 is the
+/*   items: the persistent grid deals array entries round-robin (CTA b takes b, b + grid, ...); an entry with
+ *   j tile count 0 ends its CTA's list, so a host that wants equal work per CTA can give every CTA one contiguous
+ *   stretch of (panel, j tile) pairs and pad the shorter lists (tscode_b200/_host.py: build_tf32_items_balanced).
+ *   grid_ctas: 0 = one CTA per SM, default configuration (two-stage FP32 epilogue — Samuelson's bound, then the
+ *   FP32 sign test of the key-matrix quartic with rigorous error bounds —; panel split between TMEM and shared
+ *   memory with three accumulator buffers up to 5 K blocks, whole panel in TMEM with two buffers above);
+ *   > 0 = that many CTAs; < 0 selects a measured alternative configuration (tuning aid, see rmsd_tf32ts.cu).
+ *   cand_list (may be NULL): block of cand_stride int32 pairs, element 0 = header whose first int32 is the
  *   running count (zero it first); (local row, j) of every bit the screen sets is appended from element 1.
  *   tsc_rmsd_verify works from this list when it did not overflow. */
 int tsc_rmsd_sim_tf32ts(const float* PA, const float* PB, const float* PR, const double* G,

@@ -11,19 +11,21 @@
 // there (tcgen05.mma [d], [a_tmem], b_desc): shared-memory operand traffic drops to the 1.5 KB B
 // block per MMA.
 //
-// TMEM map (512 columns x 128 lanes x 32 bit), default configuration:
-//   [0, 216)        A: component a, K block kb at columns a*8*KT + 8*kb .. +8  (KT = min(K blocks, 9); a K block is
-//                   8 TF32 or 16 FP16 atoms = 32 bytes per row)
-//   [216, 504)      two accumulator buffers of 144 columns (D_x | D_y | D_z, each 3*16 wide)
-// K blocks beyond the ninth (M > 72 heavy atoms with TF32, > 144 with FP16) do not fit next to two accumulator
-// buffers; their A blocks stay in shared memory (bulk-TMA of the tail of the panel image) and are multiplied with
-// the shared-memory form of the instruction.
+// TMEM map (512 columns x 128 lanes x 32 bit), a K block = 8 TF32 or 16 FP16 atoms = 32 bytes per row = 8 columns:
+//   "full"   (NACC = 2, KTM = 9):  [0, 216)  A: component a, K block kb at columns a*8*KT + 8*kb .. +8, KT = min(K blocks, 9)
+//                                  [216, 504) two accumulator buffers of 144 columns (D_x | D_y | D_z, each 3*16 wide)
+//   "hybrid" (NACC = 3, KTM = 3):  [0, 72)   A: the first 3 K blocks;   [72, 504) three accumulator buffers
+// K blocks of the panel that are not in TMEM stay in shared memory (bulk-TMA of the tail of the panel image) and are
+// multiplied with the shared-memory form of the instruction (63 cycles per MMA instead of ~41-56).  launch_ts picks
+// hybrid up to 5 K blocks (M <= 80 with FP16 operands) and full above.
 //
 // Roles (one persistent CTA per SM): warp 0 producer (A tail + ring of B tiles), warp 1 TMEM allocation + MMA
 // issue, the rest epilogue in groups of 4 warps: at the start of a work item they load their rows of the A panel
-// (global -> registers -> tcgen05.st), then every group takes the tiles of its accumulator buffer.  Template
-// parameters select measured alternatives (see launch_ts): column-split groups, three buffers with the panel in
-// shared memory, two MMA warps.
+// (global -> registers -> tcgen05.st), then every group takes the tiles of its accumulator buffer.  The epilogue
+// (EPI = 5, tf32_common.cuh::tf32_epilogue_tile_v5) is FP32 only: Samuelson's bound, then the FP32 sign test of the
+// key-matrix quartic with rigorous error bounds; what neither excludes is a candidate for the exact verify kernel.
+// Template parameters select measured alternatives (see launch_ts): the FP64 second stage of round 1's first
+// versions (EPI = 4), column-split groups, the panel entirely in shared memory, several MMA warps.
 #include "tf32_common.cuh"
 
 namespace tsc {

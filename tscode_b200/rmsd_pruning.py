@@ -92,7 +92,8 @@ class RmsdPruner:
     structures : (N, A, 3) float64, numpy array or torch tensor (host or device)
     atomnos    : (A,) ints; hydrogens (== 1) are ignored        (rmsd_pruning.py:178-179)
     variant    : "f16" (default) = tcgen05/TMEM pre-screen on FP16 operands (10-bit mantissa, K = 16
-                 atoms per MMA) with a rigorous error bound, exact FP64 verification of everything
+                 atoms per MMA) with a rigorous error bound and an FP32 two-stage exclusion test
+                 (Samuelson, then the key-matrix quartic), exact FP64 verification of everything
                  it cannot exclude (falls back to "dmma" above 320 heavy atoms); "tf32" = the same
                  with TF32 operands (<= 120 heavy atoms); "dmma" = FP64 tensor cores; "fma" = FP64
                  FMA pipe.  All give identical final similarity bits and masks.
