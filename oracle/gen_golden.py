@@ -99,6 +99,33 @@ def main():
             res = [r for r in res if r["N"] >= 10000]
         json.dump({"meta": meta, "rows": res}, open(os.path.join(GOLD, name), "w"), indent=1)
 
+    # ---- A4 on anisotropic molecules (elongated / planar / rod): Samuelson's bound of the tcgen05 pre-screen excludes
+    # nothing there, the FP32 quartic stage does all the excluding ------------------------------
+    if want("prune_aniso"):
+        rows = [
+            dict(seed=31, N=3000, M=40, n_clusters=300, sigma_noise=0.05, thr=0.5, scale=[6.0, 2.0, 1.0]),
+            dict(seed=32, N=2000, M=80, n_clusters=150, sigma_noise=0.08, thr=0.5, scale=[4.0, 4.0, 0.5]),
+            dict(seed=33, N=1500, M=25, n_clusters=100, sigma_noise=0.05, thr=0.3, scale=[8.0, 1.0, 1.0], mixed_h=True),
+            dict(seed=34, N=1200, M=60, n_clusters=40, sigma_noise=0.2, thr=0.5, scale=[6.0, 2.0, 1.0]),   # near thr
+            dict(seed=35, N=1000, M=150, n_clusters=80, sigma_noise=0.05, thr=0.5, scale=[5.0, 3.0, 0.3]),
+        ]
+        res = []
+        for r in rows:
+            S = gen_ensemble(r["seed"], r["N"], r["M"], r["n_clusters"], sigma_noise=r["sigma_noise"],
+                             scale=np.array(r["scale"]))
+            atomnos = np.full(r["M"], 6)
+            if r.get("mixed_h"):
+                atomnos[np.random.default_rng(r["seed"]).random(r["M"]) < 0.3] = 1
+            t0 = time.perf_counter()
+            out, mask = prune_conformers_rmsd(S, atomnos, rmsd_thr=r["thr"])
+            dt = time.perf_counter() - t0
+            assert np.array_equal(out, S[mask])
+            r = dict(r, survivors=int(mask.sum()), digest=mask_digest(mask), wall_s=round(dt, 3),
+                     mask_hex=np.packbits(mask.astype(np.uint8)).tobytes().hex())
+            res.append(r)
+            print("prune_aniso:", {k: v for k, v in r.items() if k != "mask_hex"})
+        json.dump({"meta": meta, "rows": res}, open(os.path.join(GOLD, "prune_masks_aniso.json"), "w"), indent=1)
+
     # ---- A5: _rmsd_similarity -----------------------------------------------------------------
     if want("simlist"):
         S = gen_ensemble(21, 64, 30, 6, sigma_noise=0.2)

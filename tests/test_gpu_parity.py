@@ -224,6 +224,36 @@ def test_prune_conformers_rmsd_vs_reference(gpu, r):
     assert out.dtype == S.dtype and np.array_equal(out, S[mask])
 
 
+_aniso = json.load(open(os.path.join(GOLDEN, "prune_masks_aniso.json")))["rows"]
+
+
+@pytest.mark.parametrize("r", _aniso, ids=[f"s{r['seed']}_N{r['N']}_M{r['M']}" for r in _aniso])
+def test_prune_anisotropic_molecules_vs_reference(gpu, r):
+    """Elongated / planar / rod-like molecules: Samuelson's bound excludes nothing, the FP32 quartic stage of the
+    tcgen05 epilogue does the excluding.  Masks of every screen variant (and of the previous FP64
+    second stage, configurations -2 / -8) equal the live reference's; the FP32 stage must actually exclude: the
+    candidate count of the default screen stays within a small factor of the confirmed pairs."""
+    from tscode_b200.rmsd_pruning import RmsdPruner, prune_conformers_rmsd
+    from tscode_b200.synth import gen_ensemble
+    S = gen_ensemble(r["seed"], r["N"], r["M"], r["n_clusters"], sigma_noise=r["sigma_noise"], scale=np.array(r["scale"]))
+    atomnos = _atomnos(r)
+    ref = np.unpackbits(np.frombuffer(bytes.fromhex(r["mask_hex"]), np.uint8))[:r["N"]].astype(bool)
+    out, mask = prune_conformers_rmsd(S, atomnos, r["thr"])
+    assert np.array_equal(mask, ref) and np.array_equal(out, S[ref])
+    pairs = r["N"] * (r["N"] - 1) // 2
+    for variant, cfg in (("f16", 0), ("f16", -10), ("f16", -11), ("f16", -2), ("f16", -8), ("tf32", 0), ("dmma", 0)):
+        if variant == "tf32" and int((atomnos != 1).sum()) > 120:
+            continue
+        pr = RmsdPruner(S, atomnos, r["thr"], variant=variant, grid_ctas=cfg)
+        m = pr.run().cpu().numpy()
+        st = pr.stats_dict()
+        print(r["seed"], variant, cfg, st)
+        assert np.array_equal(m, ref), (variant, cfg)
+        assert st["candidates"] >= st["confirmed"]
+        if variant == "f16" and cfg in (0, -10, -11):
+            assert st["candidates"] <= 4 * st["confirmed"] + pairs // 50, (variant, cfg, st)
+
+
 _big = json.load(open(os.path.join(GOLDEN, "prune_masks_big.json")))["rows"]
 
 

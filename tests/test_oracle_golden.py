@@ -48,6 +48,19 @@ def test_prune_mask_matches_reference(r):
     assert np.array_equal(out, S[mask])
 
 
+_aniso = json.load(open(os.path.join(GOLDEN, "prune_masks_aniso.json")))["rows"]
+
+
+@pytest.mark.parametrize("r", _aniso, ids=[f"s{r['seed']}_N{r['N']}_M{r['M']}" for r in _aniso])
+def test_prune_mask_matches_reference_anisotropic_molecules(r):
+    """Elongated / planar / rod-like molecules (fixtures from the live reference, oracle/gen_golden.py --only
+    prune_aniso): the shapes on which the pre-screen's Samuelson bound excludes nothing."""
+    S = gen_ensemble(r["seed"], r["N"], r["M"], r["n_clusters"], sigma_noise=r["sigma_noise"], scale=np.array(r["scale"]))
+    out, mask = oracle_c.prune_conformers_rmsd(S, _atomnos(r), r["thr"])
+    ref = np.unpackbits(np.frombuffer(bytes.fromhex(r["mask_hex"]), np.uint8))[:r["N"]].astype(bool)
+    assert np.array_equal(mask, ref) and mask_digest(mask) == r["digest"] and np.array_equal(out, S[mask])
+
+
 def test_prune_numpy_oracle_small():
     for r in _rows:
         if r["N"] > 400:
