@@ -182,3 +182,64 @@ def test_fp32_quartic_never_excludes_a_pair_above_the_test_point(hm):
     assert hm.hm_q32_excluded(bad, 10.0, C.byref(lm)) == 0
     bad[0] = np.nan
     assert hm.hm_q32_excluded(bad, 10.0, C.byref(lm)) == 0
+
+
+def _rd32(x):
+    y = np.float32(x)
+    return np.nextafter(y, np.float32(-np.inf)) if float(y) > x else y
+
+
+def _ru32(x):
+    y = np.float32(x)
+    return np.nextafter(y, np.float32(np.inf)) if float(y) < x else y
+
+
+@pytest.mark.parametrize("case", [
+    dict(seed=0, N=260, M=40, ncl=26, noise=0.05, thr=0.5, scale=3.0),
+    dict(seed=13, N=240, M=80, ncl=12, noise=0.2, thr=0.5, scale=3.0),                     # many pairs near the threshold
+    dict(seed=31, N=260, M=40, ncl=26, noise=0.05, thr=0.5, scale=[6.0, 2.0, 1.0]),        # elongated
+    dict(seed=32, N=220, M=80, ncl=16, noise=0.08, thr=0.5, scale=[4.0, 4.0, 0.5]),        # planar
+    dict(seed=33, N=260, M=17, ncl=20, noise=0.05, thr=0.3, scale=[8.0, 1.0, 1.0]),        # rod
+], ids=["iso", "near_thr", "elongated", "planar", "rod"])
+def test_f16_prescreen_model_never_loses_a_similar_pair(hm, case):
+    """Host model of the default pre-screen: coordinates rounded to FP16 as tsc_pack_f16 does,
+    covariance accumulated in FP32, threshold eigenvalue lowered by the operand error bound with the directed
+    roundings of tf32_row_consts / the column terms, stage 1 (Samuelson) and stage 2 (FP32 quartic through the same
+    tsc_math.cuh code the device runs).  Every pair the oracle calls similar must survive both stages; almost
+    everything else must be excluded."""
+    S = gen_ensemble(case["seed"], case["N"], case["M"], case["ncl"], sigma_noise=case["noise"],
+                     scale=np.array(case["scale"]) if isinstance(case["scale"], list) else case["scale"])
+    N, M, thr = case["N"], case["M"], case["thr"]
+    sim = oracle_c.sim_rows(S, thr, 0, N).astype(bool)
+    X = S.astype(np.float16).astype(np.float32)
+    G = (S ** 2).sum((1, 2))
+    sG = np.sqrt(G)
+    hs, cc, e_thr = 0.5 * (1.0 - 1e-10), np.sqrt(3.0) * 1.05e-3, M * thr * thr * (1.0 + 1e-6)
+    Af = [_rd32(hs * G[i] - 0.5 * e_thr) for i in range(N)]
+    Cf = [_ru32(cc * sG[i]) for i in range(N)]
+    Bf = [_rd32(hs * G[j]) for j in range(N)]
+    Df = [_ru32(sG[j]) for j in range(N)]
+    lm = C.c_double()
+    lost = excluded = dissimilar = stage2 = 0
+    for i in range(N):
+        cov = np.einsum("ma,jmb->jab", X[i], X[i + 1:]).reshape(-1, 9).astype(np.float32)
+        for k, j in enumerate(range(i + 1, N)):
+            ab = np.float32(Af[i] + Bf[j])
+            lf = np.float32(np.float64(ab) - np.float64(Cf[i]) * np.float64(Df[j]))        # one rounding, as the FMA
+            f = np.float32(0)
+            for q in range(9):
+                f = np.float32(np.float64(cov[k, q]) * np.float64(cov[k, q]) + np.float64(f))
+            t = np.float32(3.00004) * f - lf * lf
+            out = bool(lf > 0 and t < 0)
+            if not out:
+                stage2 += 1
+                lam = np.float32(np.float64(lf) - 2e-7 * (abs(float(ab)) + abs(float(lf))))
+                out = bool(hm.hm_q32_excluded(np.ascontiguousarray(cov[k]), float(lam), C.byref(lm)))
+            if sim[i, j]:
+                lost += out
+            else:
+                dissimilar += 1
+                excluded += out
+    assert lost == 0
+    assert excluded > 0.9 * dissimilar or case["noise"] >= 0.2, (excluded, dissimilar)
+    print(case, "stage 2 ran for", stage2, "of", N * (N - 1) // 2, "pairs; excluded", excluded, "of", dissimilar)
