@@ -421,6 +421,33 @@ def run_b200(args):
                  "e2e": {"value": C2["P"] / statistics.median(es), "unit": "poses/s",
                          "h2d_bytes_per_step": int(R.nbytes + tt.nbytes + conf.size * 4), "d2h_bytes_per_step": C2["P"]}}
 
+    # ---- same prune on an ELONGATED molecule (reported beside the headline, never part of it) -----------------
+    # C3's generator draws an isotropic Gaussian blob, the best case of the pre-screen's first stage
+    # (Samuelson's bound); for elongated molecules the second, FP32-quartic stage decides every pair and the epilogue
+    # rather than the tensor pipe sets the pace.
+    shaped = None
+    if world == 1 and not args.skip_extras and not args.n_conformers and args.variant in ("f16", "tf32"):
+        try:
+            S_el = gen_ensemble(cfg["seed"], N, M, cfg["n_clusters"], scale=np.array([6.0, 2.0, 1.0]))
+            pe = RmsdPruner(torch.from_numpy(S_el).to(dev), atomnos, thr, variant=args.variant, device=dev, ladder=args.ladder)
+            el_ms = {"screen": [], "step": []}
+            for it in range(5):
+                flush.fill_(1)
+                e = [ev() for _ in range(4)]
+                e[0].record(); pe.pack(); e[1].record(); pe.screen(); e[2].record(); pe.verify(); m_el = pe.eliminate(); e[3].record()
+                torch.cuda.synchronize()
+                if it >= 2:
+                    el_ms["screen"].append(e[1].elapsed_time(e[2])); el_ms["step"].append(e[0].elapsed_time(e[3]))
+            shaped = {"workload": "as C3 with the base molecule scaled (6, 2, 1) along x, y, z (elongated)",
+                      "ms_per_step": statistics.mean(el_ms["step"]), "screen_ms": statistics.mean(el_ms["screen"]),
+                      "value": pairs / (statistics.mean(el_ms["step"]) * 1e-3), "unit": UNIT,
+                      "survivors": int(m_el.sum()), "digest": mask_digest(m_el.cpu().numpy()),
+                      # the C oracle's mask of this ensemble (48 867 survivors; run in the build container)
+                      "matches_oracle": mask_digest(m_el.cpu().numpy()) == "478bc29df1e239da", **pe.stats_dict()}
+            del pe, S_el
+        except Exception as exc:                                  # an extra: never take the headline down with it
+            shaped = {"error": repr(exc)}
+
     rounds = len(pr.rounds)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
@@ -431,7 +458,7 @@ def run_b200(args):
             "parity": {"survivors": int(mask_np.sum()), "digest": mask_digest(mask_np),
                        "matches_reference": (mask_digest(mask_np) == cfg["digest"]) if cfg["digest"] else None,
                        **verify_stats},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clash": clash,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clash": clash, "elongated_molecule": shaped,
             "gpu_launches": args.steps * ((5 if args.variant in ("tf32", "f16") else 4) +
                                           (1 if pr.ladder_used == "fused" else 3 * rounds)), "clocks": clocks,
             "fp64_peaks_tflops": peaks}
