@@ -240,3 +240,42 @@ def test_native_xyz_text_is_byte_identical_to_reference_formatting():
     buf = io.StringIO()
     write_xyz(S[5], at, buf, title='x')
     assert buf.getvalue() == ref_write(S[5], at, 'x')
+
+
+def _deal_like_the_kernel(items, n_ctas):
+    """rmsd_ts_kernel's item loop: grid = min(n_ctas, n_items) CTAs, CTA b visits entries b, b + grid, ... and stops
+    at the first empty one.  Returns how often every (panel, j tile) pair is processed."""
+    n = len(items)
+    g = min(n_ctas, n)
+    seen = {}
+    for b in range(g):
+        for it in range(b, n, g):
+            p, j0, cnt, lb = items[it]
+            if cnt == 0:
+                break
+            for jt in range(j0, j0 + cnt):
+                seen[(p, jt)] = seen.get((p, jt), 0) + 1
+    return seen
+
+
+@pytest.mark.parametrize("N", [1, 129, 650, 900, 1500, 2000, 2500, 4096, 4100, 5000, 8191, 12345])
+def test_balanced_items_dealt_like_the_kernel_cover_every_tile_once(N):
+    """The balanced work list relies on the kernel's round-robin dealing AND on 'an empty entry ends the CTA's list':
+    simulate exactly that for whole launches and for the sub-launches of the pipelined upload, several ranks and
+    grid sizes (incl. grids larger than the number of stretches: the layout stride must then be the grid)."""
+    from tscode_b200.rmsd_pruning import _upload_bounds
+    njt = ((N + 127) // 128) * 8
+    n_panels = (N + 127) // 128
+    pb = _upload_bounds(N)
+    ranges = [(0, None)] + [(pb[c], pb[c + 1]) for c in range(len(pb) - 1)]
+    for world in (1, 2, 8):
+        for rank in range(min(world, 2)):
+            rb = _host.owned_row_blocks(N, rank, world)
+            own = [int(ib // 4) for ib in rb if ib % 4 == 0]
+            for n_ctas in (148, 132, 5):
+                for lo, hi in ranges:
+                    h = n_panels if hi is None else hi
+                    want = {(p, jt) for p in own if lo <= p < h for jt in range(8 * p, njt)}
+                    items = _host.build_tf32_items_balanced(N, rb, n_ctas, panel_lo=lo, panel_hi=hi)
+                    seen = _deal_like_the_kernel(items, n_ctas)
+                    assert set(seen) == want and all(v == 1 for v in seen.values()), (N, world, rank, n_ctas, lo, hi)

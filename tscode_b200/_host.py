@@ -104,6 +104,11 @@ def build_tf32_items_balanced(N: int, row_blocks: np.ndarray, n_ctas: int, panel
         bins = [[(p, j + o, min(max_item, cnt - o), lb) for p, j, cnt, lb in x for o in range(0, cnt, max_item)] for x in bins]
     rounds = max(len(x) for x in bins)
     pad_p, pad_lb = panels[0]
+    # The kernel's stride is its grid = min(n_ctas, number of entries).  One round: one entry per CTA, any grid works.
+    # Several rounds: the array is laid out with stride n_ctas exactly (CTAs without work get an empty first entry), so
+    # that the entries a CTA visits are the ones meant for it and an empty entry really ends its list.
+    if rounds > 1:
+        bins += [[] for _ in range(n_ctas - len(bins))]
     items = []
     for r in range(rounds):
         last = max(q for q in range(len(bins)) if len(bins[q]) > r)
