@@ -126,6 +126,20 @@ def main():
             print("prune_aniso:", {k: v for k, v in r.items() if k != "mask_hex"})
         json.dump({"meta": meta, "rows": res}, open(os.path.join(GOLD, "prune_masks_aniso.json"), "w"), indent=1)
 
+    # ---- the same at BASELINE size: C3's generator with an elongated / planar base molecule (digests only) -----
+    if want("prune_aniso_big"):
+        res = []
+        for r in (dict(seed=3, N=20000, M=80, n_clusters=2000, sigma_noise=0.05, thr=0.5, scale=[4.0, 4.0, 0.5]),
+                  dict(seed=3, N=50000, M=80, n_clusters=5000, sigma_noise=0.05, thr=0.5, scale=[6.0, 2.0, 1.0])):
+            S = gen_ensemble(r["seed"], r["N"], r["M"], r["n_clusters"], sigma_noise=r["sigma_noise"],
+                             scale=np.array(r["scale"]))
+            t0 = time.perf_counter()
+            out, mask = prune_conformers_rmsd(S, np.full(r["M"], 6), rmsd_thr=r["thr"])
+            dt = time.perf_counter() - t0
+            res.append(dict(r, survivors=int(mask.sum()), digest=mask_digest(mask), wall_s=round(dt, 3)))
+            print("prune_aniso_big:", res[-1])
+        json.dump({"meta": meta, "rows": res}, open(os.path.join(GOLD, "prune_masks_aniso_big.json"), "w"), indent=1)
+
     # ---- A5: _rmsd_similarity -----------------------------------------------------------------
     if want("simlist"):
         S = gen_ensemble(21, 64, 30, 6, sigma_noise=0.2)

@@ -254,6 +254,22 @@ def test_prune_anisotropic_molecules_vs_reference(gpu, r):
             assert st["candidates"] <= 4 * st["confirmed"] + pairs // 50, (variant, cfg, st)
 
 
+_aniso_big = json.load(open(os.path.join(GOLDEN, "prune_masks_aniso_big.json")))["rows"]
+
+
+@pytest.mark.parametrize("r", _aniso_big, ids=[f"N{r['N']}" for r in _aniso_big])
+def test_prune_big_anisotropic_digest_vs_reference(gpu, r):
+    """BASELINE size with a planar / elongated base molecule (the FP32 quartic stage decides every pair): the mask
+    must equal the live reference's (oracle/gen_golden.py --only prune_aniso_big)."""
+    from tscode_b200.rmsd_pruning import RmsdPruner
+    from tscode_b200.synth import gen_ensemble, mask_digest
+    S = gen_ensemble(r["seed"], r["N"], r["M"], r["n_clusters"], sigma_noise=r["sigma_noise"], scale=np.array(r["scale"]))
+    pr = RmsdPruner(S, np.full(r["M"], 6), r["thr"])
+    mask = pr.run().cpu().numpy()
+    print(r["N"], pr.stats_dict(), pr.rounds)
+    assert int(mask.sum()) == r["survivors"] and mask_digest(mask) == r["digest"]
+
+
 _big = json.load(open(os.path.join(GOLDEN, "prune_masks_big.json")))["rows"]
 
 

@@ -61,6 +61,15 @@ def test_prune_mask_matches_reference_anisotropic_molecules(r):
     assert np.array_equal(mask, ref) and mask_digest(mask) == r["digest"] and np.array_equal(out, S[mask])
 
 
+def test_prune_big_anisotropic_digest_matches_reference():
+    """20 000 x 80 with a planar base molecule: C oracle against the live reference's digest (the 50 000 x 80
+    elongated row of the same fixture file was checked the same way in the build container: 11 s)."""
+    r = json.load(open(os.path.join(GOLDEN, "prune_masks_aniso_big.json")))["rows"][0]
+    S = gen_ensemble(r["seed"], r["N"], r["M"], r["n_clusters"], sigma_noise=r["sigma_noise"], scale=np.array(r["scale"]))
+    mask, _, _ = oracle_c.prune_heavy(S, r["thr"])
+    assert int(mask.sum()) == r["survivors"] and mask_digest(mask) == r["digest"]
+
+
 def test_prune_numpy_oracle_small():
     for r in _rows:
         if r["N"] > 400:
