@@ -21,3 +21,5 @@ ncu --set full --clock-control none --import-source on -k regex:rmsd_ts_kernel -
 echo "full capture rc=$?" | tee -a $OUT/rc.txt
 ls -la $OUT
 echo "== probes" ; timeout 120 python tools/umma_probe.py > $OUT/umma_probe.log 2>&1 ; timeout 120 python tools/trace_probe.py > $OUT/trace_probe.log 2>&1 ; timeout 120 python tools/clash_run.py > $OUT/clash_run.log 2>&1; tail -3 $OUT/clash_run.log
+timeout 120 python tools/aniso_probe.py 50000 0 80 isotropic,elongated > $OUT/aniso_probe.log 2>&1 ; grep f16 $OUT/aniso_probe.log
+timeout 120 python tools/e2e_timeline.py > $OUT/e2e_timeline.log 2>&1 ; tail -12 $OUT/e2e_timeline.log
