@@ -110,6 +110,24 @@ int tsc_rmsd_sim_f16ts(const void* PA, const void* PB, const void* PR, const dou
                        const double* sG, const float* CT, int64_t N, int32_t M, const int32_t* items,
                        int32_t n_items, double thr, uint32_t* sim_bits, int32_t* cand_list,
                        int64_t cand_stride, int32_t grid_ctas, void* stream);
+/* DEFAULT all-pairs pre-screen (rmsd_screen.cu): tcgen05 / TMEM, FP16 operands, FP32 accumulation, one
+ * accumulator buffer per (128 x 32 tile, row of the covariances), MMAs of shape 128 x 96 x 16 in three skewed
+ * chains, epilogue on T = S^T S.  Replaces the pair loop of rmsd_pruning.py:43-79 together with
+ * tsc_rmsd_verify: bits are a superset of the similar pairs, every set bit is also appended to cand_list.
+ *   PA, PB, PR: tsc_screen_operand_bytes(N, M) bytes each; CT: tsc_screen_ct_floats(N) floats; G, sG: doubles for
+ *   every padded row (ceil(N/128)*128).  tsc_pack_screen writes them for conformers [row_begin, row_end)
+ *   (row_begin a multiple of 8; row_end <= 0 = all rows incl. padding).
+ *   items (n_items, 4) int32 {panel, first j tile of 32 conformers, tile count, local 32-row block of the panel's
+ *   first row in sim_bits}, dealt round-robin to the CTAs; an item with count 0 ends a CTA's list.
+ *   M <= tsc_screen_max_atoms() (192 heavy atoms); above, use tsc_rmsd_sim_tiles.  grid_ctas 0 = one CTA per SM. */
+int64_t tsc_screen_operand_bytes(int64_t N, int32_t M);
+int64_t tsc_screen_ct_floats(int64_t N);
+int32_t tsc_screen_max_atoms(void);
+int tsc_pack_screen(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M, void* PA, void* PB,
+                    void* PR, double* G, double* sG, float* CT, int64_t row_begin, int64_t row_end, void* stream);
+int tsc_rmsd_screen(const void* PA, const void* PB, const void* PR, const double* G, const double* sG,
+                    const float* CT, int64_t N, int32_t M, const int32_t* items, int32_t n_items, double thr,
+                    uint32_t* sim_bits, int32_t* cand_list, int64_t cand_stride, int32_t grid_ctas, void* stream);
 /* Measurement aid: 8*96 int64 of clock64 stamps from the first work item of CTA 0 (NULL = off). */
 void tsc_set_trace_buffer(void* dev_ptr);
 int tsc_rmsd_sim_tf32(const float* PA, const float* PB, const double* G, const double* sG, int64_t N,

@@ -101,4 +101,32 @@ int hm_q32_excluded(const float* S, float lam, double* lam_max) {
     *lam_max = tsc::key_top_eigen(tsc::key_matrix(Sd), qv, &gap);
     return tsc::quartic32_excluded(S, frob32(S), lam) ? 1 : 0;
 }
+
+// the T = S^T S form of the same stage (component-sequential screen): decision + FP64 lambda_max
+int hm_q32t_excluded(const float* S, float lam, double* lam_max) {
+    double Sd[9];
+    for (int q = 0; q < 9; q++) Sd[q] = S[q];
+    double qv[4], gap;
+    *lam_max = tsc::key_top_eigen(tsc::key_matrix(Sd), qv, &gap);
+    float t[6];
+    tsc::quartic32_T_from_rows(S, t);
+    return tsc::quartic32_T_excluded(t, lam) ? 1 : 0;
+}
+
+// d = the bound on |det S| the T form uses (before the 1 + 4u scale), next to |det S| in long double, and f
+void hm_q32t_det(const float* S, int n, double* out) {
+    for (int k = 0; k < n; k++) {
+        const float* s = S + 9 * k;
+        float t[6], f, c0, da;
+        tsc::quartic32_T_from_rows(s, t);
+        tsc::quartic32_T_coeffs<tsc::OpsF32>(t, f, c0, da);
+        long double Sd[9];
+        for (int q = 0; q < 9; q++) Sd[q] = s[q];
+        long double dS = Sd[0] * (Sd[4] * Sd[8] - Sd[5] * Sd[7]) - Sd[1] * (Sd[3] * Sd[8] - Sd[5] * Sd[6])
+                       + Sd[2] * (Sd[3] * Sd[7] - Sd[4] * Sd[6]);
+        out[3 * k + 0] = (double)sqrtf(da > 0.f ? da : 0.f);
+        out[3 * k + 1] = (double)fabsl(dS);
+        out[3 * k + 2] = (double)f;
+    }
+}
 }

@@ -473,6 +473,68 @@ def test_rot_corr_vs_reference(gpu, name):
     assert worst < 1e-9
 
 
+_rcb = json.load(open(os.path.join(GOLDEN, "rotcorr_big.json")))["fixtures"]
+
+
+def _rcb_load(name):
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import rotor_molecules as rm
+    from tscode_b200.torsion_module import TorsionInfo
+    f = _rcb[name]
+    g = np.load(os.path.join(GOLDEN, f"rotcorr_{name}.npz"))
+    S, atomnos = rm.ensemble_tritbu63(f["seed"], f["N"])
+    info = TorsionInfo([tuple(t) for t in f["torsions"]], [tuple(a) for a in f["angles"]],
+                       g["rot_masks"].astype(bool), g["node_lists"].astype(bool))
+    return f, g, S, atomnos, info
+
+
+def test_rot_corr_750_vs_unmodified_reference(gpu):
+    """The largest ensemble the reference's own size guard lets through (750 structures, torsion_module.py:1056),
+    63 atoms / six rotors, against the UNMODIFIED live reference (oracle/gen_golden_c4.py): mask and returned
+    (centred + mutated) structures, default (exact) mode; mask also in stateless mode."""
+    from tscode_b200.synth import mask_digest
+    from tscode_b200.torsion_module import prune_conformers_rmsd_rot_corr
+    f, g, S, atomnos, info = _rcb_load("tritbu63_s11_750")
+    assert f["reference"] == "unmodified" and f["N"] == 750
+    out, mask = prune_conformers_rmsd_rot_corr(S.copy(), atomnos, None, max_rmsd=f["thr"], torsion_info=info)
+    assert int(mask.sum()) == f["survivors"] and mask_digest(mask) == f["digest"]
+    assert np.array_equal(mask, g["mask"])
+    dev = float(np.abs(out - g["out"]).max())
+    print("750 structures, exact mode: max |returned - reference| =", dev)
+    assert dev < 1e-9
+    out2, mask2 = prune_conformers_rmsd_rot_corr(S.copy(), atomnos, None, max_rmsd=f["thr"], torsion_info=info,
+                                                 mode="stateless")
+    assert np.array_equal(mask2, g["mask"])
+    heavy = atomnos != 1
+    assert np.abs(out2[:, heavy] - g["out"][:, heavy]).max() < 1e-9
+
+
+def test_rot_corr_20000_vs_guard_lifted_reference(gpu):
+    """BASELINE configs[3] at size: 20 000 structures x 63 atoms.  The reference refuses such an ensemble (size guard),
+    so the fixture is the reference's own source run with that one literal changed (29 min on one host core,
+    oracle/gen_golden_c4.py, labelled "guard lifted").  The stateless forward-scan mode — the default above 2 000
+    structures — must give the same mask and the same heavy-atom coordinates of the returned structures (the
+    hydrogens of the noise-degenerate alkyne rotors may pick another of their equivalent images)."""
+    from tscode_b200.synth import mask_digest
+    from tscode_b200.torsion_module import prune_conformers_rmsd_rot_corr
+    name = [k for k in _rcb if k.startswith("tritbu63_s13_")][0]
+    f, g, S, atomnos, info = _rcb_load(name)
+    assert f["reference"].startswith("guard lifted") and f["N"] == 20000
+    out, mask = prune_conformers_rmsd_rot_corr(S, atomnos, None, max_rmsd=f["thr"], torsion_info=info, max_structures=None)
+    print("20000 structures:", int(mask.sum()), "survivors, digest", mask_digest(mask), "reference", f["digest"])
+    assert int(mask.sum()) == f["survivors"] and mask_digest(mask) == f["digest"]
+    assert np.array_equal(mask, g["mask"])
+    heavy = atomnos != 1
+    dev_h = float(np.abs(out[:, heavy] - g["out"][:, heavy]).max())
+    print("max |returned - reference| heavy atoms =", dev_h, " all atoms =", float(np.abs(out - g["out"]).max()))
+    assert dev_h < 1e-9
+    # with the guard in place the reference's behaviour: centred input, all-True mask (:1056-1060)
+    out0, mask0 = prune_conformers_rmsd_rot_corr(S[:800], atomnos, None, max_rmsd=f["thr"], torsion_info=info)
+    assert mask0.all() and np.allclose(out0, S[:800] - S[:800].mean(axis=1, keepdims=True))
+
+
 def test_rot_corr_guard_and_no_rotors(gpu):
     from tscode_b200.torsion_module import TorsionInfo, prune_conformers_rmsd_rot_corr
     f, g, S, atomnos, info = _rc_load("neopentyl_s1")

@@ -243,3 +243,118 @@ def test_f16_prescreen_model_never_loses_a_similar_pair(hm, case):
     assert lost == 0
     assert excluded > 0.9 * dissimilar or case["noise"] >= 0.2, (excluded, dissimilar)
     print(case, "stage 2 ran for", stage2, "of", N * (N - 1) // 2, "pairs; excluded", excluded, "of", dissimilar)
+
+
+# ---- T = S^T S form of the FP32 stage (component-sequential screen, rmsd_screen.cu) ------------------------------------
+@pytest.fixture(scope="module")
+def hmt(hm):
+    hm.hm_q32t_excluded.argtypes = [_fp, C.c_float, C.POINTER(C.c_double)]
+    hm.hm_q32t_det.argtypes = [_fp, C.c_int, _dp]
+    return hm
+
+
+def test_fp32_T_form_det_bound_is_an_upper_bound(hmt):
+    """d = sqrt(max(det T~, 0) + 8 u f^3) must never be below |det S| (long double), for covariances of every kind —
+    it replaces the signed determinant in the quartic's linear coefficient (tsc_math.cuh)."""
+    rng = np.random.default_rng(3)
+    u = 2.0 ** -24
+    for trial in range(10):
+        n = 20000
+        S = _q32_covariances(rng, trial % 5, n)
+        out = np.zeros(3 * n)
+        hmt.hm_q32t_det(S, n, out)
+        o = out.reshape(n, 3)
+        ok = np.isfinite(o).all(1)
+        d, true, f = o[ok, 0], o[ok, 1], o[ok, 2]
+        # (kind 3, an ensemble 7e3 A from the origin, overflows f^3 in FP32: the bound is +inf, nothing gets excluded)
+        assert ok.sum() > 0.9 * n or trial % 5 == 3
+        assert (d * (1 + 4 * u) >= true).all(), float((true - d).max())
+        # and it is not wildly loose: within the margin's own root of |det S|
+        assert (d <= true + 1.01 * np.sqrt(8 * u * f ** 3) + 1e-30).all()
+
+
+def test_fp32_T_form_never_excludes_a_pair_above_the_test_point(hmt):
+    """As test_fp32_quartic_never_excludes_a_pair_above_the_test_point for the T form: sound on every kind of
+    covariance (incl. det S < 0, where it is weaker by design), and still excluding the anisotropic pairs."""
+    rng = np.random.default_rng(4)
+    lm = C.c_double()
+    # soundness on generic covariances with test points around lambda_max
+    for kind in range(5):
+        S = _q32_covariances(rng, kind, 400)
+        for k in range(400):
+            hmt.hm_q32t_excluded(S[k], 1.0, C.byref(lm))
+            top = lm.value
+            if not np.isfinite(top) or top <= 0:
+                continue
+            for rel in (-0.5, -1e-2, -1e-4, -1e-6, 0.0):
+                assert hmt.hm_q32t_excluded(S[k], float(np.float32(top * (1 + rel))), C.byref(lm)) == 0
+    # screening power on the elongated sample of the signed form's test
+    n = 3000
+    base = rng.normal(size=(80, 3)) * np.array([6, 2, 1.0])
+    P = base + rng.normal(size=(n, 80, 3)); Q = base + rng.normal(size=(n, 80, 3))
+    S = np.ascontiguousarray(np.einsum("nma,nmb->nab", P, Q).reshape(n, 9), dtype=np.float32)
+    Gp, Gq = (P ** 2).sum((1, 2)), (Q ** 2).sum((1, 2))
+    lam_t = (0.5 * (Gp + Gq - 80 * 0.25) - 1.05e-3 * np.sqrt(3.0) * np.sqrt(Gp * Gq)).astype(np.float32)
+    excluded = 0
+    for k in range(n):
+        e = hmt.hm_q32t_excluded(S[k], float(lam_t[k]), C.byref(lm))
+        assert not (e and lm.value > lam_t[k])
+        excluded += e
+    assert excluded == n
+    for k in range(0, n, 10):     # det S > 0 here: the decision flips within 2e-3 (relative) above lambda_max
+        hmt.hm_q32t_excluded(S[k], 1.0, C.byref(lm))
+        assert hmt.hm_q32t_excluded(S[k], float(np.float32(lm.value * (1 + 2e-3))), C.byref(lm)) == 1
+    bad = np.zeros(9, np.float32)
+    assert hmt.hm_q32t_excluded(bad, 0.0, C.byref(lm)) == 0
+    bad[0] = np.inf
+    assert hmt.hm_q32t_excluded(bad, 10.0, C.byref(lm)) == 0
+    bad[0] = np.nan
+    assert hmt.hm_q32t_excluded(bad, 10.0, C.byref(lm)) == 0
+
+
+@pytest.mark.parametrize("case", [
+    dict(seed=0, N=200, M=40, ncl=20, noise=0.05, thr=0.5, scale=3.0),
+    dict(seed=13, N=200, M=80, ncl=10, noise=0.2, thr=0.5, scale=3.0),
+    dict(seed=31, N=200, M=40, ncl=20, noise=0.05, thr=0.5, scale=[6.0, 2.0, 1.0]),
+    dict(seed=32, N=200, M=80, ncl=16, noise=0.08, thr=0.5, scale=[4.0, 4.0, 0.5]),
+    dict(seed=33, N=200, M=17, ncl=20, noise=0.05, thr=0.3, scale=[8.0, 1.0, 1.0]),
+    dict(seed=34, N=200, M=30, ncl=20, noise=0.05, thr=0.5, scale=[5.0, 5.0, 0.02]),       # flat (aromatic-like)
+], ids=["iso", "near_thr", "elongated", "planar", "rod", "flat"])
+def test_screen_model_T_form_never_loses_a_similar_pair(hmt, case):
+    """Host model of the component-sequential screen: FP16 operands, FP32 covariance rows, T accumulated row by
+    row, f = tr T, Samuelson then the T-form quartic.  No similar pair may be lost; most others are excluded."""
+    S = gen_ensemble(case["seed"], case["N"], case["M"], case["ncl"], sigma_noise=case["noise"],
+                     scale=np.array(case["scale"]) if isinstance(case["scale"], list) else case["scale"])
+    N, M, thr = case["N"], case["M"], case["thr"]
+    sim = oracle_c.sim_rows(S, thr, 0, N).astype(bool)
+    X = S.astype(np.float16).astype(np.float32)
+    G = (S ** 2).sum((1, 2))
+    sG = np.sqrt(G)
+    hs, cc, e_thr = 0.5 * (1.0 - 1e-10), np.sqrt(3.0) * 1.05e-3, M * thr * thr * (1.0 + 1e-6)
+    Af = [_rd32(hs * G[i] - 0.5 * e_thr) for i in range(N)]
+    Cf = [_ru32(cc * sG[i]) for i in range(N)]
+    Bf = [_rd32(hs * G[j]) for j in range(N)]
+    Df = [_ru32(sG[j]) for j in range(N)]
+    lm = C.c_double()
+    lost = excluded = dissimilar = stage2 = 0
+    for i in range(N):
+        cov = np.einsum("ma,jmb->jab", X[i], X[i + 1:]).reshape(-1, 9).astype(np.float32)
+        for k, j in enumerate(range(i + 1, N)):
+            ab = np.float32(Af[i] + Bf[j])
+            lf = np.float32(np.float64(ab) - np.float64(Cf[i]) * np.float64(Df[j]))
+            c = cov[k].astype(np.float64)
+            f = np.float32(np.float32(np.float32((c[0::3] ** 2).sum()) + np.float32((c[1::3] ** 2).sum())) + np.float32((c[2::3] ** 2).sum()))
+            t = np.float32(3.00004) * f - lf * lf
+            out = bool(lf > 0 and t < 0)
+            if not out:
+                stage2 += 1
+                lam = np.float32(np.float64(lf) - 2e-7 * (abs(float(ab)) + abs(float(lf))))
+                out = bool(hmt.hm_q32t_excluded(np.ascontiguousarray(cov[k]), float(lam), C.byref(lm)))
+            if sim[i, j]:
+                lost += out
+            else:
+                dissimilar += 1
+                excluded += out
+    assert lost == 0
+    assert excluded > 0.9 * dissimilar or case["noise"] >= 0.2, (excluded, dissimilar)
+    print(case, "stage 2 ran for", stage2, "of", N * (N - 1) // 2, "pairs; excluded", excluded, "of", dissimilar)

@@ -63,8 +63,16 @@ def build_tf32_items(N: int, row_blocks: np.ndarray, chunk: int = 128) -> np.nda
     return np.asarray(items, dtype=np.int32).reshape(-1, 4)
 
 
+def build_screen_items(N: int, row_blocks: np.ndarray, n_ctas: int, panel_lo: int = 0, panel_hi: int | None = None,
+                       item_cost: float = 2.5) -> np.ndarray:
+    """Work items of the default screen (rmsd_screen.cu): as build_tf32_items_balanced, with j tiles of 32 conformers
+    (four per 128-row panel)."""
+    return build_tf32_items_balanced(N, row_blocks, n_ctas, panel_lo, panel_hi, item_cost, tiles_per_panel=4)
+
+
 def build_tf32_items_balanced(N: int, row_blocks: np.ndarray, n_ctas: int, panel_lo: int = 0,
-                              panel_hi: int | None = None, item_cost: float = 3.0, max_item: int = 0) -> np.ndarray:
+                              panel_hi: int | None = None, item_cost: float = 3.0, max_item: int = 0,
+                              tiles_per_panel: int = 8) -> np.ndarray:
     """Work items of the tcgen05 pre-screen for a persistent grid of `n_ctas` CTAs, each of which takes the array
     entries b, b + n_ctas, b + 2 n_ctas, ...  Same coverage as build_tf32_items (optionally only the panels in
     [panel_lo, panel_hi)), but partitioned linearly: the (panel, j tile) pairs are laid out panel after panel and
@@ -74,20 +82,21 @@ def build_tf32_items_balanced(N: int, row_blocks: np.ndarray, n_ctas: int, panel
     sub-launches of the pipelined upload.  CTAs whose stretch touches fewer panels than the longest list get
     empty items (count 0, a valid panel) in the last rounds."""
     rb = np.asarray(row_blocks, dtype=np.int64)
-    njt = ((N + 127) // 128) * 8
+    tpp = int(tiles_per_panel)
+    njt = ((N + 127) // 128) * tpp
     if panel_hi is None:
         panel_hi = (N + 127) // 128
     panels = [(int(ib // PANEL_BLOCKS), lb) for lb, ib in enumerate(rb)
               if ib % PANEL_BLOCKS == 0 and panel_lo <= ib // PANEL_BLOCKS < panel_hi]
-    total = sum(njt - 8 * p for p, _ in panels)
+    total = sum(njt - tpp * p for p, _ in panels)
     if total == 0:
         return np.zeros((0, 4), np.int32)
-    n_bins = max(1, min(n_ctas, total // 8))
+    n_bins = max(1, min(n_ctas, total // tpp))
     bins = [[] for _ in range(n_bins)]
     left = float(total + item_cost * (len(panels) + n_bins))      # cost still to hand out (upper estimate)
     b, budget = 0, left / n_bins                                  # current CTA and what it may still take
     for p, lb in panels:
-        j, end = 8 * p, njt
+        j, end = tpp * p, njt
         while j < end:
             room = int(budget - item_cost)
             if room < 4 and b + 1 < n_bins:                       # not worth starting an item here: next CTA
@@ -113,7 +122,7 @@ def build_tf32_items_balanced(N: int, row_blocks: np.ndarray, n_ctas: int, panel
     for r in range(rounds):
         last = max(q for q in range(len(bins)) if len(bins[q]) > r)
         for q in range(len(bins) if r + 1 < rounds else last + 1):
-            items.append(bins[q][r] if len(bins[q]) > r else (pad_p, 8 * pad_p, 0, pad_lb))
+            items.append(bins[q][r] if len(bins[q]) > r else (pad_p, tpp * pad_p, 0, pad_lb))
     return np.asarray(items, dtype=np.int32).reshape(-1, 4)
 
 

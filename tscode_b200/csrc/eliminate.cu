@@ -276,7 +276,10 @@ __global__ void __launch_bounds__(EF_THREADS, 1) elim_fused_kernel(const ElimFus
 
     // ---- overflow check (uniform: every thread reads the same headers) ----
     bool overflow = false;
-    for (int l = 0; l < p.n_lists; l++) overflow |= (int64_t)p.lists[l * p.stride].x > p.stride - 1;
+    for (int l = 0; l < p.n_lists; l++) {
+        const int64_t cnt = p.lists[l * p.stride].x;
+        overflow |= cnt < 0 || cnt > p.stride - 1;           // any count outside [0, capacity] is an overflow
+    }
     if (overflow) {
         if (gtid == 0) { info[1] = 0; __threadfence(); info[0] = 1; }
         return;

@@ -253,11 +253,11 @@ __global__ void __launch_bounds__((1 + NMMA + 4 * (SPLIT ? CH : NACC * CH)) * 32
         int qn = 0;
         auto flush_q = [&]() {
             __syncwarp();
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&p.cand[0].x, qn);
+            int64_t base = 0;
+            if (lane == 0) base = list_reserve(&p.cand[0].x, qn, p.cand_stride - 1);
             base = __shfl_sync(0xffffffffu, base, 0);
             for (int k = lane; k < qn; k += 32)
-                if ((int64_t)base + k < p.cand_stride - 1) p.cand[1 + base + k] = my_q[k];
+                if (base + k < p.cand_stride - 1) p.cand[1 + base + k] = my_q[k];
             __syncwarp();
             qn = 0;
         };
@@ -339,13 +339,13 @@ __global__ void __launch_bounds__((1 + NMMA + 4 * (SPLIT ? CH : NACC * CH)) * 32
                             const int32_t lrow = w.w * CB + row_in_panel;
                             if (qn + total > TS_Q) flush_q();
                             if (total > TS_Q) {                       // a dense tile: straight to the global list
-                                int base = 0;
-                                if (lane == 0) base = atomicAdd(&p.cand[0].x, total);
+                                int64_t base = 0;
+                                if (lane == 0) base = list_reserve(&p.cand[0].x, total, p.cand_stride - 1);
                                 base = __shfl_sync(0xffffffffu, base, 0);
                                 while (bb) {
                                     const int b = __ffs(bb) - 1;
                                     bb &= bb - 1;
-                                    if ((int64_t)base + at < p.cand_stride - 1)
+                                    if (base + at < p.cand_stride - 1)
                                         p.cand[1 + base + at] = make_int2(lrow, (int32_t)(j0 + b));
                                     at++;
                                 }

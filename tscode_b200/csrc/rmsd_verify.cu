@@ -176,11 +176,11 @@ __global__ void __launch_bounds__(VF_WARPS * 32) rmsd_verify_kernel(const double
             okmask |= (ok ? 1u : 0u) << k;
         }
         if (pair_list && okmask) {           // confirmed pairs of the batch -> (i, j) list, one atomic per batch
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&pair_list[0].x, __popc(okmask));
+            int64_t base = 0;
+            if (lane == 0) base = list_reserve(&pair_list[0].x, __popc(okmask), pair_stride - 1);
             base = __shfl_sync(0xffffffffu, base, 0);
             if ((okmask >> lane) & 1u) {
-                const int64_t slot = (int64_t)base + __popc(okmask & ((1u << lane) - 1u));
+                const int64_t slot = base + __popc(okmask & ((1u << lane) - 1u));
                 if (slot < pair_stride - 1) pair_list[1 + slot] = make_int2(s_i[warp][lane], s_j[warp][lane]);
             }
         }
@@ -391,11 +391,11 @@ __global__ void __launch_bounds__(VF_WARPS * 32) rmsd_verify_list_kernel(
             for (int g = 0; g < 8; g++) okmask |= ((okb >> (4 * g)) & 1u) << (pass * 8 + g);
         }
         if (pair_list && okmask) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&pair_list[0].x, __popc(okmask));
+            int64_t base = 0;
+            if (lane == 0) base = list_reserve(&pair_list[0].x, __popc(okmask), pair_stride - 1);
             base = __shfl_sync(0xffffffffu, base, 0);
             if ((okmask >> lane) & 1u) {
-                const int64_t slot = (int64_t)base + __popc(okmask & ((1u << lane) - 1u));
+                const int64_t slot = base + __popc(okmask & ((1u << lane) - 1u));
                 if (slot < pair_stride - 1) pair_list[1 + slot] = make_int2(i, j);
             }
         }

@@ -164,6 +164,19 @@ __device__ __forceinline__ float to_tf32(float x) {
     return __uint_as_float(r);
 }
 
+// Reserve `n` slots of a fixed-capacity device list whose header word is the running entry count (candidate list,
+// confirmed-pair list).  Returns the first slot, or `cap` — so that the caller's `slot < cap` test skips every store —
+// once the header has left [0, cap]: it then stays out of range (that is how consumers see the overflow) and is not
+// advanced any further, so it can neither turn negative nor wrap around to a value that looks like a complete list,
+// however many entries a very redundant ensemble produces (a header only ever overshoots by the few reservations
+// that were already in flight; hosts keep cap below 2^31 - 2^24).
+__device__ __forceinline__ int64_t list_reserve(int* header, int n, int64_t cap) {
+    const int cur = *reinterpret_cast<volatile int*>(header);
+    if (cur < 0 || (int64_t)cur > cap) return cap;
+    const int base = atomicAdd(header, n);
+    return base < 0 ? cap : (int64_t)base;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -195,6 +195,64 @@ TSC_HD void quartic32_values(const typename O::T* S, typename O::T f, typename O
     p0 = O::fma(O::fma(O::add(l2, c2), lam, c1), lam, c0);
 }
 
+// ------------------------------------------------------------------------------------------
+// The same test from T = S^T S alone (component-sequential screen, rmsd_screen.cu).
+//
+// That kernel receives the covariance one ROW at a time (row a of S = the three sums over atoms of
+// x_a(i) * x_b(j), b = 0..2: one accumulator buffer per (tile, a)) and can afford to keep six numbers per
+// pair between rows, not nine.  T = S^T S is the sum of the outer products of the rows, so it accumulates
+// row by row (mul for the first row, fma for the others: the very operation order of quartic32_values);
+// f = tr T and c0 = 2 ||T||_F^2 - f^2 follow as before.  Only det S couples the rows.  It is replaced by
+//     d >= |det S|,    d = sqrt(max(det T~, 0) + 8 u f^3) (1 + 4 u)        (det T = (det S)^2 exactly)
+// and c1 by -8 d.  For x >= 0 the true quartic P(x) = x^4 - 2 f x^2 - 8 det S x + c0 is then >= the evaluated
+// one, Pd(x); if Pd and its first three derivatives (the third is 24 lam) are positive at lam, Taylor's formula
+// gives Pd > 0 on [lam, inf), hence P > 0 there and lambda_max < lam: the pair is excluded.  When det S >= 0
+// (every pair that could be similar: the optimal superposition is then a proper rotation already) nothing is
+// lost against the signed form beyond the margin under the root.
+// Margin: every Leibniz term of det T is at most T00 T11 T22 <= (f/3)^3; the entries of T~ carry a relative
+// error <= 3 u of sqrt(T_aa T_bb), each term thus <= 9 u f^3 / 27, six terms 2 u f^3; the evaluation (nine
+// operations on quantities <= 2 f^3 / 27) adds less than u f^3.  8 u f^3 is more than twice the sum.
+// sqrt is the approximate instruction on the device (error <= 2 ulp; the factor 1 + 4 u covers it and the
+// addition under the root).  P and P' take -8 d through the same Horner steps as before, so the forward-error
+// tolerances of quartic32_margins (which even include an allowance for c1's own rounding) stay valid.
+// ------------------------------------------------------------------------------------------
+constexpr float Q32_DET_MARGIN = 4.77e-7f;    // 8 u
+constexpr float Q32_C1_SCALE = -8.000004f;    // -8 (1 + 4 u), rounded away from zero
+
+// t[6] = (T00, T11, T22, T01, T02, T12) -> f = tr T, c0, and det_arg = det T~ + 8 u f^3 (the caller clamps it at
+// zero and takes the root: packed types have no square-root instruction)
+template <class O>
+TSC_HD void quartic32_T_coeffs(const typename O::T* t, typename O::T& f, typename O::T& c0, typename O::T& det_arg) {
+    typedef typename O::T T;
+    f = O::add(O::add(t[0], t[1]), t[2]);
+    const T dg = O::fma(t[2], t[2], O::fma(t[1], t[1], O::mul(t[0], t[0])));
+    const T og = O::fma(t[5], t[5], O::fma(t[4], t[4], O::mul(t[3], t[3])));
+    const T p4 = O::fma(og, O::bc(2.0f), dg);
+    const T ff = O::mul(f, f);
+    c0 = O::sub(O::mul(p4, O::bc(2.0f)), ff);
+    // det T expanded along the first row
+    const T m0 = O::sub(O::mul(t[1], t[2]), O::mul(t[5], t[5]));
+    const T m1 = O::sub(O::mul(t[5], t[4]), O::mul(t[3], t[2]));
+    const T m2 = O::sub(O::mul(t[3], t[5]), O::mul(t[1], t[4]));
+    T d = O::mul(t[0], m0);
+    d = O::fma(t[3], m1, d);
+    d = O::fma(t[4], m2, d);
+    det_arg = O::fma(O::mul(ff, f), O::bc(Q32_DET_MARGIN), d);
+}
+
+// P, P', P'' at lam with c1 = Q32_C1_SCALE * d  (d >= 0: the caller's root of max(det_arg, 0))
+template <class O>
+TSC_HD void quartic32_T_values(typename O::T f, typename O::T c0, typename O::T d, typename O::T lam, typename O::T& p0,
+                               typename O::T& p1, typename O::T& p2) {
+    typedef typename O::T T;
+    const T c1 = O::mul(d, O::bc(Q32_C1_SCALE));
+    const T l2 = O::mul(lam, lam);
+    const T c2 = O::mul(f, O::bc(-2.0f)), c2x2 = O::mul(f, O::bc(-4.0f));
+    p2 = O::fma(O::bc(12.0f), l2, c2x2);
+    p1 = O::fma(O::fma(O::bc(4.0f), l2, c2x2), lam, c1);
+    p0 = O::fma(O::fma(O::add(l2, c2), lam, c1), lam, c0);
+}
+
 // margins of the three values over their tolerances: the pair is excluded iff lam, p1, m0, m1, m2 are all > 0
 template <class O>
 TSC_HD void quartic32_margins(typename O::T p0, typename O::T p1, typename O::T p2, typename O::T f, typename O::T lam,
@@ -217,6 +275,27 @@ TSC_HD bool quartic32_excluded(const float S[9], float f, float lam) {
     quartic32_values<OpsF32>(S, f, lam, p0, p1, p2);
     quartic32_margins<OpsF32>(p0, p1, p2, f, lam, m0, m1, m2);
     return quartic32_decide(lam, p1, m0, m1, m2);
+}
+
+// scalar form of the T-based test (host model / tests; the device runs the packed form of the same sequence)
+TSC_HD bool quartic32_T_excluded(const float t[6], float lam) {
+    float f, c0, da, p0, p1, p2, m0, m1, m2;
+    quartic32_T_coeffs<OpsF32>(t, f, c0, da);
+    const float d = sqrtf(da > 0.0f ? da : 0.0f);            // a NaN argument gives d = 0, but then f is NaN too: not excluded
+    quartic32_T_values<OpsF32>(f, c0, d, lam, p0, p1, p2);
+    quartic32_margins<OpsF32>(p0, p1, p2, f, lam, m0, m1, m2);
+    return quartic32_decide(lam, p1, m0, m1, m2);
+}
+
+// T = S^T S accumulated row by row as the component-sequential screen does (S row-major)
+TSC_HD void quartic32_T_from_rows(const float S[9], float t[6]) {
+    t[0] = OpsF32::mul(S[0], S[0]); t[1] = OpsF32::mul(S[1], S[1]); t[2] = OpsF32::mul(S[2], S[2]);
+    t[3] = OpsF32::mul(S[0], S[1]); t[4] = OpsF32::mul(S[0], S[2]); t[5] = OpsF32::mul(S[1], S[2]);
+    for (int a = 1; a < 3; a++) {
+        const float x = S[3 * a], y = S[3 * a + 1], z = S[3 * a + 2];
+        t[0] = OpsF32::fma(x, x, t[0]); t[1] = OpsF32::fma(y, y, t[1]); t[2] = OpsF32::fma(z, z, t[2]);
+        t[3] = OpsF32::fma(x, y, t[3]); t[4] = OpsF32::fma(x, z, t[4]); t[5] = OpsF32::fma(y, z, t[5]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -23,7 +23,7 @@ import functools
 
 # f16 / tf32 = tcgen05 pre-screen with the stationary operand in TMEM (FP16 or TF32 operands);
 # tf32ss = both operands from shared memory; dmma / fma = FP64 tensor cores / FMA pipe
-VARIANTS = {"dmma": 0, "fma": 1, "tf32": 2, "tf32ss": 3, "f16": 4}
+VARIANTS = {"dmma": 0, "fma": 1, "tf32": 2, "tf32ss": 3, "f16": 4, "screen": 5}
 
 
 _STAGING = {}
@@ -64,7 +64,17 @@ def _work_lists(N, rank, world, variant, device_str, n_ctas=0):
     dev = torch.device(device_str)
     rb = _host.owned_row_blocks(N, rank, world)
     out = {"row_blocks_np": rb, "row_blocks": torch.from_numpy(rb).to(dev)}
-    if variant in (2, 4):
+    if variant == 5:
+        # default screen (rmsd_screen.cu): j tiles of 32 conformers; one contiguous, equally expensive stretch of
+        # (panel, j tile) pairs per CTA of the persistent grid, plus the same per upload chunk
+        n_ctas = n_ctas if n_ctas > 0 else torch.cuda.get_device_properties(dev).multi_processor_count
+        items = np.ascontiguousarray(_host.build_screen_items(N, rb, n_ctas))
+        out["n_items"], out["items"], out["items_np"] = int(items.shape[0]), torch.from_numpy(items).to(dev), items
+        bounds = _upload_bounds(N)
+        chunks = [np.ascontiguousarray(_host.build_screen_items(N, rb, n_ctas, panel_lo=bounds[c], panel_hi=bounds[c + 1]))
+                  for c in range(len(bounds) - 1)]
+        out["chunk_items"] = [(torch.from_numpy(it).to(dev) if it.shape[0] else None, int(it.shape[0])) for it in chunks]
+    elif variant in (2, 4):
         # TMEM-operand screens: one contiguous, equally expensive stretch of (panel, j tile) pairs per CTA of the
         # persistent grid (the kernel deals array entries round-robin); plus the same per upload chunk
         n_ctas = n_ctas if n_ctas > 0 else torch.cuda.get_device_properties(dev).multi_processor_count
@@ -103,7 +113,7 @@ class RmsdPruner:
                  all-gather.
     """
 
-    def __init__(self, structures, atomnos, rmsd_thr=0.5, *, variant="f16", device=None,
+    def __init__(self, structures, atomnos, rmsd_thr=0.5, *, variant="screen", device=None,
                  rank=0, world=1, group=None, grid_ctas=0, ladder="fused", pair_cap=None, cand_cap=None,
                  pipeline_upload=True):
         torch = require_cuda()
@@ -143,7 +153,8 @@ class RmsdPruner:
         N, M = self.N, self.M
         self.nb_pad = _host.num_blocks_padded(N)
         self.W = self.nb_pad
-        if (self.variant in (2, 3) and M > TF32_MAX_M) or (self.variant == 4 and M > F16_MAX_M):
+        if (self.variant in (2, 3) and M > TF32_MAX_M) or (self.variant == 4 and M > F16_MAX_M) or \
+                (self.variant == 5 and M > int(lib().tsc_screen_max_atoms())):
             self.variant = 0             # documented fallback: FP64 tensor cores (include/tscode_b200.h)
         with torch.cuda.device(self.device):
             dev = self.device
@@ -156,6 +167,15 @@ class RmsdPruner:
             self.packed = torch.empty(max(_host.packed_doubles(N, max(M, 1)), 1), dtype=torch.float64, device=dev)
             n_g = max(self.nb_pad * _host.CB, _host.tf32_rows_padded(N))
             self.G = torch.empty(n_g, dtype=torch.float64, device=dev)
+            if self.variant == 5:
+                L = lib()
+                nbytes = max(int(L.tsc_screen_operand_bytes(N, max(M, 1))), 16)
+                self.PA = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                self.PB = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                self.PR = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                self.sG = torch.empty(n_g, dtype=torch.float64, device=dev)
+                self.G_side = torch.empty(n_g, dtype=torch.float64, device=dev)
+                self.CT = torch.empty(max(L.tsc_screen_ct_floats(N), 1), dtype=torch.float32, device=dev)
             if self.variant == 4:
                 L = lib()
                 nbytes = max(int(L.tsc_f16_operand_bytes(N, max(M, 1))), 16)
@@ -249,7 +269,7 @@ class RmsdPruner:
         L = lib()
         torch = self.torch
         with torch.cuda.device(self.device):
-            if self.variant == 4:
+            if self.variant in (4, 5):
                 # the FP64 tiled-SoA image is only read by verify: it is written on a side stream while the main
                 # stream goes on to the FP16 images and the screen (verify waits for the event)
                 main, side = torch.cuda.current_stream(), _copy_stream(str(self.device))
@@ -262,6 +282,10 @@ class RmsdPruner:
             else:
                 check(L.tsc_pack(ptr(self.S), self.N, self.A, ptr(self.heavy_idx), self.M, ptr(self.packed),
                                  ptr(self.G), stream_ptr()), "tsc_pack")
+            if self.variant == 5:
+                check(L.tsc_pack_screen(ptr(self.S), self.N, self.A, ptr(self.heavy_idx), self.M, ptr(self.PA),
+                                        ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG), ptr(self.CT), 0, 0,
+                                        stream_ptr()), "tsc_pack_screen")
             if self.variant == 4:
                 check(L.tsc_pack_f16(ptr(self.S), self.N, self.A, ptr(self.heavy_idx), self.M, ptr(self.PA),
                                      ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG), ptr(self.CT), stream_ptr()),
@@ -282,8 +306,13 @@ class RmsdPruner:
         L = lib()
         with self.torch.cuda.device(self.device):
             self.stats.zero_()
-            self.cand_list[0].fill_(0 if self.variant in (2, 4) else -1)      # -1: this screen writes no list
-            if self.variant == 4:
+            self.cand_list[0].fill_(0 if self.variant in (2, 4, 5) else -1)      # -1: this screen writes no list
+            if self.variant == 5:
+                check(L.tsc_rmsd_screen(ptr(self.PA), ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG),
+                                        ptr(self.CT), self.N, self.M, ptr(self.items), self.n_items, self.thr,
+                                        ptr(self.sim_bits), ptr(self.cand_list), self.cand_stride, self.grid_ctas,
+                                        stream_ptr()), "tsc_rmsd_screen")
+            elif self.variant == 4:
                 check(L.tsc_rmsd_sim_f16ts(ptr(self.PA), ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG),
                                            ptr(self.CT), self.N, self.M, ptr(self.items), self.n_items, self.thr,
                                            ptr(self.sim_bits), ptr(self.cand_list), self.cand_stride, self.grid_ctas,
@@ -472,7 +501,7 @@ class RmsdPruner:
         torch = self.torch
         host, N = self._host, self.N
         self._host = None                                # the next run() works from the device copy
-        if self.variant != 4 or N == 0 or self.M == 0:
+        if self.variant not in (4, 5) or N == 0 or self.M == 0:
             self._staging = None
             self.S.copy_(host)
             self.pack()
@@ -514,6 +543,17 @@ class RmsdPruner:
                 hi_pad = rows_pad if c == n_chunks - 1 else hi
                 check(L.tsc_pack_blocks(ptr(self.S), N, self.A, ptr(self.heavy_idx), self.M, ptr(self.packed), ptr(self.G),
                                         lo // 32, self.nb_pad if c == n_chunks - 1 else hi // 32, st), "tsc_pack_blocks")
+                if self.variant == 5:
+                    check(L.tsc_pack_screen(ptr(self.S), N, self.A, ptr(self.heavy_idx), self.M, ptr(self.PA), ptr(self.PB),
+                                            ptr(self.PR), ptr(self.G), ptr(self.sG), ptr(self.CT), lo, hi_pad, st),
+                          "tsc_pack_screen")
+                    it_dev, n_it = chunk_items[c]
+                    if n_it:
+                        check(L.tsc_rmsd_screen(ptr(self.PA), ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG),
+                                                ptr(self.CT), N, self.M, ptr(it_dev), n_it, self.thr, ptr(self.sim_bits),
+                                                ptr(self.cand_list), self.cand_stride, self.grid_ctas, st),
+                              "tsc_rmsd_screen")
+                    continue
                 check(L.tsc_pack_f16_rows(ptr(self.S), N, self.A, ptr(self.heavy_idx), self.M, ptr(self.PA), ptr(self.PB),
                                           ptr(self.PR), ptr(self.G), ptr(self.sG), ptr(self.CT), lo, hi_pad, st),
                       "tsc_pack_f16_rows")
