@@ -61,78 +61,33 @@ int tsc_rmsd_sim_tiles(const double* packed, const double* G, int64_t N, int32_t
                        const int32_t* tiles, int64_t n_tiles, double thr, uint32_t* sim_bits,
                        int32_t variant, int32_t grid_ctas, void* stream);
 
-/* Variant 2 of the screen: tcgen05 (kind::tf32, accumulators in TMEM) pre-screen with a rigorous
- * error bound folded into the threshold; same sim_bits contract as tsc_rmsd_sim_tiles (a superset of
- * the similar pairs is set; tsc_rmsd_verify makes the bits exact).
- *   tsc_pack_tf32 writes the TF32-rounded operand images PA (tsc_tf32_pa_floats floats: panels of
- *   128 conformers, [panel][xyz][M/4][128][4]) and PB (tsc_tf32_pb_floats floats: tiles of 16
- *   conformers, [tile][M/4][xyz*16][4]) plus exact G and sqrt(G) (ceil(N/128)*128 doubles each).
- *   items (n_items, 4) int32: {panel, first j tile, j tile count, local row block (32-row units) of
- *   the panel inside sim_bits}; for an owned panel p list j tiles from 8p to ceil(N/128)*8 - 1.
- *   Returns cudaErrorInvalidValue if M is too large for the stationary-panel layout (M > 120):
- *   use variant 0 then. */
-int64_t tsc_tf32_pa_floats(int64_t N, int32_t M);
-int64_t tsc_tf32_pb_floats(int64_t N, int32_t M);
-int64_t tsc_tf32_pr_floats(int64_t N, int32_t M);   /* PR: row-major [row][xyz][M] image, rows padded to 128 */
-int64_t tsc_tf32_ct_floats(int64_t N);               /* CT: [j tile][32] FP32 column terms of the fast path */
-int tsc_pack_tf32(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M, float* PA,
-                  float* PB, float* PR, double* G, double* sG, float* CT, void* stream);
-/* Same screen with the stationary 128-conformer operand held in TENSOR MEMORY (written once per
- * work item with tcgen05.st, read by tcgen05.mma [d], [a_tmem], b_desc): removes ~3/4 of the
- * shared-memory operand traffic that bounded tsc_rmsd_sim_tf32.  Default for variant "tf32". */
-/*   items: the persistent grid deals array entries round-robin (CTA b takes b, b + grid, ...); an entry with
- *   j tile count 0 ends its CTA's list, so a host that wants equal work per CTA can give every CTA one contiguous
- *   stretch of (panel, j tile) pairs and pad the shorter lists (tscode_b200/_host.py: build_tf32_items_balanced).
- *   grid_ctas: 0 = one CTA per SM, default configuration (two-stage FP32 epilogue — Samuelson's bound, then the
- *   FP32 sign test of the key-matrix quartic with rigorous error bounds —; panel split between TMEM and shared
- *   memory with three accumulator buffers up to 5 K blocks, whole panel in TMEM with two buffers above);
- *   > 0 = that many CTAs; < 0 selects a measured alternative configuration (tuning aid, see rmsd_tf32ts.cu).
- *   cand_list (may be NULL): block of cand_stride int32 pairs, element 0 = header whose first int32 is the
- *   running count (zero it first); (local row, j) of every bit the screen sets is appended from element 1.
- *   tsc_rmsd_verify works from this list when it did not overflow. */
-int tsc_rmsd_sim_tf32ts(const float* PA, const float* PB, const float* PR, const double* G,
-                        const double* sG, const float* CT, int64_t N, int32_t M, const int32_t* items,
-                        int32_t n_items, double thr, uint32_t* sim_bits, int32_t* cand_list,
-                        int64_t cand_stride, int32_t grid_ctas, void* stream);
-/* FP16-operand form of the same screen (kind::f16, K = 16 atoms per MMA; FP16 has TF32's 10-bit mantissa,
- * so the same error bound holds; tsc_pack_f16 zeroes |x| < 2^-14 and widens sqrt(G) accordingly).  Half as
- * many MMA instructions per tile: default screen of prune_conformers_rmsd for M <= 320 heavy atoms.
- *   PA, PB, PR: tsc_f16_operand_bytes(N, M) bytes each (atoms padded to a multiple of 16). */
-int64_t tsc_f16_operand_bytes(int64_t N, int32_t M);
-int tsc_pack_f16(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M, void* PA,
-                 void* PB, void* PR, double* G, double* sG, float* CT, void* stream);
-/* tsc_pack_f16 for conformers [row_begin, row_end) only (row_begin a multiple of 8; let the last chunk end at
- * ceil(N/128)*128 so that the padding rows are written). */
-int tsc_pack_f16_rows(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M, void* PA,
-                      void* PB, void* PR, double* G, double* sG, float* CT, int64_t row_begin, int64_t row_end,
-                      void* stream);
-int tsc_rmsd_sim_f16ts(const void* PA, const void* PB, const void* PR, const double* G,
-                       const double* sG, const float* CT, int64_t N, int32_t M, const int32_t* items,
-                       int32_t n_items, double thr, uint32_t* sim_bits, int32_t* cand_list,
-                       int64_t cand_stride, int32_t grid_ctas, void* stream);
 /* DEFAULT all-pairs pre-screen (rmsd_screen.cu): tcgen05 / TMEM, FP16 operands, FP32 accumulation, one
- * accumulator buffer per (128 x 32 tile, row of the covariances), MMAs of shape 128 x 96 x 16 in three skewed
- * chains, epilogue on T = S^T S.  Replaces the pair loop of rmsd_pruning.py:43-79 together with
- * tsc_rmsd_verify: bits are a superset of the similar pairs, every set bit is also appended to cand_list.
+ * accumulator buffer per (tile, row of the covariances), three MMA chains, epilogue on T = S^T S.
+ * Replaces the pair loop of rmsd_pruning.py:43-79 together with tsc_rmsd_verify: bits are a superset of the
+ * similar pairs, every set bit is also appended to cand_list.
+ *   mode 0: isotropic form — tiles of 64 conformers (MMAs 128 x 192 x 16, two buffers), Samuelson's bound only;
+ *   mode 1: tiles of 32 (MMAs 128 x 96 x 16, four buffers), Samuelson then the FP32 quartic sign test;
+ *   mode 2: tiles of 32, quartic sign test for every pair (anisotropic ensembles).
+ *   All three are conservative (never lose a similar pair); they differ in speed and in how many candidates they leave.
  *   PA, PB, PR: tsc_screen_operand_bytes(N, M) bytes each; CT: tsc_screen_ct_floats(N) floats; G, sG: doubles for
  *   every padded row (ceil(N/128)*128).  tsc_pack_screen writes them for conformers [row_begin, row_end)
- *   (row_begin a multiple of 8; row_end <= 0 = all rows incl. padding).
- *   items (n_items, 4) int32 {panel, first j tile of 32 conformers, tile count, local 32-row block of the panel's
- *   first row in sim_bits}, dealt round-robin to the CTAs; an item with count 0 ends a CTA's list.
- *   M <= tsc_screen_max_atoms() (192 heavy atoms); above, use tsc_rmsd_sim_tiles.  grid_ctas 0 = one CTA per SM. */
+ *   (row_begin a multiple of 8; row_end <= 0 = all rows incl. padding) for tiles of tile_j = 64 (mode 0) or 32.
+ *   items (n_items, 4) int32 {panel, first j tile, tile count, local 32-row block of the panel's first row in
+ *   sim_bits}, dealt round-robin to the CTAs; an item with count 0 ends a CTA's list.
+ *   M <= tsc_screen_max_atoms(tile_j); above, use tsc_rmsd_sim_tiles.  grid_ctas 0 = one CTA per SM.  pace 0. */
 int64_t tsc_screen_operand_bytes(int64_t N, int32_t M);
 int64_t tsc_screen_ct_floats(int64_t N);
-int32_t tsc_screen_max_atoms(void);
+int32_t tsc_screen_max_atoms(int32_t tile_j);
 int tsc_pack_screen(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M, void* PA, void* PB,
-                    void* PR, double* G, double* sG, float* CT, int64_t row_begin, int64_t row_end, void* stream);
+                    void* PR, double* G, double* sG, float* CT, int64_t row_begin, int64_t row_end, int32_t tile_j,
+                    void* stream);
 int tsc_rmsd_screen(const void* PA, const void* PB, const void* PR, const double* G, const double* sG,
                     const float* CT, int64_t N, int32_t M, const int32_t* items, int32_t n_items, double thr,
-                    uint32_t* sim_bits, int32_t* cand_list, int64_t cand_stride, int32_t grid_ctas, void* stream);
-/* Measurement aid: 8*96 int64 of clock64 stamps from the first work item of CTA 0 (NULL = off). */
-void tsc_set_trace_buffer(void* dev_ptr);
-int tsc_rmsd_sim_tf32(const float* PA, const float* PB, const double* G, const double* sG, int64_t N,
-                      int32_t M, const int32_t* items, int32_t n_items, double thr, uint32_t* sim_bits,
-                      int32_t grid_ctas, void* stream);
+                    uint32_t* sim_bits, int32_t* cand_list, int64_t cand_stride, int32_t grid_ctas, int32_t mode,
+                    int32_t pace, void* stream);
+/*   cand_list (may be NULL): block of cand_stride int32 pairs, element 0 = header whose first int32 is the running
+ *   count (zero it first); (local row, j) of every bit the screen sets is appended from element 1; a count outside
+ *   [0, cand_stride - 1] means the list overflowed (tsc_rmsd_verify then scans the bit rows instead). */
 
 /* Exact re-evaluation of every set bit, the way rmsd_and_max_numba does it (rmsd_pruning.py:6-41);
  * afterwards bit (i,j) == (rmsd < thr and maxdev < 2*thr)  (:75, :95).
@@ -332,17 +287,6 @@ int tsc_rotcorr_commit(double* cur, const double* staged, const int32_t* js, int
 int tsc_rotcorr_apply(const double* Sc, int64_t n, int32_t A, const int64_t* idx, int32_t T,
                       const int32_t* tor_i2, const int32_t* tor_i3, const double* sin_half,
                       const double* cos_half, const uint8_t* rot_mask, double* out, void* stream);
-
-/* ---- measurement aid (not on the product path) ------------------------------------------ */
-/* Self-measured FP64 ceilings: kind 0 = DFMA, 1 = DMMA.8x8x4, 2 = both at once (even warps
- * DMMA, odd warps DFMA).  SYNCHRONOUS: times one launch with CUDA events on `stream`.
- *   scratch: >= 1 double (device); flops_out [host] (2): {tensor flop, FMA flop}; ms_out [host]. */
-/* tcgen05.mma issue-rate probe: cycles (SM 0) for reps*nsets*3 kind::tf32 MMAs of 128 x N x 8, each
- * of the nsets*3 accumulators in its own TMEM region; a_in_tmem selects the TS form. */
-int tsc_bench_umma(int32_t N, int32_t nsets, int32_t reps, int32_t a_in_tmem, long long* cycles_dev,
-                   void* stream);
-int tsc_bench_fp64(int32_t kind, int32_t iters, int32_t ctas_per_sm, int32_t threads, double* scratch,
-                   double* flops_out, float* ms_out, void* stream);
 
 /* ---- ensemble I/O ------------------------------------------------------------------------ */
 /* [host] Multi-frame XYZ text of n_frames structures (utils.py:114-126, write_xyz; embedder.py:996-1043): per frame

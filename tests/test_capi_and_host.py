@@ -82,67 +82,61 @@ def test_tiles_cover_upper_triangle(N, world):
     for ib in range(nb):
         assert covered[ib, ib:].all()            # every word >= ib of every row block is written
     assert total == sum(nbp // 2 - ib // 2 for ib in range(nb))
-    # tcgen05 work items: every 16-column tile right of a panel's first row, exactly once
-    njt = ((N + 127) // 128) * 8
-    seen = set()
-    for rank in range(world):
-        rb = _host.owned_row_blocks(N, rank, world)
-        for p, j0, cnt, lb in _host.build_tf32_items(N, rb):
-            assert rb[lb] == 4 * p and cnt >= 1
-            for jt in range(j0, j0 + cnt):
-                assert (p, jt) not in seen
-                seen.add((p, jt))
-    assert seen == {(p, jt) for p in range((N + 127) // 128) for jt in range(8 * p, njt)}
-    # the balanced form (one contiguous stretch per CTA, dealt round-robin): same coverage; empty items only at the
-    # end of a CTA's list (the kernel stops at the first one)
-    for n_ctas in (148, 5):
+    # work items of the tcgen05 screen, for both tile widths: every j tile right of a panel's first row exactly once;
+    # one contiguous stretch per CTA, dealt round-robin; empty items only at the end of a CTA's list (the kernel stops
+    # at the first one)
+    for tile_j in (32, 64):
+        tpp = 128 // tile_j
+        njt = ((N + 127) // 128) * tpp
+        for n_ctas in (148, 5):
+            seen = set()
+            for rank in range(world):
+                rb = _host.owned_row_blocks(N, rank, world)
+                items = _host.build_screen_items(N, rb, n_ctas, tile_j=tile_j)
+                g = min(n_ctas, len(items))
+                for b in range(g):
+                    mine = items[b::g]
+                    live = mine[:, 2] > 0
+                    assert not live[np.argmin(live):].any() or live.all()
+                for p, j0, cnt, lb in items:
+                    assert rb[lb] == 4 * p and cnt >= 0
+                    for jt in range(j0, j0 + cnt):
+                        assert (p, jt) not in seen
+                        seen.add((p, jt))
+            assert seen == {(p, jt) for p in range((N + 127) // 128) for jt in range(tpp * p, njt)}
+        # ... and restricted to panel ranges (the sub-launches of the pipelined upload) the pieces tile the whole
         seen = set()
-        for rank in range(world):
-            rb = _host.owned_row_blocks(N, rank, world)
-            items = _host.build_tf32_items_balanced(N, rb, n_ctas)
-            g = min(n_ctas, len(items))
-            for b in range(g):
-                mine = items[b::g]
-                live = mine[:, 2] > 0
-                assert not live[np.argmin(live):].any() or live.all()
-            for p, j0, cnt, lb in items:
-                assert rb[lb] == 4 * p and cnt >= 0
+        rb = _host.owned_row_blocks(N, 0, 1)
+        n_panels = (N + 127) // 128
+        cuts = sorted({0, n_panels // 3, n_panels // 2, n_panels})
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            for p, j0, cnt, lb in _host.build_screen_items(N, rb, 148, panel_lo=lo, panel_hi=hi, tile_j=tile_j):
+                assert lo <= p < hi or cnt == 0
                 for jt in range(j0, j0 + cnt):
                     assert (p, jt) not in seen
                     seen.add((p, jt))
-        assert seen == {(p, jt) for p in range((N + 127) // 128) for jt in range(8 * p, njt)}
-    # ... and restricted to panel ranges (the sub-launches of the pipelined upload) the pieces tile the whole
-    seen = set()
-    rb = _host.owned_row_blocks(N, 0, 1)
-    n_panels = (N + 127) // 128
-    cuts = sorted({0, n_panels // 3, n_panels // 2, n_panels})
-    for lo, hi in zip(cuts[:-1], cuts[1:]):
-        for p, j0, cnt, lb in _host.build_tf32_items_balanced(N, rb, 148, panel_lo=lo, panel_hi=hi):
-            assert lo <= p < hi or cnt == 0
-            for jt in range(j0, j0 + cnt):
-                assert (p, jt) not in seen
-                seen.add((p, jt))
-    assert seen == {(p, jt) for p in range(n_panels) for jt in range(8 * p, njt)}
+        assert seen == {(p, jt) for p in range(n_panels) for jt in range(tpp * p, njt)}
 
 
 def test_row_sharding_is_balanced():
     N = 50000
     loads = [len(_host.build_tiles(N, _host.owned_row_blocks(N, r, 8))) for r in range(8)]
     assert max(loads) / min(loads) < 1.005
-    items = [_host.build_tf32_items(N, _host.owned_row_blocks(N, r, 8))[:, 2].sum() for r in range(8)]
+    items = [_host.build_screen_items(N, _host.owned_row_blocks(N, r, 8), 148)[:, 2].sum() for r in range(8)]
     assert max(items) / min(items) < 1.005
-    # inside a rank: cost (tiles + 3 per item) per CTA of the persistent grid, full launch and upload sub-launches
-    def cta_loads(items, g=148):
-        return np.array([items[b::g, 2].sum() + 3.0 * (items[b::g, 2] > 0).sum() for b in range(g)])
+    # inside a rank: cost (tiles + 2.5 per item) per CTA of the persistent grid, full launch and upload sub-launches
+    def cta_loads(items, g=148, cost=2.5):
+        return np.array([items[b::g, 2].sum() + cost * (items[b::g, 2] > 0).sum() for b in range(g)])
     for world in (1, 8):
         rb = _host.owned_row_blocks(N, 0, world)
-        loads = cta_loads(_host.build_tf32_items_balanced(N, rb, 148))
-        assert loads.max() / loads.mean() < 1.01
+        for tile_j in (32, 64):
+            loads = cta_loads(_host.build_screen_items(N, rb, 148, tile_j=tile_j), cost=2.5 * 32 / tile_j)
+            assert loads.max() / loads.mean() < 1.02, (world, tile_j, loads.max() / loads.mean())
     rb = _host.owned_row_blocks(N, 0, 1)
     n_panels = (N + 127) // 128
     for c in range(8):
-        loads = cta_loads(_host.build_tf32_items_balanced(N, rb, 148, panel_lo=n_panels * c // 8, panel_hi=n_panels * (c + 1) // 8))
-        assert loads.max() / loads.mean() < 1.05
+        loads = cta_loads(_host.build_screen_items(N, rb, 148, panel_lo=n_panels * c // 8, panel_hi=n_panels * (c + 1) // 8))
+        assert loads.max() / loads.mean() < (1.06 if c < 6 else 1.25), (c, loads.max() / loads.mean())   # (the last chunks are tiny)
 
 
 def test_ladder_schedule_matches_reference_rule():
@@ -264,7 +258,6 @@ def test_balanced_items_dealt_like_the_kernel_cover_every_tile_once(N):
     simulate exactly that for whole launches and for the sub-launches of the pipelined upload, several ranks and
     grid sizes (incl. grids larger than the number of stretches: the layout stride must then be the grid)."""
     from tscode_b200.rmsd_pruning import _upload_bounds
-    njt = ((N + 127) // 128) * 8
     n_panels = (N + 127) // 128
     pb = _upload_bounds(N)
     ranges = [(0, None)] + [(pb[c], pb[c + 1]) for c in range(len(pb) - 1)]
@@ -274,8 +267,11 @@ def test_balanced_items_dealt_like_the_kernel_cover_every_tile_once(N):
             own = [int(ib // 4) for ib in rb if ib % 4 == 0]
             for n_ctas in (148, 132, 5):
                 for lo, hi in ranges:
-                    h = n_panels if hi is None else hi
-                    want = {(p, jt) for p in own if lo <= p < h for jt in range(8 * p, njt)}
-                    items = _host.build_tf32_items_balanced(N, rb, n_ctas, panel_lo=lo, panel_hi=hi)
-                    seen = _deal_like_the_kernel(items, n_ctas)
-                    assert set(seen) == want and all(v == 1 for v in seen.values()), (N, world, rank, n_ctas, lo, hi)
+                    for tile_j in (32, 64):
+                        tpp = 128 // tile_j
+                        njt = n_panels * tpp
+                        h = n_panels if hi is None else hi
+                        want = {(p, jt) for p in own if lo <= p < h for jt in range(tpp * p, njt)}
+                        items = _host.build_screen_items(N, rb, n_ctas, panel_lo=lo, panel_hi=hi, tile_j=tile_j)
+                        seen = _deal_like_the_kernel(items, n_ctas)
+                        assert set(seen) == want and all(v == 1 for v in seen.values()), (N, world, rank, n_ctas, lo, hi, tile_j)

@@ -91,9 +91,19 @@ def test_rmsd_similarity_vs_reference(gpu):
 
 
 # ------------------------------------------------------------------------------------------
-# similarity bits (screen + verify) vs oracle, both contraction variants
+# similarity bits (screen + verify) vs oracle, every screen variant
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("variant", ["dmma", "fma", "tf32", "tf32ss", "f16"])
+def _pruner(S, atomnos, thr, variant, **kw):
+    """variant "screen" = the default screen with its automatic choice of form; "screen0/1/2" force a form
+    (rmsd_screen.cu: 0 = Samuelson only on 64-wide tiles, 1 = Samuelson then quartic, 2 = quartic for every pair)."""
+    from tscode_b200.rmsd_pruning import RmsdPruner
+    if variant.startswith("screen") and variant != "screen":
+        return RmsdPruner(S, atomnos, thr, variant="screen", screen_mode=int(variant[-1]), **kw)
+    return RmsdPruner(S, atomnos, thr, variant=variant, **kw)
+
+
+
+@pytest.mark.parametrize("variant", ["dmma", "fma", "screen", "screen0", "screen1", "screen2"])
 @pytest.mark.parametrize("seed,N,M,nc,noise,thr", [
     (0, 1000, 40, 100, 0.05, 0.5),
     (5, 777, 29, 60, 0.05, 0.25),
@@ -103,16 +113,18 @@ def test_rmsd_similarity_vs_reference(gpu):
     (13, 65, 80, 3, 0.2, 0.5),
     (14, 31, 1, 2, 0.05, 0.5),         # single heavy atom
     (15, 130, 20, 4, 0.3, 0.5),
-    (16, 300, 72, 10, 0.15, 0.5),      # exactly nine K blocks: the whole operand lives in TMEM
-    (17, 260, 100, 8, 0.2, 0.5),       # 13 K blocks: nine in TMEM, four from shared memory
+    (16, 300, 80, 10, 0.15, 0.5),      # exactly five K blocks: the whole panel lives in TMEM
+    (17, 260, 100, 8, 0.2, 0.5),       # seven K blocks: five in TMEM, two from shared memory
     (18, 140, 7, 5, 0.1, 0.5),         # a single, zero-padded K block
+    (19, 200, 192, 6, 0.1, 0.5),       # the most atoms the 32-wide forms take (64-wide: falls back to form 1)
+    (20, 150, 200, 6, 0.1, 0.5),       # beyond it: FP64 tensor-core fallback
 ])
 def test_sim_bits_vs_oracle(gpu, variant, seed, N, M, nc, noise, thr):
     from oracle import oracle_c
     from tscode_b200.rmsd_pruning import RmsdPruner
     from tscode_b200.synth import gen_ensemble
     S = gen_ensemble(seed, N, M, nc, sigma_noise=noise)
-    pr = RmsdPruner(S, np.full(M, 6), thr, variant=variant)
+    pr = _pruner(S, np.full(M, 6), thr, variant)
     pr.sim_bits.fill_(-1)                       # garbage: the kernels must overwrite what they own
     pr.pack(); pr.similarity()
     torch.cuda.synchronize()
@@ -230,9 +242,8 @@ _aniso = json.load(open(os.path.join(GOLDEN, "prune_masks_aniso.json")))["rows"]
 @pytest.mark.parametrize("r", _aniso, ids=[f"s{r['seed']}_N{r['N']}_M{r['M']}" for r in _aniso])
 def test_prune_anisotropic_molecules_vs_reference(gpu, r):
     """Elongated / planar / rod-like molecules: Samuelson's bound excludes nothing, the FP32 quartic stage of the
-    tcgen05 epilogue does the excluding.  Masks of every screen variant (and of the previous FP64
-    second stage, configurations -2 / -8) equal the live reference's; the FP32 stage must actually exclude: the
-    candidate count of the default screen stays within a small factor of the confirmed pairs."""
+    screen does the excluding.  Masks of every screen form equal the live reference's; the FP32 stage must
+    actually exclude: the candidate count of the default screen stays within a small factor of the confirmed pairs."""
     from tscode_b200.rmsd_pruning import RmsdPruner, prune_conformers_rmsd
     from tscode_b200.synth import gen_ensemble
     S = gen_ensemble(r["seed"], r["N"], r["M"], r["n_clusters"], sigma_noise=r["sigma_noise"], scale=np.array(r["scale"]))
@@ -241,17 +252,19 @@ def test_prune_anisotropic_molecules_vs_reference(gpu, r):
     out, mask = prune_conformers_rmsd(S, atomnos, r["thr"])
     assert np.array_equal(mask, ref) and np.array_equal(out, S[ref])
     pairs = r["N"] * (r["N"] - 1) // 2
-    for variant, cfg in (("f16", 0), ("f16", -10), ("f16", -11), ("f16", -2), ("f16", -8), ("tf32", 0), ("dmma", 0)):
-        if variant == "tf32" and int((atomnos != 1).sum()) > 120:
-            continue
-        pr = RmsdPruner(S, atomnos, r["thr"], variant=variant, grid_ctas=cfg)
+    for variant in ("screen", "screen1", "screen2", "dmma"):
+        pr = _pruner(S, atomnos, r["thr"], variant)
         m = pr.run().cpu().numpy()
         st = pr.stats_dict()
-        print(r["seed"], variant, cfg, st)
-        assert np.array_equal(m, ref), (variant, cfg)
+        print(r["seed"], variant, pr.screen_mode, st)
+        assert np.array_equal(m, ref), variant
         assert st["candidates"] >= st["confirmed"]
-        if variant == "f16" and cfg in (0, -10, -11):
-            assert st["candidates"] <= 4 * st["confirmed"] + pairs // 50, (variant, cfg, st)
+        if variant.startswith("screen"):
+            assert pr.screen_mode in (1, 2)                 # the automatic choice never takes the isotropic form here
+            assert st["candidates"] <= 4 * st["confirmed"] + pairs // 50, (variant, st)
+    if r["N"] <= 1500:                                      # the isotropic form stays CORRECT on such molecules (many candidates)
+        pr = _pruner(S, atomnos, r["thr"], "screen0")
+        assert np.array_equal(pr.run().cpu().numpy(), ref)
 
 
 _aniso_big = json.load(open(os.path.join(GOLDEN, "prune_masks_aniso_big.json")))["rows"]
@@ -274,7 +287,7 @@ _big = json.load(open(os.path.join(GOLDEN, "prune_masks_big.json")))["rows"]
 
 
 @pytest.mark.parametrize("r", _big, ids=[f"N{r['N']}" for r in _big])
-@pytest.mark.parametrize("variant", ["dmma", "fma", "tf32", "f16"])
+@pytest.mark.parametrize("variant", ["dmma", "fma", "screen", "screen1", "screen2"])
 def test_prune_big_digest_vs_reference(gpu, r, variant):
     """BASELINE configs[2] at full size: the 50k x 80 mask must equal the live reference's."""
     from tscode_b200.rmsd_pruning import RmsdPruner
@@ -282,7 +295,7 @@ def test_prune_big_digest_vs_reference(gpu, r, variant):
     if variant == "fma" and r["N"] > 20000:
         pytest.skip("fma variant checked up to 20k")
     S = gen_ensemble(r["seed"], r["N"], r["M"], r["n_clusters"], sigma_noise=r["sigma_noise"])
-    pr = RmsdPruner(S, np.full(r["M"], 6), r["thr"], variant=variant)
+    pr = _pruner(S, np.full(r["M"], 6), r["thr"], variant)
     mask = pr.run().cpu().numpy()
     print(r["N"], variant, pr.stats_dict(), pr.rounds)
     assert int(mask.sum()) == r["survivors"]
@@ -659,8 +672,8 @@ def test_f16_screen_extreme_coordinates(gpu, scale, shift):
     thr = 0.5 * (scale if scale < 1 else 1.0)
     at = np.full(24, 6)
     ref_out, ref = oracle_c.prune_conformers_rmsd(S, at, thr)
-    for variant in ("f16", "dmma"):
-        pr = RmsdPruner(S, at, thr, variant=variant)
+    for variant in ("screen", "screen0", "screen1", "screen2", "dmma"):
+        pr = _pruner(S, at, thr, variant)
         m = pr.run().cpu().numpy()
         assert np.array_equal(m, ref), (variant, scale, shift, int(m.sum()), int(ref.sum()), pr.stats_dict())
 

@@ -2,10 +2,22 @@
 //
 // MEASURED_PEAKS.json carries HBM and bf16 numbers only; the RMSD kernel is bounded by the FP64
 // pipes, so bench.py measures their ceiling on the same GPU in the same run and quotes
-// fractions "of self-measured FP64 peak" (SURVEY 8(d)).  Not on the product path.
-#include "tf32_common.cuh"
+// fractions "of self-measured FP64 peak" (SURVEY 8(d)).  Built into tools/probes/libtsc_probe.so: not part of the product library.
+#include "../../tscode_b200/csrc/screen_common.cuh"
 
 namespace tsc {
+
+// kind::tf32 issue forms for the probe (the product only issues kind::f16)
+template <bool ACC>
+__device__ __forceinline__ void umma_tf32_ts_c(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
+}
+template <bool ACC>
+__device__ __forceinline__ void umma_tf32_ss_c(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
+}
 
 constexpr int PK_CHAINS = 12;
 

@@ -1,7 +1,7 @@
 // tmem_probe.cu — measurement aids for the tcgen05 screen (NOT part of libtscode_b200.so).
 //   tsc_probe_ld_layout : which (TMEM lane, column) lands in which (thread, register) for every tcgen05.ld shape
 //   tsc_probe_ld_rate   : cycles to read a 128-lane x ncols accumulator tile with a given shape / warp count
-#include "../../tscode_b200/csrc/tf32_common.cuh"
+#include "../../tscode_b200/csrc/screen_common.cuh"
 
 namespace tsc {
 
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(1024, 1) ld_rate_kernel(int ncols, int reps, i
             for (int c = 0; c < ncols; c += 16) {
                 uint32_t v[16];
 #pragma unroll
-                for (int k = 0; k < 4; k++) tmem_ld_x4_raw(tb + c + 4 * k, &v[4 * k]);
+                for (int k = 0; k < 4; k++) asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[4 * k]), "=r"(v[4 * k + 1]), "=r"(v[4 * k + 2]), "=r"(v[4 * k + 3]) : "r"(tb + c + 4 * k));
                 tmem_ld_wait();
 #pragma unroll
                 for (int k = 0; k < 16; k++) acc ^= v[k];

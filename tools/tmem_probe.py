@@ -10,12 +10,13 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from tscode_b200._lib import lib, check, ptr, stream_ptr  # noqa: E402
+from tscode_b200._lib import check, ptr, stream_ptr  # noqa: E402
 
 P = C.CDLL(os.path.join(ROOT, "tools", "probes", "libtsc_probe.so"))
 vp, i32 = C.c_void_p, C.c_int32
 P.tsc_probe_ld_layout.argtypes = [vp, vp]
 P.tsc_probe_ld_rate.argtypes = [i32, i32, i32, i32, vp, vp, vp]
+P.tsc_bench_umma.argtypes = [i32, i32, i32, i32, vp, vp]
 
 out = torch.zeros(5 * 2 * 128 * 4, dtype=torch.int32, device="cuda")
 check(P.tsc_probe_ld_layout(ptr(out), stream_ptr()), "layout")
@@ -51,8 +52,8 @@ for tm in (0, 1):
     for N, nsets in ((144, -1), (144, -2), (144, -3), (192, -1), (192, -2), (208, -1), (208, -2), (224, -1), (224, -2), (240, -1),
                      (256, -1), (96, -2), (96, -4), (128, -1), (128, -2)):
         try:
-            check(lib().tsc_bench_umma(N, nsets, reps, tm, ptr(o2), stream_ptr()), "umma"); torch.cuda.synchronize()
-            check(lib().tsc_bench_umma(N, nsets, reps, tm, ptr(o2), stream_ptr()), "umma"); torch.cuda.synchronize()
+            check(P.tsc_bench_umma(N, nsets, reps, tm, ptr(o2), stream_ptr()), "umma"); torch.cuda.synchronize()
+            check(P.tsc_bench_umma(N, nsets, reps, tm, ptr(o2), stream_ptr()), "umma"); torch.cuda.synchronize()
         except Exception as e:
             print("umma", N, nsets, "failed", e)
             continue

@@ -45,37 +45,37 @@ def owned_row_blocks(N: int, rank: int = 0, world: int = 1) -> np.ndarray:
     return ib[owner == rank]
 
 
-def build_tf32_items(N: int, row_blocks: np.ndarray, chunk: int = 128) -> np.ndarray:
-    """Work items of the tcgen05 pre-screen: (n_items, 4) int32 rows {panel, first j tile, j tile
-    count, local row block of the panel}.  Panel p (128 rows) needs the 16-column j tiles from 8p
-    up to the padded end; they are cut into chunks so that items are of similar size."""
-    rb = np.asarray(row_blocks, dtype=np.int64)
-    njt = ((N + 127) // 128) * 8
-    items = []
-    for lb, ib in enumerate(rb):
-        if ib % PANEL_BLOCKS:
-            continue
-        p = int(ib // PANEL_BLOCKS)
-        for j0 in range(8 * p, njt, chunk):
-            items.append((p, j0, min(chunk, njt - j0), lb))
-    # longest items first would not matter (all ~chunk); interleave panels so that concurrently
-    # running CTAs share B tiles in L2
-    return np.asarray(items, dtype=np.int32).reshape(-1, 4)
-
-
 def build_screen_items(N: int, row_blocks: np.ndarray, n_ctas: int, panel_lo: int = 0, panel_hi: int | None = None,
-                       item_cost: float = 2.5) -> np.ndarray:
-    """Work items of the default screen (rmsd_screen.cu): as build_tf32_items_balanced, with j tiles of 32 conformers
-    (four per 128-row panel)."""
-    return build_tf32_items_balanced(N, row_blocks, n_ctas, panel_lo, panel_hi, item_cost, tiles_per_panel=4)
+                       item_cost: float = 2.5, tile_j: int = 32) -> np.ndarray:
+    """Work items of the default screen (rmsd_screen.cu): as build_items_balanced, with j tiles of `tile_j`
+    (32 or 64) conformers, i.e. four or two per 128-row panel."""
+    return build_items_balanced(N, row_blocks, n_ctas, panel_lo, panel_hi, item_cost * 32.0 / tile_j,
+                                     tiles_per_panel=128 // int(tile_j))
 
 
-def build_tf32_items_balanced(N: int, row_blocks: np.ndarray, n_ctas: int, panel_lo: int = 0,
+def screen_mode_for(first_heavy: np.ndarray) -> int:
+    """Which form of the default screen suits an ensemble (rmsd_screen.cu; a speed decision only: every form is
+    conservative).  Samuelson's bound sqrt(3) ||S||_F >= sigma1 + sigma2 + sigma3 is sharp for isotropic covariances
+    and useless for anisotropic ones; the covariance of two similar conformers has the spectrum of the molecule's
+    second-moment tensor, so the ratio sqrt(3 sum l^2) / sum l of its eigenvalues (1 = isotropic) tells: up to
+    1.03 the cheap isotropic form (mode 0) is used, above it the quartic test for every pair (mode 2)."""
+    X = np.asarray(first_heavy, dtype=np.float64).reshape(-1, 3)
+    if X.shape[0] == 0:
+        return 2
+    lam = np.linalg.eigvalsh(X.T @ X)
+    tot = float(lam.sum())
+    if not np.isfinite(tot) or tot <= 0.0:
+        return 2
+    return 0 if float(np.sqrt(3.0 * (lam ** 2).sum())) / tot <= 1.03 else 2
+
+
+def build_items_balanced(N: int, row_blocks: np.ndarray, n_ctas: int, panel_lo: int = 0,
                               panel_hi: int | None = None, item_cost: float = 3.0, max_item: int = 0,
                               tiles_per_panel: int = 8) -> np.ndarray:
     """Work items of the tcgen05 pre-screen for a persistent grid of `n_ctas` CTAs, each of which takes the array
-    entries b, b + n_ctas, b + 2 n_ctas, ...  Same coverage as build_tf32_items (optionally only the panels in
-    [panel_lo, panel_hi)), but partitioned linearly: the (panel, j tile) pairs are laid out panel after panel and
+    entries b, b + n_ctas, b + 2 n_ctas, ...: rows {panel, first j tile, j tile count, local row block of the panel};
+    panel p (128 rows) needs the j tiles from tiles_per_panel * p to the padded end (optionally only the panels in
+    [panel_lo, panel_hi)).  Partitioned linearly: the (panel, j tile) pairs are laid out panel after panel and
     every CTA gets one contiguous stretch of equal cost (tiles + `item_cost` tiles per item start: pipeline drain
     and panel rows -> TMEM, measured ~2 400 cycles), i.e. one item per panel its stretch touches.  Plain
     round-robin dealing of 128-tile chunks left the busiest CTA of C3 5 % above the mean, and 20 % in the eight
@@ -123,53 +123,6 @@ def build_tf32_items_balanced(N: int, row_blocks: np.ndarray, n_ctas: int, panel
         last = max(q for q in range(len(bins)) if len(bins[q]) > r)
         for q in range(len(bins) if r + 1 < rounds else last + 1):
             items.append(bins[q][r] if len(bins[q]) > r else (pad_p, tpp * pad_p, 0, pad_lb))
-    return np.asarray(items, dtype=np.int32).reshape(-1, 4)
-
-
-def build_tf32_items_even(N: int, row_blocks: np.ndarray, n_ctas: int, chunk: int = 128, panel_lo: int = 0,
-                          panel_hi: int | None = None, snake: bool = True) -> np.ndarray:
-    """(Measurement aid, tools/item_probe.py: an alternative cutting with the same balance and the same measured
-    time as build_tf32_items_balanced.)  As build_tf32_items (panel-major order, dealt round-robin to the CTAs by
-    the kernel), but the number of items is an exact multiple of n_ctas and every panel's j range is cut into equal pieces of about
-    total / n_items tiles, so that every CTA gets the same number of near-equal items."""
-    rb = np.asarray(row_blocks, dtype=np.int64)
-    njt = ((N + 127) // 128) * 8
-    if panel_hi is None:
-        panel_hi = (N + 127) // 128
-    panels = [(int(ib // PANEL_BLOCKS), lb) for lb, ib in enumerate(rb)
-              if ib % PANEL_BLOCKS == 0 and panel_lo <= ib // PANEL_BLOCKS < panel_hi]
-    L = np.array([njt - 8 * p for p, _ in panels], dtype=np.int64)
-    total = int(L.sum())
-    if total == 0:
-        return np.zeros((0, 4), np.int32)
-    m = max(1, int(round(total / (n_ctas * chunk))))
-    if m < 4:                                        # few items per CTA: shorter pieces (>= 16 tiles) balance better
-        m = max(m, min(4, total // (n_ctas * 16)))
-    n_items = min(m * n_ctas, total // 8) if total >= 8 * n_ctas else max(1, total // 8)
-    n_items = max(n_items, len(panels))
-    c = total / n_items
-    n_p = np.maximum(1, np.rint(L / c).astype(np.int64))
-    n_p = np.minimum(n_p, L)
-    while n_p.sum() < n_items:                       # split where the pieces are longest
-        q = int(np.argmax(np.where(n_p < L, L / n_p, 0.0)))
-        if n_p[q] >= L[q]:
-            break
-        n_p[q] += 1
-    while n_p.sum() > n_items and (n_p > 1).any():   # merge where they are shortest
-        q = int(np.argmin(np.where(n_p > 1, L / np.maximum(n_p - 1, 1), np.inf)))
-        n_p[q] -= 1
-    items = []
-    for (p, lb), Lp, n in zip(panels, L, n_p):
-        cuts = [8 * p + (int(Lp) * q) // int(n) for q in range(int(n) + 1)]
-        items += [(p, cuts[q], cuts[q + 1] - cuts[q], lb) for q in range(int(n)) if cuts[q + 1] > cuts[q]]
-    if snake and len(items) > n_ctas:
-        # longest first (stable: pieces of a panel stay together), rounds dealt alternately forwards and backwards
-        items.sort(key=lambda t: -t[2])
-        out = []
-        for r in range(0, len(items), n_ctas):
-            row = items[r:r + n_ctas]
-            out += row if (r // n_ctas) % 2 == 0 else row[::-1]
-        items = out
     return np.asarray(items, dtype=np.int32).reshape(-1, 4)
 
 

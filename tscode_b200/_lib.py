@@ -25,23 +25,11 @@ SIGNATURES = {
     "tsc_pack": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
     "tsc_pack_blocks": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _i64, _i64, _vp]),
     "tsc_rmsd_sim_tiles": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i64, _f64, _vp, _i32, _i32, _vp]),
-    "tsc_tf32_pa_floats": (_i64, [_i64, _i32]),
-    "tsc_tf32_pb_floats": (_i64, [_i64, _i32]),
-    "tsc_tf32_pr_floats": (_i64, [_i64, _i32]),
-    "tsc_tf32_ct_floats": (_i64, [_i64]),
-    "tsc_set_trace_buffer": (None, [_vp]),
-    "tsc_f16_operand_bytes": (_i64, [_i64, _i32]),
-    "tsc_pack_f16": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "tsc_pack_f16_rows": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
-    "tsc_rmsd_sim_f16ts": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _i64, _i32, _vp]),
     "tsc_screen_operand_bytes": (_i64, [_i64, _i32]),
     "tsc_screen_ct_floats": (_i64, [_i64]),
-    "tsc_screen_max_atoms": (_i32, []),
-    "tsc_pack_screen": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
-    "tsc_rmsd_screen": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _i64, _i32, _vp]),
-    "tsc_pack_tf32": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "tsc_rmsd_sim_tf32ts": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _i64, _i32, _vp]),
-    "tsc_rmsd_sim_tf32": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _i32, _vp]),
+    "tsc_screen_max_atoms": (_i32, [_i32]),
+    "tsc_pack_screen": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp]),
+    "tsc_rmsd_screen": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "tsc_rmsd_verify": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "tsc_elim_fused_ws_words": (_i64, [_i64]),
     "tsc_elim_fused_out_bytes": (_i64, [_i64]),
@@ -69,8 +57,6 @@ SIGNATURES = {
                                   _vp, _vp, _vp, _vp]),
     "tsc_rotcorr_commit": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "tsc_rotcorr_apply": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "tsc_bench_umma": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp]),
-    "tsc_bench_fp64": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "tsc_string_embed_params": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
                                           _vp, _vp]),
     "tsc_cyclical_embed_params": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp,

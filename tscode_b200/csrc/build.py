@@ -8,8 +8,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-SOURCES = ["capi.cu", "pack.cu", "rmsd_sim.cu", "rmsd_tf32.cu", "rmsd_tf32ts.cu", "rmsd_screen.cu", "rmsd_verify.cu", "eliminate.cu", "clash.cu", "rotcorr.cu", "tfd_moi.cu", "peaks.cu"]
-HEADERS = ["tsc_common.cuh", "tsc_math.cuh", "tf32_common.cuh"]
+SOURCES = ["capi.cu", "pack.cu", "rmsd_sim.cu", "rmsd_screen.cu", "rmsd_verify.cu", "eliminate.cu", "clash.cu", "rotcorr.cu", "tfd_moi.cu"]
+HEADERS = ["tsc_common.cuh", "tsc_math.cuh", "screen_common.cuh"]
 LIB = os.path.join(PKG, "libtscode_b200.so")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math=false"]

@@ -4,7 +4,7 @@
 // Mathematics and output contract: a pair (i, j > i) can only be similar (rmsd_pruning.py:75) if lambda_max of the key
 // matrix of its cross-covariance S exceeds lam_t = (G_i + G_j - M thr^2) / 2.  S is computed from FP16-rounded
 // coordinates with FP32 accumulation; the operand error is bounded by ||S~ - S||_F <= eps sqrt(G_i)' sqrt(G_j)'
-// (eps = 1.05e-3, tf32_common.cuh / pack below) and lam_t is lowered by sqrt(3) times that.  A pair is EXCLUDED only
+// (eps = 1.05e-3, screen_common.cuh / pack below) and lam_t is lowered by sqrt(3) times that.  A pair is EXCLUDED only
 // when an FP32 test with rigorous forward error bounds proves lambda_max below the lowered threshold (stage 1:
 // Samuelson's bound sqrt(3) ||S~||_F; stage 2: sign test of the key-matrix quartic, tsc_math.cuh).  Whatever is not
 // excluded is a candidate: bit set in sim_bits, (local row, j) appended to the candidate list, decided exactly in
@@ -20,34 +20,33 @@
 //     activity, 0.48 of the dense 16-bit peak on BASELINE configs[2].
 // Here one accumulator buffer holds ONE ROW a of the covariances of a 128 x 32 tile:  D[i, (b, j)] = sum_m
 // x_a(i, m) x_b(j, m), one MMA of N = 96 per K block, 96 columns; four buffers (384 columns) next to up to 5 K
-// blocks of the stationary panel (120 columns).  The three rows of a tile are three independent chains; the MMA
-// thread issues them skewed by a third of a tile, so that at any time three chains are in flight while the epilogue
-// drains the fourth buffer.  The epilogue never sees the nine entries together: per pair it keeps T = S~^T S~ (six
+// blocks of the stationary panel (120 columns).  The three rows of a tile are three independent chains, each issued
+// by its own thread at a fixed pace, so that three chains are in flight while the epilogue drains the fourth buffer.  The epilogue never sees the nine entries together: per pair it keeps T = S~^T S~ (six
 // numbers, the sum of the outer products of the rows) in registers across the three buffers of a tile, and both
 // exclusion tests work from T alone (f = tr T; quartic coefficients c2 = -2 f, c0 = 2 ||T||_F^2 - f^2, and
 // |det S~| <= sqrt(det T + margin) in place of the signed determinant: tsc_math.cuh, quartic32_T_*).
 //
-// Roles (one persistent CTA per SM, 18 warps): warp 0 producer (bulk-TMA ring of B tiles, tail of the panel for
-// K blocks beyond the 5 held in TMEM), warp 1 TMEM allocation + MMA issue (one elected thread), warps 2..17
-// epilogue: TMEM lane quarter = warp % 4, and the four warps of a quarter split the 32 columns of a tile.
+// Roles (one persistent CTA per SM, 20 warps): warp 0 producer (bulk-TMA ring of B tiles, tail of the panel for
+// K blocks beyond the 5 held in TMEM), warps 1..3 MMA issue (one elected thread each, one per row of the
+// covariances; warp 1 also owns the TMEM allocation), warps 4..19 epilogue: TMEM lane quarter = warp % 4, and the
+// four warps of a quarter split the 32 columns of a tile.
 #include <cuda_fp16.h>
-#include "tf32_common.cuh"
+#include "screen_common.cuh"
 
 namespace tsc {
 
 constexpr int SC_ROWS = 128;                  // conformers per panel (UMMA M, TMEM lanes)
-constexpr int SC_J = 32;                      // conformers per B tile
-constexpr int SC_N = 3 * SC_J;                // UMMA N = 96: (component b, conformer j)
-constexpr int SC_NBUF = 4;                    // accumulator buffers of SC_N columns
+// tile width J (conformers per B tile) is a template parameter: 32 (UMMA N = 96, four accumulator buffers) or
+// 64 (N = 192, two buffers)
 constexpr int SC_KT = 5;                      // K blocks of the panel held in TMEM (3 * 8 * 5 = 120 columns)
 constexpr int SC_ACC0 = 128;                  // first accumulator column
 constexpr int SC_TMEM = 512;
 constexpr int SC_MAX_BSTAGES = 12;
 constexpr int SC_EPI_WARPS = 16;
-constexpr int SC_COLS = SC_J / (SC_EPI_WARPS / 4);     // 8 columns of a tile per epilogue warp
 constexpr int SC_Q = 128;                     // candidate queue entries per epilogue warp
-constexpr int SC_THREADS = (2 + SC_EPI_WARPS) * 32;
-static_assert(3 * 8 * SC_KT <= SC_ACC0 && SC_ACC0 + SC_NBUF * SC_N <= SC_TMEM, "TMEM budget");
+constexpr int SC_MMA_WARPS = 3;                // one issuing thread per row a of the covariances ("chain")
+constexpr int SC_THREADS = (1 + SC_MMA_WARPS + SC_EPI_WARPS) * 32;
+static_assert(3 * 8 * SC_KT <= SC_ACC0 && SC_ACC0 + 4 * 96 <= SC_TMEM && SC_ACC0 + 2 * 192 <= SC_TMEM, "TMEM budget");
 
 struct ScParams {
     const unsigned char* PA;  // [panel][a][kc][128][16 B]     (only the chunks of K blocks >= SC_KT are read)
@@ -61,12 +60,22 @@ struct ScParams {
     int64_t N;
     int nkc;                  // 16-byte K chunks per conformer and component (two per K block)
     int nb_stages;
+    int pace;                 // cycles between two MMAs of one chain (0 = unpaced), see the MMA warps
     double e_thr;
     uint8_t* sim_bits8;
     int64_t W;                // 32-bit words per sim row
     int2* cand;
     int64_t cand_stride;
+#ifdef TSC_SCREEN_TRACE
+    long long* trace;         // measurement build only (tools/probes): clock64 stamps of CTA 0, see tools/screen_trace.py
+#endif
 };
+
+#ifdef TSC_SCREEN_TRACE
+#define SC_STAMP(cond, idx) do { if ((cond) && p.trace && blockIdx.x == 0) p.trace[(idx)] = clock64(); } while (0)
+#else
+#define SC_STAMP(cond, idx) do { } while (0)
+#endif
 
 // ---- pack: FP64 AoS -> FP16 operand images + exact G, widened sqrt(G), FP32 column terms -----------------------------
 // FP16 keeps a 10-bit mantissa (relative rounding error 2^-11) but has a 5-bit exponent: |x| >= 65520 becomes inf
@@ -76,6 +85,10 @@ struct ScParams {
 // coordinates of the conformer, alpha = 2^-14 (1 + 2^-10) / eps:
 //   ||S~ - S||_F <= 2 * 2^-11 (1 + 2^-11) sqrt(G_i G_j) + 2^-14 (1 + 2^-11) (sqrt(T_i G_j) + sqrt(G_i T_j))
 //                <= eps sqrt(G_i)' sqrt(G_j)'      (eps = 1.05e-3 also leaves 7 % for the FP32 accumulation)
+// Images: PA [panel][a][kc][128][16 B] and PR [row][a][kc][16 B] (stationary panel: shared-memory tail / TMEM part),
+// PB [j tile of J conformers][kc][(b, j) = 3 J rows][16 B] (canonical no-swizzle K-major core-matrix order: a plain
+// bulk copy of a tile is the shared-memory operand of the MMAs), CT [j tile][2 J] column terms.
+template <int J>
 __global__ void __launch_bounds__(256) pack_screen_kernel(const double* __restrict__ S, int64_t N, int A,
                                                           const int32_t* __restrict__ heavy_idx, int M, int Mp,
                                                           int64_t n_rows_end, __half* __restrict__ PA,
@@ -89,7 +102,7 @@ __global__ void __launch_bounds__(256) pack_screen_kernel(const double* __restri
     const double* src = S + (live ? i : 0) * (int64_t)A * 3;
     const int nkc = Mp / 8;
     const int64_t panel = i / SC_ROWS, r = i % SC_ROWS;
-    const int64_t jt = i / SC_J, jj = i % SC_J;
+    const int64_t jt = i / J, jj = i % J;
     double g = 0.0;
     int tiny = 0;
     const double fmin_normal = 6.103515625e-05;                 // 2^-14
@@ -110,10 +123,10 @@ __global__ void __launch_bounds__(256) pack_screen_kernel(const double* __restri
         pa[0] = hx;
         pa[(int64_t)nkc * SC_ROWS * 8] = hy;
         pa[(int64_t)2 * nkc * SC_ROWS * 8] = hz;
-        __half* pb = PB + ((jt * nkc + kc) * SC_N + jj) * 8 + e;
+        __half* pb = PB + ((jt * nkc + kc) * (3 * J) + jj) * 8 + e;
         pb[0] = hx;
-        pb[SC_J * 8] = hy;
-        pb[2 * SC_J * 8] = hz;
+        pb[J * 8] = hy;
+        pb[2 * J * 8] = hz;
         __half* pr = PR + (size_t)i * 3 * Mp + m;
         pr[0] = hx;
         pr[Mp] = hy;
@@ -126,8 +139,8 @@ __global__ void __launch_bounds__(256) pack_screen_kernel(const double* __restri
         const double alpha = 6.103515625e-05 * (1.0 + 9.765625e-4) / TF_EPS;
         const double sg = sqrt(g) + alpha * sqrt((double)tiny);
         G[i] = g; sG[i] = sg;
-        CT[jt * (2 * SC_J) + jj] = __double2float_rd(0.5 * (1.0 - 1e-10) * g);
-        CT[jt * (2 * SC_J) + SC_J + jj] = __double2float_ru(sg);
+        CT[jt * (2 * J) + jj] = __double2float_rd(0.5 * (1.0 - 1e-10) * g);
+        CT[jt * (2 * J) + J + jj] = __double2float_ru(sg);
     }
 }
 
@@ -137,14 +150,29 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     return r;
 }
 
+// MODE 0: "isotropic" form — only f = ||S~||_F^2 is accumulated across the three rows and Samuelson's bound decides;
+//         what it cannot exclude is a candidate (half the arithmetic, an eighth of the registers: 16 columns per
+//         thread, tiles of J = 64).
+// MODE 1: T = S~^T S~ accumulated; Samuelson, then the quartic sign test for column pairs with an undecided lane.
+// MODE 2: T accumulated; the quartic sign test for every pair (anisotropic ensembles, where Samuelson never excludes).
+template <int MODE, int J>
 __global__ void __launch_bounds__(SC_THREADS, 1) rmsd_screen_kernel(const ScParams p) {
+    constexpr int NN = 3 * J;                      // UMMA N: (component b, conformer j)
+    constexpr int NBUF = J == 32 ? 4 : 2;          // accumulator buffers of NN columns
+    constexpr int LBUF = J == 32 ? 2 : 1;          // log2(NBUF)
+    constexpr int LREL = J == 32 ? 12 : 6;         // lcm(NBUF, 3): ring of buffer-release barriers, see t_rel
+    constexpr int COLS = J / (SC_EPI_WARPS / 4);   // columns of a tile per epilogue warp
+    constexpr int NCP = COLS / 2;                  // column pairs (two FP32 lanes per packed instruction)
+    constexpr int NR = 3 * COLS;                   // accumulator words a thread reads per unit
+    static_assert(J == 32 || J == 64, "tile width");
+    static_assert(MODE == 0 || J == 32, "the T-accumulating modes keep 6 numbers per pair: 8 columns per thread");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int nkc = p.nkc;
     const int nkb = nkc / 2;                                   // K blocks (one MMA per component each)
     const int KT = nkb < SC_KT ? nkb : SC_KT;                  // K blocks of the panel held in TMEM
     const int tail_kc = nkc - 2 * KT;                          // chunks of the panel kept in shared memory
     const uint32_t tail_bytes = (uint32_t)tail_kc * SC_ROWS * 16u;      // per component
-    const uint32_t b_bytes = (uint32_t)nkc * SC_N * 16u;
+    const uint32_t b_bytes = (uint32_t)nkc * NN * 16u;
     unsigned char* smA = smem_raw;                             // [a][tail_kc][128][16 B]
     unsigned char* smB = smem_raw + 3u * tail_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smB + (size_t)p.nb_stages * b_bytes);
@@ -154,17 +182,24 @@ __global__ void __launch_bounds__(SC_THREADS, 1) rmsd_screen_kernel(const ScPara
     uint64_t* b_full = bars + 3;
     uint64_t* b_empty = b_full + SC_MAX_BSTAGES;               // three arrivals: one per row unit of the tile
     uint64_t* t_full = b_empty + SC_MAX_BSTAGES;
-    uint64_t* t_empty = t_full + SC_NBUF;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + SC_NBUF);
+    // Buffer release.  A waiter on an mbarrier must see every phase of it (parity waits alias two phases apart), but
+    // with three issuing threads and NBUF buffers the uses of one buffer rotate through the chains.  So the releases
+    // go to a ring of LREL = lcm(NBUF, 3) barriers indexed by the unit that may START: the epilogue, having drained
+    // unit u, arrives on t_rel[(u + NBUF) % LREL]; unit v waits on t_rel[v % LREL] — always the same chain for a
+    // given slot, once every LREL units.  (With one barrier per buffer the 64-wide form dead-locked; the 32-wide one
+    // only worked because its chains happened to arrive late.)
+    uint64_t* t_rel = t_full + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_rel + 12);
     int2* cand_q = reinterpret_cast<int2*>(reinterpret_cast<unsigned char*>(bars) + 512);     // [epilogue warp][SC_Q]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         mbar_init(at_full, 1);
         mbar_init(am_full, SC_EPI_WARPS);
-        mbar_init(a_empty, 1);
-        for (int s = 0; s < p.nb_stages; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 3); }
-        for (int t = 0; t < SC_NBUF; t++) { mbar_init(&t_full[t], 1); mbar_init(&t_empty[t], SC_EPI_WARPS); }
+        mbar_init(a_empty, SC_MMA_WARPS);
+        for (int s = 0; s < p.nb_stages; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], SC_MMA_WARPS); }
+        for (int t = 0; t < NBUF; t++) mbar_init(&t_full[t], 1);
+        for (int t = 0; t < LREL; t++) mbar_init(&t_rel[t], SC_EPI_WARPS);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, SC_TMEM);
@@ -205,63 +240,75 @@ __global__ void __launch_bounds__(SC_THREADS, 1) rmsd_screen_kernel(const ScPara
                 if (++bs == p.nb_stages) { bs = 0; bph ^= 1u; }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issue: one elected thread runs the whole schedule =====================
-        // Unit = (tile, row a of the covariances) = nkb MMAs into accumulator buffer (unit number mod 4).  Chain a
-        // ("lane" l = a) works through its units of consecutive tiles; per round one MMA of every chain is issued,
-        // chain l lagging chain 0 by l * delta K blocks, so that units complete — and buffers are needed — evenly
-        // spaced in time, in the order the epilogue consumes them.
+    } else if (warp <= SC_MMA_WARPS) {
+        // ===================== MMA issue: three warps, one elected thread each =====================
+        // Chain l = warp - 1 owns row l of the covariances: for every tile of the CTA it issues the nkb MMAs of unit
+        // (tile, l) into accumulator buffer (unit number mod NBUF) and commits them to that buffer's barrier.  MMAs
+        // that accumulate into the same buffer are a dependent chain (~144 cycles each when issued back to back); with
+        // three issuing threads the chains of different units overlap in the tensor pipe whenever buffers are free.
+        // (A single thread issuing three skewed chains needs ~70 instructions of bookkeeping per MMA: measured 245
+        // cycles per MMA.)  `pace` > 0 additionally spaces the MMAs of a chain by that many cycles (measurement aid:
+        // no gain, the epilogue is what bounds this kernel).
         if (elect_one()) {
-            const uint32_t idesc = umma_idesc_f16(SC_ROWS, SC_N);
-            const uint32_t a_lbo = SC_ROWS * 16u, b_lbo = SC_N * 16u;
+            const int l = warp - 1;
+            const uint32_t idesc = umma_idesc_f16(SC_ROWS, NN);
+            const uint32_t a_lbo = SC_ROWS * 16u, b_lbo = NN * 16u;
             const uint64_t bd0 = umma_desc_kmajor(smem_u32(smB), b_lbo, 128u);       // stage 0, K block 0
-            const uint64_t ad0 = umma_desc_kmajor(smem_u32(smA), a_lbo, 128u);       // panel tail, component x
+            const uint64_t ad0 = umma_desc_kmajor(smem_u32(smA), a_lbo, 128u) + (uint64_t)l * (tail_bytes >> 4);
             const uint64_t bd_step = (2u * b_lbo) >> 4, ad_step = (2u * a_lbo) >> 4; // start-address field, 16-byte units
-            const uint64_t b_stage_step = b_bytes >> 4, a_comp_step = tail_bytes >> 4;
-            const uint32_t a_stride = 8u * KT;                                       // TMEM columns per component
-            const int delta = nkb >= 2 ? (nkb + 2) / 3 : 0;                          // 2 delta <= nkb: no wait can deadlock
-            int st[3] = {0, 0, 0};                                                   // B stage of the chain's current tile
-            uint32_t sph[3] = {0, 0, 0};
-            uint32_t us[3] = {0, 1, 2};                                              // unit number of the chain's current unit
-            uint32_t aph = 0;
+            const uint64_t b_stage_step = b_bytes >> 4;
+            const uint32_t at0 = tmem_base + (uint32_t)l * 8u * (uint32_t)KT;        // this row's part of the panel in TMEM
+            int st = 0;
+            uint32_t sph = 0, aph = 0, us = (uint32_t)l;                             // unit number of the current unit
+            long long t_next = clock64();
+            const long long pace = p.pace;
+            auto paced = [&]() {
+                if (pace > 0) {
+                    long long now = clock64();
+                    while (now < t_next) now = clock64();
+                    t_next = now + pace;
+                }
+            };
             for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
                 const int4 w = p.items[it];
                 if (w.z == 0) break;
                 mbar_wait(am_full, aph);
                 if (tail_kc > 0) mbar_wait(at_full, aph);
                 aph ^= 1u;
-                tcgen05_fence_after();
-                const int total = w.z * nkb;
-                int k[3] = {0, 0, 0};
-                for (int r = 0; r < total + 2 * delta; r++) {
-#pragma unroll
-                    for (int l = 0; l < 3; l++) {
-                        const int kap = r - l * delta;
-                        if (kap < 0 || kap >= total) continue;
-                        const uint32_t buf = us[l] & 3u;
-                        if (k[l] == 0) {
-                            mbar_wait(&b_full[st[l]], sph[l]);
-                            mbar_wait(&t_empty[buf], ((us[l] >> 2) & 1u) ^ 1u);
-                            tcgen05_fence_after();
-                        }
-                        const uint32_t d = tmem_base + SC_ACC0 + buf * SC_N;
-                        const uint64_t bd = bd0 + (uint64_t)st[l] * b_stage_step + (uint64_t)k[l] * bd_step;
-                        if (k[l] < KT) {
-                            const uint32_t at = tmem_base + (uint32_t)l * a_stride + 8u * (uint32_t)k[l];
-                            if (k[l] == 0) umma_tf32_ts_c<false, true>(d, at, bd, idesc);
-                            else umma_tf32_ts_c<true, true>(d, at, bd, idesc);
-                        } else {                                   // K blocks whose panel block is in shared memory
-                            const uint64_t ad = ad0 + (uint64_t)l * a_comp_step + (uint64_t)(k[l] - KT) * ad_step;
-                            umma_tf32_ss_c<true, true>(d, ad, bd, idesc);
-                        }
-                        if (++k[l] == nkb) {
-                            umma_commit(&t_full[buf]);             // this row of the tile is ready for the epilogue
-                            umma_commit(&b_empty[st[l]]);          // (the stage is free after the third row's commit)
-                            k[l] = 0;
-                            us[l] += 3u;
-                            if (++st[l] == p.nb_stages) { st[l] = 0; sph[l] ^= 1u; }
-                        }
+                for (int t = 0; t < w.z; t++) {
+                    const uint32_t buf = us & (NBUF - 1);
+                    SC_STAMP(us < 192, (us * 8) + 0);
+                    mbar_wait(&b_full[st], sph);
+                    SC_STAMP(us < 192, (us * 8) + 1);
+                    if (us >= NBUF) {                           // the unit that used this buffer before has been drained
+                        const uint32_t slot = us % LREL, use = us / LREL - (slot < NBUF ? 1u : 0u);
+                        mbar_wait(&t_rel[slot], use & 1u);
                     }
+                    tcgen05_fence_after();
+                    SC_STAMP(us < 192, (us * 8) + 2);
+                    const uint32_t d = tmem_base + SC_ACC0 + buf * NN;
+                    uint64_t bd = bd0 + (uint64_t)st * b_stage_step;
+                    uint64_t ad = ad0;
+                    uint32_t at = at0;
+                    paced();
+                    umma_f16_ts<false>(d, at, bd, idesc);                   // K block 0 overwrites the buffer
+                    for (int kb = 1; kb < KT; kb++) {
+                        bd += bd_step;
+                        at += 8;
+                        paced();
+                        umma_f16_ts<true>(d, at, bd, idesc);
+                    }
+                    for (int kb = KT; kb < nkb; kb++) {                              // panel block in shared memory
+                        bd += bd_step;
+                        paced();
+                        umma_f16_ss<true>(d, ad, bd, idesc);
+                        ad += ad_step;
+                    }
+                    umma_commit(&t_full[buf]);                 // this row of the tile is ready for the epilogue
+                    umma_commit(&b_empty[st]);                 // (the stage is free after the third chain's commit)
+                    SC_STAMP(us < 192, (us * 8) + 3);
+                    us += 3u;
+                    if (++st == p.nb_stages) { st = 0; sph ^= 1u; }
                 }
                 umma_commit(a_empty);
             }
@@ -269,12 +316,12 @@ __global__ void __launch_bounds__(SC_THREADS, 1) rmsd_screen_kernel(const ScPara
         __syncwarp();
     } else {
         // ===================== epilogue: 16 warps =====================
-        const int ew = warp - 2;
+        const int ew = warp - (1 + SC_MMA_WARPS);
         const int quad = warp & 3;                               // TMEM lane quarter this warp may access
-        const int part = ew >> 2;                                // which 8 columns of every tile
+        const int part = ew >> 2;                                // which COLS columns of every tile
         const int row_in_panel = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        const int c0 = part * SC_COLS;
+        const int c0 = part * COLS;
         uint32_t eph = 0, us = 0;                                // unit number (all units of this CTA, in order)
         // Candidates (rare) go to a per-warp queue in shared memory and reach the global list in bursts with one
         // reservation per burst.
@@ -315,29 +362,45 @@ __global__ void __launch_bounds__(SC_THREADS, 1) rmsd_screen_kernel(const ScPara
             const unsigned long long Af2 = OpsF2::bc(row.Af), nCf2 = OpsF2::bc(-row.Cf);
             uint8_t* out_row = p.sim_bits8 + ((int64_t)w.w * CB + row_in_panel) * (4 * p.W);
             for (int t = 0; t < w.z; t++) {
-                const int64_t j0 = (int64_t)(w.y + t) * SC_J + c0;            // first of this warp's 8 columns
-                unsigned long long T[6][4];                                  // T = S~^T S~, two columns per register pair
+                const int64_t j0 = (int64_t)(w.y + t) * J + c0;              // first of this warp's COLS columns
+                const float4* ct = reinterpret_cast<const float4*>(p.CT + (int64_t)(w.y + t) * (2 * J) + c0);
+                float4 ctB[COLS / 4], ctD[COLS / 4];                         // B_j, D_j of this warp's columns
+                unsigned long long T[MODE == 0 ? 1 : 6][NCP];                // T = S~^T S~ (MODE 0: f), two columns per register pair
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
-                    const uint32_t buf = us & 3u;
-                    mbar_wait(&t_full[buf], (us >> 2) & 1u);
+                    uint32_t r[NR];                                          // row a of S~ for COLS columns: [b][column]
+                    const uint32_t buf = us & (NBUF - 1);
+                    SC_STAMP(ew == 0 && lane == 0 && us < 192, (us * 8) + 4);
+                    mbar_wait(&t_full[buf], (us >> LBUF) & 1u);
                     tcgen05_fence_after();
-                    const uint32_t d0 = tmem_base + lane_addr + SC_ACC0 + buf * SC_N + (uint32_t)c0;
-                    uint32_t r[24];                                          // row a of S~ for 8 columns: [b][column]
-                    tmem_ld_x8_raw(d0, &r[0]);
-                    tmem_ld_x8_raw(d0 + SC_J, &r[8]);
-                    tmem_ld_x8_raw(d0 + 2 * SC_J, &r[16]);
-                    tmem_wait_bind24(r);
-                    tcgen05_fence_before();                                  // the buffer goes back to the MMA thread
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&t_empty[buf]);
-                    us++;
+                    SC_STAMP(ew == 0 && lane == 0 && us < 192, (us * 8) + 5);
+                    const uint32_t d0 = tmem_base + lane_addr + SC_ACC0 + buf * NN + (uint32_t)c0;
 #pragma unroll
-                    for (int cp = 0; cp < 4; cp++) {
+                    for (int b = 0; b < 3; b++)
+#pragma unroll
+                        for (int h = 0; h < COLS / 8; h++) tmem_ld_x8_raw(d0 + (uint32_t)(b * J + 8 * h), &r[b * COLS + 8 * h]);
+#pragma unroll
+                    for (int h = 0; h < NR / 24; h++) tmem_wait_bind24(&r[24 * h]);
+                    SC_STAMP(ew == 0 && lane == 0 && us < 192, (us * 8) + 6);
+                    tcgen05_fence_before();                                  // the buffer goes back to its MMA thread
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&t_rel[(us + NBUF) % LREL]);
+                    SC_STAMP(ew == 15 && lane == 0 && us < 192, (us * 8) + 7);
+                    us++;
+                    if (a == 2 && MODE != 0) {                               // column terms: in flight while T is finished
+#pragma unroll
+                        for (int h = 0; h < COLS / 4; h++) { ctB[h] = __ldg(ct + h); ctD[h] = __ldg(ct + J / 4 + h); }
+                    }
+#pragma unroll
+                    for (int cp = 0; cp < NCP; cp++) {
                         const unsigned long long v0 = OpsF2::pack(r[2 * cp], r[2 * cp + 1]);
-                        const unsigned long long v1 = OpsF2::pack(r[8 + 2 * cp], r[8 + 2 * cp + 1]);
-                        const unsigned long long v2 = OpsF2::pack(r[16 + 2 * cp], r[16 + 2 * cp + 1]);
-                        if (a == 0) {
+                        const unsigned long long v1 = OpsF2::pack(r[COLS + 2 * cp], r[COLS + 2 * cp + 1]);
+                        const unsigned long long v2 = OpsF2::pack(r[2 * COLS + 2 * cp], r[2 * COLS + 2 * cp + 1]);
+                        if (MODE == 0) {
+                            T[0][cp] = (a == 0) ? OpsF2::mul(v0, v0) : OpsF2::fma(v0, v0, T[0][cp]);
+                            T[0][cp] = OpsF2::fma(v1, v1, T[0][cp]);
+                            T[0][cp] = OpsF2::fma(v2, v2, T[0][cp]);
+                        } else if (a == 0) {
                             T[0][cp] = OpsF2::mul(v0, v0); T[1][cp] = OpsF2::mul(v1, v1); T[2][cp] = OpsF2::mul(v2, v2);
                             T[3][cp] = OpsF2::mul(v0, v1); T[4][cp] = OpsF2::mul(v0, v2); T[5][cp] = OpsF2::mul(v1, v2);
                         } else {
@@ -347,33 +410,43 @@ __global__ void __launch_bounds__(SC_THREADS, 1) rmsd_screen_kernel(const ScPara
                         }
                     }
                 }
-                // ---- the tile's verdicts for this warp's 8 columns: column terms B_j (rounded down), D_j (rounded up)
-                const float2* ct = reinterpret_cast<const float2*>(p.CT + (int64_t)(w.y + t) * (2 * SC_J) + c0);
-                float2 Bj[4], Dj[4];
+                if (MODE == 0) {
 #pragma unroll
-                for (int cp = 0; cp < 4; cp++) { Bj[cp] = __ldg(ct + cp); Dj[cp] = __ldg(ct + SC_J / 2 + cp); }
+                    for (int h = 0; h < COLS / 4; h++) { ctB[h] = __ldg(ct + h); ctD[h] = __ldg(ct + J / 4 + h); }
+                }
+                // ---- the tile's verdicts for this warp's columns: column terms B_j (rounded down), D_j (rounded up)
                 uint32_t near = 0;                                           // bit c: pair of column c0 + c not excluded
 #pragma unroll
-                for (int cp = 0; cp < 4; cp++) {
-                    const unsigned long long tt[6] = {T[0][cp], T[1][cp], T[2][cp], T[3][cp], T[4][cp], T[5][cp]};
+                for (int cp = 0; cp < NCP; cp++) {
+                    unsigned long long tt[6];
+#pragma unroll
+                    for (int q = 0; q < 6; q++) tt[q] = T[MODE == 0 ? 0 : q][cp];
+                    const float4 cb = ctB[cp / 2], cd = ctD[cp / 2];
+                    const unsigned long long Bj2 = (cp & 1) ? OpsF2::pack(__float_as_uint(cb.z), __float_as_uint(cb.w))
+                                                           : OpsF2::pack(__float_as_uint(cb.x), __float_as_uint(cb.y));
+                    const unsigned long long Dj2 = (cp & 1) ? OpsF2::pack(__float_as_uint(cd.z), __float_as_uint(cd.w))
+                                                           : OpsF2::pack(__float_as_uint(cd.x), __float_as_uint(cd.y));
                     // stage 1, Samuelson: lambda_max <= sqrt(3) ||S~||_F.  With lf = A_i + B_j - C_i D_j (a lower bound
                     // of the lowered threshold eigenvalue up to a factor 1 - 1e-6, folded into the constant together with
                     // the rounding of f and of the products: 3 (1 + 9 u) / (1 - 1e-6)^2 < 3.00004) the pair is excluded
                     // iff lf > 0 and 3.00004 f - lf^2 < 0, read off the sign bits (NaN / inf: not excluded).
-                    const unsigned long long f2 = OpsF2::add(OpsF2::add(tt[0], tt[1]), tt[2]);
-                    const unsigned long long ab2 = OpsF2::add(Af2, OpsF2::pack(__float_as_uint(Bj[cp].x), __float_as_uint(Bj[cp].y)));
-                    const unsigned long long lf2 = OpsF2::fma(nCf2, OpsF2::pack(__float_as_uint(Dj[cp].x), __float_as_uint(Dj[cp].y)), ab2);
+                    const unsigned long long f2 = MODE == 0 ? tt[0] : OpsF2::add(OpsF2::add(tt[0], tt[1]), tt[2]);
+                    const unsigned long long ab2 = OpsF2::add(Af2, Bj2);
+                    const unsigned long long lf2 = OpsF2::fma(nCf2, Dj2, ab2);
                     const unsigned long long t2 = OpsF2::fma(OpsF2::bc(3.00004f), f2, OpsF2::mul(OpsF2::mul(lf2, lf2), OpsF2::bc(-1.0f)));
                     float lf[2], ab[2], tv[2];
                     OpsF2::unpack(lf2, lf[0], lf[1]);
                     OpsF2::unpack(ab2, ab[0], ab[1]);
                     OpsF2::unpack(t2, tv[0], tv[1]);
-                    uint32_t und = 0;
+                    uint32_t und = 3u;
+                    if (MODE != 2) {
+                        und = 0;
 #pragma unroll
-                    for (int h = 0; h < 2; h++)
-                        und |= (((__float_as_uint(tv[h]) & ~__float_as_uint(lf[h])) >> 31) ^ 1u) << h;
+                        for (int h = 0; h < 2; h++)
+                            und |= (((__float_as_uint(tv[h]) & ~__float_as_uint(lf[h])) >> 31) ^ 1u) << h;
+                    }
                     // stage 2, FP32 sign test of the key-matrix quartic from T, for a column pair with an undecided lane
-                    if (__any_sync(0xffffffffu, und)) {
+                    if (MODE == 2 || (MODE == 1 && __any_sync(0xffffffffu, und))) {
                         float lam[2];
 #pragma unroll
                         for (int h = 0; h < 2; h++) lam[h] = fmaf(-2e-7f, fabsf(ab[h]) + fabsf(lf[h]), lf[h]);
@@ -398,10 +471,11 @@ __global__ void __launch_bounds__(SC_THREADS, 1) rmsd_screen_kernel(const ScPara
                     near |= und << (2 * cp);
                 }
                 // validity: j > i, j < N   (rows i >= N are not stored)
-                uint32_t valid = 0xffu;
-                if (j0 + SC_COLS - 1 >= p.N) valid = (j0 >= p.N) ? 0u : (0xffu >> (j0 + SC_COLS - p.N));
-                if (j0 <= i) valid &= (i - j0 >= SC_COLS - 1) ? 0u : (0xffu << (i - j0 + 1));
-                const uint32_t bits = (i < p.N) ? (near & valid & 0xffu) : 0u;
+                constexpr uint32_t ALL = (1u << COLS) - 1u;
+                uint32_t valid = ALL;
+                if (j0 + COLS - 1 >= p.N) valid = (j0 >= p.N) ? 0u : (ALL >> (j0 + COLS - p.N));
+                if (j0 <= i) valid &= (i - j0 >= COLS - 1) ? 0u : (ALL << (i - j0 + 1));
+                const uint32_t bits = (i < p.N) ? (near & valid & ALL) : 0u;
                 if (p.cand && __any_sync(0xffffffffu, bits != 0u)) {          // append (local row, j) of every bit set
                     uint32_t bb = bits;
                     const int cnt = __popc(bb);
@@ -434,7 +508,10 @@ __global__ void __launch_bounds__(SC_THREADS, 1) rmsd_screen_kernel(const ScPara
                         qn += total;
                     }
                 }
-                if (i < p.N && (j0 >> 5) < p.W) out_row[j0 >> 3] = (uint8_t)bits;
+                if (i < p.N && (j0 >> 5) < p.W) {
+                    if (COLS == 8) out_row[j0 >> 3] = (uint8_t)bits;
+                    else *reinterpret_cast<uint16_t*>(out_row + (j0 >> 3)) = (uint16_t)bits;
+                }
             }
         }
         if (p.cand && qn) flush_q();
@@ -454,47 +531,70 @@ extern "C" int64_t tsc_screen_operand_bytes(int64_t N, int32_t M) {
 extern "C" int64_t tsc_screen_ct_floats(int64_t N) {
     return (N + tsc::SC_ROWS - 1) / tsc::SC_ROWS * tsc::SC_ROWS * 2;
 }
-// largest number of heavy atoms the screen takes (panel tail + three B stages must fit in shared memory); above it
-// the FP64 tensor-core variant runs (tsc_rmsd_sim_tiles)
-extern "C" int32_t tsc_screen_max_atoms(void) {
+static bool screen_fits(int M, int J, size_t* a_out, size_t* b_out) {
+    const int nkc = (M + 15) / 16 * 2, nkb = nkc / 2, KT = nkb < tsc::SC_KT ? nkb : tsc::SC_KT;
+    const size_t a_bytes = (size_t)3 * (nkc - 2 * KT) * tsc::SC_ROWS * 16, b_bytes = (size_t)nkc * 3 * J * 16;
+    const size_t budget = 227 * 1024 - 512 - (size_t)tsc::SC_EPI_WARPS * tsc::SC_Q * sizeof(int2);
+    if (a_out) *a_out = a_bytes;
+    if (b_out) *b_out = b_bytes;
+    return a_bytes + 3 * b_bytes <= budget;
+}
+// largest number of heavy atoms the screen takes with tiles of `tile_j` (32 or 64) conformers (panel tail + three B
+// stages must fit in shared memory); above it the FP64 tensor-core variant runs (tsc_rmsd_sim_tiles)
+extern "C" int32_t tsc_screen_max_atoms(int32_t tile_j) {
     int best = 0;
-    for (int M = 16; M <= 1024; M += 16) {
-        const int nkc = M / 8, nkb = nkc / 2, KT = nkb < tsc::SC_KT ? nkb : tsc::SC_KT;
-        const size_t a_bytes = (size_t)3 * (nkc - 2 * KT) * tsc::SC_ROWS * 16, b_bytes = (size_t)nkc * tsc::SC_N * 16;
-        const size_t budget = 227 * 1024 - 512 - (size_t)tsc::SC_EPI_WARPS * tsc::SC_Q * sizeof(int2);
-        if (a_bytes + 3 * b_bytes <= budget) best = M;
-    }
+    for (int M = 16; M <= 1024; M += 16)
+        if (screen_fits(M, tile_j == 64 ? 64 : 32, nullptr, nullptr)) best = M;
     return best;
 }
 
 // rows [row_begin, row_end) only (row_begin a multiple of 8; the last chunk should end at the padded row count
-// ceil(N/128)*128 so that the padding rows are written too); row_end <= 0: all rows
+// ceil(N/128)*128 so that the padding rows are written too); row_end <= 0: all rows.  tile_j: 32 or 64, the tile
+// width of the screen mode that will read PB / CT (tsc_rmsd_screen: mode 0 -> 64, modes 1 and 2 -> 32).
 extern "C" int tsc_pack_screen(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M, void* PA,
                                void* PB, void* PR, double* G, double* sG, float* CT, int64_t row_begin, int64_t row_end,
-                               void* stream) {
+                               int32_t tile_j, void* stream) {
     using namespace tsc;
     if (N <= 0 || M <= 0) return 0;
+    if (tile_j != 32 && tile_j != 64) return (int)cudaErrorInvalidValue;
     const int Mp = (M + 15) / 16 * 16;
     const int64_t rows_pad = (N + SC_ROWS - 1) / SC_ROWS * SC_ROWS;
     if (row_end <= 0 || row_end > rows_pad) row_end = rows_pad;
     if (row_begin < 0) row_begin = 0;
     if (row_end <= row_begin) return 0;
-    pack_screen_kernel<<<(unsigned)((row_end - row_begin + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-        S, N, A, heavy_idx, M, Mp, row_end, reinterpret_cast<__half*>(PA), reinterpret_cast<__half*>(PB),
-        reinterpret_cast<__half*>(PR), G, sG, CT, row_begin);
+    const unsigned grid = (unsigned)((row_end - row_begin + 7) / 8);
+    if (tile_j == 64)
+        pack_screen_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            S, N, A, heavy_idx, M, Mp, row_end, reinterpret_cast<__half*>(PA), reinterpret_cast<__half*>(PB),
+            reinterpret_cast<__half*>(PR), G, sG, CT, row_begin);
+    else
+        pack_screen_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            S, N, A, heavy_idx, M, Mp, row_end, reinterpret_cast<__half*>(PA), reinterpret_cast<__half*>(PB),
+            reinterpret_cast<__half*>(PR), G, sG, CT, row_begin);
     TSC_CHECK_LAUNCH();
     return 0;
 }
 
-// items (n_items, 4) int32: {panel, first j tile (32 conformers), number of j tiles, local row block (32-row units)
-// of the panel's first row inside sim_bits}; dealt round-robin to the CTAs of the persistent grid, an item with
-// count 0 ends a CTA's list (_host.build_screen_items).  cand_list: header + (local row, j) entries, or NULL.
+#ifdef TSC_SCREEN_TRACE
+static long long* g_screen_trace = nullptr;
+extern "C" void tsc_screen_set_trace(void* dev_ptr) { g_screen_trace = reinterpret_cast<long long*>(dev_ptr); }
+#endif
+
+// items (n_items, 4) int32: {panel, first j tile, number of j tiles, local row block (32-row units) of the panel's
+// first row inside sim_bits}; j tiles are 64 conformers wide in mode 0 and 32 in modes 1 / 2 (the images must have
+// been packed with the matching tile_j); dealt round-robin to the CTAs of the persistent grid, an item with count 0
+// ends a CTA's list (_host.build_screen_items).  cand_list: header + (local row, j) entries, or NULL.
+// mode: 0 = isotropic form (Samuelson only), 1 = Samuelson then quartic, 2 = quartic for every pair (see the kernel).
+// pace: 0 = none; > 0 = cycles between two MMAs of one chain (measurement aid).
 extern "C" int tsc_rmsd_screen(const void* PA, const void* PB, const void* PR, const double* G, const double* sG,
                                const float* CT, int64_t N, int32_t M, const int32_t* items, int32_t n_items, double thr,
-                               uint32_t* sim_bits, int32_t* cand_list, int64_t cand_stride, int32_t grid_ctas, void* stream) {
+                               uint32_t* sim_bits, int32_t* cand_list, int64_t cand_stride, int32_t grid_ctas, int32_t mode,
+                               int32_t pace, void* stream) {
     using namespace tsc;
     if (n_items <= 0 || N <= 0) return 0;
+    if (mode < 0 || mode > 2) return (int)cudaErrorInvalidValue;
     ScParams p;
+    p.pace = pace <= 0 ? 0 : pace;
     p.PA = reinterpret_cast<const unsigned char*>(PA);
     p.PB = reinterpret_cast<const unsigned char*>(PB);
     p.PR = reinterpret_cast<const unsigned char*>(PR);
@@ -508,23 +608,27 @@ extern "C" int tsc_rmsd_screen(const void* PA, const void* PB, const void* PR, c
     p.W = num_blocks_padded(N);
     p.cand = reinterpret_cast<int2*>(cand_list);
     p.cand_stride = cand_stride;
-    const int nkb = p.nkc / 2, KT = nkb < SC_KT ? nkb : SC_KT;
-    const size_t a_bytes = (size_t)3 * (p.nkc - 2 * KT) * SC_ROWS * 16, b_bytes = (size_t)p.nkc * SC_N * 16;
+#ifdef TSC_SCREEN_TRACE
+    p.trace = g_screen_trace;
+#endif
+    const int J = mode == 0 ? 64 : 32;
+    size_t a_bytes, b_bytes;
+    if (!screen_fits(M, J, &a_bytes, &b_bytes)) return (int)cudaErrorInvalidValue;   // more atoms than tsc_screen_max_atoms(J)
     const size_t q_bytes = (size_t)SC_EPI_WARPS * SC_Q * sizeof(int2);
     const size_t budget = 227 * 1024 - 512 - q_bytes;
-    if (a_bytes + 3 * b_bytes > budget) return (int)cudaErrorInvalidValue;      // more atoms than tsc_screen_max_atoms()
     int nb = (int)((budget - a_bytes) / b_bytes);
     if (nb > SC_MAX_BSTAGES) nb = SC_MAX_BSTAGES;
     p.nb_stages = nb;
     const size_t smem = a_bytes + nb * b_bytes + 512 + q_bytes;
-    cudaError_t e = cudaFuncSetAttribute(rmsd_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = mode == 0 ? rmsd_screen_kernel<0, 64> : mode == 2 ? rmsd_screen_kernel<2, 32> : rmsd_screen_kernel<1, 32>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid = grid_ctas > 0 ? grid_ctas : sms;
     if (grid > n_items) grid = n_items;
-    rmsd_screen_kernel<<<grid, SC_THREADS, smem, (cudaStream_t)stream>>>(p);
+    kern<<<grid, SC_THREADS, smem, (cudaStream_t)stream>>>(p);
     TSC_CHECK_LAUNCH();
     return 0;
 }

@@ -120,7 +120,7 @@ TSC_HD bool screen_candidate(const double S[9], double G, double e_thr_pad) {
 }
 
 // ------------------------------------------------------------------------------------------
-// FP32 form of the sign test: second stage of the tcgen05 pre-screens (tf32_common.cuh).
+// FP32 form of the sign test: second stage of the tcgen05 pre-screen (rmsd_screen.cu).
 //
 // Samuelson's bound sqrt(3) ||S||_F >= lambda_max is only sharp for near-isotropic covariances; for an
 // elongated or planar molecule it exceeds the threshold eigenvalue for EVERY pair (tools/aniso_probe.py:

@@ -183,7 +183,7 @@ def gather_varlen(x, world: int, group=None):
 
 
 def screen_and_prune(frags, conf, R, t, atomnos, thresh=1.5, max_clashes=0, rmsd_thr=0.5, *, rank=0, world=1,
-                     group=None, variant="f16"):
+                     group=None, variant="screen"):
     """Returns dict(verdict (P,) uint8 device tensor, keep (n_pass,) int64 global pose indices, poses
     (n_pass, A, 3) device tensor of the poses that pass the clash screen, mask (n_pass,) bool device tensor
     of the RMSD prune over them, timings of the phases in ms)."""

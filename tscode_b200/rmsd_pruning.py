@@ -21,9 +21,9 @@ from ._lib import check, lib, ptr, require_cuda, stream_ptr
 import ctypes
 import functools
 
-# f16 / tf32 = tcgen05 pre-screen with the stationary operand in TMEM (FP16 or TF32 operands);
-# tf32ss = both operands from shared memory; dmma / fma = FP64 tensor cores / FMA pipe
-VARIANTS = {"dmma": 0, "fma": 1, "tf32": 2, "tf32ss": 3, "f16": 4, "screen": 5}
+# screen = tcgen05 / TMEM pre-screen on FP16 operands (rmsd_screen.cu; default); dmma / fma = FP64 tensor cores /
+# FMA pipe (rmsd_sim.cu: the north star's FP64 variants, and the fallback above tsc_screen_max_atoms heavy atoms)
+VARIANTS = {"dmma": 0, "fma": 1, "screen": 5}
 
 
 _STAGING = {}
@@ -57,7 +57,7 @@ def _upload_bounds(N, n_chunks=UPLOAD_CHUNKS):
 
 
 @functools.lru_cache(maxsize=8)
-def _work_lists(N, rank, world, variant, device_str, n_ctas=0):
+def _work_lists(N, rank, world, variant, device_str, n_ctas=0, tile_j=32):
     """Device-resident work lists (owned row blocks, tile / item lists) — they depend only on the
     shape of the problem, so repeated prunes of same-sized ensembles reuse them."""
     import torch
@@ -68,32 +68,17 @@ def _work_lists(N, rank, world, variant, device_str, n_ctas=0):
         # default screen (rmsd_screen.cu): j tiles of 32 conformers; one contiguous, equally expensive stretch of
         # (panel, j tile) pairs per CTA of the persistent grid, plus the same per upload chunk
         n_ctas = n_ctas if n_ctas > 0 else torch.cuda.get_device_properties(dev).multi_processor_count
-        items = np.ascontiguousarray(_host.build_screen_items(N, rb, n_ctas))
+        items = np.ascontiguousarray(_host.build_screen_items(N, rb, n_ctas, tile_j=tile_j))
         out["n_items"], out["items"], out["items_np"] = int(items.shape[0]), torch.from_numpy(items).to(dev), items
         bounds = _upload_bounds(N)
-        chunks = [np.ascontiguousarray(_host.build_screen_items(N, rb, n_ctas, panel_lo=bounds[c], panel_hi=bounds[c + 1]))
+        chunks = [np.ascontiguousarray(_host.build_screen_items(N, rb, n_ctas, panel_lo=bounds[c], panel_hi=bounds[c + 1],
+                                                                tile_j=tile_j))
                   for c in range(len(bounds) - 1)]
         out["chunk_items"] = [(torch.from_numpy(it).to(dev) if it.shape[0] else None, int(it.shape[0])) for it in chunks]
-    elif variant in (2, 4):
-        # TMEM-operand screens: one contiguous, equally expensive stretch of (panel, j tile) pairs per CTA of the
-        # persistent grid (the kernel deals array entries round-robin); plus the same per upload chunk
-        n_ctas = n_ctas if n_ctas > 0 else torch.cuda.get_device_properties(dev).multi_processor_count
-        items = np.ascontiguousarray(_host.build_tf32_items_balanced(N, rb, n_ctas))
-        out["n_items"], out["items"], out["items_np"] = int(items.shape[0]), torch.from_numpy(items).to(dev), items
-        bounds = _upload_bounds(N)
-        chunks = [np.ascontiguousarray(_host.build_tf32_items_balanced(N, rb, n_ctas, panel_lo=bounds[c], panel_hi=bounds[c + 1]))
-                  for c in range(len(bounds) - 1)]
-        out["chunk_items"] = [(torch.from_numpy(it).to(dev) if it.shape[0] else None, int(it.shape[0])) for it in chunks]
-    elif variant == 3:
-        items = np.ascontiguousarray(_host.build_tf32_items(N, rb))
-        out["n_items"], out["items"], out["items_np"] = int(items.shape[0]), torch.from_numpy(items).to(dev), items
     else:
         tiles = _host.build_tiles(N, rb)
         out["n_tiles"], out["tiles"] = int(tiles.shape[0]), torch.from_numpy(tiles).to(dev)
     return out
-
-TF32_MAX_M = 120        # stationary A panel + 2 B stages must fit in shared memory
-F16_MAX_M = 320         # FP16 operands: 144 atoms of the panel in TMEM, the rest + 2 B stages in shared memory
 
 
 class RmsdPruner:
@@ -101,12 +86,14 @@ class RmsdPruner:
 
     structures : (N, A, 3) float64, numpy array or torch tensor (host or device)
     atomnos    : (A,) ints; hydrogens (== 1) are ignored        (rmsd_pruning.py:178-179)
-    variant    : "f16" (default) = tcgen05/TMEM pre-screen on FP16 operands (10-bit mantissa, K = 16
-                 atoms per MMA) with a rigorous error bound and an FP32 two-stage exclusion test
-                 (Samuelson, then the key-matrix quartic), exact FP64 verification of everything
-                 it cannot exclude (falls back to "dmma" above 320 heavy atoms); "tf32" = the same
-                 with TF32 operands (<= 120 heavy atoms); "dmma" = FP64 tensor cores; "fma" = FP64
-                 FMA pipe.  All give identical final similarity bits and masks.
+    variant    : "screen" (default) = tcgen05 / TMEM pre-screen on FP16 operands (10-bit mantissa, K = 16 atoms per
+                 MMA, FP32 accumulation) with a rigorous operand error bound and FP32 exclusion tests (Samuelson's
+                 bound; sign test of the key-matrix quartic), exact FP64 verification of everything it cannot
+                 exclude; falls back to "dmma" above tsc_screen_max_atoms heavy atoms.  "dmma" = FP64 tensor cores,
+                 "fma" = FP64 FMA pipe.  All give identical final similarity bits and masks.
+    screen_mode: form of the default screen (0 = isotropic / Samuelson only on 64-wide tiles, 1 = Samuelson then
+                 quartic, 2 = quartic for every pair); None = chosen from the shape of the first structure
+                 (_host.screen_mode_for).  A speed choice only: every form is conservative.
     rank/world/group : row-block sharding over one process per GPU (block-cyclic, SURVEY 8(e));
                  every rank holds the whole packed ensemble, computes the similarity rows it
                  owns, and per elimination round contributes its rows' verdicts to an NCCL
@@ -115,7 +102,7 @@ class RmsdPruner:
 
     def __init__(self, structures, atomnos, rmsd_thr=0.5, *, variant="screen", device=None,
                  rank=0, world=1, group=None, grid_ctas=0, ladder="fused", pair_cap=None, cand_cap=None,
-                 pipeline_upload=True):
+                 pipeline_upload=True, screen_mode=None):
         torch = require_cuda()
         self.torch = torch
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -124,6 +111,8 @@ class RmsdPruner:
         self.variant_requested = self.variant
         self.rank, self.world, self.group = int(rank), int(world), group
         self.grid_ctas = int(grid_ctas)
+        self.pace = 0                     # tsc_rmsd_screen's MMA spacing (measurement aid: tools/screen_check.py)
+        self.screen_mode = screen_mode    # form of the default screen: None = chosen from the molecule's shape (below)
         if ladder not in ("fused", "bitrows"):
             raise ValueError("ladder must be 'fused' or 'bitrows'")
         self.ladder = ladder
@@ -153,13 +142,23 @@ class RmsdPruner:
         N, M = self.N, self.M
         self.nb_pad = _host.num_blocks_padded(N)
         self.W = self.nb_pad
-        if (self.variant in (2, 3) and M > TF32_MAX_M) or (self.variant == 4 and M > F16_MAX_M) or \
-                (self.variant == 5 and M > int(lib().tsc_screen_max_atoms())):
+        if self.variant == 5 and N and M:
+            if self.screen_mode is None:
+                # isotropic molecule -> Samuelson-only form on 64-wide tiles, otherwise the quartic test for every
+                # pair (_host.screen_mode_for: a speed decision, every form is conservative)
+                first = (src[0] if not src.is_cuda else src[0].cpu()).numpy()[heavy]
+                self.screen_mode = _host.screen_mode_for(first)
+            self.tile_j = 64 if self.screen_mode == 0 else 32
+            if M > int(lib().tsc_screen_max_atoms(self.tile_j)) and self.screen_mode == 0:
+                self.screen_mode, self.tile_j = 1, 32        # too many atoms for 64-wide tiles: Samuelson, then quartic
+        else:
+            self.tile_j = 32
+        if self.variant == 5 and M > int(lib().tsc_screen_max_atoms(self.tile_j)):
             self.variant = 0             # documented fallback: FP64 tensor cores (include/tscode_b200.h)
         with torch.cuda.device(self.device):
             dev = self.device
             self.heavy_idx = torch.from_numpy(heavy).to(dev)
-            wl = _work_lists(N, self.rank, self.world, self.variant, str(dev), max(self.grid_ctas, 0))
+            wl = _work_lists(N, self.rank, self.world, self.variant, str(dev), max(self.grid_ctas, 0), self.tile_j)
             self.row_blocks_np, self.row_blocks = wl["row_blocks_np"], wl["row_blocks"]
             self.n_rb = int(self.row_blocks_np.size)
             self.n_tiles, self.tiles = wl.get("n_tiles", 0), wl.get("tiles")
@@ -176,22 +175,6 @@ class RmsdPruner:
                 self.sG = torch.empty(n_g, dtype=torch.float64, device=dev)
                 self.G_side = torch.empty(n_g, dtype=torch.float64, device=dev)
                 self.CT = torch.empty(max(L.tsc_screen_ct_floats(N), 1), dtype=torch.float32, device=dev)
-            if self.variant == 4:
-                L = lib()
-                nbytes = max(int(L.tsc_f16_operand_bytes(N, max(M, 1))), 16)
-                self.PA = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-                self.PB = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-                self.PR = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-                self.sG = torch.empty(n_g, dtype=torch.float64, device=dev)
-                self.G_side = torch.empty(n_g, dtype=torch.float64, device=dev)
-                self.CT = torch.empty(max(L.tsc_tf32_ct_floats(N), 1), dtype=torch.float32, device=dev)
-            if self.variant in (2, 3):
-                L = lib()
-                self.PR = torch.empty(max(L.tsc_tf32_pr_floats(N, max(M, 1)), 1), dtype=torch.float32, device=dev)
-                self.sG = torch.empty(n_g, dtype=torch.float64, device=dev)
-                self.PA = torch.empty(max(L.tsc_tf32_pa_floats(N, max(M, 1)), 1), dtype=torch.float32, device=dev)
-                self.PB = torch.empty(max(L.tsc_tf32_pb_floats(N, max(M, 1)), 1), dtype=torch.float32, device=dev)
-                self.CT = torch.empty(max(L.tsc_tf32_ct_floats(N), 1), dtype=torch.float32, device=dev)
             self.sim_bits = torch.empty((max(self.n_rb, 1) * _host.CB, self.W), dtype=torch.int32, device=dev)
             self.stats = torch.zeros(4, dtype=torch.int64, device=dev)
             nw = (N + 31) // 32
@@ -269,7 +252,7 @@ class RmsdPruner:
         L = lib()
         torch = self.torch
         with torch.cuda.device(self.device):
-            if self.variant in (4, 5):
+            if self.variant == 5:
                 # the FP64 tiled-SoA image is only read by verify: it is written on a side stream while the main
                 # stream goes on to the FP16 images and the screen (verify waits for the event)
                 main, side = torch.cuda.current_stream(), _copy_stream(str(self.device))
@@ -285,15 +268,7 @@ class RmsdPruner:
             if self.variant == 5:
                 check(L.tsc_pack_screen(ptr(self.S), self.N, self.A, ptr(self.heavy_idx), self.M, ptr(self.PA),
                                         ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG), ptr(self.CT), 0, 0,
-                                        stream_ptr()), "tsc_pack_screen")
-            if self.variant == 4:
-                check(L.tsc_pack_f16(ptr(self.S), self.N, self.A, ptr(self.heavy_idx), self.M, ptr(self.PA),
-                                     ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG), ptr(self.CT), stream_ptr()),
-                      "tsc_pack_f16")
-            if self.variant in (2, 3):
-                check(L.tsc_pack_tf32(ptr(self.S), self.N, self.A, ptr(self.heavy_idx), self.M, ptr(self.PA),
-                                      ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG), ptr(self.CT), stream_ptr()),
-                      "tsc_pack_tf32")
+                                        self.tile_j, stream_ptr()), "tsc_pack_screen")
         self.packed_ready = True
 
     def screen(self):
@@ -306,26 +281,12 @@ class RmsdPruner:
         L = lib()
         with self.torch.cuda.device(self.device):
             self.stats.zero_()
-            self.cand_list[0].fill_(0 if self.variant in (2, 4, 5) else -1)      # -1: this screen writes no list
+            self.cand_list[0].fill_(0 if self.variant == 5 else -1)      # -1: this screen writes no list
             if self.variant == 5:
                 check(L.tsc_rmsd_screen(ptr(self.PA), ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG),
                                         ptr(self.CT), self.N, self.M, ptr(self.items), self.n_items, self.thr,
                                         ptr(self.sim_bits), ptr(self.cand_list), self.cand_stride, self.grid_ctas,
-                                        stream_ptr()), "tsc_rmsd_screen")
-            elif self.variant == 4:
-                check(L.tsc_rmsd_sim_f16ts(ptr(self.PA), ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG),
-                                           ptr(self.CT), self.N, self.M, ptr(self.items), self.n_items, self.thr,
-                                           ptr(self.sim_bits), ptr(self.cand_list), self.cand_stride, self.grid_ctas,
-                                           stream_ptr()), "tsc_rmsd_sim_f16ts")
-            elif self.variant == 2:
-                check(L.tsc_rmsd_sim_tf32ts(ptr(self.PA), ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG),
-                                            ptr(self.CT), self.N, self.M, ptr(self.items), self.n_items, self.thr,
-                                            ptr(self.sim_bits), ptr(self.cand_list), self.cand_stride, self.grid_ctas,
-                                            stream_ptr()), "tsc_rmsd_sim_tf32ts")
-            elif self.variant == 3:
-                check(L.tsc_rmsd_sim_tf32(ptr(self.PA), ptr(self.PB), ptr(self.G), ptr(self.sG), self.N, self.M,
-                                          ptr(self.items), self.n_items, self.thr, ptr(self.sim_bits),
-                                          self.grid_ctas, stream_ptr()), "tsc_rmsd_sim_tf32")
+                                        self.screen_mode, self.pace, stream_ptr()), "tsc_rmsd_screen")
             else:
                 check(L.tsc_rmsd_sim_tiles(ptr(self.packed), ptr(self.G), self.N, self.M, ptr(self.tiles),
                                            self.n_tiles, self.thr, ptr(self.sim_bits), self.variant, self.grid_ctas,
@@ -501,7 +462,7 @@ class RmsdPruner:
         torch = self.torch
         host, N = self._host, self.N
         self._host = None                                # the next run() works from the device copy
-        if self.variant not in (4, 5) or N == 0 or self.M == 0:
+        if self.variant != 5 or N == 0 or self.M == 0:
             self._staging = None
             self.S.copy_(host)
             self.pack()
@@ -513,7 +474,7 @@ class RmsdPruner:
         n_chunks = len(pb) - 1
         bounds = [q * 128 for q in pb[:-1]] + [N]
         chunk_items = _work_lists(N, self.rank, self.world, self.variant, str(self.device),
-                                  max(self.grid_ctas, 0))["chunk_items"]
+                                  max(self.grid_ctas, 0), self.tile_j)["chunk_items"]
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream()
             copy = _copy_stream(str(self.device))
@@ -543,26 +504,15 @@ class RmsdPruner:
                 hi_pad = rows_pad if c == n_chunks - 1 else hi
                 check(L.tsc_pack_blocks(ptr(self.S), N, self.A, ptr(self.heavy_idx), self.M, ptr(self.packed), ptr(self.G),
                                         lo // 32, self.nb_pad if c == n_chunks - 1 else hi // 32, st), "tsc_pack_blocks")
-                if self.variant == 5:
-                    check(L.tsc_pack_screen(ptr(self.S), N, self.A, ptr(self.heavy_idx), self.M, ptr(self.PA), ptr(self.PB),
-                                            ptr(self.PR), ptr(self.G), ptr(self.sG), ptr(self.CT), lo, hi_pad, st),
-                          "tsc_pack_screen")
-                    it_dev, n_it = chunk_items[c]
-                    if n_it:
-                        check(L.tsc_rmsd_screen(ptr(self.PA), ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG),
-                                                ptr(self.CT), N, self.M, ptr(it_dev), n_it, self.thr, ptr(self.sim_bits),
-                                                ptr(self.cand_list), self.cand_stride, self.grid_ctas, st),
-                              "tsc_rmsd_screen")
-                    continue
-                check(L.tsc_pack_f16_rows(ptr(self.S), N, self.A, ptr(self.heavy_idx), self.M, ptr(self.PA), ptr(self.PB),
-                                          ptr(self.PR), ptr(self.G), ptr(self.sG), ptr(self.CT), lo, hi_pad, st),
-                      "tsc_pack_f16_rows")
+                check(L.tsc_pack_screen(ptr(self.S), N, self.A, ptr(self.heavy_idx), self.M, ptr(self.PA), ptr(self.PB),
+                                        ptr(self.PR), ptr(self.G), ptr(self.sG), ptr(self.CT), lo, hi_pad,
+                                        self.tile_j, st), "tsc_pack_screen")
                 it_dev, n_it = chunk_items[c]
                 if n_it:
-                    check(L.tsc_rmsd_sim_f16ts(ptr(self.PA), ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG),
-                                               ptr(self.CT), N, self.M, ptr(it_dev), n_it, self.thr,
-                                               ptr(self.sim_bits), ptr(self.cand_list), self.cand_stride, self.grid_ctas,
-                                               st), "tsc_rmsd_sim_f16ts")
+                    check(L.tsc_rmsd_screen(ptr(self.PA), ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG),
+                                            ptr(self.CT), N, self.M, ptr(it_dev), n_it, self.thr, ptr(self.sim_bits),
+                                            ptr(self.cand_list), self.cand_stride, self.grid_ctas, self.screen_mode,
+                                            self.pace, st), "tsc_rmsd_screen")
         self.packed_ready = True
 
     def set_pairs(self, pairs):

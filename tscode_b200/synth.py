@@ -13,7 +13,7 @@ import hashlib
 
 import numpy as np
 
-__all__ = ["gen_ensemble", "gen_poses", "materialise_poses", "mask_digest", "CONFIGS"]
+__all__ = ["gen_ensemble", "gen_poses", "gen_pose_groups", "gen_cyclical_groups", "materialise_poses", "mask_digest", "CONFIGS"]
 
 
 def gen_ensemble(seed, N, M, n_clusters, sigma_cluster=1.0, sigma_noise=0.05, scale=3.0):
@@ -85,6 +85,67 @@ def gen_pose_groups(seed, n_groups, steps=12, n_atoms=(30, 30), n_conf=3, blob=1
             R[g * steps + k, 1] = Rs @ R0
             t[g * steps + k, 1] = pos
     return frags, conf, np.ascontiguousarray(R), np.ascontiguousarray(t), gid
+
+
+def gen_cyclical_groups(seed, n_groups, steps=6, n_atoms=(50, 50, 50), n_conf=3, side=(3.0, 4.2), dup_every=3):
+    """A trimolecular cyclical embed as the generator loop of embeds.py:657-718 sees it (BASELINE configs[4]): three
+    fragments on the sides of a triangle, every fragment stepped through `steps` angles about the line through its
+    two reactive atoms; group = one combination of conformers and triangle, poses per group = steps^3 in the order of
+    embedder.systematic_angles (cartesian product, last molecule fastest).
+
+    Returns a dict with the per-group descriptors tscode_b200.embeds.cyclical_embed_poses takes — ref2 (G, 3, 2, 3) =
+    [end - start, directions[i]], tgt2 = [pivots[i].pivot, mol_direction], axis_src = reactive_coords[0] -
+    reactive_coords[1], atomic_pivot_mean, vec_mean = mean(vec_pair), pivot_mean = pivots[i].meanpoint, group_conf —
+    plus frags [(n_conf, n_k, 3)] and systematic_angles (steps^3, 3).
+
+    The numbers are chosen so that every stage of the pipeline has work to do: fragments are elongated away from
+    their reactive atoms, so stepping them towards the inside of the triangle makes them clash; conformer 0 of the
+    last fragment is thin around its rotation axis, so its angular images are near-duplicates (the group-local
+    de-duplication, rmsd_thr 1.0, removes them); and every `dup_every`-th group repeats the previous one with a
+    1e-3 A jitter, so the final prune_conformers_rmsd (rmsd_thr 0.5) meets the same pose twice."""
+    rng = np.random.default_rng(seed)
+    F = len(n_atoms)
+    frags = []
+    for k, n in enumerate(n_atoms):
+        X = rng.normal(size=(n_conf, n, 3)) * np.array([1.0, 1.0, 2.2]) + np.array([0.0, 0.0, 1.5])
+        if k == F - 1:                                   # a rod along its own rotation axis (the line y = 0, z = -3)
+            X[0, :, 0] = rng.normal(size=n) * 1.6
+            X[0, :, 1:] = rng.normal(size=(n, 2)) * 0.15 + np.array([0.0, -3.0])
+        X[:, 0] = np.array([-0.7, 0.0, -3.0]); X[:, 1] = np.array([0.7, 0.0, -3.0])     # the two reactive atoms
+        frags.append(np.ascontiguousarray(X))
+    angles = np.arange(steps) * (360.0 / steps)
+    sys_angles = np.array(np.meshgrid(*([angles] * F), indexing="ij")).reshape(F, -1).T.copy()
+    G = n_groups
+    ref2 = np.zeros((G, F, 2, 3)); tgt2 = np.zeros((G, F, 2, 3)); axis_src = np.zeros((G, F, 3))
+    apm = np.zeros((G, F, 3)); vmean = np.zeros((G, F, 3)); pmean = np.zeros((G, F, 3))
+    gconf = np.zeros((G, F), dtype=np.int32)
+    for g in range(G):
+        if dup_every and g % dup_every == dup_every - 1 and g > 0:
+            j = 1e-3
+            ref2[g] = ref2[g - 1]; tgt2[g] = tgt2[g - 1]; axis_src[g] = axis_src[g - 1]; apm[g] = apm[g - 1]
+            vmean[g] = vmean[g - 1] + rng.normal(size=(F, 3)) * j; pmean[g] = pmean[g - 1]; gconf[g] = gconf[g - 1]
+            continue
+        gconf[g] = rng.integers(0, n_conf, size=F)
+        L = rng.uniform(*side)
+        verts = np.array([[L / np.sqrt(3) * np.cos(a), L / np.sqrt(3) * np.sin(a), 0.0]
+                          for a in np.deg2rad([90.0, 210.0, 330.0])])
+        verts += rng.normal(size=(3, 3)) * 0.15
+        centre = verts.mean(axis=0)
+        for i in range(F):
+            start, end = verts[i], verts[(i + 1) % F]
+            mid = 0.5 * (start + end)
+            X = frags[i][gconf[g, i]]
+            r0, r1 = X[0], X[1]
+            ref2[g, i, 0] = end - start
+            ref2[g, i, 1] = centre - mid + rng.normal(size=3) * 0.05          # the molecule faces the centre
+            tgt2[g, i, 0] = (r1 - r0) * rng.uniform(0.9, 1.1)                  # pivot
+            apm[g, i] = 0.5 * (r0 + r1)
+            pmean[g, i] = apm[g, i] + np.array([0.0, 0.0, -0.8])
+            tgt2[g, i, 1] = pmean[g, i] - apm[g, i]                            # mol_direction
+            axis_src[g, i] = r0 - r1
+            vmean[g, i] = mid
+    return dict(frags=frags, group_conf=gconf, ref2=ref2, tgt2=tgt2, axis_src=axis_src, atomic_pivot_mean=apm,
+                vec_mean=vmean, pivot_mean=pmean, systematic_angles=sys_angles)
 
 
 def materialise_poses(frags, conf, R, t, sel=None):
