@@ -709,3 +709,32 @@ def test_constraint_scores_vs_live_reference(gpu):
     _, err = constraint_scores(S, cons, targets)
     assert [bool(e < g["fitness_threshold"]) for e in err] == g["fitness"]
     assert fitness_check(S[3], [tuple(c) for c in cons[3]], targets[3], g["fitness_threshold"]) == g["fitness"][3]
+
+
+_pipe = json.load(open(os.path.join(GOLDEN, "embed_pipeline.json")))["rows"]
+
+
+@pytest.mark.parametrize("name", list(_pipe))
+def test_cyclical_embed_pipeline_vs_live_reference(gpu, name):
+    """BASELINE configs[4]: trimolecular cyclical embed, pose parameters -> transform + clash screen -> group-local
+    de-duplication -> RMSD prune, against the LIVE reference's own functions run in its generator-loop order
+    (oracle/gen_golden_c5.py).  "small": 12 960 poses, every bit compared; "c5": the full 1 000 080 poses, counts and
+    digests of the three stages (the reference needed 85 s + 26 min for it)."""
+    from tscode_b200.embeds import cyclical_embed_pipeline
+    from tscode_b200.synth import gen_cyclical_groups, mask_digest
+    r = _pipe[name]
+    d = gen_cyclical_groups(r["seed"], r["n_groups"])
+    A = int(sum(f.shape[1] for f in d["frags"]))
+    res = cyclical_embed_pipeline(d, np.full(A, 6), 1.5, 0, 1.0, 0.5)
+    v, k, m = res["verdict"].cpu().numpy(), res["kept"].cpu().numpy(), res["mask"].cpu().numpy()
+    print(name, "poses", res["n_poses"], "pass", int(v.sum()), "kept", int(k.sum()), "survivors", int(m.sum()), res["ms"])
+    assert res["n_poses"] == r["poses"] and v.shape[0] == r["poses"]
+    assert int(v.sum()) == r["clash_pass"] and mask_digest(v) == r["clash_digest"]
+    assert int(k.sum()) == r["kept"] and mask_digest(k) == r["kept_digest"]
+    assert int(m.sum()) == r["survivors"] and mask_digest(m) == r["prune_digest"]
+    if "verdict_hex" in r:
+        unpack = lambda h, n: np.unpackbits(np.frombuffer(bytes.fromhex(h), np.uint8))[:n].astype(bool)
+        assert np.array_equal(v.astype(bool), unpack(r["verdict_hex"], r["poses"]))
+        assert np.array_equal(k, unpack(r["kept_hex"], r["poses"]))
+        assert np.array_equal(m, unpack(r["mask_hex"], r["kept"]))
+

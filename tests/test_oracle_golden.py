@@ -213,3 +213,36 @@ def test_oracle_constraint_scores_vs_live_reference():
     for p in range(g["N"]):
         tg = [None if (p + k) % 5 == 0 else float(dists[p, k]) for k in range(3)]
         assert bool(oracle_np.fitness_check(S[p], [tuple(c) for c in cons[p]], tg, g["fitness_threshold"])) == g["fitness"][p]
+
+
+def test_oracle_embed_pipeline_small_vs_live_reference():
+    """BASELINE configs[4] in small: the oracles' restatement of the generator loop (pose parameters, get_embed,
+    compenetration_check, group-local _rmsd_similarity, prune_conformers_rmsd) reproduces every bit the live
+    reference produced (oracle/gen_golden_c5.py, tests/golden/embed_pipeline.json)."""
+    import json
+    import os
+    from oracle import oracle_np
+    from tscode_b200.synth import gen_cyclical_groups, materialise_poses
+    r = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "embed_pipeline.json")))["rows"]["small"]
+    d = gen_cyclical_groups(r["seed"], r["n_groups"])
+    R, t = oracle_np.cyclical_embed_params(d["ref2"], d["tgt2"], d["axis_src"], d["atomic_pivot_mean"], d["vec_mean"],
+                                           d["pivot_mean"], d["systematic_angles"])
+    G, C = r["n_groups"], d["systematic_angles"].shape[0]
+    conf = np.repeat(d["group_conf"], C, axis=0)
+    v = oracle_c.embed_clash_batch(d["frags"], conf, R, t, 1.5, 0)
+    unpack = lambda h, n: np.unpackbits(np.frombuffer(bytes.fromhex(h), np.uint8))[:n].astype(bool)
+    assert np.array_equal(v.astype(bool), unpack(r["verdict_hex"], r["poses"]))
+    idx = np.flatnonzero(v)
+    P = materialise_poses(d["frags"], conf, R, t, idx)
+    gid = np.repeat(np.arange(G), C)[idx]
+    kept = np.zeros(r["poses"], bool)
+    for g in np.unique(gid):
+        members, keep = np.flatnonzero(gid == g), []
+        for i in members:
+            if not keep or not oracle_c.rmsd_similarity(P[i], P[keep], 1.0):
+                keep.append(i)
+                kept[idx[i]] = True
+    assert np.array_equal(kept, unpack(r["kept_hex"], r["poses"]))
+    A = P.shape[1]
+    _, mask = oracle_c.prune_conformers_rmsd(P[kept[idx]], np.full(A, 6), 0.5)
+    assert np.array_equal(mask, unpack(r["mask_hex"], r["kept"]))

@@ -218,3 +218,79 @@ def screen_and_prune(frags, conf, R, t, atomnos, thresh=1.5, max_clashes=0, rmsd
     return {"verdict": verdict, "keep": keep, "poses": poses, "mask": mask, "pruner": pr,
             "ms": {"clash_gather": ev[0].elapsed_time(ev[1]), "exchange": ev[1].elapsed_time(ev[2]),
                    "prune": ev[2].elapsed_time(ev[3])}}
+
+
+def group_range(G: int, rank: int, world: int):
+    """Contiguous range of groups of a rank (groups are independent units for clash screen and de-duplication)."""
+    per = (G + world - 1) // world
+    lo = min(rank * per, G)
+    return lo, min(lo + per, G)
+
+
+def cyclical_embed_pipeline(desc, atomnos, thresh=1.5, max_clashes=0, dedup_thr=1.0, rmsd_thr=0.5, *, rank=0, world=1,
+                            group=None):
+    """The whole post-generation path of a cyclical embed (BASELINE configs[4]), batched and sharded:
+
+        for every group, for every angle combination (embeds.py:657-709):   pose parameters on the device
+            get_embed -> compenetration_check (embeds.py:713-714)            fused transform + clash screen
+            _rmsd_similarity(pose, angular_poses, rmsd_thr=1) (embeds.py:715) group-local greedy de-duplication
+        prune_conformers_rmsd(poses, atomnos, rmsd_thr) (embedder.py:1363)   row-sharded all-pairs prune
+
+    desc: the per-group descriptors cyclical_embed_poses takes plus `frags` (e.g. synth.gen_cyclical_groups).
+    With several ranks the GROUPS are dealt in contiguous ranges (no data-path collective until the kept poses are
+    all-gathered for the prune).  Returns a dict: verdict (P,) uint8 and kept (P,) bool over all poses in generation
+    order, poses (n_kept, A, 3) device tensor, mask (n_kept,) bool device tensor of the prune, ms per phase.
+    Everything returned is identical on all ranks and to the single-GPU result."""
+    torch = require_cuda()
+    import torch.distributed as dist
+    G = int(desc["group_conf"].shape[0])
+    C = int(np.asarray(desc["systematic_angles"]).reshape(-1, len(desc["frags"])).shape[0])
+    lo, hi = group_range(G, rank, world)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    ev[0].record()
+    sub = {k: desc[k][lo:hi] for k in ("group_conf", "ref2", "tgt2", "axis_src", "atomic_pivot_mean", "vec_mean", "pivot_mean")}
+    if hi > lo:
+        pb, gid = cyclical_embed_poses(desc["frags"], sub["group_conf"], sub["ref2"], sub["tgt2"], sub["axis_src"],
+                                       sub["atomic_pivot_mean"], sub["vec_mean"], sub["pivot_mean"], desc["systematic_angles"])
+        dev = pb.verdict.device
+        v_loc = pb.clash(thresh, max_clashes)
+        ev[1].record()
+        idx = v_loc.nonzero().squeeze(1)
+        poses_pass = pb.gather(idx)
+        keep_pass = dedup_groups(poses_pass, gid[idx], None, dedup_thr)
+        kept_loc = torch.zeros(pb.P, dtype=torch.bool, device=dev)
+        kept_loc[idx[keep_pass]] = True
+        poses_loc = poses_pass[keep_pass]
+    else:
+        dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+        A = int(sum(f.shape[1] for f in desc["frags"]))
+        v_loc = torch.zeros(0, dtype=torch.uint8, device=dev)
+        ev[1].record()
+        kept_loc = torch.zeros(0, dtype=torch.bool, device=dev)
+        poses_loc = torch.zeros((0, A, 3), dtype=torch.float64, device=dev)
+    ev[2].record()
+    if world > 1:
+        per = (G + world - 1) // world * C
+        pad = torch.zeros((2, per), dtype=torch.uint8, device=dev)
+        pad[0, :v_loc.numel()] = v_loc
+        pad[1, :kept_loc.numel()] = kept_loc.to(torch.uint8)
+        allp = torch.empty((world, 2, per), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allp.view(-1), pad.view(-1), group=group)
+        sizes = [(group_range(G, r, world)[1] - group_range(G, r, world)[0]) * C for r in range(world)]
+        verdict = torch.cat([allp[r, 0, :sizes[r]] for r in range(world)])
+        kept = torch.cat([allp[r, 1, :sizes[r]] for r in range(world)]).to(torch.bool)
+        poses = gather_varlen(poses_loc, world, group)
+    else:
+        verdict, kept, poses = v_loc, kept_loc, poses_loc
+    ev[3].record()
+    if poses.shape[0]:
+        pr = RmsdPruner(poses, atomnos, rmsd_thr, rank=rank, world=world, group=group)
+        mask = pr.run()
+    else:
+        pr, mask = None, torch.zeros(0, dtype=torch.bool, device=dev)
+    ev[4].record()
+    torch.cuda.synchronize()
+    return {"verdict": verdict, "kept": kept, "poses": poses, "mask": mask, "pruner": pr, "n_poses": G * C,
+            "ms": {"params_clash": ev[0].elapsed_time(ev[1]), "gather_dedup": ev[1].elapsed_time(ev[2]),
+                   "exchange": ev[2].elapsed_time(ev[3]), "prune": ev[3].elapsed_time(ev[4])}}
+

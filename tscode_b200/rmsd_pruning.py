@@ -26,18 +26,38 @@ import functools
 VARIANTS = {"dmma": 0, "fma": 1, "screen": 5}
 
 
-_STAGING = {}
+import threading
+
+_STAGING = {"lock": threading.Lock(), "buf": None, "event": None}
 
 
-def _staging_buffer(numel):
-    """One cached pinned float64 buffer per process, grown on demand (cudaHostAlloc costs tens of ms: paid once).
-    Calls are serialised by the caller's synchronisation at the end of every prune."""
-    import torch
-    buf = _STAGING.get("buf")
-    if buf is None or buf.numel() < numel:
-        buf = torch.empty(numel, dtype=torch.float64).pin_memory()
-        _STAGING["buf"] = buf
-    return buf[:numel]
+class _Staging:
+    """The process-wide pinned float64 staging buffer for pageable inputs (cudaHostAlloc costs tens of ms: paid once,
+    grown on demand), handed out to ONE upload at a time: acquire() takes the lock and waits for the DMA of the
+    previous user to drain (its event), release(event) records the new user's last copy.  Two pruners built before
+    either runs, or two threads pruning at once, therefore never share live staging memory."""
+
+    @staticmethod
+    def acquire(numel):
+        import torch
+        _STAGING["lock"].acquire()
+        try:
+            if _STAGING["event"] is not None:
+                _STAGING["event"].synchronize()
+                _STAGING["event"] = None
+            buf = _STAGING["buf"]
+            if buf is None or buf.numel() < numel:
+                buf = torch.empty(numel, dtype=torch.float64).pin_memory()
+                _STAGING["buf"] = buf
+            return buf[:numel]
+        except BaseException:
+            _STAGING["lock"].release()
+            raise
+
+    @staticmethod
+    def release(event):
+        _STAGING["event"] = event
+        _STAGING["lock"].release()
 
 
 @functools.lru_cache(maxsize=8)
@@ -125,16 +145,22 @@ class RmsdPruner:
             src = torch.as_tensor(np.ascontiguousarray(structures, dtype=np.float64))
         if src.dim() != 3 or src.shape[2] != 3 or src.shape[1] != atomnos.shape[0]:
             raise ValueError(f"structures must be (N, {atomnos.shape[0]}, 3), got {tuple(src.shape)}")
-        self._staging = None
+        self._needs_staging = False
         if (pipeline_upload and not src.is_cuda and src.dtype == torch.float64 and src.is_contiguous()
                 and src.shape[0] >= 4096):
             # host input: the copy is issued in chunks by run(), overlapped with pack and screen.  Pageable memory
             # (what the reference's callers hold: np.array(poses)) goes through a cached pinned staging buffer,
             # chunk by chunk, so that the host memcpy of one chunk overlaps the DMA of the previous one.
             self._host = src
-            if not src.is_pinned():
-                self._staging = _staging_buffer(src.numel())
-            S = torch.empty(src.shape, dtype=torch.float64, device=self.device)
+            self._needs_staging = not src.is_pinned()
+            if self.world > 1:
+                # several ranks, replicated host input: every rank uploads ONE slice of rows and the slices are
+                # all-gathered over NVLink (_upload_sharded) instead of `world` full uploads from the same host
+                per = (int(src.shape[0]) + self.world - 1) // self.world
+                self._S_all = torch.empty((self.world * per,) + tuple(src.shape[1:]), dtype=torch.float64, device=self.device)
+                S = self._S_all[:src.shape[0]]
+            else:
+                S = torch.empty(src.shape, dtype=torch.float64, device=self.device)
         else:
             S = src.to(self.device, dtype=torch.float64).contiguous()
         self.S = S
@@ -246,7 +272,7 @@ class RmsdPruner:
     def pack(self):
         if self._host is not None:                       # phases driven by hand: plain upload first
             self.S.copy_(self._host)
-            self._host, self._staging = None, None
+            self._host = None
         if self.N == 0 or self.M == 0:
             return
         L = lib()
@@ -355,8 +381,12 @@ class RmsdPruner:
                     dist.all_gather_into_tensor(lists, self.pair_list[:stride], group=self.group)
             else:
                 lists = self.pair_list
-            check(L.tsc_elim_fused(ptr(lists), self.world, stride, self.N, 20, ptr(self.fused_ws),
-                                   ptr(self.fused_out), stream_ptr()), "tsc_elim_fused")
+            rc = L.tsc_elim_fused(ptr(lists), self.world, stride, self.N, 20, ptr(self.fused_ws),
+                                  ptr(self.fused_out), stream_ptr())
+            if rc == 1:                   # cudaErrorInvalidValue: the ensemble is too large for the fused kernel's
+                self._fused_enqueued = "unavailable"      # shared-memory bitmaps (N > ~690 000): bit-row ladder instead
+                return
+            check(rc, "tsc_elim_fused")
         self._fused_enqueued = tier if self.world > 1 else "full"
 
     def _eliminate_fused(self):
@@ -367,16 +397,21 @@ class RmsdPruner:
         while True:
             tier = self._fused_enqueued
             self._fused_enqueued = None
+            if tier == "unavailable":
+                return None
             with torch.cuda.device(self.device):
                 info = self.fused_out[self._info_off:self._info_off + 128].view(torch.int32).tolist()   # sync
             if info[0] == 1 and tier == "small":
                 self._enqueue_fused("full")               # a list did not fit the short prefix
                 continue
             break
-        if info[0] == 1:
-            return None                                   # pair list overflow -> bit rows (same on every rank)
         if info[0] != 0:
-            raise RuntimeError(f"tsc_elim_fused did not complete (status {info[0]})")
+            # 1: a pair list overflowed; anything else: the kernel gave up at a grid barrier (bounded spin, e.g. under a
+            # profiler or pre-emption).  Either way the bit-row ladder decides (same decision on every rank: all see
+            # the same headers; an abort on one rank only would desynchronise the ranks' collectives, so it raises)
+            if info[0] != 1 and self.world > 1:
+                raise RuntimeError(f"tsc_elim_fused did not complete (status {info[0]})")
+            return None
         self._rounds_fused = [int(k) for k in info[8:8 + info[1]]]
         self.ladder_used = "fused"
         return self.fused_out[:N].to(torch.bool)
@@ -462,8 +497,12 @@ class RmsdPruner:
         torch = self.torch
         host, N = self._host, self.N
         self._host = None                                # the next run() works from the device copy
+        if self.world > 1 and N:
+            self._upload_sharded(host)
+            self.pack()
+            self.screen()
+            return
         if self.variant != 5 or N == 0 or self.M == 0:
-            self._staging = None
             self.S.copy_(host)
             self.pack()
             self.screen()
@@ -480,19 +519,23 @@ class RmsdPruner:
             copy = _copy_stream(str(self.device))
             copy.wait_stream(main)
             events = []
-            stage = self._staging.view(host.shape) if self._staging is not None else None
-            self._staging = None
-            with torch.cuda.stream(copy):
-                for c in reversed(range(n_chunks)):
-                    lo, hi = bounds[c], bounds[c + 1]
-                    if stage is not None:
-                        stage[lo:hi].copy_(host[lo:hi])                  # host threads; the previous DMA is in flight
-                        self.S[lo:hi].copy_(stage[lo:hi], non_blocking=True)
-                    else:
-                        self.S[lo:hi].copy_(host[lo:hi], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(copy)
-                    events.append((c, ev))
+            stage = _Staging.acquire(host.numel()).view(host.shape) if self._needs_staging else None
+            ev = None
+            try:
+                with torch.cuda.stream(copy):
+                    for c in reversed(range(n_chunks)):
+                        lo, hi = bounds[c], bounds[c + 1]
+                        if stage is not None:
+                            stage[lo:hi].copy_(host[lo:hi])              # host threads; the previous DMA is in flight
+                            self.S[lo:hi].copy_(stage[lo:hi], non_blocking=True)
+                        else:
+                            self.S[lo:hi].copy_(host[lo:hi], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(copy)
+                        events.append((c, ev))
+            finally:
+                if stage is not None:
+                    _Staging.release(ev)
             self.stats.zero_()
             self.cand_list[0].fill_(0)
             self._pairs_ready = False
@@ -514,6 +557,40 @@ class RmsdPruner:
                                             ptr(self.cand_list), self.cand_stride, self.grid_ctas, self.screen_mode,
                                             self.pace, st), "tsc_rmsd_screen")
         self.packed_ready = True
+
+    def row_slice(self):
+        """[lo, hi): the contiguous rows this rank uploads (and whose survivors it returns) when the host input is
+        replicated on several ranks."""
+        per = (self.N + self.world - 1) // self.world
+        lo = min(self.rank * per, self.N)
+        return lo, min(lo + per, self.N)
+
+    def _upload_sharded(self, host):
+        """Several ranks, the same host array on each: rank r copies rows [r per, (r + 1) per) to its GPU (1 / world of
+        the bytes over its own PCIe link) and one NCCL all_gather_into_tensor over NVLink completes the ensemble on
+        every GPU — world full uploads from one host made the end-to-end call SLOWER with every GPU added."""
+        import torch.distributed as dist
+        torch = self.torch
+        lo, hi = self.row_slice()
+        per = self._S_all.shape[0] // self.world
+        with torch.cuda.device(self.device):
+            mine = self._S_all[self.rank * per:(self.rank + 1) * per]
+            if hi > lo:
+                if self._needs_staging:
+                    stage = _Staging.acquire((hi - lo) * host[0].numel()).view((hi - lo,) + tuple(host.shape[1:]))
+                    ev = None
+                    try:
+                        stage.copy_(host[lo:hi])
+                        mine[:hi - lo].copy_(stage, non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record()
+                    finally:
+                        _Staging.release(ev)
+                else:
+                    mine[:hi - lo].copy_(host[lo:hi], non_blocking=True)
+            if hi - lo < per:
+                mine[hi - lo:].zero_()
+            dist.all_gather_into_tensor(self._S_all.view(-1), mine.reshape(-1), group=self.group)
 
     def set_pairs(self, pairs):
         """Replace this rank's confirmed-pair list by explicit (i, j) rows, i < j (tests)."""
@@ -543,34 +620,62 @@ class RmsdPruner:
         return rows, dense
 
 
-def prune_conformers_rmsd(structures, atomnos, rmsd_thr=0.5):
+def prune_conformers_rmsd(structures, atomnos, rmsd_thr=0.5, *, group=None, rank=None, world=None, pinned_output=True):
     """Drop-in for tscode.rmsd_pruning.prune_conformers_rmsd (rmsd_pruning.py:164-206).
 
     Removes similar structures (rmsd < rmsd_thr and max atomic deviation < 2*rmsd_thr on the
     non-hydrogen atoms, rotation-only Kabsch about the origin) with the reference's k-ladder,
-    cache behaviour included.  Returns (structures[mask], mask) as numpy arrays."""
+    cache behaviour included.  Returns (structures[mask], mask) as numpy arrays.
+
+    Several GPUs (one process per GPU, torch.distributed NCCL group, the SAME host array on every rank): pass
+    `group` (or rank / world).  Every rank uploads 1 / world of the rows, the rest arrives over NVLink, the pair matrix
+    is row-sharded, and every rank returns the FULL mask and the survivors of its own contiguous row slice
+    (RmsdPruner.row_slice) — concatenated in rank order they are structures[mask].
+
+    Large ensembles come back in page-locked host memory (the survivors are gathered on the GPU and copied out at
+    PCIe speed instead of being re-indexed by the host); pinned_output=False returns ordinary pageable memory."""
     structures = np.asarray(structures)
     N = structures.shape[0]
     if N == 0:
         return structures[:0], np.zeros(0, dtype=np.bool_)
-    pr = RmsdPruner(structures, atomnos, rmsd_thr)
+    if group is not None or world is not None:
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if world is None else int(world)
+        rank = dist.get_rank(group) if rank is None else int(rank)
+    else:
+        rank, world = 0, 1
+    pr = RmsdPruner(structures, atomnos, rmsd_thr, rank=rank, world=world, group=group)
     pr.run_async()
+    import torch
     big = (structures.flags.c_contiguous and structures.dtype == np.float64 and structures.nbytes > (1 << 22))
+    lo, hi = pr.row_slice()
     out_buf = None
-    if big:
-        # while the GPU works: allocate the output and first-touch its pages with all host threads (page faults on
-        # a fresh 100 MB array cost more than the copy into it)
-        import torch
-        out_buf = torch.empty(structures.shape, dtype=torch.float64)
-        out_buf.zero_()
-    mask = pr.finish().cpu().numpy().astype(np.bool_)
+    if big and pinned_output:
+        # while the GPU works: the output buffer (page-locked, from torch's caching host allocator: no cudaHostAlloc
+        # after the first call of a size)
+        out_buf = torch.empty((hi - lo,) + structures.shape[1:], dtype=torch.float64, pin_memory=True)
+    elif big:
+        out_buf = torch.empty((hi - lo,) + structures.shape[1:], dtype=torch.float64)
+        out_buf.zero_()                   # first touch with all host threads (page faults cost more than the copy)
+    mask_dev = pr.finish()
+    if out_buf is not None and pinned_output:
+        with torch.cuda.device(pr.device):
+            idx = torch.nonzero(mask_dev[lo:hi]).squeeze(1)                  # (one sync: the survivor count)
+            n = int(idx.numel())
+            mask_host = torch.empty(N, dtype=torch.bool, pin_memory=True)
+            mask_host.copy_(mask_dev, non_blocking=True)
+            if n:
+                dev_rows = torch.index_select(pr.S[lo:hi], 0, idx)           # survivors gathered on the GPU ...
+                out_buf[:n].copy_(dev_rows, non_blocking=True)              # ... and copied out at PCIe speed
+            torch.cuda.current_stream().synchronize()
+        return out_buf[:n].numpy(), mask_host.numpy().astype(np.bool_, copy=True)
+    mask = mask_dev.cpu().numpy().astype(np.bool_)
     if out_buf is not None:
-        import torch
-        idx = torch.from_numpy(np.flatnonzero(mask))
+        idx = torch.from_numpy(np.flatnonzero(mask[lo:hi]))
         out = out_buf[:idx.numel()]
-        torch.index_select(torch.from_numpy(structures), 0, idx, out=out)
+        torch.index_select(torch.from_numpy(structures)[lo:hi], 0, idx, out=out)
         return out.numpy(), mask
-    return _take_rows(structures, mask), mask
+    return _take_rows(structures[lo:hi], mask[lo:hi]), mask
 
 
 def _take_rows(structures, mask):
