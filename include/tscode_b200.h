@@ -240,13 +240,13 @@ int tsc_cyclical_embed_params(const double* ref2, const double* tgt2, const doub
  *   quaternion of algebra.py:325-344 is bit-identical); rot_mask (T, A) uint8 = _get_rotation_mask
  *   (:301-325); node_mask (T, A) uint8 = heavy atoms of the rotor's sub-graph (:964-977).
  *   sim_bits (N, (N+31)/32) uint32: rows [row_begin,row_end) are zeroed, then bit j of row i set iff
- *   rmsd < max_rmsd (:1118).  codes (N, N) uint32 or NULL: best angle index of rotor t in bits
+ *   rmsd < max_rmsd (:1118).  codes (N, N) uint64 or NULL (at most 20 rotors): best angle index of rotor t in bits
  *   [3t, 3t+3).  rmsd_out (N, N) or NULL.  near_count (1) uint64: pairs within 1e-6 A of max_rmsd. */
 int tsc_rotcorr_pairs(const double* Sc, int64_t N, int32_t A, const uint8_t* heavy, int32_t T,
                       const int32_t* tor_i2, const int32_t* tor_i3, const int32_t* n_ang,
                       const double* sin_half, const double* cos_half, const uint8_t* rot_mask,
                       const uint8_t* node_mask, int64_t row_begin, int64_t row_end, double max_rmsd,
-                      uint32_t* sim_bits, uint32_t* codes, double* rmsd_out, uint64_t* near_count,
+                      uint32_t* sim_bits, uint64_t* codes, double* rmsd_out, uint64_t* near_count,
                       void* stream);
 /* [host] Inner loop of the grouping replay for one chunk [base, hi) of a ladder round, driven by the forward
  * scan's results (all pointers are HOST pointers): row i visits the columns (reach[i], min(first_hit[i], hi) - 1]
@@ -254,18 +254,19 @@ int tsc_rotcorr_pairs(const double* Sc, int64_t N, int32_t A, const uint8_t* hea
  * (torsion_module.py:1004-1008 as rotor-state algebra); matches are returned chunk-relative in the reference's
  * insertion order.  compact[off[i] + k] = 3-bit-per-rotor code of pair (i, i + 1 + k); ang_table (T, 6). */
 int64_t tsc_host_rotcorr_chunk(int64_t base, int64_t hi, const int64_t* first_hit, int64_t* reach, double* state,
-                               int32_t T, const uint32_t* compact, const int64_t* off, const double* ang_table,
+                               int32_t T, const uint64_t* compact, const int64_t* off, const double* ang_table,
                                int32_t* match_i, int32_t* match_j);
 /* Forward scan for the stateless mode at large N: first_hit[i] = min{ j > i : rmsd(i, j) < max_rmsd } (N if
- * none) for rows [row_begin, row_end).  The grouping loop (torsion_module.py:1098-1125) stops at the first
+ * none) for rows row_begin, row_begin + row_stride, ... < row_end (row_stride = number of ranks when the rows are
+ * dealt round-robin; 1 otherwise).  The grouping loop (torsion_module.py:1098-1125) stops at the first
  * similar later structure and caches dissimilar pairs, so first_hit plus the best-angle codes of the pairs
  * (i, j <= first_hit[i]) — written into the dense (N, N) codes / rmsd_out arrays, either may be NULL — is all
  * it needs.  One CTA per row, 8 pairs at a time, early exit.  row_counter: one int32 of scratch. */
 int tsc_rotcorr_scan(const double* Sc, int64_t N, int32_t A, const uint8_t* heavy, int32_t T,
                      const int32_t* tor_i2, const int32_t* tor_i3, const int32_t* n_ang,
                      const double* sin_half, const double* cos_half, const uint8_t* rot_mask,
-                     const uint8_t* node_mask, int64_t row_begin, int64_t row_end, double max_rmsd,
-                     int32_t* first_hit, uint32_t* codes, double* rmsd_out, uint64_t* near_count,
+                     const uint8_t* node_mask, int64_t row_begin, int64_t row_end, int64_t row_stride,
+                     double max_rmsd, int32_t* first_hit, uint64_t* codes, double* rmsd_out, uint64_t* near_count,
                      int32_t* row_counter, void* stream);
 /* Stateful mode — exact emulation of the reference's in-place mutation (utils.py:412 through
  * torsion_module.py:984-1008), one row of the grouping loop (:1101-1125) at a time:
@@ -277,7 +278,7 @@ int tsc_rotcorr_row(const double* cur, int64_t N, int32_t A, const uint8_t* heav
                     const int32_t* tor_i2, const int32_t* tor_i3, const int32_t* n_ang,
                     const double* sin_half, const double* cos_half, const uint8_t* rot_mask,
                     const uint8_t* node_mask, int64_t i, const int32_t* js, int32_t n, double* rmsd,
-                    uint32_t* codes, double* staged, void* stream);
+                    uint64_t* codes, double* staged, void* stream);
 int tsc_rotcorr_commit(double* cur, const double* staged, const int32_t* js, int32_t n_accept, int32_t A,
                        void* stream);
 

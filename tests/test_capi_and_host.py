@@ -275,3 +275,45 @@ def test_balanced_items_dealt_like_the_kernel_cover_every_tile_once(N):
                         items = _host.build_screen_items(N, rb, n_ctas, panel_lo=lo, panel_hi=hi, tile_j=tile_j)
                         seen = _deal_like_the_kernel(items, n_ctas)
                         assert set(seen) == want and all(v == 1 for v in seen.values()), (N, world, rank, n_ctas, lo, hi, tile_j)
+
+
+def test_cluster_survivor_choice_equals_networkx():
+    """torsion_module._cluster_rejects_fast restates how the reference picks the survivor of every cluster — nx.Graph(set
+    of matches) -> connected_components -> tuple(subgraph.nodes)[0] (torsion_module.py:1136-1152, numba_functions.py,
+    optimization_methods.py:341-355) — with plain dicts and sets; it must give networkx's answer for sets (whose
+    iteration order decides), lists and sorted lists of edges, trees, cliques and long chains alike."""
+    import random
+    from tscode_b200 import torsion_module as tm
+    rnd = random.Random(7)
+    n_checked = 0
+    for trial in range(1500):
+        m = rnd.choice((2, 3, 5, 8, 9, 16, 33, 100, 700, 5000))
+        kind = trial % 4
+        es = set()
+        if kind == 0:                                   # random sparse
+            for _ in range(rnd.randrange(1, 2 * m)):
+                a, b = rnd.randrange(m), rnd.randrange(m)
+                if a != b:
+                    es.add((min(a, b), max(a, b)))
+        elif kind == 1:                                 # first-hit structure: every row points to one later row
+            for a in range(m - 1):
+                if rnd.random() < 0.6:
+                    es.add((a, rnd.randrange(a + 1, m)))
+        elif kind == 2:                                 # chains
+            start = rnd.randrange(m)
+            for a in range(start, min(m - 1, start + rnd.randrange(1, 40))):
+                es.add((a, a + 1))
+        else:                                           # a few dense clusters
+            for _ in range(3):
+                nodes = rnd.sample(range(m), min(m, rnd.randrange(2, 7)))
+                for x in nodes:
+                    for y in nodes:
+                        if x < y:
+                            es.add((x, y))
+        if not es:
+            continue
+        for E in (es, list(es), sorted(es), sorted(es, reverse=True)):
+            assert sorted(tm._cluster_rejects_fast(E)) == sorted(tm._cluster_rejects_nx(E)), (trial, kind)
+            n_checked += 1
+    assert n_checked > 3000
+    assert tm._cluster_rejects([(0, 1), (1, 2), (5, 6)]) is not None and tm._CLUSTER_IMPL[0] is tm._cluster_rejects_fast

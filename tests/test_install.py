@@ -3,6 +3,7 @@ container (skipped on the GPU box).  No compute is executed."""
 import os
 import sys
 
+import numpy as np
 import pytest
 
 from conftest import ROOT
@@ -20,7 +21,22 @@ def test_install_rebinds_every_importer():
     import tscode.torsion_module as tm
     from tscode_b200 import install, numba_functions, rmsd_pruning, torsion_module
     orig = rp.prune_conformers_rmsd
+    # default: whole-ensemble functions and the orchestrator's loops only — the per-call scalars stay numba's
     patched = install.install_into()
+    try:
+        assert rp.prune_conformers_rmsd is rmsd_pruning.prune_conformers_rmsd
+        assert nf.compenetration_check is not numba_functions.compenetration_check
+        assert emb.get_embed is not numba_functions.get_embed
+        assert rp.rmsd_and_max_numba is not rmsd_pruning.rmsd_and_max_numba
+        from tscode.embedder import RunEmbedding
+        assert RunEmbedding.compenetration_refining is install.compenetration_refining
+        assert RunEmbedding.fitness_refining is install.fitness_refining
+        assert ("tscode.embedder.RunEmbedding", "compenetration_refining") in patched
+    finally:
+        install.uninstall()
+    from tscode.embedder import RunEmbedding
+    assert RunEmbedding.compenetration_refining is not install.compenetration_refining
+    patched = install.install_into(scalars=True)
     try:
         assert rp.prune_conformers_rmsd is rmsd_pruning.prune_conformers_rmsd
         assert rp._rmsd_similarity is rmsd_pruning._rmsd_similarity
@@ -41,3 +57,81 @@ def test_install_rebinds_every_importer():
         install.uninstall()
     assert rp.prune_conformers_rmsd is orig
     assert emb.compenetration_check is not numba_functions.compenetration_check
+
+
+class _StubRun:
+    """The attributes RunEmbedding.compenetration_refining / fitness_refining touch (embedder.py:1119-1134, :973-984,
+    :1230-1313), around real Embedder methods."""
+
+    def __init__(self, embed, structures, ids, constrained_indices, targets_by_pair):
+        import types
+        from tscode.embedder import RunEmbedding
+        self.embed, self.structures, self.ids = embed, structures, ids
+        self.constrained_indices = constrained_indices
+        self.options = types.SimpleNamespace(max_clashes=0, clash_thresh=1.5)
+        self.energies = np.zeros(len(structures))
+        self.exit_status = np.ones(len(structures), dtype=bool)
+        self.lines = []
+        self._targets = targets_by_pair
+        self.apply_mask = types.MethodType(RunEmbedding.apply_mask, self)
+
+    def log(self, string='', p=True):
+        self.lines.append(string)
+
+    def zero_candidates_check(self):
+        assert len(self.structures) > 0
+
+    def get_pairing_dists_from_constrained_indices(self, pair):
+        return self._targets.get((int(pair[0]), int(pair[1])))
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="reference tree not present")
+def test_batched_loop_patches_equal_the_reference_methods(monkeypatch):
+    """install.compenetration_refining / fitness_refining against the reference's own methods run on the same stub
+    `self` (build container: no GPU, so the two batched device calls are stood in for by the oracles — the device calls
+    themselves are parity-tested on the GPU): masks, surviving arrays and log lines must be identical."""
+    import re
+    ref_harness.install(full=True)
+    from tscode.embedder import RunEmbedding
+    from oracle import oracle_c, oracle_np
+    from tscode_b200 import install, numba_functions, optimization_methods
+    from tscode_b200.synth import gen_poses, materialise_poses
+
+    monkeypatch.setattr(numba_functions, "compenetration_check_batch",
+                        lambda S, ids=None, thresh=1.5, max_clashes=0, **kw: oracle_c.clash_structs(np.asarray(S), ids, thresh, max_clashes))
+
+    def scores(S, cons, targets):
+        S, cons = np.asarray(S), np.asarray(cons)
+        err = np.zeros(len(S))
+        for p in range(len(S)):
+            e = 0
+            for (a, b), t in zip(cons[p], targets[p]):
+                if t is not None:
+                    e += np.linalg.norm(S[p][a] - S[p][b]) - t
+            err[p] = e
+        return np.abs(err).astype(np.float32), err
+    monkeypatch.setattr(optimization_methods, "constraint_scores", scores)
+
+    frags, conf, R, t = gen_poses(3, 400, (20, 25), dmin=2.0, dmax=7.0)
+    S = materialise_poses(frags, conf, R, t)
+    ids = np.array([20, 25])
+    rng = np.random.default_rng(0)
+    cons = np.stack([np.array([[rng.integers(0, 20), 20 + rng.integers(0, 25)], [rng.integers(0, 20), 20 + rng.integers(0, 25)]])
+                     for _ in range(400)])
+    targets = {(int(a), int(b)): float(rng.uniform(2.0, 6.0)) for a, b in cons[::2, 0]}       # half of the first pairs have a target
+    strip = lambda lines: [re.sub(r"\(\d+ left, .*\)", "(left)", l) for l in lines]
+    for embed in ("multiembed", "cyclical"):
+        a, b = _StubRun(embed, S.copy(), ids, cons.copy(), targets), _StubRun(embed, S.copy(), ids, cons.copy(), targets)
+        RunEmbedding.compenetration_refining(a)
+        install.compenetration_refining(b)
+        assert np.array_equal(a.structures, b.structures) and np.array_equal(a.constrained_indices, b.constrained_indices)
+        assert 0 < len(a.structures) and (embed == "cyclical" or len(a.structures) < 400)
+        assert strip(a.lines) == strip(b.lines)
+        assert np.array_equal(a.energies, b.energies) and np.array_equal(a.exit_status, b.exit_status)
+        for thr in (5, 0.5):
+            a2, b2 = (_StubRun(embed, x.structures.copy(), ids, x.constrained_indices.copy(), targets) for x in (a, b))
+            RunEmbedding.fitness_refining(a2, threshold=thr, verbose=True)
+            install.fitness_refining(b2, threshold=thr, verbose=True)
+            assert np.array_equal(a2.structures, b2.structures) and a2.lines == b2.lines
+            assert np.array_equal(a2.energies, b2.energies) and len(a2.structures) > 0
+

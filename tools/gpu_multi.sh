@@ -1,7 +1,7 @@
 #!/bin/bash
 # Multi-GPU parity + bench (one box, N GPUs).  Usage: bash tools/gpu_multi.sh <N> [tag]
 N=${1:-2}
-TAG=${2:-r01m$N}
+TAG=${2:-r02m$N}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi -L > $OUT/gpus.txt

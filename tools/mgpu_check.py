@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Multi-GPU parity check (run under torchrun, one rank per GPU): the row-sharded prune with an
-NCCL all-gather per elimination round must give the single-GPU / live-reference mask."""
+"""Multi-GPU parity check (run under torchrun, one rank per GPU): the row-sharded prune, the drop-in with a process
+group, the row-sharded rot_corr scan and the group-sharded embed pipeline must give the live-reference digests."""
 import json
 import os
 import sys
@@ -29,6 +29,54 @@ for r in gold:
     if rank == 0:
         print(f"world={world} N={r['N']} M={r['M']} survivors={int(mask.sum())} digest={mask_digest(mask)} "
               f"{'OK' if good else 'MISMATCH'} rounds={pr.rounds}", flush=True)
+# ---- the public drop-in with a process group: sharded upload, full mask, survivors of the rank's row slice ----
+from tscode_b200.rmsd_pruning import prune_conformers_rmsd  # noqa: E402
+r = [x for x in gold if x["N"] == 10000][0]
+S = gen_ensemble(r["seed"], r["N"], r["M"], r["n_clusters"], sigma_noise=r["sigma_noise"])
+out, mask = prune_conformers_rmsd(S, np.full(r["M"], 6), r["thr"], group=dist.group.WORLD)
+per = (r["N"] + world - 1) // world
+lo, hi = rank * per, min((rank + 1) * per, r["N"])
+good = mask_digest(mask) == r["digest"] and np.array_equal(out, S[lo:hi][mask[lo:hi]])
+ok &= good
+if rank == 0:
+    print(f"world={world} drop-in with group: digest {'OK' if good else 'MISMATCH'}; rank 0 returned {out.shape[0]} survivors", flush=True)
+
+# ---- rot_corr, rows of the forward scan dealt round-robin ----
+sys.path.insert(0, "oracle")
+import rotor_molecules as rm  # noqa: E402
+from tscode_b200.torsion_module import TorsionInfo, prune_conformers_rmsd_rot_corr  # noqa: E402
+gb = json.load(open("tests/golden/rotcorr_big.json"))["fixtures"]
+for name, f in gb.items():
+    g = np.load(f"tests/golden/rotcorr_{name}.npz")
+    info = TorsionInfo([tuple(t) for t in f["torsions"]], [tuple(a) for a in f["angles"]], g["rot_masks"].astype(bool),
+                       g["node_lists"].astype(bool))
+    S4, at4 = rm.ensemble_tritbu63(f["seed"], f["N"])
+    import time
+    prune_conformers_rmsd_rot_corr(S4, at4, None, f["thr"], torsion_info=info, max_structures=None, mode="stateless",
+                                   group=dist.group.WORLD)
+    dist.barrier(); t0 = time.perf_counter()
+    o4, m4 = prune_conformers_rmsd_rot_corr(S4, at4, None, f["thr"], torsion_info=info, max_structures=None, mode="stateless",
+                                            group=dist.group.WORLD)
+    dt = time.perf_counter() - t0
+    good = mask_digest(m4) == f["digest"]
+    ok &= good
+    if rank == 0:
+        print(f"world={world} rot_corr {name}: survivors={int(m4.sum())} {'OK' if good else 'MISMATCH'} {dt * 1e3:.0f} ms", flush=True)
+
+# ---- configs[4] pipeline, groups dealt to the ranks ----
+from tscode_b200.embeds import cyclical_embed_pipeline  # noqa: E402
+from tscode_b200.synth import gen_cyclical_groups  # noqa: E402
+pipe = json.load(open("tests/golden/embed_pipeline.json"))["rows"]
+for name in ("small", "c5"):
+    rr = pipe[name]
+    d = gen_cyclical_groups(rr["seed"], rr["n_groups"])
+    res = cyclical_embed_pipeline(d, np.full(150, 6), rank=rank, world=world, group=dist.group.WORLD)
+    v, k, m = res["verdict"].cpu().numpy(), res["kept"].cpu().numpy(), res["mask"].cpu().numpy()
+    good = mask_digest(v) == rr["clash_digest"] and mask_digest(k) == rr["kept_digest"] and mask_digest(m) == rr["prune_digest"]
+    ok &= good
+    if rank == 0:
+        print(f"world={world} embed pipeline {name}: {int(v.sum())} / {int(k.sum())} / {int(m.sum())} {'OK' if good else 'MISMATCH'} {res['ms']}", flush=True)
+
 t = torch.tensor([int(ok)], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 dist.barrier()

@@ -32,7 +32,7 @@ extern "C" int32_t tsc_device_sm_count(void) {
 // ------------------------------------------------------------------------------------------
 #include <math.h>
 extern "C" int64_t tsc_host_rotcorr_chunk(int64_t base, int64_t hi, const int64_t* first_hit, int64_t* reach,
-                                          double* state, int32_t T, const uint32_t* compact, const int64_t* off,
+                                          double* state, int32_t T, const uint64_t* compact, const int64_t* off,
                                           const double* ang_table, int32_t* match_i, int32_t* match_j) {
     int64_t n_match = 0;
     for (int64_t i = base; i < hi; i++) {
@@ -40,17 +40,17 @@ extern "C" int64_t tsc_host_rotcorr_chunk(int64_t base, int64_t hi, const int64_
         const int64_t new_hi = (p - 1 < hi - 1) ? p - 1 : hi - 1;
         const int64_t lo = reach[i] + 1;
         const double* si = state + i * T;
-        const uint32_t* ci = T > 0 ? compact + off[i] - (i + 1) : nullptr;      // code of (i, j) at ci[j]
+        const uint64_t* ci = T > 0 ? compact + off[i] - (i + 1) : nullptr;      // code of (i, j) at ci[j]
         for (int64_t j = lo; T > 0 && j <= new_hi; j++) {
-            const uint32_t c = ci[j];
+            const uint64_t c = ci[j];
             double* sj = state + j * T;
-            for (int t = 0; t < T; t++) sj[t] = fmod(ang_table[t * 6 + ((c >> (3 * t)) & 7u)] + si[t], 360.0);
+            for (int t = 0; t < T; t++) sj[t] = fmod(ang_table[t * 6 + ((c >> (3 * t)) & 7ull)] + si[t], 360.0);
         }
         if (new_hi >= lo) reach[i] = new_hi;
         if (p < hi) {
-            const uint32_t c = T > 0 ? ci[p] : 0u;
+            const uint64_t c = T > 0 ? ci[p] : 0ull;
             double* sj = state + p * T;
-            for (int t = 0; t < T; t++) sj[t] = fmod(ang_table[t * 6 + ((c >> (3 * t)) & 7u)] + si[t], 360.0);
+            for (int t = 0; t < T; t++) sj[t] = fmod(ang_table[t * 6 + ((c >> (3 * t)) & 7ull)] + si[t], 360.0);
             match_i[n_match] = (int32_t)(i - base);
             match_j[n_match] = (int32_t)(p - base);
             n_match++;

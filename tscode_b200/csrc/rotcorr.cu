@@ -23,7 +23,7 @@
 namespace tsc {
 
 constexpr int RC_WARPS = 8;
-constexpr int RC_MAX_T = 10;
+constexpr int RC_MAX_T = 20;                // rotors per molecule: 3 bits of best-angle code each in a 64-bit word
 constexpr int RC_MAX_ANG = 6;
 
 struct RotCorrParams {
@@ -40,10 +40,11 @@ struct RotCorrParams {
     const uint8_t* rot_mask;     // (T, A)
     const uint8_t* node_mask;    // (T, A)
     int64_t row_begin, row_end;
+    int64_t row_stride;          // forward scan: rows row_begin, row_begin + row_stride, ... (row sharding over ranks)
     double max_rmsd;
     uint32_t* sim_bits;          // (N, Wb)
     int64_t Wb;
-    uint32_t* codes;             // (N, N) or null
+    uint64_t* codes;             // (N, N) or null: best angle index of rotor t at bits [3t, 3t + 3)
     double* rmsd_out;            // (N, N) or null
     unsigned long long* near_count;
 };
@@ -71,9 +72,9 @@ __device__ __forceinline__ void rot_point(const double R[9], double cx, double c
 // reference's in-place mutation).  All lanes return the same rmsd / code.
 __device__ __forceinline__ double rotcorr_eval(const RotCorrParams& p, const double* rx, const double* ry,
                                                const double* rz, double* cx, double* cy, double* cz, int lane,
-                                               uint32_t& code_out) {
+                                               uint64_t& code_out) {
     const int A = p.A;
-    uint32_t code = 0;
+    uint64_t code = 0;
     int best_idx[RC_MAX_T];
     // ---- search phase: every rotor on the unmodified second structure (:982-999) ----
     for (int t = 0; t < p.T; t++) {
@@ -109,7 +110,7 @@ __device__ __forceinline__ double rotcorr_eval(const RotCorrParams& p, const dou
             if (local < best) { best = local; bi = k; }
         }
         best_idx[t] = bi;
-        code |= (uint32_t)bi << (3 * t);
+        code |= (uint64_t)bi << (3 * t);
     }
     // ---- apply phase: best rotations in torsion order, each about the CURRENT axis (:1004-1008) ----
     for (int t = 0; t < p.T; t++) {
@@ -167,11 +168,11 @@ __device__ __forceinline__ double rotcorr_eval(const RotCorrParams& p, const dou
 // rotor by its angle, accumulates its own covariance and solves its own eigenproblem.  The best angle per
 // rotor is then a warp minimum over the lanes of that rotor (lowest angle index on exact ties, as the
 // reference's strict `<` in ascending order, torsion_module.py:994).  Apply phase and global RMSD unchanged.
-//   abits[a]: bit t = atom a moves with rotor t (rotation mask), bit 16 + t = atom a belongs to rotor t's
+//   abits[a]: bit t = atom a moves with rotor t (rotation mask), bit 32 + t = atom a belongs to rotor t's
 //   heavy-atom sub-graph (staged in shared memory by the caller).
-__device__ __forceinline__ double rotcorr_eval2(const RotCorrParams& p, const uint32_t* __restrict__ abits,
+__device__ __forceinline__ double rotcorr_eval2(const RotCorrParams& p, const uint64_t* __restrict__ abits,
                                                 const double* rx, const double* ry, const double* rz, double* cx,
-                                                double* cy, double* cz, int lane, uint32_t& code_out) {
+                                                double* cy, double* cz, int lane, uint64_t& code_out) {
     const int A = p.A;
     int best_idx[RC_MAX_T];
 #pragma unroll
@@ -197,9 +198,9 @@ __device__ __forceinline__ double rotcorr_eval2(const RotCorrParams& p, const ui
             rot_from_axis(cx[a2] - ox, cy[a2] - oy, cz[a2] - oz, p.sin_half[tc * RC_MAX_ANG + kc],
                           p.cos_half[tc * RC_MAX_ANG + kc], R);
             double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, G = 0.0, cnt = 0.0;
-            const uint32_t rbit = 1u << tc, nbit = 1u << (16 + tc);
+            const uint64_t rbit = 1ull << tc, nbit = 1ull << (32 + tc);
             for (int a = 0; a < A; a++) {
-                const uint32_t ab = abits[a];
+                const uint64_t ab = abits[a];
                 if (!(ab & nbit)) continue;
                 const double px = rx[a], py = ry[a], pz = rz[a];
                 double qx = cx[a], qy = cy[a], qz = cz[a];
@@ -228,8 +229,8 @@ __device__ __forceinline__ double rotcorr_eval2(const RotCorrParams& p, const ui
         }
         t_begin = t_end;
     }
-    uint32_t code = 0;
-    for (int t = 0; t < p.T; t++) code |= (uint32_t)best_idx[t] << (3 * t);
+    uint64_t code = 0;
+    for (int t = 0; t < p.T; t++) code |= (uint64_t)best_idx[t] << (3 * t);
     // ---- apply phase: best rotations in torsion order, each about the CURRENT axis (:1004-1008) ----
     for (int t = 0; t < p.T; t++) {
         const int k = best_idx[t];
@@ -241,7 +242,7 @@ __device__ __forceinline__ double rotcorr_eval2(const RotCorrParams& p, const ui
                       p.cos_half[t * RC_MAX_ANG + k], R);
         __syncwarp();
         for (int a = lane; a < A; a += 32)
-            if (abits[a] & (1u << t)) {
+            if (abits[a] & (1ull << t)) {
                 double x = cx[a], y = cy[a], z = cz[a];
                 rot_point(R, ox, oy, oz, x, y, z);
                 cx[a] = x; cy[a] = y; cz[a] = z;
@@ -278,12 +279,12 @@ __device__ __forceinline__ double rotcorr_eval2(const RotCorrParams& p, const ui
 }
 
 // rotation / sub-graph masks of every atom as one word (see rotcorr_eval2), into shared memory
-__device__ __forceinline__ void stage_abits(const RotCorrParams& p, uint32_t* abits) {
+__device__ __forceinline__ void stage_abits(const RotCorrParams& p, uint64_t* abits) {
     for (int a = threadIdx.x; a < p.A; a += blockDim.x) {
-        uint32_t w = 0;
+        uint64_t w = 0;
         for (int t = 0; t < p.T; t++) {
-            if (p.rot_mask[(size_t)t * p.A + a]) w |= 1u << t;
-            if (p.node_mask[(size_t)t * p.A + a]) w |= 1u << (16 + t);
+            if (p.rot_mask[(size_t)t * p.A + a]) w |= 1ull << t;
+            if (p.node_mask[(size_t)t * p.A + a]) w |= 1ull << (32 + t);
         }
         abits[a] = w;
     }
@@ -308,14 +309,14 @@ __global__ void __launch_bounds__(RC_WARPS * 32) rotcorr_scan_kernel(const RotCo
     double* ry = rx + A; double* rz = ry + A;
     double* cx = rz + A + (size_t)warp * 3 * A;             // second structure, per warp
     double* cy = cx + A; double* cz = cy + A;
-    uint32_t* abits = reinterpret_cast<uint32_t*>(smem + (size_t)(3 + 3 * RC_WARPS) * A);
+    uint64_t* abits = reinterpret_cast<uint64_t*>(smem + (size_t)(3 + 3 * RC_WARPS) * A);
     stage_abits(p, abits);
     unsigned long long near = 0;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) { s_row = atomicAdd(row_counter, 1); s_hit = 0x7fffffff; }
         __syncthreads();
-        const int64_t i = p.row_begin + s_row;
+        const int64_t i = p.row_begin + (int64_t)s_row * p.row_stride;
         if (i >= p.row_end) break;
         const double* Pi = p.Sc + i * (int64_t)A * 3;
         for (int a = threadIdx.x; a < A; a += blockDim.x) { rx[a] = Pi[3 * a]; ry[a] = Pi[3 * a + 1]; rz[a] = Pi[3 * a + 2]; }
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) rotcorr_scan_kernel(const RotCo
                 const double* Pj = p.Sc + j * (int64_t)A * 3;
                 for (int a = lane; a < A; a += 32) { cx[a] = Pj[3 * a]; cy[a] = Pj[3 * a + 1]; cz[a] = Pj[3 * a + 2]; }
                 __syncwarp();
-                uint32_t code;
+                uint64_t code;
                 const double rmsd = rotcorr_eval2(p, abits, rx, ry, rz, cx, cy, cz, lane, code);
                 if (lane == 0) {
                     if (p.codes) p.codes[i * p.N + j] = code;
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) rotcorr_pairs_kernel(const RotC
     double* rx = smem + (size_t)warp * 6 * A;
     double* ry = rx + A; double* rz = ry + A;
     double* cx = rz + A; double* cy = cx + A; double* cz = cy + A;
-    uint32_t* abits = reinterpret_cast<uint32_t*>(smem + (size_t)RC_WARPS * 6 * A);
+    uint64_t* abits = reinterpret_cast<uint64_t*>(smem + (size_t)RC_WARPS * 6 * A);
     stage_abits(p, abits);
     __syncthreads();
     const int64_t warp_g = (int64_t)blockIdx.x * RC_WARPS + warp;
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) rotcorr_pairs_kernel(const RotC
             cx[a] = Pj[3 * a]; cy[a] = Pj[3 * a + 1]; cz[a] = Pj[3 * a + 2];
         }
         __syncwarp();
-        uint32_t code;
+        uint64_t code;
         const double rmsd = rotcorr_eval2(p, abits, rx, ry, rz, cx, cy, cz, lane, code);
         if (lane == 0) {
             if (rmsd < p.max_rmsd) atomicOr(&p.sim_bits[i * p.Wb + (j >> 5)], 1u << (j & 31));
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) rotcorr_pairs_kernel(const RotC
 // copies of everything visited (tsc_rotcorr_commit).
 __global__ void __launch_bounds__(RC_WARPS * 32) rotcorr_row_kernel(const RotCorrParams p, int64_t i,
                                                                     const int32_t* __restrict__ js, int n,
-                                                                    double* __restrict__ rmsd, uint32_t* __restrict__ codes,
+                                                                    double* __restrict__ rmsd, uint64_t* __restrict__ codes,
                                                                     double* __restrict__ staged) {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) rotcorr_row_kernel(const RotCor
             cx[a] = Pj[3 * a]; cy[a] = Pj[3 * a + 1]; cz[a] = Pj[3 * a + 2];
         }
         __syncwarp();
-        uint32_t code;
+        uint64_t code;
         const double r = rotcorr_eval(p, rx, ry, rz, cx, cy, cz, lane, code);
         __syncwarp();
         double* O = staged + (int64_t)k * A * 3;
@@ -467,18 +468,18 @@ extern "C" int tsc_rotcorr_pairs(const double* Sc, int64_t N, int32_t A, const u
                                  const int32_t* tor_i2, const int32_t* tor_i3, const int32_t* n_ang,
                                  const double* sin_half, const double* cos_half, const uint8_t* rot_mask,
                                  const uint8_t* node_mask, int64_t row_begin, int64_t row_end, double max_rmsd,
-                                 uint32_t* sim_bits, uint32_t* codes, double* rmsd_out, uint64_t* near_count,
+                                 uint32_t* sim_bits, uint64_t* codes, double* rmsd_out, uint64_t* near_count,
                                  void* stream) {
     using namespace tsc;
     if (N <= 1 || row_end <= row_begin) return 0;
     if (T < 0 || T > RC_MAX_T) return (int)cudaErrorInvalidValue;
     RotCorrParams p{Sc, N, A, heavy, T, tor_i2, tor_i3, n_ang, sin_half, cos_half, rot_mask, node_mask, row_begin,
-                    row_end, max_rmsd, sim_bits, (N + 31) / 32, codes, rmsd_out,
+                    row_end, 1, max_rmsd, sim_bits, (N + 31) / 32, codes, rmsd_out,
                     reinterpret_cast<unsigned long long*>(near_count)};
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(sim_bits + row_begin * p.Wb, 0, (size_t)(row_end - row_begin) * p.Wb * 4, st);
     if (e != cudaSuccess) return (int)e;
-    const size_t smem = (size_t)RC_WARPS * 6 * A * sizeof(double) + (size_t)A * 4;
+    const size_t smem = (size_t)RC_WARPS * 6 * A * sizeof(double) + (size_t)A * 8;
     if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
     e = cudaFuncSetAttribute(rotcorr_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -511,11 +512,11 @@ extern "C" int tsc_rotcorr_row(const double* cur, int64_t N, int32_t A, const ui
                                const int32_t* tor_i2, const int32_t* tor_i3, const int32_t* n_ang,
                                const double* sin_half, const double* cos_half, const uint8_t* rot_mask,
                                const uint8_t* node_mask, int64_t i, const int32_t* js, int32_t n, double* rmsd,
-                               uint32_t* codes, double* staged, void* stream) {
+                               uint64_t* codes, double* staged, void* stream) {
     using namespace tsc;
     if (n <= 0) return 0;
     if (T < 0 || T > RC_MAX_T) return (int)cudaErrorInvalidValue;
-    RotCorrParams p{cur, N, A, heavy, T, tor_i2, tor_i3, n_ang, sin_half, cos_half, rot_mask, node_mask, 0, 0,
+    RotCorrParams p{cur, N, A, heavy, T, tor_i2, tor_i3, n_ang, sin_half, cos_half, rot_mask, node_mask, 0, 0, 1,
                     0.0, nullptr, 0, nullptr, nullptr, nullptr};
     const size_t smem = (size_t)RC_WARPS * 6 * A * sizeof(double);
     if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
@@ -539,28 +540,30 @@ extern "C" int tsc_rotcorr_commit(double* cur, const double* staged, const int32
     return 0;
 }
 
-// Forward scan of rows [row_begin, row_end): first_hit[i] = first j > i with rmsd(i, j) < max_rmsd (N if none);
+// Forward scan of rows row_begin, row_begin + row_stride, ... < row_end (row_stride = number of ranks when the rows are
+// dealt round-robin): first_hit[i] = first j > i with rmsd(i, j) < max_rmsd (N if none);
 // codes / rmsd_out (dense (N, N), may be NULL) are written for the pairs evaluated on the way (at least every
 // j <= first_hit[i]).  row_counter: one int32 of scratch.
 extern "C" int tsc_rotcorr_scan(const double* Sc, int64_t N, int32_t A, const uint8_t* heavy, int32_t T,
                                 const int32_t* tor_i2, const int32_t* tor_i3, const int32_t* n_ang,
                                 const double* sin_half, const double* cos_half, const uint8_t* rot_mask,
-                                const uint8_t* node_mask, int64_t row_begin, int64_t row_end, double max_rmsd,
-                                int32_t* first_hit, uint32_t* codes, double* rmsd_out, uint64_t* near_count,
-                                int32_t* row_counter, void* stream) {
+                                const uint8_t* node_mask, int64_t row_begin, int64_t row_end, int64_t row_stride,
+                                double max_rmsd, int32_t* first_hit, uint64_t* codes, double* rmsd_out,
+                                uint64_t* near_count, int32_t* row_counter, void* stream) {
     using namespace tsc;
     if (N <= 0 || row_end <= row_begin) return 0;
-    if (T < 0 || T > RC_MAX_T) return (int)cudaErrorInvalidValue;
+    if (T < 0 || T > RC_MAX_T || row_stride < 1) return (int)cudaErrorInvalidValue;
     RotCorrParams p{Sc, N, A, heavy, T, tor_i2, tor_i3, n_ang, sin_half, cos_half, rot_mask, node_mask, row_begin,
-                    row_end, max_rmsd, nullptr, 0, codes, rmsd_out, reinterpret_cast<unsigned long long*>(near_count)};
+                    row_end, row_stride, max_rmsd, nullptr, 0, codes, rmsd_out,
+                    reinterpret_cast<unsigned long long*>(near_count)};
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(row_counter, 0, 4, st);
     if (e != cudaSuccess) return (int)e;
-    const size_t smem = (size_t)(3 + 3 * RC_WARPS) * A * sizeof(double) + (size_t)A * 4;
+    const size_t smem = (size_t)(3 + 3 * RC_WARPS) * A * sizeof(double) + (size_t)A * 8;
     if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
     e = cudaFuncSetAttribute(rotcorr_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    int64_t blocks = row_end - row_begin;
+    int64_t blocks = (row_end - row_begin + row_stride - 1) / row_stride;
     if (blocks > 148 * 4) blocks = 148 * 4;
     rotcorr_scan_kernel<<<(unsigned)blocks, RC_WARPS * 32, smem, st>>>(p, first_hit, row_counter);
     TSC_CHECK_LAUNCH();

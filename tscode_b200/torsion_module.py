@@ -33,7 +33,7 @@ import numpy as np
 from . import _host
 from ._lib import check, lib, ptr, require_cuda, stream_ptr
 
-MAX_T, MAX_ANG = 10, 6
+MAX_T, MAX_ANG = 20, 6          # rotcorr.cu: 3 bits of best-angle code per rotor in a 64-bit word
 _SYMBOLS = ("X H He Li Be B C N O F Ne Na Mg Al Si P S Cl Ar K Ca Sc Ti V Cr Mn Fe Co Ni Cu Zn Ga Ge As Se Br Kr "
             "Rb Sr Y Zr Nb Mo Tc Ru Rh Pd Ag Cd In Sn Sb Te I Xe").split()
 
@@ -123,7 +123,7 @@ class RotCorrPruner:
         N = self.N
         self.Wb = (N + 31) // 32
         self.sim_bits = torch.zeros((max(N, 1), max(self.Wb, 1)), dtype=torch.int32, device=dev)
-        self.codes = torch.zeros((N, N), dtype=torch.int32, device=dev) if want_codes else None
+        self.codes = torch.empty((N, N), dtype=torch.int64, device=dev) if want_codes else None
         self.rmsd = torch.zeros((N, N), dtype=torch.float64, device=dev) if want_rmsd else None
         self.near = torch.zeros(1, dtype=torch.int64, device=dev)
 
@@ -135,43 +135,76 @@ class RotCorrPruner:
                                       ptr(self.sim_bits), ptr(self.codes), ptr(self.rmsd), ptr(self.near),
                                       stream_ptr()), "tsc_rotcorr_pairs")
 
-    def scan(self):
+    def scan(self, rank=0, world=1, group=None):
         """Forward scan (tsc_rotcorr_scan): returns (first_hit (N,) int64 numpy, lookup) where
         first_hit[i] is the first j > i similar to i (N if none) and lookup(i, js) gives the best
         rotor angles (len(js), T) of the pairs (i, j <= first_hit[i]) — all the grouping loop needs
-        in stateless mode.  The codes are compacted on the device before they cross PCIe."""
+        in stateless mode.  The codes are compacted on the device before they cross PCIe.
+        Several ranks (rot_corr): rows are dealt round-robin (row i to rank i % world: a row's cost is
+        data dependent, neighbours are alike), every rank scans its rows, first hits and compacted codes are
+        all-gathered, and every rank holds the complete result."""
         torch, N, T = self.torch, self.N, self.info.T
         dev = self.dev
         if self.codes is None:
-            self.codes = torch.zeros((N, N), dtype=torch.int32, device=dev)
-        first = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+            self.codes = torch.empty((N, N), dtype=torch.int64, device=dev)      # only entries the scan writes are read
+        first = torch.full((max(N, 1),), N, dtype=torch.int32, device=dev)
         counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.near.zero_()
         check(lib().tsc_rotcorr_scan(ptr(self.Sc), N, self.A, ptr(self.heavy), T, ptr(self.i2), ptr(self.i3),
                                      ptr(self.n_ang), ptr(self.sin_half), ptr(self.cos_half), ptr(self.rot_mask),
-                                     ptr(self.node_mask), 0, N, self.max_rmsd, ptr(first), ptr(self.codes), ptr(self.rmsd),
-                                     ptr(self.near), ptr(counter), stream_ptr()), "tsc_rotcorr_scan")
-        rows = torch.arange(N, device=dev, dtype=torch.int64)
-        last = torch.clamp(first[:N].to(torch.int64), max=N - 1)               # last column the loop can visit
+                                     ptr(self.node_mask), rank, N, world, self.max_rmsd, ptr(first), ptr(self.codes),
+                                     ptr(self.rmsd), ptr(self.near), ptr(counter), stream_ptr()), "tsc_rotcorr_scan")
+        rows = torch.arange(rank, N, world, device=dev, dtype=torch.int64)      # the rows this rank scanned
+        last = torch.clamp(first[rows].to(torch.int64), max=N - 1)               # last column the loop can visit
         lengths = torch.clamp(last - rows, min=0)
         offsets = torch.cumsum(lengths, 0) - lengths
         total = int(lengths.sum().item())
         if total:
-            r = torch.repeat_interleave(rows, lengths)
-            c = torch.arange(total, device=dev, dtype=torch.int64) - offsets[r] + r + 1
-            compact = self.codes.view(-1)[r * N + c].cpu().numpy().view(np.uint32)
+            r = torch.repeat_interleave(torch.arange(rows.numel(), device=dev), lengths)
+            c = torch.arange(total, device=dev, dtype=torch.int64) - offsets[r] + rows[r] + 1
+            compact_d = self.codes.view(-1)[rows[r] * N + c]
         else:
-            compact = np.zeros(0, np.uint32)
-        off = offsets.cpu().numpy()
+            compact_d = torch.zeros(0, dtype=torch.int64, device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            from .embeds import gather_varlen
+            per = (N + world - 1) // world
+            fpad = torch.full((per,), N, dtype=torch.int32, device=dev)
+            fpad[:rows.numel()] = first[rows]
+            fall = torch.empty(world * per, dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(fall, fpad, group=group)
+            first_all = torch.full((N,), N, dtype=torch.int32, device=dev)
+            for q in range(world):
+                nq = (N - q + world - 1) // world
+                first_all[q::world] = fall[q * per:q * per + nq]
+            compact_all = gather_varlen(compact_d, world, group)                  # rank-major: rank q's rows q, q + world, ...
+            near = self.near.clone()
+            dist.all_reduce(near, group=group)
+            self.near.copy_(near)
+            fh = first_all.cpu().numpy().astype(np.int64)
+            # offsets of every row into the rank-major compact array
+            ln = np.clip(np.minimum(fh, N - 1) - np.arange(N), 0, None)
+            off = np.zeros(N, dtype=np.int64)
+            base = 0
+            for q in range(world):
+                lq = ln[q::world]
+                off[q::world] = base + np.cumsum(lq) - lq
+                base += int(lq.sum())
+            compact = compact_all.cpu().numpy().view(np.uint64)
+            self.pairs_evaluated = int(ln.sum())
+        else:
+            fh = first[:N].cpu().numpy().astype(np.int64)
+            off = offsets.cpu().numpy()
+            compact = compact_d.cpu().numpy().view(np.uint64)
+            self.pairs_evaluated = total
         table = self.ang_table
 
         def lookup(i, js):
             cc = compact[off[i] + (np.asarray(js) - i - 1)]
-            return np.stack([table[t][(cc >> (3 * t)) & 7] for t in range(T)], axis=-1)
+            return np.stack([table[t][((cc >> np.uint64(3 * t)) & np.uint64(7)).astype(np.int64)] for t in range(T)], axis=-1)
         lookup.T = T
         lookup.compact, lookup.off, lookup.table = compact, np.ascontiguousarray(off, dtype=np.int64), table
-        self.pairs_evaluated = total
-        return first[:N].cpu().numpy().astype(np.int64), lookup
+        return fh, lookup
 
     def similar_matrix(self):
         """(N, N) bool, upper triangle, on the host."""
@@ -180,13 +213,13 @@ class RotCorrPruner:
 
     def best_angles(self):
         """Per-pair best rotor angles as a lookup `f(i, js) -> (len(js), T) degrees`, decoded lazily
-        from the (N, N) uint32 codes (3 bits per rotor) so that large N stays at 4 bytes per pair."""
-        codes = self.codes.cpu().numpy().view(np.uint32)
+        from the (N, N) uint64 codes (3 bits per rotor) so that large N stays at 8 bytes per pair."""
+        codes = self.codes.cpu().numpy().view(np.uint64)
         T, table = self.info.T, self.ang_table
 
         def lookup(i, js):
             c = codes[i, js]
-            return np.stack([table[t][(c >> (3 * t)) & 7] for t in range(T)], axis=-1)
+            return np.stack([table[t][((c >> np.uint64(3 * t)) & np.uint64(7)).astype(np.int64)] for t in range(T)], axis=-1)
         lookup.T = T
         return lookup
 
@@ -201,7 +234,7 @@ class RotCorrPruner:
         cur = self.Sc.clone()
         staged = torch.empty((N, A, 3), dtype=torch.float64, device=self.dev)
         rmsd_d = torch.empty(N, dtype=torch.float64, device=self.dev)
-        codes_d = torch.empty(N, dtype=torch.int32, device=self.dev)
+        codes_d = torch.empty(N, dtype=torch.int64, device=self.dev)
         js_d = torch.empty(N, dtype=torch.int32, device=self.dev)
         js_pin = torch.empty(N, dtype=torch.int32).pin_memory()
         final_mask = np.ones(N, dtype=bool)
@@ -247,10 +280,8 @@ class RotCorrPruner:
                         cached[i, js] = True
                     near += int(np.count_nonzero(np.abs(r[:n_acc] - self.max_rmsd) < 1e-6))
                     check(L.tsc_rotcorr_commit(ptr(cur), ptr(staged), ptr(js_d), n_acc, A, st), "tsc_rotcorr_commit")
-                g = nx.Graph(matches)
-                for group in [tuple(g.subgraph(c).nodes) for c in nx.connected_components(g)]:
-                    for rr in set(group) - {group[0]}:
-                        final_mask[rr + base] = 0
+                for rr in _cluster_rejects(matches):
+                    final_mask[rr + base] = 0
         keep = torch.from_numpy(np.flatnonzero(final_mask)).to(self.dev)
         return cur[keep].cpu().numpy(), final_mask, near
 
@@ -270,6 +301,88 @@ class RotCorrPruner:
                                       ptr(self.i2), ptr(self.i3), ptr(sh), ptr(ch), ptr(self.rot_mask), ptr(out),
                                       stream_ptr()), "tsc_rotcorr_apply")
         return out.cpu().numpy()
+
+
+def _cluster_rejects_nx(edges):
+    """The reference's survivor choice, literally (torsion_module.py:1136-1152, numba_functions.py:203-220,
+    optimization_methods.py:341-355): graph of the matches, connected components, keep `group[0]` of each."""
+    import networkx as nx
+    g = nx.Graph(edges)
+    rejects = []
+    for group in [tuple(g.subgraph(c).nodes) for c in nx.connected_components(g)]:
+        rejects.extend(set(group) - {group[0]})
+    return rejects
+
+
+def _cluster_rejects_fast(edges):
+    """Same result as _cluster_rejects_nx without building networkx objects (3 900 chunks of BASELINE configs[3] spent
+    0.45 s in Graph / subgraph-view construction).  Which member of a cluster is `group[0]` depends on iteration
+    orders, so this restates networkx 3.x step by step with plain dicts and sets — Python's own, hence the same
+    orders: nodes in order of first appearance in the edge iteration (Graph.add_edges_from), components in node
+    order, each found by the same breadth-first search into a SET (connected._plain_bfs), and the first node of
+    `G.subgraph(c).nodes` is the first element of a new set built from c when 2 |c| < |G|, else the first node of G
+    that lies in c (coreviews.FilterAtlas.__iter__).  `_cluster_rejects` checks it against networkx itself once per
+    process and falls back to the literal form if the installed networkx behaves differently."""
+    adj = {}
+    for u, v in edges:
+        if u not in adj:
+            adj[u] = {}
+        if v not in adj:
+            adj[v] = {}
+        adj[u][v] = None
+        adj[v][u] = None
+    n = len(adj)
+    seen_all = set()
+    rejects = []
+    for v0 in adj:
+        if v0 in seen_all:
+            continue
+        target = n - len(seen_all)
+        seen = {v0}
+        nextlevel = [v0]
+        full = False
+        while nextlevel and not full:
+            thislevel = nextlevel
+            nextlevel = []
+            for x in thislevel:
+                for w in adj[x]:
+                    if w not in seen:
+                        seen.add(w)
+                        nextlevel.append(w)
+                if len(seen) == target:
+                    full = True
+                    break
+        seen_all.update(seen)
+        nodes = set(x for x in seen if x in adj)                 # show_nodes(self.nbunch_iter(c))
+        if 2 * len(nodes) < n:
+            first = next(iter(nodes))
+        else:
+            first = next(x for x in adj if x in nodes)
+        rejects.extend(x for x in nodes if x != first)
+    return rejects
+
+
+_CLUSTER_IMPL = []
+
+
+def _cluster_rejects(edges):
+    if not _CLUSTER_IMPL:
+        import random
+        rnd = random.Random(12345)
+        ok = True
+        for trial in range(40):
+            m = rnd.choice((3, 8, 30, 200))
+            es = set()
+            for _ in range(rnd.randrange(1, 3 * m)):
+                a, b = rnd.randrange(m), rnd.randrange(m)
+                if a != b:
+                    es.add((min(a, b), max(a, b)))
+            es = es if trial % 2 else list(es)
+            if es and sorted(_cluster_rejects_fast(es)) != sorted(_cluster_rejects_nx(es)):
+                ok = False
+                break
+        _CLUSTER_IMPL.append(_cluster_rejects_fast if ok else _cluster_rejects_nx)
+    return _CLUSTER_IMPL[0](edges)
 
 
 def ladder_replay(similar, N, best_angles=None, verbose=False):
@@ -322,11 +435,8 @@ def ladder_replay(similar, N, best_angles=None, verbose=False):
                     matches.add((i_rel, int(js[-1] - base)))                        # :1119-1120
                 else:
                     cached[i, js] = True
-            g = nx.Graph(matches)                                                  # :1136
-            groups = [tuple(g.subgraph(c).nodes) for c in nx.connected_components(g)]
-            for group in groups:                                                   # :1141-1152
-                for r in set(group) - {group[0]}:
-                    final_mask[r + base] = 0
+            for r in _cluster_rejects(matches):                                    # :1136-1152
+                final_mask[r + base] = 0
     return final_mask, state
 
 
@@ -352,14 +462,14 @@ def ladder_replay_scan(first_hit, N, best_angles=None, verbose=False, native=Non
     if native:
         L = lib()
         if T:
-            compact = np.ascontiguousarray(best_angles.compact, dtype=np.uint32)
+            compact = np.ascontiguousarray(best_angles.compact, dtype=np.uint64)
             if compact.size == 0:
-                compact = np.zeros(1, np.uint32)
+                compact = np.zeros(1, np.uint64)
             off = best_angles.off
             table = np.ascontiguousarray(best_angles.table, dtype=np.float64)
             assert table.shape[1] == MAX_ANG
         else:                                   # no rotor states (the TFD pruning runs the same loop)
-            compact, off, table = np.zeros(1, np.uint32), np.zeros(max(N, 1), np.int64), np.zeros((1, MAX_ANG))
+            compact, off, table = np.zeros(1, np.uint64), np.zeros(max(N, 1), np.int64), np.zeros((1, MAX_ANG))
         mi, mj = np.empty(max(N, 1), np.int32), np.empty(max(N, 1), np.int32)
         vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
         p_first, p_reach, p_state, p_compact, p_off, p_table, p_mi, p_mj = (vp(a) for a in (
@@ -411,16 +521,14 @@ def ladder_replay_scan(first_hit, N, best_angles=None, verbose=False, native=Non
                         matches.add((i_rel, p - base))                              # :1119-1120
             if not matches:
                 continue
-            g = nx.Graph(matches)                                                  # :1136
-            groups = [tuple(g.subgraph(c).nodes) for c in nx.connected_components(g)]
-            for group in groups:                                                   # :1141-1152
-                for r in set(group) - {group[0]}:
-                    final_mask[r + base] = 0
+            for r in _cluster_rejects(matches):                                    # :1136-1152
+                final_mask[r + base] = 0
     return final_mask, state
 
 
 def prune_conformers_rmsd_rot_corr(structures, atomnos, graph, max_rmsd=0.25, verbose=False, logfunction=None,
-                                   *, torsion_info: TorsionInfo | None = None, max_structures=750, mode=None):
+                                   *, torsion_info: TorsionInfo | None = None, max_structures=750, mode=None,
+                                   group=None, rank=None, world=None):
     """Drop-in for tscode.torsion_module.prune_conformers_rmsd_rot_corr (:1013-1161).
 
     mode "exact" (default up to 2000 structures): row-by-row replay from the current, mutated
@@ -429,7 +537,9 @@ def prune_conformers_rmsd_rot_corr(structures, atomnos, graph, max_rmsd=0.25, ve
     up to its first similar partner (mode "allpairs": every pair) — + host replay with rotor-state algebra; masks agree with the reference on every fixture, but for rotors whose
     n-fold images differ only at noise level (e.g. a methyl-capped alkyne: the heavy atoms sit on
     the axis) the hydrogens of the returned structures may end up in another image."""
-    structures = np.array([s - s.mean(axis=0) for s in np.asarray(structures, dtype=np.float64)])     # :1023
+    structures = np.asarray(structures, dtype=np.float64)
+    structures = structures - structures.mean(axis=1, keepdims=True) if structures.ndim == 3 and structures.shape[0] \
+        else np.array([s - s.mean(axis=0) for s in structures])     # :1023 (the vectorised form is bit-identical)
     atomnos = np.asarray(atomnos)
     N = structures.shape[0]
     final_mask = np.ones(N, dtype=bool)
@@ -455,8 +565,14 @@ def prune_conformers_rmsd_rot_corr(structures, atomnos, graph, max_rmsd=0.25, ve
         pr.similarity()
         mask, state = ladder_replay(pr.similar_matrix(), N, pr.best_angles(), verbose=verbose)
     else:
+        if group is not None or world is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(group) if world is None else int(world)
+            rank = dist.get_rank(group) if rank is None else int(rank)
+        else:
+            rank, world = 0, 1
         pr = RotCorrPruner(structures, atomnos, info, max_rmsd, want_codes=False)
-        first_hit, lookup = pr.scan()
+        first_hit, lookup = pr.scan(rank, world, group)       # rows dealt to the ranks; the replay runs on every rank
         mask, state = ladder_replay_scan(first_hit, N, lookup, verbose=verbose)
     keep = np.flatnonzero(mask)
     out = pr.apply_states(keep, state[keep])
