@@ -65,16 +65,20 @@ int tsc_rmsd_sim_tiles(const double* packed, const double* G, int64_t N, int32_t
  * accumulator buffer per (tile, row of the covariances), three MMA chains, epilogue on T = S^T S.
  * Replaces the pair loop of rmsd_pruning.py:43-79 together with tsc_rmsd_verify: bits are a superset of the
  * similar pairs, every set bit is also appended to cand_list.
- *   mode 0: isotropic form — tiles of 64 conformers (MMAs 128 x 192 x 16, two buffers), Samuelson's bound only;
+ *   mode 0: isotropic form — tiles of 48 conformers (MMAs 128 x 144 x 16, three buffers = one per row of the
+ *           covariances), Samuelson's bound only;
  *   mode 1: tiles of 32 (MMAs 128 x 96 x 16, four buffers), Samuelson then the FP32 quartic sign test;
- *   mode 2: tiles of 32, quartic sign test for every pair (anisotropic ensembles).
- *   All three are conservative (never lose a similar pair); they differ in speed and in how many candidates they leave.
+ *   mode 2: tiles of 32, quartic sign test for every pair (anisotropic ensembles);
+ *   mode 3: mode 0 on tiles of 64 (MMAs 128 x 192 x 16, two buffers) — the previous default, kept for comparison.
+ *   All are conservative (never lose a similar pair); they differ in speed and in how many candidates they leave.
  *   PA, PB, PR: tsc_screen_operand_bytes(N, M) bytes each; CT: tsc_screen_ct_floats(N) floats; G, sG: doubles for
- *   every padded row (ceil(N/128)*128).  tsc_pack_screen writes them for conformers [row_begin, row_end)
- *   (row_begin a multiple of 8; row_end <= 0 = all rows incl. padding) for tiles of tile_j = 64 (mode 0) or 32.
+ *   every padded row (tsc_screen_rows_padded(N): whole 128-row panels and whole tiles).  tsc_pack_screen writes them
+ *   for conformers [row_begin, row_end) (row_begin a multiple of 8; row_end <= 0 = to the end incl. padding) for
+ *   tiles of tile_j = 48 (mode 0), 32 (modes 1, 2) or 64 (mode 3).
  *   items (n_items, 4) int32 {panel, first j tile, tile count, local 32-row block of the panel's first row in
  *   sim_bits}, dealt round-robin to the CTAs; an item with count 0 ends a CTA's list.
  *   M <= tsc_screen_max_atoms(tile_j); above, use tsc_rmsd_sim_tiles.  grid_ctas 0 = one CTA per SM.  pace 0. */
+int64_t tsc_screen_rows_padded(int64_t N);
 int64_t tsc_screen_operand_bytes(int64_t N, int32_t M);
 int64_t tsc_screen_ct_floats(int64_t N);
 int32_t tsc_screen_max_atoms(int32_t tile_j);

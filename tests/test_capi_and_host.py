@@ -85,9 +85,9 @@ def test_tiles_cover_upper_triangle(N, world):
     # work items of the tcgen05 screen, for both tile widths: every j tile right of a panel's first row exactly once;
     # one contiguous stretch per CTA, dealt round-robin; empty items only at the end of a CTA's list (the kernel stops
     # at the first one)
-    for tile_j in (32, 64):
-        tpp = 128 // tile_j
-        njt = ((N + 127) // 128) * tpp
+    for tile_j in (32, 48, 64):
+        first = lambda p: (128 * p) // tile_j                 # noqa: E731  the tile that holds the panel's first column
+        njt = (((N + 127) // 128) * 128 + tile_j - 1) // tile_j
         for n_ctas in (148, 5):
             seen = set()
             for rank in range(world):
@@ -103,7 +103,7 @@ def test_tiles_cover_upper_triangle(N, world):
                     for jt in range(j0, j0 + cnt):
                         assert (p, jt) not in seen
                         seen.add((p, jt))
-            assert seen == {(p, jt) for p in range((N + 127) // 128) for jt in range(tpp * p, njt)}
+            assert seen == {(p, jt) for p in range((N + 127) // 128) for jt in range(first(p), njt)}
         # ... and restricted to panel ranges (the sub-launches of the pipelined upload) the pieces tile the whole
         seen = set()
         rb = _host.owned_row_blocks(N, 0, 1)
@@ -115,7 +115,7 @@ def test_tiles_cover_upper_triangle(N, world):
                 for jt in range(j0, j0 + cnt):
                     assert (p, jt) not in seen
                     seen.add((p, jt))
-        assert seen == {(p, jt) for p in range(n_panels) for jt in range(tpp * p, njt)}
+        assert seen == {(p, jt) for p in range(n_panels) for jt in range(first(p), njt)}
 
 
 def test_row_sharding_is_balanced():
@@ -129,7 +129,7 @@ def test_row_sharding_is_balanced():
         return np.array([items[b::g, 2].sum() + cost * (items[b::g, 2] > 0).sum() for b in range(g)])
     for world in (1, 8):
         rb = _host.owned_row_blocks(N, 0, world)
-        for tile_j in (32, 64):
+        for tile_j in (32, 48, 64):
             loads = cta_loads(_host.build_screen_items(N, rb, 148, tile_j=tile_j), cost=2.5 * 32 / tile_j)
             assert loads.max() / loads.mean() < 1.02, (world, tile_j, loads.max() / loads.mean())
     rb = _host.owned_row_blocks(N, 0, 1)
@@ -267,11 +267,10 @@ def test_balanced_items_dealt_like_the_kernel_cover_every_tile_once(N):
             own = [int(ib // 4) for ib in rb if ib % 4 == 0]
             for n_ctas in (148, 132, 5):
                 for lo, hi in ranges:
-                    for tile_j in (32, 64):
-                        tpp = 128 // tile_j
-                        njt = n_panels * tpp
+                    for tile_j in (32, 48, 64):
+                        njt = (n_panels * 128 + tile_j - 1) // tile_j
                         h = n_panels if hi is None else hi
-                        want = {(p, jt) for p in own if lo <= p < h for jt in range(tpp * p, njt)}
+                        want = {(p, jt) for p in own if lo <= p < h for jt in range((128 * p) // tile_j, njt)}
                         items = _host.build_screen_items(N, rb, n_ctas, panel_lo=lo, panel_hi=hi, tile_j=tile_j)
                         seen = _deal_like_the_kernel(items, n_ctas)
                         assert set(seen) == want and all(v == 1 for v in seen.values()), (N, world, rank, n_ctas, lo, hi, tile_j)

@@ -94,8 +94,9 @@ def test_rmsd_similarity_vs_reference(gpu):
 # similarity bits (screen + verify) vs oracle, every screen variant
 # ------------------------------------------------------------------------------------------
 def _pruner(S, atomnos, thr, variant, **kw):
-    """variant "screen" = the default screen with its automatic choice of form; "screen0/1/2" force a form
-    (rmsd_screen.cu: 0 = Samuelson only on 64-wide tiles, 1 = Samuelson then quartic, 2 = quartic for every pair)."""
+    """variant "screen" = the default screen with its automatic choice of form; "screen0/1/2/3" force a form
+    (rmsd_screen.cu: 0 = Samuelson only on 48-wide tiles, 1 = Samuelson then quartic, 2 = quartic for every pair,
+    3 = Samuelson only on 64-wide tiles)."""
     from tscode_b200.rmsd_pruning import RmsdPruner
     if variant.startswith("screen") and variant != "screen":
         return RmsdPruner(S, atomnos, thr, variant="screen", screen_mode=int(variant[-1]), **kw)
@@ -103,7 +104,7 @@ def _pruner(S, atomnos, thr, variant, **kw):
 
 
 
-@pytest.mark.parametrize("variant", ["dmma", "fma", "screen", "screen0", "screen1", "screen2"])
+@pytest.mark.parametrize("variant", ["dmma", "fma", "screen", "screen0", "screen1", "screen2", "screen3"])
 @pytest.mark.parametrize("seed,N,M,nc,noise,thr", [
     (0, 1000, 40, 100, 0.05, 0.5),
     (5, 777, 29, 60, 0.05, 0.25),
@@ -687,7 +688,7 @@ def test_f16_screen_extreme_coordinates(gpu, scale, shift):
     thr = 0.5 * (scale if scale < 1 else 1.0)
     at = np.full(24, 6)
     ref_out, ref = oracle_c.prune_conformers_rmsd(S, at, thr)
-    for variant in ("screen", "screen0", "screen1", "screen2", "dmma"):
+    for variant in ("screen", "screen0", "screen1", "screen2", "screen3", "dmma"):
         pr = _pruner(S, at, thr, variant)
         m = pr.run().cpu().numpy()
         assert np.array_equal(m, ref), (variant, scale, shift, int(m.sum()), int(ref.sum()), pr.stats_dict())

@@ -21,7 +21,7 @@ def _arg(name, default):
 
 modes = _arg("--modes", [None])                      # screen forms to run on the isotropic ensembles (None = automatic)
 modes_aniso = _arg("--modes-aniso", [None])          # ... on the anisotropic ones (mode 0 there means billions of candidates)
-modes_small = _arg("--modes-small", [None, 0, 1, 2])
+modes_small = _arg("--modes-small", [None, 0, 1, 2, 3])
 small = "--no-small" not in sys.argv
 cases = ((0, 257, 40, 20, 0.05, 0.5, 3.0), (0, 1000, 40, 100, 0.05, 0.5, 3.0), (13, 650, 80, 30, 0.2, 0.5, 3.0),
          (4, 2000, 80, 200, 0.08, 0.5, 3.0), (5, 777, 29, 60, 0.05, 0.25, 3.0), (14, 31, 1, 2, 0.05, 0.5, 3.0),

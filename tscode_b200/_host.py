@@ -48,9 +48,9 @@ def owned_row_blocks(N: int, rank: int = 0, world: int = 1) -> np.ndarray:
 def build_screen_items(N: int, row_blocks: np.ndarray, n_ctas: int, panel_lo: int = 0, panel_hi: int | None = None,
                        item_cost: float = 2.5, tile_j: int = 32) -> np.ndarray:
     """Work items of the default screen (rmsd_screen.cu): as build_items_balanced, with j tiles of `tile_j`
-    (32 or 64) conformers, i.e. four or two per 128-row panel."""
+    (32, 48 or 64) conformers; panel p starts at the tile that holds its first column, 128 p // tile_j."""
     return build_items_balanced(N, row_blocks, n_ctas, panel_lo, panel_hi, item_cost * 32.0 / tile_j,
-                                     tiles_per_panel=128 // int(tile_j))
+                                tile_j=int(tile_j))
 
 
 def screen_mode_for(first_heavy: np.ndarray) -> int:
@@ -71,24 +71,31 @@ def screen_mode_for(first_heavy: np.ndarray) -> int:
 
 def build_items_balanced(N: int, row_blocks: np.ndarray, n_ctas: int, panel_lo: int = 0,
                               panel_hi: int | None = None, item_cost: float = 3.0, max_item: int = 0,
-                              tiles_per_panel: int = 8) -> np.ndarray:
+                              tiles_per_panel: int = 8, tile_j: int | None = None) -> np.ndarray:
     """Work items of the tcgen05 pre-screen for a persistent grid of `n_ctas` CTAs, each of which takes the array
     entries b, b + n_ctas, b + 2 n_ctas, ...: rows {panel, first j tile, j tile count, local row block of the panel};
-    panel p (128 rows) needs the j tiles from tiles_per_panel * p to the padded end (optionally only the panels in
-    [panel_lo, panel_hi)).  Partitioned linearly: the (panel, j tile) pairs are laid out panel after panel and
+    panel p (128 rows) needs the j tiles from tiles_per_panel * p (tile_j given: from 128 p // tile_j) to the padded
+    end (optionally only the panels in [panel_lo, panel_hi)).  Partitioned linearly: the (panel, j tile) pairs are laid out panel after panel and
     every CTA gets one contiguous stretch of equal cost (tiles + `item_cost` tiles per item start: pipeline drain
     and panel rows -> TMEM, measured ~2 400 cycles), i.e. one item per panel its stretch touches.  Plain
     round-robin dealing of 128-tile chunks left the busiest CTA of C3 5 % above the mean, and 20 % in the eight
     sub-launches of the pipelined upload.  CTAs whose stretch touches fewer panels than the longest list get
     empty items (count 0, a valid panel) in the last rounds."""
     rb = np.asarray(row_blocks, dtype=np.int64)
-    tpp = int(tiles_per_panel)
-    njt = ((N + 127) // 128) * tpp
+    n_pan = (N + 127) // 128
+    if tile_j is None:
+        tpp = int(tiles_per_panel)
+        njt = n_pan * tpp
+        first = lambda p: tpp * p                                  # noqa: E731
+    else:
+        tpp = max(1, 128 // int(tile_j))
+        njt = (n_pan * 128 + int(tile_j) - 1) // int(tile_j)      # tiles up to the padded width of the bit rows
+        first = lambda p: (128 * p) // int(tile_j)                # noqa: E731
     if panel_hi is None:
         panel_hi = (N + 127) // 128
     panels = [(int(ib // PANEL_BLOCKS), lb) for lb, ib in enumerate(rb)
               if ib % PANEL_BLOCKS == 0 and panel_lo <= ib // PANEL_BLOCKS < panel_hi]
-    total = sum(njt - tpp * p for p, _ in panels)
+    total = sum(njt - first(p) for p, _ in panels)
     if total == 0:
         return np.zeros((0, 4), np.int32)
     n_bins = max(1, min(n_ctas, total // tpp))
@@ -96,7 +103,7 @@ def build_items_balanced(N: int, row_blocks: np.ndarray, n_ctas: int, panel_lo: 
     left = float(total + item_cost * (len(panels) + n_bins))      # cost still to hand out (upper estimate)
     b, budget = 0, left / n_bins                                  # current CTA and what it may still take
     for p, lb in panels:
-        j, end = tpp * p, njt
+        j, end = first(p), njt
         while j < end:
             room = int(budget - item_cost)
             if room < 4 and b + 1 < n_bins:                       # not worth starting an item here: next CTA
@@ -122,12 +129,14 @@ def build_items_balanced(N: int, row_blocks: np.ndarray, n_ctas: int, panel_lo: 
     for r in range(rounds):
         last = max(q for q in range(len(bins)) if len(bins[q]) > r)
         for q in range(len(bins) if r + 1 < rounds else last + 1):
-            items.append(bins[q][r] if len(bins[q]) > r else (pad_p, tpp * pad_p, 0, pad_lb))
+            items.append(bins[q][r] if len(bins[q]) > r else (pad_p, first(pad_p), 0, pad_lb))
     return np.asarray(items, dtype=np.int32).reshape(-1, 4)
 
 
 def tf32_rows_padded(N: int) -> int:
-    return ((N + 127) // 128) * 128
+    """Rows the screen's operand images, G, sG and CT are padded to: whole 128-row panels and whole tiles of 32 / 48 / 64
+    conformers (rmsd_screen.cu: tsc_screen_rows_padded)."""
+    return ((N + 383) // 384) * 384
 
 
 def build_tiles(N: int, row_blocks: np.ndarray) -> np.ndarray:

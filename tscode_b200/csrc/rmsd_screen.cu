@@ -36,17 +36,24 @@
 namespace tsc {
 
 constexpr int SC_ROWS = 128;                  // conformers per panel (UMMA M, TMEM lanes)
-// tile width J (conformers per B tile) is a template parameter: 32 (UMMA N = 96, four accumulator buffers) or
-// 64 (N = 192, two buffers)
-constexpr int SC_KT = 5;                      // K blocks of the panel held in TMEM (3 * 8 * 5 = 120 columns)
-constexpr int SC_ACC0 = 128;                  // first accumulator column
+// tile width J (conformers per B tile) is a template parameter:
+//   32: UMMA N =  96, four accumulator buffers, 16 epilogue warps x  8 columns  (modes 1, 2: six numbers per pair)
+//   48: UMMA N = 144, three buffers = one per row a,  12 epilogue warps x 16 columns  (mode 0)
+//   64: UMMA N = 192, two buffers,  16 epilogue warps x 16 columns  (mode 0, kept for comparison: tsc_rmsd_screen mode 3)
 constexpr int SC_TMEM = 512;
 constexpr int SC_MAX_BSTAGES = 12;
-constexpr int SC_EPI_WARPS = 16;
+constexpr int SC_MAX_EPI_WARPS = 16;
 constexpr int SC_Q = 128;                     // candidate queue entries per epilogue warp
+constexpr int SC_CT_BYTES = 128;              // per epilogue warp: staged column terms of a tile (16 x B_j, 16 x D_j)
 constexpr int SC_MMA_WARPS = 3;                // one issuing thread per row a of the covariances ("chain")
-constexpr int SC_THREADS = (1 + SC_MMA_WARPS + SC_EPI_WARPS) * 32;
-static_assert(3 * 8 * SC_KT <= SC_ACC0 && SC_ACC0 + 4 * 96 <= SC_TMEM && SC_ACC0 + 2 * 192 <= SC_TMEM, "TMEM budget");
+// K blocks of the panel held in TMEM (8 columns per block and component) and first accumulator column
+__host__ __device__ constexpr int sc_kt(int J) { return J == 48 ? 3 : 5; }
+__host__ __device__ constexpr int sc_acc0(int J) { return J == 48 ? 80 : 128; }
+__host__ __device__ constexpr int sc_nbuf(int J) { return J == 32 ? 4 : J == 48 ? 3 : 2; }
+__host__ __device__ constexpr int sc_epi_warps(int J) { return J == 48 ? 12 : 16; }
+__host__ __device__ constexpr int sc_threads(int J) { return (1 + SC_MMA_WARPS + sc_epi_warps(J)) * 32; }
+static_assert(3 * 8 * sc_kt(32) <= sc_acc0(32) && sc_acc0(32) + 4 * 96 <= SC_TMEM && sc_acc0(64) + 2 * 192 <= SC_TMEM &&
+              3 * 8 * sc_kt(48) <= sc_acc0(48) && sc_acc0(48) + 3 * 144 <= SC_TMEM, "TMEM budget");
 
 struct ScParams {
     const unsigned char* PA;  // [panel][a][kc][128][16 B]     (only the chunks of K blocks >= SC_KT are read)
@@ -144,6 +151,13 @@ __global__ void __launch_bounds__(256) pack_screen_kernel(const double* __restri
     }
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ float sqrt_approx(float x) {
     float r;
     asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -156,16 +170,20 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 // MODE 1: T = S~^T S~ accumulated; Samuelson, then the quartic sign test for column pairs with an undecided lane.
 // MODE 2: T accumulated; the quartic sign test for every pair (anisotropic ensembles, where Samuelson never excludes).
 template <int MODE, int J>
-__global__ void __launch_bounds__(SC_THREADS, 1) rmsd_screen_kernel(const ScParams p) {
+__global__ void __launch_bounds__(sc_threads(J), 1) rmsd_screen_kernel(const ScParams p) {
     constexpr int NN = 3 * J;                      // UMMA N: (component b, conformer j)
-    constexpr int NBUF = J == 32 ? 4 : 2;          // accumulator buffers of NN columns
-    constexpr int LBUF = J == 32 ? 2 : 1;          // log2(NBUF)
-    constexpr int LREL = J == 32 ? 12 : 6;         // lcm(NBUF, 3): ring of buffer-release barriers, see t_rel
+    constexpr int NBUF = sc_nbuf(J);               // accumulator buffers of NN columns
+    constexpr int LBUF = J == 32 ? 2 : 1;          // log2(NBUF) (J = 48: three buffers, buffer = row a, no shifts)
+    constexpr int LREL = J == 32 ? 12 : J == 48 ? 3 : 6;   // lcm(NBUF, 3): ring of buffer-release barriers, see t_rel
+    constexpr int SC_EPI_WARPS = sc_epi_warps(J);
+    constexpr int SC_KT = sc_kt(J);
+    constexpr int SC_ACC0 = sc_acc0(J);
     constexpr int COLS = J / (SC_EPI_WARPS / 4);   // columns of a tile per epilogue warp
     constexpr int NCP = COLS / 2;                  // column pairs (two FP32 lanes per packed instruction)
     constexpr int NR = 3 * COLS;                   // accumulator words a thread reads per unit
-    static_assert(J == 32 || J == 64, "tile width");
+    static_assert(J == 32 || J == 48 || J == 64, "tile width");
     static_assert(MODE == 0 || J == 32, "the T-accumulating modes keep 6 numbers per pair: 8 columns per thread");
+    static_assert(COLS == 8 || COLS == 16, "whole bytes of the bit rows per warp");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int nkc = p.nkc;
     const int nkb = nkc / 2;                                   // K blocks (one MMA per component each)
@@ -191,6 +209,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) rmsd_screen_kernel(const ScPara
     uint64_t* t_rel = t_full + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_rel + 12);
     int2* cand_q = reinterpret_cast<int2*>(reinterpret_cast<unsigned char*>(bars) + 512);     // [epilogue warp][SC_Q]
+    unsigned char* ct_stage = reinterpret_cast<unsigned char*>(cand_q + SC_MAX_EPI_WARPS * SC_Q);   // [epilogue warp][SC_CT_BYTES]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -259,7 +278,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) rmsd_screen_kernel(const ScPara
             const uint64_t b_stage_step = b_bytes >> 4;
             const uint32_t at0 = tmem_base + (uint32_t)l * 8u * (uint32_t)KT;        // this row's part of the panel in TMEM
             int st = 0;
-            uint32_t sph = 0, aph = 0, us = (uint32_t)l;                             // unit number of the current unit
+            uint32_t sph = 0, aph = 0, rph = 0, us = (uint32_t)l;                    // unit number of the current unit
             long long t_next = clock64();
             const long long pace = p.pace;
             auto paced = [&]() {
@@ -276,13 +295,18 @@ __global__ void __launch_bounds__(SC_THREADS, 1) rmsd_screen_kernel(const ScPara
                 if (tail_kc > 0) mbar_wait(at_full, aph);
                 aph ^= 1u;
                 for (int t = 0; t < w.z; t++) {
-                    const uint32_t buf = us & (NBUF - 1);
+                    const uint32_t buf = NBUF == 3 ? (uint32_t)l : us & (NBUF - 1);   // three buffers: chain l owns buffer l
                     SC_STAMP(us < 192, (us * 8) + 0);
                     mbar_wait(&b_full[st], sph);
                     SC_STAMP(us < 192, (us * 8) + 1);
                     if (us >= NBUF) {                           // the unit that used this buffer before has been drained
-                        const uint32_t slot = us % LREL, use = us / LREL - (slot < NBUF ? 1u : 0u);
-                        mbar_wait(&t_rel[slot], use & 1u);
+                        if (NBUF == 3) {
+                            mbar_wait(&t_rel[l], rph);
+                            rph ^= 1u;
+                        } else {
+                            const uint32_t slot = us % LREL, use = us / LREL - (slot < NBUF ? 1u : 0u);
+                            mbar_wait(&t_rel[slot], use & 1u);
+                        }
                     }
                     tcgen05_fence_after();
                     SC_STAMP(us < 192, (us * 8) + 2);
@@ -323,6 +347,9 @@ __global__ void __launch_bounds__(SC_THREADS, 1) rmsd_screen_kernel(const ScPara
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         const int c0 = part * COLS;
         uint32_t eph = 0, us = 0;                                // unit number (all units of this CTA, in order)
+        uint32_t rel_slot = NBUF % LREL;                         // (us + NBUF) % LREL: where this unit's release goes
+        uint32_t tph = 0;                                        // three buffers: parity of t_full[a] = tile count & 1
+        unsigned char* my_ct = ct_stage + (size_t)ew * SC_CT_BYTES;
         // Candidates (rare) go to a per-warp queue in shared memory and reach the global list in bursts with one
         // reservation per burst.
         int2* my_q = cand_q + (size_t)ew * SC_Q;
@@ -366,12 +393,19 @@ __global__ void __launch_bounds__(SC_THREADS, 1) rmsd_screen_kernel(const ScPara
                 const float4* ct = reinterpret_cast<const float4*>(p.CT + (int64_t)(w.y + t) * (2 * J) + c0);
                 float4 ctB[COLS / 4], ctD[COLS / 4];                         // B_j, D_j of this warp's columns
                 unsigned long long T[MODE == 0 ? 1 : 6][NCP];                // T = S~^T S~ (MODE 0: f), two columns per register pair
+                if (MODE == 0) {
+                    // column terms of this tile -> this warp's staging slot, asynchronously: they are needed after the
+                    // third unit, and an L2 round trip there (16 warps waiting on it) cost ~650 cycles per tile
+                    __syncwarp();
+                    if (lane < 8) cp_async16(my_ct + lane * 16, reinterpret_cast<const float*>(ct) + (lane < 4 ? lane * 4 : J + (lane - 4) * 4));
+                    cp_async_commit();
+                }
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
                     uint32_t r[NR];                                          // row a of S~ for COLS columns: [b][column]
-                    const uint32_t buf = us & (NBUF - 1);
+                    const uint32_t buf = NBUF == 3 ? (uint32_t)a : us & (NBUF - 1);
                     SC_STAMP(ew == 0 && lane == 0 && us < 192, (us * 8) + 4);
-                    mbar_wait(&t_full[buf], (us >> LBUF) & 1u);
+                    mbar_wait(&t_full[buf], NBUF == 3 ? tph : (us >> LBUF) & 1u);
                     tcgen05_fence_after();
                     SC_STAMP(ew == 0 && lane == 0 && us < 192, (us * 8) + 5);
                     const uint32_t d0 = tmem_base + lane_addr + SC_ACC0 + buf * NN + (uint32_t)c0;
@@ -384,8 +418,9 @@ __global__ void __launch_bounds__(SC_THREADS, 1) rmsd_screen_kernel(const ScPara
                     SC_STAMP(ew == 0 && lane == 0 && us < 192, (us * 8) + 6);
                     tcgen05_fence_before();                                  // the buffer goes back to its MMA thread
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&t_rel[(us + NBUF) % LREL]);
-                    SC_STAMP(ew == 15 && lane == 0 && us < 192, (us * 8) + 7);
+                    if (lane == 0) mbar_arrive(&t_rel[rel_slot]);
+                    rel_slot = rel_slot + 1 == LREL ? 0u : rel_slot + 1u;
+                    SC_STAMP(ew == SC_EPI_WARPS - 1 && lane == 0 && us < 192, (us * 8) + 7);
                     us++;
                     if (a == 2 && MODE != 0) {                               // column terms: in flight while T is finished
 #pragma unroll
@@ -410,9 +445,13 @@ __global__ void __launch_bounds__(SC_THREADS, 1) rmsd_screen_kernel(const ScPara
                         }
                     }
                 }
+                tph ^= 1u;
                 if (MODE == 0) {
+                    cp_async_wait<0>();
+                    __syncwarp();
+                    const float4* cs = reinterpret_cast<const float4*>(my_ct);
 #pragma unroll
-                    for (int h = 0; h < COLS / 4; h++) { ctB[h] = __ldg(ct + h); ctD[h] = __ldg(ct + J / 4 + h); }
+                    for (int h = 0; h < COLS / 4; h++) { ctB[h] = cs[h]; ctD[h] = cs[4 + h]; }
                 }
                 // ---- the tile's verdicts for this warp's columns: column terms B_j (rounded down), D_j (rounded up)
                 uint32_t near = 0;                                           // bit c: pair of column c0 + c not excluded
@@ -523,48 +562,57 @@ __global__ void __launch_bounds__(SC_THREADS, 1) rmsd_screen_kernel(const ScPara
 
 }  // namespace tsc
 
+// rows the images are padded to: whole panels of 128 AND whole tiles of 32 / 48 / 64 conformers (lcm = 384); the padding
+// rows are written as zeros by tsc_pack_screen
+extern "C" int64_t tsc_screen_rows_padded(int64_t N) { return (N + 383) / 384 * 384; }
 // size in bytes of each of the three operand images (PA, PB, PR)
 extern "C" int64_t tsc_screen_operand_bytes(int64_t N, int32_t M) {
-    const int64_t Mp = (M + 15) / 16 * 16, rows = (N + tsc::SC_ROWS - 1) / tsc::SC_ROWS * tsc::SC_ROWS;
-    return rows * 3 * Mp * 2;
+    const int64_t Mp = (M + 15) / 16 * 16;
+    return tsc_screen_rows_padded(N) * 3 * Mp * 2;
 }
-extern "C" int64_t tsc_screen_ct_floats(int64_t N) {
-    return (N + tsc::SC_ROWS - 1) / tsc::SC_ROWS * tsc::SC_ROWS * 2;
+extern "C" int64_t tsc_screen_ct_floats(int64_t N) { return tsc_screen_rows_padded(N) * 2; }
+static size_t screen_side_bytes() {      // barriers, candidate queues and column-term slots of the epilogue warps
+    return 512 + (size_t)tsc::SC_MAX_EPI_WARPS * (tsc::SC_Q * sizeof(int2) + tsc::SC_CT_BYTES);
 }
 static bool screen_fits(int M, int J, size_t* a_out, size_t* b_out) {
-    const int nkc = (M + 15) / 16 * 2, nkb = nkc / 2, KT = nkb < tsc::SC_KT ? nkb : tsc::SC_KT;
+    const int nkc = (M + 15) / 16 * 2, nkb = nkc / 2, KT = nkb < tsc::sc_kt(J) ? nkb : tsc::sc_kt(J);
     const size_t a_bytes = (size_t)3 * (nkc - 2 * KT) * tsc::SC_ROWS * 16, b_bytes = (size_t)nkc * 3 * J * 16;
-    const size_t budget = 227 * 1024 - 512 - (size_t)tsc::SC_EPI_WARPS * tsc::SC_Q * sizeof(int2);
+    const size_t budget = 227 * 1024 - screen_side_bytes();
     if (a_out) *a_out = a_bytes;
     if (b_out) *b_out = b_bytes;
     return a_bytes + 3 * b_bytes <= budget;
 }
-// largest number of heavy atoms the screen takes with tiles of `tile_j` (32 or 64) conformers (panel tail + three B
-// stages must fit in shared memory); above it the FP64 tensor-core variant runs (tsc_rmsd_sim_tiles)
+// largest number of heavy atoms the screen takes with tiles of `tile_j` (32, 48 or 64) conformers (panel tail + three
+// B stages must fit in shared memory); above it the FP64 tensor-core variant runs (tsc_rmsd_sim_tiles)
 extern "C" int32_t tsc_screen_max_atoms(int32_t tile_j) {
     int best = 0;
+    if (tile_j != 32 && tile_j != 48 && tile_j != 64) return 0;
     for (int M = 16; M <= 1024; M += 16)
-        if (screen_fits(M, tile_j == 64 ? 64 : 32, nullptr, nullptr)) best = M;
+        if (screen_fits(M, tile_j, nullptr, nullptr)) best = M;
     return best;
 }
 
-// rows [row_begin, row_end) only (row_begin a multiple of 8; the last chunk should end at the padded row count
-// ceil(N/128)*128 so that the padding rows are written too); row_end <= 0: all rows.  tile_j: 32 or 64, the tile
-// width of the screen mode that will read PB / CT (tsc_rmsd_screen: mode 0 -> 64, modes 1 and 2 -> 32).
+// rows [row_begin, row_end) only (row_begin a multiple of 8; the last chunk should end at tsc_screen_rows_padded(N), or
+// pass row_end <= 0 for "to the end", so that the padding rows are written too).  tile_j: 32, 48 or 64, the tile
+// width of the screen mode that will read PB / CT (tsc_rmsd_screen: mode 0 -> 48, modes 1 and 2 -> 32, mode 3 -> 64).
 extern "C" int tsc_pack_screen(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M, void* PA,
                                void* PB, void* PR, double* G, double* sG, float* CT, int64_t row_begin, int64_t row_end,
                                int32_t tile_j, void* stream) {
     using namespace tsc;
     if (N <= 0 || M <= 0) return 0;
-    if (tile_j != 32 && tile_j != 64) return (int)cudaErrorInvalidValue;
+    if (tile_j != 32 && tile_j != 48 && tile_j != 64) return (int)cudaErrorInvalidValue;
     const int Mp = (M + 15) / 16 * 16;
-    const int64_t rows_pad = (N + SC_ROWS - 1) / SC_ROWS * SC_ROWS;
+    const int64_t rows_pad = tsc_screen_rows_padded(N);
     if (row_end <= 0 || row_end > rows_pad) row_end = rows_pad;
     if (row_begin < 0) row_begin = 0;
     if (row_end <= row_begin) return 0;
     const unsigned grid = (unsigned)((row_end - row_begin + 7) / 8);
     if (tile_j == 64)
         pack_screen_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            S, N, A, heavy_idx, M, Mp, row_end, reinterpret_cast<__half*>(PA), reinterpret_cast<__half*>(PB),
+            reinterpret_cast<__half*>(PR), G, sG, CT, row_begin);
+    else if (tile_j == 48)
+        pack_screen_kernel<48><<<grid, 256, 0, (cudaStream_t)stream>>>(
             S, N, A, heavy_idx, M, Mp, row_end, reinterpret_cast<__half*>(PA), reinterpret_cast<__half*>(PB),
             reinterpret_cast<__half*>(PR), G, sG, CT, row_begin);
     else
@@ -581,10 +629,12 @@ extern "C" void tsc_screen_set_trace(void* dev_ptr) { g_screen_trace = reinterpr
 #endif
 
 // items (n_items, 4) int32: {panel, first j tile, number of j tiles, local row block (32-row units) of the panel's
-// first row inside sim_bits}; j tiles are 64 conformers wide in mode 0 and 32 in modes 1 / 2 (the images must have
-// been packed with the matching tile_j); dealt round-robin to the CTAs of the persistent grid, an item with count 0
-// ends a CTA's list (_host.build_screen_items).  cand_list: header + (local row, j) entries, or NULL.
-// mode: 0 = isotropic form (Samuelson only), 1 = Samuelson then quartic, 2 = quartic for every pair (see the kernel).
+// first row inside sim_bits}; j tiles are 48 conformers wide in mode 0, 32 in modes 1 / 2 and 64 in mode 3 (the images
+// must have been packed with the matching tile_j; the first tile of a panel is the one holding its first column);
+// dealt round-robin to the CTAs of the persistent grid, an item with count 0 ends a CTA's list
+// (_host.build_screen_items).  cand_list: header + (local row, j) entries, or NULL.
+// mode: 0 = isotropic form (Samuelson only), 1 = Samuelson then quartic, 2 = quartic for every pair, 3 = mode 0 on
+// 64-wide tiles with two accumulator buffers (see the kernel).
 // pace: 0 = none; > 0 = cycles between two MMAs of one chain (measurement aid).
 extern "C" int tsc_rmsd_screen(const void* PA, const void* PB, const void* PR, const double* G, const double* sG,
                                const float* CT, int64_t N, int32_t M, const int32_t* items, int32_t n_items, double thr,
@@ -592,7 +642,7 @@ extern "C" int tsc_rmsd_screen(const void* PA, const void* PB, const void* PR, c
                                int32_t pace, void* stream) {
     using namespace tsc;
     if (n_items <= 0 || N <= 0) return 0;
-    if (mode < 0 || mode > 2) return (int)cudaErrorInvalidValue;
+    if (mode < 0 || mode > 3) return (int)cudaErrorInvalidValue;
     ScParams p;
     p.pace = pace <= 0 ? 0 : pace;
     p.PA = reinterpret_cast<const unsigned char*>(PA);
@@ -611,16 +661,16 @@ extern "C" int tsc_rmsd_screen(const void* PA, const void* PB, const void* PR, c
 #ifdef TSC_SCREEN_TRACE
     p.trace = g_screen_trace;
 #endif
-    const int J = mode == 0 ? 64 : 32;
+    const int J = mode == 0 ? 48 : mode == 3 ? 64 : 32;
     size_t a_bytes, b_bytes;
     if (!screen_fits(M, J, &a_bytes, &b_bytes)) return (int)cudaErrorInvalidValue;   // more atoms than tsc_screen_max_atoms(J)
-    const size_t q_bytes = (size_t)SC_EPI_WARPS * SC_Q * sizeof(int2);
-    const size_t budget = 227 * 1024 - 512 - q_bytes;
+    const size_t budget = 227 * 1024 - screen_side_bytes();
     int nb = (int)((budget - a_bytes) / b_bytes);
     if (nb > SC_MAX_BSTAGES) nb = SC_MAX_BSTAGES;
     p.nb_stages = nb;
-    const size_t smem = a_bytes + nb * b_bytes + 512 + q_bytes;
-    auto kern = mode == 0 ? rmsd_screen_kernel<0, 64> : mode == 2 ? rmsd_screen_kernel<2, 32> : rmsd_screen_kernel<1, 32>;
+    const size_t smem = a_bytes + nb * b_bytes + screen_side_bytes();
+    auto kern = mode == 0 ? rmsd_screen_kernel<0, 48> : mode == 3 ? rmsd_screen_kernel<0, 64>
+              : mode == 2 ? rmsd_screen_kernel<2, 32> : rmsd_screen_kernel<1, 32>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;
@@ -628,7 +678,7 @@ extern "C" int tsc_rmsd_screen(const void* PA, const void* PB, const void* PR, c
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid = grid_ctas > 0 ? grid_ctas : sms;
     if (grid > n_items) grid = n_items;
-    kern<<<grid, SC_THREADS, smem, (cudaStream_t)stream>>>(p);
+    kern<<<grid, sc_threads(J), smem, (cudaStream_t)stream>>>(p);
     TSC_CHECK_LAUNCH();
     return 0;
 }

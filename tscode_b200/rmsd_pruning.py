@@ -174,9 +174,9 @@ class RmsdPruner:
                 # pair (_host.screen_mode_for: a speed decision, every form is conservative)
                 first = (src[0] if not src.is_cuda else src[0].cpu()).numpy()[heavy]
                 self.screen_mode = _host.screen_mode_for(first)
-            self.tile_j = 64 if self.screen_mode == 0 else 32
-            if M > int(lib().tsc_screen_max_atoms(self.tile_j)) and self.screen_mode == 0:
-                self.screen_mode, self.tile_j = 1, 32        # too many atoms for 64-wide tiles: Samuelson, then quartic
+            self.tile_j = {0: 48, 3: 64}.get(self.screen_mode, 32)
+            if M > int(lib().tsc_screen_max_atoms(self.tile_j)) and self.screen_mode in (0, 3):
+                self.screen_mode, self.tile_j = 1, 32        # too many atoms for the wide tiles: Samuelson, then quartic
         else:
             self.tile_j = 32
         if self.variant == 5 and M > int(lib().tsc_screen_max_atoms(self.tile_j)):
@@ -539,12 +539,11 @@ class RmsdPruner:
             self.stats.zero_()
             self.cand_list[0].fill_(0)
             self._pairs_ready = False
-            rows_pad = n_panels * 128
             st = stream_ptr()
             for c, ev in events:
                 lo, hi = bounds[c], bounds[c + 1]
                 main.wait_event(ev)
-                hi_pad = rows_pad if c == n_chunks - 1 else hi
+                hi_pad = 0 if c == n_chunks - 1 else hi                  # 0: to the end of the padding rows
                 check(L.tsc_pack_blocks(ptr(self.S), N, self.A, ptr(self.heavy_idx), self.M, ptr(self.packed), ptr(self.G),
                                         lo // 32, self.nb_pad if c == n_chunks - 1 else hi // 32, st), "tsc_pack_blocks")
                 check(L.tsc_pack_screen(ptr(self.S), N, self.A, ptr(self.heavy_idx), self.M, ptr(self.PA), ptr(self.PB),
