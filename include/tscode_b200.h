@@ -84,11 +84,18 @@ int64_t tsc_screen_ct_floats(int64_t N);
 int32_t tsc_screen_max_atoms(int32_t tile_j);
 int tsc_pack_screen(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M, void* PA, void* PB,
                     void* PR, double* G, double* sG, float* CT, int64_t row_begin, int64_t row_end, int32_t tile_j,
-                    void* stream);
+                    const double* frame, void* stream);
 int tsc_rmsd_screen(const void* PA, const void* PB, const void* PR, const double* G, const double* sG,
                     const float* CT, int64_t N, int32_t M, const int32_t* items, int32_t n_items, double thr,
                     uint32_t* sim_bits, int32_t* cand_list, int64_t cand_stride, int32_t grid_ctas, int32_t mode,
-                    int32_t pace, void* stream);
+                    int32_t pace, const double* frame, void* stream);
+/*   frame (HOST memory, 12 doubles, or NULL): an orthogonal matrix Q (row-major) applied to every conformer and
+ *   three scales t applied to the column-side image along Q's axes.  With sum_b 1 / (3 t_b^2) <= 1 the Frobenius norm
+ *   of the scaled covariance still bounds lambda_max (Cauchy-Schwarz over the column norms), and in the principal-axes
+ *   frame of the molecule with t_b^2 = (l1 + l2 + l3) / (3 l_b) that bound is as sharp for elongated and planar
+ *   molecules as Samuelson's is for isotropic ones (rmsd_screen.cu, ScFrame).  NULL = identity = Samuelson.  The same
+ *   frame must be given to tsc_pack_screen and tsc_rmsd_screen; both return cudaErrorInvalidValue (1) when Q is not
+ *   orthogonal to 1e-13 or the scales violate the inequality — the conditions exclusion rests on. */
 /*   cand_list (may be NULL): block of cand_stride int32 pairs, element 0 = header whose first int32 is the running
  *   count (zero it first); (local row, j) of every bit the screen sets is appended from element 1; a count outside
  *   [0, cand_stride - 1] means the list overflowed (tsc_rmsd_verify then scans the bit rows instead). */

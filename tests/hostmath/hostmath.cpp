@@ -124,7 +124,7 @@ void hm_q32t_det(const float* S, int n, double* out) {
         for (int q = 0; q < 9; q++) Sd[q] = s[q];
         long double dS = Sd[0] * (Sd[4] * Sd[8] - Sd[5] * Sd[7]) - Sd[1] * (Sd[3] * Sd[8] - Sd[5] * Sd[6])
                        + Sd[2] * (Sd[3] * Sd[7] - Sd[4] * Sd[6]);
-        out[3 * k + 0] = (double)sqrtf(da > 0.f ? da : 0.f);
+        out[3 * k + 0] = (double)(da >= 1.17549435e-38f ? sqrtf(da) : 0.f);
         out[3 * k + 1] = (double)fabsl(dS);
         out[3 * k + 2] = (double)f;
     }

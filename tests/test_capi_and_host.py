@@ -316,3 +316,46 @@ def test_cluster_survivor_choice_equals_networkx():
             n_checked += 1
     assert n_checked > 3000
     assert tm._cluster_rejects([(0, 1), (1, 2), (5, 6)]) is not None and tm._CLUSTER_IMPL[0] is tm._cluster_rejects_fast
+
+
+def test_screen_frame_is_orthogonal_and_weights_satisfy_the_inequality():
+    """_host.screen_frame: whatever the first structure looks like, Q must be orthogonal to the library's 1e-13 and
+    sum_b 1 / (3 t_b^2) <= 1 — the two facts the weighted Samuelson bound rests on (rmsd_screen.cu, ScFrame); an
+    isotropic blob gives the identity exactly; the weighted bound never falls below lambda_max."""
+    rng = np.random.default_rng(0)
+    shapes = ([3, 3, 3], [6, 2, 1], [4, 4, 0.5], [8, 1, 1], [5, 5, 1e-6], [1e-3, 1, 1e3], [10, 0, 0])
+    for sc in shapes:
+        for M in (3, 17, 80):
+            X = rng.normal(size=(M, 3)) * np.array(sc, dtype=np.float64)
+            th = rng.normal(size=3)
+            R, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+            X = X @ R.T + 0.0 * th
+            fr, ratio = _host.screen_frame(X)
+            Q, t = fr[:9].reshape(3, 3), fr[9:]
+            assert np.abs(Q @ Q.T - np.eye(3)).max() <= 1e-13
+            assert (1.0 / (3.0 * t * t)).sum() <= 1.0 and (t > 1e-3).all() and (t < 1e3).all()
+            # the bound itself: for random pairs of perturbed copies, sqrt(3) ||Q S Q^T diag(t)||_F >= sum of singular values
+            for _ in range(20):
+                P = X + rng.normal(size=X.shape) * 0.7
+                Y = X + rng.normal(size=X.shape) * 0.7
+                S = (P @ Q.T).T @ ((Y @ Q.T) * t)
+                plain = P.T @ Y
+                assert np.sqrt(3.0) * np.linalg.norm(S) >= np.linalg.svd(plain, compute_uv=False).sum() * (1 - 1e-12)
+    fr, ratio = _host.screen_frame(np.eye(3) * 2.0)
+    assert np.array_equal(fr, np.concatenate([np.eye(3).ravel(), np.ones(3)])) and abs(ratio - 1.0) < 1e-12
+    assert _host.screen_mode_for(rng.normal(size=(80, 3)) * 3.0) == 0
+    assert _host.screen_mode_for(rng.normal(size=(80, 3)) * np.array([6.0, 2.0, 1.0])) == 1
+
+
+def test_library_rejects_a_frame_that_would_break_the_bound():
+    """tsc_pack_screen / tsc_rmsd_screen check the frame before anything touches the GPU: a non-orthogonal Q or
+    weights with sum 1 / w > 1 return cudaErrorInvalidValue (1)."""
+    L = _lib.lib()
+    good = np.concatenate([np.eye(3).ravel(), np.ones(3)])
+    bad_q = good.copy(); bad_q[1] = 1e-6
+    bad_t = good.copy(); bad_t[9:] = [0.9, 1.0, 1.0]
+    nan_t = good.copy(); nan_t[10] = np.nan
+    for fr in (bad_q, bad_t, nan_t):
+        assert L.tsc_pack_screen(None, 10, 4, None, 4, None, None, None, None, None, None, 0, 0, 32, fr.ctypes.data, None) == 1
+        assert L.tsc_rmsd_screen(None, None, None, None, None, None, 10, 4, None, 1, 0.5, None, None, 0, 0, 0, 0,
+                                 fr.ctypes.data, None) == 1

@@ -288,6 +288,21 @@ def test_fp32_T_form_never_excludes_a_pair_above_the_test_point(hmt):
                 continue
             for rel in (-0.5, -1e-2, -1e-4, -1e-6, 0.0):
                 assert hmt.hm_q32t_excluded(S[k], float(np.float32(top * (1 + rel))), C.byref(lm)) == 0
+    # tiny covariances: the device's flush-to-zero root returns d = 0 once det T + 8 u f^3 is subnormal; the test point
+    # then has to exceed Q32_LAM_MIN = 1e-4 (tsc_math.cuh, quartic32_decide) — still sound, and nothing below the cut
+    # is ever excluded
+    for scale in (1e-2, 1e-4, 1e-5, 1e-6, 3e-7):
+        for kind in (0, 1, 2, 4):
+            S = np.ascontiguousarray(_q32_covariances(rng, kind, 200) * np.float32(scale))
+            for k in range(200):
+                hmt.hm_q32t_excluded(S[k], 1.0, C.byref(lm))
+                top = lm.value
+                if not np.isfinite(top) or top <= 0:
+                    continue
+                for rel in (-0.5, -1e-3, -1e-6, 0.0):
+                    assert hmt.hm_q32t_excluded(S[k], float(np.float32(top * (1 + rel))), C.byref(lm)) == 0
+                for lam in (1e-5, 9.9e-5, 1e-4):
+                    assert hmt.hm_q32t_excluded(S[k], float(np.float32(lam)), C.byref(lm)) == 0
     # screening power on the elongated sample of the signed form's test
     n = 3000
     base = rng.normal(size=(80, 3)) * np.array([6, 2, 1.0])

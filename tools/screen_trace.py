@@ -18,7 +18,7 @@ from tscode_b200.synth import gen_ensemble  # noqa: E402
 
 P = C.CDLL(os.path.join(ROOT, "tools", "probes", "libtsc_probe.so"))
 vp, i32, i64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
-P.tsc_rmsd_screen.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, vp, i32, f64, vp, vp, i64, i32, i32, i32, vp]
+P.tsc_rmsd_screen.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, vp, i32, f64, vp, vp, i64, i32, i32, i32, vp, vp]
 P.tsc_screen_set_trace.argtypes = [vp]
 
 N, M = int(sys.argv[1]), int(sys.argv[2])
@@ -31,7 +31,7 @@ for pace in [int(x) for x in sys.argv[3].split(",")]:           # here: the scre
         pr.cand_list[0].fill_(0)
         P.tsc_screen_set_trace(ptr(trace) if rep == 1 else None)
         check(P.tsc_rmsd_screen(ptr(pr.PA), ptr(pr.PB), ptr(pr.PR), ptr(pr.G), ptr(pr.sG), ptr(pr.CT), pr.N, pr.M, ptr(pr.items),
-                                pr.n_items, pr.thr, ptr(pr.sim_bits), ptr(pr.cand_list), pr.cand_stride, 0, pace, 0, stream_ptr()), "screen")
+                                pr.n_items, pr.thr, ptr(pr.sim_bits), ptr(pr.cand_list), pr.cand_stride, 0, pace, 0, pr._frame_ptr(), stream_ptr()), "screen")
         torch.cuda.synchronize()
     P.tsc_screen_set_trace(None)
     tr = trace.cpu().numpy().reshape(192, 8)

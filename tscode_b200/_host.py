@@ -53,20 +53,43 @@ def build_screen_items(N: int, row_blocks: np.ndarray, n_ctas: int, panel_lo: in
                                 tile_j=int(tile_j))
 
 
-def screen_mode_for(first_heavy: np.ndarray) -> int:
-    """Which form of the default screen suits an ensemble (rmsd_screen.cu; a speed decision only: every form is
-    conservative).  Samuelson's bound sqrt(3) ||S||_F >= sigma1 + sigma2 + sigma3 is sharp for isotropic covariances
-    and useless for anisotropic ones; the covariance of two similar conformers has the spectrum of the molecule's
-    second-moment tensor, so the ratio sqrt(3 sum l^2) / sum l of its eigenvalues (1 = isotropic) tells: up to
-    1.03 the cheap isotropic form (mode 0) is used, above it the quartic test for every pair (mode 2)."""
+def screen_frame(first_heavy: np.ndarray):
+    """Frame and column weights of the default screen for an ensemble, from its first structure (rmsd_screen.cu, ScFrame):
+    returns (frame, ratio) with frame = 12 float64 [Q row-major (rows = principal axes of the heavy atoms' second-moment
+    tensor), t_b = sqrt(w_b / 3)], w_b = (l1 + l2 + l3) / l_b (eigenvalues floored at 1e-4 of their sum, weights then
+    inflated so that sum 1 / w_b <= 1 holds in floating point), and ratio = sqrt(3 sum l^2) / sum l, the looseness of
+    the UNweighted Samuelson bound for this shape (1 = isotropic).  For an isotropic molecule Q = I, t = 1 exactly.
+    A speed device only: any orthogonal Q and any weights with sum 1 / w_b <= 1 are sound (checked by the library)."""
+    ident = np.concatenate([np.eye(3).ravel(), np.ones(3)])
     X = np.asarray(first_heavy, dtype=np.float64).reshape(-1, 3)
-    if X.shape[0] == 0:
-        return 2
-    lam = np.linalg.eigvalsh(X.T @ X)
+    if X.shape[0] == 0 or not np.isfinite(X).all():
+        return ident, np.inf
+    lam, vec = np.linalg.eigh(X.T @ X)
     tot = float(lam.sum())
     if not np.isfinite(tot) or tot <= 0.0:
-        return 2
-    return 0 if float(np.sqrt(3.0 * (lam ** 2).sum())) / tot <= 1.03 else 2
+        return ident, np.inf
+    ratio = float(np.sqrt(3.0 * (lam ** 2).sum())) / tot
+    if ratio <= 1.0005:                                          # isotropic to the last digit that matters: plain Samuelson
+        return ident, ratio
+    lam = np.maximum(lam, 1e-4 * tot)
+    w = lam.sum() / lam * (1.0 + 1e-9)
+    Q = vec.T.copy()
+    for _ in range(2):                                           # re-orthonormalise to the library's 1e-13 (Gram-Schmidt)
+        Q[0] /= np.linalg.norm(Q[0])
+        Q[1] -= Q[0] * (Q[1] @ Q[0]); Q[1] /= np.linalg.norm(Q[1])
+        Q[2] -= Q[0] * (Q[2] @ Q[0]) + Q[1] * (Q[2] @ Q[1]); Q[2] /= np.linalg.norm(Q[2])
+    assert float((1.0 / w).sum()) <= 1.0
+    return np.concatenate([Q.ravel(), np.sqrt(w / 3.0)]), ratio
+
+
+def screen_mode_for(first_heavy: np.ndarray) -> int:
+    """Which form of the default screen suits an ensemble (rmsd_screen.cu; a speed decision only: every form is
+    conservative).  In the frame of screen_frame the weighted Samuelson bound is sharp for similar conformers of any
+    shape; what decides is how often it fails for DISsimilar pairs, which the first structure alone cannot tell.  Near-
+    isotropic molecules (unweighted looseness <= 1.03) take the cheapest form, mode 0: the bound only, on 48-wide
+    tiles; everything else mode 1: the bound, then the FP32 quartic sign test for the groups of 64 pairs in which it
+    left a pair undecided."""
+    return 0 if screen_frame(first_heavy)[1] <= 1.03 else 1
 
 
 def build_items_balanced(N: int, row_blocks: np.ndarray, n_ctas: int, panel_lo: int = 0,

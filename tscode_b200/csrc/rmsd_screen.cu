@@ -73,6 +73,8 @@ struct ScParams {
     int64_t W;                // 32-bit words per sim row
     int2* cand;
     int64_t cand_stride;
+    int scaled;               // the B-side image holds scaled coordinates (ScFrame): the quartic stage un-scales T first
+    float inv_tt[6];          // 1 / (t_b t_c) for T's entries (00, 11, 22, 01, 02, 12)
 #ifdef TSC_SCREEN_TRACE
     long long* trace;         // measurement build only (tools/probes): clock64 stamps of CTA 0, see tools/screen_trace.py
 #endif
@@ -95,13 +97,36 @@ struct ScParams {
 // Images: PA [panel][a][kc][128][16 B] and PR [row][a][kc][16 B] (stationary panel: shared-memory tail / TMEM part),
 // PB [j tile of J conformers][kc][(b, j) = 3 J rows][16 B] (canonical no-swizzle K-major core-matrix order: a plain
 // bulk copy of a tile is the shared-memory operand of the MMAs), CT [j tile][2 J] column terms.
+//
+// Frame and column weights (ScFrame).  Samuelson's bound sqrt(3) ||S||_F >= s1 + s2 + s3 is sharp only for isotropic
+// covariances; for an elongated or planar molecule it excluded nothing.  Two exact facts fix that at no cost to the
+// kernel: (1) rotating BOTH conformers by the same orthogonal Q leaves the singular values of S, hence lambda_max,
+// unchanged; (2) the nuclear norm is at most the sum of the column norms, and by Cauchy-Schwarz, for any weights
+// w_b > 0 with sum_b 1 / w_b <= 1,
+//     s1 + s2 + s3 <= sum_b ||col_b(S)|| <= sqrt(sum_b w_b ||col_b(S)||^2) = sqrt(3) || S diag(t) ||_F,  t_b = sqrt(w_b / 3).
+// S diag(t) is the covariance of conformer i with conformer j's coordinates scaled by t_b along axis b — what the MMAs
+// compute if the B-side image holds the scaled coordinates.  In the principal-axes frame of the molecule (Q from the
+// second-moment tensor of the first structure: there S is nearly diagonal, the column norms are nearly the singular
+// values) with w_b = (l1 + l2 + l3) / l_b the bound is within 1-3 % of lambda_max for elongated and planar ensembles
+// (tools/weighted_bound_probe.py), as Samuelson's is for isotropic ones, where Q = I, t = 1 reproduce it exactly.  Soundness
+// needs only Q orthogonal and sum 1 / w_b <= 1 (checked by tsc_pack_screen), never that the frame is well chosen.
+// The A-side images hold the rotated, unscaled coordinates.  Error bound: per component, |E_ab| <= 2^-10 (1 + ..)
+// ||p_a|| ||q^_b|| (relative rounding is scale invariant), so ||S^~ - S^||_F <= eps sqrt(G_i)' sqrt(G^_j)' with G^_j the
+// squared norm of the SCALED column conformer; the modes that recover T = S^T S from T^ = diag(t) T diag(t) for the
+// quartic test (entries divided by t_b t_c) get ||S~ - S||_F <= eps sqrt(G_i)' sqrt(G_j)' the same way.  The column
+// term D_j is the larger of the two widened roots, valid for both.
+struct ScFrame {
+    double q[9];              // rows = the frame's axes: x' = q[0] x + q[1] y + q[2] z, ...
+    double t[3];              // B-side scale per axis
+    double inv_tmin;          // 1 / min(t): worst growth of a flushed (absolute-error) coordinate when T is un-scaled
+};
 template <int J>
 __global__ void __launch_bounds__(256) pack_screen_kernel(const double* __restrict__ S, int64_t N, int A,
                                                           const int32_t* __restrict__ heavy_idx, int M, int Mp,
                                                           int64_t n_rows_end, __half* __restrict__ PA,
                                                           __half* __restrict__ PB, __half* __restrict__ PR,
                                                           double* __restrict__ G, double* __restrict__ sG,
-                                                          float* __restrict__ CT, int64_t row_begin) {
+                                                          float* __restrict__ CT, int64_t row_begin, const ScFrame fr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t i = row_begin + (int64_t)blockIdx.x * 8 + warp;      // one warp per conformer (incl. padding rows)
     if (i >= n_rows_end) return;
@@ -110,44 +135,57 @@ __global__ void __launch_bounds__(256) pack_screen_kernel(const double* __restri
     const int nkc = Mp / 8;
     const int64_t panel = i / SC_ROWS, r = i % SC_ROWS;
     const int64_t jt = i / J, jj = i % J;
-    double g = 0.0;
-    int tiny = 0;
+    double g = 0.0, gb = 0.0;                                   // exact squared norm (as given); of the scaled B side
+    int tiny = 0, tiny_b = 0;
     const double fmin_normal = 6.103515625e-05;                 // 2^-14
+    auto to_half = [&](double v, int& n_tiny) {
+        n_tiny += (v != 0.0 && fabs(v) < fmin_normal);
+        return fabs(v) < fmin_normal ? __float2half_rn(0.f) : __double2half(v);
+    };
     for (int m = lane; m < Mp; m += 32) {
         double x = 0.0, y = 0.0, z = 0.0;
         if (live && m < M) {
             const double* a = src + (int64_t)heavy_idx[m] * 3;
-            x = a[0]; y = a[1]; z = a[2];
-            g = fma(x, x, fma(y, y, fma(z, z, g)));
+            const double x0 = a[0], y0 = a[1], z0 = a[2];
+            g = fma(x0, x0, fma(y0, y0, fma(z0, z0, g)));
+            x = fma(fr.q[0], x0, fma(fr.q[1], y0, fr.q[2] * z0));
+            y = fma(fr.q[3], x0, fma(fr.q[4], y0, fr.q[5] * z0));
+            z = fma(fr.q[6], x0, fma(fr.q[7], y0, fr.q[8] * z0));
         }
-        tiny += (x != 0.0 && fabs(x) < fmin_normal) + (y != 0.0 && fabs(y) < fmin_normal) +
-                (z != 0.0 && fabs(z) < fmin_normal);
-        const __half hx = fabs(x) < fmin_normal ? __float2half_rn(0.f) : __double2half(x);
-        const __half hy = fabs(y) < fmin_normal ? __float2half_rn(0.f) : __double2half(y);
-        const __half hz = fabs(z) < fmin_normal ? __float2half_rn(0.f) : __double2half(z);
+        const __half hx = to_half(x, tiny), hy = to_half(y, tiny), hz = to_half(z, tiny);
+        const double xb = fr.t[0] * x, yb = fr.t[1] * y, zb = fr.t[2] * z;
+        gb = fma(xb, xb, fma(yb, yb, fma(zb, zb, gb)));
+        const __half bx = to_half(xb, tiny_b), by = to_half(yb, tiny_b), bz = to_half(zb, tiny_b);
         const int kc = m >> 3, e = m & 7;
         __half* pa = PA + (((panel * 3) * nkc + kc) * SC_ROWS + r) * 8 + e;
         pa[0] = hx;
         pa[(int64_t)nkc * SC_ROWS * 8] = hy;
         pa[(int64_t)2 * nkc * SC_ROWS * 8] = hz;
         __half* pb = PB + ((jt * nkc + kc) * (3 * J) + jj) * 8 + e;
-        pb[0] = hx;
-        pb[J * 8] = hy;
-        pb[2 * J * 8] = hz;
+        pb[0] = bx;
+        pb[J * 8] = by;
+        pb[2 * J * 8] = bz;
         __half* pr = PR + (size_t)i * 3 * Mp + m;
         pr[0] = hx;
         pr[Mp] = hy;
         pr[2 * Mp] = hz;
     }
     g = warp_sum(g);
+    gb = warp_sum(gb);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tiny += __shfl_xor_sync(0xffffffffu, tiny, o);
+    for (int o = 16; o > 0; o >>= 1) {
+        tiny += __shfl_xor_sync(0xffffffffu, tiny, o);
+        tiny_b += __shfl_xor_sync(0xffffffffu, tiny_b, o);
+    }
     if (lane == 0) {
         const double alpha = 6.103515625e-05 * (1.0 + 9.765625e-4) / TF_EPS;
-        const double sg = sqrt(g) + alpha * sqrt((double)tiny);
+        const double rot = 1.0 + 1e-12;                          // |Q x|^2 <= (1 + 1e-12) |x|^2 (Q checked to 1e-13)
+        const double sg = sqrt(g) * rot + alpha * sqrt((double)tiny);                  // row side: rotated, unscaled
+        const double sgb = sqrt(gb) * rot + alpha * sqrt((double)tiny_b);              // column side as the MMAs see it
+        const double sgu = sqrt(g) * rot + alpha * fr.inv_tmin * sqrt((double)tiny_b); // ... and un-scaled again
         G[i] = g; sG[i] = sg;
         CT[jt * (2 * J) + jj] = __double2float_rd(0.5 * (1.0 - 1e-10) * g);
-        CT[jt * (2 * J) + J + jj] = __double2float_ru(sg);
+        CT[jt * (2 * J) + J + jj] = __double2float_ru(fmax(sg, fmax(sgb, sgu)));
     }
 }
 
@@ -160,7 +198,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 __device__ __forceinline__ float sqrt_approx(float x) {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 
@@ -489,6 +527,10 @@ __global__ void __launch_bounds__(sc_threads(J), 1) rmsd_screen_kernel(const ScP
                         float lam[2];
 #pragma unroll
                         for (int h = 0; h < 2; h++) lam[h] = fmaf(-2e-7f, fabsf(ab[h]) + fabsf(lf[h]), lf[h]);
+                        if (p.scaled) {                                      // T^ = diag(t) T diag(t)  ->  T
+#pragma unroll
+                            for (int q = 0; q < 6; q++) tt[q] = OpsF2::mul(tt[q], OpsF2::bc(p.inv_tt[q]));
+                        }
                         const unsigned long long lam2 = OpsF2::pack(__float_as_uint(lam[0]), __float_as_uint(lam[1]));
                         unsigned long long fq, cc0, da, p0, p1, p2, m0, m1, m2;
                         quartic32_T_coeffs<OpsF2>(tt, fq, cc0, da);
@@ -595,11 +637,34 @@ extern "C" int32_t tsc_screen_max_atoms(int32_t tile_j) {
 // rows [row_begin, row_end) only (row_begin a multiple of 8; the last chunk should end at tsc_screen_rows_padded(N), or
 // pass row_end <= 0 for "to the end", so that the padding rows are written too).  tile_j: 32, 48 or 64, the tile
 // width of the screen mode that will read PB / CT (tsc_rmsd_screen: mode 0 -> 48, modes 1 and 2 -> 32, mode 3 -> 64).
+// frame (host memory, 12 doubles, or NULL = identity): orthogonal Q (row-major, rows = axes) and the B-side scales t
+// (ScFrame above; _host.screen_frame).  Returns cudaErrorInvalidValue unless |Q Q^T - I| <= 1e-13 and
+// sum_b 1 / (3 t_b^2) <= 1 — the two facts the exclusion tests rest on.
+static bool screen_frame_from(const double* frame, tsc::ScFrame& fr) {
+    for (int k = 0; k < 9; k++) fr.q[k] = frame ? frame[k] : (k % 4 == 0 ? 1.0 : 0.0);
+    for (int k = 0; k < 3; k++) fr.t[k] = frame ? frame[9 + k] : 1.0;
+    double inv_w = 0.0, tmin = fr.t[0];
+    for (int b = 0; b < 3; b++) {
+        if (!(fr.t[b] > 1e-3 && fr.t[b] < 1e3)) return false;
+        inv_w += 1.0 / (3.0 * fr.t[b] * fr.t[b]);
+        tmin = fr.t[b] < tmin ? fr.t[b] : tmin;
+        for (int c = 0; c < 3; c++) {
+            double d = (b == c) ? -1.0 : 0.0;
+            for (int k = 0; k < 3; k++) d += fr.q[3 * b + k] * fr.q[3 * c + k];
+            if (!(d <= 1e-13 && d >= -1e-13)) return false;
+        }
+    }
+    fr.inv_tmin = 1.0 / tmin;
+    return inv_w <= 1.0;
+}
+
 extern "C" int tsc_pack_screen(const double* S, int64_t N, int32_t A, const int32_t* heavy_idx, int32_t M, void* PA,
                                void* PB, void* PR, double* G, double* sG, float* CT, int64_t row_begin, int64_t row_end,
-                               int32_t tile_j, void* stream) {
+                               int32_t tile_j, const double* frame, void* stream) {
     using namespace tsc;
     if (N <= 0 || M <= 0) return 0;
+    ScFrame fr;
+    if (!screen_frame_from(frame, fr)) return (int)cudaErrorInvalidValue;
     if (tile_j != 32 && tile_j != 48 && tile_j != 64) return (int)cudaErrorInvalidValue;
     const int Mp = (M + 15) / 16 * 16;
     const int64_t rows_pad = tsc_screen_rows_padded(N);
@@ -610,15 +675,15 @@ extern "C" int tsc_pack_screen(const double* S, int64_t N, int32_t A, const int3
     if (tile_j == 64)
         pack_screen_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(
             S, N, A, heavy_idx, M, Mp, row_end, reinterpret_cast<__half*>(PA), reinterpret_cast<__half*>(PB),
-            reinterpret_cast<__half*>(PR), G, sG, CT, row_begin);
+            reinterpret_cast<__half*>(PR), G, sG, CT, row_begin, fr);
     else if (tile_j == 48)
         pack_screen_kernel<48><<<grid, 256, 0, (cudaStream_t)stream>>>(
             S, N, A, heavy_idx, M, Mp, row_end, reinterpret_cast<__half*>(PA), reinterpret_cast<__half*>(PB),
-            reinterpret_cast<__half*>(PR), G, sG, CT, row_begin);
+            reinterpret_cast<__half*>(PR), G, sG, CT, row_begin, fr);
     else
         pack_screen_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(
             S, N, A, heavy_idx, M, Mp, row_end, reinterpret_cast<__half*>(PA), reinterpret_cast<__half*>(PB),
-            reinterpret_cast<__half*>(PR), G, sG, CT, row_begin);
+            reinterpret_cast<__half*>(PR), G, sG, CT, row_begin, fr);
     TSC_CHECK_LAUNCH();
     return 0;
 }
@@ -635,15 +700,22 @@ extern "C" void tsc_screen_set_trace(void* dev_ptr) { g_screen_trace = reinterpr
 // (_host.build_screen_items).  cand_list: header + (local row, j) entries, or NULL.
 // mode: 0 = isotropic form (Samuelson only), 1 = Samuelson then quartic, 2 = quartic for every pair, 3 = mode 0 on
 // 64-wide tiles with two accumulator buffers (see the kernel).
-// pace: 0 = none; > 0 = cycles between two MMAs of one chain (measurement aid).
+// pace: 0 = none; > 0 = cycles between two MMAs of one chain (measurement aid).  frame: the one given to tsc_pack_screen.
 extern "C" int tsc_rmsd_screen(const void* PA, const void* PB, const void* PR, const double* G, const double* sG,
                                const float* CT, int64_t N, int32_t M, const int32_t* items, int32_t n_items, double thr,
                                uint32_t* sim_bits, int32_t* cand_list, int64_t cand_stride, int32_t grid_ctas, int32_t mode,
-                               int32_t pace, void* stream) {
+                               int32_t pace, const double* frame, void* stream) {
     using namespace tsc;
     if (n_items <= 0 || N <= 0) return 0;
     if (mode < 0 || mode > 3) return (int)cudaErrorInvalidValue;
     ScParams p;
+    ScFrame fr;
+    if (!screen_frame_from(frame, fr)) return (int)cudaErrorInvalidValue;
+    p.scaled = !(fr.t[0] == 1.0 && fr.t[1] == 1.0 && fr.t[2] == 1.0);
+    {
+        const int bb[6] = {0, 1, 2, 0, 0, 1}, cc[6] = {0, 1, 2, 1, 2, 2};
+        for (int q = 0; q < 6; q++) p.inv_tt[q] = (float)(1.0 / (fr.t[bb[q]] * fr.t[cc[q]]));
+    }
     p.pace = pace <= 0 ? 0 : pace;
     p.PA = reinterpret_cast<const unsigned char*>(PA);
     p.PB = reinterpret_cast<const unsigned char*>(PB);

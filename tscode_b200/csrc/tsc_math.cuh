@@ -212,8 +212,8 @@ TSC_HD void quartic32_values(const typename O::T* S, typename O::T f, typename O
 // Margin: every Leibniz term of det T is at most T00 T11 T22 <= (f/3)^3; the entries of T~ carry a relative
 // error <= 3 u of sqrt(T_aa T_bb), each term thus <= 9 u f^3 / 27, six terms 2 u f^3; the evaluation (nine
 // operations on quantities <= 2 f^3 / 27) adds less than u f^3.  8 u f^3 is more than twice the sum.
-// sqrt is the approximate instruction on the device (error <= 2 ulp; the factor 1 + 4 u covers it and the
-// addition under the root).  P and P' take -8 d through the same Horner steps as before, so the forward-error
+// sqrt is the approximate flush-to-zero instruction on the device (error <= 2 ulp; the factor 1 + 4 u covers it and
+// the addition under the root; arguments below 2^-126 give 0, see quartic32_decide).  P and P' take -8 d through the same Horner steps as before, so the forward-error
 // tolerances of quartic32_margins (which even include an allowance for c1's own rounding) stay valid.
 // ------------------------------------------------------------------------------------------
 constexpr float Q32_DET_MARGIN = 4.77e-7f;    // 8 u
@@ -265,9 +265,24 @@ TSC_HD void quartic32_margins(typename O::T p0, typename O::T p1, typename O::T 
     m1 = O::fma(O::mul(R2, R), O::bc(-Q32_T1SQ), O::mul(p1, p1));
 }
 
-// true = all roots of the quartic are provably below lam (NaN / inf anywhere -> false)
+// true = all roots of the quartic are provably below lam (NaN / inf anywhere -> false).
+// lam has to exceed Q32_LAM_MIN rather than 0: the device takes the root of det_arg with the flush-to-zero
+// approximate instruction (one MUFU instead of a five-instruction sequence), i.e. d = 0 for det_arg < 2^-126, short of
+// the true bound by at most 1.1e-19; then f <= 2.9e-11 (det_arg >= 8 u f^3), the terms -8 d lam of P and -8 d of P' are
+// off by <= 8.7e-19 lam and 8.7e-19, and the unused halves of the tolerances, 32 u R^2 >= 1.9e-6 lam^4 and
+// 36 u R^(3/2) >= 2.1e-6 lam^3, cover that as soon as lam >= 7.7e-5.  (A threshold eigenvalue that small means
+// G_i + G_j ~ M thr^2, a molecule the size of the threshold; the pair simply stays a candidate.)
+// On the device: two three-input NaN-propagating minima and one comparison instead of five comparisons and four selects.
+constexpr float Q32_LAM_MIN = 1e-4f;
 TSC_HD bool quartic32_decide(float lam, float p1, float m0, float m1, float m2) {
-    return (lam > 0.0f) & (p1 > 0.0f) & (m0 > 0.0f) & (m1 > 0.0f) & (m2 > 0.0f);
+#ifdef __CUDA_ARCH__
+    float t, lg = __fsub_rn(lam, Q32_LAM_MIN);              // > 0 iff lam > Q32_LAM_MIN (exact near the cut: Sterbenz)
+    asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(t) : "f"(m0), "f"(m1), "f"(m2));
+    asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(t) : "f"(t), "f"(p1), "f"(lg));
+    return t > 0.0f;
+#else
+    return (lam > Q32_LAM_MIN) & (p1 > 0.0f) & (m0 > 0.0f) & (m1 > 0.0f) & (m2 > 0.0f);
+#endif
 }
 
 TSC_HD bool quartic32_excluded(const float S[9], float f, float lam) {
@@ -281,7 +296,8 @@ TSC_HD bool quartic32_excluded(const float S[9], float f, float lam) {
 TSC_HD bool quartic32_T_excluded(const float t[6], float lam) {
     float f, c0, da, p0, p1, p2, m0, m1, m2;
     quartic32_T_coeffs<OpsF32>(t, f, c0, da);
-    const float d = sqrtf(da > 0.0f ? da : 0.0f);            // a NaN argument gives d = 0, but then f is NaN too: not excluded
+    // a NaN argument gives d = 0, but then f is NaN too: not excluded; below the smallest normal the device's root is 0
+    const float d = da >= 1.17549435e-38f ? sqrtf(da) : 0.0f;
     quartic32_T_values<OpsF32>(f, c0, d, lam, p0, p1, p2);
     quartic32_margins<OpsF32>(p0, p1, p2, f, lam, m0, m1, m2);
     return quartic32_decide(lam, p1, m0, m1, m2);

@@ -111,9 +111,13 @@ class RmsdPruner:
                  bound; sign test of the key-matrix quartic), exact FP64 verification of everything it cannot
                  exclude; falls back to "dmma" above tsc_screen_max_atoms heavy atoms.  "dmma" = FP64 tensor cores,
                  "fma" = FP64 FMA pipe.  All give identical final similarity bits and masks.
-    screen_mode: form of the default screen (0 = isotropic / Samuelson only on 64-wide tiles, 1 = Samuelson then
-                 quartic, 2 = quartic for every pair); None = chosen from the shape of the first structure
-                 (_host.screen_mode_for).  A speed choice only: every form is conservative.
+    screen_mode: form of the default screen (0 = Samuelson-type bound only, on 48-wide tiles; 1 = the bound, then
+                 the FP32 quartic test where it left a pair undecided; 2 = quartic for every pair; 3 = mode 0 on
+                 64-wide tiles); None = chosen from the shape of the first structure (_host.screen_mode_for).
+    screen_frame: rotate the ensemble into the principal axes of the first structure and weight the column-side
+                 operand (_host.screen_frame; rmsd_screen.cu, ScFrame), which makes the bound as sharp for elongated
+                 and planar molecules as it is for isotropic ones.  Both are speed choices only: every form is
+                 conservative and the final bits are exact.
     rank/world/group : row-block sharding over one process per GPU (block-cyclic, SURVEY 8(e));
                  every rank holds the whole packed ensemble, computes the similarity rows it
                  owns, and per elimination round contributes its rows' verdicts to an NCCL
@@ -122,7 +126,7 @@ class RmsdPruner:
 
     def __init__(self, structures, atomnos, rmsd_thr=0.5, *, variant="screen", device=None,
                  rank=0, world=1, group=None, grid_ctas=0, ladder="fused", pair_cap=None, cand_cap=None,
-                 pipeline_upload=True, screen_mode=None):
+                 pipeline_upload=True, screen_mode=None, screen_frame=True):
         torch = require_cuda()
         self.torch = torch
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -133,6 +137,7 @@ class RmsdPruner:
         self.grid_ctas = int(grid_ctas)
         self.pace = 0                     # tsc_rmsd_screen's MMA spacing (measurement aid: tools/screen_check.py)
         self.screen_mode = screen_mode    # form of the default screen: None = chosen from the molecule's shape (below)
+        self.frame = None                 # 12 float64 (Q, t) given to tsc_pack_screen / tsc_rmsd_screen; None = identity
         if ladder not in ("fused", "bitrows"):
             raise ValueError("ladder must be 'fused' or 'bitrows'")
         self.ladder = ladder
@@ -169,11 +174,14 @@ class RmsdPruner:
         self.nb_pad = _host.num_blocks_padded(N)
         self.W = self.nb_pad
         if self.variant == 5 and N and M:
+            # principal-axes frame and column weights of the first structure (rmsd_screen.cu, ScFrame), and from its
+            # shape the form of the screen (_host.screen_mode_for).  Speed decisions: every choice is conservative.
+            first = (src[0] if not src.is_cuda else src[0].cpu()).numpy()[heavy]
+            self.frame, ratio = _host.screen_frame(first)
+            if not screen_frame:
+                self.frame = None                            # (comparison runs: plain Samuelson in the frame as given)
             if self.screen_mode is None:
-                # isotropic molecule -> Samuelson-only form on 64-wide tiles, otherwise the quartic test for every
-                # pair (_host.screen_mode_for: a speed decision, every form is conservative)
-                first = (src[0] if not src.is_cuda else src[0].cpu()).numpy()[heavy]
-                self.screen_mode = _host.screen_mode_for(first)
+                self.screen_mode = 0 if ratio <= 1.03 else (1 if screen_frame else 2)
             self.tile_j = {0: 48, 3: 64}.get(self.screen_mode, 32)
             if M > int(lib().tsc_screen_max_atoms(self.tile_j)) and self.screen_mode in (0, 3):
                 self.screen_mode, self.tile_j = 1, 32        # too many atoms for the wide tiles: Samuelson, then quartic
@@ -294,8 +302,11 @@ class RmsdPruner:
             if self.variant == 5:
                 check(L.tsc_pack_screen(ptr(self.S), self.N, self.A, ptr(self.heavy_idx), self.M, ptr(self.PA),
                                         ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG), ptr(self.CT), 0, 0,
-                                        self.tile_j, stream_ptr()), "tsc_pack_screen")
+                                        self.tile_j, self._frame_ptr(), stream_ptr()), "tsc_pack_screen")
         self.packed_ready = True
+
+    def _frame_ptr(self):
+        return None if self.frame is None else self.frame.ctypes.data
 
     def screen(self):
         """All-pairs contraction + closed-form screen (the hot kernel)."""
@@ -312,7 +323,7 @@ class RmsdPruner:
                 check(L.tsc_rmsd_screen(ptr(self.PA), ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG),
                                         ptr(self.CT), self.N, self.M, ptr(self.items), self.n_items, self.thr,
                                         ptr(self.sim_bits), ptr(self.cand_list), self.cand_stride, self.grid_ctas,
-                                        self.screen_mode, self.pace, stream_ptr()), "tsc_rmsd_screen")
+                                        self.screen_mode, self.pace, self._frame_ptr(), stream_ptr()), "tsc_rmsd_screen")
             else:
                 check(L.tsc_rmsd_sim_tiles(ptr(self.packed), ptr(self.G), self.N, self.M, ptr(self.tiles),
                                            self.n_tiles, self.thr, ptr(self.sim_bits), self.variant, self.grid_ctas,
@@ -548,13 +559,13 @@ class RmsdPruner:
                                         lo // 32, self.nb_pad if c == n_chunks - 1 else hi // 32, st), "tsc_pack_blocks")
                 check(L.tsc_pack_screen(ptr(self.S), N, self.A, ptr(self.heavy_idx), self.M, ptr(self.PA), ptr(self.PB),
                                         ptr(self.PR), ptr(self.G), ptr(self.sG), ptr(self.CT), lo, hi_pad,
-                                        self.tile_j, st), "tsc_pack_screen")
+                                        self.tile_j, self._frame_ptr(), st), "tsc_pack_screen")
                 it_dev, n_it = chunk_items[c]
                 if n_it:
                     check(L.tsc_rmsd_screen(ptr(self.PA), ptr(self.PB), ptr(self.PR), ptr(self.G), ptr(self.sG),
                                             ptr(self.CT), N, self.M, ptr(it_dev), n_it, self.thr, ptr(self.sim_bits),
                                             ptr(self.cand_list), self.cand_stride, self.grid_ctas, self.screen_mode,
-                                            self.pace, st), "tsc_rmsd_screen")
+                                            self.pace, self._frame_ptr(), st), "tsc_rmsd_screen")
         self.packed_ready = True
 
     def row_slice(self):
