@@ -96,6 +96,15 @@ int tsc_rmsd_screen(const void* PA, const void* PB, const void* PR, const double
  *   molecules as Samuelson's is for isotropic ones (rmsd_screen.cu, ScFrame).  NULL = identity = Samuelson.  The same
  *   frame must be given to tsc_pack_screen and tsc_rmsd_screen; both return cudaErrorInvalidValue (1) when Q is not
  *   orthogonal to 1e-13 or the scales violate the inequality — the conditions exclusion rests on. */
+/* Host-side plan of the screen (capi.cu; no GPU involved): tsc_host_sample_pairs fills K fixed pseudo-random pairs
+ * i != j of [0, N); tsc_host_screen_plan takes the frame from structure `first` of the HOST array S (rows, A, 3) and
+ * reports, for the pairs (pi[k], pj[k]) (row numbers of S), the fraction the weighted bound would leave undecided, and
+ * the looseness `ratio` of the unweighted bound for that shape (1 = isotropic).  _host.screen_plan turns the two
+ * numbers into the mode given to tsc_rmsd_screen.  Speed decisions only. */
+void tsc_host_sample_pairs(int64_t N, int32_t K, int64_t* pi, int64_t* pj);
+int tsc_host_screen_plan(const double* S, int32_t A, const int32_t* heavy_idx, int32_t M, int64_t first,
+                         const int64_t* pi, const int64_t* pj, int32_t K, double thr, double* frame12, double* ratio,
+                         double* undecided);
 /*   cand_list (may be NULL): block of cand_stride int32 pairs, element 0 = header whose first int32 is the running
  *   count (zero it first); (local row, j) of every bit the screen sets is appended from element 1; a count outside
  *   [0, cand_stride - 1] means the list overflowed (tsc_rmsd_verify then scans the bit rows instead). */

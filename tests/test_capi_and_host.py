@@ -359,3 +359,31 @@ def test_library_rejects_a_frame_that_would_break_the_bound():
         assert L.tsc_pack_screen(None, 10, 4, None, 4, None, None, None, None, None, None, 0, 0, 32, fr.ctypes.data, None) == 1
         assert L.tsc_rmsd_screen(None, None, None, None, None, None, 10, 4, None, 1, 0.5, None, None, 0, 0, 0, 0,
                                  fr.ctypes.data, None) == 1
+
+
+def test_native_screen_plan_agrees_with_its_numpy_statement():
+    """capi.cu: tsc_host_screen_plan against _host.screen_plan (numpy) — same undecided fraction, same mode, and a
+    frame the library accepts; the sampled pairs are the same on every call and never pair a structure with itself."""
+    from tscode_b200.synth import gen_ensemble
+    rng = np.random.default_rng(1)
+    for scale, M, N in ((3.0, 80, 3000), (np.array([6.0, 2.0, 1.0]), 80, 3000), (np.array([4.0, 4.0, 0.5]), 30, 2000),
+                        (3.0, 12, 500)):
+        S = gen_ensemble(5, N, M, max(2, N // 10), scale=scale)
+        A = M + 3
+        full = np.zeros((N, A, 3))
+        heavy = np.sort(rng.choice(A, size=M, replace=False)).astype(np.int32)
+        full[:, heavy] = S
+        full[:, np.setdiff1d(np.arange(A), heavy)] = rng.normal(size=(N, A - M, 3)) * 50.0     # "hydrogens": ignored
+        pi, pj = _host.sample_pair_indices(N)
+        pi2, pj2 = _host.sample_pair_indices(N)
+        assert np.array_equal(pi, pi2) and np.array_equal(pj, pj2) and (pi != pj).all()
+        assert pi.min() >= 0 and pj.min() >= 0 and pi.max() < N and pj.max() < N and pi.size == _host.SAMPLE_PAIRS
+        fr, mode, und = _host.screen_plan_native(full, heavy, 0.5, 0, pi, pj)
+        fr2, mode2, und2 = _host.screen_plan(S[0], S[pi], S[pj], 0.5)
+        assert mode == mode2 and abs(und - und2) < 1e-12, (mode, mode2, und, und2)
+        Q, t = fr[:9].reshape(3, 3), fr[9:]
+        assert np.abs(Q @ Q.T - np.eye(3)).max() <= 1e-13 and (1.0 / (3.0 * t * t)).sum() <= 1.0
+        assert np.allclose(np.sort(t), np.sort(fr2[9:]), rtol=1e-9)
+    assert _host.sample_pair_indices(1)[0].size == 0
+    assert _host.plan_mode(1.0, 0.0) == 0 and _host.plan_mode(1.5, 0.0) == 1 and _host.plan_mode(1.0, 0.02) == 1
+    assert _host.plan_mode(1.0, 0.5) == 2

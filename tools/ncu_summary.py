@@ -50,6 +50,10 @@ def main():
                 if key.startswith("dram__bytes"):
                     scale = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(u, 1.0)
                     cells.append(f"{f * scale:.2f} MB")
+                elif key == "gpu__time_duration.sum":
+                    scale = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "nsecond": 1e-3,
+                             "s": 1e6, "second": 1e6}.get(u, 1.0)
+                    cells.append(f"{f * scale:.1f}")
                 elif key == "smsp__inst_executed.sum":
                     cells.append(f"{f / 1e6:.1f} M")
                 elif key == "launch__registers_per_thread":

@@ -83,13 +83,78 @@ def screen_frame(first_heavy: np.ndarray):
 
 
 def screen_mode_for(first_heavy: np.ndarray) -> int:
-    """Which form of the default screen suits an ensemble (rmsd_screen.cu; a speed decision only: every form is
-    conservative).  In the frame of screen_frame the weighted Samuelson bound is sharp for similar conformers of any
-    shape; what decides is how often it fails for DISsimilar pairs, which the first structure alone cannot tell.  Near-
-    isotropic molecules (unweighted looseness <= 1.03) take the cheapest form, mode 0: the bound only, on 48-wide
-    tiles; everything else mode 1: the bound, then the FP32 quartic sign test for the groups of 64 pairs in which it
-    left a pair undecided."""
+    """Form of the default screen from the shape of the first structure alone (rmsd_screen.cu; a speed decision only:
+    every form is conservative): near-isotropic molecules (looseness of the unweighted Samuelson bound <= 1.03) take the
+    cheapest form, mode 0: the bound only, on 48-wide tiles; everything else mode 1: the bound in the frame of
+    screen_frame, then the FP32 quartic sign test for the groups of 64 pairs in which it left a pair undecided.
+    screen_plan refines this with a sample of pairs."""
     return 0 if screen_frame(first_heavy)[1] <= 1.03 else 1
+
+
+SAMPLE_PAIRS = 128
+
+
+def plan_mode(ratio: float, undecided: float) -> int:
+    """The rule of screen_plan: sample fraction u of pairs the weighted bound leaves undecided, looseness `ratio` of the
+    unweighted bound for the first structure's shape -> form of the screen."""
+    if undecided <= 0.005 and ratio <= 1.03:
+        return 0
+    return 1 if undecided <= 0.03 else 2
+
+
+def sample_pair_indices(N: int, k: int = SAMPLE_PAIRS):
+    """Fixed pseudo-random pairs (i != j) for screen_plan: the same on every rank and every call
+    (capi.cu: tsc_host_sample_pairs)."""
+    from ._lib import lib
+    k = int(k) if N >= 2 else 0
+    pi, pj = np.empty(k, np.int64), np.empty(k, np.int64)
+    if k:
+        lib().tsc_host_sample_pairs(int(N), k, pi.ctypes.data, pj.ctypes.data)
+    return pi, pj
+
+
+def screen_plan_native(S: np.ndarray, heavy_idx: np.ndarray, thr: float, first: int, pi: np.ndarray, pj: np.ndarray):
+    """(frame, mode, undecided fraction) like screen_plan, computed by the library's host code on the caller's array S
+    (rows, A, 3) float64 C-contiguous without copying it (capi.cu: tsc_host_screen_plan; ~0.1 ms against ~2 ms of
+    numpy: it is on the latency path of every prune call)."""
+    from ._lib import lib
+    assert S.dtype == np.float64 and S.flags.c_contiguous and S.ndim == 3 and S.shape[2] == 3
+    h = np.ascontiguousarray(heavy_idx, dtype=np.int32)
+    pi = np.ascontiguousarray(pi, dtype=np.int64)
+    pj = np.ascontiguousarray(pj, dtype=np.int64)
+    frame, out = np.empty(12), np.empty(2)
+    rc = lib().tsc_host_screen_plan(S.ctypes.data, int(S.shape[1]), h.ctypes.data, int(h.size), int(first),
+                                    pi.ctypes.data, pj.ctypes.data, int(pi.size), float(thr), frame.ctypes.data,
+                                    out[0:].ctypes.data, out[1:].ctypes.data)
+    if rc != 0:
+        raise ValueError("tsc_host_screen_plan: bad arguments")
+    return frame, plan_mode(float(out[0]), float(out[1])), float(out[1])
+
+
+def screen_plan(first_heavy: np.ndarray, P: np.ndarray, Qs: np.ndarray, thr: float):
+    """(frame, mode, undecided fraction): screen_frame plus a look at a sample of pairs (P[k], Qs[k]) (heavy atoms, as
+    given).  How often the weighted bound fails to exclude a pair depends on the ENSEMBLE, not on the first structure:
+    conformers of one molecule are excluded almost always (then the bound alone, mode 0, or the bound with the
+    quartic as a backstop, mode 1, is fastest), but e.g. embedded poses of several fragments in many arrangements are
+    not, and a failed bound costs a group of 64 pairs the quartic on top (mode 2, the quartic for every pair, is
+    then cheaper).  Sample fraction u of pairs the bound leaves undecided (similar pairs included):
+        u <= 0.5 % and near-isotropic shape -> 0;   u <= 3 % -> 1;   else 2      (plan_mode)
+    A speed decision only.  (numpy statement of screen_plan_native, which is what the product calls.)"""
+    frame, ratio = screen_frame(first_heavy)
+    P = np.asarray(P, dtype=np.float64)
+    Qs = np.asarray(Qs, dtype=np.float64)
+    if P.shape[0] == 0:
+        return frame, plan_mode(ratio, 0.0), 0.0
+    Q, t = frame[:9].reshape(3, 3), frame[9:]
+    M = P.shape[1]
+    C = np.einsum("kma,kmb->kab", P, Qs)                      # plain covariances
+    Sw = np.einsum("xa,kab,yb->kxy", Q, C, Q) * t             # in the frame, columns scaled
+    f = (Sw ** 2).sum((1, 2))
+    Gi, Gj = (P ** 2).sum((1, 2)), (Qs ** 2).sum((1, 2))
+    Gw = (((Qs @ Q.T) * t) ** 2).sum((1, 2))                  # squared norm of the scaled column conformer
+    lf = 0.5 * (Gi + Gj) - 0.5 * M * thr * thr - np.sqrt(3.0) * 1.05e-3 * np.sqrt(Gi * np.maximum(Gw, Gj))
+    und = float(np.mean(~((lf > 0) & (3.00004 * f < lf * lf))))
+    return frame, plan_mode(ratio, und), und
 
 
 def build_items_balanced(N: int, row_blocks: np.ndarray, n_ctas: int, panel_lo: int = 0,

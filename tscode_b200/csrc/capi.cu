@@ -159,3 +159,136 @@ extern "C" int64_t tsc_host_write_xyz(const double* coords, int64_t n_frames, in
     }
     return total;
 }
+
+// ------------------------------------------------------------------------------------------
+// Host-side plan of the default screen (rmsd_screen.cu, ScFrame): principal-axes frame and column weights from the
+// first structure, and — from a fixed pseudo-random sample of pairs — how often the weighted Samuelson bound would
+// leave a pair undecided, which is what decides between the screen's forms (_host.screen_plan states the rule).
+// Native because it sits on the latency path of every prune call (numpy: ~2 ms; this: ~0.1 ms).  A speed device only.
+// ------------------------------------------------------------------------------------------
+namespace {
+// eigen-decomposition of a symmetric 3x3 matrix by cyclic Jacobi: a -> diagonal, v rows = eigenvectors
+void jacobi3(double a[3][3], double v[3][3]) {
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) v[i][j] = i == j ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 30; sweep++) {
+        const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+        if (off <= 1e-300 || off <= 1e-17 * (fabs(a[0][0]) + fabs(a[1][1]) + fabs(a[2][2]))) break;
+        for (int p = 0; p < 2; p++)
+            for (int q = p + 1; q < 3; q++) {
+                if (a[p][q] == 0.0) continue;
+                const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 3; k++) {                 // A <- A J
+                    const double akp = a[k][p], akq = a[k][q];
+                    a[k][p] = c * akp - s * akq;
+                    a[k][q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < 3; k++) {                 // A <- J^T A
+                    const double apk = a[p][k], aqk = a[q][k];
+                    a[p][k] = c * apk - s * aqk;
+                    a[q][k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; k++) {                 // rows of v = eigenvectors
+                    const double vpk = v[p][k], vqk = v[q][k];
+                    v[p][k] = c * vpk - s * vqk;
+                    v[q][k] = s * vpk + c * vqk;
+                }
+            }
+    }
+}
+}  // namespace
+
+// pi, pj (K): fixed pseudo-random pairs i != j of [0, N) (splitmix64 of the pair number: the same on every rank)
+extern "C" void tsc_host_sample_pairs(int64_t N, int32_t K, int64_t* pi, int64_t* pj) {
+    for (int32_t k = 0; k < K; k++) {
+        uint64_t z = 0x9E3779B97F4A7C15ull * (uint64_t)(2 * k + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+        uint64_t y = 0x9E3779B97F4A7C15ull * (uint64_t)(2 * k + 2);
+        y = (y ^ (y >> 30)) * 0xBF58476D1CE4E5B9ull; y = (y ^ (y >> 27)) * 0x94D049BB133111EBull; y ^= y >> 31;
+        const int64_t i = N > 0 ? (int64_t)(z % (uint64_t)N) : 0;
+        const int64_t j = N > 1 ? (i + 1 + (int64_t)(y % (uint64_t)(N - 1))) % N : 0;
+        pi[k] = i; pj[k] = j;
+    }
+}
+
+// S: host array (rows, A, 3); `first` = row of the structure the frame is taken from; pairs (pi[k], pj[k]) index rows
+// of S.  Out: frame12 (Q row-major, t), ratio = looseness of the unweighted bound for the first structure's shape,
+// undecided = fraction of the sampled pairs the weighted bound does not exclude.  Returns 0, or 1 for bad arguments.
+extern "C" int tsc_host_screen_plan(const double* S, int32_t A, const int32_t* heavy_idx, int32_t M, int64_t first,
+                                    const int64_t* pi, const int64_t* pj, int32_t K, double thr, double* frame12,
+                                    double* ratio, double* undecided) {
+    if (!S || !heavy_idx || !frame12 || !ratio || !undecided || M <= 0) return 1;
+    for (int k = 0; k < 12; k++) frame12[k] = (k < 9) ? (k % 4 == 0 ? 1.0 : 0.0) : 1.0;
+    *ratio = INFINITY;
+    *undecided = 0.0;
+    double Q[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, t[3] = {1, 1, 1};
+    {
+        const double* x = S + first * (int64_t)A * 3;
+        double a[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, v[3][3];
+        bool finite = true;
+        for (int m = 0; m < M; m++) {
+            const double* c = x + (int64_t)heavy_idx[m] * 3;
+            for (int p = 0; p < 3; p++) {
+                finite = finite && isfinite(c[p]);
+                for (int q = 0; q < 3; q++) a[p][q] += c[p] * c[q];
+            }
+        }
+        double l0[3] = {a[0][0], a[1][1], a[2][2]};
+        const double tot0 = l0[0] + l0[1] + l0[2];
+        if (finite && isfinite(tot0) && tot0 > 0.0) {
+            jacobi3(a, v);
+            double lam[3] = {a[0][0], a[1][1], a[2][2]};
+            const double tot = lam[0] + lam[1] + lam[2];
+            *ratio = sqrt(3.0 * (lam[0] * lam[0] + lam[1] * lam[1] + lam[2] * lam[2])) / tot;
+            if (*ratio > 1.0005) {
+                double w[3], lsum = 0.0;
+                for (int b = 0; b < 3; b++) { lam[b] = lam[b] > 1e-4 * tot ? lam[b] : 1e-4 * tot; lsum += lam[b]; }
+                for (int b = 0; b < 3; b++) w[b] = lsum / lam[b] * (1.0 + 1e-9);
+                for (int rep = 0; rep < 2; rep++) {           // Gram-Schmidt to the library's 1e-13
+                    for (int r = 0; r < 3; r++) {
+                        for (int p = 0; p < r; p++) {
+                            const double d = v[r][0] * v[p][0] + v[r][1] * v[p][1] + v[r][2] * v[p][2];
+                            for (int k = 0; k < 3; k++) v[r][k] -= d * v[p][k];
+                        }
+                        const double n = sqrt(v[r][0] * v[r][0] + v[r][1] * v[r][1] + v[r][2] * v[r][2]);
+                        for (int k = 0; k < 3; k++) v[r][k] /= n;
+                    }
+                }
+                for (int r = 0; r < 3; r++) {
+                    for (int k = 0; k < 3; k++) { Q[r][k] = v[r][k]; frame12[3 * r + k] = v[r][k]; }
+                    t[r] = sqrt(w[r] / 3.0);
+                    frame12[9 + r] = t[r];
+                }
+            }
+        }
+    }
+    int und = 0;
+    for (int32_t k = 0; k < K; k++) {
+        const double* p = S + pi[k] * (int64_t)A * 3;
+        const double* q = S + pj[k] * (int64_t)A * 3;
+        double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, gi = 0.0, gj = 0.0, gw = 0.0;
+        for (int m = 0; m < M; m++) {
+            const double* a = p + (int64_t)heavy_idx[m] * 3;
+            const double* b = q + (int64_t)heavy_idx[m] * 3;
+            double ar[3], br[3];
+            for (int r = 0; r < 3; r++) {
+                ar[r] = Q[r][0] * a[0] + Q[r][1] * a[1] + Q[r][2] * a[2];
+                br[r] = t[r] * (Q[r][0] * b[0] + Q[r][1] * b[1] + Q[r][2] * b[2]);
+            }
+            gi += a[0] * a[0] + a[1] * a[1] + a[2] * a[2];
+            gj += b[0] * b[0] + b[1] * b[1] + b[2] * b[2];
+            gw += br[0] * br[0] + br[1] * br[1] + br[2] * br[2];
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) C[r][c] += ar[r] * br[c];
+        }
+        double f = 0.0;
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) f += C[r][c] * C[r][c];
+        const double lf = 0.5 * (gi + gj) - 0.5 * M * thr * thr - 1.7320508075688772 * 1.05e-3 * sqrt(gi * (gw > gj ? gw : gj));
+        und += !(lf > 0.0 && 3.00004 * f < lf * lf);
+    }
+    *undecided = K > 0 ? (double)und / K : 0.0;
+    return 0;
+}

@@ -176,12 +176,21 @@ class RmsdPruner:
         if self.variant == 5 and N and M:
             # principal-axes frame and column weights of the first structure (rmsd_screen.cu, ScFrame), and from its
             # shape the form of the screen (_host.screen_mode_for).  Speed decisions: every choice is conservative.
-            first = (src[0] if not src.is_cuda else src[0].cpu()).numpy()[heavy]
-            self.frame, ratio = _host.screen_frame(first)
-            if not screen_frame:
-                self.frame = None                            # (comparison runs: plain Samuelson in the frame as given)
+            si, sj = _host.sample_pair_indices(N)
+            h32 = heavy.astype(np.int32)
+            if not src.is_cuda and src.dtype == torch.float64 and src.is_contiguous():
+                plan = _host.screen_plan_native(src.numpy(), h32, self.thr, 0, si, sj)      # on the caller's memory
+            else:
+                rows = torch.from_numpy(np.concatenate([[0], si, sj]).astype(np.int64))
+                smp = src.index_select(0, rows.to(src.device)).to("cpu", torch.float64).contiguous().numpy()
+                k = np.arange(si.size, dtype=np.int64)
+                plan = _host.screen_plan_native(smp, h32, self.thr, 0, 1 + k, 1 + si.size + k)
+            self.frame, mode, self.sample_undecided = plan
+            if not screen_frame:                             # (comparison runs: plain Samuelson in the frame as given)
+                ratio = _host.screen_frame((src[0].cpu() if src.is_cuda else src[0]).numpy()[heavy])[1]
+                self.frame, mode = None, (0 if ratio <= 1.03 else 2)
             if self.screen_mode is None:
-                self.screen_mode = 0 if ratio <= 1.03 else (1 if screen_frame else 2)
+                self.screen_mode = mode
             self.tile_j = {0: 48, 3: 64}.get(self.screen_mode, 32)
             if M > int(lib().tsc_screen_max_atoms(self.tile_j)) and self.screen_mode in (0, 3):
                 self.screen_mode, self.tile_j = 1, 32        # too many atoms for the wide tiles: Samuelson, then quartic
