@@ -44,7 +44,7 @@ def test_install_rebinds_every_importer():
         assert emb.get_embed is numba_functions.get_embed
         assert emb.compenetration_check is numba_functions.compenetration_check       # `from ... import` binding
         assert emb._rmsd_similarity is rmsd_pruning._rmsd_similarity
-        assert tm.prune_conformers_rmsd_rot_corr is torsion_module.prune_conformers_rmsd_rot_corr
+        assert tm.prune_conformers_rmsd_rot_corr is install.prune_conformers_rmsd_rot_corr   # GPU path + own fallback
         assert ("tscode.embeds", "compenetration_check") in patched
         import tscode.optimization_methods as om
         import tscode.operators as ops
@@ -135,3 +135,32 @@ def test_batched_loop_patches_equal_the_reference_methods(monkeypatch):
             assert np.array_equal(a2.structures, b2.structures) and a2.lines == b2.lines
             assert np.array_equal(a2.energies, b2.energies) and len(a2.structures) > 0
 
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="reference tree not present")
+def test_rot_corr_with_too_many_rotors_goes_to_the_reference(monkeypatch):
+    """a patched entry point must not raise where the reference worked.  More symmetric rotors than the
+    kernels' 64-bit code holds (torsion_module.MAX_T) -> UnsupportedRotors -> the saved original is called with the
+    reference's own signature."""
+    ref_harness.install(full=True)
+    import tscode.torsion_module as tm
+    from tscode_b200 import install, torsion_module
+    calls = []
+
+    def fake_reference(structures, atomnos, graph, max_rmsd=0.25, verbose=False, logfunction=None):
+        calls.append((len(structures), max_rmsd, verbose))
+        return structures, np.ones(len(structures), dtype=bool)
+
+    def gpu_path(*a, **k):
+        raise torsion_module.UnsupportedRotors("21 rotors")
+
+    monkeypatch.setattr(tm, "prune_conformers_rmsd_rot_corr", fake_reference)
+    install.install_into()
+    try:
+        monkeypatch.setattr(torsion_module, "prune_conformers_rmsd_rot_corr", gpu_path)
+        S = np.zeros((3, 4, 3))
+        out, mask = tm.prune_conformers_rmsd_rot_corr(S, np.full(4, 6), None, max_rmsd=0.3, verbose=True)
+        assert calls == [(3, 0.3, True)] and mask.all() and out is S
+    finally:
+        install.uninstall()
+    assert issubclass(torsion_module.UnsupportedRotors, ValueError)

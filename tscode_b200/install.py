@@ -47,9 +47,25 @@ _PATCHES = {
         "prune_by_moment_of_inertia": _om.prune_by_moment_of_inertia,
     },
     "tscode.torsion_module": {
-        "prune_conformers_rmsd_rot_corr": _tm.prune_conformers_rmsd_rot_corr,
+        "prune_conformers_rmsd_rot_corr": None,          # filled in below: GPU path with the reference as its own fallback
     },
 }
+_reference_rot_corr = []                                  # the original, saved by install_into
+
+
+def prune_conformers_rmsd_rot_corr(structures, atomnos, graph, max_rmsd=0.25, verbose=False, logfunction=None, **kw):
+    """tscode_b200.torsion_module.prune_conformers_rmsd_rot_corr; a molecule with more symmetric rotors (or rotor
+    angles) than the kernels' 64-bit code holds (torsion_module.MAX_T / MAX_ANG) is handed to the reference's own
+    function instead of raising from a patched entry point."""
+    try:
+        return _tm.prune_conformers_rmsd_rot_corr(structures, atomnos, graph, max_rmsd, verbose, logfunction, **kw)
+    except _tm.UnsupportedRotors:
+        if not _reference_rot_corr:
+            raise
+        return _reference_rot_corr[0](structures, atomnos, graph, max_rmsd=max_rmsd, verbose=verbose, logfunction=logfunction)
+
+
+_PATCHES["tscode.torsion_module"]["prune_conformers_rmsd_rot_corr"] = prune_conformers_rmsd_rot_corr
 _SCALAR_PATCHES = {
     "tscode.rmsd_pruning": {
         "rmsd_and_max_numba": _rp.rmsd_and_max_numba,
@@ -152,6 +168,8 @@ def install_into(tscode_pkg=None, strict: bool = False, scalars: bool = False, l
             for name, repl in names.items():
                 if hasattr(mod, name):
                     originals[name] = getattr(mod, name)
+                    if name == "prune_conformers_rmsd_rot_corr" and not _reference_rot_corr:
+                        _reference_rot_corr.append(originals[name])
                     _saved.append((mod, name, originals[name]))
                     setattr(mod, name, repl)
                     patched.append((modname, name))
@@ -189,6 +207,7 @@ def install_into(tscode_pkg=None, strict: bool = False, scalars: bool = False, l
 
 
 def uninstall():
+    del _reference_rot_corr[:]
     while _saved:
         mod, name, orig = _saved.pop()
         setattr(mod, name, orig)

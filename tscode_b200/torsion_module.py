@@ -34,6 +34,11 @@ from . import _host
 from ._lib import check, lib, ptr, require_cuda, stream_ptr
 
 MAX_T, MAX_ANG = 20, 6          # rotcorr.cu: 3 bits of best-angle code per rotor in a 64-bit word
+
+
+class UnsupportedRotors(ValueError):
+    """More symmetric rotors (or angles per rotor) than the kernels' 64-bit code holds; install.py's wrapper hands such a
+    call back to the reference's own function."""
 _SYMBOLS = ("X H He Li Be B C N O F Ne Na Mg Al Si P S Cl Ar K Ca Sc Ti V Cr Mn Fe Co Ni Cu Zn Ga Ge As Se Br Kr "
             "Rb Sr Y Zr Nb Mo Tc Ru Rh Pd Ag Cd In Sn Sb Te I Xe").split()
 
@@ -102,7 +107,7 @@ class RotCorrPruner:
         self.info, self.max_rmsd = info, float(max_rmsd)
         T = info.T
         if T > MAX_T or any(len(a) > MAX_ANG for a in info.angles):
-            raise ValueError(f"at most {MAX_T} rotors with {MAX_ANG} angles each are supported")
+            raise UnsupportedRotors(f"at most {MAX_T} rotors with {MAX_ANG} angles each are supported")
         self.Sc = torch.from_numpy(Sc).to(dev)
         atomnos = np.asarray(atomnos)
         self.heavy = torch.from_numpy((atomnos != 1).astype(np.uint8)).to(dev)
