@@ -14,8 +14,13 @@ sys.path.insert(0, ROOT)
 from oracle import oracle_c  # noqa: E402
 from tscode_b200.synth import gen_ensemble, mask_digest  # noqa: E402
 
-out = {}
-for w in (2, 4, 8):
+# usage: python oracle/gen_weak_digests.py [worlds, default "2 4 8"]; entries already in the file are kept
+path = os.path.join(ROOT, "tests", "golden", "prune_masks_weak.json")
+out = json.load(open(path)) if os.path.exists(path) else {}
+worlds = [int(x) for x in sys.argv[1:]] or [2, 4, 8]
+for w in worlds:
+    if str(w) in out:
+        continue
     N = int(50000 * math.sqrt(w) / 128) * 128
     S = gen_ensemble(3, N, 80, N // 10)
     t0 = time.perf_counter()
@@ -23,4 +28,4 @@ for w in (2, 4, 8):
     out[str(w)] = dict(world=w, N=N, M=80, n_clusters=N // 10, seed=3, thr=0.5, survivors=int(m.sum()), digest=mask_digest(m),
                        pairs_evaluated=int(ne), wall_s=round(time.perf_counter() - t0, 1), source="oracle/oracle.c (C port)")
     print(out[str(w)], flush=True)
-    json.dump(out, open(os.path.join(ROOT, "tests", "golden", "prune_masks_weak.json"), "w"), indent=1)
+    json.dump(out, open(path, "w"), indent=1)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Probe of the default screen (rmsd_screen.cu; run under `timeout`): on small ensembles of several shapes the
 candidate bits must be a superset of the oracle's similar pairs and the final bits / mask must match; then timing on
-BASELINE configs[2] and on its elongated / planar variants, next to the first-generation kernel ("f16")."""
+BASELINE configs[2] and on its elongated / planar variants, next to the FP64 tensor-core variant ("dmma")."""
 import os
 import sys
 
@@ -13,7 +13,7 @@ from oracle import oracle_c  # noqa: E402
 from tscode_b200.rmsd_pruning import RmsdPruner  # noqa: E402
 from tscode_b200.synth import gen_ensemble, mask_digest  # noqa: E402
 
-variants = sys.argv[1].split(",") if len(sys.argv) > 1 else ["screen", "f16"]
+variants = sys.argv[1].split(",") if len(sys.argv) > 1 else ["screen"]
 big = "--no-big" not in sys.argv
 def _arg(name, default):
     return [int(x) if x != "auto" else None for x in sys.argv[sys.argv.index(name) + 1].split(",")] if name in sys.argv else default
