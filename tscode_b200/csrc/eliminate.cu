@@ -517,6 +517,9 @@ extern "C" int tsc_elim_fused(const int32_t* lists, int32_t n_lists, int64_t str
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#ifdef TSC_EF_GRID
+    sms = TSC_EF_GRID;                                           // measurement builds (tools/probes): grid-size sweep
+#endif
     void* args[] = {(void*)&p};
     e = cudaLaunchCooperativeKernel((const void*)elim_fused_kernel, dim3(sms), dim3(EF_THREADS), args, smem, st);
     return (int)e;

@@ -322,8 +322,13 @@ __global__ void __launch_bounds__(VF_WARPS * 32) rmsd_verify_list_kernel(
     const int grp = lane >> 2, sub = lane & 3;
     const double thr2 = 2.0 * thr;
     unsigned long long n_cand = 0, n_ok = 0, n_near = 0, n_deg = 0;
-    for (int64_t b0 = gwarp * 32; b0 < n; b0 += nwarps * 32) {
-        const int count = (int)((n - b0 < 32) ? n - b0 : 32);
+    // candidates per warp and step: 32 (one eigen-solve per lane) when the list keeps every warp busy; with a short list
+    // (several ranks: 1/world of the candidates each) fewer, in multiples of the 8 a pass handles, so that the work
+    // spreads over all warps instead of queueing three passes + solve + three passes behind each other in a few
+    const int64_t per_warp = (n + nwarps - 1) / nwarps;
+    const int bs = per_warp >= 32 ? 32 : (int)((per_warp + 7) & ~int64_t(7));
+    for (int64_t b0 = gwarp * bs; b0 < n; b0 += nwarps * bs) {
+        const int count = (int)((n - b0 < bs) ? n - b0 : bs);
         int32_t lrow = 0, j = 0, i = 0;
         if (lane < count) {
             const int2 e = cand[1 + b0 + lane];
@@ -409,6 +414,194 @@ __global__ void __launch_bounds__(VF_WARPS * 32) rmsd_verify_list_kernel(
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// The same verification with COALESCED loads (default).  ncu on the kernel above (profiles/r02_ncu_kernels.md): L1/TEX
+// throughput 89 %, FP64 pipe 16 % — every lane of a load instruction reads its own 160-byte run, 32 different cache
+// lines per instruction, and the L1 processes one line per cycle: 2 x 240 line-cycles per candidate, which is exactly
+// the 0.45 ms the kernel takes on C3.  Here the 32 lanes of a warp walk ONE candidate's atoms together (lane = atom:
+// the x / y / z runs of a 20-atom slab are contiguous in the packed layout, so a load instruction touches 2-3 lines),
+// the nine covariance sums are reduced with a halving butterfly (lanes exchange the half of the values they do not
+// keep: 4 + 2 + 1 + 2 shuffles for eight values instead of 8 x 5) and parked in shared memory for lane k, the
+// eigen-solves still run one per lane for the whole batch.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double shfl_xor_d(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+
+// R = ceil(M / 32) rounds of the atom loop as a compile-time constant (1..4; 0 = any M, rolled loop): with the rounds
+// unrolled all 6 R loads of a candidate are issued before the first use, one L2 round trip per candidate and phase
+// instead of R.
+template <int R>
+__global__ void __launch_bounds__(VF_WARPS * 32) rmsd_verify_list_coop_kernel(
+    const double* __restrict__ packed, int64_t N, int M, int64_t nb_pad, const int32_t* __restrict__ row_blocks,
+    double thr, uint32_t* sim_bits, int64_t W, unsigned long long* stats, const int2* __restrict__ cand,
+    int64_t cand_stride, int2* pair_list, int64_t pair_stride) {
+    const int64_t n = cand[0].x;
+    if (n <= 0 || n > cand_stride - 1) return;
+    __shared__ double s_cov[VF_WARPS][32][9];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const double thr2 = 2.0 * thr;
+    const int64_t comp = (int64_t)CB * KS, slab_stride = nb_pad * 3 * comp;
+    unsigned long long n_cand = 0, n_ok = 0, n_near = 0, n_deg = 0;
+    const int64_t per_warp = (n + nwarps - 1) / nwarps;
+    const int bs = per_warp >= 32 ? 32 : (int)per_warp;           // short list: spread it over all warps
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    int64_t offs[R > 0 ? R : 1];                                  // this lane's atom of every round inside a conformer
+#pragma unroll
+    for (int r = 0; r < (R > 0 ? R : 1); r++) {
+        const int m = lane + 32 * r;
+        offs[r] = (int64_t)(m / KS) * slab_stride + (m % KS);
+    }
+    for (int64_t b0 = gwarp * bs; b0 < n; b0 += nwarps * bs) {
+        const int count = (int)((n - b0 < bs) ? n - b0 : bs);
+        int32_t lrow = 0, j = 0, i = 0;
+        int64_t oi = 0, oj = 0;                                   // offset of the conformer inside a slab image
+        if (lane < count) {
+            const int2 e = cand[1 + b0 + lane];
+            lrow = e.x; j = e.y;
+            i = row_blocks[lrow / CB] * CB + (lrow % CB);
+            oi = (int64_t)(i / CB) * 3 * comp + (int64_t)(i % CB) * KS;
+            oj = (int64_t)(j / CB) * 3 * comp + (int64_t)(j % CB) * KS;
+        }
+        // ---- phase A: covariances, one candidate at a time, lane = atom ----
+        for (int k = 0; k < count; k++) {
+            const double* P = packed + __shfl_sync(0xffffffffu, oi, k);
+            const double* Q = packed + __shfl_sync(0xffffffffu, oj, k);
+            double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            if (R > 0) {
+                double c[R > 0 ? R : 1][6];
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const bool in = lane + 32 * r < M;
+                    const int64_t o = in ? offs[r] : 0;                   // (atom 0: always there)
+                    c[r][0] = P[o]; c[r][1] = P[o + comp]; c[r][2] = P[o + 2 * comp];
+                    c[r][3] = Q[o]; c[r][4] = Q[o + comp]; c[r][5] = Q[o + 2 * comp];
+                    if (!in) c[r][0] = c[r][1] = c[r][2] = 0.0;
+                }
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    v[0] = fma(c[r][0], c[r][3], v[0]); v[1] = fma(c[r][0], c[r][4], v[1]); v[2] = fma(c[r][0], c[r][5], v[2]);
+                    v[3] = fma(c[r][1], c[r][3], v[3]); v[4] = fma(c[r][1], c[r][4], v[4]); v[5] = fma(c[r][1], c[r][5], v[5]);
+                    v[6] = fma(c[r][2], c[r][3], v[6]); v[7] = fma(c[r][2], c[r][4], v[7]); v[8] = fma(c[r][2], c[r][5], v[8]);
+                }
+            } else {
+                for (int m = lane; m < M; m += 32) {
+                    const int64_t o = (int64_t)(m / KS) * slab_stride + (m % KS);
+                    const double px = P[o], py = P[o + comp], pz = P[o + 2 * comp];
+                    const double qx = Q[o], qy = Q[o + comp], qz = Q[o + 2 * comp];
+                    v[0] = fma(px, qx, v[0]); v[1] = fma(px, qy, v[1]); v[2] = fma(px, qz, v[2]);
+                    v[3] = fma(py, qx, v[3]); v[4] = fma(py, qy, v[4]); v[5] = fma(py, qz, v[5]);
+                    v[6] = fma(pz, qx, v[6]); v[7] = fma(pz, qy, v[7]); v[8] = fma(pz, qz, v[8]);
+                }
+            }
+            // halving butterfly over v[0..7]: after the three exchanges lane L holds entry 4 b4 + 2 b3 + b2
+            double w4[4], w2[2], w1;
+#pragma unroll
+            for (int q = 0; q < 4; q++) w4[q] = (b4 ? v[q + 4] : v[q]) + shfl_xor_d(b4 ? v[q] : v[q + 4], 16);
+#pragma unroll
+            for (int q = 0; q < 2; q++) w2[q] = (b3 ? w4[q + 2] : w4[q]) + shfl_xor_d(b3 ? w4[q] : w4[q + 2], 8);
+            w1 = (b2 ? w2[1] : w2[0]) + shfl_xor_d(b2 ? w2[0] : w2[1], 4);
+            w1 += shfl_xor_d(w1, 2);
+            w1 += shfl_xor_d(w1, 1);
+            double v8 = v[8];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v8 += shfl_xor_d(v8, o);
+            if ((lane & 3) == 0) s_cov[warp][k][lane >> 2] = w1;
+            if (lane == 0) s_cov[warp][k][8] = v8;
+        }
+        __syncwarp();
+        // ---- phase B: one eigen-solve per lane ----
+        double Rk[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, lam = 1.0, gap = 1.0;
+        if (lane < count) {
+            double Sk[9];
+#pragma unroll
+            for (int q = 0; q < 9; q++) Sk[q] = s_cov[warp][lane][q];
+            kabsch_rot_from_cov(Sk, Rk, &lam, &gap);
+        }
+        __syncwarp();
+        // ---- phase C: explicit rotation + differences, one candidate at a time ----
+        uint32_t okmask = 0;
+        for (int k = 0; k < count; k++) {
+            const double* P = packed + __shfl_sync(0xffffffffu, oi, k);
+            const double* Q = packed + __shfl_sync(0xffffffffu, oj, k);
+            double Rm[9];
+#pragma unroll
+            for (int q = 0; q < 9; q++) Rm[q] = __shfl_sync(0xffffffffu, Rk[q], k);
+            double ss = 0.0, mx = 0.0;
+            if (R > 0) {
+                double c[R > 0 ? R : 1][6];
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const bool in = lane + 32 * r < M;
+                    const int64_t o = in ? offs[r] : 0;                   // (atom 0: always there)
+                    c[r][0] = P[o]; c[r][1] = P[o + comp]; c[r][2] = P[o + 2 * comp];
+                    c[r][3] = Q[o]; c[r][4] = Q[o + comp]; c[r][5] = Q[o + 2 * comp];
+                    if (!in) c[r][0] = c[r][1] = c[r][2] = c[r][3] = c[r][4] = c[r][5] = 0.0;
+                }
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const double dx = fma(Rm[0], c[r][0], fma(Rm[1], c[r][1], Rm[2] * c[r][2])) - c[r][3];
+                    const double dy = fma(Rm[3], c[r][0], fma(Rm[4], c[r][1], Rm[5] * c[r][2])) - c[r][4];
+                    const double dz = fma(Rm[6], c[r][0], fma(Rm[7], c[r][1], Rm[8] * c[r][2])) - c[r][5];
+                    const double d2 = fma(dx, dx, fma(dy, dy, dz * dz));
+                    ss += d2;
+                    mx = fmax(mx, d2);
+                }
+            } else {
+                for (int m = lane; m < M; m += 32) {
+                    const int64_t o = (int64_t)(m / KS) * slab_stride + (m % KS);
+                    const double px = P[o], py = P[o + comp], pz = P[o + 2 * comp];
+                    const double dx = fma(Rm[0], px, fma(Rm[1], py, Rm[2] * pz)) - Q[o];
+                    const double dy = fma(Rm[3], px, fma(Rm[4], py, Rm[5] * pz)) - Q[o + comp];
+                    const double dz = fma(Rm[6], px, fma(Rm[7], py, Rm[8] * pz)) - Q[o + 2 * comp];
+                    const double d2 = fma(dx, dx, fma(dy, dy, dz * dz));
+                    ss += d2;
+                    mx = fmax(mx, d2);
+                }
+            }
+            // two values, one exchange: the lower half-warp finishes the sum, the upper one the maximum
+            {
+                const double send = b4 ? ss : mx, got = shfl_xor_d(send, 16);
+                double r = b4 ? fmax(mx, got) : ss + got;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) {
+                    const double t = shfl_xor_d(r, o);
+                    r = b4 ? fmax(r, t) : r + t;
+                }
+                ss = __shfl_sync(0xffffffffu, r, 0);
+                mx = __shfl_sync(0xffffffffu, r, 16);
+            }
+            const double rmsd = sqrt(ss / (double)M), maxdev = sqrt(mx);
+            const bool ok = (rmsd < thr) && (maxdev < thr2);
+            if (lane == k) {
+                n_cand++;
+                n_ok += ok;
+                n_near += (fabs(rmsd - thr) < 1e-6) || ((rmsd < thr) && fabs(maxdev - thr2) < 1e-6);
+                n_deg += ok && (gap < 1e-9 * fabs(lam));
+                if (!ok) atomicAnd(&sim_bits[(int64_t)lrow * W + (j >> 5)], ~(1u << (j & 31)));
+            }
+            okmask |= (ok ? 1u : 0u) << k;
+        }
+        if (pair_list && okmask) {
+            int64_t base = 0;
+            if (lane == 0) base = list_reserve(&pair_list[0].x, __popc(okmask), pair_stride - 1);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if ((okmask >> lane) & 1u) {
+                const int64_t slot = base + __popc(okmask & ((1u << lane) - 1u));
+                if (slot < pair_stride - 1) pair_list[1 + slot] = make_int2(i, j);
+            }
+        }
+        __syncwarp();
+    }
+    n_cand = warp_sum_u64(n_cand); n_ok = warp_sum_u64(n_ok); n_near = warp_sum_u64(n_near); n_deg = warp_sum_u64(n_deg);
+    if (lane == 0 && stats) {
+        if (n_cand) atomicAdd(&stats[0], n_cand);
+        if (n_ok) atomicAdd(&stats[1], n_ok);
+        if (n_near) atomicAdd(&stats[2], n_near);
+        if (n_deg) atomicAdd(&stats[3], n_deg);
+    }
+}
+
 // Batched rmsd_and_max_numba on explicit AoS pairs: P, Q are (n, M, 3); one warp per pair.
 __global__ void __launch_bounds__(256) rmsd_pairs_kernel(const double* __restrict__ P, const double* __restrict__ Q,
                                                          int64_t n, int M, int64_t q_stride_is_zero,
@@ -477,7 +670,14 @@ extern "C" int tsc_rmsd_verify(const double* packed, int64_t N, int32_t M, const
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        rmsd_verify_list_kernel<<<sms * 4, VF_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        const int rounds = (M + 31) / 32;
+        auto kern = rounds == 1 ? rmsd_verify_list_coop_kernel<1> : rounds == 2 ? rmsd_verify_list_coop_kernel<2>
+                  : rounds == 3 ? rmsd_verify_list_coop_kernel<3> : rounds == 4 ? rmsd_verify_list_coop_kernel<4>
+                  : rounds == 5 ? rmsd_verify_list_coop_kernel<5> : rmsd_verify_list_coop_kernel<0>;
+#ifdef TSC_VERIFY_PER_LANE
+        kern = rmsd_verify_list_kernel;                           // the previous form: 4 lanes per candidate, per-lane runs
+#endif
+        kern<<<sms * 4, VF_WARPS * 32, 0, (cudaStream_t)stream>>>(
             packed, N, M, nb_pad, row_blocks, thr, sim_bits, nb_pad, reinterpret_cast<unsigned long long*>(stats),
             reinterpret_cast<const int2*>(cand_list), cand_stride, reinterpret_cast<int2*>(pair_list), pair_stride);
         TSC_CHECK_LAUNCH();
