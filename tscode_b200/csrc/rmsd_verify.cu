@@ -463,37 +463,26 @@ __global__ void __launch_bounds__(VF_WARPS * 32) rmsd_verify_list_coop_kernel(
             oi = (int64_t)(i / CB) * 3 * comp + (int64_t)(i % CB) * KS;
             oj = (int64_t)(j / CB) * 3 * comp + (int64_t)(j % CB) * KS;
         }
-        // ---- phase A: covariances, one candidate at a time, lane = atom ----
-        for (int k = 0; k < count; k++) {
+        // ---- phase A: covariances, one candidate at a time, lane = atom.  (Measured and rejected: loading candidate
+        // k + 1 into a second register set while k is reduced — 196 registers, half the resident warps — and
+        // prefetching its lines into L1 — 0.36 against 0.33 ms on C3: the extra instructions cost more.) ----
+        constexpr int RR = R > 0 ? R : 1;
+        auto load_pair = [&](int k, double (&c)[RR][6], bool zero_q) {
             const double* P = packed + __shfl_sync(0xffffffffu, oi, k);
             const double* Q = packed + __shfl_sync(0xffffffffu, oj, k);
-            double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-            if (R > 0) {
-                double c[R > 0 ? R : 1][6];
 #pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const bool in = lane + 32 * r < M;
-                    const int64_t o = in ? offs[r] : 0;                   // (atom 0: always there)
-                    c[r][0] = P[o]; c[r][1] = P[o + comp]; c[r][2] = P[o + 2 * comp];
-                    c[r][3] = Q[o]; c[r][4] = Q[o + comp]; c[r][5] = Q[o + 2 * comp];
-                    if (!in) c[r][0] = c[r][1] = c[r][2] = 0.0;
-                }
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    v[0] = fma(c[r][0], c[r][3], v[0]); v[1] = fma(c[r][0], c[r][4], v[1]); v[2] = fma(c[r][0], c[r][5], v[2]);
-                    v[3] = fma(c[r][1], c[r][3], v[3]); v[4] = fma(c[r][1], c[r][4], v[4]); v[5] = fma(c[r][1], c[r][5], v[5]);
-                    v[6] = fma(c[r][2], c[r][3], v[6]); v[7] = fma(c[r][2], c[r][4], v[7]); v[8] = fma(c[r][2], c[r][5], v[8]);
-                }
-            } else {
-                for (int m = lane; m < M; m += 32) {
-                    const int64_t o = (int64_t)(m / KS) * slab_stride + (m % KS);
-                    const double px = P[o], py = P[o + comp], pz = P[o + 2 * comp];
-                    const double qx = Q[o], qy = Q[o + comp], qz = Q[o + 2 * comp];
-                    v[0] = fma(px, qx, v[0]); v[1] = fma(px, qy, v[1]); v[2] = fma(px, qz, v[2]);
-                    v[3] = fma(py, qx, v[3]); v[4] = fma(py, qy, v[4]); v[5] = fma(py, qz, v[5]);
-                    v[6] = fma(pz, qx, v[6]); v[7] = fma(pz, qy, v[7]); v[8] = fma(pz, qz, v[8]);
+            for (int r = 0; r < RR; r++) {
+                const bool in = lane + 32 * r < M;
+                const int64_t o = in ? offs[r] : 0;                   // (atom 0: always there)
+                c[r][0] = P[o]; c[r][1] = P[o + comp]; c[r][2] = P[o + 2 * comp];
+                c[r][3] = Q[o]; c[r][4] = Q[o + comp]; c[r][5] = Q[o + 2 * comp];
+                if (!in) {
+                    c[r][0] = c[r][1] = c[r][2] = 0.0;
+                    if (zero_q) c[r][3] = c[r][4] = c[r][5] = 0.0;
                 }
             }
+        };
+        auto reduce_store = [&](int k, double (&v)[9]) {
             // halving butterfly over v[0..7]: after the three exchanges lane L holds entry 4 b4 + 2 b3 + b2
             double w4[4], w2[2], w1;
 #pragma unroll
@@ -508,6 +497,38 @@ __global__ void __launch_bounds__(VF_WARPS * 32) rmsd_verify_list_coop_kernel(
             for (int o = 16; o > 0; o >>= 1) v8 += shfl_xor_d(v8, o);
             if ((lane & 3) == 0) s_cov[warp][k][lane >> 2] = w1;
             if (lane == 0) s_cov[warp][k][8] = v8;
+        };
+        auto cov_of = [&](int k, const double (&c)[RR][6]) {
+            double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int r = 0; r < RR; r++) {
+                v[0] = fma(c[r][0], c[r][3], v[0]); v[1] = fma(c[r][0], c[r][4], v[1]); v[2] = fma(c[r][0], c[r][5], v[2]);
+                v[3] = fma(c[r][1], c[r][3], v[3]); v[4] = fma(c[r][1], c[r][4], v[4]); v[5] = fma(c[r][1], c[r][5], v[5]);
+                v[6] = fma(c[r][2], c[r][3], v[6]); v[7] = fma(c[r][2], c[r][4], v[7]); v[8] = fma(c[r][2], c[r][5], v[8]);
+            }
+            reduce_store(k, v);
+        };
+        if (R > 0) {
+            double c0[RR][6];
+            for (int k = 0; k < count; k++) {
+                load_pair(k, c0, false);
+                cov_of(k, c0);
+            }
+        } else {
+            for (int k = 0; k < count; k++) {
+                const double* P = packed + __shfl_sync(0xffffffffu, oi, k);
+                const double* Q = packed + __shfl_sync(0xffffffffu, oj, k);
+                double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                for (int m = lane; m < M; m += 32) {
+                    const int64_t o = (int64_t)(m / KS) * slab_stride + (m % KS);
+                    const double px = P[o], py = P[o + comp], pz = P[o + 2 * comp];
+                    const double qx = Q[o], qy = Q[o + comp], qz = Q[o + 2 * comp];
+                    v[0] = fma(px, qx, v[0]); v[1] = fma(px, qy, v[1]); v[2] = fma(px, qz, v[2]);
+                    v[3] = fma(py, qx, v[3]); v[4] = fma(py, qy, v[4]); v[5] = fma(py, qz, v[5]);
+                    v[6] = fma(pz, qx, v[6]); v[7] = fma(pz, qy, v[7]); v[8] = fma(pz, qz, v[8]);
+                }
+                reduce_store(k, v);
+            }
         }
         __syncwarp();
         // ---- phase B: one eigen-solve per lane ----
@@ -521,56 +542,17 @@ __global__ void __launch_bounds__(VF_WARPS * 32) rmsd_verify_list_coop_kernel(
         __syncwarp();
         // ---- phase C: explicit rotation + differences, one candidate at a time ----
         uint32_t okmask = 0;
-        for (int k = 0; k < count; k++) {
-            const double* P = packed + __shfl_sync(0xffffffffu, oi, k);
-            const double* Q = packed + __shfl_sync(0xffffffffu, oj, k);
-            double Rm[9];
-#pragma unroll
-            for (int q = 0; q < 9; q++) Rm[q] = __shfl_sync(0xffffffffu, Rk[q], k);
-            double ss = 0.0, mx = 0.0;
-            if (R > 0) {
-                double c[R > 0 ? R : 1][6];
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const bool in = lane + 32 * r < M;
-                    const int64_t o = in ? offs[r] : 0;                   // (atom 0: always there)
-                    c[r][0] = P[o]; c[r][1] = P[o + comp]; c[r][2] = P[o + 2 * comp];
-                    c[r][3] = Q[o]; c[r][4] = Q[o + comp]; c[r][5] = Q[o + 2 * comp];
-                    if (!in) c[r][0] = c[r][1] = c[r][2] = c[r][3] = c[r][4] = c[r][5] = 0.0;
-                }
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const double dx = fma(Rm[0], c[r][0], fma(Rm[1], c[r][1], Rm[2] * c[r][2])) - c[r][3];
-                    const double dy = fma(Rm[3], c[r][0], fma(Rm[4], c[r][1], Rm[5] * c[r][2])) - c[r][4];
-                    const double dz = fma(Rm[6], c[r][0], fma(Rm[7], c[r][1], Rm[8] * c[r][2])) - c[r][5];
-                    const double d2 = fma(dx, dx, fma(dy, dy, dz * dz));
-                    ss += d2;
-                    mx = fmax(mx, d2);
-                }
-            } else {
-                for (int m = lane; m < M; m += 32) {
-                    const int64_t o = (int64_t)(m / KS) * slab_stride + (m % KS);
-                    const double px = P[o], py = P[o + comp], pz = P[o + 2 * comp];
-                    const double dx = fma(Rm[0], px, fma(Rm[1], py, Rm[2] * pz)) - Q[o];
-                    const double dy = fma(Rm[3], px, fma(Rm[4], py, Rm[5] * pz)) - Q[o + comp];
-                    const double dz = fma(Rm[6], px, fma(Rm[7], py, Rm[8] * pz)) - Q[o + 2 * comp];
-                    const double d2 = fma(dx, dx, fma(dy, dy, dz * dz));
-                    ss += d2;
-                    mx = fmax(mx, d2);
-                }
-            }
+        auto finish = [&](int k, double ss, double mx) {
             // two values, one exchange: the lower half-warp finishes the sum, the upper one the maximum
-            {
-                const double send = b4 ? ss : mx, got = shfl_xor_d(send, 16);
-                double r = b4 ? fmax(mx, got) : ss + got;
+            const double send = b4 ? ss : mx, got = shfl_xor_d(send, 16);
+            double r = b4 ? fmax(mx, got) : ss + got;
 #pragma unroll
-                for (int o = 8; o > 0; o >>= 1) {
-                    const double t = shfl_xor_d(r, o);
-                    r = b4 ? fmax(r, t) : r + t;
-                }
-                ss = __shfl_sync(0xffffffffu, r, 0);
-                mx = __shfl_sync(0xffffffffu, r, 16);
+            for (int o = 8; o > 0; o >>= 1) {
+                const double t = shfl_xor_d(r, o);
+                r = b4 ? fmax(r, t) : r + t;
             }
+            ss = __shfl_sync(0xffffffffu, r, 0);
+            mx = __shfl_sync(0xffffffffu, r, 16);
             const double rmsd = sqrt(ss / (double)M), maxdev = sqrt(mx);
             const bool ok = (rmsd < thr) && (maxdev < thr2);
             if (lane == k) {
@@ -581,6 +563,49 @@ __global__ void __launch_bounds__(VF_WARPS * 32) rmsd_verify_list_coop_kernel(
                 if (!ok) atomicAnd(&sim_bits[(int64_t)lrow * W + (j >> 5)], ~(1u << (j & 31)));
             }
             okmask |= (ok ? 1u : 0u) << k;
+        };
+        auto diff_of = [&](int k, const double (&c)[RR][6]) {
+            double Rm[9];
+#pragma unroll
+            for (int q = 0; q < 9; q++) Rm[q] = __shfl_sync(0xffffffffu, Rk[q], k);
+            double ss = 0.0, mx = 0.0;
+#pragma unroll
+            for (int r = 0; r < RR; r++) {
+                const double dx = fma(Rm[0], c[r][0], fma(Rm[1], c[r][1], Rm[2] * c[r][2])) - c[r][3];
+                const double dy = fma(Rm[3], c[r][0], fma(Rm[4], c[r][1], Rm[5] * c[r][2])) - c[r][4];
+                const double dz = fma(Rm[6], c[r][0], fma(Rm[7], c[r][1], Rm[8] * c[r][2])) - c[r][5];
+                const double d2 = fma(dx, dx, fma(dy, dy, dz * dz));
+                ss += d2;
+                mx = fmax(mx, d2);
+            }
+            finish(k, ss, mx);
+        };
+        if (R > 0) {
+            double c0[RR][6];
+            for (int k = 0; k < count; k++) {
+                load_pair(k, c0, true);
+                diff_of(k, c0);
+            }
+        } else {
+            for (int k = 0; k < count; k++) {
+                const double* P = packed + __shfl_sync(0xffffffffu, oi, k);
+                const double* Q = packed + __shfl_sync(0xffffffffu, oj, k);
+                double Rm[9];
+#pragma unroll
+                for (int q = 0; q < 9; q++) Rm[q] = __shfl_sync(0xffffffffu, Rk[q], k);
+                double ss = 0.0, mx = 0.0;
+                for (int m = lane; m < M; m += 32) {
+                    const int64_t o = (int64_t)(m / KS) * slab_stride + (m % KS);
+                    const double px = P[o], py = P[o + comp], pz = P[o + 2 * comp];
+                    const double dx = fma(Rm[0], px, fma(Rm[1], py, Rm[2] * pz)) - Q[o];
+                    const double dy = fma(Rm[3], px, fma(Rm[4], py, Rm[5] * pz)) - Q[o + comp];
+                    const double dz = fma(Rm[6], px, fma(Rm[7], py, Rm[8] * pz)) - Q[o + 2 * comp];
+                    const double d2 = fma(dx, dx, fma(dy, dy, dz * dz));
+                    ss += d2;
+                    mx = fmax(mx, d2);
+                }
+                finish(k, ss, mx);
+            }
         }
         if (pair_list && okmask) {
             int64_t base = 0;
