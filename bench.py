@@ -419,16 +419,22 @@ def run_b200(args):
         ok = bool(np.array_equal(m2, mask_np)) and int(n_out) == int(mask_np.sum())
         lo, hi = pr.row_slice()
         ok = ok and bool(np.array_equal(out, S_host[lo:hi][mask_np[lo:hi]]))
+        from tscode_b200 import rmsd_pruning as _rp
+        host_share = float(_rp.HOST_GATHER_SHARE)
         e2e = {"value": pairs / t_e2e, "unit": UNIT, "ms_per_call": t_e2e * 1e3,
                "h2d_bytes_per_step": int(S_host.nbytes),                      # summed over ranks: each uploads 1 / world
-               "d2h_bytes_per_step": int(mask_np.sum()) * M * 24 + N * world,
+               # survivors that cross the bus (the API takes HOST_GATHER_SHARE of them from the caller's own host array
+               # while the rest is in flight) + the mask
+               "d2h_bytes_per_step": int(round(int(mask_np.sum()) * (1.0 - host_share))) * M * 24 + N * world,
+               "host_gather_share": host_share,
                "result_equals_device_path": ok,
                "api": "tscode_b200.rmsd_pruning.prune_conformers_rmsd(structures: numpy (pinned), atomnos, rmsd_thr"
                       + (", group=WORLD) on every rank -> (survivors of the rank's row slice, full mask)" if world > 1
                          else ") -> (structures[mask], mask)")
-                      + "; H2D of the structures, GPU gather + D2H of the survivors and of the mask inside the timed region"}
+                      + "; H2D of the structures, GPU gather + D2H of the survivors (part of them copied from the caller's "
+                        "host array by host threads meanwhile) and of the mask inside the timed region"}
         pcie = {"h2d_gbps_measured": 54.0, "d2h_gbps_measured": 57.0, "source": "tools/pcie_probe.py on this pool (profiles/)"}
-        floor_ms = (S_host.nbytes / world / 54e9 + int(mask_np.sum()) * M * 24 / world / 57e9) * 1e3
+        floor_ms = (S_host.nbytes / world / 54e9 + int(mask_np.sum()) * (1.0 - host_share) * M * 24 / world / 57e9) * 1e3
         e2e["pcie_roofline"] = {**pcie, "copy_floor_ms": floor_ms, "frac": floor_ms / (t_e2e * 1e3)}
 
     # ---- secondary metric at every N: clash-checked poses/s (configs[1]), pose-sharded -------------------------

@@ -124,6 +124,14 @@ int tsc_host_screen_plan(const double* S, int32_t A, const int32_t* heavy_idx, i
 int tsc_rmsd_verify(const double* packed, int64_t N, int32_t M, const int32_t* row_blocks,
                     int32_t n_rb, double thr, uint32_t* sim_bits, uint64_t* stats, int32_t* pair_list,
                     int64_t pair_stride, const int32_t* cand_list, int64_t cand_stride, void* stream);
+/* Incremental form: verifies only the candidate-list entries appended since the previous call and advances
+ * progress[0] (device int32; zero it together with the list header).  For callers that interleave screen launches and
+ * verification on one stream, so that only the last launch's candidates are left when the screen ends.  final_call != 0
+ * also runs the bit-row scan that takes over when the list has overflowed (once, at the end). */
+int tsc_rmsd_verify_incr(const double* packed, int64_t N, int32_t M, const int32_t* row_blocks, int32_t n_rb,
+                         double thr, uint32_t* sim_bits, uint64_t* stats, int32_t* pair_list, int64_t pair_stride,
+                         const int32_t* cand_list, int64_t cand_stride, int32_t* progress, int32_t final_call,
+                         void* stream);
 
 /* Batched rmsd_and_max_numba on explicit pairs: P, Q (n, M, 3) -> rmsd (n), maxdev (n).
  * broadcast_p = 1 compares P[0] with every Q[k] (_rmsd_similarity, rmsd_pruning.py:208-224). */

@@ -34,6 +34,7 @@ SIGNATURES = {
     "tsc_pack_screen": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp]),
     "tsc_rmsd_screen": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "tsc_rmsd_verify": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
+    "tsc_rmsd_verify_incr": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i32, _vp]),
     "tsc_elim_fused_ws_words": (_i64, [_i64]),
     "tsc_elim_fused_out_bytes": (_i64, [_i64]),
     "tsc_elim_fused": (C.c_int, [_vp, _i32, _i64, _i64, _i32, _vp, _vp, _vp]),

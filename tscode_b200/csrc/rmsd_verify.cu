@@ -312,9 +312,13 @@ __device__ __forceinline__ void slab_diff(const double* __restrict__ P, const do
 __global__ void __launch_bounds__(VF_WARPS * 32) rmsd_verify_list_kernel(
     const double* __restrict__ packed, int64_t N, int M, int64_t nb_pad, const int32_t* __restrict__ row_blocks,
     double thr, uint32_t* sim_bits, int64_t W, unsigned long long* stats, const int2* __restrict__ cand,
-    int64_t cand_stride, int2* pair_list, int64_t pair_stride) {
-    const int64_t n = cand[0].x;
-    if (n <= 0 || n > cand_stride - 1) return;
+    int64_t cand_stride, int2* pair_list, int64_t pair_stride, const int32_t* __restrict__ progress) {
+    const int64_t n_all = cand[0].x;
+    if (n_all <= 0 || n_all > cand_stride - 1) return;
+    const int64_t done = progress ? progress[0] : 0;
+    const int64_t n = n_all - done;
+    if (n <= 0) return;
+    cand += done;
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -433,9 +437,15 @@ template <int R>
 __global__ void __launch_bounds__(VF_WARPS * 32) rmsd_verify_list_coop_kernel(
     const double* __restrict__ packed, int64_t N, int M, int64_t nb_pad, const int32_t* __restrict__ row_blocks,
     double thr, uint32_t* sim_bits, int64_t W, unsigned long long* stats, const int2* __restrict__ cand,
-    int64_t cand_stride, int2* pair_list, int64_t pair_stride) {
-    const int64_t n = cand[0].x;
-    if (n <= 0 || n > cand_stride - 1) return;
+    int64_t cand_stride, int2* pair_list, int64_t pair_stride, const int32_t* __restrict__ progress) {
+    // entries [progress[0], count) of the list: a caller that verifies while the screen is still producing (the
+    // pipelined upload) passes the number of entries earlier calls have dealt with (tsc_rmsd_verify_incr)
+    const int64_t n_all = cand[0].x;
+    if (n_all <= 0 || n_all > cand_stride - 1) return;
+    const int64_t done = progress ? progress[0] : 0;
+    const int64_t n = n_all - done;
+    if (n <= 0) return;
+    cand += done;
     __shared__ double s_cov[VF_WARPS][32][9];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -685,9 +695,40 @@ __global__ void group_greedy_kernel(const int32_t* __restrict__ g_begin, int32_t
 
 }  // namespace tsc
 
+namespace tsc {
+__global__ void verify_progress_kernel(const int32_t* cand_header, int64_t cand_stride, int32_t* progress) {
+    const int64_t n = cand_header[0];
+    if (n >= 0 && n <= cand_stride - 1) progress[0] = (int32_t)n;       // (an overflowed list is never advanced)
+}
+}  // namespace tsc
+
+static int verify_impl(const double* packed, int64_t N, int32_t M, const int32_t* row_blocks, int32_t n_rb, double thr,
+                       uint32_t* sim_bits, uint64_t* stats, int32_t* pair_list, int64_t pair_stride,
+                       const int32_t* cand_list, int64_t cand_stride, int32_t* progress, int32_t final_call, void* stream);
+
 extern "C" int tsc_rmsd_verify(const double* packed, int64_t N, int32_t M, const int32_t* row_blocks,
                                int32_t n_rb, double thr, uint32_t* sim_bits, uint64_t* stats, int32_t* pair_list,
                                int64_t pair_stride, const int32_t* cand_list, int64_t cand_stride, void* stream) {
+    return verify_impl(packed, N, M, row_blocks, n_rb, thr, sim_bits, stats, pair_list, pair_stride, cand_list, cand_stride,
+                       nullptr, 1, stream);
+}
+
+// Incremental form for callers that interleave screen launches and verification on one stream (the pipelined upload
+// of rmsd_pruning.py): verifies the candidate-list entries appended since the previous call and then advances
+// progress[0] (device int32, zero it before the first screen launch).  final_call != 0 additionally runs the bit-row
+// scan that takes over when the list has overflowed (it re-examines every set bit, so it must run once, at the end).
+extern "C" int tsc_rmsd_verify_incr(const double* packed, int64_t N, int32_t M, const int32_t* row_blocks,
+                                    int32_t n_rb, double thr, uint32_t* sim_bits, uint64_t* stats, int32_t* pair_list,
+                                    int64_t pair_stride, const int32_t* cand_list, int64_t cand_stride,
+                                    int32_t* progress, int32_t final_call, void* stream) {
+    if (!cand_list || !progress) return (int)cudaErrorInvalidValue;
+    return verify_impl(packed, N, M, row_blocks, n_rb, thr, sim_bits, stats, pair_list, pair_stride, cand_list, cand_stride,
+                       progress, final_call, stream);
+}
+
+static int verify_impl(const double* packed, int64_t N, int32_t M, const int32_t* row_blocks, int32_t n_rb, double thr,
+                       uint32_t* sim_bits, uint64_t* stats, int32_t* pair_list, int64_t pair_stride,
+                       const int32_t* cand_list, int64_t cand_stride, int32_t* progress, int32_t final_call, void* stream) {
     using namespace tsc;
     if (N <= 0 || n_rb <= 0) return 0;
     const int64_t nb_pad = num_blocks_padded(N);
@@ -704,9 +745,15 @@ extern "C" int tsc_rmsd_verify(const double* packed, int64_t N, int32_t M, const
 #endif
         kern<<<sms * 4, VF_WARPS * 32, 0, (cudaStream_t)stream>>>(
             packed, N, M, nb_pad, row_blocks, thr, sim_bits, nb_pad, reinterpret_cast<unsigned long long*>(stats),
-            reinterpret_cast<const int2*>(cand_list), cand_stride, reinterpret_cast<int2*>(pair_list), pair_stride);
+            reinterpret_cast<const int2*>(cand_list), cand_stride, reinterpret_cast<int2*>(pair_list), pair_stride,
+            progress);
         TSC_CHECK_LAUNCH();
+        if (progress) {
+            verify_progress_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(cand_list, cand_stride, progress);
+            TSC_CHECK_LAUNCH();
+        }
     }
+    if (!final_call) return 0;
     int64_t rows = (int64_t)n_rb * CB;
     int64_t blocks = (rows + 4 * VF_WARPS - 1) / (4 * VF_WARPS);       // ~4 rows per warp: fuller batches
     if (blocks > 148 * 8) blocks = 148 * 8;
