@@ -19,14 +19,18 @@ $CMD > $OUT/bench_plain.json 2> $OUT/bench_plain.err && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv $CMD > $OUT/ncu_launches.log 2>&1
 echo "launch list rc=$?" | tee -a $OUT/rc.txt
 $CMD > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:rmsd_screen_kernel -c 5 -o $OUT/screen_c3 $CMD > $OUT/ncu_screen.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:rmsd_screen_kernel -c 2 -o $OUT/screen_c3 $CMD > $OUT/ncu_screen.log 2>&1
 echo "screen capture rc=$?" | tee -a $OUT/rc.txt
 K="python tools/profile_kernels.py"
 $K > $OUT/profile_kernels_plain.json 2> $OUT/profile_kernels.err && \
-ncu --set full --clock-control none --import-source on -k regex:"rmsd_screen_kernel|rmsd_verify_list|elim_fused|embed_clash_kernel|rotcorr_scan" -c 24 -o $OUT/prof_kernels $K > $OUT/ncu_kernels.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"rmsd_screen_kernel|rmsd_verify_list|elim_fused|embed_clash_kernel|rotcorr_scan" -c 14 -o $OUT/prof_kernels $K > $OUT/ncu_kernels.log 2>&1
 echo "kernel captures rc=$?" | tee -a $OUT/rc.txt
 echo "== probes"
 timeout 120 python tools/screen_trace.py 30000 80 0,1,2 > $OUT/screen_trace.log 2>&1 ; grep steady $OUT/screen_trace.log
 timeout 300 python tools/screen_check.py screen > $OUT/screen_check.log 2>&1 ; grep -E "small cases|screen mode" $OUT/screen_check.log | cut -c1-140
 timeout 120 python tools/clash_run.py > $OUT/clash_run.log 2>&1 ; tail -2 $OUT/clash_run.log
+# gpurun brings back at most 64 MiB: summaries are made here, and the big report is dropped if the total would not fit
+python tools/ncu_summary.py $OUT/screen_c3.ncu-rep > $OUT/ncu_screen_c3.md 2>/dev/null
+python tools/ncu_summary.py $OUT/prof_kernels.ncu-rep > $OUT/ncu_kernels.md 2>/dev/null
+[ $(du -sm gpurun_out | cut -f1) -gt 60 ] && rm -f $OUT/prof_kernels.ncu-rep
 ls -la $OUT
