@@ -551,9 +551,10 @@ __global__ void __launch_bounds__(VF_WARPS * 32) rmsd_verify_list_coop_kernel(
         }
         __syncwarp();
         // ---- phase C: explicit rotation + differences, one candidate at a time ----
-        uint32_t okmask = 0;
+        double my_ss = 0.0, my_mx = 0.0;                          // lane k: sum and maximum of candidate k
         auto finish = [&](int k, double ss, double mx) {
-            // two values, one exchange: the lower half-warp finishes the sum, the upper one the maximum
+            // two values, one exchange: the lower half-warp finishes the sum, the upper one the maximum; lane k keeps
+            // both (the divisions and square roots of the whole batch then run once, one candidate per lane)
             const double send = b4 ? ss : mx, got = shfl_xor_d(send, 16);
             double r = b4 ? fmax(mx, got) : ss + got;
 #pragma unroll
@@ -561,18 +562,8 @@ __global__ void __launch_bounds__(VF_WARPS * 32) rmsd_verify_list_coop_kernel(
                 const double t = shfl_xor_d(r, o);
                 r = b4 ? fmax(r, t) : r + t;
             }
-            ss = __shfl_sync(0xffffffffu, r, 0);
-            mx = __shfl_sync(0xffffffffu, r, 16);
-            const double rmsd = sqrt(ss / (double)M), maxdev = sqrt(mx);
-            const bool ok = (rmsd < thr) && (maxdev < thr2);
-            if (lane == k) {
-                n_cand++;
-                n_ok += ok;
-                n_near += (fabs(rmsd - thr) < 1e-6) || ((rmsd < thr) && fabs(maxdev - thr2) < 1e-6);
-                n_deg += ok && (gap < 1e-9 * fabs(lam));
-                if (!ok) atomicAnd(&sim_bits[(int64_t)lrow * W + (j >> 5)], ~(1u << (j & 31)));
-            }
-            okmask |= (ok ? 1u : 0u) << k;
+            const double s_all = __shfl_sync(0xffffffffu, r, 0), m_all = __shfl_sync(0xffffffffu, r, 16);
+            if (lane == k) { my_ss = s_all; my_mx = m_all; }
         };
         auto diff_of = [&](int k, const double (&c)[RR][6]) {
             double Rm[9];
@@ -617,6 +608,17 @@ __global__ void __launch_bounds__(VF_WARPS * 32) rmsd_verify_list_coop_kernel(
                 finish(k, ss, mx);
             }
         }
+        bool ok = false;
+        if (lane < count) {
+            const double rmsd = sqrt(my_ss / (double)M), maxdev = sqrt(my_mx);
+            ok = (rmsd < thr) && (maxdev < thr2);
+            n_cand++;
+            n_ok += ok;
+            n_near += (fabs(rmsd - thr) < 1e-6) || ((rmsd < thr) && fabs(maxdev - thr2) < 1e-6);
+            n_deg += ok && (gap < 1e-9 * fabs(lam));
+            if (!ok) atomicAnd(&sim_bits[(int64_t)lrow * W + (j >> 5)], ~(1u << (j & 31)));
+        }
+        const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
         if (pair_list && okmask) {
             int64_t base = 0;
             if (lane == 0) base = list_reserve(&pair_list[0].x, __popc(okmask), pair_stride - 1);
