@@ -61,12 +61,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.rows, self.times, self.proc, self.idx = [], [], None, gpu_index
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -76,18 +76,30 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
+            self.times.append(time.perf_counter())
 
-    def stop(self):
+    def stop(self, window=None):
+        """window = (t0, t1) in time.perf_counter(): only samples received inside it count (the sampler is started
+        before the warm-up steps so that it is already running when the short timed region begins); if none fell
+        inside, the samples of the 150 ms before it — the warm-up steps of the same workload — are used and the result
+        says so."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        rows, where = list(self.rows), "whole run of the sampler"
+        if window is not None:
+            t0, t1 = window
+            pairs = list(zip(self.times, self.rows))
+            rows, where = [r for t, r in pairs if t0 <= t <= t1 + 0.02], "timed region"
+            if not rows:
+                rows, where = [r for t, r in pairs if t0 - 0.15 <= t <= t1 + 0.02], "timed region + the warm-up steps right before it"
         sm, smax, power, reasons = [], [], [], set()
-        for r in self.rows:
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -99,7 +111,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "sampled": where,
+                "reasons": sorted(reasons)}
 
 
 def fp64_peaks(torch):
@@ -352,12 +365,23 @@ def run_b200(args):
                 phase_ms[name].append(e[k].elapsed_time(e[k + 1]))
         return mask
 
-    for _ in range(max(args.warmup, 3)):
-        mask = step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        mask = step()
+    barrier()
+    # nvidia-smi needs ~0.1 s to print its first line: keep the GPU on the same workload (untimed) until the sampler is
+    # alive (several ranks: the step holds collectives, so every rank runs the same fixed number of extra steps)
+    if world == 1:
+        t_up = time.perf_counter() + 0.5
+        while not sampler.rows and time.perf_counter() < t_up:
+            step()
+            torch.cuda.synchronize()
+    else:
+        for _ in range(60):
+            step()
+        torch.cuda.synchronize()
     barrier()
     t_events = []
     w0 = time.perf_counter()
@@ -371,7 +395,7 @@ def run_b200(args):
         t_events.append(e0.elapsed_time(e1))
     barrier()
     wall_ms = (time.perf_counter() - w0) * 1e3
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(window=(w0, time.perf_counter())) if rank == 0 else None
     verify_stats = pr.stats_dict()          # counters of the last timed step
     if rank == 0 and not args.skip_extras:
         # The timed region lasts a few tens of ms: nvidia-smi (100 ms period) sees it once at best.  Untimed addition:
@@ -420,7 +444,7 @@ def run_b200(args):
         lo, hi = pr.row_slice()
         ok = ok and bool(np.array_equal(out, S_host[lo:hi][mask_np[lo:hi]]))
         from tscode_b200 import rmsd_pruning as _rp
-        host_share = float(_rp.HOST_GATHER_SHARE)
+        host_share = float(_rp.HOST_GATHER_SHARE) if world == 1 else 0.0
         e2e = {"value": pairs / t_e2e, "unit": UNIT, "ms_per_call": t_e2e * 1e3,
                "h2d_bytes_per_step": int(S_host.nbytes),                      # summed over ranks: each uploads 1 / world
                # survivors that cross the bus (the API takes HOST_GATHER_SHARE of them from the caller's own host array

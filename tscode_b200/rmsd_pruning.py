@@ -710,7 +710,9 @@ def prune_conformers_rmsd(structures, atomnos, rmsd_thr=0.5, *, group=None, rank
             # The survivors exist twice — in the caller's host array and on the device — so they are fetched from
             # both at once: the first HOST_GATHER_SHARE of them by a multi-threaded host gather out of `structures`,
             # the rest gathered on the GPU and copied out at PCIe speed (94 MB over PCIe alone: 1.7 ms on C3).
-            n_host = int(n * HOST_GATHER_SHARE) if n >= 4096 else 0
+            # (one rank only: with several ranks every rank's D2H is 1 / world already and runs on its own link, while
+            # the host gathers of all ranks would share the same cores and memory — measured 6.35 against 4.9 ms at 2)
+            n_host = int(n * HOST_GATHER_SHARE) if (n >= 4096 and world == 1) else 0
             idx_host = idx[:n_host].cpu() if n_host else None                # (small D2H; the stream is idle here)
             if n > n_host:
                 dev_rows = torch.index_select(pr.S[lo:hi], 0, idx[n_host:])
