@@ -358,7 +358,10 @@ def _cluster_rejects_fast(edges):
                     full = True
                     break
         seen_all.update(seen)
-        nodes = set(x for x in seen if x in adj)                 # show_nodes(self.nbunch_iter(c))
+        # show_nodes(self.nbunch_iter(c)): a NEW set filled element by element in c's iteration order (every element
+        # of c is a node, so the membership test of nbunch_iter is dropped; set(iter(..)) inserts one by one exactly as
+        # the generator form does, whereas set(seen) would copy the table with a different pre-sizing)
+        nodes = set(iter(seen))
         if 2 * len(nodes) < n:
             first = next(iter(nodes))
         else:
@@ -499,8 +502,8 @@ def ladder_replay_scan(first_hit, N, best_angles=None, verbose=False, native=Non
             if native:
                 n = int(L.tsc_host_rotcorr_chunk(base, hi, p_first, p_reach, p_state, T, p_compact, p_off, p_table,
                                                  p_mi, p_mj))
-                for a, b in zip(mi[:n].tolist(), mj[:n].tolist()):                 # same insertion order (:1119-1120)
-                    matches.add((a, b))
+                if n:                                                              # same insertion order (:1119-1120)
+                    matches = set(zip(mi[:n].tolist(), mj[:n].tolist()))
             else:
                 fh = first_hit[base:hi]
                 new_hi = np.minimum(fh - 1, hi - 1)
