@@ -754,3 +754,35 @@ def test_cyclical_embed_pipeline_vs_live_reference(gpu, name):
         assert np.array_equal(k, unpack(r["kept_hex"], r["poses"]))
         assert np.array_equal(m, unpack(r["mask_hex"], r["kept"]))
 
+
+
+@pytest.mark.gpu
+def test_pipelined_upload_with_incremental_verify_equals_device_path(gpu):
+    """Host input >= 4096 structures goes through the chunked upload, which screens and verifies chunk by chunk
+    (tsc_rmsd_verify_incr with a device-side progress counter).  Confirmed pairs, final similarity bits of the rows,
+    verify counters and mask must equal those of the one-shot path on a device-resident copy — for every form of the
+    screen, with and without the frame."""
+    from tscode_b200.rmsd_pruning import RmsdPruner
+    from tscode_b200.synth import gen_ensemble
+    for scale, M in ((3.0, 40), (np.array([6.0, 2.0, 1.0]), 33)):
+        S = gen_ensemble(21, 6000, M, 500, scale=scale)
+        atomnos = np.full(M, 6)
+        for mode, frame in ((None, True), (0, True), (1, True), (2, False), (3, True)):
+            a = RmsdPruner(torch.from_numpy(S).to(gpu), atomnos, 0.5, screen_mode=mode, screen_frame=frame)
+            ma = a.run().cpu().numpy()
+            b = RmsdPruner(S, atomnos, 0.5, screen_mode=mode, screen_frame=frame)          # host input: pipelined
+            assert b._host is not None
+            mb = b.run().cpu().numpy()
+            assert np.array_equal(ma, mb), (M, mode)
+            # final bits, from each row's own panel on (words left of it are never read; never-written ones are garbage)
+            Nr, W = S.shape[0], a.sim_bits.shape[1]
+            live = torch.arange(W, device=gpu)[None, :] >= (torch.arange(Nr, device=gpu) // 128 * 4)[:, None]
+            assert torch.equal(a.sim_bits[:Nr][live], b.sim_bits[:Nr][live]), (M, mode)
+            na, nb = int(a.pair_list[0, 0]), int(b.pair_list[0, 0])
+            pa = {tuple(p) for p in a.pair_list[1:1 + na].cpu().numpy().tolist()}
+            pb = {tuple(p) for p in b.pair_list[1:1 + nb].cpu().numpy().tolist()}
+            assert na == nb == len(pa) and pa == pb, (M, mode, na, nb)
+            sa, sb = a.stats_dict(), b.stats_dict()
+            assert sa["confirmed"] == sb["confirmed"] == na
+            assert sa["candidates"] == sb["candidates"], (sa, sb)         # every candidate verified exactly once
+            assert int(b._verify_progress[0]) == int(b.cand_list[0, 0])
