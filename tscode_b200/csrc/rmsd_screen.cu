@@ -493,8 +493,33 @@ __global__ void __launch_bounds__(sc_threads(J), 1) rmsd_screen_kernel(const ScP
                 }
                 // ---- the tile's verdicts for this warp's columns: column terms B_j (rounded down), D_j (rounded up)
                 uint32_t near = 0;                                           // bit c: pair of column c0 + c not excluded
+                if (MODE == 0) {
+                    // Samuelson only (the bound and its constant: see the general form below), leaner bit gathering:
+                    // with lfp = max(lf, 0) the single value t = 3.00004 f - lfp^2 is negative exactly for the excluded
+                    // pairs (lf <= 0 or NaN -> lfp = 0 -> t >= 0; f NaN -> t = NaN, sign clear), and its sign bits are
+                    // shifted into the word one funnel shift per pair, last column first
+                    uint32_t excl = 0;
 #pragma unroll
-                for (int cp = 0; cp < NCP; cp++) {
+                    for (int cp = NCP - 1; cp >= 0; cp--) {
+                        const float4 cb = ctB[cp / 2], cd = ctD[cp / 2];
+                        const unsigned long long Bj2 = (cp & 1) ? OpsF2::pack(__float_as_uint(cb.z), __float_as_uint(cb.w))
+                                                               : OpsF2::pack(__float_as_uint(cb.x), __float_as_uint(cb.y));
+                        const unsigned long long Dj2 = (cp & 1) ? OpsF2::pack(__float_as_uint(cd.z), __float_as_uint(cd.w))
+                                                               : OpsF2::pack(__float_as_uint(cd.x), __float_as_uint(cd.y));
+                        const unsigned long long lf2 = OpsF2::fma(nCf2, Dj2, OpsF2::add(Af2, Bj2));
+                        float l0, l1, t0, t1;
+                        OpsF2::unpack(lf2, l0, l1);
+                        const unsigned long long lp2 = OpsF2::pack(__float_as_uint(fmaxf(l0, 0.0f)), __float_as_uint(fmaxf(l1, 0.0f)));
+                        const unsigned long long t2 =
+                            OpsF2::fma(OpsF2::bc(3.00004f), T[0][cp], OpsF2::mul(OpsF2::mul(lp2, lp2), OpsF2::bc(-1.0f)));
+                        OpsF2::unpack(t2, t0, t1);
+                        excl = __funnelshift_l(__float_as_uint(t1), excl, 1);
+                        excl = __funnelshift_l(__float_as_uint(t0), excl, 1);
+                    }
+                    near = ~excl;
+                }
+#pragma unroll
+                for (int cp = 0; cp < (MODE == 0 ? 0 : NCP); cp++) {
                     unsigned long long tt[6];
 #pragma unroll
                     for (int q = 0; q < 6; q++) tt[q] = T[MODE == 0 ? 0 : q][cp];
