@@ -204,7 +204,7 @@ def _ru32(x):
 def test_f16_prescreen_model_never_loses_a_similar_pair(hm, case):
     """Host model of the default pre-screen: coordinates rounded to FP16 as tsc_pack_f16 does,
     covariance accumulated in FP32, threshold eigenvalue lowered by the operand error bound with the directed
-    roundings of tf32_row_consts / the column terms, stage 1 (Samuelson) and stage 2 (FP32 quartic through the same
+    roundings of screen_row_consts / the column terms, stage 1 (Samuelson) and stage 2 (FP32 quartic through the same
     tsc_math.cuh code the device runs).  Every pair the oracle calls similar must survive both stages; almost
     everything else must be excluded."""
     S = gen_ensemble(case["seed"], case["N"], case["M"], case["ncl"], sigma_noise=case["noise"],

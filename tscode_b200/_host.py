@@ -221,7 +221,7 @@ def build_items_balanced(N: int, row_blocks: np.ndarray, n_ctas: int, panel_lo: 
     return np.asarray(items, dtype=np.int32).reshape(-1, 4)
 
 
-def tf32_rows_padded(N: int) -> int:
+def screen_rows_padded(N: int) -> int:
     """Rows the screen's operand images, G, sG and CT are padded to: whole 128-row panels and whole tiles of 32 / 48 / 64
     conformers (rmsd_screen.cu: tsc_screen_rows_padded)."""
     return ((N + 383) // 384) * 384

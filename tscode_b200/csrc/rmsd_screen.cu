@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(sc_threads(J), 1) rmsd_screen_kernel(const ScP
                 __syncwarp();
                 if (lane == 0) mbar_arrive(am_full);
             }
-            const TfRow row = tf32_row_consts(p.G[i], p.sG[i], p.e_thr);
+            const ScRow row = screen_row_consts(p.G[i], p.sG[i], p.e_thr);
             const unsigned long long Af2 = OpsF2::bc(row.Af), nCf2 = OpsF2::bc(-row.Cf);
             uint8_t* out_row = p.sim_bits8 + ((int64_t)w.w * CB + row_in_panel) * (4 * p.W);
             for (int t = 0; t < w.z; t++) {

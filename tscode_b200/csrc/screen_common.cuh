@@ -59,13 +59,13 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, ui
 // The epilogue works with a guaranteed LOWER bound lf = A_i + B_j - C_i D_j from directed-rounded FP32 terms:
 // per row A_i = float_rd(hs G_i - 0.5 e_thr), C_i = float_ru(sqrt(3) eps sqrt(G_i)'); per column (pack)
 // B_j = float_rd(hs G_j), D_j = float_ru(sqrt(G_j)').
-struct TfRow {                 // per-thread (row i) constants
+struct ScRow {                 // per-thread (row i) constants
     float Af, Cf;              // A_i = float_rd(hs G_i - 0.5 e_thr),  C_i = float_ru(sqrt(3) eps sqrt(G_i))
     double hi, ci;             // the same in FP64: hi = hs G_i - 0.5 e_thr,  ci = -sqrt(3) eps sqrt(G_i)
 };
-__device__ __forceinline__ TfRow tf32_row_consts(double Gi, double sGi, double e_thr) {
+__device__ __forceinline__ ScRow screen_row_consts(double Gi, double sGi, double e_thr) {
     const double hs = 0.5 * (1.0 - 1e-10), cc = 1.7320508075688772 * TF_EPS;
-    TfRow r;
+    ScRow r;
     r.hi = fma(hs, Gi, -0.5 * e_thr);
     r.ci = -cc * sGi;
     r.Af = __double2float_rd(r.hi);

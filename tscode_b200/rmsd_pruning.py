@@ -114,7 +114,7 @@ class RmsdPruner:
                  "fma" = FP64 FMA pipe.  All give identical final similarity bits and masks.
     screen_mode: form of the default screen (0 = Samuelson-type bound only, on 48-wide tiles; 1 = the bound, then
                  the FP32 quartic test where it left a pair undecided; 2 = quartic for every pair; 3 = mode 0 on
-                 64-wide tiles); None = chosen from the shape of the first structure (_host.screen_mode_for).
+                 64-wide tiles); None = chosen from the first structure and a sample of pairs (_host.screen_plan_native).
     screen_frame: rotate the ensemble into the principal axes of the first structure and weight the column-side
                  operand (_host.screen_frame; rmsd_screen.cu, ScFrame), which makes the bound as sharp for elongated
                  and planar molecules as it is for isotropic ones.  Both are speed choices only: every form is
@@ -210,7 +210,7 @@ class RmsdPruner:
             self.n_tiles, self.tiles = wl.get("n_tiles", 0), wl.get("tiles")
             self.n_items, self.items = wl.get("n_items", 0), wl.get("items")
             self.packed = torch.empty(max(_host.packed_doubles(N, max(M, 1)), 1), dtype=torch.float64, device=dev)
-            n_g = max(self.nb_pad * _host.CB, _host.tf32_rows_padded(N))
+            n_g = max(self.nb_pad * _host.CB, _host.screen_rows_padded(N))
             self.G = torch.empty(n_g, dtype=torch.float64, device=dev)
             if self.variant == 5:
                 L = lib()
@@ -305,7 +305,7 @@ class RmsdPruner:
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
                     check(L.tsc_pack(ptr(self.S), self.N, self.A, ptr(self.heavy_idx), self.M, ptr(self.packed),
-                                     ptr(self.G_side), stream_ptr()), "tsc_pack")      # (G itself comes from pack_f16)
+                                     ptr(self.G_side), stream_ptr()), "tsc_pack")      # (G itself comes from tsc_pack_screen)
                     self._packed_event = torch.cuda.Event()
                     self._packed_event.record(side)
             else:
