@@ -140,6 +140,7 @@ class RmsdPruner:
         self.screen_mode = screen_mode    # form of the default screen: None = chosen from the molecule's shape (below)
         self.frame = None                 # 12 float64 (Q, t) given to tsc_pack_screen / tsc_rmsd_screen; None = identity
         self._verify_progress = None      # device int32: candidate-list entries already verified (pipelined upload)
+        self._info_host = None            # pinned landing buffer of the fused ladder's status words
         self._verify_incremental = False
         if ladder not in ("fused", "bitrows"):
             raise ValueError("ladder must be 'fused' or 'bitrows'")
@@ -432,7 +433,11 @@ class RmsdPruner:
             if tier == "unavailable":
                 return None
             with torch.cuda.device(self.device):
-                info = self.fused_out[self._info_off:self._info_off + 128].view(torch.int32).tolist()   # sync
+                if self._info_host is None:
+                    self._info_host = torch.empty(32, dtype=torch.int32, pin_memory=True)
+                self._info_host.copy_(self.fused_out[self._info_off:self._info_off + 128].view(torch.int32), non_blocking=True)
+                torch.cuda.current_stream().synchronize()                                      # the one sync of the ladder
+                info = self._info_host.tolist()
             if info[0] == 1 and tier == "small":
                 self._enqueue_fused("full")               # a list did not fit the short prefix
                 continue
