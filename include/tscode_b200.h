@@ -184,6 +184,16 @@ int64_t tsc_elim_fused_ws_words(int64_t N);
 int64_t tsc_elim_fused_out_bytes(int64_t N);
 int tsc_elim_fused(const int32_t* lists, int32_t n_lists, int64_t stride, int64_t N, int32_t gate,
                    int32_t* ws, uint8_t* out, void* stream);
+/* Several ranks without a collective: every rank copies its confirmed-pair list into block `rank` of every rank's list
+ * array through NVLink peer mappings (symmetric memory: peer_lists[q] / peer_flags[q] = rank q's array / flag words as
+ * mapped on this GPU, own rank included; device arrays of `world` addresses), sized on the device from the list's own
+ * header, then raises flags[rank] = epoch on every rank (system-scope release).  tsc_elim_fused_p2p is tsc_elim_fused
+ * on such an array: block l is read after flags[l] == epoch (status word 3 if a flag does not arrive within ~2 s).
+ * Use two arrays alternately (a rank may be one call ahead of its peers). */
+int tsc_pairs_push(const int32_t* local_list, int64_t stride, void* const* peer_lists, void* const* peer_flags,
+                   int32_t rank, int32_t world, int32_t epoch, void* stream);
+int tsc_elim_fused_p2p(const int32_t* lists, int32_t n_lists, int64_t stride, int64_t N, int32_t gate, int32_t* ws,
+                       uint8_t* out, const int32_t* flags, int32_t epoch, void* stream);
 
 /* ---- prune_conformers_tfd / prune_by_moment_of_inertia (run right before the RMSD prune, embedder.py:1325-1352) */
 /* Torsion fingerprints (numba_functions.py:233-239, 258-268; dihedral of algebra.py:24-57): tf (N, Q) float32

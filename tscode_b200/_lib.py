@@ -38,6 +38,8 @@ SIGNATURES = {
     "tsc_elim_fused_ws_words": (_i64, [_i64]),
     "tsc_elim_fused_out_bytes": (_i64, [_i64]),
     "tsc_elim_fused": (C.c_int, [_vp, _i32, _i64, _i64, _i32, _vp, _vp, _vp]),
+    "tsc_elim_fused_p2p": (C.c_int, [_vp, _i32, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _vp]),
+    "tsc_pairs_push": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _vp]),
     "tsc_rmsd_pairs": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "tsc_rmsd_pairs_idx": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _f64, _vp, _vp]),
     "tsc_group_greedy": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),

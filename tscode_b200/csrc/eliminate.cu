@@ -189,6 +189,9 @@ struct ElimFusedParams {
     int n_ladder;
     int gate;
     int64_t ladder[EF_MAX_LADDER];
+    // several ranks, peer-written lists (tsc_pairs_push): block l of `lists` is complete once flags[l] == epoch
+    const int32_t* flags;     // NULL: the lists are complete at launch
+    int32_t epoch;
 };
 
 __device__ __forceinline__ long long globaltimer_ns() {
@@ -274,6 +277,28 @@ __global__ void __launch_bounds__(EF_THREADS, 1) elim_fused_kernel(const ElimFus
     int n_stamp = 0;
 #define EF_STAMP() do { if (gtid == 0 && n_stamp < 30) info[32 + n_stamp] = (int32_t)(globaltimer_ns() - t_start); n_stamp++; } while (0)
 
+    // ---- peer-written lists: wait until every rank has published its block (system-scope acquire; bounded) ----
+    if (p.flags) {
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            int ok = 1;
+            for (int l = 0; l < p.n_lists && ok; l++) {
+                uint32_t spins = 0;
+                while (true) {
+                    int32_t v;
+                    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p.flags + l) : "memory");
+                    if (v == p.epoch) break;
+                    if ((++spins & 63u) == 0u && clock64() - t0 > EF_SPIN_LIMIT) { ok = 0; break; }
+                }
+            }
+            s_flag = ok;
+        }
+        __syncthreads();
+        if (!s_flag) {
+            if (gtid == 0) { info[1] = 0; __threadfence(); info[0] = 3; }      // 3: a peer never published its list
+            return;
+        }
+    }
     // ---- overflow check (uniform: every thread reads the same headers) ----
     bool overflow = false;
     for (int l = 0; l < p.n_lists; l++) {
@@ -487,8 +512,67 @@ extern "C" int64_t tsc_elim_fused_ws_words(int64_t N) {
 
 extern "C" int64_t tsc_elim_fused_out_bytes(int64_t N) { return ((N + 3) / 4) * 4 + 64 * 4; }
 
+static int elim_fused_impl(const int32_t* lists, int32_t n_lists, int64_t stride, int64_t N, int32_t gate, int32_t* ws,
+                           uint8_t* out, const int32_t* flags, int32_t epoch, void* stream);
+
 extern "C" int tsc_elim_fused(const int32_t* lists, int32_t n_lists, int64_t stride, int64_t N, int32_t gate,
                               int32_t* ws, uint8_t* out, void* stream) {
+    return elim_fused_impl(lists, n_lists, stride, N, gate, ws, out, nullptr, 0, stream);
+}
+
+// The same on lists that the ranks write into each other's memory (tsc_pairs_push): block l is read only after
+// flags[l] (device memory of THIS rank, written by rank l) holds `epoch`.  Status 3 in the info words: a flag never
+// arrived within ~2 s.
+extern "C" int tsc_elim_fused_p2p(const int32_t* lists, int32_t n_lists, int64_t stride, int64_t N, int32_t gate,
+                                  int32_t* ws, uint8_t* out, const int32_t* flags, int32_t epoch, void* stream) {
+    if (!flags) return (int)cudaErrorInvalidValue;
+    return elim_fused_impl(lists, n_lists, stride, N, gate, ws, out, flags, epoch, stream);
+}
+
+namespace tsc {
+// rank `rank` copies its confirmed-pair list (header = count, then the pairs) into block `rank` of every peer's
+// list array; peer_lists[q] = base address of rank q's array as seen from this GPU (NVLink peer mapping)
+__global__ void __launch_bounds__(256) pairs_push_kernel(const int2* __restrict__ local, int64_t stride,
+                                                         int2* const* __restrict__ peer_lists, int rank, int world) {
+    const int64_t cnt = local[0].x;
+    const int64_t n = (cnt < 0 || cnt > stride - 1) ? 0 : cnt;                 // overflowed: only the header travels
+    const int64_t total = (n + 1) * world;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int q = (int)(t / (n + 1));
+        const int64_t e = t - (int64_t)q * (n + 1);
+        peer_lists[q][(int64_t)rank * stride + e] = local[e];
+    }
+}
+// after the copies (stream order): flags of block `rank` on every peer <- epoch, released at system scope
+__global__ void pairs_flag_kernel(int32_t* const* __restrict__ peer_flags, int rank, int world, int32_t epoch) {
+    const int q = threadIdx.x;
+    if (q < world) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(peer_flags[q] + rank), "r"(epoch) : "memory");
+    }
+}
+}  // namespace tsc
+
+// All-gather of the confirmed-pair lists by peer writes, sized on the device: local_list (header + pairs, this rank's
+// verify output) -> block `rank` of every rank's list array, then flags[rank] <- epoch on every rank.  peer_lists /
+// peer_flags: device arrays of `world` addresses (symmetric-memory mappings, the own rank included).  Nothing is read
+// back; tsc_elim_fused_p2p waits for the flags.
+extern "C" int tsc_pairs_push(const int32_t* local_list, int64_t stride, void* const* peer_lists,
+                              void* const* peer_flags, int32_t rank, int32_t world, int32_t epoch, void* stream) {
+    using namespace tsc;
+    if (world <= 0 || world > 64 || rank < 0 || rank >= world || !local_list || !peer_lists || !peer_flags)
+        return (int)cudaErrorInvalidValue;
+    cudaStream_t st = (cudaStream_t)stream;
+    pairs_push_kernel<<<148, 256, 0, st>>>(reinterpret_cast<const int2*>(local_list), stride,
+                                           reinterpret_cast<int2* const*>(peer_lists), rank, world);
+    TSC_CHECK_LAUNCH();
+    pairs_flag_kernel<<<1, 64, 0, st>>>(reinterpret_cast<int32_t* const*>(peer_flags), rank, world, epoch);
+    TSC_CHECK_LAUNCH();
+    return 0;
+}
+
+static int elim_fused_impl(const int32_t* lists, int32_t n_lists, int64_t stride, int64_t N, int32_t gate, int32_t* ws,
+                           uint8_t* out, const int32_t* flags, int32_t epoch, void* stream) {
     using namespace tsc;
     if (N <= 0) return 0;
     static const int64_t LADDER[18] = {500000, 200000, 100000, 50000, 20000, 10000, 5000, 2000, 1000,
@@ -502,6 +586,8 @@ extern "C" int tsc_elim_fused(const int32_t* lists, int32_t n_lists, int64_t str
     p.out = out;
     p.n_ladder = 18;
     p.gate = gate;
+    p.flags = flags;
+    p.epoch = epoch;
     for (int i = 0; i < 18; i++) p.ladder[i] = LADDER[i];
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)(2 * ((N + 31) / 32 + 2) + 2 * EF_SMEM_CHUNKS) * 4;

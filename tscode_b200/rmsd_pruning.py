@@ -70,6 +70,64 @@ UPLOAD_CHUNKS = 8       # pieces a host ensemble is uploaded in (_upload_pack_sc
 HOST_GATHER_SHARE = 0.45     # part of structures[mask] taken from the caller's host array while the rest comes over PCIe
 
 
+class _PeerLists:
+    """Several ranks: the confirmed-pair lists are exchanged WITHOUT a collective.  One symmetric-memory allocation per
+    (group, world, list capacity) holds two list arrays (world blocks each) and two rows of flags; every rank maps every
+    peer's copy over NVLink (torch.distributed._symmetric_memory) and, after its verify kernels, pushes its own list into
+    block `rank` of every rank's array with plain stores, sized on the device from the list's header, then raises its
+    flag on every rank (eliminate.cu: tsc_pairs_push); the ladder kernel of every rank waits for all flags
+    (tsc_elim_fused_p2p).  The arrays alternate from call to call because a rank can be one call ahead of its peers.
+    Creation is collective (rendezvous + an agreement on whether it worked); if symmetric memory is not available on any
+    rank, all ranks use the NCCL all-gather instead."""
+    _cache = {}
+    enabled = True
+
+    @classmethod
+    def get(cls, group, rank, world, stride, device):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return None
+        g = group if group is not None else dist.group.WORLD
+        key = (id(g), world, int(stride), str(device))
+        obj = cls._cache.pop(key, None)
+        if obj is None:
+            obj = cls(g, rank, world, int(stride), device)
+        cls._cache[key] = obj                             # most recently used last
+        while len(cls._cache) > 4:                        # (the same sequence on every rank: constructors run in step)
+            cls._cache.pop(next(iter(cls._cache)))
+        return obj if obj.ok else None
+
+    def __init__(self, group, rank, world, stride, device):
+        import torch
+        import torch.distributed as dist
+        self.ok, self.err, self.calls = False, None, 0
+        n_list = world * stride * 2                       # int32 words of one list array
+        try:
+            if not self.enabled:
+                raise RuntimeError("disabled")
+            import torch.distributed._symmetric_memory as symm
+            with torch.cuda.device(device):
+                self.buf = symm.empty(2 * n_list + 128, dtype=torch.int32, device=device)
+                self.buf.zero_()
+                torch.cuda.current_stream().synchronize()
+                self.hdl = symm.rendezvous(self.buf, group)
+                ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+                assert len(ptrs) == world
+                self.peer_lists = [torch.tensor([p + 4 * par * n_list for p in ptrs], dtype=torch.int64, device=device)
+                                   for par in (0, 1)]
+                self.peer_flags = [torch.tensor([p + 4 * (2 * n_list + 64 * par) for p in ptrs], dtype=torch.int64,
+                                                device=device) for par in (0, 1)]
+                self.lists = [self.buf[par * n_list:(par + 1) * n_list].view(world * stride, 2) for par in (0, 1)]
+                self.flags = [self.buf[2 * n_list + 64 * par:2 * n_list + 64 * par + 64] for par in (0, 1)]
+            good = 1
+        except Exception as e:                            # no symmetric memory here: every rank falls back together
+            self.err = repr(e)
+            good = 0
+        t = torch.tensor([good], dtype=torch.int32, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)       # (also orders the zeroing before any peer write)
+        self.ok = bool(int(t.item()))
+
+
 def _upload_bounds(N, n_chunks=UPLOAD_CHUNKS):
     """Panel boundaries of the upload chunks: chunk c = panels [b[c], b[c+1])."""
     n_panels = (N + 127) // 128
@@ -241,6 +299,9 @@ class RmsdPruner:
             self.pair_list = torch.zeros((self.pair_stride, 2), dtype=torch.int32, device=dev)
             self.pair_all = (torch.zeros((self.world * self.pair_stride, 2), dtype=torch.int32, device=dev)
                              if self.world > 1 else self.pair_list)
+            # peer-written lists (no collective) when symmetric memory is available; else the NCCL all-gather below
+            self._peer = (_PeerLists.get(self.group, self.rank, self.world, self.pair_stride, dev)
+                          if (self.world > 1 and self.ladder == "fused") else None)
             self.pair_stride_small = min(self.pair_stride, 8 * N // self.world + 2048 + 1)
             self.pair_all_small = (torch.zeros((self.world * self.pair_stride_small, 2), dtype=torch.int32, device=dev)
                                    if self.world > 1 else self.pair_list)
@@ -404,6 +465,20 @@ class RmsdPruner:
         L = lib()
         stride = self.pair_stride_small if (tier == "small" and self.world > 1) else self.pair_stride
         with torch.cuda.device(self.device):
+            if self.world > 1 and self._peer is not None:
+                pl = self._peer
+                pl.calls += 1
+                epoch, par = pl.calls, pl.calls & 1
+                check(L.tsc_pairs_push(ptr(self.pair_list), self.pair_stride, ptr(pl.peer_lists[par]),
+                                       ptr(pl.peer_flags[par]), self.rank, self.world, epoch, stream_ptr()), "tsc_pairs_push")
+                rc = L.tsc_elim_fused_p2p(ptr(pl.lists[par]), self.world, self.pair_stride, self.N, 20, ptr(self.fused_ws),
+                                          ptr(self.fused_out), ptr(pl.flags[par]), epoch, stream_ptr())
+                if rc == 1:
+                    self._fused_enqueued = "unavailable"
+                    return
+                check(rc, "tsc_elim_fused_p2p")
+                self._fused_enqueued = "full"
+                return
             if self.world > 1:
                 import torch.distributed as dist
                 if stride == self.pair_stride:
@@ -447,7 +522,8 @@ class RmsdPruner:
             # profiler or pre-emption).  Either way the bit-row ladder decides (same decision on every rank: all see
             # the same headers; an abort on one rank only would desynchronise the ranks' collectives, so it raises)
             if info[0] != 1 and self.world > 1:
-                raise RuntimeError(f"tsc_elim_fused did not complete (status {info[0]})")
+                raise RuntimeError(f"tsc_elim_fused did not complete (status {info[0]}"
+                                   + (": a peer never published its pair list)" if info[0] == 3 else ")"))
             return None
         self._rounds_fused = [int(k) for k in info[8:8 + info[1]]]
         self.ladder_used = "fused"
