@@ -29,6 +29,20 @@ for r in gold:
     if rank == 0:
         print(f"world={world} N={r['N']} M={r['M']} survivors={int(mask.sum())} digest={mask_digest(mask)} "
               f"{'OK' if good else 'MISMATCH'} rounds={pr.rounds}", flush=True)
+# ---- an overflowing pair list (tiny capacity): every rank sees the same headers and takes the bit-row ladder ----
+r = [x for x in gold if x["N"] == 2000][0]
+S = gen_ensemble(r["seed"], r["N"], r["M"], r["n_clusters"], sigma_noise=r["sigma_noise"])
+for rep in range(3):                                    # (repeated: the peer-written arrays alternate between calls)
+    pr = RmsdPruner(S, np.full(r["M"], 6), r["thr"], rank=rank, world=world, pair_cap=64)
+    mask = pr.run().cpu().numpy()
+    good = mask_digest(mask) == r["digest"] and pr.ladder_used == "bitrows"
+    ok &= good
+    pr2 = RmsdPruner(S, np.full(r["M"], 6), r["thr"], rank=rank, world=world)
+    good2 = mask_digest(pr2.run().cpu().numpy()) == r["digest"] and pr2.ladder_used == "fused"
+    ok &= good2
+    if rank == 0:
+        print(f"world={world} overflowing pair list -> {pr.ladder_used}: {'OK' if good else 'MISMATCH'}; then fused again: "
+              f"{'OK' if good2 else 'MISMATCH'} (peer lists: {pr2._peer is not None})", flush=True)
 # ---- the public drop-in with a process group: sharded upload, full mask, survivors of the rank's row slice ----
 from tscode_b200.rmsd_pruning import prune_conformers_rmsd  # noqa: E402
 r = [x for x in gold if x["N"] == 10000][0]
