@@ -48,6 +48,23 @@ def test_sass_uses_dmma_and_bulk_tma():
     assert "DFMA" in sass
 
 
+def test_sass_of_the_default_screen_uses_tcgen05_tmem_and_bulk_copies():
+    """The default screen is a tcgen05 kernel: UTCHMMA (tcgen05.mma kind::f16), TMEM loads / stores (LDTM / STTM),
+    tcgen05.commit (UTCBAR), bulk copies (UBLKCP), packed FP32 arithmetic (FFMA2) and the staged column terms
+    (LDGSTS = cp.async) — for every instantiated form."""
+    from tscode_b200.csrc import build
+    so = build.build()
+    for mode, J in ((0, 48), (1, 32), (2, 32), (0, 64)):
+        fn = f"_ZN3tsc18rmsd_screen_kernelILi{mode}ELi{J}EEEvNS_8ScParamsE"
+        sass = subprocess.run(["cuobjdump", "-sass", "-fun", fn, so], capture_output=True, text=True).stdout
+        for mnemonic in ("UTCHMMA", "LDTM.x8", "STTM.x4", "UTCBAR", "UBLKCP", "FFMA2"):
+            assert mnemonic in sass, (mode, J, mnemonic)
+        if mode == 0:
+            assert "LDGSTS" in sass
+        if mode != 0:
+            assert "FMNMX3.NAN" in sass and "MUFU.SQRT" in sass        # the quartic stage's lean decision and root
+
+
 def test_product_has_no_oracle_or_cpu_fallback():
     for root, _, files in os.walk(os.path.join(ROOT, "tscode_b200")):
         for f in files:
