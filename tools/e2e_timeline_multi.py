@@ -29,7 +29,6 @@ for rep in range(8):
     torch.cuda.synchronize(); dist.barrier()
     t = [time.perf_counter()]
     pr = RmsdPruner(S, atomnos, 0.5, rank=rank, world=world, group=g); t.append(time.perf_counter())
-    pr._upload_sharded_probe = True
     pr.run_async(); t.append(time.perf_counter())
     torch.cuda.current_stream().synchronize(); t.append(time.perf_counter())
     lo, hi = pr.row_slice()

@@ -297,14 +297,12 @@ class RmsdPruner:
             cap = int(pair_cap) if pair_cap is not None else 32 * N // self.world + 4096
             self.pair_stride = cap + 1
             self.pair_list = torch.zeros((self.pair_stride, 2), dtype=torch.int32, device=dev)
-            self.pair_all = (torch.zeros((self.world * self.pair_stride, 2), dtype=torch.int32, device=dev)
-                             if self.world > 1 else self.pair_list)
-            # peer-written lists (no collective) when symmetric memory is available; else the NCCL all-gather below
+            # peer-written lists (no collective) when symmetric memory is available; else the NCCL all-gather, whose
+            # landing buffers are only allocated if it is ever used (_enqueue_fused)
             self._peer = (_PeerLists.get(self.group, self.rank, self.world, self.pair_stride, dev)
                           if (self.world > 1 and self.ladder == "fused") else None)
             self.pair_stride_small = min(self.pair_stride, 8 * N // self.world + 2048 + 1)
-            self.pair_all_small = (torch.zeros((self.world * self.pair_stride_small, 2), dtype=torch.int32, device=dev)
-                                   if self.world > 1 else self.pair_list)
+            self.pair_all = self.pair_all_small = self.pair_list if self.world == 1 else None
             # candidate list the tcgen05 screens append to (local row, j); verify works from it
             self.cand_stride = (int(cand_cap) if cand_cap is not None else 64 * N // self.world + 8192) + 1
             self.cand_list = torch.zeros((self.cand_stride, 2), dtype=torch.int32, device=dev)
@@ -481,6 +479,10 @@ class RmsdPruner:
                 return
             if self.world > 1:
                 import torch.distributed as dist
+                if self.pair_all is None:
+                    self.pair_all = torch.zeros((self.world * self.pair_stride, 2), dtype=torch.int32, device=self.device)
+                    self.pair_all_small = torch.zeros((self.world * self.pair_stride_small, 2), dtype=torch.int32,
+                                                      device=self.device)
                 if stride == self.pair_stride:
                     lists = self.pair_all
                     dist.all_gather_into_tensor(lists, self.pair_list, group=self.group)
