@@ -113,6 +113,24 @@ int hm_q32t_excluded(const float* S, float lam, double* lam_max) {
     return tsc::quartic32_T_excluded(t, lam) ? 1 : 0;
 }
 
+// the same with a SCALED column side (rmsd_screen.cu, ScFrame): the accumulators hold S^ = S diag(t) (here: the float
+// products s_ab * t_b, rounded — the MMA's own sums of FP16 products are exact to within the operand bound), T^ is
+// accumulated from its rows, un-scaled entry by entry with the float constants 1 / (t_b t_c) as the kernel does, and the
+// quartic runs on that T.  lam_max is that of the UNscaled float covariance in FP64.
+int hm_q32t_excluded_scaled(const float* S, const double* t3, float lam, double* lam_max) {
+    double Sd[9];
+    for (int q = 0; q < 9; q++) Sd[q] = S[q];
+    double qv[4], gap;
+    *lam_max = tsc::key_top_eigen(tsc::key_matrix(Sd), qv, &gap);
+    float Ss[9], t[6];
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) Ss[3 * a + b] = (float)((double)S[3 * a + b] * t3[b]);
+    tsc::quartic32_T_from_rows(Ss, t);
+    const int bb[6] = {0, 1, 2, 0, 0, 1}, cc[6] = {0, 1, 2, 1, 2, 2};
+    for (int q = 0; q < 6; q++) t[q] = tsc::OpsF32::mul(t[q], (float)(1.0 / (t3[bb[q]] * t3[cc[q]])));
+    return tsc::quartic32_T_excluded(t, lam) ? 1 : 0;
+}
+
 // d = the bound on |det S| the T form uses (before the 1 + 4u scale), next to |det S| in long double, and f
 void hm_q32t_det(const float* S, int n, double* out) {
     for (int k = 0; k < n; k++) {

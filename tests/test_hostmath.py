@@ -250,6 +250,7 @@ def test_f16_prescreen_model_never_loses_a_similar_pair(hm, case):
 def hmt(hm):
     hm.hm_q32t_excluded.argtypes = [_fp, C.c_float, C.POINTER(C.c_double)]
     hm.hm_q32t_det.argtypes = [_fp, C.c_int, _dp]
+    hm.hm_q32t_excluded_scaled.argtypes = [_fp, _dp, C.c_float, C.POINTER(C.c_double)]
     return hm
 
 
@@ -373,3 +374,34 @@ def test_screen_model_T_form_never_loses_a_similar_pair(hmt, case):
     assert lost == 0
     assert excluded > 0.9 * dissimilar or case["noise"] >= 0.2, (excluded, dissimilar)
     print(case, "stage 2 ran for", stage2, "of", N * (N - 1) // 2, "pairs; excluded", excluded, "of", dissimilar)
+
+
+def test_fp32_T_form_with_scaled_columns_stays_sound(hmt):
+    """ScFrame: the column-side operand is scaled per axis and the quartic stage un-scales T^ = diag(t) T diag(t) with
+    float constants before it runs (one more rounding per entry: 5 u instead of 3 u, inside the doubled tolerances,
+    tsc_math.cuh).  For weights as _host.screen_frame produces them (elongated, planar, rod, extreme) the stage must
+    never exclude a pair whose lambda_max reaches the test point, and must still exclude clearly separated ones."""
+    rng = np.random.default_rng(11)
+    lm = C.c_double()
+    shapes = ([6.0, 2.0, 1.0], [4.0, 4.0, 0.5], [8.0, 1.0, 1.0], [1.0, 1.0, 1.0], [30.0, 1.0, 0.3])
+    excluded = total = 0
+    for sc in shapes:
+        lam3 = np.maximum(np.array(sc) ** 2, 1e-4 * float(np.sum(np.array(sc) ** 2)))
+        w = lam3.sum() / lam3 * (1 + 1e-9)
+        t3 = np.ascontiguousarray(np.sqrt(w / 3.0))
+        assert (1.0 / w).sum() <= 1.0
+        base = rng.normal(size=(60, 3)) * np.array(sc)
+        for k in range(400):
+            P = base + rng.normal(size=base.shape) * rng.choice([0.05, 0.5, 2.0])
+            Q = base + rng.normal(size=base.shape) * rng.choice([0.05, 0.5, 2.0])
+            S = np.ascontiguousarray((P.T @ Q).reshape(9), dtype=np.float32)
+            hmt.hm_q32t_excluded_scaled(S, t3, 1.0, C.byref(lm))
+            top = lm.value
+            if not np.isfinite(top) or top <= 0:
+                continue
+            for rel in (-0.3, -1e-2, -1e-4, -1e-6, 0.0):
+                assert hmt.hm_q32t_excluded_scaled(S, t3, float(np.float32(top * (1 + rel))), C.byref(lm)) == 0
+            total += 1
+            excluded += hmt.hm_q32t_excluded_scaled(S, t3, float(np.float32(top * 1.01)), C.byref(lm))
+    # (screening power: not sharp for the heavily perturbed pairs, whose det S can be negative — weaker by design)
+    assert excluded > 0.5 * total, (excluded, total)

@@ -216,6 +216,12 @@ TSC_HD void quartic32_values(const typename O::T* S, typename O::T f, typename O
 // the addition under the root; arguments below 2^-126 give 0, see quartic32_decide).  P and P' take -8 d through the same Horner steps as before, so the forward-error
 // tolerances of quartic32_margins (which even include an allowance for c1's own rounding) stay valid.
 // ------------------------------------------------------------------------------------------
+// With a scaled column side (rmsd_screen.cu, ScFrame) the kernel accumulates T^ = diag(t) T diag(t) and multiplies every
+// entry by the float constant 1 / (t_b t_c) before this stage: one more rounding of the constant and one of the product,
+// i.e. entries with 5 u instead of 3 u of relative error.  The budgets above scale accordingly — p4: 17 u f^2, c0: 57 u
+// s^4 <= 3.6 u rho^4 (total for P still < 30 u rho^4 against the 64 u R^2 tolerance), the Leibniz terms of det T:
+// 3.3 u f^3 + u f^3 of evaluation = 4.3 u f^3 against the 8 u f^3 margin — and stay inside the tolerances
+// (tests/test_hostmath.py: test_fp32_T_form_with_scaled_columns_stays_sound).
 constexpr float Q32_DET_MARGIN = 4.77e-7f;    // 8 u
 constexpr float Q32_C1_SCALE = -8.000004f;    // -8 (1 + 4 u), rounded away from zero
 
