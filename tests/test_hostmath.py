@@ -405,3 +405,70 @@ def test_fp32_T_form_with_scaled_columns_stays_sound(hmt):
             excluded += hmt.hm_q32t_excluded_scaled(S, t3, float(np.float32(top * 1.01)), C.byref(lm))
     # (screening power: not sharp for the heavily perturbed pairs, whose det S can be negative — weaker by design)
     assert excluded > 0.5 * total, (excluded, total)
+
+
+def _f32_dir(x, up):
+    """float32 rounding of a float64 towards +inf (up) or -inf."""
+    y = np.float32(x)
+    if up and float(y) < x:
+        y = np.nextafter(y, np.float32(np.inf))
+    if (not up) and float(y) > x:
+        y = np.nextafter(y, np.float32(-np.inf))
+    return y
+
+
+def test_weighted_samuelson_stage_with_fp16_operands_never_excludes_a_similar_pair():
+    """numpy model of the whole first stage as rmsd_screen.cu runs it with a frame (ScFrame): rotate, scale the column
+    side, round both sides to FP16 (flush below 2^-14), covariance from the rounded operands, f^ = ||S^~||_F^2 in float32,
+    directed-rounded row / column constants, lf = A_i + B_j - C_i D_j, excluded iff lf > 0 and 3.00004 f^ < lf^2.  Pairs
+    are generated AROUND the similarity threshold (where a wrong exclusion would change the mask) for several shapes;
+    an excluded pair must have lambda_max below the true threshold eigenvalue (float64 SVD of the unrounded data)."""
+    from tscode_b200 import _host
+    rng = np.random.default_rng(5)
+    eps, thr = 1.05e-3, 0.5
+    n_excl = n_tot = 0
+    for sc in ([3.0, 3.0, 3.0], [6.0, 2.0, 1.0], [4.0, 4.0, 0.5], [8.0, 1.0, 1.0], [20.0, 0.5, 0.2]):
+        for M in (12, 40, 80):
+            base = rng.normal(size=(M, 3)) * np.array(sc)
+            R0, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+            base = base @ R0.T                                        # arbitrary orientation: the frame has to find it
+            fr, _ = _host.screen_frame(base)
+            Q, t = fr[:9].reshape(3, 3), fr[9:]
+            e_thr = M * thr * thr * (1 + 1e-6)
+            for k in range(300):
+                s = rng.choice([0.1, 0.3, 0.42, 0.5, 0.6, 1.0])      # per-atom noise: rmsd from well below to above thr
+                P = base + rng.normal(size=base.shape) * 0.05
+                Y = P + rng.normal(size=base.shape) * s / np.sqrt(3.0)
+                # ---- pack ----
+                Pa, Yb = P @ Q.T, (Y @ Q.T) * t
+                ha = Pa.astype(np.float16).astype(np.float64); ha[np.abs(Pa) < 2.0 ** -14] = 0.0
+                hb = Yb.astype(np.float16).astype(np.float64); hb[np.abs(Yb) < 2.0 ** -14] = 0.0
+                tiny_a = int(((Pa != 0) & (np.abs(Pa) < 2.0 ** -14)).sum())
+                tiny_b = int(((Yb != 0) & (np.abs(Yb) < 2.0 ** -14)).sum())
+                Gi, Gj = float((P ** 2).sum()), float((Y ** 2).sum())
+                alpha = 2.0 ** -14 * (1 + 2.0 ** -10) / eps
+                sg_i = np.sqrt(Gi) * (1 + 1e-12) + alpha * np.sqrt(tiny_a)
+                sgb = np.sqrt(float((Yb ** 2).sum())) * (1 + 1e-12) + alpha * np.sqrt(tiny_b)
+                sgu = np.sqrt(Gj) * (1 + 1e-12) + alpha / t.min() * np.sqrt(tiny_b)
+                sg_j_row = np.sqrt(Gj) * (1 + 1e-12)
+                hs = 0.5 * (1 - 1e-10)
+                A = _f32_dir(hs * Gi - 0.5 * e_thr, up=False)
+                Cc = _f32_dir(np.sqrt(3.0) * eps * sg_i, up=True)
+                B = _f32_dir(hs * Gj, up=False)
+                D = _f32_dir(max(sg_j_row, sgb, sgu), up=True)
+                # ---- kernel ----
+                S32 = (ha.T @ hb).astype(np.float32)                  # FP32 accumulators (products of FP16 values)
+                f = np.float32(0)
+                for v in S32.ravel():
+                    f = np.float32(f + np.float32(v * v))
+                ab = np.float32(A + B)
+                lf = np.float32(np.float64(ab) - np.float64(Cc) * np.float64(D))        # one rounding: fma
+                tv = np.float32(np.float64(np.float32(3.00004)) * np.float64(f) - np.float64(np.float32(lf * lf)))
+                excluded = bool(lf > 0 and tv < 0)
+                # ---- truth ----
+                sv = np.linalg.svd(P.T @ Y, compute_uv=False)
+                lam_max = sv[0] + sv[1] + (sv[2] if np.linalg.det(P.T @ Y) >= 0 else -sv[2])
+                lam_true = 0.5 * (Gi + Gj - M * thr * thr)
+                assert not (excluded and lam_max >= lam_true), (sc, M, s, lam_max, lam_true)
+                n_excl += excluded; n_tot += 1
+    assert 0.05 * n_tot < n_excl < n_tot                             # the stage does exclude, and not everything
