@@ -18,18 +18,22 @@
 //     128 x 56 pairs.  The first-generation kernel (rows = conformers i, columns = (a, b, j) for 16 conformers j,
 //     three MMAs of N = 48 per K block, three 144-column buffers) was therefore stuck at N = 48: 38 % tensor-pipe
 //     activity, 0.48 of the dense 16-bit peak on BASELINE configs[2].
-// Here one accumulator buffer holds ONE ROW a of the covariances of a 128 x 32 tile:  D[i, (b, j)] = sum_m
-// x_a(i, m) x_b(j, m), one MMA of N = 96 per K block, 96 columns; four buffers (384 columns) next to up to 5 K
-// blocks of the stationary panel (120 columns).  The three rows of a tile are three independent chains, each issued
-// by its own thread at a fixed pace, so that three chains are in flight while the epilogue drains the fourth buffer.  The epilogue never sees the nine entries together: per pair it keeps T = S~^T S~ (six
-// numbers, the sum of the outer products of the rows) in registers across the three buffers of a tile, and both
-// exclusion tests work from T alone (f = tr T; quartic coefficients c2 = -2 f, c0 = 2 ||T||_F^2 - f^2, and
+// Here one accumulator buffer holds ONE ROW a of the covariances of a 128 x J tile:  D[i, (b, j)] = sum_m
+// x_a(i, m) x_b(j, m), one MMA of N = 3 J per K block.  The three rows of a tile are three independent chains, each
+// issued by its own thread, so that several chains are in flight while the epilogue drains a buffer.  The epilogue never
+// sees the nine entries together: per pair it keeps f = ||S~||_F^2 (mode 0) or T = S~^T S~ (six numbers, the sum of the
+// outer products of the rows; modes 1 / 2) in registers across the three buffers of a tile, and both exclusion tests
+// work from those alone (f = tr T; quartic coefficients c2 = -2 f, c0 = 2 ||T||_F^2 - f^2, and
 // |det S~| <= sqrt(det T + margin) in place of the signed determinant: tsc_math.cuh, quartic32_T_*).
+// Three tilings (template parameter J, table below): J = 48 with THREE buffers, one per row a, so that every row's MMAs
+// may start a whole tile ahead of the epilogue (mode 0: with two buffers of J = 64 the per-tile final stage outlasted
+// the look-ahead and the tensor pipe idled, profiles/r02_ncu_kernels.md); J = 32 with four rotating buffers for the
+// T-accumulating modes (six numbers per pair: 8 columns per thread); J = 64 kept for comparison.
 //
-// Roles (one persistent CTA per SM, 20 warps): warp 0 producer (bulk-TMA ring of B tiles, tail of the panel for
-// K blocks beyond the 5 held in TMEM), warps 1..3 MMA issue (one elected thread each, one per row of the
-// covariances; warp 1 also owns the TMEM allocation), warps 4..19 epilogue: TMEM lane quarter = warp % 4, and the
-// four warps of a quarter split the 32 columns of a tile.
+// Roles (one persistent CTA per SM): warp 0 producer (bulk-TMA ring of B tiles, tail of the panel for the K blocks
+// beyond those held in TMEM), warps 1..3 MMA issue (one elected thread each, one per row of the covariances; warp 1
+// also owns the TMEM allocation), the remaining 12 (J = 48) or 16 warps epilogue: TMEM lane quarter = warp % 4, and the
+// warps of a quarter split the columns of a tile.
 #include <cuda_fp16.h>
 #include "screen_common.cuh"
 
