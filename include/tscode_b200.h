@@ -96,6 +96,13 @@ int tsc_rmsd_screen(const void* PA, const void* PB, const void* PR, const double
  *   molecules as Samuelson's is for isotropic ones (rmsd_screen.cu, ScFrame).  NULL = identity = Samuelson.  The same
  *   frame must be given to tsc_pack_screen and tsc_rmsd_screen; both return cudaErrorInvalidValue (1) when Q is not
  *   orthogonal to 1e-13 or the scales violate the inequality — the conditions exclusion rests on. */
+/* The reference's survivor choice inside one chunk of a grouping loop (torsion_module.py:1136-1152,
+ * numba_functions.py:203-220, optimization_methods.py:341-355: `nx.Graph(matches)`, connected components, keep
+ * group[0]) in native host code, with CPython's set / dict iteration orders restated exactly — which member is
+ * group[0] depends on them (capi.cu).  mi, mj (n): the matches (chunk-relative, i < j, insertion order);
+ * n_nodes_max: chunk length; rejects: the members not kept.  Returns their number (-1: bad arguments). */
+int64_t tsc_host_cluster_rejects(const int32_t* mi, const int32_t* mj, int64_t n, int64_t n_nodes_max, int32_t* rejects);
+
 /* Host-side plan of the screen (capi.cu; no GPU involved): tsc_host_sample_pairs fills K fixed pseudo-random pairs
  * i != j of [0, N); tsc_host_screen_plan takes the frame from structure `first` of the HOST array S (rows, A, 3) and
  * reports, for the pairs (pi[k], pj[k]) (row numbers of S), the fraction the weighted bound would leave undecided, and

@@ -404,3 +404,49 @@ def test_native_screen_plan_agrees_with_its_numpy_statement():
     assert _host.sample_pair_indices(1)[0].size == 0
     assert _host.plan_mode(1.0, 0.0) == 0 and _host.plan_mode(1.5, 0.0) == 1 and _host.plan_mode(1.0, 0.02) == 1
     assert _host.plan_mode(1.0, 0.5) == 2
+
+
+def test_native_cluster_survivor_choice_equals_python_and_networkx():
+    """capi.cu: tsc_host_cluster_rejects restates CPython's set / dict iteration orders (tuple hash, open-addressing
+    probe sequence, growth policy) to pick the same `group[0]` per connected component as the reference's
+    nx.Graph(set_of_tuples) does.  Against the Python restatement on 1 500 random match sets (sizes across several
+    table growths, both branches of the subgraph-view iteration) and against networkx itself on a tenth of them."""
+    import random
+    from tscode_b200 import torsion_module as tm
+    L = _lib.lib()
+
+    def c_rejects(mi, mj, nmax):
+        mi = np.ascontiguousarray(mi, dtype=np.int32)
+        mj = np.ascontiguousarray(mj, dtype=np.int32)
+        rej = np.empty(max(2 * len(mi), 1), dtype=np.int32)
+        n = L.tsc_host_cluster_rejects(mi.ctypes.data, mj.ctypes.data, len(mi), nmax, rej.ctypes.data)
+        assert n >= 0
+        return sorted(rej[:n].tolist())
+
+    rnd = random.Random(7)
+    cases = 0
+    for trial in range(1500):
+        m = rnd.choice((3, 8, 30, 200, 1000, 6000))
+        mi, mj, seen = [], [], set()
+        if rnd.random() < 0.6:                       # as the replay produces them: rows ascending, one match per row
+            dens = rnd.random()
+            for i in range(m - 1):
+                if rnd.random() < dens:
+                    mi.append(i); mj.append(rnd.randrange(i + 1, m))
+        else:
+            for _ in range(rnd.randrange(1, 3 * m if m < 1000 else m)):
+                a, b = rnd.randrange(m), rnd.randrange(m)
+                if a != b and (min(a, b), max(a, b)) not in seen:
+                    seen.add((min(a, b), max(a, b))); mi.append(min(a, b)); mj.append(max(a, b))
+        if not mi:
+            continue
+        matches = set(zip(mi, mj))
+        got = c_rejects(mi, mj, m)
+        assert got == sorted(tm._cluster_rejects_fast(matches)), (m, len(mi))
+        if trial % 10 == 0:
+            assert got == sorted(tm._cluster_rejects_nx(matches)), (m, len(mi))
+        cases += 1
+    assert cases > 1000
+    assert L.tsc_host_cluster_rejects(None, None, 0, 5, None) == 0
+    bad = np.array([7], dtype=np.int32)
+    assert L.tsc_host_cluster_rejects(bad.ctypes.data, bad.ctypes.data, 1, 5, bad.ctypes.data) == -1

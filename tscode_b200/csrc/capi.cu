@@ -292,3 +292,181 @@ extern "C" int tsc_host_screen_plan(const double* S, int32_t A, const int32_t* h
     *undecided = K > 0 ? (double)und / K : 0.0;
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// The reference's survivor choice inside one chunk of a grouping loop (torsion_module.py:1136-1152,
+// numba_functions.py:203-220, optimization_methods.py:341-355):
+//     matches = set of (i, j) tuples;  G = nx.Graph(matches);  for every connected component keep `group[0]`
+// in native code.  WHICH member of a component is group[0] depends on iteration orders of CPython sets and dicts, so
+// this restates them exactly (CPython 3.8+ / networkx 3.x; torsion_module._cluster_rejects_fast is the same in Python
+// and is checked against networkx itself; tests/test_capi_and_host.py compares all three on random graphs):
+//   * a set is an open-addressing table of (hash, key): slot i = hash & mask, then up to 9 linear probes, then
+//     i = (5 i + 1 + (perturb >>= 5)) & mask; it grows when 5 fill >= 3 mask, to the first power of two above 4 used
+//     (2 used beyond 50 000 entries), re-inserting in table order; iteration is table order;
+//   * hash(int) = the value; hash((a, b)) = the xxHash-style tuple hash of Objects/tupleobject.c;
+//   * Graph.add_edges_from inserts nodes in order of first appearance in the edge iteration (dict order), adjacency
+//     in insertion order; components are found in node order by a breadth-first search whose `seen` is a set;
+//   * G.subgraph(c).nodes iterates a NEW set filled from c element by element when 2 |c| < |G|, else the nodes of G in
+//     order, filtered by membership in c (coreviews.FilterAtlas.__iter__).
+// It replaced 0.2 s of Python per BASELINE configs[3] prune (3 900 chunks).
+// ------------------------------------------------------------------------------------------
+namespace {
+struct PySetModel {                       // keys: (a, b) with b = -1 for plain ints
+    std::vector<uint64_t> h;
+    std::vector<int32_t> a, b;
+    std::vector<uint8_t> used_slot;
+    size_t mask = 7, fill = 0;
+    PySetModel() : h(8), a(8), b(8), used_slot(8, 0) {}
+    size_t size() const { return fill; }
+    void insert_clean(std::vector<uint64_t>& nh, std::vector<int32_t>& na, std::vector<int32_t>& nb,
+                      std::vector<uint8_t>& nu, size_t nmask, uint64_t hash, int32_t ka, int32_t kb) const {
+        size_t i = (size_t)hash & nmask;
+        uint64_t perturb = hash;
+        while (true) {
+            size_t j = i;
+            if (!nu[j]) { nh[j] = hash; na[j] = ka; nb[j] = kb; nu[j] = 1; return; }
+            if (i + 9 <= nmask)
+                for (j = i + 1; j <= i + 9; j++)
+                    if (!nu[j]) { nh[j] = hash; na[j] = ka; nb[j] = kb; nu[j] = 1; return; }
+            perturb >>= 5;
+            i = (i * 5 + 1 + (size_t)perturb) & nmask;
+        }
+    }
+    void resize(size_t minused) {
+        size_t newsize = 8;
+        while (newsize <= minused) newsize <<= 1;
+        std::vector<uint64_t> nh(newsize);
+        std::vector<int32_t> na(newsize), nb(newsize);
+        std::vector<uint8_t> nu(newsize, 0);
+        for (size_t s = 0; s <= mask; s++)
+            if (used_slot[s]) insert_clean(nh, na, nb, nu, newsize - 1, h[s], a[s], b[s]);
+        h.swap(nh); a.swap(na); b.swap(nb); used_slot.swap(nu);
+        mask = newsize - 1;
+    }
+    bool contains(uint64_t hash, int32_t ka, int32_t kb) const {
+        size_t i = (size_t)hash & mask;
+        uint64_t perturb = hash;
+        while (true) {
+            int probes = (i + 9 <= mask) ? 9 : 0;
+            size_t j = i;
+            while (true) {
+                if (!used_slot[j]) return false;
+                if (h[j] == hash && a[j] == ka && b[j] == kb) return true;
+                if (probes-- == 0) break;
+                j++;
+            }
+            perturb >>= 5;
+            i = (i * 5 + 1 + (size_t)perturb) & mask;
+        }
+    }
+    void add(uint64_t hash, int32_t ka, int32_t kb) {
+        size_t i = (size_t)hash & mask;
+        uint64_t perturb = hash;
+        while (true) {
+            int probes = (i + 9 <= mask) ? 9 : 0;
+            size_t j = i;
+            bool placed = false;
+            while (true) {
+                if (!used_slot[j]) { h[j] = hash; a[j] = ka; b[j] = kb; used_slot[j] = 1; placed = true; break; }
+                if (h[j] == hash && a[j] == ka && b[j] == kb) return;
+                if (probes-- == 0) break;
+                j++;
+            }
+            if (placed) break;
+            perturb >>= 5;
+            i = (i * 5 + 1 + (size_t)perturb) & mask;
+        }
+        fill++;
+        if (fill * 5 < mask * 3) return;
+        resize(fill > 50000 ? fill * 2 : fill * 4);
+    }
+};
+inline uint64_t py_hash_int(int32_t v) { return (uint64_t)(int64_t)v; }          // (v >= 0 here; hash(-1) is -2 in CPython)
+inline uint64_t py_hash_pair(int32_t x, int32_t y) {
+    const uint64_t P1 = 11400714785074694791ULL, P2 = 14029467366897019727ULL, P5 = 2870177450012600261ULL;
+    uint64_t acc = P5;
+    const uint64_t lanes[2] = {py_hash_int(x), py_hash_int(y)};
+    for (int k = 0; k < 2; k++) {
+        acc += lanes[k] * P2;
+        acc = (acc << 31) | (acc >> 33);
+        acc *= P1;
+    }
+    acc += 2ULL ^ (P5 ^ 3527539ULL);
+    return acc == (uint64_t)-1 ? 1546275796ULL : acc;
+}
+}  // namespace
+
+// mi, mj (n): the chunk's matches (i_rel < j_rel, chunk-relative, in insertion order); n_nodes_max: the chunk length
+// (every index < n_nodes_max).  rejects (>= number of distinct nodes): the members that are NOT kept.  Returns their
+// number, or -1 for bad arguments.
+extern "C" int64_t tsc_host_cluster_rejects(const int32_t* mi, const int32_t* mj, int64_t n, int64_t n_nodes_max,
+                                            int32_t* rejects) {
+    if (n < 0 || n_nodes_max <= 0 || (n > 0 && (!mi || !mj || !rejects))) return -1;
+    if (n == 0) return 0;
+    PySetModel matches;
+    for (int64_t k = 0; k < n; k++) {
+        if (mi[k] < 0 || mj[k] < 0 || mi[k] >= n_nodes_max || mj[k] >= n_nodes_max) return -1;
+        matches.add(py_hash_pair(mi[k], mj[k]), mi[k], mj[k]);
+    }
+    // Graph(matches): nodes in order of first appearance, adjacency in insertion order
+    std::vector<int32_t> node_of;                                // dense index -> node
+    std::vector<int32_t> idx_of((size_t)n_nodes_max, -1);
+    std::vector<std::vector<int32_t>> adj;
+    auto node_index = [&](int32_t v) {
+        if (idx_of[v] < 0) { idx_of[v] = (int32_t)node_of.size(); node_of.push_back(v); adj.emplace_back(); }
+        return idx_of[v];
+    };
+    for (size_t s = 0; s <= matches.mask; s++) {
+        if (!matches.used_slot[s]) continue;
+        const int32_t u = matches.a[s], v = matches.b[s];
+        const int32_t iu = node_index(u);
+        const int32_t iv = node_index(v);
+        bool dup = false;                                        // adj[u][v] = None is idempotent
+        for (int32_t w : adj[iu]) dup = dup || w == v;
+        if (!dup) { adj[iu].push_back(v); if (u != v) adj[iv].push_back(u); }
+    }
+    const size_t n_nodes = node_of.size();
+    std::vector<uint8_t> seen_all(n_nodes, 0), in_comp(n_nodes, 0);
+    int64_t n_rej = 0;
+    std::vector<int32_t> level, next_level, comp;
+    for (size_t q0 = 0; q0 < n_nodes; q0++) {
+        if (seen_all[q0]) continue;
+        const int32_t v0 = node_of[q0];
+        PySetModel seen;
+        seen.add(py_hash_int(v0), v0, -1);
+        next_level.assign(1, v0);
+        while (!next_level.empty()) {
+            level.swap(next_level);
+            next_level.clear();
+            for (int32_t x : level)
+                for (int32_t w : adj[idx_of[x]])
+                    if (!seen.contains(py_hash_int(w), w, -1)) {
+                        seen.add(py_hash_int(w), w, -1);
+                        next_level.push_back(w);
+                    }
+        }
+        // nodes = set(iter(seen)); first = next(iter(nodes)) if 2 |nodes| < |G| else first node of G in nodes
+        comp.clear();
+        PySetModel nodes;
+        for (size_t s = 0; s <= seen.mask; s++)
+            if (seen.used_slot[s]) {
+                nodes.add(seen.h[s], seen.a[s], -1);
+                comp.push_back(seen.a[s]);
+                seen_all[idx_of[seen.a[s]]] = 1;
+                in_comp[idx_of[seen.a[s]]] = 1;
+            }
+        int32_t first = -1;
+        if (2 * comp.size() < n_nodes) {
+            for (size_t s = 0; s <= nodes.mask && first < 0; s++)
+                if (nodes.used_slot[s]) first = nodes.a[s];
+        } else {
+            for (size_t q = 0; q < n_nodes && first < 0; q++)
+                if (in_comp[q]) first = node_of[q];
+        }
+        for (int32_t x : comp) {
+            in_comp[idx_of[x]] = 0;
+            if (x != first) rejects[n_rej++] = x;
+        }
+    }
+    return n_rej;
+}

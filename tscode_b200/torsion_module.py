@@ -479,9 +479,10 @@ def ladder_replay_scan(first_hit, N, best_angles=None, verbose=False, native=Non
         else:                                   # no rotor states (the TFD pruning runs the same loop)
             compact, off, table = np.zeros(1, np.uint64), np.zeros(max(N, 1), np.int64), np.zeros((1, MAX_ANG))
         mi, mj = np.empty(max(N, 1), np.int32), np.empty(max(N, 1), np.int32)
+        rej = np.empty(max(N, 1), np.int32)
         vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-        p_first, p_reach, p_state, p_compact, p_off, p_table, p_mi, p_mj = (vp(a) for a in (
-            first_hit, reach, state, compact, off, table, mi, mj))           # the arrays never move
+        p_first, p_reach, p_state, p_compact, p_off, p_table, p_mi, p_mj, p_rej = (vp(a) for a in (
+            first_hit, reach, state, compact, off, table, mi, mj, rej))      # the arrays never move
     for k in _host.LADDER:
         num_active = int(np.count_nonzero(final_mask))
         if not (k == 1 or 5 * k < num_active):                                     # :1083
@@ -502,8 +503,14 @@ def ladder_replay_scan(first_hit, N, best_angles=None, verbose=False, native=Non
             if native:
                 n = int(L.tsc_host_rotcorr_chunk(base, hi, p_first, p_reach, p_state, T, p_compact, p_off, p_table,
                                                  p_mi, p_mj))
-                if n:                                                              # same insertion order (:1119-1120)
-                    matches = set(zip(mi[:n].tolist(), mj[:n].tolist()))
+                if n:
+                    # survivor choice of the chunk (:1136-1152) in native code as well: CPython's set / dict orders
+                    # restated exactly (capi.cu: tsc_host_cluster_rejects; checked against networkx in the tests)
+                    nr = int(L.tsc_host_cluster_rejects(p_mi, p_mj, n, _l, p_rej))
+                    if nr < 0:
+                        raise RuntimeError("tsc_host_cluster_rejects: bad arguments")
+                    final_mask[base + rej[:nr]] = False
+                continue
             else:
                 fh = first_hit[base:hi]
                 new_hi = np.minimum(fh - 1, hi - 1)
