@@ -102,6 +102,14 @@ int tsc_rmsd_screen(const void* PA, const void* PB, const void* PR, const double
  * group[0] depends on them (capi.cu).  mi, mj (n): the matches (chunk-relative, i < j, insertion order);
  * n_nodes_max: chunk length; rejects: the members not kept.  Returns their number (-1: bad arguments). */
 int64_t tsc_host_cluster_rejects(const int32_t* mi, const int32_t* mj, int64_t n, int64_t n_nodes_max, int32_t* rejects);
+/* The whole grouping loop on the host (torsion_module.py:1076-1152 and its TFD / MOI siblings): ladder of k values, gate
+ * `k == 1 or gate * k < active`, k chunks per round (the last one ending at the ACTIVE count: the reference's quirk), per
+ * chunk tsc_host_rotcorr_chunk + tsc_host_cluster_rejects.  final_mask: N bytes, all 1 on entry; scratch: 3 N int32;
+ * T = 0: no rotor states (state / compact / off / ang_table unused).  Returns the number of chunks with matches. */
+int64_t tsc_host_ladder_replay(int64_t N, const int64_t* ladder, int32_t n_ladder, int32_t gate,
+                               const int64_t* first_hit, int64_t* reach, double* state, int32_t T,
+                               const uint64_t* compact, const int64_t* off, const double* ang_table,
+                               uint8_t* final_mask, int32_t* scratch);
 
 /* Host-side plan of the screen (capi.cu; no GPU involved): tsc_host_sample_pairs fills K fixed pseudo-random pairs
  * i != j of [0, N); tsc_host_screen_plan takes the frame from structure `first` of the HOST array S (rows, A, 3) and

@@ -30,6 +30,7 @@ SIGNATURES = {
     "tsc_screen_rows_padded": (_i64, [_i64]),
     "tsc_host_sample_pairs": (None, [_i64, _i32, _vp, _vp]),
     "tsc_host_cluster_rejects": (_i64, [_vp, _vp, _i64, _i64, _vp]),
+    "tsc_host_ladder_replay": (_i64, [_i64, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "tsc_host_screen_plan": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _f64, _vp, _vp, _vp]),
     "tsc_screen_max_atoms": (_i32, [_i32]),
     "tsc_pack_screen": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp]),

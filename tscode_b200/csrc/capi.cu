@@ -470,3 +470,41 @@ extern "C" int64_t tsc_host_cluster_rejects(const int32_t* mi, const int32_t* mj
     }
     return n_rej;
 }
+
+// The whole grouping loop of torsion_module.py:1076-1152 (and of its TFD / MOI siblings) on the host: for every k of the
+// ladder whose gate is open (k == 1 or gate * k < active structures; gate = 5 there), the k chunks in order — the last
+// one ends at the number of ACTIVE structures, the reference's quirk (:1093-1094) —, per chunk the first-hit walk with
+// rotor-state algebra (tsc_host_rotcorr_chunk) and the survivor choice (tsc_host_cluster_rejects).  The Python loop
+// around the two spent 25 us per chunk on 3 900 chunks of BASELINE configs[3]: 0.09 of 0.13 s.
+//   final_mask (N bytes, all 1 on entry); scratch: 3 N int32.  Returns the number of chunks that had matches, -1 on
+//   bad arguments.
+extern "C" int64_t tsc_host_ladder_replay(int64_t N, const int64_t* ladder, int32_t n_ladder, int32_t gate,
+                                          const int64_t* first_hit, int64_t* reach, double* state, int32_t T,
+                                          const uint64_t* compact, const int64_t* off, const double* ang_table,
+                                          uint8_t* final_mask, int32_t* scratch) {
+    if (N <= 0 || !ladder || !first_hit || !reach || !final_mask || !scratch || (T > 0 && (!state || !compact || !off || !ang_table)))
+        return -1;
+    int32_t* mi = scratch;
+    int32_t* mj = scratch + N;
+    int32_t* rej = scratch + 2 * N;
+    int64_t busy = 0;
+    for (int32_t q = 0; q < n_ladder; q++) {
+        const int64_t k = ladder[q];
+        int64_t num_active = 0;
+        for (int64_t i = 0; i < N; i++) num_active += final_mask[i] != 0;
+        if (!(k == 1 || (int64_t)gate * k < num_active)) continue;
+        const int64_t d = N / k;
+        for (int64_t step = 0; step < k; step++) {
+            const int64_t base = d * step;
+            const int64_t len = (step == k - 1) ? (num_active > base ? num_active - base : 0) : d;
+            if (len <= 1) continue;
+            const int64_t n = tsc_host_rotcorr_chunk(base, base + len, first_hit, reach, state, T, compact, off, ang_table, mi, mj);
+            if (n <= 0) continue;
+            const int64_t nr = tsc_host_cluster_rejects(mi, mj, n, len, rej);
+            if (nr < 0) return -1;
+            for (int64_t r = 0; r < nr; r++) final_mask[base + rej[r]] = 0;
+            busy++;
+        }
+    }
+    return busy;
+}

@@ -483,6 +483,16 @@ def ladder_replay_scan(first_hit, N, best_angles=None, verbose=False, native=Non
         vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
         p_first, p_reach, p_state, p_compact, p_off, p_table, p_mi, p_mj, p_rej = (vp(a) for a in (
             first_hit, reach, state, compact, off, table, mi, mj, rej))      # the arrays never move
+    if native and not verbose and N > 0:
+        # the whole loop below in native code (capi.cu: tsc_host_ladder_replay; the Python loop spent 25 us per chunk)
+        ladder = np.ascontiguousarray(_host.LADDER, dtype=np.int64)
+        mask8 = np.ones(N, dtype=np.uint8)
+        scratch = np.empty(3 * N, dtype=np.int32)
+        rc = int(L.tsc_host_ladder_replay(N, vp(ladder), int(ladder.size), 5, p_first, p_reach, p_state, T, p_compact, p_off,
+                                          p_table, vp(mask8), vp(scratch)))
+        if rc < 0:
+            raise RuntimeError("tsc_host_ladder_replay: bad arguments")
+        return mask8.astype(bool), state
     for k in _host.LADDER:
         num_active = int(np.count_nonzero(final_mask))
         if not (k == 1 or 5 * k < num_active):                                     # :1083
