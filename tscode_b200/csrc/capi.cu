@@ -31,6 +31,16 @@ extern "C" int32_t tsc_device_sm_count(void) {
 //   pruning, numba_functions.py:155-231, runs the same loop) ignores compact / off / ang_table / state.
 // ------------------------------------------------------------------------------------------
 #include <math.h>
+// (a + b) % 360.0 as Python evaluates it, for the values that occur (angles and states in [0, 360)): one exact
+// subtraction instead of fmod; anything else takes fmod
+static inline double add_mod360(double a, double b) {
+    const double s = a + b;
+    if (s >= 0.0 && s < 360.0) return s;
+    if (s >= 360.0 && s < 720.0) return s - 360.0;
+    double r = fmod(s, 360.0);
+    if (r != 0.0 && r < 0.0) r += 360.0;                 // Python's % takes the sign of the divisor
+    return r;
+}
 extern "C" int64_t tsc_host_rotcorr_chunk(int64_t base, int64_t hi, const int64_t* first_hit, int64_t* reach,
                                           double* state, int32_t T, const uint64_t* compact, const int64_t* off,
                                           const double* ang_table, int32_t* match_i, int32_t* match_j) {
@@ -44,13 +54,13 @@ extern "C" int64_t tsc_host_rotcorr_chunk(int64_t base, int64_t hi, const int64_
         for (int64_t j = lo; T > 0 && j <= new_hi; j++) {
             const uint64_t c = ci[j];
             double* sj = state + j * T;
-            for (int t = 0; t < T; t++) sj[t] = fmod(ang_table[t * 6 + ((c >> (3 * t)) & 7ull)] + si[t], 360.0);
+            for (int t = 0; t < T; t++) sj[t] = add_mod360(ang_table[t * 6 + ((c >> (3 * t)) & 7ull)], si[t]);
         }
         if (new_hi >= lo) reach[i] = new_hi;
         if (p < hi) {
             const uint64_t c = T > 0 ? ci[p] : 0ull;
             double* sj = state + p * T;
-            for (int t = 0; t < T; t++) sj[t] = fmod(ang_table[t * 6 + ((c >> (3 * t)) & 7ull)] + si[t], 360.0);
+            for (int t = 0; t < T; t++) sj[t] = add_mod360(ang_table[t * 6 + ((c >> (3 * t)) & 7ull)], si[t]);
             match_i[n_match] = (int32_t)(i - base);
             match_j[n_match] = (int32_t)(p - base);
             n_match++;
