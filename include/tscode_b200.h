@@ -342,6 +342,12 @@ int tsc_rotcorr_apply(const double* Sc, int64_t n, int32_t A, const int64_t* idx
                       const int32_t* tor_i2, const int32_t* tor_i3, const double* sin_half,
                       const double* cos_half, const uint8_t* rot_mask, double* out, void* stream);
 
+/* [host] Every structure minus its centroid (torsion_module.py:1023, the first statement of
+ * prune_conformers_rmsd_rot_corr: `np.array([s - s.mean(axis=0) for s in structures])`), bit-identical to numpy: the A
+ * rows are added in order, the sums divided by A, then subtracted.  S, out (N, A, 3) HOST doubles (out may alias S).
+ * Structures are dealt to n_threads host threads.  Returns 0, or -1 on bad arguments. */
+int32_t tsc_host_centre(const double* S, int64_t N, int32_t A, double* out, int32_t n_threads);
+
 /* ---- ensemble I/O ------------------------------------------------------------------------ */
 /* [host] Multi-frame XYZ text of n_frames structures (utils.py:114-126, write_xyz; embedder.py:996-1043): per frame
  * "<A>\n<title>\n" and per atom '%s     % .6f % .6f % .6f\n', byte-identical to the reference's Python formatting.

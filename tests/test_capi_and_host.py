@@ -225,6 +225,42 @@ def test_rotcorr_scan_replay_equals_dense_replay(N, dens, seed):
         assert np.array_equal(m1, m2) and np.array_equal(s1, s2), native
 
 
+@pytest.mark.parametrize("N,n_clusters,seed", [(2500, 12, 0), (1200, 200, 1), (3000, 1, 2)])
+def test_native_replay_on_clustered_first_hits(N, n_clusters, seed):
+    """The shape BASELINE configs[3] has — a few clusters, every row's first hit = the next member of its cluster —
+    with 2-, 3- and 6-fold rotors: the native replay (tsc_host_ladder_replay: per-row image tables for rows with many
+    visits, direct sums for short ones, the survivor choice on re-used set models) against the Python loop, mask and
+    rotor states bit for bit; several ladder rounds run (N > 5 k for k up to 500 / 200)."""
+    from tscode_b200.torsion_module import ladder_replay_scan
+    rng = np.random.default_rng(seed)
+    cl = rng.integers(0, n_clusters, N)
+    first = np.full(N, N, dtype=np.int64)
+    last = {}
+    for i in range(N - 1, -1, -1):
+        if cl[i] in last:
+            first[i] = last[cl[i]]
+        last[cl[i]] = i
+    n_ang = [2, 3, 6, 3, 1]
+    T = len(n_ang)
+    table = np.zeros((T, 6))
+    for t, n in enumerate(n_ang):
+        table[t, :n] = np.arange(n) * (360.0 / n)
+    lengths = np.maximum(np.minimum(first, N - 1) - np.arange(N), 0)
+    off = (np.cumsum(lengths) - lengths).astype(np.int64)
+    compact = np.zeros(max(int(lengths.sum()), 1), dtype=np.uint64)
+    for t, n in enumerate(n_ang):
+        compact[:int(lengths.sum())] |= rng.integers(0, n, size=int(lengths.sum())).astype(np.uint64) << np.uint64(3 * t)
+
+    def lookup(i, js):
+        cc = compact[off[i] + (np.asarray(js) - i - 1)]
+        return np.stack([table[t][((cc >> np.uint64(3 * t)) & np.uint64(7)).astype(np.int64)] for t in range(T)], axis=-1)
+    lookup.T, lookup.compact, lookup.off, lookup.table = T, compact, off, table
+    m_py, s_py = ladder_replay_scan(first.copy(), N, lookup, native=False)
+    m_c, s_c = ladder_replay_scan(first.copy(), N, lookup, native=True)
+    assert np.array_equal(m_py, m_c) and np.array_equal(s_py, s_c)
+    assert 0 < m_c.sum() < N and (s_c >= 0).all() and (s_c < 360).all() and len(np.unique(s_c)) > 2
+
+
 def test_native_xyz_text_is_byte_identical_to_reference_formatting():
     """(f)-4: tsc_host_write_xyz against the reference's per-atom '%s     % .6f % .6f % .6f\\n' (utils.py:114-126),
     including half-way decimals, negative zero, huge values, inf / nan, and per-frame titles."""
@@ -404,6 +440,37 @@ def test_native_screen_plan_agrees_with_its_numpy_statement():
     assert _host.sample_pair_indices(1)[0].size == 0
     assert _host.plan_mode(1.0, 0.0) == 0 and _host.plan_mode(1.5, 0.0) == 1 and _host.plan_mode(1.0, 0.02) == 1
     assert _host.plan_mode(1.0, 0.5) == 2
+
+
+def test_native_centring_is_bit_identical_to_numpy():
+    """capi.cu: tsc_host_centre == `np.array([s - s.mean(axis=0) for s in structures])` (torsion_module.py:1023) to
+    the last bit, for sizes from one atom to more than a thousand, widely different magnitudes and offsets, any number
+    of threads, in place as well; torsion_module.centre_structures routes regular inputs to it and ragged / empty
+    ones to numpy."""
+    from tscode_b200 import torsion_module as tm
+    L = _lib.lib()
+    rng = np.random.default_rng(11)
+    for N, A in [(1, 1), (3, 2), (7, 8), (300, 129), (50, 1025), (1000, 200), (4000, 63)]:
+        S = rng.normal(size=(N, A, 3)) * rng.choice([1e-6, 1e-3, 1.0, 1e3]) + rng.normal(size=(N, 1, 3)) * 10.0
+        ref = np.array([s - s.mean(axis=0) for s in S])
+        for nt in (1, 3, 16):
+            out = np.full_like(S, np.nan)
+            assert L.tsc_host_centre(S.ctypes.data, N, A, out.ctypes.data, nt) == 0
+            assert np.array_equal(out, ref), (N, A, nt)
+        inplace = S.copy()
+        assert L.tsc_host_centre(inplace.ctypes.data, N, A, inplace.ctypes.data, 4) == 0
+        assert np.array_equal(inplace, ref)
+        assert np.array_equal(tm.centre_structures(S), ref)
+        assert np.array_equal(tm.centre_structures(S.astype(np.float32)),
+                              np.array([s - s.mean(axis=0) for s in S.astype(np.float32).astype(np.float64)]))
+        assert np.array_equal(tm.centre_structures(S[:, ::-1][:, :, ::-1]),                 # non-contiguous view
+                              np.array([s - s.mean(axis=0) for s in S[:, ::-1][:, :, ::-1]]))
+        assert np.array_equal(tm.centre_structures(list(S)), ref)
+    assert L.tsc_host_centre(None, 0, 5, None, 1) == 0 and L.tsc_host_centre(None, 4, 5, None, 1) == -1
+    assert tm.centre_structures(np.zeros((0, 5, 3))).shape[0] == 0
+    inf = np.ones((2, 3, 3)); inf[0, 1, 0] = np.inf; inf[1, 2, 2] = np.nan
+    with np.errstate(invalid="ignore"):
+        assert np.array_equal(tm.centre_structures(inf), np.array([s - s.mean(axis=0) for s in inf]), equal_nan=True)
 
 
 def test_native_cluster_survivor_choice_equals_python_and_networkx():

@@ -31,12 +31,12 @@ extern "C" int32_t tsc_device_sm_count(void) {
 //   pruning, numba_functions.py:155-231, runs the same loop) ignores compact / off / ang_table / state.
 // ------------------------------------------------------------------------------------------
 #include <math.h>
+#define TSC_HOST_MAX_T 21                 // rotcorr.cu: 3 bits of angle code per rotor in a 64-bit word
 // (a + b) % 360.0 as Python evaluates it, for the values that occur (angles and states in [0, 360)): one exact
 // subtraction instead of fmod; anything else takes fmod
 static inline double add_mod360(double a, double b) {
     const double s = a + b;
-    if (s >= 0.0 && s < 360.0) return s;
-    if (s >= 360.0 && s < 720.0) return s - 360.0;
+    if (s >= 0.0 && s < 720.0) return s - (s >= 360.0 ? 360.0 : 0.0);      // x - 0.0 == x for every x >= 0
     double r = fmod(s, 360.0);
     if (r != 0.0 && r < 0.0) r += 360.0;                 // Python's % takes the sign of the divisor
     return r;
@@ -45,22 +45,46 @@ extern "C" int64_t tsc_host_rotcorr_chunk(int64_t base, int64_t hi, const int64_
                                           double* state, int32_t T, const uint64_t* compact, const int64_t* off,
                                           const double* ang_table, int32_t* match_i, int32_t* match_j) {
     int64_t n_match = 0;
+    double img[TSC_HOST_MAX_T * 8];         // img[t * 8 + v] = (angle v of rotor t + state of row i) mod 360
+    if (T > TSC_HOST_MAX_T) return -1;
     for (int64_t i = base; i < hi; i++) {
         const int64_t p = first_hit[i];
         const int64_t new_hi = (p - 1 < hi - 1) ? p - 1 : hi - 1;
         const int64_t lo = reach[i] + 1;
-        const double* si = state + i * T;
-        const uint64_t* ci = T > 0 ? compact + off[i] - (i + 1) : nullptr;      // code of (i, j) at ci[j]
-        for (int64_t j = lo; T > 0 && j <= new_hi; j++) {
-            const uint64_t c = ci[j];
-            double* sj = state + j * T;
-            for (int t = 0; t < T; t++) sj[t] = add_mod360(ang_table[t * 6 + ((c >> (3 * t)) & 7ull)], si[t]);
+        const bool hit = p < hi;
+        const int64_t visits = (new_hi >= lo ? new_hi - lo + 1 : 0) + (hit ? 1 : 0);
+        if (T > 0 && visits > 0) {
+            const double* si = state + i * T;
+            const uint64_t* ci = compact + off[i] - (i + 1);                    // code of (i, j) at ci[j]
+            if (visits >= 8) {
+                // every structure this row visits gets one of at most 6 images per rotor of row i's state: the
+                // images are computed once per row (the same additions the per-visit form makes), the visits are
+                // look-ups
+                for (int t = 0; t < T; t++) {
+                    for (int v = 0; v < 6; v++) img[t * 8 + v] = add_mod360(ang_table[t * 6 + v], si[t]);
+                    img[t * 8 + 6] = img[t * 8 + 7] = 0.0;                       // codes 6, 7 do not occur
+                }
+                for (int64_t j = lo; j <= new_hi; j++) {
+                    const uint64_t c = ci[j];
+                    double* sj = state + j * T;
+                    for (int t = 0; t < T; t++) sj[t] = img[t * 8 + ((c >> (3 * t)) & 7ull)];
+                }
+                if (hit) {
+                    const uint64_t c = ci[p];
+                    double* sj = state + p * T;
+                    for (int t = 0; t < T; t++) sj[t] = img[t * 8 + ((c >> (3 * t)) & 7ull)];
+                }
+            } else {
+                for (int64_t q = 0; q < visits; q++) {
+                    const int64_t j = (q == visits - 1 && hit) ? p : lo + q;
+                    const uint64_t c = ci[j];
+                    double* sj = state + j * T;
+                    for (int t = 0; t < T; t++) sj[t] = add_mod360(ang_table[t * 6 + ((c >> (3 * t)) & 7ull)], si[t]);
+                }
+            }
         }
         if (new_hi >= lo) reach[i] = new_hi;
-        if (p < hi) {
-            const uint64_t c = T > 0 ? ci[p] : 0ull;
-            double* sj = state + p * T;
-            for (int t = 0; t < T; t++) sj[t] = add_mod360(ang_table[t * 6 + ((c >> (3 * t)) & 7ull)], si[t]);
+        if (hit) {
             match_i[n_match] = (int32_t)(i - base);
             match_j[n_match] = (int32_t)(p - base);
             n_match++;
@@ -168,6 +192,41 @@ extern "C" int64_t tsc_host_write_xyz(const double* coords, int64_t n_frames, in
         for (auto& t : th) t.join();
     }
     return total;
+}
+
+// ------------------------------------------------------------------------------------------
+// [host] Centring of every structure on its centroid (torsion_module.py:1023,
+//     structures = np.array([s - s.mean(axis=0) for s in structures])
+// the first statement of prune_conformers_rmsd_rot_corr).  numpy reduces axis 0 of an (A, 3) array by adding the
+// rows in order, then divides the three sums by A; the same operations in the same order here (no reassociation, no
+// reciprocal), so the result is bit-identical — tests/test_capi_and_host.py compares with numpy.  Native because on
+// 20 000 x 63 atoms the numpy statement is a third of the whole call; structures are dealt to a few host threads.
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t tsc_host_centre(const double* S, int64_t N, int32_t A, double* out, int32_t n_threads) {
+    if (N < 0 || A < 1 || !S || !out) return N == 0 ? 0 : -1;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    if (N * (int64_t)A < 65536) n_threads = 1;
+    const int64_t per = (N + n_threads - 1) / n_threads;
+    auto work = [&](int64_t lo, int64_t hi) {
+        const double cnt = (double)A;
+        for (int64_t s = lo; s < hi; s++) {
+            const double* x = S + s * (int64_t)A * 3;
+            double* o = out + s * (int64_t)A * 3;
+            double sx = x[0], sy = x[1], sz = x[2];
+            for (int a = 1; a < A; a++) { sx += x[3 * a]; sy += x[3 * a + 1]; sz += x[3 * a + 2]; }
+            const double mx = sx / cnt, my = sy / cnt, mz = sz / cnt;
+            for (int a = 0; a < A; a++) { o[3 * a] = x[3 * a] - mx; o[3 * a + 1] = x[3 * a + 1] - my; o[3 * a + 2] = x[3 * a + 2] - mz; }
+        }
+    };
+    if (n_threads == 1) { work(0, N); return 0; }
+    std::vector<std::thread> th;
+    for (int w = 0; w < n_threads; w++) {
+        const int64_t lo = w * per, hi = (lo + per < N) ? lo + per : N;
+        if (lo < hi) th.emplace_back(work, lo, hi);
+    }
+    for (auto& t : th) t.join();
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -321,23 +380,44 @@ extern "C" int tsc_host_screen_plan(const double* S, int32_t A, const int32_t* h
 // It replaced 0.2 s of Python per BASELINE configs[3] prune (3 900 chunks).
 // ------------------------------------------------------------------------------------------
 namespace {
-struct PySetModel {                       // keys: (a, b) with b = -1 for plain ints
-    std::vector<uint64_t> h;
-    std::vector<int32_t> a, b;
-    std::vector<uint8_t> used_slot;
+// Storage is kept between uses (reset() only rewinds to CPython's initial 8-slot table) and a slot is one small record
+// (a BASELINE configs[3] prune builds ~1e5 of these sets and probes them ~1e6 times).  Two key types: PairKey = a tuple
+// (a, b) with its tuple hash, IntKey = a non-negative int, whose hash is its value.  a == -1 marks a free slot.
+struct PairKey {
+    uint64_t h; int32_t a, b;
+    bool free_slot() const { return a < 0; }
+    bool same(const PairKey& o) const { return h == o.h && a == o.a && b == o.b; }
+    uint64_t hash() const { return h; }
+};
+struct IntKey {
+    int32_t a;
+    bool free_slot() const { return a < 0; }
+    bool same(const IntKey& o) const { return a == o.a; }
+    uint64_t hash() const { return (uint64_t)(int64_t)a; }
+};
+template <class Key>
+struct PySetModel {
+    std::vector<Key> cur, alt;
     size_t mask = 7, fill = 0;
-    PySetModel() : h(8), a(8), b(8), used_slot(8, 0) {}
-    size_t size() const { return fill; }
-    void insert_clean(std::vector<uint64_t>& nh, std::vector<int32_t>& na, std::vector<int32_t>& nb,
-                      std::vector<uint8_t>& nu, size_t nmask, uint64_t hash, int32_t ka, int32_t kb) const {
+    static void prepare(std::vector<Key>& t, size_t n) {
+        if (t.size() < n) t.resize(n);
+        memset((void*)t.data(), 0xFF, n * sizeof(Key));          // every a = -1
+    }
+    PySetModel() { prepare(cur, 8); }
+    void reset() { mask = 7; fill = 0; prepare(cur, 8); }
+    size_t size_used() const { return fill; }
+    bool slot_used(size_t s) const { return !cur[s].free_slot(); }
+    const Key& key(size_t s) const { return cur[s]; }
+    static void insert_clean(std::vector<Key>& t, size_t nmask, const Key& k) {
+        const uint64_t hash = k.hash();
         size_t i = (size_t)hash & nmask;
         uint64_t perturb = hash;
         while (true) {
             size_t j = i;
-            if (!nu[j]) { nh[j] = hash; na[j] = ka; nb[j] = kb; nu[j] = 1; return; }
+            if (t[j].free_slot()) { t[j] = k; return; }
             if (i + 9 <= nmask)
                 for (j = i + 1; j <= i + 9; j++)
-                    if (!nu[j]) { nh[j] = hash; na[j] = ka; nb[j] = kb; nu[j] = 1; return; }
+                    if (t[j].free_slot()) { t[j] = k; return; }
             perturb >>= 5;
             i = (i * 5 + 1 + (size_t)perturb) & nmask;
         }
@@ -345,31 +425,14 @@ struct PySetModel {                       // keys: (a, b) with b = -1 for plain 
     void resize(size_t minused) {
         size_t newsize = 8;
         while (newsize <= minused) newsize <<= 1;
-        std::vector<uint64_t> nh(newsize);
-        std::vector<int32_t> na(newsize), nb(newsize);
-        std::vector<uint8_t> nu(newsize, 0);
+        prepare(alt, newsize);
         for (size_t s = 0; s <= mask; s++)
-            if (used_slot[s]) insert_clean(nh, na, nb, nu, newsize - 1, h[s], a[s], b[s]);
-        h.swap(nh); a.swap(na); b.swap(nb); used_slot.swap(nu);
+            if (!cur[s].free_slot()) insert_clean(alt, newsize - 1, cur[s]);
+        cur.swap(alt);
         mask = newsize - 1;
     }
-    bool contains(uint64_t hash, int32_t ka, int32_t kb) const {
-        size_t i = (size_t)hash & mask;
-        uint64_t perturb = hash;
-        while (true) {
-            int probes = (i + 9 <= mask) ? 9 : 0;
-            size_t j = i;
-            while (true) {
-                if (!used_slot[j]) return false;
-                if (h[j] == hash && a[j] == ka && b[j] == kb) return true;
-                if (probes-- == 0) break;
-                j++;
-            }
-            perturb >>= 5;
-            i = (i * 5 + 1 + (size_t)perturb) & mask;
-        }
-    }
-    void add(uint64_t hash, int32_t ka, int32_t kb) {
+    bool add(const Key& k) {                                     // true if the key was new
+        const uint64_t hash = k.hash();
         size_t i = (size_t)hash & mask;
         uint64_t perturb = hash;
         while (true) {
@@ -377,8 +440,8 @@ struct PySetModel {                       // keys: (a, b) with b = -1 for plain 
             size_t j = i;
             bool placed = false;
             while (true) {
-                if (!used_slot[j]) { h[j] = hash; a[j] = ka; b[j] = kb; used_slot[j] = 1; placed = true; break; }
-                if (h[j] == hash && a[j] == ka && b[j] == kb) return;
+                if (cur[j].free_slot()) { cur[j] = k; placed = true; break; }
+                if (cur[j].same(k)) return false;
                 if (probes-- == 0) break;
                 j++;
             }
@@ -387,8 +450,8 @@ struct PySetModel {                       // keys: (a, b) with b = -1 for plain 
             i = (i * 5 + 1 + (size_t)perturb) & mask;
         }
         fill++;
-        if (fill * 5 < mask * 3) return;
-        resize(fill > 50000 ? fill * 2 : fill * 4);
+        if (fill * 5 >= mask * 3) resize(fill > 50000 ? fill * 2 : fill * 4);
+        return true;
     }
 };
 inline uint64_t py_hash_int(int32_t v) { return (uint64_t)(int64_t)v; }          // (v >= 0 here; hash(-1) is -2 in CPython)
@@ -404,6 +467,17 @@ inline uint64_t py_hash_pair(int32_t x, int32_t y) {
     acc += 2ULL ^ (P5 ^ 3527539ULL);
     return acc == (uint64_t)-1 ? 1546275796ULL : acc;
 }
+// per-thread working storage of tsc_host_cluster_rejects, kept between calls
+struct ClusterScratch {
+    PySetModel<PairKey> matches;
+    PySetModel<IntKey> seen, nodes;
+    std::vector<int32_t> node_of;             // dense index -> node, in order of first appearance
+    std::vector<int32_t> idx_of;              // node -> dense index, -1 outside a call
+    std::vector<int32_t> head, tail;          // per dense index: first / last adjacency entry (-1: none)
+    std::vector<int32_t> adj_to, adj_next;    // adjacency entries in insertion order, chained per node
+    std::vector<uint8_t> seen_all, in_comp;
+    std::vector<int32_t> level, next_level, comp;
+};
 }  // namespace
 
 // mi, mj (n): the chunk's matches (i_rel < j_rel, chunk-relative, in insertion order); n_nodes_max: the chunk length
@@ -413,71 +487,83 @@ extern "C" int64_t tsc_host_cluster_rejects(const int32_t* mi, const int32_t* mj
                                             int32_t* rejects) {
     if (n < 0 || n_nodes_max <= 0 || (n > 0 && (!mi || !mj || !rejects))) return -1;
     if (n == 0) return 0;
-    PySetModel matches;
-    for (int64_t k = 0; k < n; k++) {
+    for (int64_t k = 0; k < n; k++)
         if (mi[k] < 0 || mj[k] < 0 || mi[k] >= n_nodes_max || mj[k] >= n_nodes_max) return -1;
-        matches.add(py_hash_pair(mi[k], mj[k]), mi[k], mj[k]);
-    }
+    static thread_local ClusterScratch W;
+    PySetModel<PairKey>& matches = W.matches;
+    matches.reset();
+    for (int64_t k = 0; k < n; k++) matches.add(PairKey{py_hash_pair(mi[k], mj[k]), mi[k], mj[k]});
     // Graph(matches): nodes in order of first appearance, adjacency in insertion order
-    std::vector<int32_t> node_of;                                // dense index -> node
-    std::vector<int32_t> idx_of((size_t)n_nodes_max, -1);
-    std::vector<std::vector<int32_t>> adj;
+    if (W.idx_of.size() < (size_t)n_nodes_max) W.idx_of.resize((size_t)n_nodes_max, -1);
+    std::vector<int32_t>& node_of = W.node_of;
+    std::vector<int32_t>& idx_of = W.idx_of;
+    node_of.clear(); W.head.clear(); W.tail.clear(); W.adj_to.clear(); W.adj_next.clear();
     auto node_index = [&](int32_t v) {
-        if (idx_of[v] < 0) { idx_of[v] = (int32_t)node_of.size(); node_of.push_back(v); adj.emplace_back(); }
+        if (idx_of[v] < 0) { idx_of[v] = (int32_t)node_of.size(); node_of.push_back(v); W.head.push_back(-1); W.tail.push_back(-1); }
         return idx_of[v];
     };
+    auto append = [&](int32_t iu, int32_t v) {
+        const int32_t e = (int32_t)W.adj_to.size();
+        W.adj_to.push_back(v); W.adj_next.push_back(-1);
+        if (W.tail[iu] < 0) W.head[iu] = e; else W.adj_next[W.tail[iu]] = e;
+        W.tail[iu] = e;
+    };
     for (size_t s = 0; s <= matches.mask; s++) {
-        if (!matches.used_slot[s]) continue;
-        const int32_t u = matches.a[s], v = matches.b[s];
+        if (!matches.slot_used(s)) continue;
+        const int32_t u = matches.key(s).a, v = matches.key(s).b;
         const int32_t iu = node_index(u);
         const int32_t iv = node_index(v);
         bool dup = false;                                        // adj[u][v] = None is idempotent
-        for (int32_t w : adj[iu]) dup = dup || w == v;
-        if (!dup) { adj[iu].push_back(v); if (u != v) adj[iv].push_back(u); }
+        for (int32_t e = W.head[iu]; e >= 0; e = W.adj_next[e]) dup = dup || W.adj_to[e] == v;
+        if (!dup) { append(iu, v); if (u != v) append(iv, u); }
     }
     const size_t n_nodes = node_of.size();
-    std::vector<uint8_t> seen_all(n_nodes, 0), in_comp(n_nodes, 0);
+    W.seen_all.assign(n_nodes, 0); W.in_comp.assign(n_nodes, 0);
     int64_t n_rej = 0;
-    std::vector<int32_t> level, next_level, comp;
+    std::vector<int32_t>&level = W.level, &next_level = W.next_level, &comp = W.comp;
+    PySetModel<IntKey>&seen = W.seen, &nodes = W.nodes;
     for (size_t q0 = 0; q0 < n_nodes; q0++) {
-        if (seen_all[q0]) continue;
+        if (W.seen_all[q0]) continue;
         const int32_t v0 = node_of[q0];
-        PySetModel seen;
-        seen.add(py_hash_int(v0), v0, -1);
+        seen.reset();
+        seen.add(IntKey{v0});
+        W.seen_all[q0] = 1;
         next_level.assign(1, v0);
         while (!next_level.empty()) {
             level.swap(next_level);
             next_level.clear();
             for (int32_t x : level)
-                for (int32_t w : adj[idx_of[x]])
-                    if (!seen.contains(py_hash_int(w), w, -1)) {
-                        seen.add(py_hash_int(w), w, -1);
-                        next_level.push_back(w);
-                    }
+                for (int32_t e = W.head[idx_of[x]]; e >= 0; e = W.adj_next[e]) {
+                    const int32_t w = W.adj_to[e];
+                    uint8_t& in_seen = W.seen_all[idx_of[w]];        // `w not in seen` without probing the set model
+                    if (!in_seen) { in_seen = 1; seen.add(IntKey{w}); next_level.push_back(w); }
+                }
         }
         // nodes = set(iter(seen)); first = next(iter(nodes)) if 2 |nodes| < |G| else first node of G in nodes
         comp.clear();
-        PySetModel nodes;
+        const bool small = 2 * seen.size_used() < n_nodes;
+        if (small) nodes.reset();
         for (size_t s = 0; s <= seen.mask; s++)
-            if (seen.used_slot[s]) {
-                nodes.add(seen.h[s], seen.a[s], -1);
-                comp.push_back(seen.a[s]);
-                seen_all[idx_of[seen.a[s]]] = 1;
-                in_comp[idx_of[seen.a[s]]] = 1;
+            if (seen.slot_used(s)) {
+                const int32_t x = seen.key(s).a;
+                if (small) nodes.add(IntKey{x});
+                comp.push_back(x);
+                W.in_comp[idx_of[x]] = 1;
             }
         int32_t first = -1;
-        if (2 * comp.size() < n_nodes) {
+        if (small) {
             for (size_t s = 0; s <= nodes.mask && first < 0; s++)
-                if (nodes.used_slot[s]) first = nodes.a[s];
+                if (nodes.slot_used(s)) first = nodes.key(s).a;
         } else {
             for (size_t q = 0; q < n_nodes && first < 0; q++)
-                if (in_comp[q]) first = node_of[q];
+                if (W.in_comp[q]) first = node_of[q];
         }
         for (int32_t x : comp) {
-            in_comp[idx_of[x]] = 0;
+            W.in_comp[idx_of[x]] = 0;
             if (x != first) rejects[n_rej++] = x;
         }
     }
+    for (int32_t v : node_of) idx_of[v] = -1;
     return n_rej;
 }
 
@@ -492,7 +578,8 @@ extern "C" int64_t tsc_host_ladder_replay(int64_t N, const int64_t* ladder, int3
                                           const int64_t* first_hit, int64_t* reach, double* state, int32_t T,
                                           const uint64_t* compact, const int64_t* off, const double* ang_table,
                                           uint8_t* final_mask, int32_t* scratch) {
-    if (N <= 0 || !ladder || !first_hit || !reach || !final_mask || !scratch || (T > 0 && (!state || !compact || !off || !ang_table)))
+    if (N <= 0 || !ladder || !first_hit || !reach || !final_mask || !scratch || T > TSC_HOST_MAX_T ||
+        (T > 0 && (!state || !compact || !off || !ang_table)))
         return -1;
     int32_t* mi = scratch;
     int32_t* mj = scratch + N;
