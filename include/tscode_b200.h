@@ -342,6 +342,18 @@ int tsc_rotcorr_apply(const double* Sc, int64_t n, int32_t A, const int64_t* idx
                       const int32_t* tor_i2, const int32_t* tor_i3, const double* sin_half,
                       const double* cos_half, const uint8_t* rot_mask, double* out, void* stream);
 
+/* [host] Work items of the default screen for a persistent grid of n_ctas CTAs (read by tsc_rmsd_screen; the rule is
+ * tscode_b200/_host.py: build_items_balanced): one contiguous, equally expensive stretch of (panel, j tile) pairs per CTA,
+ * one item {panel, first j tile, j tile count, local row block} per panel a stretch touches, laid out round by round
+ * with stride n_ctas (empty items, count 0, end a CTA's list).  The reference has no counterpart: this schedules the
+ * pair loop of rmsd_pruning.py:43-79 over the SMs.  row_blocks (n_rb): the rank's 32-row blocks, ascending;
+ * panel_lo / panel_hi: only these 128-row panels (panel_hi < 0: all); tile_j: 32, 48 or 64 columns per j tile
+ * (<= 0: tiles_per_panel tiles per panel); max_item > 0 cuts items (measurement aid).  out (cap, 4) int32 or NULL.
+ * Returns the number of items (at most cap are written), -1 on bad arguments. */
+int64_t tsc_host_screen_items(int64_t N, const int32_t* row_blocks, int64_t n_rb, int32_t n_ctas, int64_t panel_lo,
+                              int64_t panel_hi, double item_cost, int32_t max_item, int32_t tiles_per_panel,
+                              int32_t tile_j, int32_t* out, int64_t cap);
+
 /* [host] Every structure minus its centroid (torsion_module.py:1023, the first statement of
  * prune_conformers_rmsd_rot_corr: `np.array([s - s.mean(axis=0) for s in structures])`), bit-identical to numpy: the A
  * rows are added in order, the sums divided by A, then subtracted.  S, out (N, A, 3) HOST doubles (out may alias S).

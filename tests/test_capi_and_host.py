@@ -442,6 +442,57 @@ def test_native_screen_plan_agrees_with_its_numpy_statement():
     assert _host.plan_mode(1.0, 0.5) == 2
 
 
+def test_native_screen_items_equal_the_python_rule():
+    """capi.cu: tsc_host_screen_items (what _host.build_screen_items calls) against the rule as _host.build_items_balanced
+    states it, entry by entry: every tile width, whole ensembles and upload chunks, 1 / 2 / 8 ranks, grids of 1 / 16 /
+    148 CTAs, sizes from 1 structure to 2e5; and through the raw entry point the forms build_screen_items does not use
+    (tiles_per_panel layout, max_item cutting, a too small output buffer, bad arguments)."""
+    from tscode_b200.rmsd_pruning import _upload_bounds
+    L = _lib.lib()
+    n_cases = 0
+    for N in list(range(1, 700, 61)) + [1000, 4097, 10000, 50000, 75892, 200000]:
+        for world in (1, 2, 8):
+            for rank in sorted({0, world - 1}):
+                rb = _host.owned_row_blocks(N, rank, world)
+                b = _upload_bounds(N)
+                for tile_j in (32, 48, 64):
+                    for n_ctas in (148, 16, 1):
+                        for lo, hi in [(0, None)] + [(b[c], b[c + 1]) for c in range(len(b) - 1)]:
+                            got = _host.build_screen_items(N, rb, n_ctas, panel_lo=lo, panel_hi=hi, tile_j=tile_j)
+                            want = _host.build_items_balanced(N, rb, n_ctas, lo, hi, 2.5 * 32.0 / tile_j, tile_j=tile_j)
+                            assert got.dtype == np.int32 and got.shape == want.shape and np.array_equal(got, want), \
+                                (N, world, rank, tile_j, n_ctas, lo, hi)
+                            n_cases += 1
+    assert n_cases > 3000
+
+    def raw(N, rb, n_ctas, lo, hi, cost, max_item, tpp, tile_j, cap=None):
+        rb = np.ascontiguousarray(rb, dtype=np.int32)
+        n = int(L.tsc_host_screen_items(N, rb.ctypes.data, rb.size, n_ctas, lo, hi, cost, max_item, tpp, tile_j, None, 0))
+        out = np.full((max(n if cap is None else cap, 1), 4), -7, dtype=np.int32)
+        n2 = int(L.tsc_host_screen_items(N, rb.ctypes.data, rb.size, n_ctas, lo, hi, cost, max_item, tpp, tile_j,
+                                         out.ctypes.data, n if cap is None else cap))
+        assert n2 == n
+        return n, out
+    for N in (130, 5000, 30000):
+        rb = _host.owned_row_blocks(N, 0, 1)
+        for tpp in (8, 4):                                       # tile_j None: tiles_per_panel tiles per panel
+            n, out = raw(N, rb, 148, 0, -1, 3.0, 0, tpp, 0)
+            want = _host.build_items_balanced(N, rb, 148, tiles_per_panel=tpp)
+            assert n == want.shape[0] and np.array_equal(out[:n], want)
+        for max_item in (1, 5):
+            n, out = raw(N, rb, 148, 0, -1, 2.5, max_item, 8, 32)
+            want = _host.build_items_balanced(N, rb, 148, item_cost=2.5, max_item=max_item, tile_j=32)
+            assert n == want.shape[0] and np.array_equal(out[:n], want)
+        n, out = raw(N, rb, 148, 0, -1, 2.5, 0, 8, 48, cap=3)     # short buffer: count reported, only cap items written
+        want = _host.build_items_balanced(N, rb, 148, item_cost=2.5, tile_j=48)
+        assert n == want.shape[0] and np.array_equal(out[:3], want[:3])
+    rb = _host.owned_row_blocks(1000, 0, 1)
+    assert raw(1000, rb, 148, 5, 5, 2.5, 0, 8, 32)[0] == 0          # empty panel range
+    assert L.tsc_host_screen_items(1000, rb.ctypes.data, rb.size, 0, 0, -1, 2.5, 0, 8, 32, None, 0) == -1
+    assert L.tsc_host_screen_items(1000, None, 3, 148, 0, -1, 2.5, 0, 8, 32, None, 0) == -1
+    assert L.tsc_host_screen_items(0, None, 0, 148, 0, -1, 2.5, 0, 8, 32, None, 0) == 0
+
+
 def test_native_centring_is_bit_identical_to_numpy():
     """capi.cu: tsc_host_centre == `np.array([s - s.mean(axis=0) for s in structures])` (torsion_module.py:1023) to
     the last bit, for sizes from one atom to more than a thousand, widely different magnitudes and offsets, any number

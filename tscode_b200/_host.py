@@ -48,9 +48,21 @@ def owned_row_blocks(N: int, rank: int = 0, world: int = 1) -> np.ndarray:
 def build_screen_items(N: int, row_blocks: np.ndarray, n_ctas: int, panel_lo: int = 0, panel_hi: int | None = None,
                        item_cost: float = 2.5, tile_j: int = 32) -> np.ndarray:
     """Work items of the default screen (rmsd_screen.cu): as build_items_balanced, with j tiles of `tile_j`
-    (32, 48 or 64) conformers; panel p starts at the tile that holds its first column, 128 p // tile_j."""
-    return build_items_balanced(N, row_blocks, n_ctas, panel_lo, panel_hi, item_cost * 32.0 / tile_j,
-                                tile_j=int(tile_j))
+    (32, 48 or 64) conformers; panel p starts at the tile that holds its first column, 128 p // tile_j.  Built by the
+    library's host code (capi.cu: tsc_host_screen_items — the same rule, compared with build_items_balanced entry by
+    entry in the tests): every new ensemble size needs nine such lists before its first launch, 12 ms of Python for
+    50 000 structures against 0.1 ms."""
+    from ._lib import lib
+    rb = np.ascontiguousarray(row_blocks, dtype=np.int32)
+    args = (int(N), rb.ctypes.data, int(rb.size), int(n_ctas), int(panel_lo), -1 if panel_hi is None else int(panel_hi),
+            float(item_cost * 32.0 / tile_j), 0, 8, int(tile_j))
+    n = int(lib().tsc_host_screen_items(*args, None, 0))
+    if n < 0:
+        raise ValueError("tsc_host_screen_items: bad arguments")
+    items = np.empty((n, 4), dtype=np.int32)
+    if n and int(lib().tsc_host_screen_items(*args, items.ctypes.data, n)) != n:
+        raise RuntimeError("tsc_host_screen_items: inconsistent item count")
+    return items
 
 
 def screen_frame(first_heavy: np.ndarray):

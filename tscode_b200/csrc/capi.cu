@@ -107,6 +107,7 @@ extern "C" int64_t tsc_host_rotcorr_chunk(int64_t base, int64_t hi, const int64_
 // ------------------------------------------------------------------------------------------
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 #include <thread>
 #include <vector>
 namespace {
@@ -604,4 +605,97 @@ extern "C" int64_t tsc_host_ladder_replay(int64_t N, const int64_t* ladder, int3
         }
     }
     return busy;
+}
+
+// ------------------------------------------------------------------------------------------
+// [host] Work items of the default screen for a persistent grid (rmsd_screen.cu reads them; the rule is stated in
+// tscode_b200/_host.py: build_items_balanced, which the tests compare this with entry by entry): the (panel, j tile)
+// pairs of the owned 128-row panels, panel after panel, are cut into one contiguous stretch of equal cost per CTA
+// (tiles + item_cost tiles per item start), one item {panel, first j tile, j tile count, local row block} per panel a
+// stretch touches; laid out round by round with stride n_ctas, CTAs with fewer items than the longest list getting
+// empty items (count 0).  Native because every NEW ensemble size pays it before its first launch (the lists are
+// cached per size): 12 ms of Python for 50 000 structures — nine lists: the whole ensemble and the eight upload
+// chunks —, more than two whole prunes.
+//   row_blocks (n_rb): the rank's 32-row blocks, ascending (a panel is owned when its first block is);
+//   panel_hi < 0: all panels;  tile_j <= 0: `tiles_per_panel` j tiles per panel (the FP64 variants' 16-column tiles),
+//   else tiles of tile_j columns, panel p starting at tile 128 p / tile_j;  max_item > 0 cuts items (measurement aid).
+//   out: (cap, 4) int32 or NULL.  Returns the number of items (also when out is NULL or cap is too small: at most cap
+//   items are written), -1 on bad arguments.
+// ------------------------------------------------------------------------------------------
+extern "C" int64_t tsc_host_screen_items(int64_t N, const int32_t* row_blocks, int64_t n_rb, int32_t n_ctas,
+                                         int64_t panel_lo, int64_t panel_hi, double item_cost, int32_t max_item,
+                                         int32_t tiles_per_panel, int32_t tile_j, int32_t* out, int64_t cap) {
+    if (N < 0 || n_rb < 0 || (n_rb > 0 && !row_blocks) || n_ctas < 1 || (tile_j <= 0 && tiles_per_panel < 1)) return -1;
+    struct Item { int32_t p, j, cnt, lb; };
+    const int64_t PB = 4;                                        // 32-row blocks per 128-row panel
+    const int64_t n_pan = (N + 127) / 128;
+    const int64_t tpp = tile_j > 0 ? (128 / tile_j > 1 ? 128 / tile_j : 1) : tiles_per_panel;
+    const int64_t njt = tile_j > 0 ? (n_pan * 128 + tile_j - 1) / tile_j : n_pan * tpp;
+    auto first = [&](int64_t p) { return tile_j > 0 ? (128 * p) / tile_j : tpp * p; };
+    if (panel_hi < 0) panel_hi = n_pan;
+    std::vector<int64_t> pan_p, pan_lb;
+    int64_t total = 0;
+    for (int64_t lb = 0; lb < n_rb; lb++) {
+        const int64_t ib = row_blocks[lb];
+        if (ib < 0) return -1;
+        if (ib % PB == 0 && panel_lo <= ib / PB && ib / PB < panel_hi) {
+            pan_p.push_back(ib / PB); pan_lb.push_back(lb);
+            total += njt - first(ib / PB);
+        }
+    }
+    if (total == 0) return 0;
+    const int64_t n_bins = std::max<int64_t>(1, std::min<int64_t>(n_ctas, total / tpp));
+    std::vector<Item> flat;                                      // items in the order they are cut; bin ids ascend
+    std::vector<int64_t> bin_of;
+    double left = (double)total + item_cost * (double)((int64_t)pan_p.size() + n_bins);   // cost still to hand out
+    int64_t b = 0;
+    double budget = left / (double)n_bins;                       // what the current CTA may still take
+    for (size_t q = 0; q < pan_p.size(); q++) {
+        int64_t j = first(pan_p[q]);
+        const int64_t end = njt;
+        while (j < end) {
+            const int64_t room = (int64_t)(budget - item_cost);
+            if (room < 4 && b + 1 < n_bins) {                    // not worth starting an item here: next CTA
+                b++;
+                budget = left / (double)(n_bins - b);            // re-balance over the CTAs that are left
+                continue;
+            }
+            const int64_t take = (b + 1 == n_bins) ? end - j : std::max<int64_t>(1, std::min<int64_t>(end - j, room));
+            flat.push_back(Item{(int32_t)pan_p[q], (int32_t)j, (int32_t)take, (int32_t)pan_lb[q]});
+            bin_of.push_back(b);
+            j += take;
+            budget -= (double)take + item_cost;
+            left -= (double)take + item_cost;
+        }
+    }
+    // non-empty bins in order; optionally the same stretches cut into short items
+    std::vector<std::vector<Item>> bins;
+    int64_t prev = -1;
+    for (size_t e = 0; e < flat.size(); e++) {
+        if (bin_of[e] != prev) { bins.emplace_back(); prev = bin_of[e]; }
+        if (max_item > 0)
+            for (int32_t o = 0; o < flat[e].cnt; o += max_item)
+                bins.back().push_back(Item{flat[e].p, flat[e].j + o, std::min<int32_t>(max_item, flat[e].cnt - o), flat[e].lb});
+        else
+            bins.back().push_back(flat[e]);
+    }
+    size_t rounds = 0;
+    for (auto& x : bins) rounds = std::max(rounds, x.size());
+    const Item pad{(int32_t)pan_p[0], (int32_t)first(pan_p[0]), 0, (int32_t)pan_lb[0]};
+    // one round: one entry per CTA, any grid works; several: stride n_ctas exactly, so that the entries a CTA visits
+    // are the ones meant for it and an empty entry really ends its list
+    size_t n_bins_out = bins.size();
+    if (rounds > 1 && (size_t)n_ctas > n_bins_out) n_bins_out = (size_t)n_ctas;
+    int64_t n_items = 0;
+    for (size_t r = 0; r < rounds; r++) {
+        size_t last = 0;
+        for (size_t q = 0; q < bins.size(); q++) if (bins[q].size() > r) last = q;
+        const size_t width = (r + 1 < rounds) ? n_bins_out : last + 1;
+        for (size_t q = 0; q < width; q++) {
+            const Item& it = (q < bins.size() && bins[q].size() > r) ? bins[q][r] : pad;
+            if (out && n_items < cap) { int32_t* o = out + 4 * n_items; o[0] = it.p; o[1] = it.j; o[2] = it.cnt; o[3] = it.lb; }
+            n_items++;
+        }
+    }
+    return n_items;
 }
