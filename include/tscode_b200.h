@@ -369,6 +369,17 @@ int32_t tsc_host_centre(const double* S, int64_t N, int32_t A, double* out, int3
 int64_t tsc_host_write_xyz(const double* coords, int64_t n_frames, int32_t A, const char* symbols, const char* titles,
                            char* out, int64_t cap, int32_t n_threads);
 
+/* [host] Multi-frame XYZ text -> coordinates: the input side of the same format (utils.py:128-135, read_xyz = cclib's
+ * ccread; callers use .atomcoords and .atomnos: hypermolecule_class.py:163-168, operators.py:109, 169, 285).  Follows
+ * cclib's XYZ reader: per frame an optional blank line, the atom count, a comment line, `count` lines "symbol x y z
+ * [ignored ...]"; an incomplete last frame is dropped; numbers converted like Python's float() (correctly rounded).
+ * text (len bytes, HOST); *n_atoms receives A; coords (max_frames, A, 3) doubles or NULL (count only); symbols: A x 4
+ * bytes (zero-terminated, those of the last frame) or NULL; title_span: (offset, length) of each comment line or NULL.
+ * Returns the number of frames; -1 bad arguments, -2 malformed frame, -3 frames of different sizes, -4 a coordinate
+ * that is not a number, -5 max_frames too small. */
+int64_t tsc_host_read_xyz(const char* text, int64_t len, int32_t* n_atoms, double* coords, int64_t max_frames,
+                          char* symbols, int64_t* title_span, int32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif

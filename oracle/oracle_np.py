@@ -375,3 +375,37 @@ def fitness_check(coords, constraints, targets, threshold):
             v = coords[a] - coords[b]
             error += (np.sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) - target)
     return error < threshold
+
+
+def xyz_reader_model(text):
+    """The XYZ reader behind the reference's read_xyz (utils.py:128-135 = cclib's ccread; cclib==1.7 is pinned in the
+    reference's setup.py:50 and is NOT in the reference tree or this image), restated from its published source
+    (cclib/io/xyzreader.py, XYZ.generate_repr): lines from str.splitlines(); per frame one optional blank line, the
+    atom count = int(first token), the comment line, `count` lines of >= 4 whitespace-separated tokens (symbol, x, y,
+    z; further columns ignored); StopIteration anywhere ends the parse, dropping an incomplete frame (its comment is
+    kept); symbols are those of the last complete frame; ccData turns the coordinate strings into float64.
+    Returns (atomcoords (n, A, 3), symbols, comments).  PARITY UNPINNED against cclib itself (absent); pinned against
+    Python's float() and the reference's own write_xyz format (tests/test_capi_and_host.py)."""
+    it = iter(text.splitlines())
+    all_atomcoords, comments, atomsyms = [], [], []
+    while True:
+        try:
+            line = next(it)
+            if line.strip() == '':
+                line = next(it)
+            tokens = line.split()
+            assert len(tokens) >= 1
+            natom = int(tokens[0])
+            comments.append(next(it))
+            lines = []
+            for _ in range(natom):
+                line = next(it)
+                tokens = line.split()
+                assert len(tokens) >= 4
+                lines.append(tokens)
+            assert len(lines) == natom
+            atomsyms = [ln[0] for ln in lines]
+            all_atomcoords.append([[float(x) for x in ln[1:4]] for ln in lines])
+        except StopIteration:
+            break
+    return np.array(all_atomcoords, dtype=np.float64), atomsyms, comments

@@ -442,6 +442,94 @@ def test_native_screen_plan_agrees_with_its_numpy_statement():
     assert _host.plan_mode(1.0, 0.5) == 2
 
 
+def test_native_xyz_reader_equals_the_cclib_reader_model():
+    """(f)-4, input side: tsc_host_read_xyz / utils.parse_xyz against the restated algorithm of the XYZ reader behind
+    the reference's read_xyz (oracle_np.xyz_reader_model; cclib itself is absent: parity against it is unpinned) — on
+    the reference's own output format (write_xyz), on free-form files (tabs, extra columns, blank lines between frames,
+    CRLF and bare-CR line ends, no final newline, exponents, signs, inf / nan), an incomplete last frame, and the
+    malformed cases the reader rejects; numbers bit-identical to Python's float()."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import oracle_np
+    from tscode_b200.utils import _SYMBOLS, parse_xyz, read_xyz, xyz_text
+
+    def check(text, n_threads=None):
+        want_c, want_sym, want_com = oracle_np.xyz_reader_model(text)
+        got = parse_xyz(text, n_threads=n_threads)
+        n = want_c.shape[0]
+        assert got.atomcoords.shape[0] == n
+        if n:
+            assert got.atomcoords.shape == want_c.shape
+            assert np.array_equal(got.atomcoords.view(np.uint64), want_c.view(np.uint64))      # bit for bit, -0.0 and nan too
+            assert [_SYMBOLS[z] for z in got.atomnos] == want_sym
+            assert got.metadata["comments"] == want_com[:n]
+        return got
+
+    rng = np.random.default_rng(5)
+    S = rng.normal(size=(300, 37, 3)) * np.array([1, 10, 1000])
+    S[0, 0] = [0.0, -0.0, -1e-9]; S[0, 1] = [0.5e-6, 1.5e-6, 2.5e-6]; S[0, 2] = [123456.7890125, -0.0000005, 1e15]
+    S[0, 3] = [np.inf, -np.inf, np.nan]; S[0, 4] = [1e300, -1e300, 1e-300]
+    at = rng.choice([1, 6, 7, 8, 17, 35], size=37)
+    text = xyz_text(S, at, [f"conf {k}  E = {k * 0.1:.4f}" for k in range(len(S))]).decode()
+    for nt in (1, 5):
+        got = check(text, nt)
+    assert np.array_equal(got.atomnos, at) and got.natom == 37
+    fin = np.isfinite(S) & (np.abs(S) < 1e6)
+    assert np.abs(got.atomcoords[fin] - S[fin]).max() <= 0.50001e-6             # what '% .6f' keeps
+    big = xyz_text(rng.normal(size=(3000, 12, 3)), np.full(12, 6)).decode()       # enough frames for several threads
+    check(big, 7)
+    free = ("\n  3 atoms\nwater  # comment with 4 tokens 1 2\nO\t0.0 0 1e-3 extra columns ignored\n"
+            "H   +0.757   .586  -0.0\nH  -7.57E-1 5.86e+00 1.\n"
+            "\n3\n\nO 1 2 3\nH 4 5 6\nH 123456789012345678901234567890e-25 0.1000000000000000055511151231257827 4.9e-324\n"
+            "3\nthird\nO inf -Infinity nan\nH 1e400 -1e400 1e-400\nCl 2.2250738585072011e-308 17976931348623157e292 9007199254740993")
+    got = check(free)
+    assert got.atomcoords.shape == (3, 3, 3) and list(got.atomnos) == [8, 1, 17]
+    check(free.replace("\n", "\r\n"))
+    check(free.replace("\n", "\r"))
+    check(free + "\n")
+    check(free + "\n\n3\nincomplete frame: dropped\nO 0 0 0\nH 0 0 1")          # the text ends inside a frame
+    check(free + "\n3")                                                           # ... or right after a count line
+    check("")
+    check("\n")
+    assert parse_xyz(b"1\nx\nH 0 0 0\n").atomcoords.shape == (1, 1, 3)
+    # random decimal strings: every digit count, exponents beyond the exact fast path, leading / trailing zeros
+    import random
+    rnd = random.Random(9)
+    toks = []
+    for _ in range(3000):
+        nd = rnd.randrange(1, 25)
+        digits = "".join(rnd.choice("0123456789") for _ in range(nd))
+        cut = rnd.randrange(0, nd + 1)
+        t = rnd.choice(["", "-", "+"]) + digits[:cut] + rnd.choice([".", ""] if cut == nd and cut else ["."]) + digits[cut:]
+        if t.strip("+-") in (".", ""):
+            t += "0"
+        if rnd.random() < 0.5:
+            t += rnd.choice("eE") + rnd.choice(["", "-", "+"]) + str(rnd.randrange(0, 330))
+        toks.append(t)
+    body = "".join(f"C {toks[3 * a]} {toks[3 * a + 1]} {toks[3 * a + 2]}\n" for a in range(1000))
+    check("1000\nfuzz\n" + body)
+    for bad, exc in [("x\nc\nH 0 0 0\n", ValueError), ("-1\nc\n", ValueError), ("2\nc\nH 0 0 0\nH 0 0\n", ValueError),
+                     ("1\nc\nH 0 0 zero\n", ValueError), ("1\nc\nH 0 0 1e\n", ValueError), ("1\nc\nH 0 0 0x10\n", ValueError),
+                     ("1\nc\nH 0 0 0\n2\nc\nH 0 0 0\nH 0 0 1\n", ValueError), ("1\nc\nQq 0 0 0\n", KeyError)]:
+        with pytest.raises(exc):
+            parse_xyz(bad)
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        fn = os.path.join(d, "ens.xyz")
+        with open(fn, "w") as f:
+            f.write(text)
+        mol = read_xyz(fn)
+        assert np.array_equal(mol.atomcoords.view(np.uint64), got_bits(text, oracle_np)) and np.array_equal(mol.atomnos, at)
+        with open(fn, "w") as f:
+            f.write("")
+        with pytest.raises(AssertionError):
+            read_xyz(fn)
+
+
+def got_bits(text, oracle_np):
+    return oracle_np.xyz_reader_model(text)[0].view(np.uint64)
+
+
 def test_native_screen_items_equal_the_python_rule():
     """capi.cu: tsc_host_screen_items (what _host.build_screen_items calls) against the rule as _host.build_items_balanced
     states it, entry by entry: every tile width, whole ensembles and upload chunks, 1 / 2 / 8 ranks, grids of 1 / 16 /

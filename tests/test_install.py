@@ -59,6 +59,47 @@ def test_install_rebinds_every_importer():
     assert emb.compenetration_check is not numba_functions.compenetration_check
 
 
+@pytest.mark.skipif(not ref_harness.available(), reason="reference tree not present")
+def test_install_io_rebinds_xyz_helpers_with_reference_fallback(tmp_path):
+    """install_into(io=True): utils.write_xyz / read_xyz and their `from ... import` bindings go to the
+    native formatter / reader; a `.xyz` file is read natively, anything else (and a file the native reader rejects) is
+    handed to the reference's own read_xyz; off by default; uninstall restores."""
+    ref_harness.install(full=True)
+    import tscode.utils as ut
+    import tscode.hypermolecule_class as hm
+    import tscode.optimization_methods as om
+    from tscode_b200 import install, utils
+    orig_r, orig_w = ut.read_xyz, ut.write_xyz
+    install.install_into()
+    try:
+        assert ut.read_xyz is orig_r and ut.write_xyz is orig_w
+    finally:
+        install.uninstall()
+    patched = install.install_into(io=True)
+    try:
+        assert ut.read_xyz is install.read_xyz and ut.write_xyz is utils.write_xyz
+        assert hm.read_xyz is install.read_xyz and om.write_xyz is utils.write_xyz
+        assert ("tscode.hypermolecule_class", "read_xyz") in patched
+        S = np.random.default_rng(0).normal(size=(3, 5, 3))
+        at = np.array([6, 1, 1, 8, 7])
+        fn = tmp_path / "ens.xyz"
+        with open(fn, "w") as f:
+            for k, c in enumerate(S):
+                ut.write_xyz(c, at, f, title=f"frame {k}")
+        mol = hm.read_xyz(str(fn))
+        assert isinstance(mol, utils.XyzEnsemble) and np.array_equal(mol.atomnos, at)
+        assert np.abs(mol.atomcoords - S).max() <= 0.50001e-6 and mol.metadata["comments"] == ["frame 0", "frame 1", "frame 2"]
+        log = tmp_path / "calc.out"
+        log.write_text("not an xyz file")
+        assert not isinstance(ut.read_xyz(str(log)), utils.XyzEnsemble)            # the reference's ccread wrapper
+        bad = tmp_path / "bad.xyz"
+        bad.write_text("2\nc\nH 0 0 0\nH 0 0\n")
+        assert not isinstance(ut.read_xyz(str(bad)), utils.XyzEnsemble)            # rejected natively -> reference
+    finally:
+        install.uninstall()
+    assert ut.read_xyz is orig_r and ut.write_xyz is orig_w and hm.read_xyz is orig_r
+
+
 class _StubRun:
     """The attributes RunEmbedding.compenetration_refining / fitness_refining touch (embedder.py:1119-1134, :973-984,
     :1230-1313), around real Embedder methods."""

@@ -58,6 +58,7 @@ SIGNATURES = {
     "tsc_rotcorr_pairs": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f64,
                                     _vp, _vp, _vp, _vp, _vp]),
     "tsc_host_screen_items": (_i64, [_i64, _vp, _i64, _i32, _i64, _i64, _f64, _i32, _i32, _i32, _vp, _i64]),
+    "tsc_host_read_xyz": (_i64, [C.c_char_p, _i64, _vp, _vp, _i64, _vp, _vp, _i32]),
     "tsc_host_centre": (_i32, [_vp, _i64, _i32, _vp, _i32]),
     "tsc_host_write_xyz": (_i64, [_vp, _i64, _i32, C.c_char_p, C.c_char_p, _vp, _i64, _i32]),
     "tsc_host_rotcorr_chunk": (_i64, [_i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),

@@ -699,3 +699,199 @@ extern "C" int64_t tsc_host_screen_items(int64_t N, const int32_t* row_blocks, i
     }
     return n_items;
 }
+
+// ------------------------------------------------------------------------------------------
+// [host] Multi-frame XYZ text -> coordinates (the input side of SURVEY 8(f)-4: utils.py:128-135, read_xyz, a wrapper
+// of cclib's ccread; hypermolecule_class.py:163-168 and operators.py:109, 169, 285 use .atomcoords and .atomnos of the
+// result).  cclib is a third-party dependency absent from the reference tree; this follows the published algorithm
+// of its XYZ reader (cclib/io/xyzreader.py, 1.7-1.8): per frame an optional single blank line, a line whose first
+// token is the atom count, a comment line, then `count` lines of at least four whitespace-separated tokens — symbol,
+// x, y, z, anything further ignored; the text may end anywhere (an incomplete last frame is dropped); the symbols
+// reported are those of the last complete frame.  Numbers are converted like Python's float(): correctly rounded
+// (exact fast path for up to 19 digits and |exponent| <= 22, otherwise strtod in the C locale).
+// A first serial pass finds the frames (line ends only), then n_threads host threads tokenise and convert them.
+//   coords: (max_frames, A, 3) doubles or NULL (with symbols NULL as well: frames counted, atom lines not checked); symbols: A x 4 bytes, zero-terminated, or NULL;
+//   title_span: 2 int64 per frame (offset, length of the comment line) or NULL.
+// Returns the number of complete frames; -1 bad arguments, -2 malformed frame (cclib: AssertionError / ValueError),
+// -3 frames with different atom counts, -4 a coordinate that is not a number, -5 max_frames too small.
+// ------------------------------------------------------------------------------------------
+#include <locale.h>
+#include <atomic>
+namespace {
+inline bool xyz_space(char c) { return c == ' ' || c == '\t' || c == '\v' || c == '\f' || c == '\r' || c == '\n'; }
+// next line [b, e) of [p, end): split at \n, \r\n or \r; returns false at the end of the text
+template <bool BARE_CR>
+inline bool xyz_next_line(const char*& p, const char* end, const char*& b, const char*& e) {
+    if (p >= end) return false;
+    b = p;
+    if (BARE_CR) {
+        while (p < end && *p != '\n' && *p != '\r') p++;
+        e = p;
+        if (p < end) { if (*p == '\r' && p + 1 < end && p[1] == '\n') p += 2; else p++; }
+    } else {                                 // only \n and \r\n occur: a \r left at the end of a line is whitespace
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+        e = nl ? nl : end;
+        p = nl ? nl + 1 : end;
+    }
+    return true;
+}
+inline bool xyz_next_token(const char*& p, const char* e, const char*& tb, const char*& te) {
+    while (p < e && xyz_space(*p)) p++;
+    if (p >= e) return false;
+    tb = p;
+    while (p < e && !xyz_space(*p)) p++;
+    te = p;
+    return true;
+}
+inline bool xyz_blank(const char* b, const char* e) { while (b < e && xyz_space(*b)) b++; return b >= e; }
+inline bool xyz_ieq(const char* b, const char* e, const char* word) {
+    for (; b < e && *word; b++, word++) if ((*b | 0x20) != *word) return false;
+    return b == e && !*word;
+}
+bool xyz_parse_double(const char* b, const char* e, double* out) {
+    static const double P10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16,
+                                   1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+    const char* p = b;
+    bool neg = false;
+    if (p < e && (*p == '+' || *p == '-')) { neg = *p == '-'; p++; }
+    if (xyz_ieq(p, e, "inf") || xyz_ieq(p, e, "infinity")) { *out = neg ? -INFINITY : INFINITY; return true; }
+    if (xyz_ieq(p, e, "nan")) { *out = neg ? -NAN : NAN; return true; }
+    uint64_t mant = 0;
+    int n_sig = 0, n_dig = 0;
+    int64_t exp10 = 0;
+    bool exact = true;
+    for (; p < e && *p >= '0' && *p <= '9'; p++) {
+        n_dig++;
+        if (n_sig < 19) { mant = mant * 10 + (uint64_t)(*p - '0'); if (mant) n_sig++; } else { exact = false; }
+    }
+    if (p < e && *p == '.') {
+        p++;
+        for (; p < e && *p >= '0' && *p <= '9'; p++) {
+            n_dig++;
+            if (n_sig < 19) { mant = mant * 10 + (uint64_t)(*p - '0'); if (mant) n_sig++; exp10--; } else { exact = false; }
+        }
+    }
+    if (n_dig == 0) return false;
+    if (p < e && (*p == 'e' || *p == 'E')) {
+        p++;
+        bool eneg = false;
+        if (p < e && (*p == '+' || *p == '-')) { eneg = *p == '-'; p++; }
+        if (p >= e || *p < '0' || *p > '9') return false;
+        int64_t ex = 0;
+        for (; p < e && *p >= '0' && *p <= '9'; p++) if (ex < 100000) ex = ex * 10 + (*p - '0');
+        exp10 += eneg ? -ex : ex;
+    }
+    if (p != e) return false;
+    if (exact && mant < (1ull << 53) && exp10 >= -22 && exp10 <= 22) {        // one correctly rounded operation
+        double v = (double)mant;
+        v = exp10 >= 0 ? v * P10[exp10] : v / P10[-exp10];
+        *out = neg ? -v : v;
+        return true;
+    }
+    static locale_t c_loc = newlocale(LC_ALL_MASK, "C", (locale_t)0);
+    char tmp[512];
+    const size_t n = (size_t)(e - b);
+    std::vector<char> big;
+    char* s = tmp;
+    if (n >= sizeof(tmp)) { big.resize(n + 1); s = big.data(); }
+    memcpy(s, b, n); s[n] = 0;
+    char* endp = nullptr;
+    *out = strtod_l(s, &endp, c_loc);
+    return endp == s + n;
+}
+struct XyzFrame { const char* atoms; const char* title_b; const char* title_e; };
+}  // namespace
+
+template <bool BARE_CR>
+static int64_t read_xyz_impl(const char* text, int64_t len, int32_t* n_atoms, double* coords, int64_t max_frames,
+                             char* symbols, int64_t* title_span, int32_t n_threads) {
+    const char* p = text;
+    const char* end = text + len;
+    std::vector<XyzFrame> frames;
+    int64_t A = -1;
+    // serial pass: frame boundaries only (count line, comment line, `count` lines skipped)
+    while (true) {
+        const char *b, *e, *tb, *te;
+        if (!xyz_next_line<BARE_CR>(p, end, b, e)) break;
+        if (xyz_blank(b, e) && !xyz_next_line<BARE_CR>(p, end, b, e)) break;  // one optional blank line
+        const char* q = b;
+        if (!xyz_next_token(q, e, tb, te)) return -2;                        // assert len(tokens) >= 1
+        int64_t natom = 0;
+        {
+            const char* d = tb;
+            if (d < te && (*d == '+' || *d == '-')) { if (*d == '-') return -2; d++; }
+            if (d >= te) return -2;
+            for (; d < te; d++) { if (*d < '0' || *d > '9' || natom > 100000000) return -2; natom = natom * 10 + (*d - '0'); }
+        }
+        if (natom < 1) return -2;
+        XyzFrame f;
+        if (!xyz_next_line<BARE_CR>(p, end, f.title_b, f.title_e)) break;    // comment line
+        if (!BARE_CR && f.title_e > f.title_b && f.title_e[-1] == '\r') f.title_e--;
+        f.atoms = p;
+        bool complete = true;
+        for (int64_t a = 0; a < natom; a++)
+            if (!xyz_next_line<BARE_CR>(p, end, b, e)) { complete = false; break; }
+        if (!complete) break;                                                // the text ended inside a frame: dropped
+        if (A >= 0 && natom != A) return -3;
+        A = natom;
+        frames.push_back(f);
+    }
+    const int64_t n_frames = (int64_t)frames.size();
+    *n_atoms = (int32_t)(A < 0 ? 0 : A);
+    if (title_span)
+        for (int64_t f = 0; f < n_frames && f < max_frames; f++) {
+            title_span[2 * f] = frames[f].title_b - text;
+            title_span[2 * f + 1] = frames[f].title_e - frames[f].title_b;
+        }
+    if (n_frames == 0 || (!coords && !symbols)) return n_frames;           // count only: the atom lines are not looked at
+    if (coords && max_frames < n_frames) return -5;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    if (n_frames * A < 4096) n_threads = 1;
+    // parallel pass: every atom line tokenised (>= 4 tokens or the frame is malformed), numbers converted
+    std::atomic<int> bad{0};
+    auto work = [&](int64_t lo, int64_t hi) {
+        double sink[3];
+        for (int64_t f = lo; f < hi && !bad.load(std::memory_order_relaxed); f++) {
+            const char* q = frames[f].atoms;
+            for (int64_t a = 0; a < A; a++) {
+                const char *b, *e, *tb, *te;
+                xyz_next_line<BARE_CR>(q, end, b, e);
+                const char* w = b;
+                if (!xyz_next_token(w, e, tb, te)) { bad.store(2); return; }              // symbol
+                if (symbols && f == n_frames - 1) {
+                    if (te - tb > 3) { bad.store(2); return; }                            // no element symbol is that long
+                    memset(symbols + 4 * a, 0, 4);
+                    memcpy(symbols + 4 * a, tb, (size_t)(te - tb));
+                }
+                double* o = coords ? coords + (f * A + a) * 3 : sink;
+                for (int c = 0; c < 3; c++) {
+                    if (!xyz_next_token(w, e, tb, te)) { bad.store(2); return; }          // assert len(tokens) >= 4
+                    if (!xyz_parse_double(tb, te, o + c)) { bad.store(4); return; }
+                }
+            }
+        }
+    };
+    if (n_threads == 1) work(0, n_frames);
+    else {
+        const int64_t per = (n_frames + n_threads - 1) / n_threads;
+        std::vector<std::thread> th;
+        for (int w = 0; w < n_threads; w++) {
+            const int64_t lo = w * per, hi = std::min<int64_t>(lo + per, n_frames);
+            if (lo < hi) th.emplace_back(work, lo, hi);
+        }
+        for (auto& t : th) t.join();
+    }
+    return bad.load() ? -(int64_t)bad.load() : n_frames;
+}
+
+extern "C" int64_t tsc_host_read_xyz(const char* text, int64_t len, int32_t* n_atoms, double* coords, int64_t max_frames,
+                                     char* symbols, int64_t* title_span, int32_t n_threads) {
+    if (!text || len < 0 || !n_atoms) return -1;
+    bool bare_cr = false;                                        // a \r that is not part of \r\n: old Mac line ends
+    for (const char* r = (const char*)memchr(text, '\r', (size_t)len); r && !bare_cr;
+         r = (const char*)memchr(r + 1, '\r', (size_t)(text + len - r - 1)))
+        bare_cr = r + 1 >= text + len || r[1] != '\n';
+    return bare_cr ? read_xyz_impl<true>(text, len, n_atoms, coords, max_frames, symbols, title_span, n_threads)
+                   : read_xyz_impl<false>(text, len, n_atoms, coords, max_frames, symbols, title_span, n_threads);
+}

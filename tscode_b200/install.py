@@ -33,6 +33,7 @@ from . import numba_functions as _nf
 from . import optimization_methods as _om
 from . import rmsd_pruning as _rp
 from . import torsion_module as _tm
+from . import utils as _ut
 
 # defining module -> {name: replacement}
 _PATCHES = {
@@ -84,6 +85,32 @@ _SCALAR_PATCHES = {
 # modules that import those names with `from ... import`
 _IMPORTERS = ("tscode.embedder", "tscode.embeds", "tscode.operators", "tscode.optimization_methods",
               "tscode.automep", "tscode.atropisomer_module", "tscode.multiembed", "tscode.torsion_module")
+# `from tscode.utils import read_xyz / write_xyz` (and pka.py:23, which takes write_xyz from optimization_methods)
+_IO_IMPORTERS = ("tscode.hypermolecule_class", "tscode.embedder_options", "tscode.pka", "tscode.concurrent_test")
+_reference_read_xyz = []                                  # the original, saved by install_into(io=True)
+
+
+def read_xyz(filename):
+    """Installed in place of tscode.utils.read_xyz by install_into(io=True): `.xyz` files go through the native reader
+    (utils.read_xyz: .atomcoords / .atomnos / .metadata['comments'], what the reference's callers use); any other
+    format ccread understands, and any file the native reader rejects, is handed to the reference's own function."""
+    if str(filename).lower().endswith(".xyz"):
+        try:
+            return _ut.read_xyz(filename)
+        except (ValueError, KeyError, AssertionError):
+            if not _reference_read_xyz:
+                raise
+    if not _reference_read_xyz:
+        raise ValueError(f"{filename}: only .xyz files can be read without the reference's read_xyz")
+    return _reference_read_xyz[0](filename)
+
+
+_IO_PATCHES = {
+    "tscode.utils": {
+        "write_xyz": _ut.write_xyz,
+        "read_xyz": read_xyz,
+    },
+}
 
 _saved = []
 
@@ -150,13 +177,15 @@ _METHOD_PATCHES = {
 }
 
 
-def install_into(tscode_pkg=None, strict: bool = False, scalars: bool = False, loops: bool = True):
+def install_into(tscode_pkg=None, strict: bool = False, scalars: bool = False, loops: bool = True, io: bool = False):
     """Rebind the reference's hot-path names to the CUDA implementations.  Returns the list of
     (module, name) pairs that were patched.  Modules that are not importable in this
-    environment are skipped unless strict=True.  scalars / loops: see the module docstring."""
+    environment are skipped unless strict=True.  scalars / loops: see the module docstring.  io=True also rebinds
+    utils.write_xyz / read_xyz to the native formatter and reader (read_xyz above: `.xyz` only, the
+    reference's function for everything else)."""
     patched = []
     originals = {}
-    tables = [_PATCHES] + ([_SCALAR_PATCHES] if scalars else [])
+    tables = [_PATCHES] + ([_SCALAR_PATCHES] if scalars else []) + ([_IO_PATCHES] if io else [])
     for table in tables:
         for modname, names in table.items():
             try:
@@ -170,10 +199,12 @@ def install_into(tscode_pkg=None, strict: bool = False, scalars: bool = False, l
                     originals[name] = getattr(mod, name)
                     if name == "prune_conformers_rmsd_rot_corr" and not _reference_rot_corr:
                         _reference_rot_corr.append(originals[name])
+                    if name == "read_xyz" and not _reference_read_xyz:
+                        _reference_read_xyz.append(originals[name])
                     _saved.append((mod, name, originals[name]))
                     setattr(mod, name, repl)
                     patched.append((modname, name))
-    for modname in _IMPORTERS:
+    for modname in _IMPORTERS + (_IO_IMPORTERS if io else ()):
         mod = sys.modules.get(modname)
         if mod is None:
             try:
@@ -208,6 +239,7 @@ def install_into(tscode_pkg=None, strict: bool = False, scalars: bool = False, l
 
 def uninstall():
     del _reference_rot_corr[:]
+    del _reference_read_xyz[:]
     while _saved:
         mod, name, orig = _saved.pop()
         setattr(mod, name, orig)
