@@ -100,6 +100,58 @@ def test_install_io_rebinds_xyz_helpers_with_reference_fallback(tmp_path):
     assert ut.read_xyz is orig_r and ut.write_xyz is orig_w and hm.read_xyz is orig_r
 
 
+@pytest.mark.skipif(not ref_harness.available(), reason="reference tree not present")
+def test_install_io_write_structures_writes_the_reference_file(tmp_path, monkeypatch):
+    """Embedder.write_structures (embedder.py:996-1043) as patched by install_into(io=True) — one native call for all
+    frames — writes byte for byte the file the reference's per-structure loop writes, for both alignments, with and
+    without energies, and truncates / logs the same way."""
+    import types
+    ref_harness.install(full=True)
+    from tscode.embedder import Embedder
+    from tscode_b200 import install
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.default_rng(3)
+    atomnos = np.array([6, 6, 8, 7, 1, 1, 1, 1, 17, 16, 9, 1])        # elements of the harness periodic table
+    base = rng.normal(size=(12, 3)) * 2.0
+
+    def stub(n, let=False):
+        st = types.SimpleNamespace()
+        st.structures = base[None] + rng.normal(size=(n, 12, 3)) * 0.3
+        st.energies = rng.normal(size=n) * 5.0
+        st.atomnos = atomnos
+        st.options = types.SimpleNamespace(let=let)
+        st.stamp = "stamp"
+        st.lines = []
+        st.log = lambda string='', p=True: st.lines.append(string)
+        return st
+
+    ref_method = Embedder.write_structures
+    cases = [dict(tag="a", n=7), dict(tag="b", n=7, energies=False, extra=" | extra text"), dict(tag="c", n=5, align="moi"),
+             dict(tag="d", n=6, relative=False, p=False), dict(tag="e", n=4, indices=np.array([0, 2, 3])),
+             dict(tag="f", n=10003)]                                  # truncated to 10 000 frames, with the log line
+    for case in cases:
+        n = case.pop("n")
+        tag = case.pop("tag")
+        state = rng.bit_generator.state
+        a = stub(n)
+        rng.bit_generator.state = state
+        b = stub(n)
+        ref_method(a, tag, **case)
+        want = open(a.outname, "rb").read()
+        os.remove(a.outname)
+        install.write_structures(b, tag, **case)
+        got = open(b.outname, "rb").read()
+        assert got == want and len(want) > 100, tag
+        assert a.lines == b.lines and a.outname == b.outname and np.array_equal(a.energies, b.energies)
+    patched = install.install_into(io=True)
+    try:
+        assert Embedder.write_structures is install.write_structures
+        assert ("tscode.embedder.Embedder", "write_structures") in patched
+    finally:
+        install.uninstall()
+    assert Embedder.write_structures is ref_method
+
+
 class _StubRun:
     """The attributes RunEmbedding.compenetration_refining / fitness_refining touch (embedder.py:1119-1134, :973-984,
     :1230-1313), around real Embedder methods."""

@@ -169,6 +169,47 @@ def fitness_refining(self, threshold=5, verbose=False):
     self.zero_candidates_check()
 
 
+def write_structures(self, tag, indices=None, energies=True, relative=True, extra='', align='indices', p=True):
+    """Embedder.write_structures (embedder.py:996-1043) with the per-structure write_xyz loop (:1034-1041) replaced by
+    one call of the native formatter on all frames (utils.xyz_text); alignment, titles, truncation and log lines are
+    the reference's own, line by line (including `rel_e -= min`, which edits self.energies in place)."""
+    from tscode.hypermolecule_class import align_by_moi, align_structures
+    align_functions = {
+        'indices': align_structures,
+        'moi': align_by_moi,
+    }
+    if energies:
+        rel_e = self.energies
+        if relative:
+            rel_e -= np.min(self.energies)
+    # truncate if there are too many (embed debug first dump)
+    if len(self.structures) > 10000 and not self.options.let:
+        self.log(f'Truncated {tag} output structures to 10000 (from {len(self.structures)} - keyword LET to override).')
+        output_structures = self.structures[0:10000]
+    else:
+        output_structures = self.structures
+    self.outname = f'tscode_{tag}_{self.stamp}.xyz'
+    with open(self.outname, 'w') as f:
+        aligned = align_functions[align](output_structures, atomnos=self.atomnos, indices=indices)
+        titles = []
+        for i in range(len(aligned)):
+            title = f'Strucure {i+1} - {tag}'
+            if energies:
+                title += f' - Rel. E. = {round(rel_e[i], 3)} kcal/mol '
+            title += extra
+            titles.append(title)
+        if len(aligned):
+            f.write(_ut.xyz_text(np.asarray(aligned), self.atomnos, titles).decode())
+    if p:
+        self.log(f'Wrote {len(output_structures)} {tag} structures to {self.outname} file.\n')
+
+
+_IO_METHOD_PATCHES = {
+    ("tscode.embedder", "Embedder"): {
+        "write_structures": write_structures,
+    },
+}
+
 _METHOD_PATCHES = {
     ("tscode.embedder", "RunEmbedding"): {
         "compenetration_refining": compenetration_refining,
@@ -221,8 +262,9 @@ def install_into(tscode_pkg=None, strict: bool = False, scalars: bool = False, l
                         _saved.append((mod, name, cur))
                         setattr(mod, name, repl)
                         patched.append((modname, name))
-    if loops:
-        for (modname, clsname), methods in _METHOD_PATCHES.items():
+    method_tables = ([_METHOD_PATCHES] if loops else []) + ([_IO_METHOD_PATCHES] if io else [])
+    for method_table in method_tables:
+        for (modname, clsname), methods in method_table.items():
             try:
                 cls = getattr(importlib.import_module(modname), clsname)
             except Exception:
